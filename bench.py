@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- Graph WaveNet training throughput on B200 (driver contract).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+Workload (BASELINE.json metric "train samples/sec (fwd+bwd) METR-LA shape @1/2/4/8 B200"):
+gwnet METR-LA shape -- N=207 nodes, seq 12 (+1 pad), in_dim 2, doubletransition supports + adaptive
+adjacency, dropout 0.3, batch 64 PER GPU (weak scaling; N GPUs = global batch 64*N, config 5 at N=8)
+-- on synthetic data and seed-999 random-init weights.  One step = one full `trainer.train` call
+(forward, masked-MAE loss, backward, [gradient all-reduce], clip, Adam, 3 metrics).
+
+`value`  : samples/s with the step's inputs already resident in HBM.
+`e2e`    : same metric through the public API with HOST (pinned) inputs: per step H2D copy of x and y,
+           and the D2H read of the three metrics (inside trainer.train).
+`--impl reference`: the reference's CPU path (oracle port: same torch ops as the reference's model.py /
+           engine.py) on the host cores, bounded sample, same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NODES, SEQ, IN_DIM, BATCH = 207, 12, 2, 64
+DROPOUT = 0.3
+METRIC = "train samples/sec (fwd+bwd) METR-LA shape"
+WORKLOAD = "gwnet METR-LA shape N=207 seq=12 in_dim=2 batch=64/GPU doubletransition+adaptive, dropout 0.3, full trainer.train step"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_gflop_per_step(batch):
+    """SURVEY.md App. B, METR-LA: 217.4 GFLOP per 64-sample fwd+bwd step."""
+    return 217.4 * batch / 64.0
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    import torch
+    from oracle import gwnet_oracle as O
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.GwnetConfig(num_nodes=NODES, dropout=DROPOUT, n_static_supports=2)
+    gen = torch.Generator().manual_seed(0)
+    sup = O.synthetic_supports(NODES, 0.05, gen)
+    torch.manual_seed(999)
+    tr = O.OracleTrainer(cfg, O.init_state(cfg), sup, 54.0, 20.0)
+    x, y = O.synthetic_batch(BATCH, NODES, SEQ, IN_DIM, gen)
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 1))
+    for _ in range(warm):
+        tr.train(x, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.train(x, y)
+    dt = (time.perf_counter() - t0) / steps
+    v = BATCH / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "device": "host CPU"},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} full trainer.train steps at batch 64 (oracle port of model.py/engine.py, torch CPU ops)"},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ native arm
+def cpu_baseline_leg(steps=3):
+    import torch
+    from oracle import gwnet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.GwnetConfig(num_nodes=NODES, dropout=DROPOUT, n_static_supports=2)
+    gen = torch.Generator().manual_seed(0)
+    sup = O.synthetic_supports(NODES, 0.05, gen)
+    torch.manual_seed(999)
+    tr = O.OracleTrainer(cfg, O.init_state(cfg), sup, 54.0, 20.0)
+    x, y = O.synthetic_batch(BATCH, NODES, SEQ, IN_DIM, gen)
+    tr.train(x, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.train(x, y)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": BATCH / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} full trainer.train steps at batch 64 after 1 warm-up (oracle port, torch CPU ops, {cores} threads)"}
+
+
+def roofline_leg(lib, dev, iters=20):
+    """Dominant kernel = the node contraction (nconv, model.py:13): time it alone at every layer's
+    shape (B=64, C=32, N=207, L_i) with CUDA events on the launching stream; algorithmic FLOPs
+    2*B*C*L*N^2 per launch."""
+    import torch
+    pk, src = peaks()
+    Ls = [12, 10, 9, 7, 6, 4, 3, 1]
+    A = torch.softmax(torch.randn(NODES, NODES, device=dev), dim=1)
+    flops = t_ms = 0.0
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    st = torch.cuda.current_stream(dev)
+    for L in Ls:
+        x = torch.randn(BATCH, L, NODES, 32, device=dev)
+        y = torch.empty_like(x)
+        for _ in range(3):
+            lib.check(lib.dll.gwn_nconv_fwd(x.data_ptr(), A.data_ptr(), NODES, y.data_ptr(), BATCH, L, NODES, 32, 0, st.cuda_stream))
+        tot = 0.0
+        for _ in range(iters):
+            flush.zero_()                      # L2 flush between timed launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            lib.check(lib.dll.gwn_nconv_fwd(x.data_ptr(), A.data_ptr(), NODES, y.data_ptr(), BATCH, L, NODES, 32, 0, st.cuda_stream))
+            e1.record(st)
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        t_ms += tot / iters
+        flops += 2.0 * BATCH * 32 * L * NODES * NODES
+    achieved = flops / (t_ms * 1e-3) / 1e12
+    peak = pk.get("bf16_tflops", 1590.0)
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "kernel": "gemm_kernel<Tile<128,128,8,8>,LdSupport,LdSlab,EpSlab> (nconv node contraction, fp32 FMA tier)",
+            "peak_source": f"bf16_tflops burst, {src} (kernel timed alone)",
+            "note": "fp32 SIMT parity tier: not on the tensor pipe; fraction is against the bf16 tensor peak by contract"}
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    from oracle import gwnet_oracle as O           # synthetic workload generator only
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ge.build()
+    ge.load_package()
+    from graph_wavenet_b200 import engine as E, native as NV
+    from graph_wavenet_b200.metrics import StandardScaler
+    lib = NV.get_lib()
+
+    gen = torch.Generator().manual_seed(0)
+    sup = [s.to(dev) for s in O.synthetic_supports(NODES, 0.05, gen)]
+    torch.manual_seed(999)
+    tr = E.trainer(StandardScaler(54.0, 20.0), IN_DIM, SEQ, NODES, 32, DROPOUT, 1e-3, 1e-4, dev, sup, True, True, None)
+    if world > 1:
+        tr.enable_data_parallel()
+    gen = torch.Generator().manual_seed(100 + rank)
+    nbuf = 4
+    host = [O.synthetic_batch(BATCH, NODES, SEQ, IN_DIM, gen) for _ in range(nbuf)]
+    host = [(x.contiguous().pin_memory(), y.contiguous().pin_memory()) for x, y in host]   # x logical [B,F,N,T]
+    devb = [(x.to(dev), y.to(dev)) for x, y in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms / steps
+
+    def step_resident(i):
+        x, y = devb[i % nbuf]
+        tr.train(x, y)
+
+    def step_e2e(i):
+        hx, hy = host[i % nbuf]
+        x = hx.to(dev, non_blocking=True)
+        y = hy.to(dev, non_blocking=True)
+        tr.train(x, y)
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    lib.dll.gwn_launch_count(1)
+    step_resident(0)
+    torch.cuda.synchronize(dev)
+    launches_per_step = int(lib.dll.gwn_launch_count(1))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank == 0:
+        h2d = sum(t.numel() * t.element_size() for t in host[0])
+        line = {"metric": METRIC, "value": BATCH * world / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": BATCH * world,
+                           "parallelism": f"dp{world}" if world > 1 else "single",
+                           "precision_tier": "fp32 (FMA) -- 1e-4 parity tier",
+                           "l2_policy": "per-step working set (~0.9 GB of saved activations) exceeds the 126 MB L2; 4 rotating input batches"},
+                "e2e": {"value": BATCH * world / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e},
+                "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+                "model_tflops": algorithmic_gflop_per_step(BATCH * world) / ms, "clocks": clocks}
+        if world == 1:
+            line["roofline"] = roofline_leg(lib, dev)
+            line["cpu_baseline"] = cpu_baseline_leg()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

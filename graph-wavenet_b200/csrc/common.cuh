@@ -1,0 +1,184 @@
+// Common definitions for the gwnet_b200 kernels.
+//
+// The same sources build two ways:
+//   * nvcc, sm_100a           -> libgwnet_b200.so, the product (CUDA only, no CPU fallback);
+//   * g++ -DGWN_HOST_EMU      -> tests/_hostemu/libgwnet_hostemu.so, a TEST-ONLY emulation in which
+//     every kernel launch is replaced by a serial host loop over the very same loader / epilogue
+//     functors.  It exists so the index arithmetic and the plan orchestration can be checked against
+//     the oracle in the GPU-less build container.  The python package never loads it.
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <cassert>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <type_traits>
+
+#include <cuda_runtime.h>
+
+#include "../../include/gwnet_b200.h"
+
+#ifdef GWN_HOST_EMU
+#define GWN_HD
+#define GWN_DEV
+#define GWN_EMU 1
+#else
+#define GWN_HD __host__ __device__ __forceinline__
+#define GWN_DEV __device__ __forceinline__
+#define GWN_EMU 0
+#endif
+
+namespace gwn {
+
+typedef long long i64;
+
+void set_error(const char* fmt, ...);
+void count_launch();   // bumps the counter behind gwn_launch_count()
+
+#define GWN_CHECK_ARG(cond, ...)                  \
+  do {                                            \
+    if (!(cond)) {                                \
+      ::gwn::set_error(__VA_ARGS__);              \
+      return GWN_ERR_INVALID;                     \
+    }                                             \
+  } while (0)
+
+#define GWN_TRY(expr)                 \
+  do {                                \
+    int _st = (expr);                 \
+    if (_st != 0) return _st;         \
+  } while (0)
+
+#if !GWN_EMU
+#define GWN_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::gwn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return GWN_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+#define GWN_LAUNCH_CHECK() GWN_CUDA(cudaGetLastError())
+#endif
+
+// ---------------------------------------------------------------- small device helpers
+GWN_HD float4 ld4(const float* p) {
+#if GWN_EMU
+  assert((reinterpret_cast<uintptr_t>(p) & 15) == 0 && "misaligned float4 load");
+#endif
+  return *reinterpret_cast<const float4*>(p);
+}
+GWN_HD void st4(float* p, float4 v) {
+#if GWN_EMU
+  assert((reinterpret_cast<uintptr_t>(p) & 15) == 0 && "misaligned float4 store");
+#endif
+  *reinterpret_cast<float4*>(p) = v;
+}
+
+GWN_HD void atomic_add_f(float* p, float v) {
+#if GWN_EMU
+  *p += v;
+#else
+#ifdef __CUDA_ARCH__
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+#endif
+}
+GWN_HD void atomic_add_d(double* p, double v) {
+#if GWN_EMU
+  *p += v;
+#else
+#ifdef __CUDA_ARCH__
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+#endif
+}
+
+GWN_HD float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Row remap between two BLNC tensors that share (B, N) but differ in time length:
+// position p = (b, t, n) of a tensor with lon_out = L_out*N rows per sample maps to
+// row (b, t + off_t, n) of a tensor with lon_in = L_in*N rows per sample; off = off_t*N.
+struct Remap {
+  int lon_out, lon_in, off;
+  GWN_HD i64 operator()(i64 p) const {
+    i64 b = p / lon_out;
+    i64 r = p - b * lon_out;
+    return b * lon_in + off + r;
+  }
+};
+inline Remap make_remap(int L_out, int L_in, int off_t, int N) { return Remap{L_out * N, L_in * N, off_t * N}; }
+inline Remap identity_remap() { return Remap{1 << 30, 1 << 30, 0}; }
+
+// ---------------------------------------------------------------- Philox4x32-10 (dropout)
+struct Philox {
+  static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  GWN_HD static void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    uint64_t p = (uint64_t)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+  }
+  // 4 uniform 32-bit words for (key, counter)
+  GWN_HD static void gen(uint64_t key, uint64_t ctr_lo, uint64_t ctr_hi, uint32_t (&out)[4]) {
+    uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+    uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t h0, l0, h1, l1;
+      mulhilo(M0, c0, h0, l0);
+      mulhilo(M1, c2, h1, l1);
+      uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  }
+};
+
+// Dropout keep-scale for 4 consecutive elements starting at flat element index e (e % 4 == 0).
+struct DropoutSrc {
+  int mode;              // gwn_dropout_mode
+  const uint8_t* mask;   // GWN_DROPOUT_MASK
+  uint64_t seed, stream; // GWN_DROPOUT_PHILOX: key = seed, counter hi = stream (layer id)
+  float p, scale;        // scale = 1/(1-p)
+  GWN_HD void keep4(i64 e, float (&k)[4]) const {
+    if (mode == GWN_DROPOUT_NONE) {
+      k[0] = k[1] = k[2] = k[3] = 1.0f;
+    } else if (mode == GWN_DROPOUT_MASK) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) k[i] = mask[e + i] ? scale : 0.0f;
+    } else {
+      uint32_t r[4];
+      Philox::gen(seed, (uint64_t)(e >> 2), stream, r);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float u = (float)(r[i] >> 8) * (1.0f / 16777216.0f);  // [0,1)
+        k[i] = (u >= p) ? scale : 0.0f;
+      }
+    }
+  }
+};
+inline DropoutSrc make_dropout(int mode, const uint8_t* mask, uint64_t seed, uint64_t stream, float p) {
+  DropoutSrc d;
+  d.mode = (p <= 0.0f) ? (int)GWN_DROPOUT_NONE : mode;
+  d.mask = mask;
+  d.seed = seed;
+  d.stream = stream;
+  d.p = p;
+  d.scale = (p < 1.0f) ? 1.0f / (1.0f - p) : 0.0f;
+  return d;
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline i64 round_up64(i64 x, i64 m) { return (x + m - 1) / m * m; }
+
+}  // namespace gwn

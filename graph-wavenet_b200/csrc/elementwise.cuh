@@ -1,0 +1,283 @@
+// Non-GEMM kernels of the hot path: layout conversion, support packing, adaptive adjacency
+// (model.py:187) forward/backward, start conv (model.py:181), BatchNorm finalize / backward apply
+// (model.py:236), head-window add.  Each kernel body is written once; under GWN_HOST_EMU (tests only)
+// the launch macro turns into a serial host loop over the same body.
+#pragma once
+#include "common.cuh"
+
+namespace gwn {
+
+#if GWN_EMU
+#define GWN_GLOBAL static void
+#define GWN_FOR_EACH(i, n) for (i64 i = 0; i < (i64)(n); ++i)
+#define GWN_FOR_EACH_WARP_ROW(row, nrows, lane, WS) \
+  const int WS = 1;                                 \
+  const int lane = 0;                               \
+  for (i64 row = 0; row < (i64)(nrows); ++row)
+#define GWN_LAUNCH_1D(kernel, n, stream, ...) \
+  do {                                        \
+    (void)(stream);                           \
+    kernel(__VA_ARGS__);                      \
+  } while (0)
+#define GWN_LAUNCH_WARP_ROWS(kernel, nrows, stream, ...) GWN_LAUNCH_1D(kernel, nrows, stream, __VA_ARGS__)
+template <class T>
+inline T warp_sum(T v) { return v; }
+template <class T>
+inline T warp_max(T v) { return v; }
+#else
+#define GWN_GLOBAL static __global__ void
+#define GWN_FOR_EACH(i, n)                                                                  \
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < (i64)(n); i += (i64)gridDim.x * blockDim.x)
+#define GWN_FOR_EACH_WARP_ROW(row, nrows, lane, WS)                                         \
+  const int WS = 32;                                                                        \
+  const int lane = threadIdx.x & 31;                                                        \
+  for (i64 row = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < (i64)(nrows);     \
+       row += ((i64)gridDim.x * blockDim.x) >> 5)
+#define GWN_LAUNCH_1D(kernel, n, stream, ...)                                               \
+  do {                                                                                      \
+    i64 _n = (i64)(n);                                                                      \
+    if (_n > 0) {                                                                           \
+      i64 _b = (_n + 255) / 256;                                                            \
+      if (_b > 148 * 32) _b = 148 * 32;                                                     \
+      kernel<<<(unsigned)_b, 256, 0, stream>>>(__VA_ARGS__);                                \
+      GWN_LAUNCH_CHECK();                                                                   \
+      ::gwn::count_launch();                                                                \
+    }                                                                                       \
+  } while (0)
+#define GWN_LAUNCH_WARP_ROWS(kernel, nrows, stream, ...)                                    \
+  do {                                                                                      \
+    i64 _n = (i64)(nrows);                                                                  \
+    if (_n > 0) {                                                                           \
+      i64 _b = (_n + 7) / 8;                                                                \
+      if (_b > 148 * 16) _b = 148 * 16;                                                     \
+      kernel<<<(unsigned)_b, 256, 0, stream>>>(__VA_ARGS__);                                \
+      GWN_LAUNCH_CHECK();                                                                   \
+      ::gwn::count_launch();                                                                \
+    }                                                                                       \
+  } while (0)
+template <class T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+#endif
+
+struct Strides4 {
+  i64 s[4];
+};
+struct Sizes4 {
+  i64 n[4];
+};
+
+// dst[i0,i1,i2,i3] = src[i0,i1,i2,i3]; iteration is dst-major over `order` (a permutation of the dims
+// sorted by decreasing dst stride) so writes coalesce.
+GWN_GLOBAL permute4d_kernel(const float* src, Strides4 ss, float* dst, Strides4 ds, Sizes4 sz, Sizes4 ord, i64 total) {
+  GWN_FOR_EACH(i, total) {
+    i64 r = i, idx[4];
+#pragma unroll
+    for (int d = 3; d >= 0; --d) {
+      int dim = (int)ord.n[d];
+      idx[dim] = r % sz.n[dim];
+      r /= sz.n[dim];
+    }
+    i64 so = 0, dof = 0;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      so += idx[d] * ss.s[d];
+      dof += idx[d] * ds.s[d];
+    }
+    dst[dof] = src[so];
+  }
+}
+
+// Pack a static support into zero-padded row-major A[v*ld + w] and its transpose AT[w*ld + v].
+GWN_GLOBAL support_pack_kernel(const float* A, i64 rs, i64 cs, float* Ap, float* ATp, int N, int ld) {
+  GWN_FOR_EACH(i, (i64)N * ld) {
+    int v = (int)(i / ld), w = (int)(i - (i64)v * ld);
+    float val = (w < N) ? A[v * rs + w * cs] : 0.0f;
+    Ap[(i64)v * ld + w] = val;
+    if (w < N) ATp[(i64)w * ld + v] = val;
+    else ATp[(i64)v * ld + w] = 0.0f;
+  }
+}
+
+// adp = softmax(relu(E1 @ E2), dim=1)   (model.py:187); one warp per row; writes A and A^T (padded).
+GWN_GLOBAL adp_fwd_kernel(const float* E1, const float* E2, int R, float* Ap, float* ATp, int N, int ld) {
+  GWN_FOR_EACH_WARP_ROW(v, N, lane, WS) {
+    float* row = Ap + v * ld;
+    float mx = 0.0f;  // relu output is >= 0
+    for (int w = lane; w < N; w += WS) {
+      float acc = 0.0f;
+      for (int k = 0; k < R; ++k) acc = fmaf(E1[v * R + k], E2[(i64)k * N + w], acc);
+      acc = fmaxf(acc, 0.0f);
+      row[w] = acc;
+      mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int w = lane; w < N; w += WS) {
+      float e = expf(row[w] - mx);
+      row[w] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    float inv = 1.0f / sum;
+    for (int w = lane; w < ld; w += WS) {
+      float p = (w < N) ? row[w] * inv : 0.0f;
+      row[w] = p;
+      if (w < N) ATp[(i64)w * ld + v] = p;
+      else ATp[v * ld + w] = 0.0f;
+    }
+  }
+}
+
+// Backward of adp: dR = P*(dP - sum_w dP*P) masked by (E1@E2 > 0); dE1[v,k] = sum_w dR[v,w] E2[k,w].
+GWN_GLOBAL adp_bwd_rows_kernel(const float* dA, const float* Ap, const float* E1, const float* E2, int R, float* dR,
+                               float* dE1, int N, int ld) {
+  GWN_FOR_EACH_WARP_ROW(v, N, lane, WS) {
+    float s = 0.0f;
+    for (int w = lane; w < N; w += WS) s = fmaf(dA[v * ld + w], Ap[v * ld + w], s);
+    s = warp_sum(s);
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.0f;
+    for (int w = lane; w < N; w += WS) {
+      float pre = 0.0f;
+      for (int k = 0; k < R; ++k) pre = fmaf(E1[v * R + k], E2[(i64)k * N + w], pre);
+      float g = (pre > 0.0f) ? Ap[v * ld + w] * (dA[v * ld + w] - s) : 0.0f;
+      dR[v * ld + w] = g;
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (k < R) acc[k] = fmaf(g, E2[(i64)k * N + w], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (k < R) {
+        float t = warp_sum(acc[k]);
+        if (lane == 0) dE1[v * R + k] = t;
+      }
+    }
+  }
+}
+// dE2[k,w] = sum_v E1[v,k] dR[v,w]
+GWN_GLOBAL adp_bwd_cols_kernel(const float* dR, const float* E1, int R, float* dE2, int N, int ld) {
+  GWN_FOR_EACH(i, (i64)R * N) {
+    int k = (int)(i / N), w = (int)(i - (i64)k * N);
+    float acc = 0.0f;
+    for (int v = 0; v < N; ++v) acc = fmaf(E1[(i64)v * R + k], dR[(i64)v * ld + w], acc);
+    dE2[i] = acc;
+  }
+}
+
+// start_conv (model.py:181) fused with the receptive-field left pad (model.py:176-180):
+// x0[b,t,n,c] = bias[c] + sum_f W[c,f] * (t >= pad ? in[b,f,n,t-pad] : 0)
+GWN_GLOBAL start_fwd_kernel(const float* in, Strides4 is, const float* W, const float* bias, float* x0, int B, int F,
+                            int N, int L0, int pad, int C) {
+  GWN_FOR_EACH(i, (i64)B * L0 * N * C) {
+    int c = (int)(i % C);
+    i64 p = i / C;
+    int n = (int)(p % N);
+    i64 bt = p / N;
+    int t = (int)(bt % L0);
+    i64 b = bt / L0;
+    float acc = bias[c];
+    if (t >= pad)
+      for (int f = 0; f < F; ++f) acc = fmaf(W[c * F + f], in[b * is.s[0] + f * is.s[1] + n * is.s[2] + (t - pad) * is.s[3]], acc);
+    x0[i] = acc;
+  }
+}
+// grad wrt the network input, contiguous [B,F,N,T]: gi[b,f,n,t] = sum_c W[c,f] dx0[(b,t+pad,n), c]
+GWN_GLOBAL start_dgrad_kernel(const float* dx0, const float* W, float* gi, int B, int F, int N, int T, int L0, int pad,
+                              int C) {
+  GWN_FOR_EACH(i, (i64)B * F * N * T) {
+    int t = (int)(i % T);
+    i64 r = i / T;
+    int n = (int)(r % N);
+    r /= N;
+    int f = (int)(r % F);
+    i64 b = r / F;
+    const float* d = dx0 + ((b * L0 + t + pad) * N + n) * C;
+    float acc = 0.0f;
+    for (int c = 0; c < C; ++c) acc = fmaf(W[c * F + f], d[c], acc);
+    gi[i] = acc;
+  }
+}
+
+// BatchNorm2d training-mode finalize (model.py:236): batch mean / biased var -> fold constants
+// a = gamma*rstd, c = beta - mean*a; running stats with momentum and unbiased var; num_batches_tracked += 1.
+GWN_GLOBAL bn_finalize_kernel(const double* sums, double count, const float* gamma, const float* beta, float* rmean,
+                              float* rvar, long long* nbt, float eps, float momentum, float* ac, float* mr, int C) {
+  GWN_FOR_EACH(c, C) {
+    double mean = sums[c] / count;
+    double var = sums[C + c] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float a = gamma[c] * rstd;
+    ac[c] = a;
+    ac[C + c] = beta[c] - (float)mean * a;
+    mr[c] = (float)mean;
+    mr[C + c] = rstd;
+    double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    rmean[c] = (1.0f - momentum) * rmean[c] + momentum * (float)mean;
+    rvar[c] = (1.0f - momentum) * rvar[c] + momentum * (float)unbiased;
+    if (c == 0) nbt[0] += 1;
+  }
+}
+// Eval mode: fold constants from the running statistics.
+GWN_GLOBAL bn_eval_kernel(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps,
+                          float* ac, float* mr, int C) {
+  GWN_FOR_EACH(c, C) {
+    float rstd = 1.0f / sqrtf(rvar[c] + eps);
+    float a = gamma[c] * rstd;
+    ac[c] = a;
+    ac[C + c] = beta[c] - rmean[c] * a;
+    mr[c] = rmean[c];
+    mr[C + c] = rstd;
+  }
+}
+// BatchNorm backward apply, in place on dy:  du = a*(dy - S1/n - xhat*S2/n)  (train) | a*dy (eval);
+// also emits dgamma = S2, dbeta = S1.
+GWN_GLOBAL bn_bwd_apply_kernel(float* dy, const float* u, const float* ac, const float* mr, const double* bsum,
+                               double count, int training, float* dgamma, float* dbeta, i64 P, int C) {
+  GWN_FOR_EACH(i, P * C) {
+    int c = (int)(i % C);
+    float a = ac[c];
+    float g = dy[i];
+    float r;
+    if (training) {
+      float xh = (u[i] - mr[c]) * mr[C + c];
+      float m1 = (float)(bsum[c] / count), m2 = (float)(bsum[C + c] / count);
+      r = a * (g - m1 - xh * m2);
+    } else {
+      r = a * g;
+    }
+    dy[i] = r;
+    if (i < C) {
+      dgamma[i] = (float)bsum[C + i];
+      dbeta[i] = (float)bsum[i];
+    }
+  }
+}
+
+// dst[p, c] = (src ? src[p,c] : 0) + (t >= L - T_out ? win[(b, t-(L-T_out), n), c] : 0)
+GWN_GLOBAL add_window_kernel(float* dst, const float* src, const float* win, int B, int L, int N, int C, int T_out) {
+  GWN_FOR_EACH(i, (i64)B * L * N * C) {
+    i64 p = i / C;
+    int c = (int)(i - p * C);
+    int n = (int)(p % N);
+    i64 bt = p / N;
+    int t = (int)(bt % L);
+    i64 b = bt / L;
+    float v = src ? src[i] : 0.0f;
+    if (t >= L - T_out) v += win[((b * T_out + (t - (L - T_out))) * N + n) * C + c];
+    dst[i] = v;
+  }
+}
+
+}  // namespace gwn

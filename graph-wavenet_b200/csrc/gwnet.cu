@@ -1,0 +1,918 @@
+// gwnet_b200: whole-network plan (gwn_plan_*) and the op-level C ABI (include/gwnet_b200.h).
+// Replaces gwnet.forward (model.py:175-241) and its autograd graph with explicit fused launches.
+#include "ops.cuh"
+
+#include <atomic>
+#include <cstdarg>
+#include <vector>
+#include <string>
+
+namespace gwn {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+#if GWN_EMU
+static int dev_memset(void* p, int v, size_t bytes, cudaStream_t) {
+  if (bytes) memset(p, v, bytes);
+  return 0;
+}
+#else
+static int dev_memset(void* p, int v, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return 0;
+  GWN_CUDA(cudaMemsetAsync(p, v, bytes, s));
+  return 0;
+}
+#endif
+
+static int require_device() {
+#if GWN_EMU
+  return 0;
+#else
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_error("no CUDA device available (%s); gwnet_b200 has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    cudaGetLastError();
+    return GWN_ERR_NO_DEVICE;
+  }
+  return 0;
+#endif
+}
+
+static int permute4d(const float* src, const int64_t* ss, float* dst, const int64_t* ds, const int64_t* sz,
+                     cudaStream_t stream) {
+  Strides4 s, d;
+  Sizes4 n, ord;
+  i64 total = 1;
+  for (int i = 0; i < 4; ++i) {
+    s.s[i] = ss[i]; d.s[i] = ds[i]; n.n[i] = sz[i]; ord.n[i] = i;
+    total *= sz[i];
+  }
+  for (int i = 0; i < 4; ++i)   // iterate dst-major so that writes coalesce
+    for (int j = i + 1; j < 4; ++j)
+      if (d.s[ord.n[j]] > d.s[ord.n[i]]) std::swap(ord.n[i], ord.n[j]);
+  GWN_LAUNCH_1D(permute4d_kernel, total, stream, src, s, dst, d, n, ord, total);
+  return 0;
+}
+
+struct Entry {
+  std::string name;
+  i64 numel;
+  i64 grad_off;  // -1 for buffers
+};
+struct LayerIdx {
+  int fw, fb, gw, gb, rw, rb, sw, sb, bnw, bnb, bnm, bnv, bnt, mw, mb;
+};
+
+}  // namespace gwn
+
+struct gwn_plan {
+  gwn_config c;
+  int nL, S, nseg, nseg_mod, RF, L0, pad, T_out, ld, ldo;
+  std::vector<int> dil, L;  // per layer dilation and output length
+  std::vector<gwn::Entry> entries;
+  std::vector<gwn::LayerIdx> li;
+  int i_nv1, i_nv2, i_startw, i_startb, i_e1w, i_e1b, i_e2w, i_e2b;
+  gwn::i64 grad_floats;
+  // forward workspace offsets (floats)
+  gwn::i64 o_sup, o_supT, o_x0, o_skip, o_e1, fwd_floats;
+  std::vector<gwn::i64> o_g, o_u, o_ac, o_mr, o_sums;
+  // backward scratch offsets (floats)
+  gwn::i64 o_buf0, o_buf1, o_dsegs, o_dg, o_dpre, o_dgh, o_dout, o_de1, o_dskip, o_dA, o_dR, o_bsum, bwd_floats;
+  gwn::i64 P(int i) const { return (gwn::i64)c.batch * L[i] * c.num_nodes; }
+  gwn::i64 P0() const { return (gwn::i64)c.batch * L0 * c.num_nodes; }
+  gwn::i64 PT() const { return (gwn::i64)c.batch * T_out * c.num_nodes; }
+  int Lin(int i) const { return i == 0 ? L0 : L[i - 1]; }
+};
+
+namespace gwn {
+
+static i64 align_up(i64 x) { return (x + 63) / 64 * 64; }
+
+static int build_plan(gwn_plan* p) {
+  const gwn_config& c = p->c;
+  GWN_CHECK_ARG(c.batch >= 1 && c.num_nodes >= 1 && c.seq_len >= 1 && c.in_dim >= 1 && c.out_dim >= 1, "plan: bad dims");
+  GWN_CHECK_ARG(c.kernel_size == 2, "plan: kernel_size %d unsupported (the reference default 2 only)", c.kernel_size);
+  GWN_CHECK_ARG(c.residual_channels % 4 == 0 && c.dilation_channels % 4 == 0 && c.skip_channels % 4 == 0 &&
+                    c.end_channels % 4 == 0,
+                "plan: channel counts must be multiples of 4");
+  GWN_CHECK_ARG(c.blocks >= 1 && c.layers >= 1 && c.blocks * c.layers <= MAXSEG, "plan: blocks*layers must be in [1,%d]", MAXSEG);
+  GWN_CHECK_ARG(c.precision == GWN_PREC_FP32, "plan: precision %d not available in this build", c.precision);
+  GWN_CHECK_ARG(c.order >= 1 && c.order <= MAXSUP, "plan: order must be in [1,%d]", MAXSUP);
+  GWN_CHECK_ARG(c.dropout >= 0.f && c.dropout < 1.f, "plan: dropout must be in [0,1)");
+  GWN_CHECK_ARG(c.n_static_supports >= 0, "plan: negative support count");
+  GWN_CHECK_ARG(!c.gcn || c.gcn_bool, "plan: gcn active without gcn_bool");
+  GWN_CHECK_ARG(!c.adaptive || c.gcn, "plan: adaptive adjacency implies an active gcn");
+  p->nL = c.blocks * c.layers;
+  const int supports_len = c.n_static_supports + (c.adaptive ? 1 : 0);  // model.py:109-128
+  p->S = c.gcn ? supports_len : 0;
+  GWN_CHECK_ARG(p->S <= MAXSUP, "plan: too many supports");
+  GWN_CHECK_ARG(!c.gcn || p->S >= 1, "plan: gcn enabled without supports");
+  GWN_CHECK_ARG(!c.adaptive || (c.apt_rank >= 1 && c.apt_rank <= 16), "plan: apt_rank must be in [1,16]");
+  p->nseg_mod = 1 + c.order * supports_len;   // c_in multiplier of the gconv modules (model.py:36)
+  p->nseg = c.gcn ? p->nseg_mod : 1;
+  GWN_CHECK_ARG(p->nseg_mod <= MAXSEG, "plan: too many gcn segments");
+  p->dil.clear();
+  int rf = 1;
+  for (int b = 0; b < c.blocks; ++b) {   // model.py:130-155
+    int d = 1, scope = c.kernel_size - 1;
+    for (int l = 0; l < c.layers; ++l) {
+      p->dil.push_back(d);
+      d *= 2;
+      rf += scope;
+      scope *= 2;
+    }
+  }
+  p->RF = rf;
+  p->L0 = std::max(c.seq_len, rf);
+  p->pad = p->L0 - c.seq_len;
+  p->L.resize(p->nL);
+  int Lc = p->L0;
+  for (int i = 0; i < p->nL; ++i) {
+    Lc -= p->dil[i];
+    p->L[i] = Lc;
+  }
+  p->T_out = Lc;
+  GWN_CHECK_ARG(p->T_out >= 1, "plan: sequence shorter than the receptive field after padding");
+  p->ld = round_up(c.num_nodes, 4);
+  p->ldo = round_up(c.out_dim, 4);
+
+  // ---- parameter table in reference state_dict order
+  const int C = c.residual_channels, D = c.dilation_channels, Sk = c.skip_channels, E = c.end_channels;
+  const int nL = p->nL;
+  p->entries.clear();
+  p->li.assign(nL, LayerIdx());
+  i64 goff = 0;
+  auto add = [&](const std::string& name, i64 numel, bool is_param) {
+    Entry e;
+    e.name = name;
+    e.numel = numel;
+    e.grad_off = -1;
+    if (is_param) {
+      e.grad_off = goff;
+      goff += round_up64(numel, 4);
+    }
+    p->entries.push_back(e);
+    return (int)p->entries.size() - 1;
+  };
+  auto nm = [](const char* grp, int i, const char* leaf) {
+    char buf[128];
+    snprintf(buf, sizeof(buf), "%s.%d.%s", grp, i, leaf);
+    return std::string(buf);
+  };
+  p->i_nv1 = p->i_nv2 = -1;
+  if (c.adaptive) {
+    p->i_nv1 = add("nodevec1", (i64)c.num_nodes * c.apt_rank, true);
+    p->i_nv2 = add("nodevec2", (i64)c.apt_rank * c.num_nodes, true);
+  }
+  for (int i = 0; i < nL; ++i) {
+    p->li[i].fw = add(nm("filter_convs", i, "weight"), (i64)D * C * 2, true);
+    p->li[i].fb = add(nm("filter_convs", i, "bias"), D, true);
+  }
+  for (int i = 0; i < nL; ++i) {
+    p->li[i].gw = add(nm("gate_convs", i, "weight"), (i64)D * C * 2, true);
+    p->li[i].gb = add(nm("gate_convs", i, "bias"), D, true);
+  }
+  for (int i = 0; i < nL; ++i) {
+    p->li[i].rw = add(nm("residual_convs", i, "weight"), (i64)C * D, true);
+    p->li[i].rb = add(nm("residual_convs", i, "bias"), C, true);
+  }
+  for (int i = 0; i < nL; ++i) {
+    p->li[i].sw = add(nm("skip_convs", i, "weight"), (i64)Sk * D, true);
+    p->li[i].sb = add(nm("skip_convs", i, "bias"), Sk, true);
+  }
+  for (int i = 0; i < nL; ++i) {
+    p->li[i].bnw = add(nm("bn", i, "weight"), C, true);
+    p->li[i].bnb = add(nm("bn", i, "bias"), C, true);
+    p->li[i].bnm = add(nm("bn", i, "running_mean"), C, false);
+    p->li[i].bnv = add(nm("bn", i, "running_var"), C, false);
+    p->li[i].bnt = add(nm("bn", i, "num_batches_tracked"), 1, false);
+  }
+  for (int i = 0; i < nL; ++i) {
+    p->li[i].mw = p->li[i].mb = -1;
+    if (c.gcn_bool) {
+      p->li[i].mw = add(nm("gconv", i, "mlp.mlp.weight"), (i64)C * p->nseg_mod * D, true);
+      p->li[i].mb = add(nm("gconv", i, "mlp.mlp.bias"), C, true);
+    }
+  }
+  p->i_startw = add("start_conv.weight", (i64)C * c.in_dim, true);
+  p->i_startb = add("start_conv.bias", C, true);
+  p->i_e1w = add("end_conv_1.weight", (i64)E * Sk, true);
+  p->i_e1b = add("end_conv_1.bias", E, true);
+  p->i_e2w = add("end_conv_2.weight", (i64)c.out_dim * E, true);
+  p->i_e2b = add("end_conv_2.bias", c.out_dim, true);
+  p->grad_floats = goff;
+
+  // ---- forward workspace
+  const i64 N = c.num_nodes;
+  i64 o = 0;
+  auto take = [&](i64 n) {
+    i64 r = o;
+    o += align_up(n);
+    return r;
+  };
+  p->o_sup = take((i64)std::max(p->S, 1) * N * p->ld);
+  p->o_supT = take((i64)std::max(p->S, 1) * N * p->ld);
+  p->o_x0 = take(p->P0() * C);
+  p->o_g.resize(nL); p->o_u.resize(nL); p->o_ac.resize(nL); p->o_mr.resize(nL); p->o_sums.resize(nL);
+  for (int i = 0; i < nL; ++i) {
+    p->o_g[i] = take(p->P(i) * D * p->nseg);  // g_i followed by its hop tensors
+    p->o_u[i] = take(p->P(i) * C);
+    p->o_ac[i] = take(2 * C);
+    p->o_mr[i] = take(2 * C);
+    p->o_sums[i] = take(4 * C);               // 2*C doubles
+  }
+  p->o_skip = take(p->PT() * Sk);
+  p->o_e1 = take(p->PT() * E);
+  p->fwd_floats = o;
+
+  // ---- backward scratch
+  o = 0;
+  i64 maxP = p->P0();
+  for (int i = 0; i < nL; ++i) maxP = std::max(maxP, p->P(i));
+  i64 maxPi = 0;
+  for (int i = 0; i < nL; ++i) maxPi = std::max(maxPi, p->P(i));
+  p->o_buf0 = take(maxP * C);
+  p->o_buf1 = take(maxP * C);
+  p->o_dsegs = take(maxPi * D * p->nseg);
+  p->o_dg = take(maxPi * D);
+  p->o_dpre = take(maxPi * 2 * D);
+  p->o_dgh = take((i64)nL * p->PT() * D);
+  p->o_dout = take(p->PT() * p->ldo);
+  p->o_de1 = take(p->PT() * E);
+  p->o_dskip = take(p->PT() * Sk);
+  p->o_dA = take(N * p->ld);
+  p->o_dR = take(N * p->ld);
+  p->o_bsum = take((i64)nL * 4 * C);          // per layer 2*C doubles
+  p->bwd_floats = o;
+  return 0;
+}
+
+template <class T>
+static const T* P_(const void* const* params, int idx) {
+  return idx < 0 ? nullptr : reinterpret_cast<const T*>(params[idx]);
+}
+
+static int check_ptr_table(const gwn_plan* p, const void* const* params) {
+  GWN_CHECK_ARG(params != nullptr, "null parameter table");
+  for (size_t i = 0; i < p->entries.size(); ++i) {
+    GWN_CHECK_ARG(params[i] != nullptr, "parameter %s is null", p->entries[i].name.c_str());
+    GWN_CHECK_ARG((reinterpret_cast<uintptr_t>(params[i]) & 15) == 0 || p->entries[i].numel == 1,
+                  "parameter %s is not 16-byte aligned", p->entries[i].name.c_str());
+  }
+  return 0;
+}
+
+struct TcnGeom {
+  int L_in, L_out, d;
+};
+
+// A operand of the gated conv (forward and the recompute in backward): two taps of the previous layer's
+// pre-BN tensor with the BatchNorm affine folded into the load.
+static LdRows tcn_rows(const gwn_plan* p, const float* prev, const float* prev_ac, int i) {
+  LdRows a;
+  memset(&a, 0, sizeof(a));
+  const int N = p->c.num_nodes;
+  a.p[0] = prev; a.p[1] = prev;
+  a.rm[0] = make_remap(p->L[i], p->Lin(i), 0, N);
+  a.rm[1] = make_remap(p->L[i], p->Lin(i), p->dil[i], N);
+  a.wd = p->c.residual_channels;
+  a.use_remap = 1;
+  a.ac = prev_ac;
+  return a;
+}
+
+static DropoutSrc layer_dropout(const gwn_plan* p, int training, int mode, const uint8_t* const* masks, uint64_t seed, int i) {
+  if (!training || !p->c.gcn) return make_dropout(GWN_DROPOUT_NONE, nullptr, 0, 0, 0.f);
+  return make_dropout(mode, (mode == GWN_DROPOUT_MASK && masks) ? masks[i] : nullptr, seed, (uint64_t)i, p->c.dropout);
+}
+
+static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
+  GWN_TRY(require_device());
+  GWN_TRY(check_ptr_table(p, a->params));
+  GWN_CHECK_ARG(a->input && a->output && a->workspace, "forward: null input/output/workspace");
+  const gwn_config& c = p->c;
+  GWN_CHECK_ARG(!(a->training && c.dropout > 0.f && c.gcn) || a->dropout_mode != GWN_DROPOUT_MASK || a->keep_masks,
+                "forward: GWN_DROPOUT_MASK without keep_masks");
+  cudaStream_t st = (cudaStream_t)a->stream;
+  float* ws = reinterpret_cast<float*>(a->workspace);
+  const int N = c.num_nodes, C = c.residual_channels, D = c.dilation_channels, Sk = c.skip_channels, E = c.end_channels;
+  const int nL = p->nL, B = c.batch;
+  const void* const* prm = a->params;
+
+  // ---- supports: pack static ones, compute the adaptive one (model.py:185-188)
+  SupportView supF[MAXSUP], supB[MAXSUP];
+  for (int s = 0; s < p->S; ++s) {
+    float* Ap = ws + p->o_sup + (i64)s * N * p->ld;
+    float* ATp = ws + p->o_supT + (i64)s * N * p->ld;
+    if (s < c.n_static_supports) {
+      GWN_CHECK_ARG(a->supports && a->supports[s] && a->support_strides, "forward: support %d missing", s);
+      GWN_LAUNCH_1D(support_pack_kernel, (i64)N * p->ld, st, a->supports[s], (i64)a->support_strides[2 * s],
+                    (i64)a->support_strides[2 * s + 1], Ap, ATp, N, p->ld);
+    } else {
+      GWN_LAUNCH_WARP_ROWS(adp_fwd_kernel, N, st, P_<float>(prm, p->i_nv1), P_<float>(prm, p->i_nv2), c.apt_rank, Ap, ATp, N,
+                           p->ld);
+    }
+    supF[s] = support_padded(Ap, p->ld);
+    supB[s] = support_padded(ATp, p->ld);
+  }
+  // ---- BN bookkeeping
+  if (a->training) {
+    for (int i = 0; i < nL; ++i) GWN_TRY(dev_memset(ws + p->o_sums[i], 0, sizeof(double) * 2 * C, st));
+  } else {
+    for (int i = 0; i < nL; ++i)
+      GWN_LAUNCH_1D(bn_eval_kernel, C, st, P_<float>(prm, p->li[i].bnw), P_<float>(prm, p->li[i].bnb),
+                    P_<float>(prm, p->li[i].bnm), P_<float>(prm, p->li[i].bnv), c.bn_eps, ws + p->o_ac[i], ws + p->o_mr[i], C);
+  }
+  // ---- start conv (+ left pad)
+  {
+    Strides4 is;
+    for (int k = 0; k < 4; ++k) is.s[k] = a->input_strides[k];
+    GWN_LAUNCH_1D(start_fwd_kernel, p->P0() * C, st, a->input, is, P_<float>(prm, p->i_startw), P_<float>(prm, p->i_startb),
+                  ws + p->o_x0, B, c.in_dim, N, p->L0, p->pad, C);
+  }
+  // ---- WaveNet layers (model.py:192-236)
+  for (int i = 0; i < nL; ++i) {
+    const float* prev = i == 0 ? ws + p->o_x0 : ws + p->o_u[i - 1];
+    const float* prev_ac = i == 0 ? nullptr : ws + p->o_ac[i - 1];
+    float* g = ws + p->o_g[i];
+    const i64 Pi = p->P(i);
+    {  // gated dilated conv
+      LdRows la = tcn_rows(p, prev, prev_ac, i);
+      LdWTcn lb{P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw), C};
+      EpGate ep{g, P_<float>(prm, p->li[i].fb), P_<float>(prm, p->li[i].gb), D};
+      GemmShape sh{Pi, 2 * D, 2 * C, 1, 1};
+      GWN_TRY((launch_gemm<TPos64>(la, lb, ep, sh, st)));
+    }
+    const float* segs[MAXSEG];
+    for (int q = 0; q < p->nseg; ++q) segs[q] = g + (i64)q * Pi * D;
+    MlpFwdArgs m;
+    memset(&m, 0, sizeof(m));
+    if (c.gcn) {
+      GcnShape gs{B, p->L[i], N, D, C, p->S, c.order};
+      GWN_TRY(gcn_hops_forward(gs, g, supF, g + Pi * D, st));
+      m.W = P_<float>(prm, p->li[i].mw);
+      m.bias = P_<float>(prm, p->li[i].mb);
+    } else {  // model.py:232
+      m.W = P_<float>(prm, p->li[i].rw);
+      m.bias = P_<float>(prm, p->li[i].rb);
+    }
+    m.segs = segs; m.nseg = p->nseg; m.P = Pi; m.D = D; m.C_out = C;
+    m.drop = layer_dropout(p, a->training, a->dropout_mode, a->keep_masks, a->seed, i);
+    m.res = prev;
+    m.rrm = make_remap(p->L[i], p->Lin(i), p->Lin(i) - p->L[i], N);
+    m.rac = prev_ac;
+    m.stats = a->training ? reinterpret_cast<double*>(ws + p->o_sums[i]) : nullptr;
+    m.y = ws + p->o_u[i];
+    GWN_TRY(mlp_forward(m, st));
+    if (a->training) {
+      GWN_LAUNCH_1D(bn_finalize_kernel, C, st, reinterpret_cast<const double*>(ws + p->o_sums[i]), (double)Pi,
+                    P_<float>(prm, p->li[i].bnw), P_<float>(prm, p->li[i].bnb), const_cast<float*>(P_<float>(prm, p->li[i].bnm)),
+                    const_cast<float*>(P_<float>(prm, p->li[i].bnv)), const_cast<long long*>(P_<long long>(prm, p->li[i].bnt)),
+                    c.bn_eps, c.bn_momentum, ws + p->o_ac[i], ws + p->o_mr[i], C);
+    }
+  }
+  // ---- head: skip sum over the live columns (G5), relu, end convs (model.py:216-222,238-240)
+  const i64 PT = p->PT();
+  {
+    LdRows la;
+    memset(&la, 0, sizeof(la));
+    LdWK lb;
+    memset(&lb, 0, sizeof(lb));
+    EpRows ep;
+    memset(&ep, 0, sizeof(ep));
+    for (int i = 0; i < nL; ++i) {
+      la.p[i] = ws + p->o_g[i];
+      la.rm[i] = make_remap(p->T_out, p->L[i], p->L[i] - p->T_out, N);
+      lb.p[i] = P_<float>(prm, p->li[i].sw);
+      ep.bias[i] = P_<float>(prm, p->li[i].sb);
+    }
+    la.wd = D; la.use_remap = 1;
+    lb.wd = D; lb.ldw = D;
+    ep.y = ws + p->o_skip; ep.ldy = Sk; ep.M = PT; ep.nbias = nL; ep.relu = 1;
+    GemmShape sh{PT, Sk, nL * D, 1, 1};
+    GWN_TRY((launch_gemm<TBig>(la, lb, ep, sh, st)));
+  }
+  {
+    LdRows la;
+    memset(&la, 0, sizeof(la));
+    la.p[0] = ws + p->o_skip; la.wd = Sk;
+    LdWK lb;
+    memset(&lb, 0, sizeof(lb));
+    lb.p[0] = P_<float>(prm, p->i_e1w); lb.wd = Sk; lb.ldw = Sk;
+    EpRows ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.y = ws + p->o_e1; ep.ldy = E; ep.M = PT; ep.bias[0] = P_<float>(prm, p->i_e1b); ep.nbias = 1; ep.relu = 1;
+    GemmShape sh{PT, E, Sk, 1, 1};
+    GWN_TRY((launch_gemm<TBig>(la, lb, ep, sh, st)));
+  }
+  {
+    LdRows la;
+    memset(&la, 0, sizeof(la));
+    la.p[0] = ws + p->o_e1; la.wd = E;
+    LdWK lb;
+    memset(&lb, 0, sizeof(lb));
+    lb.p[0] = P_<float>(prm, p->i_e2w); lb.wd = E; lb.ldw = E;
+    EpNCHW ep;
+    ep.y = a->output; ep.bias = P_<float>(prm, p->i_e2b); ep.N = N; ep.T = p->T_out;
+    ep.sb = (i64)c.out_dim * N * p->T_out; ep.so = (i64)N * p->T_out; ep.sn = p->T_out; ep.st = 1;
+    GemmShape sh{PT, c.out_dim, E, 1, 1};
+    GWN_TRY((launch_gemm<TPos32>(la, lb, ep, sh, st)));
+  }
+  return 0;
+}
+
+static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
+  GWN_TRY(require_device());
+  GWN_TRY(check_ptr_table(p, a->params));
+  GWN_CHECK_ARG(a->grad_output && a->workspace && a->scratch && a->grad_flat && a->input, "backward: null argument");
+  const gwn_config& c = p->c;
+  cudaStream_t st = (cudaStream_t)a->stream;
+  const float* ws = reinterpret_cast<const float*>(a->workspace);
+  float* sc = reinterpret_cast<float*>(a->scratch);
+  float* gf = a->grad_flat;
+  const int N = c.num_nodes, C = c.residual_channels, D = c.dilation_channels, Sk = c.skip_channels, E = c.end_channels;
+  const int nL = p->nL, B = c.batch, O = c.out_dim;
+  const void* const* prm = a->params;
+  const i64 PT = p->PT();
+  auto G = [&](int idx) { return gf + p->entries[idx].grad_off; };
+  const int training = a->training ? 1 : 0;
+  const int dmode = a->dropout_mode;
+
+  GWN_TRY(dev_memset(gf, 0, sizeof(float) * p->grad_floats, st));
+  GWN_TRY(dev_memset(sc + p->o_bsum, 0, sizeof(float) * (i64)nL * 4 * C, st));
+  if (c.adaptive) GWN_TRY(dev_memset(sc + p->o_dA, 0, sizeof(float) * (i64)N * p->ld, st));
+  GWN_TRY(dev_memset(sc + p->o_dout, 0, sizeof(float) * PT * p->ldo, st));
+
+  SupportView supB[MAXSUP];
+  for (int s = 0; s < p->S; ++s) supB[s] = support_padded(ws + p->o_supT + (i64)s * N * p->ld, p->ld);
+
+  // ---- head backward
+  {
+    // grad_output [B,O,N,T_out] contiguous -> dout [P_T, ldo]
+    int64_t sz[4] = {B, O, N, p->T_out};
+    int64_t ss[4] = {(int64_t)O * N * p->T_out, (int64_t)N * p->T_out, p->T_out, 1};
+    int64_t ds[4] = {(int64_t)p->T_out * N * p->ldo, 1, p->ldo, (int64_t)N * p->ldo};
+    GWN_TRY(permute4d(a->grad_output, ss, sc + p->o_dout, ds, sz, st));
+  }
+  const float* dout = sc + p->o_dout;
+  const float* e1 = ws + p->o_e1;
+  const float* skip = ws + p->o_skip;
+  float* de1 = sc + p->o_de1;
+  float* dskip = sc + p->o_dskip;
+  float* dgh = sc + p->o_dgh;
+  GWN_CHECK_ARG(PT < 2147483647LL, "backward: too many output positions");
+  {  // (a) de1 = (dout . W2) * (e1 > 0)
+    LdRows la;
+    memset(&la, 0, sizeof(la));
+    la.p[0] = dout; la.wd = p->ldo;
+    LdWN lb;
+    memset(&lb, 0, sizeof(lb));
+    lb.p[0] = P_<float>(prm, p->i_e2w); lb.wd = E; lb.ldw = E;
+    EpRows ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.y = de1; ep.ldy = E; ep.M = PT; ep.gate = e1;
+    GemmShape sh{PT, E, O, 1, 1};
+    GWN_TRY((launch_gemm<TBig>(la, lb, ep, sh, st)));
+  }
+  {  // (b) dW2, db2
+    LdCols la;
+    memset(&la, 0, sizeof(la));
+    la.p[0] = dout; la.wd = p->ldo; la.nseg = 1;
+    LdCols lb;
+    memset(&lb, 0, sizeof(lb));
+    lb.p[0] = e1; lb.wd = E; lb.nseg = 1; lb.ones = 1;
+    EpWgrad ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.dw[0] = G(p->i_e2w); ep.db[0] = G(p->i_e2b); ep.wd = E; ep.nseg = 1; ep.ldw = E; ep.nbias = 1;
+    GemmShape sh{(i64)O, E + 1, (int)PT, pick_ksplit(O, E + 1, PT, TW32::BM, TW32::BN, kTargetBlocks), 1};
+    GWN_TRY((launch_gemm<TW32>(la, lb, ep, sh, st)));
+  }
+  {  // (c) dskip = (de1 . W1) * (skip > 0)
+    LdRows la;
+    memset(&la, 0, sizeof(la));
+    la.p[0] = de1; la.wd = E;
+    LdWN lb;
+    memset(&lb, 0, sizeof(lb));
+    lb.p[0] = P_<float>(prm, p->i_e1w); lb.wd = Sk; lb.ldw = Sk;
+    EpRows ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.y = dskip; ep.ldy = Sk; ep.M = PT; ep.gate = skip;
+    GemmShape sh{PT, Sk, E, 1, 1};
+    GWN_TRY((launch_gemm<TBig>(la, lb, ep, sh, st)));
+  }
+  {  // (d) dW1, db1
+    LdCols la;
+    memset(&la, 0, sizeof(la));
+    la.p[0] = de1; la.wd = E; la.nseg = 1;
+    LdCols lb;
+    memset(&lb, 0, sizeof(lb));
+    lb.p[0] = skip; lb.wd = Sk; lb.nseg = 1; lb.ones = 1;
+    EpWgrad ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.dw[0] = G(p->i_e1w); ep.db[0] = G(p->i_e1b); ep.wd = Sk; ep.nseg = 1; ep.ldw = Sk; ep.nbias = 1;
+    GemmShape sh{(i64)E, Sk + 1, (int)PT, pick_ksplit(E, Sk + 1, PT, TBig::BM, TBig::BN, kTargetBlocks), 1};
+    GWN_TRY((launch_gemm<TBig>(la, lb, ep, sh, st)));
+  }
+  {  // (e) skip conv weight / bias gradients of every layer; (f) gradient into the live columns of every g_i
+    LdCols la;
+    memset(&la, 0, sizeof(la));
+    la.p[0] = dskip; la.wd = Sk; la.nseg = 1;
+    LdCols lb;
+    memset(&lb, 0, sizeof(lb));
+    EpWgrad ep;
+    memset(&ep, 0, sizeof(ep));
+    LdWN lw;
+    memset(&lw, 0, sizeof(lw));
+    for (int i = 0; i < nL; ++i) {
+      lb.p[i] = ws + p->o_g[i];
+      lb.rm[i] = make_remap(p->T_out, p->L[i], p->L[i] - p->T_out, N);
+      ep.dw[i] = G(p->li[i].sw);
+      ep.db[i] = G(p->li[i].sb);
+      lw.p[i] = P_<float>(prm, p->li[i].sw);
+    }
+    lb.wd = D; lb.nseg = nL; lb.use_remap = 1; lb.ones = 1;
+    ep.wd = D; ep.nseg = nL; ep.ldw = D; ep.nbias = nL;
+    GemmShape sh{(i64)Sk, nL * D + 1, (int)PT, pick_ksplit(Sk, nL * D + 1, PT, TBig::BM, TBig::BN, kTargetBlocks), 1};
+    GWN_TRY((launch_gemm<TBig>(la, lb, ep, sh, st)));
+
+    LdRows lr;
+    memset(&lr, 0, sizeof(lr));
+    lr.p[0] = dskip; lr.wd = Sk;
+    lw.wd = D; lw.ldw = D;
+    EpRows es;
+    memset(&es, 0, sizeof(es));
+    es.y = dgh; es.M = PT; es.seg_wd = D;
+    GemmShape sh2{PT, nL * D, Sk, 1, 1};
+    GWN_TRY((launch_gemm<TBig>(lr, lw, es, sh2, st)));
+  }
+
+  // ---- layers in reverse
+  float* cur = sc + p->o_buf0;   // holds d(loss)/d(x_{i+1}) on entry of layer i (unused for the last layer)
+  float* oth = sc + p->o_buf1;
+  float* dsegs = sc + p->o_dsegs;
+  float* dg = sc + p->o_dg;
+  float* dpre = sc + p->o_dpre;
+  for (int i = nL - 1; i >= 0; --i) {
+    const bool live = i < nL - 1;   // the last layer's gcn/bn output is discarded (model.py:238)
+    const i64 Pi = p->P(i);
+    const float* prev = i == 0 ? ws + p->o_x0 : ws + p->o_u[i - 1];
+    const float* prev_ac = i == 0 ? nullptr : ws + p->o_ac[i - 1];
+    const float* g = ws + p->o_g[i];
+    const float* dgh_i = dgh + (i64)i * PT * D;
+    const float* dgp;   // gradient wrt g_i
+    if (live) {
+      GWN_LAUNCH_1D(bn_bwd_apply_kernel, Pi * C, st, cur, ws + p->o_u[i], ws + p->o_ac[i], ws + p->o_mr[i],
+                    reinterpret_cast<const double*>(sc + p->o_bsum + (i64)i * 4 * C), (double)Pi, training,
+                    G(p->li[i].bnw), G(p->li[i].bnb), Pi, C);
+      const float* segs[MAXSEG];
+      for (int q = 0; q < p->nseg; ++q) segs[q] = g + (i64)q * Pi * D;
+      MlpBwdArgs m;
+      memset(&m, 0, sizeof(m));
+      m.dh = cur;
+      m.drop = layer_dropout(p, training, dmode, a->keep_masks, a->seed, i);
+      m.segs = segs; m.nseg = p->nseg; m.P = Pi; m.D = D; m.C_out = C;
+      m.W = P_<float>(prm, c.gcn ? p->li[i].mw : p->li[i].rw);
+      m.dsegs = dsegs;
+      m.dW = G(c.gcn ? p->li[i].mw : p->li[i].rw);
+      m.dbias = G(c.gcn ? p->li[i].mb : p->li[i].rb);
+      GWN_TRY(mlp_backward(m, st));
+      if (c.gcn) {
+        GcnShape gs{B, p->L[i], N, D, C, p->S, c.order};
+        float* dsup[MAXSUP];
+        i64 ldds[MAXSUP];
+        for (int s = 0; s < p->S; ++s) { dsup[s] = nullptr; ldds[s] = p->ld; }
+        if (c.adaptive) dsup[p->S - 1] = sc + p->o_dA;
+        GWN_TRY(gcn_hops_backward(gs, g, g + Pi * D, supB, dsegs, dg, dgh_i, p->T_out, dsup, ldds, st));
+      } else {
+        GWN_LAUNCH_1D(add_window_kernel, Pi * D, st, dg, (const float*)dsegs, dgh_i, B, p->L[i], N, D, p->T_out);
+      }
+      dgp = dg;
+    } else {
+      GWN_LAUNCH_1D(add_window_kernel, Pi * D, st, dg, (const float*)nullptr, dgh_i, B, p->L[i], N, D, p->T_out);
+      dgp = dg;
+    }
+    // gated conv backward: recompute pre-activations -> dpre
+    {
+      LdRows la = tcn_rows(p, prev, prev_ac, i);
+      LdWTcn lb{P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw), C};
+      EpGateBwd ep{dpre, dgp, P_<float>(prm, p->li[i].fb), P_<float>(prm, p->li[i].gb), D};
+      GemmShape sh{Pi, 2 * D, 2 * C, 1, 1};
+      GWN_TRY((launch_gemm<TPos64>(la, lb, ep, sh, st)));
+    }
+    const i64 Pin = (i64)B * p->Lin(i) * N;
+    {  // input gradient (+ residual path, + BN-backward sums of the layer below)
+      LdDpreTaps la{dpre, 2 * D, N, p->Lin(i), p->L[i], p->dil[i]};
+      LdWTcnT lb{P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw), C, 2 * D};
+      EpTcnDgrad<TPos32> ep;
+      memset(&ep, 0, sizeof(ep));
+      ep.dx = oth; ep.du = live ? cur : nullptr; ep.C = C; ep.N = N; ep.L_in = p->Lin(i); ep.L_out = p->L[i];
+      if (i > 0) {
+        ep.uprev = ws + p->o_u[i - 1];
+        ep.mr = ws + p->o_mr[i - 1];
+        ep.bsum = reinterpret_cast<double*>(sc + p->o_bsum + (i64)(i - 1) * 4 * C);
+      }
+      GemmShape sh{Pin, C, 4 * D, 1, 1};
+      GWN_TRY((launch_gemm<TPos32>(la, lb, ep, sh, st)));
+    }
+    {  // filter / gate weight and bias gradients
+      LdCols la;
+      memset(&la, 0, sizeof(la));
+      la.p[0] = dpre; la.wd = 2 * D; la.nseg = 1;
+      LdCols lb;
+      memset(&lb, 0, sizeof(lb));
+      lb.p[0] = prev; lb.p[1] = prev;
+      lb.rm[0] = make_remap(p->L[i], p->Lin(i), 0, N);
+      lb.rm[1] = make_remap(p->L[i], p->Lin(i), p->dil[i], N);
+      lb.wd = C; lb.nseg = 2; lb.use_remap = 1; lb.ones = 1; lb.ac = prev_ac;
+      EpWgradTcn ep{G(p->li[i].fw), G(p->li[i].gw), G(p->li[i].fb), G(p->li[i].gb), C};
+      GWN_CHECK_ARG(Pi < 2147483647LL, "backward: too many positions");
+      GemmShape sh{(i64)2 * D, 2 * C + 1, (int)Pi, pick_ksplit(2 * D, 2 * C + 1, Pi, TW64::BM, TW64::BN, kTargetBlocks), 1};
+      GWN_TRY((launch_gemm<TW64>(la, lb, ep, sh, st)));
+    }
+    std::swap(cur, oth);
+  }
+  // ---- start conv backward: cur = d(loss)/d(x0)
+  {
+    LdCols la;
+    memset(&la, 0, sizeof(la));
+    la.p[0] = cur; la.wd = C; la.nseg = 1;
+    LdInputCols lb;
+    lb.in = a->input;
+    lb.sb = a->input_strides[0]; lb.sf = a->input_strides[1]; lb.sn = a->input_strides[2]; lb.st = a->input_strides[3];
+    lb.F = c.in_dim; lb.N = N; lb.L0 = p->L0; lb.pad = p->pad; lb.ones = 1;
+    EpWgrad ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.dw[0] = G(p->i_startw); ep.db[0] = G(p->i_startb); ep.wd = c.in_dim; ep.nseg = 1; ep.ldw = c.in_dim; ep.nbias = 1;
+    GWN_CHECK_ARG(p->P0() < 2147483647LL, "backward: too many input positions");
+    GemmShape sh{(i64)C, c.in_dim + 1, (int)p->P0(), pick_ksplit(C, c.in_dim + 1, p->P0(), TW32::BM, TW32::BN, kTargetBlocks), 1};
+    GWN_TRY((launch_gemm<TW32>(la, lb, ep, sh, st)));
+    if (a->grad_input)
+      GWN_LAUNCH_1D(start_dgrad_kernel, (i64)B * c.in_dim * N * c.seq_len, st, (const float*)cur, P_<float>(prm, p->i_startw),
+                    a->grad_input, B, c.in_dim, N, c.seq_len, p->L0, p->pad, C);
+  }
+  // ---- adaptive adjacency backward (model.py:187)
+  if (c.adaptive) {
+    const float* Ap = ws + p->o_sup + (i64)(p->S - 1) * N * p->ld;
+    GWN_LAUNCH_WARP_ROWS(adp_bwd_rows_kernel, N, st, (const float*)(sc + p->o_dA), Ap, P_<float>(prm, p->i_nv1),
+                         P_<float>(prm, p->i_nv2), c.apt_rank, sc + p->o_dR, G(p->i_nv1), N, p->ld);
+    GWN_LAUNCH_1D(adp_bwd_cols_kernel, (i64)c.apt_rank * N, st, (const float*)(sc + p->o_dR), P_<float>(prm, p->i_nv1),
+                  c.apt_rank, G(p->i_nv2), N, p->ld);
+  }
+  return 0;
+}
+
+}  // namespace gwn
+
+// =============================================================================== C ABI
+using namespace gwn;
+
+extern "C" {
+
+const char* gwn_last_error(void) { return g_err; }
+int gwn_abi_version(void) { return GWN_ABI_VERSION; }
+long long gwn_launch_count(int reset) {
+  long long v = g_launches.load(std::memory_order_relaxed);
+  if (reset) g_launches.store(0, std::memory_order_relaxed);
+  return v;
+}
+
+int gwn_device_info(int* n_devices, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor) {
+#if GWN_EMU
+  if (n_devices) *n_devices = 0;
+  if (name && name_len > 0) snprintf(name, name_len, "host-emulation (tests only)");
+  if (sm_count) *sm_count = 0;
+  if (cc_major) *cc_major = 0;
+  if (cc_minor) *cc_minor = 0;
+  return 0;
+#else
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { n = 0; cudaGetLastError(); }
+  if (n_devices) *n_devices = n;
+  if (n <= 0) {
+    if (name && name_len > 0) name[0] = 0;
+    return 0;
+  }
+  int dev = 0;
+  GWN_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp pr;
+  GWN_CUDA(cudaGetDeviceProperties(&pr, dev));
+  if (name && name_len > 0) snprintf(name, name_len, "%s", pr.name);
+  if (sm_count) *sm_count = pr.multiProcessorCount;
+  if (cc_major) *cc_major = pr.major;
+  if (cc_minor) *cc_minor = pr.minor;
+  return 0;
+#endif
+}
+
+int gwn_permute4d(const float* src, const int64_t src_strides[4], float* dst, const int64_t dst_strides[4],
+                  const int64_t sizes[4], void* stream) {
+  GWN_TRY(require_device());
+  GWN_CHECK_ARG(src && dst, "permute4d: null pointer");
+  return permute4d(src, src_strides, dst, dst_strides, sizes, (cudaStream_t)stream);
+}
+
+int gwn_nconv_fwd(const float* x, const float* A, int64_t lda, float* y, int B, int L, int V, int C, int precision,
+                  void* stream) {
+  GWN_TRY(require_device());
+  GWN_CHECK_ARG(x && A && y, "nconv_fwd: null pointer");
+  GWN_CHECK_ARG(precision == GWN_PREC_FP32, "nconv_fwd: precision %d not available in this build", precision);
+  SupportView sv = support_fwd(A, lda, 1);
+  const float* X[1] = {x};
+  float* Y[1] = {y};
+  return node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, B, L, 0, V, C, (cudaStream_t)stream);
+}
+
+int gwn_nconv_bwd(const float* dy, const float* x, const float* A, int64_t lda, float* dx, float* dA, int64_t ldda, int B,
+                  int L, int V, int C, int precision, void* stream) {
+  GWN_TRY(require_device());
+  GWN_CHECK_ARG(dy && A, "nconv_bwd: null pointer");
+  GWN_CHECK_ARG(precision == GWN_PREC_FP32, "nconv_bwd: precision %d not available in this build", precision);
+  if (dx) {
+    SupportView sv = support_bwd(A, lda, 1);
+    const float* X[1] = {dy};
+    float* Y[1] = {dx};
+    GWN_TRY(node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, B, L, 0, V, C, (cudaStream_t)stream));
+  }
+  if (dA) {
+    GWN_CHECK_ARG(x != nullptr, "nconv_bwd: x needed for dA");
+    const float* Xp[1] = {x};
+    const float* Yp[1] = {dy};
+    GWN_TRY(support_grad_gemm(Xp, Yp, 1, dA, ldda, B, L, V, C, (cudaStream_t)stream));
+  }
+  return 0;
+}
+
+int gwn_linear_fwd(const float* x, const float* W, const float* bias, float* y, int64_t positions, int c_in, int c_out,
+                   void* stream) {
+  GWN_TRY(require_device());
+  GWN_CHECK_ARG(x && W && bias && y, "linear_fwd: null pointer");
+  GWN_CHECK_ARG(c_in % 4 == 0, "linear_fwd: c_in must be a multiple of 4");
+  const float* segs[1] = {x};
+  MlpFwdArgs m;
+  memset(&m, 0, sizeof(m));
+  m.segs = segs; m.nseg = 1; m.P = positions; m.D = c_in; m.C_out = c_out; m.W = W; m.bias = bias;
+  m.drop = make_dropout(GWN_DROPOUT_NONE, nullptr, 0, 0, 0.f);
+  m.y = y;
+  return mlp_forward(m, (cudaStream_t)stream);
+}
+
+int gwn_linear_bwd(const float* dy, const float* x, const float* W, float* dx, float* dW, float* dbias, int64_t positions,
+                   int c_in, int c_out, void* stream) {
+  GWN_TRY(require_device());
+  GWN_CHECK_ARG(dy && x && W, "linear_bwd: null pointer");
+  GWN_CHECK_ARG((dW == nullptr) == (dbias == nullptr), "linear_bwd: dW and dbias must be given together");
+  const float* segs[1] = {x};
+  MlpBwdArgs m;
+  memset(&m, 0, sizeof(m));
+  m.dh = dy; m.drop = make_dropout(GWN_DROPOUT_NONE, nullptr, 0, 0, 0.f);
+  m.segs = segs; m.nseg = 1; m.P = positions; m.D = c_in; m.C_out = c_out; m.W = W;
+  m.dsegs = dx; m.dW = dW; m.dbias = dbias;
+  if (dW) {
+    GWN_TRY(dev_memset(dW, 0, sizeof(float) * (size_t)c_in * c_out, (cudaStream_t)stream));
+    GWN_TRY(dev_memset(dbias, 0, sizeof(float) * (size_t)c_out, (cudaStream_t)stream));
+  }
+  return mlp_backward(m, (cudaStream_t)stream);
+}
+
+static int gcn_check(const gwn_gcn_desc* d) {
+  GWN_CHECK_ARG(d != nullptr, "gcn: null descriptor");
+  GWN_CHECK_ARG(d->B >= 1 && d->L >= 1 && d->V >= 1 && d->C >= 4 && d->C % 4 == 0 && d->c_out >= 1, "gcn: bad dims");
+  GWN_CHECK_ARG(d->c_out % 4 == 0, "gcn: c_out must be a multiple of 4");
+  GWN_CHECK_ARG(d->n_supports >= 1 && d->n_supports <= MAXSUP && d->order >= 1 && d->order <= MAXSUP &&
+                    1 + d->n_supports * d->order <= MAXSEG,
+                "gcn: bad support count / order");
+  GWN_CHECK_ARG(d->precision == GWN_PREC_FP32, "gcn: precision %d not available in this build", d->precision);
+  GWN_CHECK_ARG(d->dropout_p >= 0.f && d->dropout_p < 1.f, "gcn: dropout must be in [0,1)");
+  return 0;
+}
+
+int gwn_gcn_fwd(const gwn_gcn_desc* d, const float* x, const float* const* supports, const int64_t* lds, const float* W,
+                const float* bias, const uint8_t* keep_mask, float* hops, float* y, void* stream) {
+  GWN_TRY(require_device());
+  GWN_TRY(gcn_check(d));
+  GWN_CHECK_ARG(x && supports && lds && W && bias && hops && y, "gcn_fwd: null pointer");
+  GWN_CHECK_ARG(d->dropout_mode != GWN_DROPOUT_MASK || keep_mask, "gcn_fwd: GWN_DROPOUT_MASK without keep_mask");
+  cudaStream_t st = (cudaStream_t)stream;
+  GcnShape gs{d->B, d->L, d->V, d->C, d->c_out, d->n_supports, d->order};
+  SupportView sv[MAXSUP];
+  for (int s = 0; s < d->n_supports; ++s) sv[s] = support_fwd(supports[s], lds[s], 1);
+  GWN_TRY(gcn_hops_forward(gs, x, sv, hops, st));
+  const i64 P = (i64)d->B * d->L * d->V;
+  const int nseg = 1 + d->n_supports * d->order;
+  const float* segs[MAXSEG];
+  segs[0] = x;
+  for (int q = 1; q < nseg; ++q) segs[q] = hops + (i64)(q - 1) * P * d->C;
+  MlpFwdArgs m;
+  memset(&m, 0, sizeof(m));
+  m.segs = segs; m.nseg = nseg; m.P = P; m.D = d->C; m.C_out = d->c_out; m.W = W; m.bias = bias;
+  m.drop = make_dropout(d->dropout_mode, keep_mask, d->seed, d->offset, d->dropout_p);
+  m.y = y;
+  return mlp_forward(m, st);
+}
+
+size_t gwn_gcn_bwd_scratch_floats(const gwn_gcn_desc* d) {
+  if (!d) return 0;
+  return (size_t)(1 + d->n_supports * d->order) * d->B * d->L * d->V * d->C;
+}
+
+int gwn_gcn_bwd(const gwn_gcn_desc* d, const float* dy, const float* x, const float* const* supports, const int64_t* lds,
+                const float* W, const uint8_t* keep_mask, const float* hops, float* dx, float* dW, float* dbias,
+                float* const* dsupports, const int64_t* ldds, float* scratch, void* stream) {
+  GWN_TRY(require_device());
+  GWN_TRY(gcn_check(d));
+  GWN_CHECK_ARG(dy && x && supports && lds && W && hops && dx && scratch, "gcn_bwd: null pointer");
+  GWN_CHECK_ARG((dW == nullptr) == (dbias == nullptr), "gcn_bwd: dW and dbias must be given together");
+  cudaStream_t st = (cudaStream_t)stream;
+  GcnShape gs{d->B, d->L, d->V, d->C, d->c_out, d->n_supports, d->order};
+  const i64 P = (i64)d->B * d->L * d->V;
+  const int nseg = 1 + d->n_supports * d->order;
+  const float* segs[MAXSEG];
+  segs[0] = x;
+  for (int q = 1; q < nseg; ++q) segs[q] = hops + (i64)(q - 1) * P * d->C;
+  MlpBwdArgs m;
+  memset(&m, 0, sizeof(m));
+  m.dh = dy;
+  m.drop = make_dropout(d->dropout_mode, keep_mask, d->seed, d->offset, d->dropout_p);
+  m.segs = segs; m.nseg = nseg; m.P = P; m.D = d->C; m.C_out = d->c_out; m.W = W;
+  m.dsegs = scratch; m.dW = dW; m.dbias = dbias;
+  if (dW) {
+    GWN_TRY(dev_memset(dW, 0, sizeof(float) * (size_t)d->c_out * nseg * d->C, st));
+    GWN_TRY(dev_memset(dbias, 0, sizeof(float) * (size_t)d->c_out, st));
+  }
+  GWN_TRY(mlp_backward(m, st));
+  SupportView sv[MAXSUP];
+  i64 ldd[MAXSUP];
+  for (int s = 0; s < d->n_supports; ++s) {
+    sv[s] = support_bwd(supports[s], lds[s], 1);
+    ldd[s] = ldds ? ldds[s] : d->V;
+  }
+  return gcn_hops_backward(gs, x, hops, sv, scratch, dx, nullptr, 0, dsupports, ldd, st);
+}
+
+int gwn_plan_create(const gwn_config* cfg, gwn_plan** out) {
+  GWN_CHECK_ARG(cfg && out, "plan_create: null argument");
+  gwn_plan* p = new gwn_plan();
+  p->c = *cfg;
+  int st = build_plan(p);
+  if (st != 0) {
+    delete p;
+    return st;
+  }
+  *out = p;
+  return 0;
+}
+
+void gwn_plan_destroy(gwn_plan* p) { delete p; }
+
+int gwn_plan_workspace_bytes(const gwn_plan* p, size_t* fwd, size_t* bwd) {
+  GWN_CHECK_ARG(p, "null plan");
+  if (fwd) *fwd = (size_t)p->fwd_floats * sizeof(float);
+  if (bwd) *bwd = (size_t)p->bwd_floats * sizeof(float);
+  return 0;
+}
+
+int gwn_plan_param_count(const gwn_plan* p, int* n_entries, int64_t* grad_floats) {
+  GWN_CHECK_ARG(p, "null plan");
+  if (n_entries) *n_entries = (int)p->entries.size();
+  if (grad_floats) *grad_floats = p->grad_floats;
+  return 0;
+}
+
+int gwn_plan_param_info(const gwn_plan* p, int i, char* name, int name_len, int64_t* grad_offset, int64_t* numel) {
+  GWN_CHECK_ARG(p && i >= 0 && i < (int)p->entries.size(), "param_info: bad index");
+  if (name && name_len > 0) snprintf(name, name_len, "%s", p->entries[i].name.c_str());
+  if (grad_offset) *grad_offset = p->entries[i].grad_off;
+  if (numel) *numel = p->entries[i].numel;
+  return 0;
+}
+
+int gwn_plan_out_len(const gwn_plan* p, int* t_out, int* receptive_field) {
+  GWN_CHECK_ARG(p, "null plan");
+  if (t_out) *t_out = p->T_out;
+  if (receptive_field) *receptive_field = p->RF;
+  return 0;
+}
+
+int gwn_plan_forward(gwn_plan* p, const gwn_forward_args* a) {
+  GWN_CHECK_ARG(p && a, "plan_forward: null argument");
+  return plan_forward(p, a);
+}
+
+int gwn_plan_backward(gwn_plan* p, const gwn_backward_args* a) {
+  GWN_CHECK_ARG(p && a, "plan_backward: null argument");
+  return plan_backward(p, a);
+}
+
+}  // extern "C"

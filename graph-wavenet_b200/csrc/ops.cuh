@@ -1,0 +1,227 @@
+// Host-side launchers of the fused operators (fp32 tier) shared by the op-level C ABI
+// (gwn_nconv_*, gwn_linear_*, gwn_gcn_*) and the whole-network plan (gwn_plan_*).
+#pragma once
+#include "functors.cuh"
+#include "elementwise.cuh"
+
+namespace gwn {
+
+typedef Tile<128, 128, 8, 8> TBig;    // node contraction, wide position GEMMs (256 threads)
+typedef Tile<128, 64, 8, 4> TPos64;   // gated conv: N = 2*D = 64 (256 threads)
+typedef Tile<128, 32, 8, 4> TPos32;   // N <= 32 outputs per position (128 threads)
+typedef Tile<32, 128, 4, 4> TW32;     // weight gradients with <= 32 output rows (256 threads)
+typedef Tile<64, 64, 4, 4> TW64;      // small square reductions: gated-conv wgrad, dA (256 threads)
+
+constexpr int kTargetBlocks = 148 * 3;
+
+// One support as the node-contraction A operand: op(k, m) = p[k*ks + m*ms].
+//   forward  y[w] = sum_v A[v,w] x[v]:  k = v, m = w  -> (ks, ms) = (row stride, col stride) of A
+//   backward dx[v] = sum_w A[v,w] dy[w]: k = w, m = v -> (ks, ms) = (col stride, row stride) of A, or the
+//   row-major strides of a materialised A^T.
+struct SupportView {
+  const float* p;
+  i64 ks, ms;
+  int mlim;  // readable extent along m when ms == 1 (zero-padded ld), or 0 if only [0, M) is readable
+};
+inline SupportView support_fwd(const float* A, i64 rs, i64 cs) { return SupportView{A, rs, cs, 0}; }
+inline SupportView support_bwd(const float* A, i64 rs, i64 cs) { return SupportView{A, cs, rs, 0}; }
+inline SupportView support_padded(const float* Ap, int ld) { return SupportView{Ap, ld, 1, ld}; }
+
+inline void fill_support(LdSupport& l, int idx, const SupportView& s, int M) {
+  l.p[idx] = s.p;
+  l.rs[idx] = s.ks;
+  l.cs[idx] = s.ms;
+  bool aligned = ((reinterpret_cast<uintptr_t>(s.p) & 15) == 0) && (s.ks % 4 == 0) && (s.ms == 1);
+  l.vec[idx] = aligned ? 1 : 0;
+  l.xlim[idx] = (s.mlim > 0) ? s.mlim : M;
+}
+
+// Y_s[m] = sum_k op_s(k,m) X_s[k] (+ add_s) for s < nsup (batched), or, when kcat,
+// Y_0[m] = sum_s sum_k op_s(k,m) X_s[k] (+ add_0 + window(add2)).
+inline int node_gemm(const SupportView* sup, int nsup, bool kcat, const float* const* X,
+                     float* const* Y, const float* const* add, const float* add2, int B, int L, int T_out, int V, int C,
+                     cudaStream_t stream) {
+  GWN_CHECK_ARG(nsup >= 1 && nsup <= MAXSUP, "node_gemm: %d supports (max %d)", nsup, MAXSUP);
+  GWN_CHECK_ARG(C % 4 == 0, "node_gemm: channels (%d) must be a multiple of 4", C);
+  LdSupport a;
+  LdSlab b;
+  EpSlab e;
+  memset(&a, 0, sizeof(a));
+  memset(&b, 0, sizeof(b));
+  memset(&e, 0, sizeof(e));
+  for (int s = 0; s < nsup; ++s) {
+    fill_support(a, s, sup[s], V);
+    b.p[s] = X[s];
+  }
+  a.kper = V; a.kcat = kcat ? 1 : 0;
+  b.V = V; b.C = C; b.kper = V; b.kcat = kcat ? 1 : 0;
+  int nout = kcat ? 1 : nsup;
+  for (int s = 0; s < nout; ++s) {
+    e.y[s] = Y[s];
+    e.add[s] = add ? add[s] : nullptr;
+  }
+  e.add2 = add2;
+  e.V = V; e.C = C; e.L = L; e.T_out = T_out;
+  GemmShape sh{(i64)V, (int)((i64)B * L * C), kcat ? nsup * V : V, 1, nout};
+  GWN_CHECK_ARG((i64)B * L * C < 2147483647LL, "node_gemm: B*L*C too large");
+  return launch_gemm<TBig>(a, b, e, sh, stream);
+}
+
+// dA[v,w] += sum over pairs, slabs, c of Xp[(slab,v),c] * Yp[(slab,w),c]
+inline int support_grad_gemm(const float* const* Xp, const float* const* Yp, int npairs, float* dA, i64 ldda, int B, int L,
+                             int V, int C, cudaStream_t stream) {
+  GWN_CHECK_ARG(npairs >= 1 && npairs <= MAXSUP, "support_grad: bad pair count %d", npairs);
+  LdSlabK a, b;
+  memset(&a, 0, sizeof(a));
+  memset(&b, 0, sizeof(b));
+  for (int i = 0; i < npairs; ++i) { a.p[i] = Xp[i]; b.p[i] = Yp[i]; }
+  a.V = b.V = V; a.C = b.C = C;
+  a.kper = b.kper = (i64)B * L * C;
+  i64 K = a.kper * npairs;
+  GWN_CHECK_ARG(K < 2147483647LL, "support_grad: K too large");
+  EpAtomicMat e{dA, ldda};
+  GemmShape sh{(i64)V, V, (int)K, pick_ksplit(V, V, K, TW64::BM, TW64::BN, kTargetBlocks), 1};
+  return launch_gemm<TW64>(a, b, e, sh, stream);
+}
+
+struct MlpFwdArgs {
+  const float* const* segs;  // nseg tensors [P, D]
+  int nseg;
+  i64 P;
+  int D, C_out;
+  const float* W;            // [C_out, nseg*D]
+  const float* bias;
+  DropoutSrc drop;
+  const float* res;          // nullable residual source
+  Remap rrm;
+  const float* rac;
+  double* stats;             // nullable
+  float* y;
+};
+inline int mlp_forward(const MlpFwdArgs& m, cudaStream_t stream) {
+  GWN_CHECK_ARG(m.nseg >= 1 && m.nseg <= MAXSEG, "mlp: %d segments (max %d)", m.nseg, MAXSEG);
+  GWN_CHECK_ARG(m.D % 4 == 0, "mlp: c_in per segment (%d) must be a multiple of 4", m.D);
+  GWN_CHECK_ARG((reinterpret_cast<uintptr_t>(m.W) & 15) == 0, "mlp: weight pointer must be 16-byte aligned");
+  LdRows a;
+  memset(&a, 0, sizeof(a));
+  for (int q = 0; q < m.nseg; ++q) a.p[q] = m.segs[q];
+  a.wd = m.D;
+  LdWK b;
+  memset(&b, 0, sizeof(b));
+  b.p[0] = m.W; b.wd = m.nseg * m.D; b.ldw = m.nseg * m.D;
+  EpMlp<TPos32> e;
+  memset(&e, 0, sizeof(e));
+  e.y = m.y; e.bias = m.bias; e.C = m.C_out; e.drop = m.drop; e.res = m.res; e.rrm = m.rrm; e.rac = m.rac; e.stats = m.stats;
+  GemmShape sh{m.P, m.C_out, m.nseg * m.D, 1, 1};
+  return launch_gemm<TPos32>(a, b, e, sh, stream);
+}
+
+struct MlpBwdArgs {
+  const float* dh;            // [P, C_out] gradient wrt the (post-dropout) mlp output
+  DropoutSrc drop;
+  const float* const* segs;   // nseg saved inputs [P, D]
+  int nseg;
+  i64 P;
+  int D, C_out;
+  const float* W;
+  float* dsegs;               // [nseg][P][D] (written); nullable to skip the data gradient
+  float* dW;                  // accumulated (atomic); nullable
+  float* dbias;               // accumulated; nullable iff dW is
+};
+inline int mlp_backward(const MlpBwdArgs& m, cudaStream_t stream) {
+  GWN_CHECK_ARG(m.nseg >= 1 && m.nseg <= MAXSEG && m.D % 4 == 0 && m.C_out % 4 == 0,
+                "mlp bwd: unsupported shape (nseg=%d D=%d C_out=%d)", m.nseg, m.D, m.C_out);
+  const int Ktot = m.nseg * m.D;
+  if (m.dsegs) {
+    LdRows a;
+    memset(&a, 0, sizeof(a));
+    a.p[0] = m.dh; a.wd = m.C_out; a.drop = m.drop;
+    LdWN b;
+    memset(&b, 0, sizeof(b));
+    b.p[0] = m.W; b.wd = Ktot; b.ldw = Ktot;
+    EpRows e;
+    memset(&e, 0, sizeof(e));
+    e.y = m.dsegs; e.M = m.P; e.seg_wd = m.D;
+    GemmShape sh{m.P, Ktot, m.C_out, 1, 1};
+    GWN_TRY((launch_gemm<TBig>(a, b, e, sh, stream)));
+  }
+  if (m.dW) {
+    LdCols a;
+    memset(&a, 0, sizeof(a));
+    a.p[0] = m.dh; a.wd = m.C_out; a.nseg = 1; a.drop = m.drop;
+    LdCols b;
+    memset(&b, 0, sizeof(b));
+    for (int q = 0; q < m.nseg; ++q) b.p[q] = m.segs[q];
+    b.wd = m.D; b.nseg = m.nseg; b.ones = 1;
+    EpWgrad e;
+    memset(&e, 0, sizeof(e));
+    e.dw[0] = m.dW; e.db[0] = m.dbias; e.wd = Ktot; e.nseg = 1; e.ldw = Ktot; e.nbias = 1;
+    GWN_CHECK_ARG(m.P < 2147483647LL, "mlp bwd: too many positions");
+    GemmShape sh{(i64)m.C_out, Ktot + 1, (int)m.P, pick_ksplit(m.C_out, Ktot + 1, m.P, TW32::BM, TW32::BN, kTargetBlocks), 1};
+    GWN_TRY((launch_gemm<TW32>(a, b, e, sh, stream)));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------- gcn (model.py:41-55)
+struct GcnShape {
+  int B, L, V, D, C_out, S, order;
+};
+inline int hop_index(const GcnShape& g, int s, int k) { return 1 + s * g.order + (k - 1); }  // cat order (model.py:42-52)
+
+// hops[q-1] (q >= 1) receives the q-th concatenated tensor; x is segment 0.
+inline int gcn_hops_forward(const GcnShape& g, const float* x, const SupportView* sup_fwd, float* hops,
+                            cudaStream_t stream) {
+  const i64 PD = (i64)g.B * g.L * g.V * g.D;
+  for (int k = 1; k <= g.order; ++k) {
+    const float* X[MAXSUP];
+    float* Y[MAXSUP];
+    for (int s = 0; s < g.S; ++s) {
+      X[s] = (k == 1) ? x : hops + (i64)(hop_index(g, s, k - 1) - 1) * PD;
+      Y[s] = hops + (i64)(hop_index(g, s, k) - 1) * PD;
+    }
+    GWN_TRY(node_gemm(sup_fwd, g.S, false, X, Y, nullptr, nullptr, g.B, g.L, 0, g.V, g.D, stream));
+  }
+  return 0;
+}
+
+// Backward through the diffusion chain.  dsegs: [1+S*order][P][D] gradient wrt each concatenated segment
+// (overwritten in place by the chained t tensors).  dx = dseg_0 + sum_s A_s t_{s,1} (+ window(add2)).
+// dsup[s] (nullable) += sum_k hop_{s,k-1}^T t_{s,k}.
+inline int gcn_hops_backward(const GcnShape& g, const float* x, const float* hops, const SupportView* sup_bwd, float* dsegs,
+                             float* dx, const float* add2, int T_out, float* const* dsup, const i64* ldds,
+                             cudaStream_t stream) {
+  const i64 PD = (i64)g.B * g.L * g.V * g.D;
+  for (int k = g.order; k >= 2; --k) {
+    const float* X[MAXSUP];
+    float* Y[MAXSUP];
+    const float* A[MAXSUP];
+    for (int s = 0; s < g.S; ++s) {
+      X[s] = dsegs + (i64)hop_index(g, s, k) * PD;
+      Y[s] = dsegs + (i64)hop_index(g, s, k - 1) * PD;
+      A[s] = Y[s];
+    }
+    GWN_TRY(node_gemm(sup_bwd, g.S, false, X, Y, A, nullptr, g.B, g.L, 0, g.V, g.D, stream));
+  }
+  for (int s = 0; s < g.S; ++s) {
+    if (!dsup || !dsup[s]) continue;
+    const float* Xp[MAXSUP];
+    const float* Yp[MAXSUP];
+    GWN_CHECK_ARG(g.order <= MAXSUP, "gcn bwd: order too large");
+    for (int k = 1; k <= g.order; ++k) {
+      Xp[k - 1] = (k == 1) ? x : hops + (i64)(hop_index(g, s, k - 1) - 1) * PD;
+      Yp[k - 1] = dsegs + (i64)hop_index(g, s, k) * PD;
+    }
+    GWN_TRY(support_grad_gemm(Xp, Yp, g.order, dsup[s], ldds[s], g.B, g.L, g.V, g.D, stream));
+  }
+  {
+    const float* X[MAXSUP];
+    for (int s = 0; s < g.S; ++s) X[s] = dsegs + (i64)hop_index(g, s, 1) * PD;
+    float* Y[1] = {dx};
+    const float* A[1] = {dsegs};
+    GWN_TRY(node_gemm(sup_bwd, g.S, true, X, Y, A, add2, g.B, g.L, T_out, g.V, g.D, stream));
+  }
+  return 0;
+}
+
+}  // namespace gwn

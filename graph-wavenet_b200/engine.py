@@ -1,0 +1,89 @@
+"""Mirror of the reference ``engine.trainer`` for the gwnet path (engine.py:9-58,119-130): same
+constructor arguments, attributes (``model optimizer scaler clip loss``) and ``train`` / ``eval``
+signatures and return values.  The forward/backward inside runs on the native CUDA plan."""
+import torch
+import torch.nn as nn
+import torch.optim as optim
+
+if __package__:
+    from . import metrics as util
+    from .model import gwnet
+else:  # top-level import next to ``model`` (the reference's style)
+    import importlib as _il
+    from model import gwnet  # noqa: F401
+    util = _il.import_module("graph_wavenet_b200.metrics")
+
+
+class trainer():
+    def __init__(self, scaler, in_dim, seq_length, num_nodes, nhid, dropout, lrate, wdecay, device, supports, gcn_bool,
+                 addaptadj, aptinit, blocks=4, layers=2):
+        if type(supports) == dict:
+            raise NotImplementedError("per-sample graphs (gwnet_diff_G, engine.py:14-25) are outside the accelerated "
+                                      "hot path (SURVEY.md §8(f) row 2)")
+        self.model = gwnet(device, num_nodes, dropout, supports=supports, gcn_bool=gcn_bool, addaptadj=addaptadj,
+                           aptinit=aptinit, in_dim=in_dim, out_dim=seq_length, residual_channels=nhid,
+                           dilation_channels=nhid, skip_channels=nhid * 8, end_channels=nhid * 16, blocks=blocks,
+                           layers=layers)
+        self.model.to(device)
+        self.optimizer = optim.Adam(self.model.parameters(), lr=lrate, weight_decay=wdecay)
+        self.loss = util.masked_mae
+        self.scaler = scaler
+        self.clip = 5
+        self.supports = supports
+        self.aptinit = aptinit
+        self.state = None
+        self.world = 1
+
+    # ---- data parallelism (no reference counterpart): one process per GPU, batch sharded,
+    # parameters replicated, ONE NCCL all-reduce per step over the flat gradient buffer the backward call fills.
+    def enable_data_parallel(self):
+        import torch.distributed as dist
+        self.world = dist.get_world_size()
+        with torch.no_grad():
+            for t in self.model.state_dict().values():
+                dist.broadcast(t, src=0)
+
+    def _allreduce_grads(self):
+        import torch.distributed as dist
+        flat = getattr(self.model, "_last_grad_flat", None)
+        grads = [p.grad for p in self.model.parameters() if p.grad is not None]
+        lo, hi = (flat.data_ptr(), flat.data_ptr() + flat.numel() * 4) if flat is not None else (0, 0)
+        if flat is not None and all(lo <= g.data_ptr() < hi for g in grads):
+            dist.all_reduce(flat)                 # every p.grad is a view of this buffer
+            flat.mul_(1.0 / self.world)
+        else:
+            for g in grads:
+                dist.all_reduce(g)
+                g.mul_(1.0 / self.world)
+
+    def train(self, input, real_val):
+        self.model.train()
+        self.optimizer.zero_grad()
+        input = nn.functional.pad(input, (1, 0, 0, 0))
+        output = self.model(input)
+        output = output.transpose(1, 3)
+        real = torch.unsqueeze(real_val, dim=1)
+        predict = self.scaler.inverse_transform(output)
+        loss = self.loss(predict, real, 0.0)
+        loss.backward()
+        if self.world > 1:
+            self._allreduce_grads()
+        if self.clip is not None:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip)
+        self.optimizer.step()
+        mape = util.masked_mape(predict, real, 0.0).item()
+        rmse = util.masked_rmse(predict, real, 0.0).item()
+        return loss.item(), mape, rmse
+
+    def eval(self, input, real_val):
+        self.model.eval()
+        input = nn.functional.pad(input, (1, 0, 0, 0))
+        with torch.no_grad():   # the reference builds and discards a graph here; results are identical
+            output = self.model(input)
+        output = output.transpose(1, 3)
+        real = torch.unsqueeze(real_val, dim=1)
+        predict = self.scaler.inverse_transform(output)
+        loss = self.loss(predict, real, 0.0)
+        mape = util.masked_mape(predict, real, 0.0).item()
+        rmse = util.masked_rmse(predict, real, 0.0).item()
+        return loss.item(), mape, rmse

@@ -1,0 +1,464 @@
+"""Drop-in replacement for the reference ``model.py`` (sklin93/Graph-WaveNet).
+
+Same public surface -- ``nconv``, ``linear``, ``gcn``, ``gwnet`` with the reference constructor
+arguments, attribute names and ``state_dict`` keys (model.py:8-55,82-241), plus the names ``torch``,
+``nn`` and ``F`` that ``engine.py`` / ``test.py`` pick up through ``from model import *`` -- but every
+forward/backward runs hand-written sm_100a CUDA kernels behind the C ABI of
+``include/gwnet_b200.h``.  There is no PyTorch-op or CPU fallback: tensors must live on a CUDA
+device and the extension must be built, otherwise the call raises.
+
+Use it exactly like the reference: put this directory on ``sys.path`` ahead of the reference's and
+``import model``; or ``graph_wavenet_b200.model`` via ``__graft_entry__.load_package()``.
+"""
+import os
+import sys
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F  # noqa: F401  (re-exported: engine.py:44, test.py:36 use it via the star import)
+
+if __package__:
+    from . import native as _N
+    from .runtime import PlanRunner as _PlanRunner, make_config as _make_config
+else:  # imported as top-level ``model`` (the reference's own import style): bootstrap the package
+    import importlib.util as _ilu
+    _dir = os.path.dirname(os.path.abspath(__file__))
+    _name = "graph_wavenet_b200"
+    if _name not in sys.modules:
+        _spec = _ilu.spec_from_file_location(_name, os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+        _mod = _ilu.module_from_spec(_spec)
+        sys.modules[_name] = _mod
+        _spec.loader.exec_module(_mod)
+    import importlib as _il
+    _N = _il.import_module(_name + ".native")
+    _rt = _il.import_module(_name + ".runtime")
+    _PlanRunner, _make_config = _rt.PlanRunner, _rt.make_config
+
+_PRECISIONS = {"fp32": _N.PREC_FP32, "tf32": _N.PREC_TF32, "bf16": _N.PREC_BF16}
+
+
+def _default_precision() -> int:
+    return _PRECISIONS[os.environ.get("GWNET_B200_PRECISION", "fp32").lower()]
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"gwnet_b200: {what} must be a CUDA tensor (got device {t.device}); "
+                           "this implementation is sm_100a-only and has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"gwnet_b200: {what} must be float32, got {t.dtype}")
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _i64x4(v):
+    import ctypes
+    return (ctypes.c_int64 * 4)(*[int(a) for a in v])
+
+
+def _to_blnc(x: torch.Tensor) -> torch.Tensor:
+    """Logical NCHW [B,C,N,L] tensor -> contiguous physical [B,L,N,C] buffer (no copy if it already is)."""
+    v = x.permute(0, 3, 2, 1)
+    if v.is_contiguous():
+        return v
+    lib = _N.get_lib()
+    B, C, Nn, L = x.shape
+    out = torch.empty((B, L, Nn, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        lib.check(lib.dll.gwn_permute4d(x.data_ptr(), _i64x4(x.stride()), out.data_ptr(),
+                                        _i64x4((L * Nn * C, 1, C, Nn * C)), _i64x4(x.shape), _stream(x)), "gwn_permute4d")
+    return out
+
+
+def _blnc_to_nchw(y: torch.Tensor) -> torch.Tensor:
+    """Physical [B,L,N,C] buffer -> contiguous logical NCHW [B,C,N,L] tensor."""
+    B, L, Nn, C = y.shape
+    lib = _N.get_lib()
+    out = torch.empty((B, C, Nn, L), dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        lib.check(lib.dll.gwn_permute4d(y.data_ptr(), _i64x4((L * Nn * C, 1, C, Nn * C)), out.data_ptr(),
+                                        _i64x4(out.stride()), _i64x4(out.shape), _stream(y)), "gwn_permute4d")
+    return out
+
+
+# ============================================================================== nconv
+class _NconvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, A, precision):
+        _require_cuda(x, "nconv input")
+        _require_cuda(A, "nconv support")
+        lib = _N.get_lib()
+        B, C, V, L = x.shape
+        if A.dim() != 2 or A.shape[0] != V or A.shape[1] != V:
+            raise RuntimeError(f"nconv: support must be [{V},{V}], got {tuple(A.shape)}")
+        if C % 4:
+            raise RuntimeError("nconv: channel count must be a multiple of 4")
+        xb = _to_blnc(x)
+        Ac = A.contiguous()
+        yb = torch.empty_like(xb)
+        with torch.cuda.device(x.device):
+            lib.check(lib.dll.gwn_nconv_fwd(xb.data_ptr(), Ac.data_ptr(), V, yb.data_ptr(), B, L, V, C, precision,
+                                            _stream(x)), "gwn_nconv_fwd")
+        ctx.save_for_backward(xb, Ac)
+        ctx.precision = precision
+        return _blnc_to_nchw(yb)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xb, Ac = ctx.saved_tensors
+        lib = _N.get_lib()
+        B, L, V, C = xb.shape
+        gyb = _to_blnc(gy)
+        need_x, need_A = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dxb = torch.empty_like(xb) if need_x else None
+        dA = torch.zeros_like(Ac) if need_A else None
+        with torch.cuda.device(gy.device):
+            lib.check(lib.dll.gwn_nconv_bwd(gyb.data_ptr(), xb.data_ptr(), Ac.data_ptr(), V,
+                                            dxb.data_ptr() if need_x else None, dA.data_ptr() if need_A else None, V,
+                                            B, L, V, C, ctx.precision, _stream(gy)), "gwn_nconv_bwd")
+        return (_blnc_to_nchw(dxb) if need_x else None), dA, None
+
+
+class nconv(nn.Module):
+    """model.py:8-14 -- ``einsum('ncvl,vw->ncwl')`` + ``.contiguous()``."""
+
+    def __init__(self):
+        super(nconv, self).__init__()
+        self.precision = _default_precision()
+
+    def forward(self, x, A):
+        return _NconvFn.apply(x, A, self.precision)
+
+
+# ============================================================================== linear
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _require_cuda(x, "linear input")
+        lib = _N.get_lib()
+        B, Cin, V, L = x.shape
+        Cout = weight.shape[0]
+        if Cin % 4 or Cout % 4:
+            raise RuntimeError("linear: channel counts must be multiples of 4")
+        xb = _to_blnc(x)
+        w = weight.contiguous()
+        yb = torch.empty((B, L, V, Cout), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            lib.check(lib.dll.gwn_linear_fwd(xb.data_ptr(), w.data_ptr(), bias.data_ptr(), yb.data_ptr(), B * L * V, Cin, Cout,
+                                             _stream(x)), "gwn_linear_fwd")
+        ctx.save_for_backward(xb, w)
+        return _blnc_to_nchw(yb)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xb, w = ctx.saved_tensors
+        lib = _N.get_lib()
+        B, L, V, Cin = xb.shape
+        Cout = w.shape[0]
+        gyb = _to_blnc(gy)
+        dxb = torch.empty_like(xb)
+        dW = torch.empty_like(w)
+        db = torch.empty(Cout, dtype=torch.float32, device=gy.device)
+        with torch.cuda.device(gy.device):
+            lib.check(lib.dll.gwn_linear_bwd(gyb.data_ptr(), xb.data_ptr(), w.data_ptr(), dxb.data_ptr(), dW.data_ptr(),
+                                             db.data_ptr(), B * L * V, Cin, Cout, _stream(gy)), "gwn_linear_bwd")
+        return _blnc_to_nchw(dxb), dW, db
+
+
+class linear(nn.Module):
+    """model.py:24-30 -- 1x1 ``Conv2d`` with bias, held as ``.mlp`` (state_dict keys ``mlp.weight/bias``)."""
+
+    def __init__(self, c_in, c_out):
+        super(linear, self).__init__()
+        self.mlp = torch.nn.Conv2d(c_in, c_out, kernel_size=(1, 1), padding=(0, 0), stride=(1, 1), bias=True)
+
+    def forward(self, x):
+        return _LinearFn.apply(x, self.mlp.weight, self.mlp.bias)
+
+
+# ============================================================================== gcn
+class _GcnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, order, p, training, precision, keep_mask, seed, *supports):
+        import ctypes
+        _require_cuda(x, "gcn input")
+        lib = _N.get_lib()
+        B, Cin, V, L = x.shape
+        S = len(supports)
+        Cout = weight.shape[0]
+        if weight.shape[1] != (order * S + 1) * Cin:
+            raise RuntimeError(f"gcn: mlp expects {(order * S + 1) * Cin} input channels, weight has {weight.shape[1]}")
+        xb = _to_blnc(x)
+        sup = [s.contiguous() for s in supports]
+        w = weight.contiguous()
+        hops = torch.empty((order * S, B, L, V, Cin), dtype=torch.float32, device=x.device)
+        yb = torch.empty((B, L, V, Cout), dtype=torch.float32, device=x.device)
+        mode = _N.DROPOUT_NONE
+        if training and p > 0:
+            mode = _N.DROPOUT_MASK if keep_mask is not None else _N.DROPOUT_PHILOX
+        d = _N.GwnGcnDesc(B, L, V, Cin, Cout, S, order, precision, mode, float(p), int(seed), 0)
+        sp = _N.ptr_array([s.data_ptr() for s in sup])
+        lds = (ctypes.c_int64 * max(S, 1))(*[V] * S)
+        with torch.cuda.device(x.device):
+            lib.check(lib.dll.gwn_gcn_fwd(ctypes.byref(d), xb.data_ptr(), sp, lds, w.data_ptr(), bias.data_ptr(),
+                                          keep_mask.data_ptr() if keep_mask is not None else None, hops.data_ptr(),
+                                          yb.data_ptr(), _stream(x)), "gwn_gcn_fwd")
+        ctx.save_for_backward(xb, w, hops, *sup)
+        ctx.desc, ctx.keep_mask = d, keep_mask
+        return _blnc_to_nchw(yb)
+
+    @staticmethod
+    def backward(ctx, gy):
+        import ctypes
+        xb, w, hops, *sup = ctx.saved_tensors
+        lib = _N.get_lib()
+        d = ctx.desc
+        S = d.n_supports
+        gyb = _to_blnc(gy)
+        dxb = torch.empty_like(xb)
+        dW = torch.empty_like(w)
+        db = torch.empty(d.c_out, dtype=torch.float32, device=gy.device)
+        need = ctx.needs_input_grad[9:]
+        dsup = [torch.zeros_like(s) if n else None for s, n in zip(sup, need)]
+        scratch = torch.empty(lib.dll.gwn_gcn_bwd_scratch_floats(ctypes.byref(d)), dtype=torch.float32, device=gy.device)
+        sp = _N.ptr_array([s.data_ptr() for s in sup])
+        dsp = _N.ptr_array([t.data_ptr() if t is not None else None for t in dsup])
+        lds = (ctypes.c_int64 * max(S, 1))(*[d.V] * S)
+        km = ctx.keep_mask
+        with torch.cuda.device(gy.device):
+            lib.check(lib.dll.gwn_gcn_bwd(ctypes.byref(d), gyb.data_ptr(), xb.data_ptr(), sp, lds, w.data_ptr(),
+                                          km.data_ptr() if km is not None else None, hops.data_ptr(), dxb.data_ptr(),
+                                          dW.data_ptr(), db.data_ptr(), dsp, lds, scratch.data_ptr(), _stream(gy)),
+                      "gwn_gcn_bwd")
+        return (_blnc_to_nchw(dxb), dW, db, None, None, None, None, None, None, *dsup)
+
+
+class gcn(nn.Module):
+    """model.py:32-55 -- K-hop diffusion over every support, channel concat, 1x1 mlp, dropout."""
+
+    def __init__(self, c_in, c_out, dropout, support_len=3, order=2):
+        super(gcn, self).__init__()
+        self.nconv = nconv()
+        c_in = (order * support_len + 1) * c_in
+        self.mlp = linear(c_in, c_out)
+        self.dropout = dropout
+        self.order = order
+        self.precision = _default_precision()
+        self._keep_mask = None     # test hook: uint8 BLNC keep-mask replacing the Philox draw
+
+    def forward(self, x, support):
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (self.training and self.dropout > 0) else 0
+        return _GcnFn.apply(x, self.mlp.mlp.weight, self.mlp.mlp.bias, self.order, self.dropout, self.training,
+                            self.precision, self._keep_mask, seed, *support)
+
+
+# ============================================================================== per-sample-graph variants
+class _NotOnHotPath(nn.Module):
+    _what = ""
+
+    def __init__(self, *a, **k):
+        super().__init__()
+        raise NotImplementedError(
+            f"{self._what} (per-sample adjacency, model.py:16-22,57-80,244-407) is outside the gwnet hot path this "
+            "package accelerates (SURVEY.md §8(f) row 2); use the reference implementation for it")
+
+
+class nconv2(_NotOnHotPath):
+    _what = "nconv2"
+
+
+class gcn2(_NotOnHotPath):
+    _what = "gcn2"
+
+
+class gwnet_diff_G(_NotOnHotPath):
+    _what = "gwnet_diff_G"
+
+
+# ============================================================================== gwnet
+class _GwnetFn(torch.autograd.Function):
+    """One autograd node for the whole network: forward and backward are each a single C-ABI call."""
+
+    @staticmethod
+    def forward(ctx, module, inp, *params):
+        out, fctx = module._run_forward(inp, save=True)
+        ctx.module, ctx.fctx = module, fctx
+        ctx.n_params = len(params)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        module = ctx.module
+        grads, gin = module._run_backward(ctx.fctx, grad_out, ctx.needs_input_grad[1])
+        return (None, gin, *grads)
+
+
+class gwnet(nn.Module):
+    """model.py:82-241.  Constructor arguments, submodule layout, parameter initialisation order
+    (hence the values drawn for a given seed) and ``state_dict`` keys follow the reference."""
+
+    def __init__(self, device, num_nodes, dropout=0.3, supports=None, gcn_bool=True, addaptadj=True, aptinit=None,
+                 in_dim=2, out_dim=12, residual_channels=32, dilation_channels=32, skip_channels=256, end_channels=512,
+                 kernel_size=2, blocks=4, layers=2):
+        super(gwnet, self).__init__()
+        self.dropout = dropout
+        self.blocks = blocks
+        self.layers = layers
+        self.gcn_bool = gcn_bool
+        self.addaptadj = addaptadj
+
+        self.filter_convs = nn.ModuleList()
+        self.gate_convs = nn.ModuleList()
+        self.residual_convs = nn.ModuleList()
+        self.skip_convs = nn.ModuleList()
+        self.bn = nn.ModuleList()
+        self.gconv = nn.ModuleList()
+
+        self.start_conv = nn.Conv2d(in_channels=in_dim, out_channels=residual_channels, kernel_size=(1, 1))
+        self.supports = supports
+        receptive_field = 1
+        self.supports_len = 0
+        if supports is not None:
+            self.supports_len += len(supports)
+
+        if gcn_bool and addaptadj:
+            if supports is None:
+                self.supports = []
+            if aptinit is None:
+                self.nodevec1 = nn.Parameter(torch.randn(num_nodes, 10).to(device), requires_grad=True)
+                self.nodevec2 = nn.Parameter(torch.randn(10, num_nodes).to(device), requires_grad=True)
+            else:
+                m, p, n = torch.svd(aptinit)
+                initemb1 = torch.mm(m[:, :10], torch.diag(p[:10] ** 0.5))
+                initemb2 = torch.mm(torch.diag(p[:10] ** 0.5), n[:, :10].t())
+                self.nodevec1 = nn.Parameter(initemb1.to(device), requires_grad=True)
+                self.nodevec2 = nn.Parameter(initemb2.to(device), requires_grad=True)
+            self.supports_len += 1
+
+        for b in range(blocks):
+            additional_scope = kernel_size - 1
+            new_dilation = 1
+            for i in range(layers):
+                # the reference declares gate/residual/skip as Conv1d with 2-D kernels (model.py:139-151);
+                # Conv2d draws bit-identical parameters with identical shapes and keys
+                self.filter_convs.append(nn.Conv2d(residual_channels, dilation_channels, kernel_size=(1, kernel_size),
+                                                   dilation=new_dilation))
+                self.gate_convs.append(nn.Conv2d(residual_channels, dilation_channels, kernel_size=(1, kernel_size),
+                                                 dilation=new_dilation))
+                self.residual_convs.append(nn.Conv2d(dilation_channels, residual_channels, kernel_size=(1, 1)))
+                self.skip_convs.append(nn.Conv2d(dilation_channels, skip_channels, kernel_size=(1, 1)))
+                self.bn.append(nn.BatchNorm2d(residual_channels))
+                new_dilation *= 2
+                receptive_field += additional_scope
+                additional_scope *= 2
+                if self.gcn_bool:
+                    self.gconv.append(gcn(dilation_channels, residual_channels, dropout, support_len=self.supports_len))
+
+        self.end_conv_1 = nn.Conv2d(skip_channels, end_channels, kernel_size=(1, 1), bias=True)
+        self.end_conv_2 = nn.Conv2d(end_channels, out_dim, kernel_size=(1, 1), bias=True)
+        self.receptive_field = receptive_field
+
+        # ---- native-plan bookkeeping (not part of the reference surface)
+        self._geom = dict(num_nodes=num_nodes, in_dim=in_dim, out_dim=out_dim, residual_channels=residual_channels,
+                          dilation_channels=dilation_channels, skip_channels=skip_channels, end_channels=end_channels,
+                          kernel_size=kernel_size, blocks=blocks, layers=layers)
+        self.precision = _default_precision()
+        self._runners = {}
+        self._entries = None
+        self._dropout_masks = None   # test hook: list of uint8 BLNC keep-masks, one per layer
+        self._static_workspace = None
+
+    # ---- plan plumbing
+    def _apply(self, fn, *a, **k):
+        self._entries = None
+        return super()._apply(fn, *a, **k)
+
+    def _n_static(self):
+        return len(self.supports) if self.supports is not None else 0
+
+    def _adaptive(self):
+        return bool(self.gcn_bool and self.addaptadj)
+
+    def _gcn_active(self):
+        return bool(self.gcn_bool and self.supports is not None)   # model.py:225
+
+    def _runner(self, batch, seq_len):
+        key = (batch, seq_len, self.precision, self._n_static(), float(self.dropout))
+        r = self._runners.get(key)
+        if r is None:
+            g = self._geom
+            cfg = _make_config(batch=batch, seq_len=seq_len, n_static_supports=self._n_static(), gcn_bool=self.gcn_bool,
+                               adaptive=self._adaptive(), gcn=self._gcn_active(), order=2, apt_rank=10,
+                               precision=self.precision, dropout=self.dropout, bn_eps=self.bn[0].eps,
+                               bn_momentum=self.bn[0].momentum, **g)
+            r = _PlanRunner(_N.get_lib(), cfg)
+            names = list(self.state_dict(keep_vars=True).keys())
+            if names != r.plan.names:
+                raise RuntimeError("gwnet_b200: state_dict layout does not match the native plan")
+            self._runners[key] = r
+        return r
+
+    def _table(self):
+        if self._entries is None:
+            self._entries = list(self.state_dict(keep_vars=True).values())
+        return self._entries
+
+    def _live(self, name):
+        """False for parameters the reference leaves without gradient."""
+        last = self.blocks * self.layers - 1
+        if name.startswith("residual_convs."):
+            return (not self._gcn_active()) and not name.startswith(f"residual_convs.{last}.")
+        if name.startswith("gconv."):
+            return self._gcn_active() and not name.startswith(f"gconv.{last}.")
+        if name.startswith(f"bn.{last}."):
+            return False
+        return True
+
+    def _run_forward(self, inp, save):
+        _require_cuda(inp, "gwnet input")
+        if inp.dim() != 4:
+            raise RuntimeError(f"gwnet: expected [B,in_dim,N,T] input, got {tuple(inp.shape)}")
+        r = self._runner(inp.shape[0], inp.shape[3])
+        table = [t.detach() for t in self._table()]
+        for t in table:
+            if not t.is_cuda:
+                raise RuntimeError("gwnet_b200: module parameters must be on a CUDA device (call .to(device))")
+        for s in (self.supports or []):
+            _require_cuda(s, "gwnet support")
+        training = self.training
+        mode, masks, seed = _N.DROPOUT_NONE, None, 0
+        if training and self.dropout > 0 and self._gcn_active():
+            if self._dropout_masks is not None:
+                mode, masks = _N.DROPOUT_MASK, self._dropout_masks
+            else:
+                mode, seed = _N.DROPOUT_PHILOX, int(torch.randint(0, 2 ** 62, (1,)).item())
+        with torch.cuda.device(inp.device):
+            out, fctx = r.forward(table, self.supports, inp.detach(), training, mode, masks, seed)
+        fctx.runner = r
+        return out, (fctx if save else None)
+
+    def _run_backward(self, fctx, grad_out, need_input_grad):
+        r = fctx.runner
+        table = [t.detach() for t in self._table()]
+        with torch.cuda.device(grad_out.device):
+            gflat, gin = r.backward(fctx, table, grad_out, need_input_grad)
+        grads = []
+        for (name, p), off, ne in zip(self.named_parameters(), self._param_offsets(r), self._param_numels(r)):
+            grads.append(gflat[off:off + ne].view(p.shape) if (p.requires_grad and self._live(name)) else None)
+        self._last_grad_flat = gflat
+        return grads, gin
+
+    def _param_offsets(self, r):
+        return [o for o in r.plan.grad_offsets if o >= 0]
+
+    def _param_numels(self, r):
+        return [n for n, o in zip(r.plan.numels, r.plan.grad_offsets) if o >= 0]
+
+    def forward(self, input):
+        params = [p for _, p in self.named_parameters()]
+        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in params)):
+            return _GwnetFn.apply(self, input, *params)
+        out, _ = self._run_forward(input, save=False)
+        return out

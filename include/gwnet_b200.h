@@ -1,0 +1,190 @@
+/*
+ * gwnet_b200 -- C ABI of the B200-native Graph WaveNet forward/backward hot path.
+ *
+ * This is the drop-in boundary: the reference (sklin93/Graph-WaveNet) is pure
+ * Python/PyTorch and has no FFI of its own, so each entry point below names the
+ * reference call site it replaces (file:line in /root/reference).  A reference
+ * maintainer binds these with ctypes; the host-side mirror
+ * of model.py in graph-wavenet_b200/ does exactly that.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, ints, floats; no torch / C++ types.
+ *   - every function returns 0 on success, else a gwn_status / cudaError code;
+ *     gwn_last_error() returns a thread-local message.  Nothing throws or exits.
+ *   - the caller owns every buffer (parameters, activations, workspace); the
+ *     library allocates no device memory.
+ *   - all work is enqueued on the cudaStream_t passed as `stream` (void*), on the
+ *     caller's current device; no implicit synchronisation; re-entrant (forward
+ *     is called from the main thread, backward from PyTorch's autograd thread).
+ *   - activation tensors are fp32 in the "BLNC" physical layout
+ *         x[b][l][n][c]   (batch, time, node, channel; channel innermost)
+ *     which is the reference's logical NCHW tensor [B,C,N,L] viewed with strides
+ *     (L*N*C, 1, C, N*C).  gwn_permute4d converts from/to any 4-D strided tensor.
+ *   - there is NO CPU fallback: every entry point fails if no CUDA device backs
+ *     the pointers.
+ */
+#ifndef GWNET_B200_H
+#define GWNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GWN_ABI_VERSION 1
+
+typedef enum gwn_status {
+  GWN_OK = 0,
+  GWN_ERR_INVALID = 10001,     /* bad argument / unsupported shape */
+  GWN_ERR_CUDA = 10002,        /* a CUDA runtime call failed (message has the detail) */
+  GWN_ERR_UNSUPPORTED = 10003, /* valid but not implemented by this build */
+  GWN_ERR_NO_DEVICE = 10004    /* no CUDA device: there is no CPU fallback */
+} gwn_status;
+
+/* Precision of the contractions (storage is always fp32). */
+typedef enum gwn_precision {
+  GWN_PREC_FP32 = 0,  /* fp32 FMA everywhere: the 1e-4 parity tier                 */
+  GWN_PREC_TF32 = 1,  /* node contraction on tcgen05 kind::tf32 (fp32 accumulate)   */
+  GWN_PREC_BF16 = 2   /* node contraction on tcgen05 kind::f16/bf16 (2e-2 tier)     */
+} gwn_precision;
+
+/* Dropout source for gcn (model.py:54). */
+typedef enum gwn_dropout_mode {
+  GWN_DROPOUT_NONE = 0,   /* eval mode or p == 0                                    */
+  GWN_DROPOUT_MASK = 1,   /* caller supplies uint8 keep-masks (parity tests, G7)     */
+  GWN_DROPOUT_PHILOX = 2  /* in-kernel Philox4x32-10 keyed by (seed, layer, element) */
+} gwn_dropout_mode;
+
+const char* gwn_last_error(void);
+int gwn_abi_version(void);
+/* Kernels launched by this library so far in this process (optionally reset). */
+long long gwn_launch_count(int reset);
+/* Number of CUDA devices visible; fills name (<=255 chars) and SM count of the current one. */
+int gwn_device_info(int* n_devices, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ layout helpers */
+/* dst[i0,i1,i2,i3] = src[i0,i1,i2,i3] for two arbitrarily strided fp32 4-D tensors
+ * (element strides).  Used at true layout boundaries only (NCHW <-> BLNC).        */
+int gwn_permute4d(const float* src, const int64_t src_strides[4], float* dst, const int64_t dst_strides[4],
+                  const int64_t sizes[4], void* stream);
+
+/* ------------------------------------------------------------------ nconv (model.py:8-14)
+ * y[b,l,w,c] = sum_v x[b,l,v,c] * A[v,w].   x,y: BLNC [B,L,V,C]; A: [V,V] row-major, ld = lda.
+ * Replaces torch.einsum('ncvl,vw->ncwl') + .contiguous().                          */
+int gwn_nconv_fwd(const float* x, const float* A, int64_t lda, float* y, int B, int L, int V, int C,
+                  int precision, void* stream);
+/* Autograd of nconv: dx = dy . A^T ; dA += x^T dy summed over (b,l,c) when dA != NULL
+ * (dA is accumulated into -- zero it first).                                        */
+int gwn_nconv_bwd(const float* dy, const float* x, const float* A, int64_t lda, float* dx, float* dA, int64_t ldda,
+                  int B, int L, int V, int C, int precision, void* stream);
+
+/* ------------------------------------------------------------------ linear (model.py:24-30)
+ * 1x1 Conv2d with bias: y[p,co] = sum_ci W[co,ci] x[p,ci] + b[co], p over B*L*N positions. */
+int gwn_linear_fwd(const float* x, const float* W, const float* bias, float* y, int64_t positions, int c_in, int c_out,
+                   void* stream);
+int gwn_linear_bwd(const float* dy, const float* x, const float* W, float* dx, float* dW, float* dbias,
+                   int64_t positions, int c_in, int c_out, void* stream);
+
+/* ------------------------------------------------------------------ gcn (model.py:32-55)
+ * h = dropout(mlp(cat([x, A1 x, A1^2 x, ..., As^order x], channel))).
+ * hops: caller buffer for the order*S diffused tensors, [order*S][B*L*V*C] (saved for backward).
+ * keep_mask: uint8 [B*L*V*c_out] when dropout_mode == GWN_DROPOUT_MASK.             */
+typedef struct gwn_gcn_desc {
+  int B, L, V, C;          /* input BLNC dims; C = c_in per hop                      */
+  int c_out;
+  int n_supports;          /* S                                                      */
+  int order;               /* K hops per support                                     */
+  int precision;           /* gwn_precision                                          */
+  int dropout_mode;        /* gwn_dropout_mode                                       */
+  float dropout_p;
+  uint64_t seed;           /* Philox key                                             */
+  uint64_t offset;         /* Philox stream offset (layer id)                        */
+} gwn_gcn_desc;
+
+int gwn_gcn_fwd(const gwn_gcn_desc* d, const float* x, const float* const* supports, const int64_t* lds,
+                const float* W, const float* bias, const uint8_t* keep_mask, float* hops, float* y, void* stream);
+/* dsupports[s] may be NULL (no gradient wanted for that support); non-NULL ones are accumulated into.
+ * scratch: caller buffer of gwn_gcn_bwd_scratch_floats(d) floats.                    */
+size_t gwn_gcn_bwd_scratch_floats(const gwn_gcn_desc* d);
+int gwn_gcn_bwd(const gwn_gcn_desc* d, const float* dy, const float* x, const float* const* supports, const int64_t* lds,
+                const float* W, const uint8_t* keep_mask, const float* hops, float* dx, float* dW, float* dbias,
+                float* const* dsupports, const int64_t* ldds, float* scratch, void* stream);
+
+/* ------------------------------------------------------------------ gwnet (model.py:82-241)
+ * Whole-network plan: replaces gwnet.forward and its autograd graph.                 */
+typedef struct gwn_config {
+  int batch;
+  int num_nodes;
+  int seq_len;             /* T of the tensor handed to gwnet.forward                 */
+  int in_dim, out_dim;
+  int residual_channels, dilation_channels, skip_channels, end_channels;
+  int kernel_size;         /* only 2 (the reference default) is supported             */
+  int blocks, layers;
+  int n_static_supports;   /* len(self.supports) without the adaptive one             */
+  int gcn_bool;            /* constructor flag: gconv modules exist (model.py:156)    */
+  int adaptive;            /* gcn_bool and addaptadj (model.py:114)                   */
+  int gcn;                 /* gcn_bool and self.supports is not None (model.py:225)   */
+  int order;               /* 2 (model.py:33)                                         */
+  int apt_rank;            /* 10 (model.py:117-118)                                   */
+  int precision;           /* gwn_precision                                           */
+  float dropout;
+  float bn_eps, bn_momentum;
+} gwn_config;
+
+typedef struct gwn_plan gwn_plan;
+
+int gwn_plan_create(const gwn_config* cfg, gwn_plan** out);
+void gwn_plan_destroy(gwn_plan* p);
+/* Bytes of caller-owned workspace: `fwd` holds everything forward saves for backward,
+ * `bwd` is backward scratch.                                                         */
+int gwn_plan_workspace_bytes(const gwn_plan* p, size_t* fwd, size_t* bwd);
+/* Number of entries of the parameter table (reference state_dict order, App. F of SURVEY.md:
+ * parameters and BN buffers) and of floats in the flat gradient buffer.              */
+int gwn_plan_param_count(const gwn_plan* p, int* n_entries, int64_t* grad_floats);
+/* Name, element offset into the flat gradient buffer (-1 for buffers) and element count of entry i. */
+int gwn_plan_param_info(const gwn_plan* p, int i, char* name, int name_len, int64_t* grad_offset, int64_t* numel);
+int gwn_plan_out_len(const gwn_plan* p, int* t_out, int* receptive_field);
+
+typedef struct gwn_forward_args {
+  const void* const* params;     /* n_entries device pointers, state_dict order            */
+  const float* const* supports;  /* n_static_supports device pointers [N,N]                */
+  const int64_t* support_strides;/* 2 per support: (row stride, col stride) in elements    */
+  const float* input;            /* [B,in_dim,N,T] fp32, any strides                        */
+  int64_t input_strides[4];
+  float* output;                 /* [B,out_dim,N,T_out] fp32 contiguous NCHW                */
+  void* workspace;               /* fwd bytes                                               */
+  int training;                  /* BN batch stats + running-stat update + dropout          */
+  int dropout_mode;              /* gwn_dropout_mode (ignored when !training)               */
+  const uint8_t* const* keep_masks; /* n_layers pointers [B*L_i*N*C] (GWN_DROPOUT_MASK)     */
+  uint64_t seed;                 /* Philox key (GWN_DROPOUT_PHILOX)                         */
+  void* stream;
+} gwn_forward_args;
+
+int gwn_plan_forward(gwn_plan* p, const gwn_forward_args* a);
+
+typedef struct gwn_backward_args {
+  const void* const* params;
+  const float* const* supports;
+  const int64_t* support_strides;
+  const float* input;
+  int64_t input_strides[4];
+  const float* grad_output;      /* [B,out_dim,N,T_out] fp32 contiguous NCHW                */
+  const void* workspace;         /* the forward workspace of the matching forward call      */
+  void* scratch;                 /* bwd bytes                                               */
+  float* grad_flat;              /* grad_floats floats; zeroed by this call                  */
+  float* grad_input;             /* [B,in_dim,N,T] contiguous NCHW or NULL                   */
+  int training;                  /* the `training` flag of the matching forward call         */
+  int dropout_mode;
+  const uint8_t* const* keep_masks;
+  uint64_t seed;
+  void* stream;
+} gwn_backward_args;
+
+int gwn_plan_backward(gwn_plan* p, const gwn_backward_args* a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GWNET_B200_H */

@@ -1,0 +1,245 @@
+"""GPU: the CUDA path (through the drop-in ``model`` module and the C ABI) against the oracle and
+the committed reference golden vectors.  Tolerances: fp32 tier = 1e-4 relative (north star), stated
+as norm-relative per tensor with a global-norm floor for mathematically-zero gradients."""
+import pytest
+import torch
+
+import __graft_entry__ as ge
+from oracle import gwnet_oracle as O
+from helpers import CASES, load_case, sub, assert_close_rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def M():
+    ge.build()
+    ge.load_package()
+    from graph_wavenet_b200 import model
+    return model
+
+
+def build_model(M, cfg, supports, dev, aptinit=None):
+    sup = [s.to(dev) for s in supports] if (supports is not None and cfg.has_supports) else None
+    return M.gwnet(dev, cfg.num_nodes, cfg.dropout, supports=sup, gcn_bool=cfg.gcn_bool, addaptadj=cfg.addaptadj,
+                   aptinit=aptinit, in_dim=cfg.in_dim, out_dim=cfg.out_dim, residual_channels=cfg.residual_channels,
+                   dilation_channels=cfg.dilation_channels, skip_channels=cfg.skip_channels,
+                   end_channels=cfg.end_channels, kernel_size=cfg.kernel_size, blocks=cfg.blocks, layers=cfg.layers).to(dev)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_gwnet_matches_reference_golden(M, name):
+    dev = torch.device("cuda:0")
+    rec = load_case(name)
+    cfg = rec["cfg"]
+    m = build_model(M, cfg, rec["supports"], dev, rec.get("aptinit"))
+    m.load_state_dict(rec["state0"])
+    x = torch.nn.functional.pad(rec["x"], (1, 0, 0, 0)).to(dev)
+    m.eval()
+    with torch.no_grad():
+        assert_close_rel(m(x), rec["out_eval"], TOL, "eval output")
+    m.train()
+    xg = x.clone().requires_grad_(True)
+    out = m(xg)
+    assert_close_rel(out, rec["out_train"], TOL, "train output")
+    (out * rec["probe"].to(dev)).sum().backward()
+    assert_close_rel(xg.grad, rec["grad_input"], TOL, "grad input")
+    ref = sub(rec, "grad/")
+    gnorm = sum(float(g.double().pow(2).sum()) for g in ref.values()) ** 0.5
+    for k, p in m.named_parameters():
+        if k not in ref:
+            assert p.grad is None, f"{k} must have no gradient (SURVEY G4)"
+            continue
+        assert_close_rel(p.grad, ref[k], TOL, "grad " + k, floor=2e-6 * gnorm)
+    for k, v in m.state_dict().items():
+        if O.is_buffer(k):
+            assert_close_rel(v.float(), rec["buf1/" + k].float(), TOL, "buffer " + k)
+
+
+@pytest.mark.parametrize("name", ["dbl_adp", "aptonly"])
+def test_trainer_steps_match_reference(M, name):
+    from graph_wavenet_b200 import engine as E
+    from graph_wavenet_b200.metrics import StandardScaler
+    dev = torch.device("cuda:0")
+    rec = load_case(name)
+    cfg = rec["cfg"]
+    sup = [s.to(dev) for s in rec["supports"]] if cfg.has_supports else None
+    tr = E.trainer(StandardScaler(54.0, 20.0), cfg.in_dim, cfg.out_dim, cfg.num_nodes, cfg.residual_channels, cfg.dropout,
+                   1e-3, 1e-4, dev, sup, cfg.gcn_bool, cfg.addaptadj, None, cfg.blocks, cfg.layers)
+    tr.model.load_state_dict(rec["state0"])
+    x, y = rec["x"].to(dev), rec["y"][:, :, : cfg.out_dim].to(dev)
+    got = [tr.train(x, y) for _ in range(3)]
+    got.append(tr.eval(x, y))
+    for g, w in zip(got, rec["trainer_metrics"].tolist()):
+        for a, b in zip(g, w):
+            assert abs(a - b) <= 1e-4 * abs(b) + 1e-6, (got, rec["trainer_metrics"])
+    for k, v in tr.model.state_dict().items():
+        assert_close_rel(v.float(), rec["state3/" + k].float(), TOL, "state after 3 steps " + k, floor=1e-6)
+
+
+@pytest.mark.parametrize("V,C,L,B", [(207, 32, 12, 8), (325, 32, 3, 4), (50, 8, 1, 3), (130, 64, 5, 2)])
+def test_nconv_operator(M, V, C, L, B):
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(V)
+    x = torch.randn(B, C, V, L, generator=gen)
+    A = torch.softmax(torch.randn(V, V, generator=gen), dim=1)
+    gy = torch.randn(B, C, V, L, generator=gen)
+    xr, Ar = x.clone().requires_grad_(True), A.clone().requires_grad_(True)
+    yr = O.nconv(xr, Ar)
+    yr.backward(gy)
+    xc, Ac = x.to(dev).requires_grad_(True), A.to(dev).requires_grad_(True)
+    y = M.nconv()(xc, Ac)
+    assert y.is_contiguous() and y.shape == yr.shape
+    y.backward(gy.to(dev))
+    assert_close_rel(y, yr.detach(), TOL, "nconv y")
+    assert_close_rel(xc.grad, xr.grad, TOL, "nconv dx")
+    assert_close_rel(Ac.grad, Ar.grad, TOL, "nconv dA")
+    # strided (BLNC-physical) input takes the no-copy path and must agree
+    xs = x.permute(0, 3, 2, 1).contiguous().permute(0, 3, 2, 1).to(dev)
+    assert_close_rel(M.nconv()(xs, A.to(dev)), yr.detach(), TOL, "nconv strided input")
+
+
+@pytest.mark.parametrize("S,order,p", [(3, 2, 0.0), (1, 2, 0.0), (2, 3, 0.0), (3, 2, 0.3)])
+def test_gcn_operator(M, S, order, p):
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(S * 10 + order)
+    B, C, V, L, Co = 3, 16, 37, 5, 24
+    x = torch.randn(B, C, V, L, generator=gen)
+    sup = [torch.softmax(torch.randn(V, V, generator=gen), dim=1) for _ in range(S)]
+    g = M.gcn(C, Co, p, support_len=S, order=order).to(dev)
+    g.train()
+    keep = None
+    if p > 0:
+        keep = (torch.rand(B, L, V, Co, generator=gen) >= p).to(torch.uint8)
+        g._keep_mask = keep.to(dev)
+    W, b = g.mlp.mlp.weight.detach().cpu().clone().requires_grad_(True), g.mlp.mlp.bias.detach().cpu().clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    supr = [s.clone().requires_grad_(True) for s in sup]
+    km = keep.permute(0, 3, 2, 1).float() / (1 - p) if keep is not None else None
+    yr = O.gcn(xr, supr, W, b, order, p, True, km)
+    gy = torch.randn(yr.shape, generator=gen)
+    yr.backward(gy)
+    xc = x.to(dev).requires_grad_(True)
+    supc = [s.to(dev).requires_grad_(True) for s in sup]
+    y = g(xc, supc)
+    y.backward(gy.to(dev))
+    assert_close_rel(y, yr.detach(), TOL, "gcn y")
+    assert_close_rel(xc.grad, xr.grad, TOL, "gcn dx")
+    assert_close_rel(g.mlp.mlp.weight.grad, W.grad, TOL, "gcn dW")
+    assert_close_rel(g.mlp.mlp.bias.grad, b.grad, TOL, "gcn db")
+    for a, r in zip(supc, supr):
+        assert_close_rel(a.grad, r.grad, TOL, "gcn dA")
+
+
+def test_linear_operator(M):
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(4)
+    lin = M.linear(224, 32).to(dev)
+    x = torch.randn(2, 224, 19, 3, generator=gen)
+    W, b = lin.mlp.weight.detach().cpu().clone().requires_grad_(True), lin.mlp.bias.detach().cpu().clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, W, b)
+    gy = torch.randn(yr.shape, generator=gen)
+    yr.backward(gy)
+    xc = x.to(dev).requires_grad_(True)
+    y = lin(xc)
+    y.backward(gy.to(dev))
+    assert_close_rel(y, yr.detach(), TOL, "linear y")
+    assert_close_rel(xc.grad, xr.grad, TOL, "linear dx")
+    assert_close_rel(lin.mlp.weight.grad, W.grad, TOL, "linear dW")
+    assert_close_rel(lin.mlp.bias.grad, b.grad, TOL, "linear db")
+
+
+def _fullsize(M, cfg, B, dens, dropout_masks=False):
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(0)
+    sup = O.synthetic_supports(cfg.num_nodes, dens, gen) if cfg.has_supports else None
+    x, _ = O.synthetic_batch(B, cfg.num_nodes, 12, cfg.in_dim, gen)
+    x = torch.nn.functional.pad(x, (1, 0, 0, 0))
+    torch.manual_seed(999)
+    m = build_model(M, cfg, sup, dev)
+    state = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    m.train()
+    out = m(x.to(dev))
+    probe = torch.randn(out.shape, generator=gen)
+    (out * probe.to(dev)).sum().backward()
+    pk = [k for k in state if not O.is_buffer(k)]
+    for k in pk:
+        state[k].requires_grad_(True)
+    oout = O.forward(state, cfg, x, sup, True)
+    (oout * probe).sum().backward()
+    assert_close_rel(out, oout.detach(), TOL, "output")
+    gn = sum(float(state[k].grad.double().pow(2).sum()) for k in pk if state[k].grad is not None) ** 0.5
+    gd = 0.0
+    for k, p in m.named_parameters():
+        if state[k].grad is None:
+            assert p.grad is None, k
+            continue
+        assert_close_rel(p.grad, state[k].grad, TOL, "grad " + k, floor=2e-6 * gn)
+        gd += float((p.grad.cpu() - state[k].grad).double().pow(2).sum())
+    assert gd ** 0.5 <= TOL * gn
+    for k, v in m.state_dict().items():
+        if O.is_buffer(k):
+            assert_close_rel(v.float(), state[k].float(), TOL, "buffer " + k)
+    return out
+
+
+def test_metr_la_full_size(M):
+    """BASELINE config 1 at its full size (N=207, B=64, doubletransition + adaptive)."""
+    import json, os
+    out = _fullsize(M, O.GwnetConfig(num_nodes=207, dropout=0.0, n_static_supports=2), 64, 0.05)
+    rep = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "fullsize_report.json")))["metr-la"]
+    got = out.flatten()[:8].cpu().tolist()
+    for a, b in zip(got, rep["out_first8"]):      # the REAL reference's first outputs on the same seeded inputs
+        assert abs(a - b) <= 1e-4 * max(abs(b), 0.05), (got, rep["out_first8"])
+
+
+def test_pems_bay_aptonly_full_size(M):
+    """BASELINE config 2 (N=325, adaptive adjacency only)."""
+    _fullsize(M, O.GwnetConfig(num_nodes=325, dropout=0.0, n_static_supports=0, has_supports=False), 16, 0.05)
+
+
+def test_crash_shape_long_sequence(M):
+    """BASELINE config 3 secondary: N=200, seq 48 -> T_out = 37, out_dim 48 (skip slicing with T_out > 1)."""
+    dev = torch.device("cuda:0")
+    cfg = O.GwnetConfig(num_nodes=200, dropout=0.0, n_static_supports=2, out_dim=48)
+    gen = torch.Generator().manual_seed(1)
+    sup = O.synthetic_supports(200, 0.05, gen)
+    x, _ = O.synthetic_batch(4, 200, 48, 2, gen)
+    x = torch.nn.functional.pad(x, (1, 0, 0, 0))
+    torch.manual_seed(5)
+    m = build_model(M, cfg, sup, dev)
+    state = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    m.train()
+    out = m(x.to(dev))
+    assert tuple(out.shape) == (4, 48, 200, 37)
+    oout = O.forward(state, cfg, x, sup, True)
+    assert_close_rel(out, oout, TOL, "T_out=37 output")
+
+
+def test_dropout_statistics_and_determinism(M):
+    dev = torch.device("cuda:0")
+    cfg = O.GwnetConfig(num_nodes=64, dropout=0.3, n_static_supports=2)
+    gen = torch.Generator().manual_seed(2)
+    sup = O.synthetic_supports(64, 0.1, gen)
+    x, _ = O.synthetic_batch(8, 64, 12, 2, gen)
+    x = torch.nn.functional.pad(x, (1, 0, 0, 0)).to(dev)
+    torch.manual_seed(3)
+    m = build_model(M, cfg, sup, dev)
+    m.train()
+    torch.manual_seed(10)
+    a = m(x)
+    torch.manual_seed(10)
+    b = m(x)
+    c = m(x)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    g = M.gcn(32, 32, 0.3, support_len=1).to(dev)
+    g.train()
+    with torch.no_grad():
+        g.mlp.mlp.weight.zero_()
+        g.mlp.mlp.bias.fill_(1.0)
+    y = g(torch.zeros(8, 32, 64, 12, device=dev), [torch.eye(64, device=dev)])
+    keep = (y != 0).float().mean().item()
+    assert abs(keep - 0.7) < 0.01, keep
+    assert abs(y.max().item() - 1 / 0.7) < 1e-5
