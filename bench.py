@@ -266,8 +266,9 @@ def run_native(args):
                         "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e},
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
                 "model_tflops": algorithmic_gflop_per_step(BATCH * world) / ms, "clocks": clocks}
-        if world == 1:
+        if world == 1 and not args.skip_roofline:
             line["roofline"] = roofline_leg(lib, dev)
+        if world == 1 and not args.skip_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -281,6 +282,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only")
+    ap.add_argument("--skip-roofline", action="store_true", help="profiling runs only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

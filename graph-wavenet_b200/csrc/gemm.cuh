@@ -83,7 +83,7 @@ __device__ __forceinline__ void tile_commit(float* s, const float (&r)[(T::BK * 
 }
 
 template <class T, class AL, class BL, class EP>
-__global__ void __launch_bounds__(T::NT) gemm_kernel(AL al, BL bl, EP ep, i64 M, int N, int K, int kchunk, int ksplit) {
+__global__ void __launch_bounds__(T::NT, 512 / T::NT) gemm_kernel(AL al, BL bl, EP ep, i64 M, int N, int K, int kchunk, int ksplit) {
   constexpr int BM = T::BM, BN = T::BN, BK = T::BK, TM = T::TM, TN = T::TN;
   constexpr int AS = T::AS, BS = T::BS;
   __shared__ __align__(16) float As[2][BK * AS];

@@ -905,6 +905,43 @@ int gwn_plan_out_len(const gwn_plan* p, int* t_out, int* receptive_field) {
   return 0;
 }
 
+int gwn_plan_debug_layout(const gwn_plan* p, char* buf, int len) {
+  GWN_CHECK_ARG(p && buf && len > 0, "debug_layout: bad argument");
+  std::string s;
+  char t[160];
+  auto put = [&](const char* space, const char* name, int idx, i64 off, i64 n) {
+    snprintf(t, sizeof(t), "%s %s%d %lld %lld\n", space, name, idx, (long long)off, (long long)n);
+    s += t;
+  };
+  const gwn_config& c = p->c;
+  const i64 N = c.num_nodes;
+  const int C = c.residual_channels, D = c.dilation_channels;
+  put("fwd", "sup", 0, p->o_sup, (i64)std::max(p->S, 1) * N * p->ld);
+  put("fwd", "supT", 0, p->o_supT, (i64)std::max(p->S, 1) * N * p->ld);
+  put("fwd", "x0_", 0, p->o_x0, p->P0() * C);
+  for (int i = 0; i < p->nL; ++i) {
+    for (int q = 0; q < p->nseg; ++q) put("fwd", q == 0 ? "g" : (q == 1 ? "hopA_" : (q == 2 ? "hopB_" : "hopN_")), i, p->o_g[i] + (i64)q * p->P(i) * D, p->P(i) * D);
+    put("fwd", "u", i, p->o_u[i], p->P(i) * C);
+    put("fwd", "ac", i, p->o_ac[i], 2 * C);
+    put("fwd", "mr", i, p->o_mr[i], 2 * C);
+  }
+  put("fwd", "skip", 0, p->o_skip, p->PT() * c.skip_channels);
+  put("fwd", "e1_", 0, p->o_e1, p->PT() * c.end_channels);
+  put("bwd", "dgh", 0, p->o_dgh, (i64)p->nL * p->PT() * D);
+  put("bwd", "dout", 0, p->o_dout, p->PT() * p->ldo);
+  put("bwd", "de1_", 0, p->o_de1, p->PT() * c.end_channels);
+  put("bwd", "dskip", 0, p->o_dskip, p->PT() * c.skip_channels);
+  put("bwd", "dA", 0, p->o_dA, N * p->ld);
+  put("bwd", "dR", 0, p->o_dR, N * p->ld);
+  put("bwd", "buf", 0, p->o_buf0, p->P0() * C);
+  put("bwd", "buf", 1, p->o_buf1, p->P0() * C);
+  put("bwd", "dsegs", 0, p->o_dsegs, p->P(0) * D * p->nseg);
+  put("bwd", "dg", 0, p->o_dg, p->P(0) * D);
+  put("bwd", "dpre", 0, p->o_dpre, p->P(0) * 2 * D);
+  snprintf(buf, len, "%s", s.c_str());
+  return 0;
+}
+
 int gwn_plan_forward(gwn_plan* p, const gwn_forward_args* a) {
   GWN_CHECK_ARG(p && a, "plan_forward: null argument");
   return plan_forward(p, a);

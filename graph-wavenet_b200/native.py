@@ -68,7 +68,7 @@ EXPORTS = [
     "gwn_nconv_fwd", "gwn_nconv_bwd", "gwn_linear_fwd", "gwn_linear_bwd",
     "gwn_gcn_fwd", "gwn_gcn_bwd_scratch_floats", "gwn_gcn_bwd",
     "gwn_plan_create", "gwn_plan_destroy", "gwn_plan_workspace_bytes", "gwn_plan_param_count",
-    "gwn_plan_param_info", "gwn_plan_out_len", "gwn_plan_forward", "gwn_plan_backward",
+    "gwn_plan_param_info", "gwn_plan_out_len", "gwn_plan_debug_layout", "gwn_plan_forward", "gwn_plan_backward",
 ]
 
 
@@ -119,6 +119,7 @@ class Lib:
         d.gwn_plan_param_info.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64),
                                           C.POINTER(C.c_int64)]
         d.gwn_plan_out_len.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        d.gwn_plan_debug_layout.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         d.gwn_plan_forward.argtypes = [C.c_void_p, C.POINTER(GwnForwardArgs)]
         d.gwn_plan_backward.argtypes = [C.c_void_p, C.POINTER(GwnBackwardArgs)]
         if d.gwn_abi_version() != 1:

@@ -146,6 +146,8 @@ int gwn_plan_param_count(const gwn_plan* p, int* n_entries, int64_t* grad_floats
 /* Name, element offset into the flat gradient buffer (-1 for buffers) and element count of entry i. */
 int gwn_plan_param_info(const gwn_plan* p, int i, char* name, int name_len, int64_t* grad_offset, int64_t* numel);
 int gwn_plan_out_len(const gwn_plan* p, int* t_out, int* receptive_field);
+/* Debug aid: text listing "<fwd|bwd> <name> <float offset> <floats>" of the workspace / scratch regions. */
+int gwn_plan_debug_layout(const gwn_plan* p, char* buf, int len);
 
 typedef struct gwn_forward_args {
   const void* const* params;     /* n_entries device pointers, state_dict order            */

@@ -23,7 +23,7 @@ def run_smoke():
     m.train()
     state = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
     out = m(x.to(dev))
-    probe = torch.randn(out.shape, generator=gen)
+    probe = torch.randn(out.shape, generator=gen) * O.relu_safe_positions(state, cfg, x, sup, True)
     (out * probe.to(dev)).sum().backward()
     torch.cuda.synchronize()
     pk = [k for k in state if not O.is_buffer(k)]
