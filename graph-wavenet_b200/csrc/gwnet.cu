@@ -107,7 +107,10 @@ static int build_plan(gwn_plan* p) {
                     c.end_channels % 4 == 0,
                 "plan: channel counts must be multiples of 4");
   GWN_CHECK_ARG(c.blocks >= 1 && c.layers >= 1 && c.blocks * c.layers <= MAXSEG, "plan: blocks*layers must be in [1,%d]", MAXSEG);
-  GWN_CHECK_ARG(c.precision == GWN_PREC_FP32, "plan: precision %d not available in this build", c.precision);
+  GWN_CHECK_ARG(c.precision == GWN_PREC_FP32 || c.precision == GWN_PREC_TF32, "plan: precision %d not available in this build",
+                c.precision);
+  GWN_CHECK_ARG(c.precision == GWN_PREC_FP32 || !c.gcn || c.dilation_channels == 32,
+                "plan: the tcgen05 (tf32) tier needs dilation_channels == 32");
   GWN_CHECK_ARG(c.order >= 1 && c.order <= MAXSUP, "plan: order must be in [1,%d]", MAXSUP);
   GWN_CHECK_ARG(c.dropout >= 0.f && c.dropout < 1.f, "plan: dropout must be in [0,1)");
   GWN_CHECK_ARG(c.n_static_supports >= 0, "plan: negative support count");
@@ -312,6 +315,8 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
 
   // ---- supports: pack static ones, compute the adaptive one (model.py:185-188)
   SupportView supF[MAXSUP], supB[MAXSUP];
+  TcSupports tcF;
+  memset(&tcF, 0, sizeof(tcF));
   for (int s = 0; s < p->S; ++s) {
     float* Ap = ws + p->o_sup + (i64)s * N * p->ld;
     float* ATp = ws + p->o_supT + (i64)s * N * p->ld;
@@ -325,7 +330,11 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     }
     supF[s] = support_padded(Ap, p->ld);
     supB[s] = support_padded(ATp, p->ld);
+    tcF.S[s] = ATp;   // forward contraction y[w] = sum_v A[v,w] x[v]: K-contiguous rows are those of A^T
   }
+  tcF.ld = p->ld;
+  tcF.precision = c.precision;
+  (void)supB;
   // ---- BN bookkeeping
   if (a->training) {
     for (int i = 0; i < nL; ++i) GWN_TRY(dev_memset(ws + p->o_sums[i], 0, sizeof(double) * 2 * C, st));
@@ -360,7 +369,7 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     memset(&m, 0, sizeof(m));
     if (c.gcn) {
       GcnShape gs{B, p->L[i], N, D, C, p->S, c.order};
-      GWN_TRY(gcn_hops_forward(gs, g, supF, g + Pi * D, st));
+      GWN_TRY(gcn_hops_forward(gs, g, supF, g + Pi * D, st, &tcF));
       m.W = P_<float>(prm, p->li[i].mw);
       m.bias = P_<float>(prm, p->li[i].mb);
     } else {  // model.py:232
@@ -455,7 +464,14 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
   GWN_TRY(dev_memset(sc + p->o_dout, 0, sizeof(float) * PT * p->ldo, st));
 
   SupportView supB[MAXSUP];
-  for (int s = 0; s < p->S; ++s) supB[s] = support_padded(ws + p->o_supT + (i64)s * N * p->ld, p->ld);
+  TcSupports tcB;
+  memset(&tcB, 0, sizeof(tcB));
+  for (int s = 0; s < p->S; ++s) {
+    supB[s] = support_padded(ws + p->o_supT + (i64)s * N * p->ld, p->ld);
+    tcB.S[s] = ws + p->o_sup + (i64)s * N * p->ld;   // dx[v] = sum_w A[v,w] dy[w]: K-contiguous rows are those of A
+  }
+  tcB.ld = p->ld;
+  tcB.precision = c.precision;
 
   // ---- head backward
   {
@@ -593,7 +609,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
         i64 ldds[MAXSUP];
         for (int s = 0; s < p->S; ++s) { dsup[s] = nullptr; ldds[s] = p->ld; }
         if (c.adaptive) dsup[p->S - 1] = sc + p->o_dA;
-        GWN_TRY(gcn_hops_backward(gs, g, g + Pi * D, supB, dsegs, dg, dgh_i, p->T_out, dsup, ldds, st));
+        GWN_TRY(gcn_hops_backward(gs, g, g + Pi * D, supB, dsegs, dg, dgh_i, p->T_out, dsup, ldds, st, &tcB));
       } else {
         GWN_LAUNCH_1D(add_window_kernel, Pi * D, st, dg, (const float*)dsegs, dgh_i, B, p->L[i], N, D, p->T_out);
       }
@@ -721,6 +737,23 @@ int gwn_permute4d(const float* src, const int64_t src_strides[4], float* dst, co
   GWN_TRY(require_device());
   GWN_CHECK_ARG(src && dst, "permute4d: null pointer");
   return permute4d(src, src_strides, dst, dst_strides, sizes, (cudaStream_t)stream);
+}
+
+int gwn_tc_error_flag(int reset) { return tc_error_flag(reset); }
+void gwn_tc_debug_buffer(float* p) { tc_set_debug_buffer(p); }
+void gwn_tc_debug_mode(int m) { tc_set_debug_mode(m); }
+
+int gwn_node_contract(const float* x, const float* S, int64_t ld, float* y, int B, int L, int V, int C, int precision,
+                      void* stream) {
+  GWN_TRY(require_device());
+  GWN_CHECK_ARG(x && S && y, "node_contract: null pointer");
+  SupportView sv = SupportView{S, 1, ld, 0};   // op(k, m) = S[m*ld + k]
+  TcSupports tcs;
+  memset(&tcs, 0, sizeof(tcs));
+  tcs.S[0] = S; tcs.ld = (int)ld; tcs.precision = precision;
+  const float* X[1] = {x};
+  float* Y[1] = {y};
+  return node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, B, L, 0, V, C, (cudaStream_t)stream, &tcs);
 }
 
 int gwn_nconv_fwd(const float* x, const float* A, int64_t lda, float* y, int B, int L, int V, int C, int precision,

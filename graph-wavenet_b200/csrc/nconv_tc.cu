@@ -1,0 +1,434 @@
+// tcgen05 / TMEM / TMA node contraction -- see nconv_tc.cuh for the GEMM mapping.
+#include "nconv_tc.cuh"
+
+#if !GWN_EMU
+#include <cuda.h>
+#include <mutex>
+
+namespace gwn {
+namespace tc {
+
+constexpr int BLOCK_M = 128;   // 4 slabs x 32 channels
+constexpr int SLABS = 4;
+constexpr int CH = 32;
+constexpr int BLOCK_K = 32;    // nodes per pipeline stage: one 128-byte swizzle row of K for the support tile
+constexpr int UMMA_K = 8;      // kind::tf32: 32 bytes of K per instruction
+constexpr int X_STAGE_BYTES = SLABS * BLOCK_K * CH * 4;   // 16 KB
+constexpr int NUM_THREADS = 256;                          // warps 0-3: control roles, warps 4-7: epilogue
+constexpr int ACC_COLS = 256;                             // TMEM columns per accumulator buffer (2 buffers)
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+struct Maps {
+  CUtensorMap x[TC_MAXSUP];
+  CUtensorMap s[TC_MAXSUP];
+};
+
+struct Params {
+  float* Y[TC_MAXSUP];
+  const float* add[TC_MAXSUP];
+  const float* add2;
+  int nsup, kcat, V, L, T_out, nslabs;
+  int n_tile, n_wt, n_jt, nkb, stages, total_tiles;
+  int mode;     // debug: 0 normal, 1 = TMEM st/ld self-test (no MMA), 2 = A operand := support tile (K-major)
+  float* dbg;   // debug: dump of the first pipeline stage (X tile then support tile) by block 0
+};
+
+__device__ int g_tc_err = 0;   // first pipeline time-out (role code), 0 = none
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug must never hang the GPU -- after ~1.5 s (or once another role has failed) give up.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int code) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0) {
+      if (clock64() - t0 > 3000000000LL || *(volatile int*)&g_tc_err != 0) {
+        atomicCAS(&g_tc_err, 0, code);
+        return false;
+      }
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor field layout).
+// layout: 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms) -- the latter is the only
+// legal shared-memory layout of an MN-major tf32 operand; its TMA counterpart is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;           // SWIZZLE_128B atoms need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  const int stage_bytes = X_STAGE_BYTES + p.n_tile * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  const uint32_t bar0 = base + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * p.stages + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nsup; ++s) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x[s]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.s[s]) : "memory");
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * ACC_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int per_out = p.n_jt * p.n_wt;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================== TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+      const int o = tile / per_out, rem = tile - o * per_out;
+      const int wt = rem / p.n_jt, jt = rem - wt * p.n_jt;
+      const int s0 = p.kcat ? 0 : o, s1 = p.kcat ? p.nsup : o + 1;
+      for (int s = s0; s < s1 && ok; ++s) {
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          if (!mbar_wait(empty_bar(stage), phase ^ 1u, 1)) { ok = false; break; }
+          const uint32_t dst = base + stage * stage_bytes;
+          mbar_expect_tx(full_bar(stage), (uint32_t)stage_bytes);
+          tma_load_3d(dst, &maps.x[s], full_bar(stage), 0, kb * BLOCK_K, jt * SLABS);
+          tma_load_2d(dst + X_STAGE_BYTES, &maps.s[s], full_bar(stage), kb * BLOCK_K, wt * p.n_tile);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================================== MMA issuer (one thread)
+    // instruction descriptor: D=f32, A=B=tf32, A MN-major, B K-major, N = n_tile, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(p.n_tile >> 3) << 17) |
+                           ((uint32_t)(BLOCK_M >> 4) << 24);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, accphase = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+      if (!mbar_wait(tempty_bar(acc), accphase ^ 1u, 2)) break;
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+      const int nk_total = (p.kcat ? p.nsup : 1) * p.nkb;
+      for (int it = 0; it < nk_total; ++it) {
+        if (!mbar_wait(full_bar(stage), phase, 3)) { ok = false; break; }
+        tc_fence_after();
+        if (p.dbg && blockIdx.x == 0 && tile == 0 && it == 0) {
+          const float* sm = reinterpret_cast<const float*>(smem + (size_t)stage * stage_bytes);
+          for (int i = 0; i < stage_bytes / 4; ++i) p.dbg[i] = sm[i];
+        }
+        const uint32_t xs = base + stage * stage_bytes;
+        const uint32_t bs = xs + X_STAGE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+          // A (X^T, MN-major, 32-byte-atom swizzle): atoms of 4 k-rows x 128 B (SBO = 512 B between them);
+          // the next 32 rows of M (next slab) lie BLOCK_K*128 B further (LBO); this k-step starts 8 rows in.
+          uint64_t adesc = make_desc(xs + kk * (UMMA_K * 128), BLOCK_K * 128, 4 * 128, 1);
+          uint32_t idesc_k = idesc;
+          if (p.mode == 2) {   // debug: A := first 128 rows of the support tile, K-major
+            adesc = make_desc(bs + kk * (UMMA_K * 4), 16, 1024);
+            idesc_k = idesc & ~(1u << 15);
+          }
+          // B (support, K-major): rows of 128 B (32 k), 8-row groups 1024 B apart; this k-step starts 32 B in
+          const uint64_t bdesc = make_desc(bs + kk * (UMMA_K * 4), 16, 1024);
+          if (p.mode != 1) tc_mma_tf32(d_tmem, adesc, bdesc, idesc_k, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc_commit(empty_bar(stage));     // frees the smem stage once these MMAs have read it
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      if (!ok) break;
+      tc_commit(tfull_bar(acc));         // accumulator complete -> epilogue
+      acc ^= 1;
+      if (acc == 0) accphase ^= 1u;
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue: TMEM -> registers -> global
+    const int ew = warp - 4;             // == warp % 4: TMEM lanes 32*ew .. 32*ew+31 = slab ew of the tile, lane = channel
+    int acc = 0;
+    uint32_t accphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int o = tile / per_out, rem = tile - o * per_out;
+      const int wt = rem / p.n_jt, jt = rem - wt * p.n_jt;
+      if (!mbar_wait(tfull_bar(acc), accphase, 4)) break;
+      tc_fence_after();
+      const int slab = jt * SLABS + ew;
+      const bool slab_ok = slab < p.nslabs;
+      float* y = p.Y[o] + (size_t)slab * p.V * CH + lane;
+      const float* ad = p.add[o] ? p.add[o] + (size_t)slab * p.V * CH + lane : nullptr;
+      const float* ad2 = nullptr;
+      if (p.add2 && slab_ok) {
+        const int b = slab / p.L, l = slab - b * p.L;
+        if (l >= p.L - p.T_out) ad2 = p.add2 + ((size_t)(b * p.T_out + (l - (p.L - p.T_out))) * p.V) * CH + lane;
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * ACC_COLS);
+      const int w_base = wt * p.n_tile;
+      if (p.mode == 1) {   // debug: write lane*1000 + column into TMEM, read it back below
+        for (int c0 = 0; c0 < p.n_tile; ++c0) {
+          const uint32_t v = __float_as_uint((float)((32 * ew + lane) * 1000 + c0));
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr + c0), "r"(v) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+        uint32_t r[16];
+        tc_ld16(taddr + c0, r);
+        tc_wait_ld();
+        if (slab_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int w = w_base + c0 + j;
+            if (w < p.V) {
+              float v = __uint_as_float(r[j]);
+              if (ad) v += ad[(size_t)w * CH];
+              if (ad2) v += ad2[(size_t)w * CH];
+              y[(size_t)w * CH] = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) accphase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * ACC_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+static int encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return GWN_ERR_CUDA;
+  }
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+    return GWN_ERR_CUDA;
+  }
+  return 0;
+}
+
+}  // namespace tc
+
+static float* g_dbg_ptr = nullptr;
+static int g_dbg_mode = 0;
+void tc_set_debug_buffer(float* p) { g_dbg_ptr = p; }
+void tc_set_debug_mode(int m) { g_dbg_mode = m; }
+
+int tc_error_flag(int reset) {
+  int v = 0;
+  cudaMemcpyFromSymbol(&v, tc::g_tc_err, sizeof(int));
+  if (reset) {
+    int z = 0;
+    cudaMemcpyToSymbol(tc::g_tc_err, &z, sizeof(int));
+  }
+  return v;
+}
+
+int node_gemm_tc(const NodeTcArgs& a, cudaStream_t stream) {
+  using namespace tc;
+  if (a.nsup < 1 || a.nsup > TC_MAXSUP) {
+    set_error("node_gemm_tc: %d supports (max %d)", a.nsup, TC_MAXSUP);
+    return GWN_ERR_UNSUPPORTED;
+  }
+  if (a.ld % 4 != 0 || a.ld < a.V) {
+    set_error("node_gemm_tc: support leading dimension %d must be a multiple of 4 and >= V", a.ld);
+    return GWN_ERR_UNSUPPORTED;
+  }
+  const long long nslabs = (long long)a.B * a.L;
+  if (nslabs <= 0 || a.V <= 0) return 0;
+  Maps maps;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.nsup = a.nsup; p.kcat = a.kcat; p.V = a.V; p.L = a.L; p.T_out = a.T_out; p.nslabs = (int)nslabs;
+  p.n_tile = a.V > 256 ? 256 : round_up(a.V, 16);
+  p.n_wt = (a.V + p.n_tile - 1) / p.n_tile;
+  p.n_jt = (int)((nslabs + SLABS - 1) / SLABS);
+  p.nkb = (a.V + BLOCK_K - 1) / BLOCK_K;
+  const int stage_bytes = X_STAGE_BYTES + p.n_tile * 128;
+  p.stages = (SMEM_LIMIT - 2048) / stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages < 2) {
+    set_error("node_gemm_tc: tile does not fit shared memory");
+    return GWN_ERR_UNSUPPORTED;
+  }
+  const int nout = a.kcat ? 1 : a.nsup;
+  const long long tiles = (long long)p.n_jt * p.n_wt * nout;
+  if (tiles > 2147483647LL) {
+    set_error("node_gemm_tc: too many tiles");
+    return GWN_ERR_UNSUPPORTED;
+  }
+  p.total_tiles = (int)tiles;
+  for (int s = 0; s < a.nsup; ++s) {
+    if ((reinterpret_cast<uintptr_t>(a.X[s]) & 15) || (reinterpret_cast<uintptr_t>(a.S[s]) & 15)) {
+      set_error("node_gemm_tc: operands must be 16-byte aligned");
+      return GWN_ERR_UNSUPPORTED;
+    }
+    cuuint64_t xd[3] = {(cuuint64_t)CH, (cuuint64_t)a.V, (cuuint64_t)nslabs};
+    cuuint64_t xs[2] = {(cuuint64_t)CH * 4, (cuuint64_t)a.V * CH * 4};
+    cuuint32_t xb[3] = {CH, BLOCK_K, SLABS};
+    GWN_TRY(encode(&maps.x[s], a.X[s], 3, xd, xs, xb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    cuuint64_t sd[2] = {(cuuint64_t)a.V, (cuuint64_t)a.V};
+    cuuint64_t ss[1] = {(cuuint64_t)a.ld * 4};
+    cuuint32_t sb[2] = {BLOCK_K, (cuuint32_t)p.n_tile};
+    GWN_TRY(encode(&maps.s[s], a.S[s], 2, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  for (int s = a.nsup; s < TC_MAXSUP; ++s) { maps.x[s] = maps.x[0]; maps.s[s] = maps.s[0]; }
+  for (int o = 0; o < nout; ++o) {
+    p.Y[o] = a.Y[o];
+    p.add[o] = a.add[o];
+  }
+  p.add2 = a.add2;
+  p.dbg = g_dbg_ptr;
+  p.mode = g_dbg_mode;
+
+  const int smem_bytes = p.stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  static int num_sms = 148;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(nconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(attr_err));
+    return GWN_ERR_CUDA;
+  }
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  nconv_tc_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(maps, p);
+  GWN_LAUNCH_CHECK();
+  count_launch();
+  return 0;
+}
+
+}  // namespace gwn
+
+#else   // GWN_EMU: the tensor-core tier exists only on the GPU
+namespace gwn {
+void tc_set_debug_buffer(float*) {}
+void tc_set_debug_mode(int) {}
+int tc_error_flag(int) { return 0; }
+int node_gemm_tc(const NodeTcArgs&, cudaStream_t) {
+  set_error("the tcgen05 tier is not part of the host emulation");
+  return GWN_ERR_UNSUPPORTED;
+}
+}  // namespace gwn
+#endif

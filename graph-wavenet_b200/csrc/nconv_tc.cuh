@@ -1,0 +1,36 @@
+// Tensor-core node contraction (nconv, model.py:13 and its autograd) for sm_100a:
+// tcgen05.mma kind::tf32 with the accumulator in TMEM, operands staged by TMA (128-byte swizzle),
+// warp-specialised (TMA producer / MMA issuer / 4 epilogue warps), persistent over tiles.
+//
+//   D[j, m] = sum_s sum_k X_s[k, j] * S_s[m, k]          j = (slab, channel) row, m = output node
+//
+// GEMM orientation: M = 128 rows of j (4 slabs x 32 channels: each slab's [node][32 ch] block is
+// exactly one MN-major SWIZZLE_128B atom column), N = output nodes (<= 256 per tile), K = nodes.
+// The support is read from a K-contiguous ("k-major") padded buffer S[m][k] (A^T for the forward
+// contraction, A itself for dX = A.dY).
+#pragma once
+#include "common.cuh"
+
+namespace gwn {
+
+constexpr int TC_MAXSUP = 4;
+
+struct NodeTcArgs {
+  const float* X[TC_MAXSUP];       // slab tensors [nslabs][V][32]
+  const float* S[TC_MAXSUP];       // k-major supports [V][ld]
+  int ld;
+  int nsup;
+  int kcat;                        // 1: one output, summed over supports; 0: nsup independent outputs
+  float* Y[TC_MAXSUP];
+  const float* add[TC_MAXSUP];     // nullable, same layout as Y
+  const float* add2;               // nullable head window [B][T_out][V][32]
+  int B, L, T_out, V;
+};
+
+// Returns GWN_ERR_UNSUPPORTED (with a message) when the shape cannot use this kernel.
+int node_gemm_tc(const NodeTcArgs& a, cudaStream_t stream);
+int tc_error_flag(int reset);
+void tc_set_debug_buffer(float* p);
+void tc_set_debug_mode(int m);
+
+}  // namespace gwn

@@ -3,6 +3,7 @@
 #pragma once
 #include "functors.cuh"
 #include "elementwise.cuh"
+#include "nconv_tc.cuh"
 
 namespace gwn {
 
@@ -38,11 +39,29 @@ inline void fill_support(LdSupport& l, int idx, const SupportView& s, int M) {
 
 // Y_s[m] = sum_k op_s(k,m) X_s[k] (+ add_s) for s < nsup (batched), or, when kcat,
 // Y_0[m] = sum_s sum_k op_s(k,m) X_s[k] (+ add_0 + window(add2)).
+// `tcs` (nullable): the same supports as K-contiguous padded buffers S[m][k] (ld = tc_ld) for the tcgen05 tier.
+struct TcSupports {
+  const float* S[MAXSUP];
+  int ld;
+  int precision;   // gwn_precision
+};
 inline int node_gemm(const SupportView* sup, int nsup, bool kcat, const float* const* X,
                      float* const* Y, const float* const* add, const float* add2, int B, int L, int T_out, int V, int C,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const TcSupports* tcs = nullptr) {
   GWN_CHECK_ARG(nsup >= 1 && nsup <= MAXSUP, "node_gemm: %d supports (max %d)", nsup, MAXSUP);
   GWN_CHECK_ARG(C % 4 == 0, "node_gemm: channels (%d) must be a multiple of 4", C);
+  if (tcs && tcs->precision != GWN_PREC_FP32) {
+    GWN_CHECK_ARG(tcs->precision == GWN_PREC_TF32, "node_gemm: precision %d not available in this build", tcs->precision);
+    GWN_CHECK_ARG(C == 32, "node_gemm: the tcgen05 tier needs 32 channels per slab row (got %d)", C);
+    GWN_CHECK_ARG(nsup <= TC_MAXSUP, "node_gemm: the tcgen05 tier takes at most %d supports", TC_MAXSUP);
+    NodeTcArgs t;
+    memset(&t, 0, sizeof(t));
+    for (int s = 0; s < nsup; ++s) { t.X[s] = X[s]; t.S[s] = tcs->S[s]; }
+    const int nout = kcat ? 1 : nsup;
+    for (int s = 0; s < nout; ++s) { t.Y[s] = Y[s]; t.add[s] = add ? add[s] : nullptr; }
+    t.ld = tcs->ld; t.nsup = nsup; t.kcat = kcat ? 1 : 0; t.add2 = add2; t.B = B; t.L = L; t.T_out = T_out; t.V = V;
+    return node_gemm_tc(t, stream);
+  }
   LdSupport a;
   LdSlab b;
   EpSlab e;
@@ -171,7 +190,7 @@ inline int hop_index(const GcnShape& g, int s, int k) { return 1 + s * g.order +
 
 // hops[q-1] (q >= 1) receives the q-th concatenated tensor; x is segment 0.
 inline int gcn_hops_forward(const GcnShape& g, const float* x, const SupportView* sup_fwd, float* hops,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, const TcSupports* tcs = nullptr) {
   const i64 PD = (i64)g.B * g.L * g.V * g.D;
   for (int k = 1; k <= g.order; ++k) {
     const float* X[MAXSUP];
@@ -180,7 +199,7 @@ inline int gcn_hops_forward(const GcnShape& g, const float* x, const SupportView
       X[s] = (k == 1) ? x : hops + (i64)(hop_index(g, s, k - 1) - 1) * PD;
       Y[s] = hops + (i64)(hop_index(g, s, k) - 1) * PD;
     }
-    GWN_TRY(node_gemm(sup_fwd, g.S, false, X, Y, nullptr, nullptr, g.B, g.L, 0, g.V, g.D, stream));
+    GWN_TRY(node_gemm(sup_fwd, g.S, false, X, Y, nullptr, nullptr, g.B, g.L, 0, g.V, g.D, stream, tcs));
   }
   return 0;
 }
@@ -190,7 +209,7 @@ inline int gcn_hops_forward(const GcnShape& g, const float* x, const SupportView
 // dsup[s] (nullable) += sum_k hop_{s,k-1}^T t_{s,k}.
 inline int gcn_hops_backward(const GcnShape& g, const float* x, const float* hops, const SupportView* sup_bwd, float* dsegs,
                              float* dx, const float* add2, int T_out, float* const* dsup, const i64* ldds,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, const TcSupports* tcs = nullptr) {
   const i64 PD = (i64)g.B * g.L * g.V * g.D;
   for (int k = g.order; k >= 2; --k) {
     const float* X[MAXSUP];
@@ -201,7 +220,7 @@ inline int gcn_hops_backward(const GcnShape& g, const float* x, const float* hop
       Y[s] = dsegs + (i64)hop_index(g, s, k - 1) * PD;
       A[s] = Y[s];
     }
-    GWN_TRY(node_gemm(sup_bwd, g.S, false, X, Y, A, nullptr, g.B, g.L, 0, g.V, g.D, stream));
+    GWN_TRY(node_gemm(sup_bwd, g.S, false, X, Y, A, nullptr, g.B, g.L, 0, g.V, g.D, stream, tcs));
   }
   for (int s = 0; s < g.S; ++s) {
     if (!dsup || !dsup[s]) continue;
@@ -219,7 +238,7 @@ inline int gcn_hops_backward(const GcnShape& g, const float* x, const float* hop
     for (int s = 0; s < g.S; ++s) X[s] = dsegs + (i64)hop_index(g, s, 1) * PD;
     float* Y[1] = {dx};
     const float* A[1] = {dsegs};
-    GWN_TRY(node_gemm(sup_bwd, g.S, true, X, Y, A, add2, g.B, g.L, T_out, g.V, g.D, stream));
+    GWN_TRY(node_gemm(sup_bwd, g.S, true, X, Y, A, add2, g.B, g.L, T_out, g.V, g.D, stream, tcs));
   }
   return 0;
 }

@@ -70,6 +70,17 @@ int gwn_device_info(int* n_devices, char* name, int name_len, int* sm_count, int
 int gwn_permute4d(const float* src, const int64_t src_strides[4], float* dst, const int64_t dst_strides[4],
                   const int64_t sizes[4], void* stream);
 
+/* Node contraction with the support given K-contiguous: y[b,l,m,c] = sum_k S[m*ld + k] * x[b,l,k,c].
+ * (nconv forward is this with S = A^T, its input gradient with S = A.)  precision GWN_PREC_TF32 runs the
+ * tcgen05/TMEM/TMA kernel (needs C == 32, ld % 4 == 0, 16-byte aligned pointers); GWN_PREC_FP32 the FMA tier. */
+int gwn_node_contract(const float* x, const float* S, int64_t ld, float* y, int B, int L, int V, int C, int precision,
+                      void* stream);
+/* First pipeline time-out recorded by the tcgen05 kernels (0 = none); synchronises the device. Debug aid. */
+int gwn_tc_error_flag(int reset);
+/* Debug aid: device buffer that receives a dump of the first pipeline stage of subsequent tcgen05 launches (NULL = off). */
+void gwn_tc_debug_buffer(float* p);
+void gwn_tc_debug_mode(int mode);   /* 0 = normal; non-zero = kernel self-test modes (development only) */
+
 /* ------------------------------------------------------------------ nconv (model.py:8-14)
  * y[b,l,w,c] = sum_v x[b,l,v,c] * A[v,w].   x,y: BLNC [B,L,V,C]; A: [V,V] row-major, ld = lda.
  * Replaces torch.einsum('ncvl,vw->ncwl') + .contiguous().                          */

@@ -248,3 +248,92 @@ def test_dropout_statistics_and_determinism(M):
     keep = (y != 0).float().mean().item()
     assert abs(keep - 0.7) < 0.01, keep
     assert abs(y.max().item() - 1 / 0.7) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 (tf32) tier
+TOL_TF32 = 2e-2     # reduced-precision tier (north star: 2e-2); measured errors are printed and are ~1e-3
+
+
+@pytest.mark.parametrize("B,L,V", [(1, 4, 32), (2, 3, 207), (3, 5, 50), (5, 1, 325), (2, 2, 300), (7, 3, 17)])
+def test_tcgen05_node_contract(M, B, L, V):
+    """gwn_node_contract on the tcgen05/TMEM/TMA kernel vs fp64: ragged node counts (V % 16, V % 32 != 0, V > 256)
+    and slab counts that do not fill the 4-slab tile."""
+    from graph_wavenet_b200 import native as NV
+    lib = NV.get_lib()
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(V + L)
+    ld = (V + 3) // 4 * 4
+    S = torch.zeros(V, ld)
+    S[:, :V] = torch.softmax(torch.randn(V, V, generator=gen), dim=1)
+    x = torch.randn(B, L, V, 32, generator=gen)
+    ref = torch.einsum("mk,blkc->blmc", S[:, :V].double(), x.double())
+    Sd, xd = S.to(dev), x.to(dev)
+    y = torch.full((B, L, V, 32), float("nan"), device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    lib.check(lib.dll.gwn_node_contract(xd.data_ptr(), Sd.data_ptr(), ld, y.data_ptr(), B, L, V, 32, NV.PREC_TF32, st))
+    torch.cuda.synchronize()
+    assert lib.dll.gwn_tc_error_flag(1) == 0
+    assert not torch.isnan(y).any()
+    assert_close_rel(y, ref, 2e-3, "tf32 node contraction")
+
+
+@pytest.mark.parametrize("name", ["c32"])
+def test_tf32_tier_matches_reference_golden(M, name):
+    dev = torch.device("cuda:0")
+    rec = load_case(name)
+    cfg = rec["cfg"]
+    m = build_model(M, cfg, rec["supports"], dev, rec.get("aptinit"))
+    from graph_wavenet_b200 import native as NV
+    m.precision = NV.PREC_TF32
+    m.load_state_dict(rec["state0"])
+    x = torch.nn.functional.pad(rec["x"], (1, 0, 0, 0)).to(dev)
+    m.train()
+    xg = x.clone().requires_grad_(True)
+    out = m(xg)
+    assert_close_rel(out, rec["out_train"], TOL_TF32, "tf32 train output")
+    (out * rec["probe"].to(dev)).sum().backward()
+    ref = sub(rec, "grad/")
+    gnorm = sum(float(g.double().pow(2).sum()) for g in ref.values()) ** 0.5
+    for k, p in m.named_parameters():
+        if k in ref:
+            assert_close_rel(p.grad, ref[k], TOL_TF32, "tf32 grad " + k, floor=1e-4 * gnorm)
+
+
+def test_tf32_tier_metr_la_full_size(M):
+    """METR-LA full size with the node contraction on tcgen05 (TF32 operands, fp32 accumulate)."""
+    dev = torch.device("cuda:0")
+    from graph_wavenet_b200 import native as NV
+    cfg = O.GwnetConfig(num_nodes=207, dropout=0.0, n_static_supports=2)
+    gen = torch.Generator().manual_seed(0)
+    sup = O.synthetic_supports(207, 0.05, gen)
+    x, _ = O.synthetic_batch(64, 207, 12, 2, gen)
+    x = torch.nn.functional.pad(x, (1, 0, 0, 0))
+    torch.manual_seed(999)
+    m = build_model(M, cfg, sup, dev)
+    m.precision = NV.PREC_TF32
+    state = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    m.train()
+    out = m(x.to(dev))
+    probe = torch.randn(out.shape, generator=gen) * O.relu_safe_positions(state, cfg, x, sup, True, tau=1e-2)
+    (out * probe.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert NV.get_lib().dll.gwn_tc_error_flag(1) == 0
+    pk = [k for k in state if not O.is_buffer(k)]
+    for k in pk:
+        state[k].requires_grad_(True)
+    oout = O.forward(state, cfg, x, sup, True)
+    (oout * probe).sum().backward()
+    assert_close_rel(out, oout.detach(), TOL_TF32, "tf32 output")
+    gn = sum(float(state[k].grad.double().pow(2).sum()) for k in pk if state[k].grad is not None) ** 0.5
+    gd, worst = 0.0, (0.0, "")
+    for k, p in m.named_parameters():
+        if state[k].grad is None:
+            continue
+        assert_close_rel(p.grad, state[k].grad, 5e-2, "tf32 grad " + k, floor=1e-3 * gn)
+        e = float((p.grad.cpu() - state[k].grad).norm() / (state[k].grad.norm() + 1e-30))
+        if "mlp.mlp.bias" not in k:
+            worst = max(worst, (e, k))
+        gd += float((p.grad.cpu() - state[k].grad).double().pow(2).sum())
+    print(f"[tf32 tier] output rel-L2 {float((out.cpu() - oout.detach()).norm() / oout.detach().norm()):.2e}, "
+          f"global grad rel-L2 {gd ** 0.5 / gn:.2e}, worst tensor {worst[1]} {worst[0]:.2e}")
+    assert gd ** 0.5 <= TOL_TF32 * gn
