@@ -200,7 +200,7 @@ def run_native(args):
     sup = [s.to(dev) for s in O.synthetic_supports(NODES, 0.05, gen)]
     torch.manual_seed(999)
     tr = E.trainer(StandardScaler(54.0, 20.0), IN_DIM, SEQ, NODES, 32, DROPOUT, 1e-3, 1e-4, dev, sup, True, True, None)
-    tr.model.precision = {"fp32": NV.PREC_FP32, "tf32": NV.PREC_TF32}[args.precision]
+    tr.model.precision = {"fp32": NV.PREC_FP32, "tf32": NV.PREC_TF32, "fp32x3": NV.PREC_FP32X3}[args.precision]
     if world > 1:
         tr.enable_data_parallel()
     gen = torch.Generator().manual_seed(100 + rank)
@@ -261,8 +261,10 @@ def run_native(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": BATCH * world,
                            "parallelism": f"dp{world}" if world > 1 else "single",
-                           "precision_tier": ("fp32 (FMA) -- 1e-4 parity tier" if args.precision == "fp32" else
-                                              "tf32: node contraction on tcgen05 kind::tf32, fp32 accumulate; other ops fp32 FMA"),
+                           "precision_tier": {"fp32": "fp32 (FMA) -- 1e-4 parity tier",
+                                              "fp32x3": "fp32-grade 3xTF32 split on tensor cores (mma.sync) -- 1e-4 parity tier",
+                                              "tf32": "tf32: node contraction on tcgen05 kind::tf32, other contractions single-pass TF32 "
+                                                      "mma.sync, fp32 accumulate -- 2e-2 tier"}[args.precision],
                            "l2_policy": "per-step working set (~0.9 GB of saved activations) exceeds the 126 MB L2; 4 rotating input batches"},
                 "e2e": {"value": BATCH * world / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e},
@@ -284,7 +286,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("GWNET_B200_PRECISION", "fp32"), choices=["fp32", "tf32"],
+    ap.add_argument("--precision", default=os.environ.get("GWNET_B200_PRECISION", "fp32"), choices=["fp32", "fp32x3", "tf32"],
                     help="fp32 = FMA parity tier (1e-4); tf32 = node contraction on tcgen05 (2e-2 tier)")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only")
     ap.add_argument("--skip-roofline", action="store_true", help="profiling runs only")

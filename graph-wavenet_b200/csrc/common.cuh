@@ -24,8 +24,8 @@
 #include "../../include/gwnet_b200.h"
 
 #ifdef GWN_HOST_EMU
-#define GWN_HD
-#define GWN_DEV
+#define GWN_HD inline
+#define GWN_DEV inline
 #define GWN_EMU 1
 #else
 #define GWN_HD __host__ __device__ __forceinline__
@@ -110,12 +110,26 @@ GWN_HD float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 // row (b, t + off_t, n) of a tensor with lon_in = L_in*N rows per sample; off = off_t*N.
 struct Remap {
   int lon_out, lon_in, off;
-  GWN_HD i64 operator()(i64 p) const {
-    i64 b = p / lon_out;
-    i64 r = p - b * lon_out;
-    return b * lon_in + off + r;
+  GWN_HD i64 operator()(i64 p) const {   // positions are < 2^31 (checked on the host): 32-bit division
+    unsigned b = (unsigned)p / (unsigned)lon_out;
+    unsigned r = (unsigned)p - b * (unsigned)lon_out;
+    return (i64)b * lon_in + off + r;
   }
 };
+
+// Division by a channel width that is almost always a power of two (32, 64, 256 ...).
+struct DivW {
+  int d, shift;   // shift >= 0 when d == 1 << shift
+  GWN_HD int div(int k) const { return shift >= 0 ? (k >> shift) : k / d; }
+};
+inline DivW make_divw(int d) {
+  DivW w;
+  w.d = d;
+  w.shift = -1;
+  for (int s = 0; s < 31; ++s)
+    if ((1 << s) == d) w.shift = s;
+  return w;
+}
 inline Remap make_remap(int L_out, int L_in, int off_t, int N) { return Remap{L_out * N, L_in * N, off_t * N}; }
 inline Remap identity_remap() { return Remap{1 << 30, 1 << 30, 0}; }
 

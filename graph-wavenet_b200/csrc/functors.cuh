@@ -85,6 +85,7 @@ struct EpSlab {
     }
     st4(y[bz_] + idx, r);
   }
+  template <int MATH>
   GWN_DEV void finish(float*, int) const {}
 };
 
@@ -95,13 +96,15 @@ struct LdRows {
   const float* p[MAXSEG];
   Remap rm[MAXSEG];
   int wd, use_remap;
+  DivW wdiv;         // set by set_wd()
   const float* ac;   // nullable BN fold: x*ac[ci] + ac[wd+ci]
   DropoutSrc drop;   // single-segment only
+  void set_wd(int w) { wd = w; wdiv = make_divw(w); }
   GWN_HD void init(int) {}
   GWN_HD void load4(float (&v)[4], int k, i64 m, int K, i64 M) const {
     zero4(v);
     if (k >= K || m >= M) return;
-    int q = k / wd, ci = k - q * wd;
+    int q = wdiv.div(k), ci = k - q * wd;
     i64 row = use_remap ? rm[q](m) : m;
     i64 e = row * wd + ci;
     get4(v, ld4(p[q] + e));
@@ -125,8 +128,10 @@ struct LdCols {
   const float* p[MAXSEG];
   Remap rm[MAXSEG];
   int wd, nseg, use_remap, ones;
+  DivW wdiv;
   const float* ac;
   DropoutSrc drop;
+  void set_wd(int w) { wd = w; wdiv = make_divw(w); }
   GWN_HD void init(int) {}
   GWN_HD void load4(float (&v)[4], int k, i64 x, int K, i64 X) const {
     zero4(v);
@@ -135,7 +140,7 @@ struct LdCols {
       if (ones) v[0] = 1.0f;
       return;
     }
-    int q = (int)(x / wd), ci = (int)(x - (i64)q * wd);
+    int q = wdiv.div((int)x), ci = (int)x - q * wd;
     i64 row = use_remap ? rm[q]((i64)k) : (i64)k;
     i64 e = row * wd + ci;
     get4(v, ld4(p[q] + e));
@@ -206,11 +211,13 @@ struct LdWK {
   static constexpr bool kInner = true;
   const float* p[MAXSEG];
   int wd, ldw;
+  DivW wdiv;
+  void set_wd(int w) { wd = w; wdiv = make_divw(w); }
   GWN_HD void init(int) {}
   GWN_HD void load4(float (&v)[4], int k, i64 n, int K, i64 N) const {
     zero4(v);
     if (k >= K || n >= N) return;
-    int q = k / wd, kk = k - q * wd;
+    int q = wdiv.div(k), kk = k - q * wd;
     const float* w = p[q] + n * ldw + kk;
     if (k + 3 < K) {
       get4(v, ld4(w));
@@ -227,11 +234,13 @@ struct LdWN {
   static constexpr bool kInner = false;
   const float* p[MAXSEG];
   int wd, ldw;
+  DivW wdiv;
+  void set_wd(int w) { wd = w; wdiv = make_divw(w); }
   GWN_HD void init(int) {}
   GWN_HD void load4(float (&v)[4], int k, i64 n, int K, i64 N) const {
     zero4(v);
     if (k >= K || n >= N) return;
-    int q = (int)(n / wd), nn = (int)(n - (i64)q * wd);
+    int q = wdiv.div((int)n), nn = (int)n - q * wd;
     const float* w = p[q] + (i64)k * ldw + nn;
     if (n + 3 < N) {
       get4(v, ld4(w));
@@ -289,6 +298,8 @@ struct EpRows {
   i64 ldy, M;
   const float* bias[MAXSEG];
   int nbias, relu, seg_wd;
+  DivW segdiv;
+  void set_seg(int w) { seg_wd = w; segdiv = make_divw(w); }
   const float* gate;  // nullable: multiply by (gate[m*ldy+n] > 0)
   GWN_HD void init(int) {}
   GWN_HD void store4(i64 m, int n, const float (&v)[4], int nvalid, int) const {
@@ -302,7 +313,7 @@ struct EpRows {
       for (int i = 0; i < 4; ++i) r[i] = fmaxf(r[i], 0.0f);
     i64 idx;
     if (seg_wd > 0) {
-      int q = n / seg_wd;
+      int q = segdiv.div(n);
       idx = ((i64)q * M + m) * seg_wd + (n - q * seg_wd);
     } else {
       idx = m * ldy + n;
@@ -317,6 +328,7 @@ struct EpRows {
       for (int i = 0; i < nvalid; ++i) y[idx + i] = r[i];
     }
   }
+  template <int MATH>
   GWN_DEV void finish(float*, int) const {}
 };
 
@@ -335,6 +347,7 @@ struct EpNCHW {
     int t = r / N, node = r - t * N;
     for (int i = 0; i < nvalid; ++i) y[b * sb + (n + i) * so + node * sn + t * st] = v[i] + bias[n + i];
   }
+  template <int MATH>
   GWN_DEV void finish(float*, int) const {}
 };
 
@@ -352,6 +365,7 @@ struct EpGate {
     y[m * D + ch] = o0;
     if (nvalid == 4) y[m * D + ch + 1] = tanhf(v[2] + bf[ch + 1]) * sigmoidf_(v[3] + bg[ch + 1]);
   }
+  template <int MATH>
   GWN_DEV void finish(float*, int) const {}
 };
 
@@ -376,32 +390,66 @@ struct EpGateBwd {
     one(m, ch, v[0], v[1], o);
     if (nvalid == 4) one(m, ch + 1, v[2], v[3], o + 2);
   }
+  template <int MATH>
   GWN_DEV void finish(float*, int) const {}
 };
 
 // Column partial sums (two per column) reduced over the block, then added to global doubles.
 template <class T>
 struct ColStats {
-  float s1[T::TN], s2[T::TN];
+  float s1[T::SLOTS * 4], s2[T::SLOTS * 4];   // indexed by (slot, i): the 4-wide column groups this thread owns
   GWN_HD void reset() {
 #pragma unroll
-    for (int i = 0; i < T::TN; ++i) s1[i] = s2[i] = 0.0f;
+    for (int i = 0; i < T::SLOTS * 4; ++i) s1[i] = s2[i] = 0.0f;
   }
+  template <int MATH>
   GWN_DEV void reduce(float* smem, int tid, double* g1, double* g2, int ncols) {
 #if !GWN_EMU
     float* c1 = smem;
     float* c2 = smem + T::BN;
     for (int i = tid; i < 2 * T::BN; i += T::NT) smem[i] = 0.0f;
     __syncthreads();
-    const int tx = tid % T::TX;
+    // Lanes of a warp that own the same columns are summed with shuffles first; a float atomicAdd on shared
+    // memory is a CAS loop, and 16 lanes hitting one address made it 40 % of this kernel's instructions.
+    const int lane = tid & 31;
+    if (MATH == 0) {
+      const int tx = tid % T::TX;
 #pragma unroll
-    for (int gn = 0; gn < T::GN; ++gn)
+      for (int gn = 0; gn < T::GN; ++gn)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int col = gn * (T::BN / T::GN) + tx * 4 + j;
-        atomicAdd(c1 + col, s1[gn * 4 + j]);
-        atomicAdd(c2 + col, s2[gn * 4 + j]);
-      }
+        for (int j = 0; j < 4; ++j) {
+          float a = s1[gn * 4 + j], b = s2[gn * 4 + j];
+#pragma unroll
+          for (int o = T::TX; o < 32; o <<= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+          }
+          if (T::TX >= 32 || lane < T::TX) {
+            int col = gn * (T::BN / T::GN) + tx * 4 + j;
+            atomicAdd(c1 + col, a);
+            atomicAdd(c2 + col, b);
+          }
+        }
+    } else {   // tensor mode: slot = n8 tile of the warp; lanes with equal (lane >> 1) & 1 own the same 4 columns
+      const int wn = (tid >> 5) / T::WM, t = tid & 3;
+#pragma unroll
+      for (int sl = 0; sl < T::NTL; ++sl)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a = s1[sl * 4 + j], b = s2[sl * 4 + j];
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            if (o == 2) continue;
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+          }
+          if ((lane & 29) == 0) {
+            int col = wn * T::WTN + sl * 8 + (t >> 1) * 4 + j;
+            atomicAdd(c1 + col, a);
+            atomicAdd(c2 + col, b);
+          }
+        }
+    }
     __syncthreads();
     const int n0 = blockIdx.y * T::BN;
     for (int i = tid; i < T::BN; i += T::NT) {
@@ -458,8 +506,9 @@ struct EpMlp {
 #endif
     }
   }
+  template <int MATH>
   GWN_DEV void finish(float* smem, int tid) {
-    if (stats) cs.reduce(smem, tid, stats, stats + C, C);
+    if (stats) cs.template reduce<MATH>(smem, tid, stats, stats + C, C);
   }
 };
 
@@ -505,8 +554,9 @@ struct EpTcnDgrad {
       }
     }
   }
+  template <int MATH>
   GWN_DEV void finish(float* smem, int tid) {
-    if (uprev) cs.reduce(smem, tid, bsum, bsum + C, C);
+    if (uprev) cs.template reduce<MATH>(smem, tid, bsum, bsum + C, C);
   }
 };
 
@@ -517,18 +567,21 @@ struct EpWgrad {
   float* dw[MAXSEG];
   float* db[MAXSEG];
   int wd, nseg, ldw, nbias;
+  DivW wdiv;
+  void set_wd(int w) { wd = w; wdiv = make_divw(w); }
   GWN_HD void init(int) {}
   GWN_HD void store4(i64 m, int n, const float (&v)[4], int nvalid, int) const {
     for (int i = 0; i < nvalid; ++i) {
       int nn = n + i;
       if (nn < nseg * wd) {
-        int q = nn / wd;
+        int q = wdiv.div(nn);
         atomic_add_f(dw[q] + m * ldw + (nn - q * wd), v[i]);
       } else {
         for (int q = 0; q < nbias; ++q) atomic_add_f(db[q] + m, v[i]);
       }
     }
   }
+  template <int MATH>
   GWN_DEV void finish(float*, int) const {}
 };
 
@@ -553,6 +606,7 @@ struct EpWgradTcn {
       }
     }
   }
+  template <int MATH>
   GWN_DEV void finish(float*, int) const {}
 };
 
@@ -565,6 +619,7 @@ struct EpAtomicMat {
   GWN_HD void store4(i64 m, int n, const float (&v)[4], int nvalid, int) const {
     for (int i = 0; i < nvalid; ++i) atomic_add_f(y + m * ld + n + i, v[i]);
   }
+  template <int MATH>
   GWN_DEV void finish(float*, int) const {}
 };
 
@@ -573,16 +628,17 @@ struct LdSlabK {
   static constexpr bool kInner = true;
   const float* p[MAXSUP];
   int V, C;
-  i64 kper;   // slabs*C per pair
+  int kper;   // slabs*C per pair (< 2^31, checked on the host)
+  DivW cdiv;
   GWN_HD void init(int) {}
   GWN_HD void load4(float (&v)[4], int k, i64 m, int K, i64 M) const {
     zero4(v);
     if (k >= K || m >= M) return;
-    int pr = (int)(k / kper);
-    i64 kk = k - (i64)pr * kper;
-    i64 slab = kk / C;
-    int c = (int)(kk - slab * C);
-    get4(v, ld4(p[pr] + (slab * V + m) * C + c));
+    int pr = 0, kk = k;
+    while (kk >= kper) { kk -= kper; ++pr; }   // a handful of pairs at most
+    int slab = cdiv.div(kk);
+    int c = kk - slab * C;
+    get4(v, ld4(p[pr] + ((i64)slab * V + (int)m) * C + c));
   }
 };
 

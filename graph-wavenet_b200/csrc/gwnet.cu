@@ -12,6 +12,11 @@ namespace gwn {
 static thread_local char g_err[1024] = "";
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static thread_local int g_math = 0;
+int current_math() { return g_math; }
+void set_current_math(int m) { g_math = m; }
+// gwn_precision -> GEMM math mode (gemm.cuh)
+static int math_of(int precision) { return precision == GWN_PREC_TF32 ? 1 : (precision == GWN_PREC_FP32X3 ? 3 : 0); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -107,9 +112,9 @@ static int build_plan(gwn_plan* p) {
                     c.end_channels % 4 == 0,
                 "plan: channel counts must be multiples of 4");
   GWN_CHECK_ARG(c.blocks >= 1 && c.layers >= 1 && c.blocks * c.layers <= MAXSEG, "plan: blocks*layers must be in [1,%d]", MAXSEG);
-  GWN_CHECK_ARG(c.precision == GWN_PREC_FP32 || c.precision == GWN_PREC_TF32, "plan: precision %d not available in this build",
-                c.precision);
-  GWN_CHECK_ARG(c.precision == GWN_PREC_FP32 || !c.gcn || c.dilation_channels == 32,
+  GWN_CHECK_ARG(c.precision == GWN_PREC_FP32 || c.precision == GWN_PREC_TF32 || c.precision == GWN_PREC_FP32X3,
+                "plan: precision %d not available in this build", c.precision);
+  GWN_CHECK_ARG(c.precision != GWN_PREC_TF32 || !c.gcn || c.dilation_channels == 32,
                 "plan: the tcgen05 (tf32) tier needs dilation_channels == 32");
   GWN_CHECK_ARG(c.order >= 1 && c.order <= MAXSUP, "plan: order must be in [1,%d]", MAXSUP);
   GWN_CHECK_ARG(c.dropout >= 0.f && c.dropout < 1.f, "plan: dropout must be in [0,1)");
@@ -289,7 +294,7 @@ static LdRows tcn_rows(const gwn_plan* p, const float* prev, const float* prev_a
   a.p[0] = prev; a.p[1] = prev;
   a.rm[0] = make_remap(p->L[i], p->Lin(i), 0, N);
   a.rm[1] = make_remap(p->L[i], p->Lin(i), p->dil[i], N);
-  a.wd = p->c.residual_channels;
+  a.set_wd(p->c.residual_channels);
   a.use_remap = 1;
   a.ac = prev_ac;
   return a;
@@ -301,6 +306,7 @@ static DropoutSrc layer_dropout(const gwn_plan* p, int training, int mode, const
 }
 
 static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
+  MathScope math_scope(math_of(p->c.precision));
   GWN_TRY(require_device());
   GWN_TRY(check_ptr_table(p, a->params));
   GWN_CHECK_ARG(a->input && a->output && a->workspace, "forward: null input/output/workspace");
@@ -406,8 +412,8 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
       lb.p[i] = P_<float>(prm, p->li[i].sw);
       ep.bias[i] = P_<float>(prm, p->li[i].sb);
     }
-    la.wd = D; la.use_remap = 1;
-    lb.wd = D; lb.ldw = D;
+    la.set_wd(D); la.use_remap = 1;
+    lb.set_wd(D); lb.ldw = D;
     ep.y = ws + p->o_skip; ep.ldy = Sk; ep.M = PT; ep.nbias = nL; ep.relu = 1;
     GemmShape sh{PT, Sk, nL * D, 1, 1};
     GWN_TRY((launch_gemm<TBig>(la, lb, ep, sh, st)));
@@ -415,10 +421,10 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
   {
     LdRows la;
     memset(&la, 0, sizeof(la));
-    la.p[0] = ws + p->o_skip; la.wd = Sk;
+    la.p[0] = ws + p->o_skip; la.set_wd(Sk);
     LdWK lb;
     memset(&lb, 0, sizeof(lb));
-    lb.p[0] = P_<float>(prm, p->i_e1w); lb.wd = Sk; lb.ldw = Sk;
+    lb.p[0] = P_<float>(prm, p->i_e1w); lb.set_wd(Sk); lb.ldw = Sk;
     EpRows ep;
     memset(&ep, 0, sizeof(ep));
     ep.y = ws + p->o_e1; ep.ldy = E; ep.M = PT; ep.bias[0] = P_<float>(prm, p->i_e1b); ep.nbias = 1; ep.relu = 1;
@@ -428,10 +434,10 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
   {
     LdRows la;
     memset(&la, 0, sizeof(la));
-    la.p[0] = ws + p->o_e1; la.wd = E;
+    la.p[0] = ws + p->o_e1; la.set_wd(E);
     LdWK lb;
     memset(&lb, 0, sizeof(lb));
-    lb.p[0] = P_<float>(prm, p->i_e2w); lb.wd = E; lb.ldw = E;
+    lb.p[0] = P_<float>(prm, p->i_e2w); lb.set_wd(E); lb.ldw = E;
     EpNCHW ep;
     ep.y = a->output; ep.bias = P_<float>(prm, p->i_e2b); ep.N = N; ep.T = p->T_out;
     ep.sb = (i64)c.out_dim * N * p->T_out; ep.so = (i64)N * p->T_out; ep.sn = p->T_out; ep.st = 1;
@@ -442,6 +448,7 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
 }
 
 static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
+  MathScope math_scope(math_of(p->c.precision));
   GWN_TRY(require_device());
   GWN_TRY(check_ptr_table(p, a->params));
   GWN_CHECK_ARG(a->grad_output && a->workspace && a->scratch && a->grad_flat && a->input, "backward: null argument");
@@ -491,10 +498,10 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
   {  // (a) de1 = (dout . W2) * (e1 > 0)
     LdRows la;
     memset(&la, 0, sizeof(la));
-    la.p[0] = dout; la.wd = p->ldo;
+    la.p[0] = dout; la.set_wd(p->ldo);
     LdWN lb;
     memset(&lb, 0, sizeof(lb));
-    lb.p[0] = P_<float>(prm, p->i_e2w); lb.wd = E; lb.ldw = E;
+    lb.p[0] = P_<float>(prm, p->i_e2w); lb.set_wd(E); lb.ldw = E;
     EpRows ep;
     memset(&ep, 0, sizeof(ep));
     ep.y = de1; ep.ldy = E; ep.M = PT; ep.gate = e1;
@@ -504,23 +511,23 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
   {  // (b) dW2, db2
     LdCols la;
     memset(&la, 0, sizeof(la));
-    la.p[0] = dout; la.wd = p->ldo; la.nseg = 1;
+    la.p[0] = dout; la.set_wd(p->ldo); la.nseg = 1;
     LdCols lb;
     memset(&lb, 0, sizeof(lb));
-    lb.p[0] = e1; lb.wd = E; lb.nseg = 1; lb.ones = 1;
+    lb.p[0] = e1; lb.set_wd(E); lb.nseg = 1; lb.ones = 1;
     EpWgrad ep;
     memset(&ep, 0, sizeof(ep));
-    ep.dw[0] = G(p->i_e2w); ep.db[0] = G(p->i_e2b); ep.wd = E; ep.nseg = 1; ep.ldw = E; ep.nbias = 1;
+    ep.dw[0] = G(p->i_e2w); ep.db[0] = G(p->i_e2b); ep.set_wd(E); ep.nseg = 1; ep.ldw = E; ep.nbias = 1;
     GemmShape sh{(i64)O, E + 1, (int)PT, pick_ksplit(O, E + 1, PT, TW32::BM, TW32::BN, kTargetBlocks), 1};
     GWN_TRY((launch_gemm<TW32>(la, lb, ep, sh, st)));
   }
   {  // (c) dskip = (de1 . W1) * (skip > 0)
     LdRows la;
     memset(&la, 0, sizeof(la));
-    la.p[0] = de1; la.wd = E;
+    la.p[0] = de1; la.set_wd(E);
     LdWN lb;
     memset(&lb, 0, sizeof(lb));
-    lb.p[0] = P_<float>(prm, p->i_e1w); lb.wd = Sk; lb.ldw = Sk;
+    lb.p[0] = P_<float>(prm, p->i_e1w); lb.set_wd(Sk); lb.ldw = Sk;
     EpRows ep;
     memset(&ep, 0, sizeof(ep));
     ep.y = dskip; ep.ldy = Sk; ep.M = PT; ep.gate = skip;
@@ -530,20 +537,20 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
   {  // (d) dW1, db1
     LdCols la;
     memset(&la, 0, sizeof(la));
-    la.p[0] = de1; la.wd = E; la.nseg = 1;
+    la.p[0] = de1; la.set_wd(E); la.nseg = 1;
     LdCols lb;
     memset(&lb, 0, sizeof(lb));
-    lb.p[0] = skip; lb.wd = Sk; lb.nseg = 1; lb.ones = 1;
+    lb.p[0] = skip; lb.set_wd(Sk); lb.nseg = 1; lb.ones = 1;
     EpWgrad ep;
     memset(&ep, 0, sizeof(ep));
-    ep.dw[0] = G(p->i_e1w); ep.db[0] = G(p->i_e1b); ep.wd = Sk; ep.nseg = 1; ep.ldw = Sk; ep.nbias = 1;
+    ep.dw[0] = G(p->i_e1w); ep.db[0] = G(p->i_e1b); ep.set_wd(Sk); ep.nseg = 1; ep.ldw = Sk; ep.nbias = 1;
     GemmShape sh{(i64)E, Sk + 1, (int)PT, pick_ksplit(E, Sk + 1, PT, TBig::BM, TBig::BN, kTargetBlocks), 1};
     GWN_TRY((launch_gemm<TBig>(la, lb, ep, sh, st)));
   }
   {  // (e) skip conv weight / bias gradients of every layer; (f) gradient into the live columns of every g_i
     LdCols la;
     memset(&la, 0, sizeof(la));
-    la.p[0] = dskip; la.wd = Sk; la.nseg = 1;
+    la.p[0] = dskip; la.set_wd(Sk); la.nseg = 1;
     LdCols lb;
     memset(&lb, 0, sizeof(lb));
     EpWgrad ep;
@@ -557,18 +564,18 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
       ep.db[i] = G(p->li[i].sb);
       lw.p[i] = P_<float>(prm, p->li[i].sw);
     }
-    lb.wd = D; lb.nseg = nL; lb.use_remap = 1; lb.ones = 1;
-    ep.wd = D; ep.nseg = nL; ep.ldw = D; ep.nbias = nL;
+    lb.set_wd(D); lb.nseg = nL; lb.use_remap = 1; lb.ones = 1;
+    ep.set_wd(D); ep.nseg = nL; ep.ldw = D; ep.nbias = nL;
     GemmShape sh{(i64)Sk, nL * D + 1, (int)PT, pick_ksplit(Sk, nL * D + 1, PT, TBig::BM, TBig::BN, kTargetBlocks), 1};
     GWN_TRY((launch_gemm<TBig>(la, lb, ep, sh, st)));
 
     LdRows lr;
     memset(&lr, 0, sizeof(lr));
-    lr.p[0] = dskip; lr.wd = Sk;
-    lw.wd = D; lw.ldw = D;
+    lr.p[0] = dskip; lr.set_wd(Sk);
+    lw.set_wd(D); lw.ldw = D;
     EpRows es;
     memset(&es, 0, sizeof(es));
-    es.y = dgh; es.M = PT; es.seg_wd = D;
+    es.y = dgh; es.M = PT; es.set_seg(D);
     GemmShape sh2{PT, nL * D, Sk, 1, 1};
     GWN_TRY((launch_gemm<TBig>(lr, lw, es, sh2, st)));
   }
@@ -644,13 +651,13 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
     {  // filter / gate weight and bias gradients
       LdCols la;
       memset(&la, 0, sizeof(la));
-      la.p[0] = dpre; la.wd = 2 * D; la.nseg = 1;
+      la.p[0] = dpre; la.set_wd(2 * D); la.nseg = 1;
       LdCols lb;
       memset(&lb, 0, sizeof(lb));
       lb.p[0] = prev; lb.p[1] = prev;
       lb.rm[0] = make_remap(p->L[i], p->Lin(i), 0, N);
       lb.rm[1] = make_remap(p->L[i], p->Lin(i), p->dil[i], N);
-      lb.wd = C; lb.nseg = 2; lb.use_remap = 1; lb.ones = 1; lb.ac = prev_ac;
+      lb.set_wd(C); lb.nseg = 2; lb.use_remap = 1; lb.ones = 1; lb.ac = prev_ac;
       EpWgradTcn ep{G(p->li[i].fw), G(p->li[i].gw), G(p->li[i].fb), G(p->li[i].gb), C};
       GWN_CHECK_ARG(Pi < 2147483647LL, "backward: too many positions");
       GemmShape sh{(i64)2 * D, 2 * C + 1, (int)Pi, pick_ksplit(2 * D, 2 * C + 1, Pi, TW64::BM, TW64::BN, kTargetBlocks), 1};
@@ -662,14 +669,14 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
   {
     LdCols la;
     memset(&la, 0, sizeof(la));
-    la.p[0] = cur; la.wd = C; la.nseg = 1;
+    la.p[0] = cur; la.set_wd(C); la.nseg = 1;
     LdInputCols lb;
     lb.in = a->input;
     lb.sb = a->input_strides[0]; lb.sf = a->input_strides[1]; lb.sn = a->input_strides[2]; lb.st = a->input_strides[3];
     lb.F = c.in_dim; lb.N = N; lb.L0 = p->L0; lb.pad = p->pad; lb.ones = 1;
     EpWgrad ep;
     memset(&ep, 0, sizeof(ep));
-    ep.dw[0] = G(p->i_startw); ep.db[0] = G(p->i_startb); ep.wd = c.in_dim; ep.nseg = 1; ep.ldw = c.in_dim; ep.nbias = 1;
+    ep.dw[0] = G(p->i_startw); ep.db[0] = G(p->i_startb); ep.set_wd(c.in_dim); ep.nseg = 1; ep.ldw = c.in_dim; ep.nbias = 1;
     GWN_CHECK_ARG(p->P0() < 2147483647LL, "backward: too many input positions");
     GemmShape sh{(i64)C, c.in_dim + 1, (int)p->P0(), pick_ksplit(C, c.in_dim + 1, p->P0(), TW32::BM, TW32::BN, kTargetBlocks), 1};
     GWN_TRY((launch_gemm<TW32>(la, lb, ep, sh, st)));
@@ -747,6 +754,7 @@ int gwn_node_contract(const float* x, const float* S, int64_t ld, float* y, int 
                       void* stream) {
   GWN_TRY(require_device());
   GWN_CHECK_ARG(x && S && y, "node_contract: null pointer");
+  MathScope math_scope(math_of(precision));
   SupportView sv = SupportView{S, 1, ld, 0};   // op(k, m) = S[m*ld + k]
   TcSupports tcs;
   memset(&tcs, 0, sizeof(tcs));

@@ -256,7 +256,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
+      const bool has_ad = ad != nullptr, has_ad2 = ad2 != nullptr;   // warp-uniform
       for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+        // Addends first -- unconditional, clamped addresses so that the 16 loads issue back to back (per-element
+        // predication made each load its own reconvergence block and serialised their latencies) -- then the
+        // accumulator columns, then the stores.
+        float av[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) av[j] = 0.0f;
+        if (slab_ok && has_ad) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) av[j] = __ldg(ad + (size_t)min(w_base + c0 + j, p.V - 1) * CH);
+        }
+        if (slab_ok && has_ad2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) av[j] += __ldg(ad2 + (size_t)min(w_base + c0 + j, p.V - 1) * CH);
+        }
         uint32_t r[16];
         tc_ld16(taddr + c0, r);
         tc_wait_ld();
@@ -264,12 +279,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int w = w_base + c0 + j;
-            if (w < p.V) {
-              float v = __uint_as_float(r[j]);
-              if (ad) v += ad[(size_t)w * CH];
-              if (ad2) v += ad2[(size_t)w * CH];
-              y[(size_t)w * CH] = v;
-            }
+            if (w < p.V) y[(size_t)w * CH] = __uint_as_float(r[j]) + av[j];
           }
         }
       }

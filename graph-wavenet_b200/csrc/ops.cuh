@@ -10,10 +10,10 @@ namespace gwn {
 typedef Tile<128, 128, 8, 8> TBig;    // node contraction, wide position GEMMs (256 threads)
 typedef Tile<128, 64, 8, 4> TPos64;   // gated conv: N = 2*D = 64 (256 threads)
 typedef Tile<128, 32, 8, 4> TPos32;   // N <= 32 outputs per position (128 threads)
-typedef Tile<32, 128, 4, 4> TW32;     // weight gradients with <= 32 output rows (256 threads)
-typedef Tile<64, 64, 4, 4> TW64;      // small square reductions: gated-conv wgrad, dA (256 threads)
+typedef Tile<32, 128, 4, 4, 32> TW32; // weight gradients with <= 32 output rows (256 threads), BK = 32: more loads in flight
+typedef Tile<64, 64, 4, 4, 32> TW64;  // small square reductions: gated-conv wgrad, dA (256 threads), BK = 32
 
-constexpr int kTargetBlocks = 148 * 3;
+constexpr int kTargetBlocks = 148 * 2;   // split-K reductions: one resident wave (2 blocks of 256 threads per SM)
 
 // One support as the node-contraction A operand: op(k, m) = p[k*ks + m*ms].
 //   forward  y[w] = sum_v A[v,w] x[v]:  k = v, m = w  -> (ks, ms) = (row stride, col stride) of A
@@ -50,8 +50,7 @@ inline int node_gemm(const SupportView* sup, int nsup, bool kcat, const float* c
                      cudaStream_t stream, const TcSupports* tcs = nullptr) {
   GWN_CHECK_ARG(nsup >= 1 && nsup <= MAXSUP, "node_gemm: %d supports (max %d)", nsup, MAXSUP);
   GWN_CHECK_ARG(C % 4 == 0, "node_gemm: channels (%d) must be a multiple of 4", C);
-  if (tcs && tcs->precision != GWN_PREC_FP32) {
-    GWN_CHECK_ARG(tcs->precision == GWN_PREC_TF32, "node_gemm: precision %d not available in this build", tcs->precision);
+  if (tcs && tcs->precision == GWN_PREC_TF32) {
     GWN_CHECK_ARG(C == 32, "node_gemm: the tcgen05 tier needs 32 channels per slab row (got %d)", C);
     GWN_CHECK_ARG(nsup <= TC_MAXSUP, "node_gemm: the tcgen05 tier takes at most %d supports", TC_MAXSUP);
     NodeTcArgs t;
@@ -95,9 +94,10 @@ inline int support_grad_gemm(const float* const* Xp, const float* const* Yp, int
   memset(&b, 0, sizeof(b));
   for (int i = 0; i < npairs; ++i) { a.p[i] = Xp[i]; b.p[i] = Yp[i]; }
   a.V = b.V = V; a.C = b.C = C;
-  a.kper = b.kper = (i64)B * L * C;
-  i64 K = a.kper * npairs;
+  a.cdiv = b.cdiv = make_divw(C);
+  i64 K = (i64)B * L * C * npairs;
   GWN_CHECK_ARG(K < 2147483647LL, "support_grad: K too large");
+  a.kper = b.kper = (int)((i64)B * L * C);
   EpAtomicMat e{dA, ldda};
   GemmShape sh{(i64)V, V, (int)K, pick_ksplit(V, V, K, TW64::BM, TW64::BN, kTargetBlocks), 1};
   return launch_gemm<TW64>(a, b, e, sh, stream);
@@ -124,10 +124,10 @@ inline int mlp_forward(const MlpFwdArgs& m, cudaStream_t stream) {
   LdRows a;
   memset(&a, 0, sizeof(a));
   for (int q = 0; q < m.nseg; ++q) a.p[q] = m.segs[q];
-  a.wd = m.D;
+  a.set_wd(m.D);
   LdWK b;
   memset(&b, 0, sizeof(b));
-  b.p[0] = m.W; b.wd = m.nseg * m.D; b.ldw = m.nseg * m.D;
+  b.p[0] = m.W; b.set_wd(m.nseg * m.D); b.ldw = m.nseg * m.D;
   EpMlp<TPos32> e;
   memset(&e, 0, sizeof(e));
   e.y = m.y; e.bias = m.bias; e.C = m.C_out; e.drop = m.drop; e.res = m.res; e.rrm = m.rrm; e.rac = m.rac; e.stats = m.stats;
@@ -154,27 +154,27 @@ inline int mlp_backward(const MlpBwdArgs& m, cudaStream_t stream) {
   if (m.dsegs) {
     LdRows a;
     memset(&a, 0, sizeof(a));
-    a.p[0] = m.dh; a.wd = m.C_out; a.drop = m.drop;
+    a.p[0] = m.dh; a.set_wd(m.C_out); a.drop = m.drop;
     LdWN b;
     memset(&b, 0, sizeof(b));
-    b.p[0] = m.W; b.wd = Ktot; b.ldw = Ktot;
+    b.p[0] = m.W; b.set_wd(Ktot); b.ldw = Ktot;
     EpRows e;
     memset(&e, 0, sizeof(e));
-    e.y = m.dsegs; e.M = m.P; e.seg_wd = m.D;
+    e.y = m.dsegs; e.M = m.P; e.set_seg(m.D);
     GemmShape sh{m.P, Ktot, m.C_out, 1, 1};
     GWN_TRY((launch_gemm<TBig>(a, b, e, sh, stream)));
   }
   if (m.dW) {
     LdCols a;
     memset(&a, 0, sizeof(a));
-    a.p[0] = m.dh; a.wd = m.C_out; a.nseg = 1; a.drop = m.drop;
+    a.p[0] = m.dh; a.set_wd(m.C_out); a.nseg = 1; a.drop = m.drop;
     LdCols b;
     memset(&b, 0, sizeof(b));
     for (int q = 0; q < m.nseg; ++q) b.p[q] = m.segs[q];
-    b.wd = m.D; b.nseg = m.nseg; b.ones = 1;
+    b.set_wd(m.D); b.nseg = m.nseg; b.ones = 1;
     EpWgrad e;
     memset(&e, 0, sizeof(e));
-    e.dw[0] = m.dW; e.db[0] = m.dbias; e.wd = Ktot; e.nseg = 1; e.ldw = Ktot; e.nbias = 1;
+    e.dw[0] = m.dW; e.db[0] = m.dbias; e.set_wd(Ktot); e.nseg = 1; e.ldw = Ktot; e.nbias = 1;
     GWN_CHECK_ARG(m.P < 2147483647LL, "mlp bwd: too many positions");
     GemmShape sh{(i64)m.C_out, Ktot + 1, (int)m.P, pick_ksplit(m.C_out, Ktot + 1, m.P, TW32::BM, TW32::BN, kTargetBlocks), 1};
     GWN_TRY((launch_gemm<TW32>(a, b, e, sh, stream)));

@@ -34,7 +34,7 @@ else:  # imported as top-level ``model`` (the reference's own import style): boo
     _rt = _il.import_module(_name + ".runtime")
     _PlanRunner, _make_config = _rt.PlanRunner, _rt.make_config
 
-_PRECISIONS = {"fp32": _N.PREC_FP32, "tf32": _N.PREC_TF32, "bf16": _N.PREC_BF16}
+_PRECISIONS = {"fp32": _N.PREC_FP32, "tf32": _N.PREC_TF32, "fp32x3": _N.PREC_FP32X3}
 
 
 def _default_precision() -> int:

@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libgwnet_b200.so")
 
-PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
+PREC_FP32, PREC_TF32, PREC_BF16, PREC_FP32X3 = 0, 1, 2, 3
 DROPOUT_NONE, DROPOUT_MASK, DROPOUT_PHILOX = 0, 1, 2
 
 c_float_p = C.POINTER(C.c_float)

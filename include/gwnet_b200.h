@@ -46,8 +46,10 @@ typedef enum gwn_status {
 /* Precision of the contractions (storage is always fp32). */
 typedef enum gwn_precision {
   GWN_PREC_FP32 = 0,  /* fp32 FMA everywhere: the 1e-4 parity tier                 */
-  GWN_PREC_TF32 = 1,  /* node contraction on tcgen05 kind::tf32 (fp32 accumulate)   */
-  GWN_PREC_BF16 = 2   /* node contraction on tcgen05 kind::f16/bf16 (2e-2 tier)     */
+  GWN_PREC_TF32 = 1,  /* node contraction on tcgen05 kind::tf32, other contractions
+                         single-pass TF32 mma.sync; fp32 accumulate (2e-2 tier)     */
+  GWN_PREC_BF16 = 2,  /* reserved: bf16 operands (not in this build)                 */
+  GWN_PREC_FP32X3 = 3 /* fp32-grade on the tensor cores: 3xTF32 split (mma.sync)     */
 } gwn_precision;
 
 /* Dropout source for gcn (model.py:54). */

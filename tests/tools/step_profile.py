@@ -14,7 +14,7 @@ gen = torch.Generator().manual_seed(0)
 sup = [s.to(dev) for s in O.synthetic_supports(207, 0.05, gen)]
 torch.manual_seed(999)
 tr = E.trainer(StandardScaler(54.0, 20.0), 2, 12, 207, 32, 0.3, 1e-3, 1e-4, dev, sup, True, True, None)
-tr.model.precision = {"fp32": 0, "tf32": 1}[prec]
+tr.model.precision = {"fp32": 0, "tf32": 1, "fp32x3": 3}[prec]
 x, y = O.synthetic_batch(64, 207, 12, 2, gen)
 x, y = x.to(dev), y.to(dev)
 for _ in range(5):
