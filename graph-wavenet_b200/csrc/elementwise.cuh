@@ -243,9 +243,17 @@ GWN_GLOBAL bn_eval_kernel(const float* gamma, const float* beta, const float* rm
 }
 // BatchNorm backward apply, in place on dy:  du = a*(dy - S1/n - xhat*S2/n)  (train) | a*dy (eval);
 // also emits dgamma = S2, dbeta = S1.
+// `dh` (nullable) additionally receives du * dropout-keep, the gradient wrt the pre-dropout mlp output, so that the
+// mlp gradient GEMMs need not regenerate the mask (i is visited in groups of 4 consecutive elements per thread).
 GWN_GLOBAL bn_bwd_apply_kernel(float* dy, const float* u, const float* ac, const float* mr, const double* bsum,
-                               double count, int training, float* dgamma, float* dbeta, i64 P, int C) {
-  GWN_FOR_EACH(i, P * C) {
+                               double count, int training, float* dgamma, float* dbeta, i64 P, int C, float* dh,
+                               DropoutSrc drop) {
+  GWN_FOR_EACH(i4, P * C / 4) {
+    float kp[4] = {1.f, 1.f, 1.f, 1.f};
+    if (dh) drop.keep4(i4 * 4, kp);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+    const i64 i = i4 * 4 + j;
     int c = (int)(i % C);
     float a = ac[c];
     float g = dy[i];
@@ -258,9 +266,11 @@ GWN_GLOBAL bn_bwd_apply_kernel(float* dy, const float* u, const float* ac, const
       r = a * g;
     }
     dy[i] = r;
+    if (dh) dh[i] = r * kp[j];
     if (i < C) {
       dgamma[i] = (float)bsum[C + i];
       dbeta[i] = (float)bsum[i];
+    }
     }
   }
 }

@@ -93,7 +93,7 @@ struct gwn_plan {
   gwn::i64 o_sup, o_supT, o_x0, o_skip, o_e1, fwd_floats;
   std::vector<gwn::i64> o_g, o_u, o_ac, o_mr, o_sums;
   // backward scratch offsets (floats)
-  gwn::i64 o_buf0, o_buf1, o_dsegs, o_dg, o_dpre, o_dgh, o_dout, o_de1, o_dskip, o_dA, o_dR, o_bsum, bwd_floats;
+  gwn::i64 o_buf0, o_buf1, o_dh, o_dsegs, o_dg, o_dpre, o_dgh, o_dout, o_de1, o_dskip, o_dA, o_dR, o_bsum, bwd_floats;
   gwn::i64 P(int i) const { return (gwn::i64)c.batch * L[i] * c.num_nodes; }
   gwn::i64 P0() const { return (gwn::i64)c.batch * L0 * c.num_nodes; }
   gwn::i64 PT() const { return (gwn::i64)c.batch * T_out * c.num_nodes; }
@@ -252,6 +252,7 @@ static int build_plan(gwn_plan* p) {
   for (int i = 0; i < nL; ++i) maxPi = std::max(maxPi, p->P(i));
   p->o_buf0 = take(maxP * C);
   p->o_buf1 = take(maxP * C);
+  p->o_dh = take(maxPi * C);   // du * dropout keep-mask (gradient wrt the pre-dropout mlp output)
   p->o_dsegs = take(maxPi * D * p->nseg);
   p->o_dg = take(maxPi * D);
   p->o_dpre = take(maxPi * 2 * D);
@@ -298,6 +299,24 @@ static LdRows tcn_rows(const gwn_plan* p, const float* prev, const float* prev_a
   a.use_remap = 1;
   a.ac = prev_ac;
   return a;
+}
+
+// The same operand for posgemm.cuh (tensor-core tiers, C == 32): two K segments = the two taps.
+static ARows tcn_arows(const gwn_plan* p, const float* prev, const float* prev_ac, int i) {
+  ARows a;
+  memset(&a, 0, sizeof(a));
+  const int N = p->c.num_nodes;
+  a.P[0] = prev; a.P[1] = prev;
+  a.rmap[0] = 0; a.rmap[1] = 1;
+  a.rm[0] = rowmap_shift(p->L[i], p->Lin(i), 0, N);
+  a.rm[1] = rowmap_shift(p->L[i], p->Lin(i), p->dil[i], N);
+  a.nseg = 2;
+  a.rs = p->c.residual_channels;
+  a.ac = prev_ac;
+  return a;
+}
+static bool pg_ok(const gwn_plan* p) {
+  return current_math() != 0 && p->c.residual_channels == PG_WD && p->c.dilation_channels == PG_WD;
 }
 
 static DropoutSrc layer_dropout(const gwn_plan* p, int training, int mode, const uint8_t* const* masks, uint64_t seed, int i) {
@@ -366,8 +385,12 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
       LdRows la = tcn_rows(p, prev, prev_ac, i);
       LdWTcn lb{P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw), C};
       EpGate ep{g, P_<float>(prm, p->li[i].fb), P_<float>(prm, p->li[i].gb), D};
-      GemmShape sh{Pi, 2 * D, 2 * C, 1, 1};
-      GWN_TRY((launch_gemm<TPos64>(la, lb, ep, sh, st)));
+      int pst = pg_ok(p) ? launch_posgemm<TPG, 64>(tcn_arows(p, prev, prev_ac, i), lb, ep, Pi, 2 * D, st) : -1;
+      if (pst > 0) return pst;
+      if (pst < 0) {
+        GemmShape sh{Pi, 2 * D, 2 * C, 1, 1};
+        GWN_TRY((launch_gemm<TPos64>(la, lb, ep, sh, st)));
+      }
     }
     const float* segs[MAXSEG];
     for (int q = 0; q < p->nseg; ++q) segs[q] = g + (i64)q * Pi * D;
@@ -595,15 +618,17 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
     const float* dgh_i = dgh + (i64)i * PT * D;
     const float* dgp;   // gradient wrt g_i
     if (live) {
-      GWN_LAUNCH_1D(bn_bwd_apply_kernel, Pi * C, st, cur, ws + p->o_u[i], ws + p->o_ac[i], ws + p->o_mr[i],
+      const DropoutSrc ldrop = layer_dropout(p, training, dmode, a->keep_masks, a->seed, i);
+      const bool use_dh = ldrop.mode != GWN_DROPOUT_NONE;   // materialise du * keep once instead of regenerating masks
+      GWN_LAUNCH_1D(bn_bwd_apply_kernel, Pi * C / 4, st, cur, ws + p->o_u[i], ws + p->o_ac[i], ws + p->o_mr[i],
                     reinterpret_cast<const double*>(sc + p->o_bsum + (i64)i * 4 * C), (double)Pi, training,
-                    G(p->li[i].bnw), G(p->li[i].bnb), Pi, C);
+                    G(p->li[i].bnw), G(p->li[i].bnb), Pi, C, use_dh ? sc + p->o_dh : (float*)nullptr, ldrop);
       const float* segs[MAXSEG];
       for (int q = 0; q < p->nseg; ++q) segs[q] = g + (i64)q * Pi * D;
       MlpBwdArgs m;
       memset(&m, 0, sizeof(m));
-      m.dh = cur;
-      m.drop = layer_dropout(p, training, dmode, a->keep_masks, a->seed, i);
+      m.dh = use_dh ? sc + p->o_dh : cur;
+      m.drop = make_dropout(GWN_DROPOUT_NONE, nullptr, 0, 0, 0.f);
       m.segs = segs; m.nseg = p->nseg; m.P = Pi; m.D = D; m.C_out = C;
       m.W = P_<float>(prm, c.gcn ? p->li[i].mw : p->li[i].rw);
       m.dsegs = dsegs;
@@ -630,8 +655,12 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
       LdRows la = tcn_rows(p, prev, prev_ac, i);
       LdWTcn lb{P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw), C};
       EpGateBwd ep{dpre, dgp, P_<float>(prm, p->li[i].fb), P_<float>(prm, p->li[i].gb), D};
-      GemmShape sh{Pi, 2 * D, 2 * C, 1, 1};
-      GWN_TRY((launch_gemm<TPos64>(la, lb, ep, sh, st)));
+      int pst = pg_ok(p) ? launch_posgemm<TPG, 64>(tcn_arows(p, prev, prev_ac, i), lb, ep, Pi, 2 * D, st) : -1;
+      if (pst > 0) return pst;
+      if (pst < 0) {
+        GemmShape sh{Pi, 2 * D, 2 * C, 1, 1};
+        GWN_TRY((launch_gemm<TPos64>(la, lb, ep, sh, st)));
+      }
     }
     const i64 Pin = (i64)B * p->Lin(i) * N;
     {  // input gradient (+ residual path, + BN-backward sums of the layer below)
@@ -645,8 +674,25 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
         ep.mr = ws + p->o_mr[i - 1];
         ep.bsum = reinterpret_cast<double*>(sc + p->o_bsum + (i64)(i - 1) * 4 * C);
       }
-      GemmShape sh{Pin, C, 4 * D, 1, 1};
-      GWN_TRY((launch_gemm<TPos32>(la, lb, ep, sh, st)));
+      int pst = -1;
+      if (pg_ok(p)) {
+        EpTcnDgrad<TPG> eg;
+        memset(&eg, 0, sizeof(eg));
+        eg.dx = ep.dx; eg.du = ep.du; eg.C = C; eg.N = N; eg.L_in = ep.L_in; eg.L_out = ep.L_out;
+        eg.uprev = ep.uprev; eg.mr = ep.mr; eg.bsum = ep.bsum;
+        ARows ar;
+        memset(&ar, 0, sizeof(ar));
+        for (int q = 0; q < 4; ++q) { ar.P[q] = dpre + (q & 1) * PG_WD; ar.rmap[q] = (unsigned char)(q >> 1); }
+        ar.rm[0] = rowmap_shift(p->Lin(i), p->L[i], 0, N);
+        ar.rm[1] = rowmap_shift(p->Lin(i), p->L[i], -p->dil[i], N);
+        ar.nseg = 4; ar.rs = 2 * D;
+        pst = launch_posgemm<TPG, 32>(ar, lb, eg, Pin, C, st);
+        if (pst > 0) return pst;
+      }
+      if (pst < 0) {
+        GemmShape sh{Pin, C, 4 * D, 1, 1};
+        GWN_TRY((launch_gemm<TPos32>(la, lb, ep, sh, st)));
+      }
     }
     {  // filter / gate weight and bias gradients
       LdCols la;

@@ -4,6 +4,7 @@
 #include "functors.cuh"
 #include "elementwise.cuh"
 #include "nconv_tc.cuh"
+#include "posgemm.cuh"
 
 namespace gwn {
 
@@ -12,6 +13,8 @@ typedef Tile<128, 64, 8, 4> TPos64;   // gated conv: N = 2*D = 64 (256 threads)
 typedef Tile<128, 32, 8, 4> TPos32;   // N <= 32 outputs per position (128 threads)
 typedef Tile<32, 128, 4, 4, 32> TW32; // weight gradients with <= 32 output rows (256 threads), BK = 32: more loads in flight
 typedef Tile<64, 64, 4, 4, 32> TW64;  // small square reductions: gated-conv wgrad, dA (256 threads), BK = 32
+
+typedef Tile<256, 32, 8, 4> TPG;      // epilogue mapping of posgemm.cuh: 8 warps x 32 rows, 32 columns per pass
 
 constexpr int kTargetBlocks = 148 * 2;   // split-K reductions: one resident wave (2 blocks of 256 threads per SM)
 
@@ -121,13 +124,25 @@ inline int mlp_forward(const MlpFwdArgs& m, cudaStream_t stream) {
   GWN_CHECK_ARG(m.nseg >= 1 && m.nseg <= MAXSEG, "mlp: %d segments (max %d)", m.nseg, MAXSEG);
   GWN_CHECK_ARG(m.D % 4 == 0, "mlp: c_in per segment (%d) must be a multiple of 4", m.D);
   GWN_CHECK_ARG((reinterpret_cast<uintptr_t>(m.W) & 15) == 0, "mlp: weight pointer must be 16-byte aligned");
+  LdWK b;
+  memset(&b, 0, sizeof(b));
+  b.p[0] = m.W; b.set_wd(m.nseg * m.D); b.ldw = m.nseg * m.D;
+  if (current_math() != 0 && m.D == PG_WD && m.nseg <= PG_MAXSEG && m.C_out == 32) {   // direct-fragment tensor-core path
+    ARows ar;
+    memset(&ar, 0, sizeof(ar));
+    for (int q = 0; q < m.nseg; ++q) ar.P[q] = m.segs[q];
+    ar.rm[0] = ar.rm[1] = rowmap_identity();
+    ar.nseg = m.nseg; ar.rs = m.D;
+    EpMlp<TPG> eg;
+    memset(&eg, 0, sizeof(eg));
+    eg.y = m.y; eg.bias = m.bias; eg.C = m.C_out; eg.drop = m.drop; eg.res = m.res; eg.rrm = m.rrm; eg.rac = m.rac; eg.stats = m.stats;
+    int st = launch_posgemm<TPG, 32>(ar, b, eg, m.P, m.C_out, stream);
+    if (st >= 0) return st;
+  }
   LdRows a;
   memset(&a, 0, sizeof(a));
   for (int q = 0; q < m.nseg; ++q) a.p[q] = m.segs[q];
   a.set_wd(m.D);
-  LdWK b;
-  memset(&b, 0, sizeof(b));
-  b.p[0] = m.W; b.set_wd(m.nseg * m.D); b.ldw = m.nseg * m.D;
   EpMlp<TPos32> e;
   memset(&e, 0, sizeof(e));
   e.y = m.y; e.bias = m.bias; e.C = m.C_out; e.drop = m.drop; e.res = m.res; e.rrm = m.rrm; e.rac = m.rac; e.stats = m.stats;
@@ -152,17 +167,29 @@ inline int mlp_backward(const MlpBwdArgs& m, cudaStream_t stream) {
                 "mlp bwd: unsupported shape (nseg=%d D=%d C_out=%d)", m.nseg, m.D, m.C_out);
   const int Ktot = m.nseg * m.D;
   if (m.dsegs) {
-    LdRows a;
-    memset(&a, 0, sizeof(a));
-    a.p[0] = m.dh; a.set_wd(m.C_out); a.drop = m.drop;
     LdWN b;
     memset(&b, 0, sizeof(b));
     b.p[0] = m.W; b.set_wd(Ktot); b.ldw = Ktot;
     EpRows e;
     memset(&e, 0, sizeof(e));
     e.y = m.dsegs; e.M = m.P; e.set_seg(m.D);
-    GemmShape sh{m.P, Ktot, m.C_out, 1, 1};
-    GWN_TRY((launch_gemm<TBig>(a, b, e, sh, stream)));
+    int st = -1;
+    if (current_math() != 0 && m.C_out == PG_WD && m.drop.mode == GWN_DROPOUT_NONE && Ktot <= 256) {
+      ARows ar;
+      memset(&ar, 0, sizeof(ar));
+      ar.P[0] = m.dh;
+      ar.rm[0] = ar.rm[1] = rowmap_identity();
+      ar.nseg = 1; ar.rs = m.C_out;
+      st = launch_posgemm<TPG, 32>(ar, b, e, m.P, Ktot, stream);
+      if (st > 0) return st;
+    }
+    if (st < 0) {
+      LdRows a;
+      memset(&a, 0, sizeof(a));
+      a.p[0] = m.dh; a.set_wd(m.C_out); a.drop = m.drop;
+      GemmShape sh{m.P, Ktot, m.C_out, 1, 1};
+      GWN_TRY((launch_gemm<TBig>(a, b, e, sh, stream)));
+    }
   }
   if (m.dW) {
     LdCols a;
