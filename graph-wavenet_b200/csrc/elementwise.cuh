@@ -275,6 +275,57 @@ GWN_GLOBAL bn_bwd_apply_kernel(float* dy, const float* u, const float* ac, const
   }
 }
 
+// ---- weight packing for the tcgen05 position GEMMs (tcpos.cuh): all K-major [N][K] fp32 ----------------------------
+// Gated conv, BatchNorm affine of the layer below folded in:  Wp[2ch+g][tap*C+ci] = W_g[ch][ci][tap] * a[ci];
+// bias_g'[ch] = b_g[ch] + sum_{tap,ci} W_g[ch][ci][tap] * c[ci]      (conv(W, a*u + c) = conv(W*diag(a), u) + W.c)
+GWN_GLOBAL pack_tcn_fwd_kernel(const float* wf, const float* wg, const float* bf, const float* bg, const float* ac, float* Wp,
+                               float* bfp, float* bgp, int D, int C) {
+  GWN_FOR_EACH(n, 2 * D) {
+    const int ch = (int)(n >> 1), g = (int)(n & 1);
+    const float* w = g ? wg : wf;
+    float extra = 0.0f;
+    for (int tap = 0; tap < 2; ++tap)
+      for (int ci = 0; ci < C; ++ci) {
+        const float v = w[((i64)ch * C + ci) * 2 + tap];
+        Wp[n * (2 * C) + tap * C + ci] = ac ? v * ac[ci] : v;
+        if (ac) extra = fmaf(v, ac[C + ci], extra);
+      }
+    (g ? bgp : bfp)[ch] = (g ? bg : bf)[ch] + extra;
+  }
+}
+// Gated conv input gradient:  Wd[ci][tap*2D + j] = W_{j&1}[j>>1][ci][tap]
+GWN_GLOBAL pack_tcn_dgrad_kernel(const float* wf, const float* wg, float* Wd, int D, int C) {
+  GWN_FOR_EACH(i, (i64)C * 4 * D) {
+    const int ci = (int)(i / (4 * D)), k = (int)(i - (i64)ci * 4 * D);
+    const int tap = k / (2 * D), j = k - tap * 2 * D;
+    Wd[i] = ((j & 1) ? wg : wf)[((i64)(j >> 1) * C + ci) * 2 + tap];
+  }
+}
+// Gated-conv weight gradient from the raw tcgen05 reduction (tcred.cuh, kind 1): R[(tap*C+ci)*2D + j] = sum_p u[p+tap][ci] dpre[p][j],
+// S[j] = sum_p dpre[p][j].  With the BatchNorm affine x = a*u + c of the layer below:  dW = a[ci]*R + c[ci]*S,  db = S.
+GWN_GLOBAL tcn_wgrad_finalize_kernel(const float* R, const float* S, const float* ac, float* dwf, float* dwg, float* dbf,
+                                     float* dbg, int D, int C) {
+  GWN_FOR_EACH(i, (i64)2 * D * 2 * C + 2 * D) {
+    if (i < (i64)2 * D * 2 * C) {
+      const int j = (int)(i / (2 * C)), k = (int)(i - (i64)j * 2 * C);
+      const int tap = k / C, ci = k - tap * C;
+      float v = R[(i64)(tap * C + ci) * (2 * D) + j];
+      if (ac) v = ac[ci] * v + ac[C + ci] * S[j];
+      ((j & 1) ? dwg : dwf)[((i64)(j >> 1) * C + ci) * 2 + tap] = v;
+    } else {
+      const int j = (int)(i - (i64)2 * D * 2 * C);
+      ((j & 1) ? dbg : dbf)[j >> 1] = S[j];
+    }
+  }
+}
+// WT[c][r] = W[r][c]
+GWN_GLOBAL transpose_kernel(const float* W, float* WT, int R, int Cc) {
+  GWN_FOR_EACH(i, (i64)R * Cc) {
+    const int c = (int)(i / R), r = (int)(i - (i64)c * R);
+    WT[i] = W[(i64)r * Cc + c];
+  }
+}
+
 // dst[p, c] = (src ? src[p,c] : 0) + (t >= L - T_out ? win[(b, t-(L-T_out), n), c] : 0)
 GWN_GLOBAL add_window_kernel(float* dst, const float* src, const float* win, int B, int L, int N, int C, int T_out) {
   GWN_FOR_EACH(i, (i64)B * L * N * C) {

@@ -402,6 +402,32 @@ struct ColStats {
 #pragma unroll
     for (int i = 0; i < T::SLOTS * 4; ++i) s1[i] = s2[i] = 0.0f;
   }
+  // Row-owner variant (tcpos.cuh): each of the 128 epilogue threads owns whole rows, i.e. holds a partial for every
+  // one of the (<= 32) columns, indexed directly by column.  `etid` = thread index within the 4 epilogue warps.
+  GWN_DEV void reduce_rows(float* smem, int etid, double* g1, double* g2, int ncols) {
+#if !GWN_EMU
+    if (etid < 64) smem[etid] = 0.0f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+    for (int col = 0; col < T::SLOTS * 4; ++col) {
+      float a = s1[col], b = s2[col];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if ((etid & 31) == 0 && col < 32) {
+        atomicAdd(smem + col, a);
+        atomicAdd(smem + 32 + col, b);
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (etid < 32 && etid < ncols) {
+      atomicAdd(g1 + etid, (double)smem[etid]);
+      atomicAdd(g2 + etid, (double)smem[32 + etid]);
+    }
+#endif
+  }
   template <int MATH>
   GWN_DEV void reduce(float* smem, int tid, double* g1, double* g2, int ncols) {
 #if !GWN_EMU
@@ -510,6 +536,9 @@ struct EpMlp {
   GWN_DEV void finish(float* smem, int tid) {
     if (stats) cs.template reduce<MATH>(smem, tid, stats, stats + C, C);
   }
+  GWN_DEV void finish_rows(float* smem, int etid) {
+    if (stats) cs.reduce_rows(smem, etid, stats, stats + C, C);
+  }
 };
 
 // Input gradient of the gated conv + residual path + BatchNorm-backward statistics of the layer below:
@@ -557,6 +586,9 @@ struct EpTcnDgrad {
   template <int MATH>
   GWN_DEV void finish(float* smem, int tid) {
     if (uprev) cs.template reduce<MATH>(smem, tid, bsum, bsum + C, C);
+  }
+  GWN_DEV void finish_rows(float* smem, int etid) {
+    if (uprev) cs.reduce_rows(smem, etid, bsum, bsum + C, C);
   }
 };
 

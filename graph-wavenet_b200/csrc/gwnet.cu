@@ -1,6 +1,7 @@
 // gwnet_b200: whole-network plan (gwn_plan_*) and the op-level C ABI (include/gwnet_b200.h).
 // Replaces gwnet.forward (model.py:175-241) and its autograd graph with explicit fused launches.
 #include "ops.cuh"
+#include "nconv_tc_impl.cuh"
 
 #include <atomic>
 #include <cstdarg>
@@ -91,9 +92,10 @@ struct gwn_plan {
   gwn::i64 grad_floats;
   // forward workspace offsets (floats)
   gwn::i64 o_sup, o_supT, o_x0, o_skip, o_e1, fwd_floats;
-  std::vector<gwn::i64> o_g, o_u, o_ac, o_mr, o_sums;
+  std::vector<gwn::i64> o_g, o_u, o_ac, o_mr, o_sums, o_pack;
+  gwn::i64 pk_wp, pk_bf, pk_bg, pk_wd, pk_wt;   // offsets inside a layer's pack region (tf32 tier)
   // backward scratch offsets (floats)
-  gwn::i64 o_buf0, o_buf1, o_dh, o_dsegs, o_dg, o_dpre, o_dgh, o_dout, o_de1, o_dskip, o_dA, o_dR, o_bsum, bwd_floats;
+  gwn::i64 o_rs, o_buf0, o_buf1, o_dh, o_dsegs, o_dg, o_dpre, o_dgh, o_dout, o_de1, o_dskip, o_dA, o_dR, o_bsum, bwd_floats;
   gwn::i64 P(int i) const { return (gwn::i64)c.batch * L[i] * c.num_nodes; }
   gwn::i64 P0() const { return (gwn::i64)c.batch * L0 * c.num_nodes; }
   gwn::i64 PT() const { return (gwn::i64)c.batch * T_out * c.num_nodes; }
@@ -232,13 +234,20 @@ static int build_plan(gwn_plan* p) {
   p->o_sup = take((i64)std::max(p->S, 1) * N * p->ld);
   p->o_supT = take((i64)std::max(p->S, 1) * N * p->ld);
   p->o_x0 = take(p->P0() * C);
-  p->o_g.resize(nL); p->o_u.resize(nL); p->o_ac.resize(nL); p->o_mr.resize(nL); p->o_sums.resize(nL);
+  p->o_g.resize(nL); p->o_u.resize(nL); p->o_ac.resize(nL); p->o_mr.resize(nL); p->o_sums.resize(nL); p->o_pack.resize(nL);
+  p->pk_wp = 0;
+  p->pk_bf = p->pk_wp + align_up((i64)2 * D * 2 * C);
+  p->pk_bg = p->pk_bf + align_up(D);
+  p->pk_wd = p->pk_bg + align_up(D);
+  p->pk_wt = p->pk_wd + align_up((i64)C * 4 * D);
+  const i64 pack_floats = p->pk_wt + align_up((i64)p->nseg * D * C);
   for (int i = 0; i < nL; ++i) {
     p->o_g[i] = take(p->P(i) * D * p->nseg);  // g_i followed by its hop tensors
     p->o_u[i] = take(p->P(i) * C);
     p->o_ac[i] = take(2 * C);
     p->o_mr[i] = take(2 * C);
     p->o_sums[i] = take(4 * C);               // 2*C doubles
+    p->o_pack[i] = take(pack_floats);         // K-major packed weights for the tcgen05 position GEMMs
   }
   p->o_skip = take(p->PT() * Sk);
   p->o_e1 = take(p->PT() * E);
@@ -250,6 +259,7 @@ static int build_plan(gwn_plan* p) {
   for (int i = 0; i < nL; ++i) maxP = std::max(maxP, p->P(i));
   i64 maxPi = 0;
   for (int i = 0; i < nL; ++i) maxPi = std::max(maxPi, p->P(i));
+  p->o_rs = take((i64)2 * C * 2 * D + 2 * D + 64);   // raw gated-conv weight-gradient accumulators (tf32 tier)
   p->o_buf0 = take(maxP * C);
   p->o_buf1 = take(maxP * C);
   p->o_dh = take(maxPi * C);   // du * dropout keep-mask (gradient wrt the pre-dropout mlp output)
@@ -314,6 +324,19 @@ static ARows tcn_arows(const gwn_plan* p, const float* prev, const float* prev_a
   a.rs = p->c.residual_channels;
   a.ac = prev_ac;
   return a;
+}
+// tcgen05 + TMA position GEMMs: tf32 tier with the reference's default widths.
+static bool tcpos_ok(const gwn_plan* p) {
+  return p->c.precision == GWN_PREC_TF32 && p->c.residual_channels == 32 && p->c.dilation_channels == 32;
+}
+static TcPosArgs tcn_tcpos_args(const gwn_plan* p, const float* prev, const float* Wp, int i) {
+  TcPosArgs t;
+  memset(&t, 0, sizeof(t));
+  const int N = p->c.num_nodes;
+  t.seg[0] = TcPosSeg{prev, p->Lin(i) * N, 32, 0, 0};
+  t.seg[1] = TcPosSeg{prev, p->Lin(i) * N, 32, 0, p->dil[i] * N};
+  t.nseg = 2; t.nb = p->c.batch; t.rows_out = p->L[i] * N; t.Wp = Wp; t.N = 64;
+  return t;
 }
 static bool pg_ok(const gwn_plan* p) {
   return current_math() != 0 && p->c.residual_channels == PG_WD && p->c.dilation_channels == PG_WD;
@@ -385,8 +408,20 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
       LdRows la = tcn_rows(p, prev, prev_ac, i);
       LdWTcn lb{P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw), C};
       EpGate ep{g, P_<float>(prm, p->li[i].fb), P_<float>(prm, p->li[i].gb), D};
-      int pst = pg_ok(p) ? launch_posgemm<TPG, 64>(tcn_arows(p, prev, prev_ac, i), lb, ep, Pi, 2 * D, st) : -1;
-      if (pst > 0) return pst;
+      int pst = -1;
+      if (tcpos_ok(p)) {
+        float* pk = ws + p->o_pack[i];
+        GWN_LAUNCH_1D(pack_tcn_fwd_kernel, 2 * D, st, P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw),
+                      P_<float>(prm, p->li[i].fb), P_<float>(prm, p->li[i].gb), prev_ac, pk + p->pk_wp, pk + p->pk_bf,
+                      pk + p->pk_bg, D, C);
+        EpGate eg{g, pk + p->pk_bf, pk + p->pk_bg, D};
+        pst = launch_tcpos<64>(tcn_tcpos_args(p, prev, pk + p->pk_wp, i), eg, st);
+        if (pst > 0) return pst;
+      }
+      if (pst < 0 && pg_ok(p)) {
+        pst = launch_posgemm<TPG, 64>(tcn_arows(p, prev, prev_ac, i), lb, ep, Pi, 2 * D, st);
+        if (pst > 0) return pst;
+      }
       if (pst < 0) {
         GemmShape sh{Pi, 2 * D, 2 * C, 1, 1};
         GWN_TRY((launch_gemm<TPos64>(la, lb, ep, sh, st)));
@@ -396,6 +431,7 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     for (int q = 0; q < p->nseg; ++q) segs[q] = g + (i64)q * Pi * D;
     MlpFwdArgs m;
     memset(&m, 0, sizeof(m));
+    m.tf32_tc = tcpos_ok(p) ? 1 : 0;
     if (c.gcn) {
       GcnShape gs{B, p->L[i], N, D, C, p->S, c.order};
       GWN_TRY(gcn_hops_forward(gs, g, supF, g + Pi * D, st, &tcF));
@@ -632,6 +668,11 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
       m.segs = segs; m.nseg = p->nseg; m.P = Pi; m.D = D; m.C_out = C;
       m.W = P_<float>(prm, c.gcn ? p->li[i].mw : p->li[i].rw);
       m.dsegs = dsegs;
+      if (tcpos_ok(p)) {
+        float* pk = const_cast<float*>(ws) + p->o_pack[i];
+        GWN_LAUNCH_1D(transpose_kernel, (i64)C * p->nseg * D, st, m.W, pk + p->pk_wt, C, p->nseg * D);
+        m.WT = pk + p->pk_wt;
+      }
       m.dW = G(c.gcn ? p->li[i].mw : p->li[i].rw);
       m.dbias = G(c.gcn ? p->li[i].mb : p->li[i].rb);
       GWN_TRY(mlp_backward(m, st));
@@ -655,7 +696,14 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
       LdRows la = tcn_rows(p, prev, prev_ac, i);
       LdWTcn lb{P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw), C};
       EpGateBwd ep{dpre, dgp, P_<float>(prm, p->li[i].fb), P_<float>(prm, p->li[i].gb), D};
-      int pst = pg_ok(p) ? launch_posgemm<TPG, 64>(tcn_arows(p, prev, prev_ac, i), lb, ep, Pi, 2 * D, st) : -1;
+      int pst = -1;
+      if (tcpos_ok(p) && training) {   // packed weights (BN fold included) were written by the forward pass
+        const float* pk = ws + p->o_pack[i];
+        EpGateBwd eg{dpre, dgp, pk + p->pk_bf, pk + p->pk_bg, D};
+        pst = launch_tcpos<64>(tcn_tcpos_args(p, prev, pk + p->pk_wp, i), eg, st);
+        if (pst > 0) return pst;
+      }
+      if (pst < 0 && pg_ok(p)) pst = launch_posgemm<TPG, 64>(tcn_arows(p, prev, prev_ac, i), lb, ep, Pi, 2 * D, st);
       if (pst > 0) return pst;
       if (pst < 0) {
         GemmShape sh{Pi, 2 * D, 2 * C, 1, 1};
@@ -675,7 +723,22 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
         ep.bsum = reinterpret_cast<double*>(sc + p->o_bsum + (i64)(i - 1) * 4 * C);
       }
       int pst = -1;
-      if (pg_ok(p)) {
+      if (tcpos_ok(p)) {
+        float* pk = const_cast<float*>(ws) + p->o_pack[i];
+        GWN_LAUNCH_1D(pack_tcn_dgrad_kernel, (i64)C * 4 * D, st, P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw),
+                      pk + p->pk_wd, D, C);
+        EpTcnDgrad<TRow> eg;
+        memset(&eg, 0, sizeof(eg));
+        eg.dx = ep.dx; eg.du = ep.du; eg.C = C; eg.N = N; eg.L_in = ep.L_in; eg.L_out = ep.L_out;
+        eg.uprev = ep.uprev; eg.mr = ep.mr; eg.bsum = ep.bsum;
+        TcPosArgs t;
+        memset(&t, 0, sizeof(t));
+        for (int q = 0; q < 4; ++q) t.seg[q] = TcPosSeg{dpre, p->L[i] * N, 2 * D, (q & 1) * 32, -(q >> 1) * p->dil[i] * N};
+        t.nseg = 4; t.nb = B; t.rows_out = p->Lin(i) * N; t.Wp = pk + p->pk_wd; t.N = 32;
+        pst = launch_tcpos<32>(t, eg, st);
+        if (pst > 0) return pst;
+      }
+      if (pst < 0 && pg_ok(p)) {
         EpTcnDgrad<TPG> eg;
         memset(&eg, 0, sizeof(eg));
         eg.dx = ep.dx; eg.du = ep.du; eg.C = C; eg.N = N; eg.L_in = ep.L_in; eg.L_out = ep.L_out;
@@ -694,7 +757,28 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
         GWN_TRY((launch_gemm<TPos32>(la, lb, ep, sh, st)));
       }
     }
-    {  // filter / gate weight and bias gradients
+    bool wgrad_done = false;
+    if (tcpos_ok(p)) {   // tcgen05 + TMA reduction over all positions, then fold the BatchNorm affine of the layer below
+      float* R = sc + p->o_rs;
+      float* S = R + (i64)2 * C * 2 * D;
+      GWN_TRY(dev_memset(R, 0, sizeof(float) * ((i64)2 * C * 2 * D + 2 * D), st));
+      TcRedArgs t;
+      memset(&t, 0, sizeof(t));
+      t.mode = 0; t.na = 2;
+      t.a[0] = TcRedSrc{prev, p->Lin(i) * N, 32, 0, 0};
+      t.a[1] = TcRedSrc{prev, p->Lin(i) * N, 32, 0, p->dil[i] * N};
+      t.b[0] = TcRedSrc{dpre, p->L[i] * N, 2 * D, 0, 0};
+      t.N = 2 * D; t.nb = B; t.rows = p->L[i] * N;
+      t.out.kind = 1; t.out.out = R; t.out.out_bias = S; t.out.nblk_real = 2;
+      int rst = launch_tcred(t, st);
+      if (rst > 0) return rst;
+      if (rst == 0) {
+        GWN_LAUNCH_1D(tcn_wgrad_finalize_kernel, (i64)2 * D * 2 * C + 2 * D, st, (const float*)R, (const float*)S, prev_ac,
+                      G(p->li[i].fw), G(p->li[i].gw), G(p->li[i].fb), G(p->li[i].gb), D, C);
+        wgrad_done = true;
+      }
+    }
+    if (!wgrad_done) {  // filter / gate weight and bias gradients
       LdCols la;
       memset(&la, 0, sizeof(la));
       la.p[0] = dpre; la.set_wd(2 * D); la.nseg = 1;

@@ -5,6 +5,8 @@
 #include "elementwise.cuh"
 #include "nconv_tc.cuh"
 #include "posgemm.cuh"
+#include "tcpos.cuh"
+#include "tcred.cuh"
 
 namespace gwn {
 
@@ -92,6 +94,19 @@ inline int node_gemm(const SupportView* sup, int nsup, bool kcat, const float* c
 inline int support_grad_gemm(const float* const* Xp, const float* const* Yp, int npairs, float* dA, i64 ldda, int B, int L,
                              int V, int C, cudaStream_t stream) {
   GWN_CHECK_ARG(npairs >= 1 && npairs <= MAXSUP, "support_grad: bad pair count %d", npairs);
+  if (current_math() == 1 && C == 32 && V <= 256 && npairs <= TR_MAXSRC && (ldda % 1) == 0) {   // tf32 tier: tcgen05 + TMA
+    TcRedArgs t;
+    memset(&t, 0, sizeof(t));
+    t.mode = 1; t.na = npairs;
+    for (int i = 0; i < npairs; ++i) {
+      t.a[i] = TcRedSrc{Xp[i], V, 32, 0, 0};
+      t.b[i] = TcRedSrc{Yp[i], V, 32, 0, 0};
+    }
+    t.N = round_up(V, 16); t.nb = B * L; t.rows = V;
+    t.out.kind = 2; t.out.out = dA; t.out.ldw = (int)ldda; t.out.V = V;
+    int st = launch_tcred(t, stream);
+    if (st >= 0) return st;
+  }
   LdSlabK a, b;
   memset(&a, 0, sizeof(a));
   memset(&b, 0, sizeof(b));
@@ -119,6 +134,7 @@ struct MlpFwdArgs {
   const float* rac;
   double* stats;             // nullable
   float* y;
+  int tf32_tc;               // 1: tf32 tier -> tcgen05/TMA kernel when the shape allows
 };
 inline int mlp_forward(const MlpFwdArgs& m, cudaStream_t stream) {
   GWN_CHECK_ARG(m.nseg >= 1 && m.nseg <= MAXSEG, "mlp: %d segments (max %d)", m.nseg, MAXSEG);
@@ -127,6 +143,17 @@ inline int mlp_forward(const MlpFwdArgs& m, cudaStream_t stream) {
   LdWK b;
   memset(&b, 0, sizeof(b));
   b.p[0] = m.W; b.set_wd(m.nseg * m.D); b.ldw = m.nseg * m.D;
+  if (m.tf32_tc && m.D == 32 && m.C_out == 32 && m.nseg <= TP_MAXSEG && m.P < 2147483647LL) {   // tcgen05 + TMA path
+    TcPosArgs t;
+    memset(&t, 0, sizeof(t));
+    for (int q = 0; q < m.nseg; ++q) t.seg[q] = TcPosSeg{m.segs[q], (int)m.P, 32, 0, 0};
+    t.nseg = m.nseg; t.nb = 1; t.rows_out = (int)m.P; t.Wp = m.W; t.N = 32;
+    EpMlp<TRow> eg;
+    memset(&eg, 0, sizeof(eg));
+    eg.y = m.y; eg.bias = m.bias; eg.C = m.C_out; eg.drop = m.drop; eg.res = m.res; eg.rrm = m.rrm; eg.rac = m.rac; eg.stats = m.stats;
+    int st = launch_tcpos<32>(t, eg, stream);
+    if (st >= 0) return st;
+  }
   if (current_math() != 0 && m.D == PG_WD && m.nseg <= PG_MAXSEG && m.C_out == 32) {   // direct-fragment tensor-core path
     ARows ar;
     memset(&ar, 0, sizeof(ar));
@@ -161,6 +188,7 @@ struct MlpBwdArgs {
   float* dsegs;               // [nseg][P][D] (written); nullable to skip the data gradient
   float* dW;                  // accumulated (atomic); nullable
   float* dbias;               // accumulated; nullable iff dW is
+  const float* WT;            // nullable: W transposed [nseg*D][C_out] -> tcgen05/TMA input-gradient kernel (tf32 tier)
 };
 inline int mlp_backward(const MlpBwdArgs& m, cudaStream_t stream) {
   GWN_CHECK_ARG(m.nseg >= 1 && m.nseg <= MAXSEG && m.D % 4 == 0 && m.C_out % 4 == 0,
@@ -174,7 +202,15 @@ inline int mlp_backward(const MlpBwdArgs& m, cudaStream_t stream) {
     memset(&e, 0, sizeof(e));
     e.y = m.dsegs; e.M = m.P; e.set_seg(m.D);
     int st = -1;
-    if (current_math() != 0 && m.C_out == PG_WD && m.drop.mode == GWN_DROPOUT_NONE && Ktot <= 256) {
+    if (m.WT && m.C_out == 32 && m.drop.mode == GWN_DROPOUT_NONE && Ktot <= 256 && Ktot % 16 == 0 && m.P < 2147483647LL) {
+      TcPosArgs t;
+      memset(&t, 0, sizeof(t));
+      t.seg[0] = TcPosSeg{m.dh, (int)m.P, 32, 0, 0};
+      t.nseg = 1; t.nb = 1; t.rows_out = (int)m.P; t.Wp = m.WT; t.N = Ktot;
+      st = launch_tcpos<0>(t, e, stream);
+      if (st > 0) return st;
+    }
+    if (st < 0 && current_math() != 0 && m.C_out == PG_WD && m.drop.mode == GWN_DROPOUT_NONE && Ktot <= 256) {
       ARows ar;
       memset(&ar, 0, sizeof(ar));
       ar.P[0] = m.dh;
@@ -190,6 +226,18 @@ inline int mlp_backward(const MlpBwdArgs& m, cudaStream_t stream) {
       GemmShape sh{m.P, Ktot, m.C_out, 1, 1};
       GWN_TRY((launch_gemm<TBig>(a, b, e, sh, stream)));
     }
+  }
+  if (m.dW && current_math() == 1 && m.D == 32 && m.C_out == 32 && m.nseg <= 7 && m.drop.mode == GWN_DROPOUT_NONE &&
+      m.P < 2147483647LL) {   // tf32 tier: tcgen05 + TMA reduction (weights and, through the all-ones block, the bias)
+    TcRedArgs t;
+    memset(&t, 0, sizeof(t));
+    t.mode = 0; t.na = m.nseg;
+    for (int q = 0; q < m.nseg; ++q) t.a[q] = TcRedSrc{m.segs[q], (int)m.P, 32, 0, 0};
+    t.b[0] = TcRedSrc{m.dh, (int)m.P, 32, 0, 0};
+    t.N = 32; t.nb = 1; t.rows = (int)m.P;
+    t.out.kind = 0; t.out.out = m.dW; t.out.out_bias = m.dbias; t.out.ldw = Ktot; t.out.nblk_real = m.nseg;
+    int st = launch_tcred(t, stream);
+    if (st >= 0) return st;
   }
   if (m.dW) {
     LdCols a;

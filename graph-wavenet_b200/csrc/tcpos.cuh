@@ -1,0 +1,261 @@
+// Position GEMM on tcgen05 / TMEM fed by TMA (tf32 tier):
+//
+//     out[m, n] = epilogue( sum_seg sum_k  A_seg[row_seg(m)][col0_seg + k] * Wp[n][seg*32 + k] )
+//
+//   m : BLNC position rows, tiled 128 at a time inside each of `nb` samples (so that a time-shifted source --
+//       the second tap of the dilated conv, or dpre in its input gradient -- is one 3-D TMA box per segment,
+//       out-of-range rows arriving as zeros);  K = nseg x 32;  N = output channels (multiple of 16, <= 256).
+//   A : K-major SWIZZLE_128B tiles [128 rows][32 floats] straight from the fp32 activations (kind::tf32 reads fp32 bits);
+//   Wp: packed weights [N][K] row-major, loaded once per persistent CTA and kept resident in shared memory;
+//   D : fp32 in TMEM, double-buffered; the 4 epilogue warps own one position row per thread and run the same
+//       epilogue functors as the other GEMM paths (store4 / finish_rows).
+//
+// Used for the gated (1,2) conv and its backward recompute, the gcn mlp forward and input gradient, and the
+// gated conv's input gradient -- the HBM-bound convolutions of SURVEY.md §8(a) rows a3, a4, a7, a9.
+#pragma once
+#include "functors.cuh"
+#include "tc_common.cuh"
+
+namespace gwn {
+
+constexpr int TP_MAXSEG = 16;
+
+struct TcPosSeg {
+  const float* src;   // [nb][rows_src][row_width] fp32
+  int rows_src;       // rows per sample in the source
+  int row_width;      // floats per source row (32 or 64)
+  int col0;           // first column of this K segment inside the source row
+  int rshift;         // source row = output row + rshift (may be negative; out-of-range rows read as 0)
+};
+struct TcPosArgs {
+  TcPosSeg seg[TP_MAXSEG];
+  int nseg;
+  int nb;             // samples
+  int rows_out;       // output rows per sample
+  const float* Wp;    // packed weights [N][nseg*32]
+  int N;
+};
+
+// Dummy "tile" for the column-statistics state of row-owner epilogues: 8 slots of 4 columns = 32 columns.
+struct TRow {
+  static constexpr int SLOTS = 8, NTL = 8, BN = 32, NT = 128, TX = 8, GN = 1, WM = 4, WTN = 32, BM = 128;
+};
+
+#if !GWN_EMU
+namespace tc {
+
+constexpr int TP_A_BYTES = 128 * 128;   // one A tile: 128 rows x 32 floats
+
+struct TpMaps {
+  CUtensorMap a[TP_MAXSEG];
+  CUtensorMap w;
+};
+struct TpParams {
+  int nseg, nb, rows_out, tiles_per_sample, total_tiles, N, stages;
+  int col0[TP_MAXSEG], rshift[TP_MAXSEG];
+};
+
+template <class EP, int NCT>   // NCT > 0: compile-time column count (keeps per-slot epilogue state in registers)
+__global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ TpMaps maps, const TpParams p, const EP ep_in) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const int w_bytes = p.nseg * p.N * 128;                 // resident weights: [seg][N rows][128 B]
+  const uint32_t a0 = base + w_bytes;                     // A stages
+  const uint32_t bar0 = a0 + p.stages * TP_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + w_bytes + (size_t)p.stages * TP_A_BYTES);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * p.stages + 2 + a); };
+  const uint32_t w_bar = bar0 + 8u * (2 * p.stages + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 5);
+  float* red = reinterpret_cast<float*>(bars + 2 * p.stages + 6);   // 64 floats for the statistics reduce
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[s]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================== TMA producer
+    mbar_expect_tx(w_bar, (uint32_t)w_bytes);
+    for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + s * p.N * 128, &maps.w, w_bar, s * 32, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_sample, rt = tile - b * p.tiles_per_sample;
+      for (int s = 0; s < p.nseg; ++s) {
+        if (!mbar_wait(empty_bar(stage), phase ^ 1u, 11)) { ok = false; break; }
+        mbar_expect_tx(full_bar(stage), TP_A_BYTES);
+        tma_load_3d(a0 + stage * TP_A_BYTES, &maps.a[s], full_bar(stage), p.col0[s], rt * 128 + p.rshift[s], b);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================================== MMA issuer: D[128 x N] += A[128 x 32] . Wseg[N x 32]^T
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, accphase = 0;
+    bool ok = mbar_wait(w_bar, 0, 12);
+    tc_fence_after();
+    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+      if (!mbar_wait(tempty_bar(acc), accphase ^ 1u, 13)) break;
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+      for (int s = 0; s < p.nseg; ++s) {
+        if (!mbar_wait(full_bar(stage), phase, 14)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t as = a0 + stage * TP_A_BYTES;
+        const uint32_t ws = base + s * p.N * 128;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          // both operands K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart, this k-step 32 B in
+          tc_mma_tf32(d_tmem, make_desc(as + kk * 32, 16, 1024), make_desc(ws + kk * 32, 16, 1024), idesc,
+                      (s > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc_commit(empty_bar(stage));
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      if (!ok) break;
+      tc_commit(tfull_bar(acc));
+      acc ^= 1;
+      if (acc == 0) accphase ^= 1u;
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue: one position row per thread
+    EP ep = ep_in;
+    ep.init(0);
+    const int ew = warp - 4;
+    int acc = 0;
+    uint32_t accphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_sample, rt = tile - b * p.tiles_per_sample;
+      if (!mbar_wait(tfull_bar(acc), accphase, 15)) break;
+      tc_fence_after();
+      const int rl = rt * 128 + ew * 32 + lane;
+      const bool valid = rl < p.rows_out;
+      const i64 m = (i64)b * p.rows_out + rl;
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * 256);
+      const int ncols = NCT > 0 ? NCT : p.N;
+#pragma unroll
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        uint32_t r[16];
+        tc_ld16(taddr + c0, r);
+        tc_wait_ld();
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float v[4] = {__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                __uint_as_float(r[4 * q + 3])};
+            ep.store4(m, c0 + 4 * q, v, 4, (c0 >> 2) + q);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) accphase ^= 1u;
+    }
+    if constexpr (EP::kHasFinish) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      ep.finish_rows(red, threadIdx.x - 128);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+}  // namespace tc
+#endif
+
+// Returns 0 after launching; -1 when the shape is not eligible (caller falls back); > 0 on error.
+template <int NCT, class EP>
+int launch_tcpos(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
+#if GWN_EMU
+  (void)a; (void)ep; (void)stream;
+  return -1;
+#else
+  using namespace tc;
+  if (NCT > 0 && a.N != NCT) return -1;
+  if (a.nseg < 1 || a.nseg > TP_MAXSEG || a.N < 16 || a.N > 256 || a.N % 16 != 0 || a.nb < 1 || a.rows_out < 1) return -1;
+  if (reinterpret_cast<uintptr_t>(a.Wp) & 15) return -1;
+  TpMaps maps;
+  TpParams p;
+  memset(&p, 0, sizeof(p));
+  p.nseg = a.nseg; p.nb = a.nb; p.rows_out = a.rows_out; p.N = a.N;
+  p.tiles_per_sample = (a.rows_out + 127) / 128;
+  const long long tiles = (long long)p.tiles_per_sample * a.nb;
+  if (tiles > 2147483647LL) return -1;
+  p.total_tiles = (int)tiles;
+  const int w_bytes = a.nseg * a.N * 128;
+  p.stages = (SMEM_LIMIT - 2048 - w_bytes) / TP_A_BYTES;
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages < 2) return -1;
+  for (int s = 0; s < a.nseg; ++s) {
+    const TcPosSeg& g = a.seg[s];
+    if ((reinterpret_cast<uintptr_t>(g.src) & 15) || g.row_width % 4 != 0 || g.col0 + 32 > g.row_width) return -1;
+    cuuint64_t d[3] = {(cuuint64_t)g.row_width, (cuuint64_t)g.rows_src, (cuuint64_t)a.nb};
+    cuuint64_t st[2] = {(cuuint64_t)g.row_width * 4, (cuuint64_t)g.rows_src * g.row_width * 4};
+    cuuint32_t box[3] = {32, 128, 1};
+    GWN_TRY(encode(&maps.a[s], g.src, 3, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    p.col0[s] = g.col0;
+    p.rshift[s] = g.rshift;
+  }
+  for (int s = a.nseg; s < TP_MAXSEG; ++s) maps.a[s] = maps.a[0];
+  {
+    const int K = a.nseg * 32;
+    cuuint64_t d[2] = {(cuuint64_t)K, (cuuint64_t)a.N};
+    cuuint64_t st[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)a.N};
+    GWN_TRY(encode(&maps.w, a.Wp, 2, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  const int smem_bytes = w_bytes + p.stages * TP_A_BYTES + 1024 + 512;
+  static cudaError_t attr = cudaFuncSetAttribute(tcpos_kernel<EP, NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  if (attr != cudaSuccess) {
+    set_error("tcpos: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr));
+    return GWN_ERR_CUDA;
+  }
+  static int num_sms = [] {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  tcpos_kernel<EP, NCT><<<grid, 256, smem_bytes, stream>>>(maps, p, ep);
+  GWN_LAUNCH_CHECK();
+  count_launch();
+  return 0;
+#endif
+}
+
+}  // namespace gwn

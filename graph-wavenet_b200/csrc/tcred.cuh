@@ -1,0 +1,297 @@
+// Reduction GEMMs on tcgen05 / TMEM fed by TMA (tf32 tier): the contractions whose K dimension is the huge one
+// (all positions of the batch) and whose output is a small matrix accumulated over the whole batch:
+//
+//   MODE_MN  weight gradients      D[(blk, i), n] = sum_p  A_blk[p][i] * B[p][n]
+//              A: up to 8 blocks of 32 columns taken from position-row tensors (the 7 concatenated gcn inputs,
+//                 or the two taps of the gated conv's input) + one synthetic all-ones block whose rows deliver the
+//                 column sums of B, i.e. the bias gradient;  B: the output gradient rows (dh or dpre), N = 32 or 64.
+//              Both operands are MN-major (positions are K): 32-byte-atom 128B swizzle, like X in nconv_tc.
+//   MODE_K   support gradient      D[v, w] = sum_{slab, c} X[slab][v][c] * T[slab][w][c]      
+//              Both operands K-major (channels are K within a slab), plain 128B swizzle, like tcpos.
+//
+// Each persistent CTA takes a contiguous range of K chunks, accumulates its partial D in TMEM over the whole
+// range (no intermediate epilogues), and adds it to the global result with coalesced red.global.add at the end.
+#pragma once
+#include "functors.cuh"
+#include "tc_common.cuh"
+
+namespace gwn {
+
+constexpr int TR_MAXSRC = 8;
+
+struct TcRedSrc {
+  const float* src;   // [nb][rows_src][row_width]
+  int rows_src, row_width, col0, rshift;
+};
+// Where an accumulator element goes: MODE_MN element (blk, i, n); MODE_K element (v, w).
+struct TcRedOut {
+  int kind;           // 0: mlp wgrad  dW[n*ldw + blk*32 + i], ones block -> db[n]
+                      // 1: raw gated-conv wgrad  R[(blk*32 + i)*64 + n], ones block -> S[n]
+                      // 2: dA[v*ld + w]
+  float* out;
+  float* out_bias;
+  int ldw, nblk_real, V;
+};
+struct TcRedArgs {
+  int mode;           // 0 = MODE_MN, 1 = MODE_K
+  TcRedSrc a[TR_MAXSRC];
+  int na;             // MODE_MN: real A blocks (<= 7; the ones block is appended); MODE_K: number of (X, T) pairs
+  TcRedSrc b[TR_MAXSRC];   // MODE_MN: b[0] only; MODE_K: one per pair
+  int N;              // MODE_MN: 32 or 64; MODE_K: output columns (multiple of 16, <= 256)
+  int nb, rows;       // MODE_MN: samples and B rows per sample; MODE_K: nb = slabs, rows = V
+  TcRedOut out;
+};
+
+#if !GWN_EMU
+namespace tc {
+
+struct TrMaps {
+  CUtensorMap a[TR_MAXSRC];
+  CUtensorMap b[TR_MAXSRC];
+};
+struct TrParams {
+  int mode, na, nblk, mtiles, N, nbn, nb, chunks_per_sample, total_chunks, stages, a_bytes, b_bytes, tx_bytes;
+  int acol0[TR_MAXSRC], arshift[TR_MAXSRC], bcol0[TR_MAXSRC];
+  TcRedOut out;
+};
+
+__global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ TrMaps maps, const TrParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+  const uint32_t st0 = base;
+  const uint32_t bar0 = st0 + p.stages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
+  const uint32_t done_bar = bar0 + 8u * (2 * p.stages);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.mode == 0) {
+    // A blocks that TMA never writes: block `na` of every stage is the all-ones block (its accumulator rows become
+    // the column sums of B = the bias gradient); blocks beyond it are zero.
+    for (int s = 0; s < p.stages; ++s) {
+      float* blk = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + (size_t)p.na * 4096);
+      const int nfill = (p.mtiles * 4 - p.na) * 1024;
+      for (int i = threadIdx.x; i < nfill; i += 256) blk[i] = i < 1024 ? 1.0f : 0.0f;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.na; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[s]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[0]) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // contiguous chunk range of this CTA
+  const long long c_beg = (long long)p.total_chunks * blockIdx.x / gridDim.x;
+  const long long c_end = (long long)p.total_chunks * (blockIdx.x + 1) / gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================== TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long c = c_beg; c < c_end; ++c) {
+      if (!mbar_wait(empty_bar(stage), phase ^ 1u, 21)) break;
+      const uint32_t sa = st0 + stage * stage_bytes, sb = sa + p.a_bytes;
+      mbar_expect_tx(full_bar(stage), (uint32_t)p.tx_bytes);
+      if (p.mode == 0) {
+        const int b = (int)(c / p.chunks_per_sample), r0 = (int)(c - (long long)b * p.chunks_per_sample) * 32;
+        for (int j = 0; j < p.na; ++j) tma_load_3d(sa + j * 4096, &maps.a[j], full_bar(stage), p.acol0[j], r0 + p.arshift[j], b);
+        for (int j = 0; j < p.nbn; ++j) tma_load_3d(sb + j * 4096, &maps.b[0], full_bar(stage), p.bcol0[j], r0, b);
+      } else {
+        const int pair = (int)(c / p.nb), slab = (int)(c - (long long)pair * p.nb);
+        for (int t = 0; t < p.mtiles; ++t) tma_load_3d(sa + t * 16384, &maps.a[pair], full_bar(stage), 0, t * 128, slab);
+        tma_load_3d(sb, &maps.b[pair], full_bar(stage), 0, 0, slab);
+      }
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================================== MMA issuer
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (p.mode == 0 ? ((1u << 15) | (1u << 16)) : 0u) |
+                           ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+    for (long long c = c_beg; c < c_end; ++c) {
+      if (!mbar_wait(full_bar(stage), phase, 22)) break;
+      tc_fence_after();
+      const uint32_t sa = st0 + stage * stage_bytes, sb = sa + p.a_bytes;
+#pragma unroll 1
+      for (int t = 0; t < p.mtiles; ++t) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint64_t adesc, bdesc;
+          if (p.mode == 0) {
+            // MN-major, 32-byte-atom swizzle: atoms of 4 k-rows x 128 B (SBO 512 B), next 32-wide block 4096 B on (LBO)
+            adesc = make_desc(sa + t * 16384 + kk * 1024, 4096, 512, 1);
+            bdesc = make_desc(sb + kk * 1024, 4096, 512, 1);
+          } else {
+            adesc = make_desc(sa + t * 16384 + kk * 32, 16, 1024, 2);
+            bdesc = make_desc(sb + kk * 32, 16, 1024, 2);
+          }
+          tc_mma_tf32(d_tmem, adesc, bdesc, idesc, (!first || kk > 0) ? 1u : 0u);
+        }
+      }
+      first = false;
+      tc_commit(empty_bar(stage));
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+    }
+    tc_commit(done_bar);
+  } else if (warp >= 4) {
+    // ===================================================== epilogue: add this CTA's partial result to global
+    if (c_end > c_beg && mbar_wait(done_bar, 0, 23)) {
+      tc_fence_after();
+      const int ew = warp - 4;
+      const int row = ew * 32 + lane;
+      for (int t = 0; t < p.mtiles; ++t) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(t * 256);
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          uint32_t r[16];
+          tc_ld16(taddr + c0, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = c0 + j;
+            const float v = __uint_as_float(r[j]);
+            if (p.out.kind == 2) {
+              const int vv = t * 128 + row;
+              if (vv < p.out.V && n < p.out.V) atomicAdd(p.out.out + (size_t)vv * p.out.ldw + n, v);
+            } else {
+              const int blk = t * 4 + ew, i = lane;
+              if (blk < p.out.nblk_real) {
+                if (p.out.kind == 0) atomicAdd(p.out.out + (size_t)n * p.out.ldw + blk * 32 + i, v);
+                else atomicAdd(p.out.out + (size_t)(blk * 32 + i) * 64 + n, v);
+              } else if (blk == p.out.nblk_real && i == 0 && p.out.out_bias) {
+                atomicAdd(p.out.out_bias + n, v);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+}  // namespace tc
+#endif
+
+// 0 = launched, -1 = not eligible (caller falls back), > 0 = error.
+inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream) {
+#if GWN_EMU
+  (void)a; (void)stream;
+  return -1;
+#else
+  using namespace tc;
+  TrMaps maps;
+  TrParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = a.mode; p.na = a.na; p.N = a.N; p.nb = a.nb; p.out = a.out;
+  if (a.na < 1 || a.na > TR_MAXSRC || a.nb < 1 || a.rows < 1 || a.N % 16 != 0 || a.N < 16 || a.N > 256) return -1;
+  if (a.mode == 0) {
+    if (a.na > 7 || (a.N != 32 && a.N != 64)) return -1;
+    p.nblk = a.na + 1;                       // + the all-ones block
+    p.mtiles = (p.nblk + 3) / 4;
+    p.nbn = a.N / 32;
+    p.a_bytes = p.mtiles * 16384;
+    p.b_bytes = p.nbn * 4096;
+    p.tx_bytes = (a.na + p.nbn) * 4096;
+    p.chunks_per_sample = (a.rows + 31) / 32;
+    const long long tot = (long long)p.chunks_per_sample * a.nb;
+    if (tot > 2147483647LL) return -1;
+    p.total_chunks = (int)tot;
+    for (int j = 0; j < a.na; ++j) {
+      const TcRedSrc& g = a.a[j];
+      if ((reinterpret_cast<uintptr_t>(g.src) & 15) || g.row_width % 4 || g.col0 + 32 > g.row_width) return -1;
+      cuuint64_t d[3] = {(cuuint64_t)g.row_width, (cuuint64_t)g.rows_src, (cuuint64_t)a.nb};
+      cuuint64_t st[2] = {(cuuint64_t)g.row_width * 4, (cuuint64_t)g.rows_src * g.row_width * 4};
+      cuuint32_t box[3] = {32, 32, 1};
+      GWN_TRY(encode(&maps.a[j], g.src, 3, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+      p.acol0[j] = g.col0;
+      p.arshift[j] = g.rshift;
+    }
+    {
+      const TcRedSrc& g = a.b[0];
+      if ((reinterpret_cast<uintptr_t>(g.src) & 15) || g.row_width % 4 || a.N > g.row_width) return -1;
+      cuuint64_t d[3] = {(cuuint64_t)g.row_width, (cuuint64_t)g.rows_src, (cuuint64_t)a.nb};
+      cuuint64_t st[2] = {(cuuint64_t)g.row_width * 4, (cuuint64_t)g.rows_src * g.row_width * 4};
+      cuuint32_t box[3] = {32, 32, 1};
+      GWN_TRY(encode(&maps.b[0], g.src, 3, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+      for (int j = 0; j < p.nbn; ++j) p.bcol0[j] = g.col0 + 32 * j;
+    }
+    for (int j = a.na; j < TR_MAXSRC; ++j) maps.a[j] = maps.a[0];
+    for (int j = 1; j < TR_MAXSRC; ++j) maps.b[j] = maps.b[0];
+  } else {
+    if (a.rows > 256) return -1;              // V <= 256 (two 128-row M tiles)
+    p.nblk = 0;
+    p.mtiles = (a.rows + 127) / 128;
+    p.a_bytes = p.mtiles * 16384;
+    p.b_bytes = a.N * 128;
+    p.tx_bytes = p.a_bytes + p.b_bytes;
+    const long long tot = (long long)a.na * a.nb;
+    if (tot > 2147483647LL) return -1;
+    p.total_chunks = (int)tot;
+    for (int j = 0; j < a.na; ++j) {
+      const TcRedSrc* gs[2] = {&a.a[j], &a.b[j]};
+      for (int w = 0; w < 2; ++w) {
+        const TcRedSrc& g = *gs[w];
+        if ((reinterpret_cast<uintptr_t>(g.src) & 15) || g.row_width != 32) return -1;
+        cuuint64_t d[3] = {32, (cuuint64_t)a.rows, (cuuint64_t)a.nb};
+        cuuint64_t st[2] = {128, (cuuint64_t)a.rows * 128};
+        cuuint32_t box[3] = {32, (cuuint32_t)(w == 0 ? 128 : a.N), 1};
+        GWN_TRY(encode(w == 0 ? &maps.a[j] : &maps.b[j], g.src, 3, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B));
+      }
+    }
+    for (int j = a.na; j < TR_MAXSRC; ++j) { maps.a[j] = maps.a[0]; maps.b[j] = maps.b[0]; }
+  }
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+  p.stages = (SMEM_LIMIT - 2048) / stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages < 2) return -1;
+  const int smem_bytes = p.stages * stage_bytes + 1024 + 256;
+  static cudaError_t attr = cudaFuncSetAttribute(tcred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  if (attr != cudaSuccess) {
+    set_error("tcred: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr));
+    return GWN_ERR_CUDA;
+  }
+  static int num_sms = [] {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  const int grid = p.total_chunks < num_sms ? p.total_chunks : num_sms;
+  tcred_kernel<<<grid, 256, smem_bytes, stream>>>(maps, p);
+  GWN_LAUNCH_CHECK();
+  count_launch();
+  return 0;
+#endif
+}
+
+}  // namespace gwn
