@@ -414,7 +414,9 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
         GWN_LAUNCH_1D(pack_tcn_fwd_kernel, 2 * D, st, P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw),
                       P_<float>(prm, p->li[i].fb), P_<float>(prm, p->li[i].gb), prev_ac, pk + p->pk_wp, pk + p->pk_bf,
                       pk + p->pk_bg, D, C);
-        EpGate eg{g, pk + p->pk_bf, pk + p->pk_bg, D};
+        RowGate eg;
+        memset(&eg, 0, sizeof(eg));
+        eg.y = g; eg.bf = pk + p->pk_bf; eg.bg = pk + p->pk_bg;
         pst = launch_tcpos<64>(tcn_tcpos_args(p, prev, pk + p->pk_wp, i), eg, st);
         if (pst > 0) return pst;
       }
@@ -699,7 +701,9 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
       int pst = -1;
       if (tcpos_ok(p) && training) {   // packed weights (BN fold included) were written by the forward pass
         const float* pk = ws + p->o_pack[i];
-        EpGateBwd eg{dpre, dgp, pk + p->pk_bf, pk + p->pk_bg, D};
+        RowGateBwd eg;
+        memset(&eg, 0, sizeof(eg));
+        eg.dpre = dpre; eg.dg = dgp; eg.bf = pk + p->pk_bf; eg.bg = pk + p->pk_bg;
         pst = launch_tcpos<64>(tcn_tcpos_args(p, prev, pk + p->pk_wp, i), eg, st);
         if (pst > 0) return pst;
       }
@@ -727,9 +731,9 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
         float* pk = const_cast<float*>(ws) + p->o_pack[i];
         GWN_LAUNCH_1D(pack_tcn_dgrad_kernel, (i64)C * 4 * D, st, P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw),
                       pk + p->pk_wd, D, C);
-        EpTcnDgrad<TRow> eg;
+        RowTcnDgrad eg;
         memset(&eg, 0, sizeof(eg));
-        eg.dx = ep.dx; eg.du = ep.du; eg.C = C; eg.N = N; eg.L_in = ep.L_in; eg.L_out = ep.L_out;
+        eg.dx = ep.dx; eg.du = ep.du; eg.N = N; eg.L_in = ep.L_in; eg.L_out = ep.L_out;
         eg.uprev = ep.uprev; eg.mr = ep.mr; eg.bsum = ep.bsum;
         TcPosArgs t;
         memset(&t, 0, sizeof(t));

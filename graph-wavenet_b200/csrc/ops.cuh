@@ -148,9 +148,9 @@ inline int mlp_forward(const MlpFwdArgs& m, cudaStream_t stream) {
     memset(&t, 0, sizeof(t));
     for (int q = 0; q < m.nseg; ++q) t.seg[q] = TcPosSeg{m.segs[q], (int)m.P, 32, 0, 0};
     t.nseg = m.nseg; t.nb = 1; t.rows_out = (int)m.P; t.Wp = m.W; t.N = 32;
-    EpMlp<TRow> eg;
+    RowMlp eg;
     memset(&eg, 0, sizeof(eg));
-    eg.y = m.y; eg.bias = m.bias; eg.C = m.C_out; eg.drop = m.drop; eg.res = m.res; eg.rrm = m.rrm; eg.rac = m.rac; eg.stats = m.stats;
+    eg.y = m.y; eg.bias = m.bias; eg.drop = m.drop; eg.res = m.res; eg.rrm = m.rrm; eg.rac = m.rac; eg.stats = m.stats;
     int st = launch_tcpos<32>(t, eg, stream);
     if (st >= 0) return st;
   }
@@ -207,7 +207,10 @@ inline int mlp_backward(const MlpBwdArgs& m, cudaStream_t stream) {
       memset(&t, 0, sizeof(t));
       t.seg[0] = TcPosSeg{m.dh, (int)m.P, 32, 0, 0};
       t.nseg = 1; t.nb = 1; t.rows_out = (int)m.P; t.Wp = m.WT; t.N = Ktot;
-      st = launch_tcpos<0>(t, e, stream);
+      RowSeg rs;
+      memset(&rs, 0, sizeof(rs));
+      rs.out = m.dsegs; rs.M = m.P;
+      st = launch_tcpos<0>(t, rs, stream);
       if (st > 0) return st;
     }
     if (st < 0 && current_math() != 0 && m.C_out == PG_WD && m.drop.mode == GWN_DROPOUT_NONE && Ktot <= 256) {

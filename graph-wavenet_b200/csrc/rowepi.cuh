@@ -1,0 +1,220 @@
+// Row-owner epilogues of the tcgen05 position GEMM (tcpos.cuh): each of the 128 epilogue threads owns one whole
+// position row of the accumulator tile.  Contract:
+//     void init();
+//     void prefetch(i64 m, bool valid);                    // issue the global loads of the row's addends (128-bit)
+//     void consume16(i64 m, int c0, const float (&v)[16]); // accumulator columns c0..c0+15 of row m (valid rows only)
+//     void finish_rows(float* red, int etid);              // if kHasFinish: block-level reduce of column statistics
+// Addends are fetched as whole 128-byte rows BEFORE the accumulator is waited for (ncu on the first version, which
+// loaded them 4 floats at a time inside the column loop, showed the epilogue stalled on those dependent loads
+// for ~10k cycles per tile); outputs leave as 128-bit stores.  Same arithmetic as the functors of functors.cuh.
+#pragma once
+#include "functors.cuh"
+
+namespace gwn {
+
+#if !GWN_EMU
+__device__ __forceinline__ void ld_row32(float (&r)[32], const float* p) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(p) + q);
+    r[4 * q] = f.x; r[4 * q + 1] = f.y; r[4 * q + 2] = f.z; r[4 * q + 3] = f.w;
+  }
+}
+__device__ __forceinline__ void st16(float* p, const float (&o)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+}
+
+// Per-thread column statistics over 32 columns, reduced across the 128 epilogue threads at the end.
+struct RowStats32 {
+  float s1[32], s2[32];
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s1[i] = s2[i] = 0.0f;
+  }
+  __device__ __forceinline__ void reduce(float* smem, int etid, double* g1, double* g2, int ncols) {
+    if (etid < 64) smem[etid] = 0.0f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+    for (int col = 0; col < 32; ++col) {
+      float a = s1[col], b = s2[col];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if ((etid & 31) == 0) {
+        atomicAdd(smem + col, a);
+        atomicAdd(smem + 32 + col, b);
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (etid < 32 && etid < ncols) {
+      atomicAdd(g1 + etid, (double)smem[etid]);
+      atomicAdd(g2 + etid, (double)smem[32 + etid]);
+    }
+  }
+};
+
+// model.py:208-212 -- accumulator columns interleaved (f0,g0,f1,g1,...), N = 64 -> 32 gated outputs.
+struct RowGate {
+  static constexpr bool kHasFinish = false;
+  float* y;          // [P, 32]
+  const float* bf;
+  const float* bg;
+  __device__ __forceinline__ void init() {}
+  __device__ __forceinline__ void prefetch(i64, bool) {}
+  __device__ __forceinline__ void consume16(i64 m, int c0, const float (&v)[16]) {
+    const int ch0 = c0 >> 1;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = tanhf(v[2 * j] + __ldg(bf + ch0 + j)) * sigmoidf_(v[2 * j + 1] + __ldg(bg + ch0 + j));
+    float* p = y + m * 32 + ch0;
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  }
+  __device__ __forceinline__ void finish_rows(float*, int) {}
+};
+
+// Gate backward from recomputed pre-activations: dpre[m][2ch+{0,1}] (interleaved, 64 wide).
+struct RowGateBwd {
+  static constexpr bool kHasFinish = false;
+  float* dpre;       // [P, 64]
+  const float* dg;   // [P, 32]
+  const float* bf;
+  const float* bg;
+  float g[32];
+  __device__ __forceinline__ void init() {}
+  __device__ __forceinline__ void prefetch(i64 m, bool valid) {
+    if (valid) ld_row32(g, dg + m * 32);
+  }
+  __device__ __forceinline__ void consume16(i64 m, int c0, const float (&v)[16]) {
+    const int ch0 = c0 >> 1;
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float f = tanhf(v[2 * j] + __ldg(bf + ch0 + j)), s = sigmoidf_(v[2 * j + 1] + __ldg(bg + ch0 + j));
+      const float gg = g[ch0 + j];
+      o[2 * j] = gg * s * (1.0f - f * f);
+      o[2 * j + 1] = gg * f * s * (1.0f - s);
+    }
+    st16(dpre + m * 64 + c0, o);
+  }
+  __device__ __forceinline__ void finish_rows(float*, int) {}
+};
+
+// gcn tail + residual + BatchNorm statistics (model.py:53-54, 234-236), N = 32.
+struct RowMlp {
+  static constexpr bool kHasFinish = true;
+  float* y;            // [P, 32]
+  const float* bias;
+  DropoutSrc drop;
+  const float* res;    // nullable
+  Remap rrm;
+  const float* rac;    // nullable fold of the residual
+  double* stats;       // nullable
+  float rrow[32];
+  RowStats32 cs;
+  __device__ __forceinline__ void init() { cs.reset(); }
+  __device__ __forceinline__ void prefetch(i64 m, bool valid) {
+    if (res && valid) ld_row32(rrow, res + rrm(m) * 32);
+  }
+  __device__ __forceinline__ void consume16(i64 m, int c0, const float (&v)[16]) {
+    float o[16];
+    const i64 e = m * 32 + c0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float kp[4];
+      drop.keep4(e + 4 * q, kp);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = 4 * q + i;
+        float r = (v[c] + __ldg(bias + c0 + c)) * kp[i];
+        if (res) {
+          float x = rrow[c0 + c];
+          if (rac) x = fmaf(x, __ldg(rac + c0 + c), __ldg(rac + 32 + c0 + c));
+          r += x;
+        }
+        o[c] = r;
+      }
+    }
+    st16(y + e, o);
+    if (stats) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) { cs.s1[c0 + c] += o[c]; cs.s2[c0 + c] += o[c] * o[c]; }
+    }
+  }
+  __device__ __forceinline__ void finish_rows(float* red, int etid) {
+    if (stats) cs.reduce(red, etid, stats, stats + 32, 32);
+  }
+};
+
+// mlp input gradient: N = nseg*32 columns scattered to the per-segment tensors out[(q*M + m)*32 + nn].
+struct RowSeg {
+  static constexpr bool kHasFinish = false;
+  float* out;
+  i64 M;
+  __device__ __forceinline__ void init() {}
+  __device__ __forceinline__ void prefetch(i64, bool) {}
+  __device__ __forceinline__ void consume16(i64 m, int c0, const float (&v)[16]) {
+    const int q = c0 >> 5, nn = c0 & 31;
+    st16(out + ((i64)q * M + m) * 32 + nn, v);
+  }
+  __device__ __forceinline__ void finish_rows(float*, int) {}
+};
+
+// Gated-conv input gradient + residual path + BatchNorm-backward statistics of the layer below, N = 32.
+struct RowTcnDgrad {
+  static constexpr bool kHasFinish = true;
+  float* dx;           // [P_in, 32]
+  const float* du;     // nullable [P_out, 32]
+  int N, L_in, L_out;
+  const float* uprev;  // nullable
+  const float* mr;     // mean[32], rstd[32]
+  double* bsum;
+  float durow[32], urow[32];
+  bool has_du;
+  RowStats32 cs;
+  __device__ __forceinline__ void init() { cs.reset(); }
+  __device__ __forceinline__ void prefetch(i64 m, bool valid) {
+    has_du = false;
+    if (!valid) return;
+    if (du) {
+      const unsigned lon = (unsigned)L_in * (unsigned)N;
+      const unsigned b = (unsigned)m / lon, rr = (unsigned)m - b * lon;
+      const int tp = (int)(rr / (unsigned)N), node = (int)(rr - (unsigned)tp * (unsigned)N);
+      const int t = tp - (L_in - L_out);
+      if (t >= 0) {
+        has_du = true;
+        ld_row32(durow, du + (((i64)b * L_out + t) * N + node) * 32);
+      }
+    }
+    if (uprev) ld_row32(urow, uprev + m * 32);
+  }
+  __device__ __forceinline__ void consume16(i64 m, int c0, const float (&v)[16]) {
+    float o[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = v[c] + (has_du ? durow[c0 + c] : 0.0f);
+    st16(dx + m * 32 + c0, o);
+    if (uprev) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float xh = (urow[c0 + c] - __ldg(mr + c0 + c)) * __ldg(mr + 32 + c0 + c);
+        cs.s1[c0 + c] += o[c];
+        cs.s2[c0 + c] += o[c] * xh;
+      }
+    }
+  }
+  __device__ __forceinline__ void finish_rows(float* red, int etid) {
+    if (uprev) cs.reduce(red, etid, bsum, bsum + 32, 32);
+  }
+};
+#else
+struct RowGate { float* y; const float* bf; const float* bg; };
+struct RowGateBwd { float* dpre; const float* dg; const float* bf; const float* bg; };
+struct RowMlp { float* y; const float* bias; DropoutSrc drop; const float* res; Remap rrm; const float* rac; double* stats; };
+struct RowSeg { float* out; i64 M; };
+struct RowTcnDgrad { float* dx; const float* du; int N, L_in, L_out; const float* uprev; const float* mr; double* bsum; };
+#endif
+
+}  // namespace gwn

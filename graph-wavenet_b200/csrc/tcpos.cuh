@@ -8,12 +8,13 @@
 //   A : K-major SWIZZLE_128B tiles [128 rows][32 floats] straight from the fp32 activations (kind::tf32 reads fp32 bits);
 //   Wp: packed weights [N][K] row-major, loaded once per persistent CTA and kept resident in shared memory;
 //   D : fp32 in TMEM, double-buffered; the 4 epilogue warps own one position row per thread and run the same
-//       epilogue functors as the other GEMM paths (store4 / finish_rows).
+//       row epilogues of rowepi.cuh (whole-row 128-bit loads of the addends, 128-bit stores).
 //
 // Used for the gated (1,2) conv and its backward recompute, the gcn mlp forward and input gradient, and the
 // gated conv's input gradient -- the HBM-bound convolutions of SURVEY.md §8(a) rows a3, a4, a7, a9.
 #pragma once
 #include "functors.cuh"
+#include "rowepi.cuh"
 #include "tc_common.cuh"
 
 namespace gwn {
@@ -148,17 +149,18 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
   } else if (warp >= 4) {
     // ===================================================== epilogue: one position row per thread
     EP ep = ep_in;
-    ep.init(0);
+    ep.init();
     const int ew = warp - 4;
     int acc = 0;
     uint32_t accphase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_sample, rt = tile - b * p.tiles_per_sample;
-      if (!mbar_wait(tfull_bar(acc), accphase, 15)) break;
-      tc_fence_after();
       const int rl = rt * 128 + ew * 32 + lane;
       const bool valid = rl < p.rows_out;
       const i64 m = (i64)b * p.rows_out + rl;
+      ep.prefetch(m, valid);               // addend rows are in flight while the MMAs of this tile finish
+      if (!mbar_wait(tfull_bar(acc), accphase, 15)) break;
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * 256);
       const int ncols = NCT > 0 ? NCT : p.N;
 #pragma unroll
@@ -167,12 +169,10 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
         tc_ld16(taddr + c0, r);
         tc_wait_ld();
         if (valid) {
+          float v[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float v[4] = {__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                                __uint_as_float(r[4 * q + 3])};
-            ep.store4(m, c0 + 4 * q, v, 4, (c0 >> 2) + q);
-          }
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          ep.consume16(m, c0, v);
         }
       }
       tc_fence_before();
