@@ -142,39 +142,47 @@ def cpu_baseline_leg(steps=3):
             "sample": f"{steps} full trainer.train steps at batch 64 after 1 warm-up (oracle port, torch CPU ops, {cores} threads)"}
 
 
-def roofline_leg(lib, dev, iters=20):
-    """Dominant kernel = the node contraction (nconv, model.py:13): time it alone at every layer's
-    shape (B=64, C=32, N=207, L_i) with CUDA events on the launching stream; algorithmic FLOPs
-    2*B*C*L*N^2 per launch."""
+def roofline_leg(lib, step_fn, dev, steps=5):
+    """Per-operator device timing of the same train step (CUDA events on the launching stream, recorded by
+    the library around every operator of the plan: gwn_profile_begin/end) -> achieved GB/s and TFLOP/s per
+    operator from its ALGORITHMIC bytes / flops.  `roofline` is the
+    operator with the largest share of the step."""
+    import ctypes
     import torch
     pk, src = peaks()
-    Ls = [12, 10, 9, 7, 6, 4, 3, 1]
-    A = torch.softmax(torch.randn(NODES, NODES, device=dev), dim=1)
-    flops = t_ms = 0.0
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-    st = torch.cuda.current_stream(dev)
-    for L in Ls:
-        x = torch.randn(BATCH, L, NODES, 32, device=dev)
-        y = torch.empty_like(x)
-        for _ in range(3):
-            lib.check(lib.dll.gwn_nconv_fwd(x.data_ptr(), A.data_ptr(), NODES, y.data_ptr(), BATCH, L, NODES, 32, 0, st.cuda_stream))
-        tot = 0.0
-        for _ in range(iters):
-            flush.zero_()                      # L2 flush between timed launches
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(st)
-            lib.check(lib.dll.gwn_nconv_fwd(x.data_ptr(), A.data_ptr(), NODES, y.data_ptr(), BATCH, L, NODES, 32, 0, st.cuda_stream))
-            e1.record(st)
-            e1.synchronize()
-            tot += e0.elapsed_time(e1)
-        t_ms += tot / iters
-        flops += 2.0 * BATCH * 32 * L * NODES * NODES
-    achieved = flops / (t_ms * 1e-3) / 1e12
-    peak = pk.get("bf16_tflops", 1590.0)
-    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-            "kernel": "gemm_kernel<Tile<128,128,8,8>,LdSupport,LdSlab,EpSlab> (nconv node contraction, fp32 FMA tier)",
-            "peak_source": f"bf16_tflops burst, {src} (kernel timed alone)",
-            "note": "fp32 SIMT parity tier: not on the tensor pipe; fraction is against the bf16 tensor peak by contract"}
+    hbm_peak = pk.get("hbm_gbs", 6650.0)
+    tens_peak = pk.get("bf16_tflops_sustained", 1400.0)       # kernels timed inside a long step
+    for i in range(2):
+        step_fn(i)
+    torch.cuda.synchronize(dev)
+    lib.check(lib.dll.gwn_profile_begin(), "gwn_profile_begin")
+    for i in range(steps):
+        step_fn(i)
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.check(lib.dll.gwn_profile_end(buf, len(buf)), "gwn_profile_end")
+    ops = json.loads(buf.value.decode())
+    total = sum(o["ms"] for o in ops) or 1.0
+    ridge = tens_peak * 1e12 / (hbm_peak * 1e9)               # flop/byte where the bf16 tensor roof meets the HBM roof
+    table = []
+    for o in ops:
+        sec = o["ms"] * 1e-3
+        if sec <= 0:
+            continue
+        gbs, tfs = o["bytes"] / sec / 1e9, o["flops"] / sec / 1e12
+        ai = o["flops"] / o["bytes"] if o["bytes"] else 0.0
+        table.append({"op": o["op"], "launch_groups_per_step": o["calls"] / steps, "ms_per_step": o["ms"] / steps,
+                      "share": o["ms"] / total, "GBps": gbs, "hbm_frac": gbs / hbm_peak, "TFLOPs": tfs,
+                      "tensor_frac": tfs / tens_peak, "flop_per_byte": ai, "bound": "tensor" if ai > ridge else "hbm"})
+    table.sort(key=lambda r: -r["share"])
+    top = table[0]
+    if top["bound"] == "hbm":
+        roof = {"bound": "hbm", "achieved": top["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": top["hbm_frac"]}
+    else:
+        roof = {"bound": "tensor", "achieved": top["TFLOPs"], "peak": tens_peak, "unit": "TFLOP/s", "frac": top["tensor_frac"]}
+    roof.update({"traffic": None, "kernel": top["op"], "share_of_step": top["share"],
+                 "peak_source": f"MEASURED_PEAKS.json ({src}): hbm_gbs, bf16_tflops_sustained (operators timed inside the step)",
+                 "ridge_flop_per_byte": ridge, "profiled_steps": steps, "op_ms_per_step": total / steps})
+    return roof, table
 
 
 def run_native(args):
@@ -239,12 +247,19 @@ def run_native(args):
         y = hy.to(dev, non_blocking=True)
         tr.train(x, y)
 
-    for i in range(max(args.warmup, 3)):
+    # kernels of ours per step: counted on an eager (un-captured) run of the same fused step; the CUDA graph that the
+    # timed region replays consists of exactly these launches (+ memset / NCCL / copy nodes)
+    graph_mode = bool(getattr(tr, "use_graph", False)) and not args.no_graph
+    tr.use_graph = False
+    for i in range(2):
         step_resident(i)
     lib.dll.gwn_launch_count(1)
     step_resident(0)
     torch.cuda.synchronize(dev)
     launches_per_step = int(lib.dll.gwn_launch_count(1))
+    tr.use_graph = graph_mode
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -253,25 +268,33 @@ def run_native(args):
     for i in range(2):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
+    roof = None
+    if rank == 0 and world == 1 and not args.skip_roofline:
+        tr.use_graph = False            # per-operator CUDA events need un-captured launches
+        roof = roofline_leg(lib, step_resident, dev)
+        tr.use_graph = graph_mode
 
     if rank == 0:
         h2d = sum(t.numel() * t.element_size() for t in host[0])
         line = {"metric": METRIC, "value": BATCH * world / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "fp32x3": "f32 (3xTF32)", "tf32": "tf32"}[args.precision],
+                "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": BATCH * world,
                            "parallelism": f"dp{world}" if world > 1 else "single",
                            "precision_tier": {"fp32": "fp32 (FMA) -- 1e-4 parity tier",
                                               "fp32x3": "fp32-grade 3xTF32 split on tensor cores (mma.sync) -- 1e-4 parity tier",
                                               "tf32": "tf32: node contraction on tcgen05 kind::tf32, other contractions single-pass TF32 "
                                                       "mma.sync, fp32 accumulate -- 2e-2 tier"}[args.precision],
+                           "step": ("one CUDA graph per step: forward + masked-MAE loss + backward + clip + Adam + metrics" if graph_mode
+                                    else "eager launches of the same fused step"),
                            "l2_policy": "per-step working set (~0.9 GB of saved activations) exceeds the 126 MB L2; 4 rotating input batches"},
                 "e2e": {"value": BATCH * world / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e},
+                        "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e},
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
                 "model_tflops": algorithmic_gflop_per_step(BATCH * world) / ms, "clocks": clocks}
-        if world == 1 and not args.skip_roofline:
-            line["roofline"] = roofline_leg(lib, dev)
+        if roof is not None:
+            line["roofline"], line["operators"] = roof
         if world == 1 and not args.skip_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line), flush=True)
@@ -286,8 +309,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("GWNET_B200_PRECISION", "fp32"), choices=["fp32", "fp32x3", "tf32"],
+    ap.add_argument("--precision", default=os.environ.get("GWNET_B200_PRECISION", "tf32"), choices=["fp32", "fp32x3", "tf32"],
                     help="fp32 = FMA parity tier (1e-4); tf32 = node contraction on tcgen05 (2e-2 tier)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the fused step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only")
     ap.add_argument("--skip-roofline", action="store_true", help="profiling runs only")
     args = ap.parse_args()

@@ -40,6 +40,16 @@ typedef long long i64;
 void set_error(const char* fmt, ...);
 void count_launch();   // bumps the counter behind gwn_launch_count()
 
+// Per-op device timing for bench.py's roofline table (gwn_profile_begin / gwn_profile_end): when recording is on,
+// a scope brackets the launches of one operator with CUDA events on the launching stream and carries the
+// operator's ALGORITHMIC bytes and flops.  Off (the default): two predictable branches.
+struct ProfScope {
+  int idx;
+  cudaStream_t st;
+  ProfScope(const char* tag, cudaStream_t stream, double bytes, double flops);
+  ~ProfScope();
+};
+
 #define GWN_CHECK_ARG(cond, ...)                  \
   do {                                            \
     if (!(cond)) {                                \
@@ -163,6 +173,7 @@ struct DropoutSrc {
   int mode;              // gwn_dropout_mode
   const uint8_t* mask;   // GWN_DROPOUT_MASK
   uint64_t seed, stream; // GWN_DROPOUT_PHILOX: key = seed, counter hi = stream (layer id)
+  const unsigned long long* seed_dev;   // non-null: the key is read from device memory (CUDA-graph replays draw fresh masks)
   float p, scale;        // scale = 1/(1-p)
   GWN_HD void keep4(i64 e, float (&k)[4]) const {
     if (mode == GWN_DROPOUT_NONE) {
@@ -172,7 +183,7 @@ struct DropoutSrc {
       for (int i = 0; i < 4; ++i) k[i] = mask[e + i] ? scale : 0.0f;
     } else {
       uint32_t r[4];
-      Philox::gen(seed, (uint64_t)(e >> 2), stream, r);
+      Philox::gen(seed_dev ? (uint64_t)*seed_dev : seed, (uint64_t)(e >> 2), stream, r);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float u = (float)(r[i] >> 8) * (1.0f / 16777216.0f);  // [0,1)
@@ -181,8 +192,10 @@ struct DropoutSrc {
     }
   }
 };
-inline DropoutSrc make_dropout(int mode, const uint8_t* mask, uint64_t seed, uint64_t stream, float p) {
+inline DropoutSrc make_dropout(int mode, const uint8_t* mask, uint64_t seed, uint64_t stream, float p,
+                               const unsigned long long* seed_dev = nullptr) {
   DropoutSrc d;
+  d.seed_dev = seed_dev;
   d.mode = (p <= 0.0f) ? (int)GWN_DROPOUT_NONE : mode;
   d.mask = mask;
   d.seed = seed;

@@ -2,9 +2,12 @@
 // Replaces gwnet.forward (model.py:175-241) and its autograd graph with explicit fused launches.
 #include "ops.cuh"
 #include "nconv_tc_impl.cuh"
+#include "train_tail.cuh"
 
 #include <atomic>
 #include <cstdarg>
+#include <map>
+#include <mutex>
 #include <vector>
 #include <string>
 
@@ -18,6 +21,36 @@ int current_math() { return g_math; }
 void set_current_math(int m) { g_math = m; }
 // gwn_precision -> GEMM math mode (gemm.cuh)
 static int math_of(int precision) { return precision == GWN_PREC_TF32 ? 1 : (precision == GWN_PREC_FP32X3 ? 3 : 0); }
+
+// ---- per-op device timing (see common.cuh)
+#if !GWN_EMU
+struct ProfRec {
+  const char* tag;
+  cudaEvent_t e0, e1;
+  double bytes, flops;
+};
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+ProfScope::ProfScope(const char* tag, cudaStream_t stream, double bytes, double flops) : idx(-1), st(stream) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec r;
+  r.tag = tag; r.bytes = bytes; r.flops = flops;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, stream);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+  idx = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (idx < (int)g_prof.size()) cudaEventRecord(g_prof[idx].e1, st);
+}
+#else
+ProfScope::ProfScope(const char*, cudaStream_t stream, double, double) : idx(-1), st(stream) {}
+ProfScope::~ProfScope() {}
+#endif
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -342,9 +375,11 @@ static bool pg_ok(const gwn_plan* p) {
   return current_math() != 0 && p->c.residual_channels == PG_WD && p->c.dilation_channels == PG_WD;
 }
 
-static DropoutSrc layer_dropout(const gwn_plan* p, int training, int mode, const uint8_t* const* masks, uint64_t seed, int i) {
+static DropoutSrc layer_dropout(const gwn_plan* p, int training, int mode, const uint8_t* const* masks, uint64_t seed, int i,
+                                const uint64_t* seed_dev) {
   if (!training || !p->c.gcn) return make_dropout(GWN_DROPOUT_NONE, nullptr, 0, 0, 0.f);
-  return make_dropout(mode, (mode == GWN_DROPOUT_MASK && masks) ? masks[i] : nullptr, seed, (uint64_t)i, p->c.dropout);
+  return make_dropout(mode, (mode == GWN_DROPOUT_MASK && masks) ? masks[i] : nullptr, seed, (uint64_t)i, p->c.dropout,
+                      reinterpret_cast<const unsigned long long*>(seed_dev));
 }
 
 static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
@@ -393,6 +428,7 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
   }
   // ---- start conv (+ left pad)
   {
+    ProfScope prof("start_conv_fwd", st, 4.0 * p->P0() * (c.in_dim + C), 2.0 * p->P0() * c.in_dim * C);
     Strides4 is;
     for (int k = 0; k < 4; ++k) is.s[k] = a->input_strides[k];
     GWN_LAUNCH_1D(start_fwd_kernel, p->P0() * C, st, a->input, is, P_<float>(prm, p->i_startw), P_<float>(prm, p->i_startb),
@@ -405,6 +441,7 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     float* g = ws + p->o_g[i];
     const i64 Pi = p->P(i);
     {  // gated dilated conv
+      ProfScope prof("gated_tcn_fwd", st, 4.0 * ((double)B * p->Lin(i) * N * C + (double)Pi * D), 2.0 * Pi * 2 * C * 2 * D);
       LdRows la = tcn_rows(p, prev, prev_ac, i);
       LdWTcn lb{P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw), C};
       EpGate ep{g, P_<float>(prm, p->li[i].fb), P_<float>(prm, p->li[i].gb), D};
@@ -444,7 +481,7 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
       m.bias = P_<float>(prm, p->li[i].rb);
     }
     m.segs = segs; m.nseg = p->nseg; m.P = Pi; m.D = D; m.C_out = C;
-    m.drop = layer_dropout(p, a->training, a->dropout_mode, a->keep_masks, a->seed, i);
+    m.drop = layer_dropout(p, a->training, a->dropout_mode, a->keep_masks, a->seed, i, a->seed_device);
     m.res = prev;
     m.rrm = make_remap(p->L[i], p->Lin(i), p->Lin(i) - p->L[i], N);
     m.rac = prev_ac;
@@ -460,6 +497,8 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
   }
   // ---- head: skip sum over the live columns (G5), relu, end convs (model.py:216-222,238-240)
   const i64 PT = p->PT();
+  ProfScope prof_head("head_fwd", st, 4.0 * PT * ((double)nL * D + 2.0 * Sk + 2.0 * E + c.out_dim),
+                      2.0 * PT * ((double)nL * D * Sk + (double)Sk * E + (double)E * c.out_dim));
   {
     LdRows la;
     memset(&la, 0, sizeof(la));
@@ -508,11 +547,11 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
   return 0;
 }
 
-static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
+static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_ready = false) {
   MathScope math_scope(math_of(p->c.precision));
   GWN_TRY(require_device());
   GWN_TRY(check_ptr_table(p, a->params));
-  GWN_CHECK_ARG(a->grad_output && a->workspace && a->scratch && a->grad_flat && a->input, "backward: null argument");
+  GWN_CHECK_ARG((a->grad_output || dout_ready) && a->workspace && a->scratch && a->grad_flat && a->input, "backward: null argument");
   const gwn_config& c = p->c;
   cudaStream_t st = (cudaStream_t)a->stream;
   const float* ws = reinterpret_cast<const float*>(a->workspace);
@@ -529,7 +568,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
   GWN_TRY(dev_memset(gf, 0, sizeof(float) * p->grad_floats, st));
   GWN_TRY(dev_memset(sc + p->o_bsum, 0, sizeof(float) * (i64)nL * 4 * C, st));
   if (c.adaptive) GWN_TRY(dev_memset(sc + p->o_dA, 0, sizeof(float) * (i64)N * p->ld, st));
-  GWN_TRY(dev_memset(sc + p->o_dout, 0, sizeof(float) * PT * p->ldo, st));
+  if (!dout_ready) GWN_TRY(dev_memset(sc + p->o_dout, 0, sizeof(float) * PT * p->ldo, st));
 
   SupportView supB[MAXSUP];
   TcSupports tcB;
@@ -542,7 +581,9 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
   tcB.precision = c.precision;
 
   // ---- head backward
-  {
+  ProfScope* prof_hb = new ProfScope("head_bwd", st, 4.0 * PT * (c.out_dim + 3.0 * E + 3.0 * Sk + 2.0 * nL * D),
+                                     2.0 * PT * (2.0 * E * c.out_dim + 2.0 * Sk * E + 2.0 * nL * D * Sk));
+  if (!dout_ready) {
     // grad_output [B,O,N,T_out] contiguous -> dout [P_T, ldo]
     int64_t sz[4] = {B, O, N, p->T_out};
     int64_t ss[4] = {(int64_t)O * N * p->T_out, (int64_t)N * p->T_out, p->T_out, 1};
@@ -641,6 +682,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
     GWN_TRY((launch_gemm<TBig>(lr, lw, es, sh2, st)));
   }
 
+  delete prof_hb;
   // ---- layers in reverse
   float* cur = sc + p->o_buf0;   // holds d(loss)/d(x_{i+1}) on entry of layer i (unused for the last layer)
   float* oth = sc + p->o_buf1;
@@ -656,11 +698,14 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
     const float* dgh_i = dgh + (i64)i * PT * D;
     const float* dgp;   // gradient wrt g_i
     if (live) {
-      const DropoutSrc ldrop = layer_dropout(p, training, dmode, a->keep_masks, a->seed, i);
+      const DropoutSrc ldrop = layer_dropout(p, training, dmode, a->keep_masks, a->seed, i, a->seed_device);
       const bool use_dh = ldrop.mode != GWN_DROPOUT_NONE;   // materialise du * keep once instead of regenerating masks
+      {
+      ProfScope prof("bn_bwd_apply", st, 4.0 * Pi * C * (use_dh ? 4.0 : 3.0), 0.0);
       GWN_LAUNCH_1D(bn_bwd_apply_kernel, Pi * C / 4, st, cur, ws + p->o_u[i], ws + p->o_ac[i], ws + p->o_mr[i],
                     reinterpret_cast<const double*>(sc + p->o_bsum + (i64)i * 4 * C), (double)Pi, training,
                     G(p->li[i].bnw), G(p->li[i].bnb), Pi, C, use_dh ? sc + p->o_dh : (float*)nullptr, ldrop);
+      }
       const float* segs[MAXSEG];
       for (int q = 0; q < p->nseg; ++q) segs[q] = g + (i64)q * Pi * D;
       MlpBwdArgs m;
@@ -695,6 +740,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
     }
     // gated conv backward: recompute pre-activations -> dpre
     {
+      ProfScope prof("gated_tcn_bwd_gate", st, 4.0 * ((double)B * p->Lin(i) * N * C + (double)Pi * 3 * D), 2.0 * Pi * 2 * C * 2 * D);
       LdRows la = tcn_rows(p, prev, prev_ac, i);
       LdWTcn lb{P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw), C};
       EpGateBwd ep{dpre, dgp, P_<float>(prm, p->li[i].fb), P_<float>(prm, p->li[i].gb), D};
@@ -716,6 +762,8 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
     }
     const i64 Pin = (i64)B * p->Lin(i) * N;
     {  // input gradient (+ residual path, + BN-backward sums of the layer below)
+      ProfScope prof("gated_tcn_dgrad", st, 4.0 * ((double)Pi * 2 * D + (live ? (double)Pi * C : 0.0) + (double)Pin * C * (i > 0 ? 2 : 1)),
+                     2.0 * Pin * 4 * D * C);
       LdDpreTaps la{dpre, 2 * D, N, p->Lin(i), p->L[i], p->dil[i]};
       LdWTcnT lb{P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw), C, 2 * D};
       EpTcnDgrad<TPos32> ep;
@@ -762,6 +810,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
       }
     }
     bool wgrad_done = false;
+    ProfScope prof_w("gated_tcn_wgrad", st, 4.0 * ((double)Pin * C + (double)Pi * 2 * D), 2.0 * Pi * 2 * D * (2.0 * C + 1));
     if (tcpos_ok(p)) {   // tcgen05 + TMA reduction over all positions, then fold the BatchNorm affine of the layer below
       float* R = sc + p->o_rs;
       float* S = R + (i64)2 * C * 2 * D;
@@ -801,6 +850,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a) {
   }
   // ---- start conv backward: cur = d(loss)/d(x0)
   {
+    ProfScope prof("start_conv_bwd", st, 4.0 * p->P0() * (C + c.in_dim), 2.0 * p->P0() * C * (c.in_dim + 1));
     LdCols la;
     memset(&la, 0, sizeof(la));
     la.p[0] = cur; la.set_wd(C); la.nseg = 1;
@@ -842,6 +892,51 @@ long long gwn_launch_count(int reset) {
   long long v = g_launches.load(std::memory_order_relaxed);
   if (reset) g_launches.store(0, std::memory_order_relaxed);
   return v;
+}
+
+int gwn_profile_begin(void) {
+#if !GWN_EMU
+  GWN_TRY(require_device());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  g_prof_on.store(1);
+#endif
+  return 0;
+}
+
+int gwn_profile_end(char* buf, int len) {
+  GWN_CHECK_ARG(buf && len > 2, "profile_end: bad buffer");
+  std::string s = "[";
+#if !GWN_EMU
+  g_prof_on.store(0);
+  GWN_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  struct Agg { long long calls = 0; double ms = 0, bytes = 0, flops = 0; };
+  std::map<std::string, Agg> agg;
+  std::vector<std::string> order;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { ms = 0.f; cudaGetLastError(); }
+    if (!agg.count(r.tag)) order.push_back(r.tag);
+    Agg& a = agg[r.tag];
+    a.calls += 1; a.ms += ms; a.bytes += r.bytes; a.flops += r.flops;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  char t[256];
+  for (size_t i = 0; i < order.size(); ++i) {
+    const Agg& a = agg[order[i]];
+    snprintf(t, sizeof(t), "%s{\"op\":\"%s\",\"calls\":%lld,\"ms\":%.6f,\"bytes\":%.0f,\"flops\":%.0f}", i ? "," : "",
+             order[i].c_str(), a.calls, a.ms, a.bytes, a.flops);
+    s += t;
+  }
+#endif
+  s += "]";
+  GWN_CHECK_ARG((int)s.size() < len, "profile_end: buffer too small (%d needed)", (int)s.size() + 1);
+  snprintf(buf, len, "%s", s.c_str());
+  return 0;
 }
 
 int gwn_device_info(int* n_devices, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor) {
@@ -1125,6 +1220,86 @@ int gwn_plan_forward(gwn_plan* p, const gwn_forward_args* a) {
 int gwn_plan_backward(gwn_plan* p, const gwn_backward_args* a) {
   GWN_CHECK_ARG(p && a, "plan_backward: null argument");
   return plan_backward(p, a);
+}
+
+size_t gwn_train_ctrl_bytes(void) { return sizeof(TrainCtrl); }
+
+int gwn_train_ctrl_init(void* ctrl, uint64_t seed, int64_t step) {
+  GWN_CHECK_ARG(ctrl, "train_ctrl_init: null control block");
+  TrainCtrl c;
+  memset(&c, 0, sizeof(c));
+  c.seed = seed;
+  c.step = step;
+#if GWN_EMU
+  memcpy(ctrl, &c, sizeof(c));
+#else
+  GWN_TRY(require_device());
+  GWN_CUDA(cudaMemcpy(ctrl, &c, sizeof(c), cudaMemcpyHostToDevice));
+#endif
+  return 0;
+}
+
+int gwn_train_ctrl_read(const void* ctrl, uint64_t* seed, int64_t* step) {
+  GWN_CHECK_ARG(ctrl, "train_ctrl_read: null control block");
+  TrainCtrl c;
+#if GWN_EMU
+  memcpy(&c, ctrl, sizeof(c));
+#else
+  GWN_TRY(require_device());
+  GWN_CUDA(cudaMemcpy(&c, ctrl, sizeof(c), cudaMemcpyDeviceToHost));
+#endif
+  if (seed) *seed = c.seed;
+  if (step) *step = c.step;
+  return 0;
+}
+
+int gwn_plan_train_fwd_bwd(gwn_plan* p, const gwn_train_args* a) {
+  GWN_CHECK_ARG(p && a, "train_fwd_bwd: null argument");
+  GWN_CHECK_ARG(a->ctrl && a->metrics && a->target && a->scratch && a->grad_flat && a->fwd.output, "train_fwd_bwd: null buffer");
+  GWN_TRY(require_device());
+  const gwn_config& c = p->c;
+  cudaStream_t st = (cudaStream_t)a->fwd.stream;
+  TrainCtrl* ctrl = reinterpret_cast<TrainCtrl*>(a->ctrl);
+  GWN_LAUNCH_1D(train_begin_kernel, 1, st, ctrl);
+  gwn_forward_args fa = a->fwd;
+  fa.training = 1;
+  fa.seed = 0;
+  fa.seed_device = reinterpret_cast<const uint64_t*>(&ctrl->seed);
+  GWN_TRY(plan_forward(p, &fa));
+  float* sc = reinterpret_cast<float*>(a->scratch);
+  {
+    const i64 n = (i64)c.batch * c.out_dim * c.num_nodes * p->T_out;
+    ProfScope prof("loss_metrics", st, 4.0 * n * 3.0 + 4.0 * p->PT() * p->ldo, 0.0);
+    GWN_LAUNCH_1D(loss_reduce_kernel, n, st, (const float*)a->fwd.output, a->target, (i64)a->target_strides[0],
+                  (i64)a->target_strides[1], (i64)a->target_strides[2], a->scaler_mean, a->scaler_std, c.batch, c.out_dim,
+                  c.num_nodes, p->T_out, ctrl);
+    GWN_LAUNCH_1D(loss_grad_kernel, p->PT() * p->ldo, st, (const float*)a->fwd.output, a->target, (i64)a->target_strides[0],
+                  (i64)a->target_strides[1], (i64)a->target_strides[2], a->scaler_mean, a->scaler_std, c.batch, c.out_dim,
+                  c.num_nodes, p->T_out, p->ldo, (const TrainCtrl*)ctrl, sc + p->o_dout, a->metrics);
+  }
+  gwn_backward_args ba;
+  memset(&ba, 0, sizeof(ba));
+  ba.params = fa.params; ba.supports = fa.supports; ba.support_strides = fa.support_strides; ba.input = fa.input;
+  for (int k = 0; k < 4; ++k) ba.input_strides[k] = fa.input_strides[k];
+  ba.grad_output = nullptr; ba.workspace = fa.workspace; ba.scratch = a->scratch; ba.grad_flat = a->grad_flat;
+  ba.grad_input = nullptr; ba.training = 1; ba.dropout_mode = fa.dropout_mode; ba.keep_masks = fa.keep_masks;
+  ba.seed = 0; ba.stream = fa.stream; ba.seed_device = fa.seed_device;
+  return plan_backward(p, &ba, true);
+}
+
+int gwn_adam_step(const gwn_adam_args* a) {
+  GWN_CHECK_ARG(a && a->param_flat && a->grad_flat && a->exp_avg && a->exp_avg_sq && a->live4 && a->hyper && a->ctrl,
+                "adam_step: null argument");
+  GWN_CHECK_ARG(a->n > 0 && a->n % 4 == 0, "adam_step: n must be a positive multiple of 4");
+  GWN_TRY(require_device());
+  cudaStream_t st = (cudaStream_t)a->stream;
+  TrainCtrl* ctrl = reinterpret_cast<TrainCtrl*>(a->ctrl);
+  ProfScope prof("clip_adam", st, 4.0 * a->n * 8.0, 0.0);
+  GWN_TRY(dev_memset(&ctrl->acc[4], 0, sizeof(double), st));
+  GWN_LAUNCH_1D(gradnorm_kernel, a->n / 4, st, (const float*)a->grad_flat, a->live4, a->n / 4, ctrl);
+  GWN_LAUNCH_1D(adam_kernel, a->n / 4, st, a->param_flat, a->grad_flat, a->exp_avg, a->exp_avg_sq, a->live4, a->n / 4,
+                reinterpret_cast<const AdamHyper*>(a->hyper), (const TrainCtrl*)ctrl, a->metrics);
+  return 0;
 }
 
 }  // extern "C"

@@ -140,6 +140,8 @@ inline int mlp_forward(const MlpFwdArgs& m, cudaStream_t stream) {
   GWN_CHECK_ARG(m.nseg >= 1 && m.nseg <= MAXSEG, "mlp: %d segments (max %d)", m.nseg, MAXSEG);
   GWN_CHECK_ARG(m.D % 4 == 0, "mlp: c_in per segment (%d) must be a multiple of 4", m.D);
   GWN_CHECK_ARG((reinterpret_cast<uintptr_t>(m.W) & 15) == 0, "mlp: weight pointer must be 16-byte aligned");
+  ProfScope prof("gcn_mlp_fwd", stream, 4.0 * m.P * ((double)m.nseg * m.D + (m.res ? 2.0 : 1.0) * m.C_out),
+                 2.0 * m.P * m.nseg * m.D * m.C_out);
   LdWK b;
   memset(&b, 0, sizeof(b));
   b.p[0] = m.W; b.set_wd(m.nseg * m.D); b.ldw = m.nseg * m.D;
@@ -195,6 +197,7 @@ inline int mlp_backward(const MlpBwdArgs& m, cudaStream_t stream) {
                 "mlp bwd: unsupported shape (nseg=%d D=%d C_out=%d)", m.nseg, m.D, m.C_out);
   const int Ktot = m.nseg * m.D;
   if (m.dsegs) {
+    ProfScope prof("gcn_mlp_dgrad", stream, 4.0 * m.P * ((double)Ktot + m.C_out), 2.0 * m.P * Ktot * m.C_out);
     LdWN b;
     memset(&b, 0, sizeof(b));
     b.p[0] = m.W; b.set_wd(Ktot); b.ldw = Ktot;
@@ -230,6 +233,8 @@ inline int mlp_backward(const MlpBwdArgs& m, cudaStream_t stream) {
       GWN_TRY((launch_gemm<TBig>(a, b, e, sh, stream)));
     }
   }
+  ProfScope prof_w("gcn_mlp_wgrad", stream, m.dW ? 4.0 * m.P * ((double)Ktot + m.C_out) : 0.0,
+                   m.dW ? 2.0 * m.P * (Ktot + 1.0) * m.C_out : 0.0);
   if (m.dW && current_math() == 1 && m.D == 32 && m.C_out == 32 && m.nseg <= 7 && m.drop.mode == GWN_DROPOUT_NONE &&
       m.P < 2147483647LL) {   // tf32 tier: tcgen05 + TMA reduction (weights and, through the all-ones block, the bias)
     TcRedArgs t;
@@ -270,6 +275,7 @@ inline int hop_index(const GcnShape& g, int s, int k) { return 1 + s * g.order +
 inline int gcn_hops_forward(const GcnShape& g, const float* x, const SupportView* sup_fwd, float* hops,
                             cudaStream_t stream, const TcSupports* tcs = nullptr) {
   const i64 PD = (i64)g.B * g.L * g.V * g.D;
+  ProfScope prof("nconv_fwd", stream, 4.0 * PD * (1 + g.S + 2.0 * g.S * (g.order - 1)), 2.0 * PD * g.V * g.S * g.order);
   for (int k = 1; k <= g.order; ++k) {
     const float* X[MAXSUP];
     float* Y[MAXSUP];
@@ -289,19 +295,23 @@ inline int gcn_hops_backward(const GcnShape& g, const float* x, const float* hop
                              float* dx, const float* add2, int T_out, float* const* dsup, const i64* ldds,
                              cudaStream_t stream, const TcSupports* tcs = nullptr) {
   const i64 PD = (i64)g.B * g.L * g.V * g.D;
-  for (int k = g.order; k >= 2; --k) {
-    const float* X[MAXSUP];
-    float* Y[MAXSUP];
-    const float* A[MAXSUP];
-    for (int s = 0; s < g.S; ++s) {
-      X[s] = dsegs + (i64)hop_index(g, s, k) * PD;
-      Y[s] = dsegs + (i64)hop_index(g, s, k - 1) * PD;
-      A[s] = Y[s];
+  {
+    ProfScope prof("nconv_bwd_dx_hops", stream, 4.0 * PD * 3.0 * g.S * (g.order - 1), 2.0 * PD * g.V * g.S * (g.order - 1));
+    for (int k = g.order; k >= 2; --k) {
+      const float* X[MAXSUP];
+      float* Y[MAXSUP];
+      const float* A[MAXSUP];
+      for (int s = 0; s < g.S; ++s) {
+        X[s] = dsegs + (i64)hop_index(g, s, k) * PD;
+        Y[s] = dsegs + (i64)hop_index(g, s, k - 1) * PD;
+        A[s] = Y[s];
+      }
+      GWN_TRY(node_gemm(sup_bwd, g.S, false, X, Y, A, nullptr, g.B, g.L, 0, g.V, g.D, stream, tcs));
     }
-    GWN_TRY(node_gemm(sup_bwd, g.S, false, X, Y, A, nullptr, g.B, g.L, 0, g.V, g.D, stream, tcs));
   }
   for (int s = 0; s < g.S; ++s) {
     if (!dsup || !dsup[s]) continue;
+    ProfScope prof("nconv_bwd_dA", stream, 4.0 * PD * 2.0 * g.order, 2.0 * PD * g.V * g.order);
     const float* Xp[MAXSUP];
     const float* Yp[MAXSUP];
     GWN_CHECK_ARG(g.order <= MAXSUP, "gcn bwd: order too large");
@@ -312,6 +322,7 @@ inline int gcn_hops_backward(const GcnShape& g, const float* x, const float* hop
     GWN_TRY(support_grad_gemm(Xp, Yp, g.order, dsup[s], ldds[s], g.B, g.L, g.V, g.D, stream));
   }
   {
+    ProfScope prof("nconv_bwd_dx_sum", stream, 4.0 * PD * (g.S + 2.0) + 4.0 * PD / g.L * T_out, 2.0 * PD * g.V * g.S);
     const float* X[MAXSUP];
     for (int s = 0; s < g.S; ++s) X[s] = dsegs + (i64)hop_index(g, s, 1) * PD;
     float* Y[1] = {dx};

@@ -17,29 +17,29 @@
 
 namespace gwn {
 
-constexpr int TR_MAXSRC = 8;
+constexpr int TR_MAXSRC = 16;
 
 struct TcRedSrc {
   const float* src;   // [nb][rows_src][row_width]
   int rows_src, row_width, col0, rshift;
-};
-// Where an accumulator element goes: MODE_MN element (blk, i, n); MODE_K element (v, w).
-struct TcRedOut {
-  int kind;           // 0: mlp wgrad  dW[n*ldw + blk*32 + i], ones block -> db[n]
-                      // 1: raw gated-conv wgrad  R[(blk*32 + i)*64 + n], ones block -> S[n]
-                      // 2: dA[v*ld + w]
-  float* out;
-  float* out_bias;
-  int ldw, nblk_real, V;
+  int nb;             // MODE_K: slabs of this pair (0 = TcRedArgs::nb)
 };
 struct TcRedArgs {
   int mode;           // 0 = MODE_MN, 1 = MODE_K
   TcRedSrc a[TR_MAXSRC];
   int na;             // MODE_MN: real A blocks (<= 7; the ones block is appended); MODE_K: number of (X, T) pairs
   TcRedSrc b[TR_MAXSRC];   // MODE_MN: b[0] only; MODE_K: one per pair
-  int N;              // MODE_MN: 32 or 64; MODE_K: output columns (multiple of 16, <= 256)
-  int nb, rows;       // MODE_MN: samples and B rows per sample; MODE_K: nb = slabs, rows = V
-  TcRedOut out;
+  int N;              // MODE_MN: 32 or 64; MODE_K: ignored (derived from rows)
+  int nb, rows;       // MODE_MN: samples and B rows per sample; MODE_K: default slabs per pair, rows = V
+  float* partial;     // scratch for the per-CTA partial results
+  i64 partial_floats; // its capacity
+};
+// What the launch produced: `nslots` partial results of `slot_floats` floats each.
+//   MODE_MN: slot layout [mtiles*128 rows = (blk, i)][N]; MODE_K: [mtiles*128 rows = v][Ntile], slot s covers the
+//   output columns (s % n_nt)*Ntile .. +Ntile.
+struct TcRedResult {
+  int nslots, mtiles, N, n_nt;
+  i64 slot_floats;
 };
 
 #if !GWN_EMU
@@ -50,9 +50,11 @@ struct TrMaps {
   CUtensorMap b[TR_MAXSRC];
 };
 struct TrParams {
-  int mode, na, nblk, mtiles, N, nbn, nb, chunks_per_sample, total_chunks, stages, a_bytes, b_bytes, tx_bytes;
+  int mode, na, nblk, mtiles, N, nbn, nb, chunks_per_sample, total_chunks, stages, a_bytes, b_bytes, tx_bytes, n_nt;
   int acol0[TR_MAXSRC], arshift[TR_MAXSRC], bcol0[TR_MAXSRC];
-  TcRedOut out;
+  int pair_end[TR_MAXSRC];   // MODE_K: cumulative chunk (slab) counts per pair
+  float* partial;
+  i64 slot_floats;
 };
 
 __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ TrMaps maps, const TrParams p) {
@@ -101,26 +103,29 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // contiguous chunk range of this CTA
-  const long long c_beg = (long long)p.total_chunks * blockIdx.x / gridDim.x;
-  const long long c_end = (long long)p.total_chunks * (blockIdx.x + 1) / gridDim.x;
+  // contiguous chunk range of this CTA (MODE_K: CTAs are split over n_nt column tiles of the output)
+  const int ntile = (int)(blockIdx.x % p.n_nt), kslot = (int)(blockIdx.x / p.n_nt), nk = (int)(gridDim.x / p.n_nt);
+  const int c_beg = (int)((long long)p.total_chunks * kslot / nk);
+  const int c_end = (int)((long long)p.total_chunks * (kslot + 1) / nk);
 
   if (warp == 0 && lane == 0) {
     // ===================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (long long c = c_beg; c < c_end; ++c) {
+    int pair = 0;
+    for (int c = c_beg; c < c_end; ++c) {
       if (!mbar_wait(empty_bar(stage), phase ^ 1u, 21)) break;
       const uint32_t sa = st0 + stage * stage_bytes, sb = sa + p.a_bytes;
       mbar_expect_tx(full_bar(stage), (uint32_t)p.tx_bytes);
       if (p.mode == 0) {
-        const int b = (int)(c / p.chunks_per_sample), r0 = (int)(c - (long long)b * p.chunks_per_sample) * 32;
+        const int b = c / p.chunks_per_sample, r0 = (c - b * p.chunks_per_sample) * 32;
         for (int j = 0; j < p.na; ++j) tma_load_3d(sa + j * 4096, &maps.a[j], full_bar(stage), p.acol0[j], r0 + p.arshift[j], b);
         for (int j = 0; j < p.nbn; ++j) tma_load_3d(sb + j * 4096, &maps.b[0], full_bar(stage), p.bcol0[j], r0, b);
       } else {
-        const int pair = (int)(c / p.nb), slab = (int)(c - (long long)pair * p.nb);
+        while (c >= p.pair_end[pair]) ++pair;
+        const int slab = c - (pair ? p.pair_end[pair - 1] : 0);
         for (int t = 0; t < p.mtiles; ++t) tma_load_3d(sa + t * 16384, &maps.a[pair], full_bar(stage), 0, t * 128, slab);
-        tma_load_3d(sb, &maps.b[pair], full_bar(stage), 0, 0, slab);
+        tma_load_3d(sb, &maps.b[pair], full_bar(stage), 0, ntile * p.N, slab);
       }
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
@@ -131,13 +136,13 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     int stage = 0;
     uint32_t phase = 0;
     bool first = true;
-    for (long long c = c_beg; c < c_end; ++c) {
+    for (int c = c_beg; c < c_end; ++c) {
       if (!mbar_wait(full_bar(stage), phase, 22)) break;
       tc_fence_after();
       const uint32_t sa = st0 + stage * stage_bytes, sb = sa + p.a_bytes;
 #pragma unroll 1
       for (int t = 0; t < p.mtiles; ++t) {
-        const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.N);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           uint64_t adesc, bdesc;
@@ -158,34 +163,25 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     }
     tc_commit(done_bar);
   } else if (warp >= 4) {
-    // ===================================================== epilogue: add this CTA's partial result to global
+    // ===================================================== epilogue: this CTA's partial result -> its private slot
+    // (plain 128-bit stores; a small follow-up kernel sums the slots -- float atomics from 148 CTAs onto the same
+    // few thousand addresses cost ~35-85 us per launch, ncu r01b)
     if (c_end > c_beg && mbar_wait(done_bar, 0, 23)) {
       tc_fence_after();
       const int ew = warp - 4;
       const int row = ew * 32 + lane;
+      float* slot = p.partial + (size_t)blockIdx.x * p.slot_floats;
       for (int t = 0; t < p.mtiles; ++t) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(t * 256);
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(t * p.N);
+        float* orow = slot + (size_t)(t * 128 + row) * p.N;
         for (int c0 = 0; c0 < p.N; c0 += 16) {
           uint32_t r[16];
           tc_ld16(taddr + c0, r);
           tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = c0 + j;
-            const float v = __uint_as_float(r[j]);
-            if (p.out.kind == 2) {
-              const int vv = t * 128 + row;
-              if (vv < p.out.V && n < p.out.V) atomicAdd(p.out.out + (size_t)vv * p.out.ldw + n, v);
-            } else {
-              const int blk = t * 4 + ew, i = lane;
-              if (blk < p.out.nblk_real) {
-                if (p.out.kind == 0) atomicAdd(p.out.out + (size_t)n * p.out.ldw + blk * 32 + i, v);
-                else atomicAdd(p.out.out + (size_t)(blk * 32 + i) * 64 + n, v);
-              } else if (blk == p.out.nblk_real && i == 0 && p.out.out_bias) {
-                atomicAdd(p.out.out_bias + n, v);
-              }
-            }
-          }
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(orow + c0 + 4 * q) = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                                         __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
         }
       }
     }

@@ -7,11 +7,13 @@ import torch.optim as optim
 
 if __package__:
     from . import metrics as util
+    from . import fused as _fused
     from .model import gwnet
 else:  # top-level import next to ``model`` (the reference's style)
     import importlib as _il
     from model import gwnet  # noqa: F401
     util = _il.import_module("graph_wavenet_b200.metrics")
+    _fused = _il.import_module("graph_wavenet_b200.fused")
 
 
 class trainer():
@@ -25,7 +27,15 @@ class trainer():
                            dilation_channels=nhid, skip_channels=nhid * 8, end_channels=nhid * 16, blocks=blocks,
                            layers=layers)
         self.model.to(device)
-        self.optimizer = optim.Adam(self.model.parameters(), lr=lrate, weight_decay=wdecay)
+        # engine.py:33 -- Adam(lr, weight_decay as L2-in-gradient).  The fused step (default) runs clip + Adam as one
+        # pass of gwn_adam_step over flat buffers; GWNET_B200_FUSED_STEP=0 keeps torch.optim.Adam on the autograd path.
+        self.fused = _fused.fused_enabled()
+        self.use_graph = _fused.graph_enabled()
+        if self.fused:
+            self.optimizer = _fused.FusedAdam(self.model.parameters(), lr=lrate, weight_decay=wdecay)
+        else:
+            self.optimizer = optim.Adam(self.model.parameters(), lr=lrate, weight_decay=wdecay)
+        self._steps = {}
         self.loss = util.masked_mae
         self.scaler = scaler
         self.clip = 5
@@ -46,6 +56,8 @@ class trainer():
     def _allreduce_grads(self):
         import torch.distributed as dist
         flat = getattr(self.model, "_last_grad_flat", None)
+        if getattr(self.model, "_flat", None) is not None:
+            flat = self.model._flat.grad
         grads = [p.grad for p in self.model.parameters() if p.grad is not None]
         lo, hi = (flat.data_ptr(), flat.data_ptr() + flat.numel() * 4) if flat is not None else (0, 0)
         if flat is not None and all(lo <= g.data_ptr() < hi for g in grads):
@@ -56,9 +68,37 @@ class trainer():
                 dist.all_reduce(g)
                 g.mul_(1.0 / self.world)
 
+    def _bind_flat(self, input):
+        m = self.model
+        if m._flat is None or not m._flat.intact():
+            m._flat = _fused.FlatParams(m, m._runner(input.shape[0], input.shape[3]).plan)
+            self.optimizer._flat = None
+        if not self.optimizer.bound:
+            self.optimizer.bind(m._flat, int(torch.randint(0, 2 ** 62, (1,)).item()))
+
+    def _fused_step(self, input, real_val):
+        key = (tuple(input.shape), tuple(real_val.shape), self.model.precision, bool(self.use_graph), float(self.model.dropout))
+        st = self._steps.get(key)
+        if st is None or not st.valid():
+            self._steps = {k: v for k, v in self._steps.items() if v.valid()}
+            st = _fused.FusedStep(self, input, real_val, self.use_graph)
+            self._steps[key] = st
+        return st
+
     def train(self, input, real_val):
         self.model.train()
-        self.optimizer.zero_grad()
+        if self.fused and self.loss is util.masked_mae:
+            # forward + masked-MAE loss + backward + [all-reduce] + clip + Adam + metrics: one CUDA graph, one host sync.
+            # (the +1 left pad of engine.py:44 and the receptive-field pad of model.py:176-180 are the same zero column,
+            # folded into the start conv)
+            return self._fused_step(input, real_val).run(input, real_val)
+        # autograd path: a custom self.loss, or GWNET_B200_FUSED_STEP=0
+        if isinstance(self.optimizer, _fused.FusedAdam):
+            self._bind_flat(input)
+            self.optimizer.zero_grad(set_to_none=False)     # p.grad are views of the flat gradient buffer: keep them
+            self.optimizer.max_norm, self.optimizer.grad_scale = 0.0, 1.0
+        else:
+            self.optimizer.zero_grad()
         input = nn.functional.pad(input, (1, 0, 0, 0))
         output = self.model(input)
         output = output.transpose(1, 3)

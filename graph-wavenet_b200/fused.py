@@ -1,0 +1,274 @@
+"""Fused optimisation step of ``engine.trainer.train`` (engine.py:41-58).
+
+``FlatParams`` re-homes the model's parameters (and their ``.grad``) as views of two flat fp32 buffers laid out
+like the plan's flat gradient buffer, ``FusedAdam`` is the ``torch.optim``-shaped front of ``gwn_adam_step``
+(clip_grad_norm_ + Adam with L2 weight decay in one pass over those buffers) and ``FusedStep`` strings
+``gwn_plan_train_fwd_bwd`` -> [NCCL all-reduce] -> ``gwn_adam_step`` -> metrics read-back into ONE CUDA graph.
+PyTorch supplies memory, the stream, graph capture and the collective; all arithmetic is behind the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+from . import native as N
+
+
+import contextlib
+
+
+def _dev_ctx(dev):
+    return torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0
+
+
+def _sync(dev):
+    if dev.type == "cuda":
+        torch.cuda.current_stream(dev).synchronize()
+
+
+def _pinned(t, dev):
+    return t.pin_memory() if dev.type == "cuda" else t
+
+
+class FlatParams:
+    """Parameters and gradients of one ``gwnet`` as views of flat buffers (offsets = the plan's gradient layout)."""
+
+    def __init__(self, model, plan):
+        named = list(model.named_parameters())
+        offs = [o for o in plan.grad_offsets if o >= 0]
+        nums = [n for n, o in zip(plan.numels, plan.grad_offsets) if o >= 0]
+        if len(named) != len(offs):
+            raise N.GwnError("gwnet_b200: parameter list does not match the native plan")
+        dev = named[0][1].device
+        self.n = plan.grad_floats
+        if self.n % 4:
+            raise N.GwnError("flat gradient buffer must be a multiple of 4 floats")
+        self.param = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        live4 = torch.zeros(self.n // 4, dtype=torch.uint8)
+        with torch.no_grad():
+            for (name, p), off, ne in zip(named, offs, nums):
+                if p.numel() != ne or p.dtype != torch.float32:
+                    raise N.GwnError(f"parameter {name}: unexpected size/dtype for the native plan")
+                self.param[off:off + ne].copy_(p.detach().reshape(-1))
+                p.data = self.param[off:off + ne].view(p.shape)
+                if p.requires_grad and model._live(name):
+                    p.grad = self.grad[off:off + ne].view(p.shape)
+                    live4[off // 4:(off + ne + 3) // 4] = 1
+                else:
+                    p.grad = None
+        self.live4 = live4.to(dev)
+        self.ptr0 = named[0][1].data_ptr()
+        self.probe = named[0][1]
+        model._entries = None
+
+    def intact(self) -> bool:
+        """False once something (``model.to``, ``p.data = ...``) moved the parameters out of the flat buffer."""
+        return self.probe.data_ptr() == self.ptr0
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """``torch.optim.Adam(params, lr, weight_decay=wd)`` semantics (engine.py:33) executed by ``gwn_adam_step`` on the
+    flat buffers; ``max_norm`` folds ``clip_grad_norm_`` (engine.py:53-54) into the same pass.  Hyper-parameters are
+    read from ``param_groups[0]`` before every step, so schedulers that edit ``lr`` keep working."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._flat: Optional[FlatParams] = None
+        self._hyper_cached = None
+        self.max_norm = 0.0        # set by the trainer (self.clip)
+        self.grad_scale = 1.0      # 1/world under data parallelism
+
+    # -- binding to a model's flat buffers (done by the trainer on first use)
+    def bind(self, flat: FlatParams, seed: int):
+        lib = N.get_lib()
+        dev = flat.param.device
+        self._lib = lib
+        self._flat = flat
+        self.exp_avg = torch.zeros_like(flat.param)
+        self.exp_avg_sq = torch.zeros_like(flat.param)
+        self.ctrl = torch.zeros(int(lib.dll.gwn_train_ctrl_bytes()), dtype=torch.uint8, device=dev)
+        self.metrics = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        self._hyper_host = _pinned(torch.zeros(8, dtype=torch.float32), dev)
+        with _dev_ctx(dev):
+            _sync(dev)
+            lib.check(lib.dll.gwn_train_ctrl_init(self.ctrl.data_ptr(), int(seed) & (2 ** 64 - 1), 0), "gwn_train_ctrl_init")
+        self._hyper_cached = None
+
+    @property
+    def bound(self):
+        return self._flat is not None
+
+    def step_count(self) -> int:
+        seed, step = C.c_uint64(0), C.c_int64(0)
+        self._lib.check(self._lib.dll.gwn_train_ctrl_read(self.ctrl.data_ptr(), C.byref(seed), C.byref(step)))
+        return step.value
+
+    def sync_hyper(self):
+        g = self.param_groups[0]
+        h = (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
+             float(self.max_norm or 0.0), float(self.grad_scale), 0.0)
+        if h != self._hyper_cached:
+            self._hyper_host.copy_(torch.tensor(h, dtype=torch.float32))
+            self.hyper.copy_(self._hyper_host, non_blocking=True)
+            self._hyper_cached = h
+
+    def adam_args(self, stream: int) -> N.GwnAdamArgs:
+        f = self._flat
+        a = N.GwnAdamArgs()
+        a.param_flat, a.grad_flat = f.param.data_ptr(), f.grad.data_ptr()
+        a.exp_avg, a.exp_avg_sq = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        a.live4, a.n = f.live4.data_ptr(), f.n
+        a.hyper, a.ctrl, a.metrics, a.stream = self.hyper.data_ptr(), self.ctrl.data_ptr(), self.metrics.data_ptr(), stream
+        return a
+
+    def launch(self):
+        """Enqueue clip + Adam on the current stream (capturable)."""
+        dev = self._flat.param.device
+        a = self.adam_args(_stream(dev))
+        self._lib.check(self._lib.dll.gwn_adam_step(C.byref(a)), "gwn_adam_step")
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        """Eager use (``loss.backward(); optimizer.step()``): gradients must live in the bound flat buffer."""
+        loss = closure() if closure is not None else None
+        if not self.bound:
+            raise N.GwnError("FusedAdam.step: optimizer is not bound to a gwnet (trainer.train does it on first use)")
+        f = self._flat
+        lo, hi = f.grad.data_ptr(), f.grad.data_ptr() + 4 * f.n
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is not None and not (lo <= p.grad.data_ptr() < hi):
+                    raise N.GwnError("FusedAdam.step: a gradient lives outside the flat gradient buffer")
+        self.sync_hyper()
+        with _dev_ctx(f.param.device):
+            self.launch()
+        return loss
+
+
+class FusedStep:
+    """One captured ``trainer.train`` step for a fixed (batch, seq) shape."""
+
+    def __init__(self, trainer, x: torch.Tensor, y: torch.Tensor, use_graph: bool):
+        model, opt = trainer.model, trainer.optimizer
+        lib = N.get_lib()
+        self.lib, self.trainer = lib, trainer
+        dev = x.device
+        B, F, Nn, T = x.shape
+        runner = model._runner(B, T)
+        self.runner, self.plan = runner, runner.plan
+        if model._flat is None or not model._flat.intact():
+            model._flat = FlatParams(model, runner.plan)
+            opt._flat = None
+        if not opt.bound:
+            opt.bind(model._flat, int(torch.randint(0, 2 ** 62, (1,)).item()))
+        self.flat = model._flat
+        cfg = runner.cfg
+        # static buffers (the graph bakes their addresses)
+        self.x = torch.empty((B, T, Nn, F), dtype=torch.float32, device=dev).permute(0, 3, 2, 1)   # loader layout [B,T,N,F]
+        self.y = torch.empty(tuple(y.shape), dtype=torch.float32, device=dev)
+        self.out = torch.empty((B, cfg.out_dim, Nn, self.plan.t_out), dtype=torch.float32, device=dev)
+        self.workspace = torch.empty(self.plan.fwd_bytes, dtype=torch.uint8, device=dev)
+        self.scratch = torch.empty(self.plan.bwd_bytes, dtype=torch.uint8, device=dev)
+        self.metrics_host = _pinned(torch.zeros(4, dtype=torch.float32), dev)
+        self.table = [t.detach() for t in model._table()]
+        self.ptab = runner._param_table(self.table)
+        self.sup, self.sptrs, self.sstrides = runner._supports(model.supports)
+        if y.dim() != 3 or y.shape[0] != B or y.shape[1] != Nn or y.shape[2] != cfg.out_dim:
+            raise N.GwnError(f"real_val must be [B={B}, N={Nn}, out_dim={cfg.out_dim}], got {tuple(y.shape)}")
+        self.use_dropout = cfg.dropout > 0 and cfg.gcn
+        self.masks = model._dropout_masks
+        self.mptrs = None
+        self.graph = None
+        self.use_graph = use_graph = bool(use_graph and dev.type == "cuda")
+        self.key_ptrs = self._ptr_key()
+        if use_graph:
+            if trainer.world > 1:     # NCCL must have built its communicator before capture
+                import torch.distributed as dist
+                dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self.graph = g
+
+    def _ptr_key(self):
+        return (self.table[0].data_ptr(), self.table[-1].data_ptr(), tuple(s.data_ptr() for s in self.sup),
+                self.trainer.world, id(self.trainer.model._dropout_masks))
+
+    def valid(self) -> bool:
+        m = self.trainer.model
+        return (self.flat is m._flat and self.flat.intact() and m._entries is not None
+                and self.key_ptrs[2] == tuple(s.data_ptr() for s in (m.supports or [])[:len(self.sup)])
+                and self.key_ptrs[3] == self.trainer.world and self.key_ptrs[4] == id(m._dropout_masks))
+
+    def _train_args(self, stream: int) -> N.GwnTrainArgs:
+        a = N.GwnTrainArgs()
+        f = a.fwd
+        f.params, f.supports, f.support_strides = self.ptab, self.sptrs, self.sstrides
+        f.input = self.x.data_ptr()
+        for k in range(4):
+            f.input_strides[k] = self.x.stride(k)
+        f.output, f.workspace, f.training = self.out.data_ptr(), self.workspace.data_ptr(), 1
+        f.dropout_mode = N.DROPOUT_NONE
+        if self.use_dropout:
+            if self.masks is not None:
+                f.dropout_mode = N.DROPOUT_MASK
+                self.mptrs = N.ptr_array([m.data_ptr() for m in self.masks])
+                f.keep_masks = self.mptrs
+            else:
+                f.dropout_mode = N.DROPOUT_PHILOX
+        f.stream = stream
+        opt = self.trainer.optimizer
+        a.scratch, a.grad_flat, a.target = self.scratch.data_ptr(), self.flat.grad.data_ptr(), self.y.data_ptr()
+        for k in range(3):
+            a.target_strides[k] = self.y.stride(k)
+        a.scaler_mean, a.scaler_std = float(self.trainer.scaler.mean), float(self.trainer.scaler.std)
+        a.ctrl, a.metrics = opt.ctrl.data_ptr(), opt.metrics.data_ptr()
+        return a
+
+    def _enqueue(self):
+        tr = self.trainer
+        dev = self.x.device
+        with _dev_ctx(dev):
+            stream = _stream(dev)
+            a = self._train_args(stream)
+            self.lib.check(self.lib.dll.gwn_plan_train_fwd_bwd(self.plan.handle, C.byref(a)), "gwn_plan_train_fwd_bwd")
+            if tr.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(self.flat.grad)          # ONE collective per step; 1/world is folded into Adam
+            tr.optimizer.launch()
+            self.metrics_host.copy_(tr.optimizer.metrics, non_blocking=True)
+
+    def run(self, x: torch.Tensor, y: torch.Tensor):
+        tr = self.trainer
+        opt = tr.optimizer
+        opt.max_norm = float(tr.clip) if tr.clip is not None else 0.0
+        opt.grad_scale = 1.0 / tr.world
+        opt.sync_hyper()
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+        _sync(self.x.device)      # the step's single host sync
+        tr.model._last_grad_flat = self.flat.grad
+        m = self.metrics_host
+        return float(m[0]), float(m[1]), float(m[2])
+
+
+def fused_enabled() -> bool:
+    return os.environ.get("GWNET_B200_FUSED_STEP", "1") != "0"
+
+
+def graph_enabled() -> bool:
+    return os.environ.get("GWNET_B200_GRAPH", "1") != "0"

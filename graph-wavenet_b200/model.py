@@ -369,6 +369,7 @@ class gwnet(nn.Module):
         self._entries = None
         self._dropout_masks = None   # test hook: list of uint8 BLNC keep-masks, one per layer
         self._static_workspace = None
+        self._flat = None            # FlatParams of the fused trainer step (fused.py)
 
     # ---- plan plumbing
     def _apply(self, fn, *a, **k):

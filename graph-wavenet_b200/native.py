@@ -40,7 +40,7 @@ class GwnForwardArgs(C.Structure):
         ("params", c_void_pp), ("supports", c_void_pp), ("support_strides", C.POINTER(C.c_int64)),
         ("input", C.c_void_p), ("input_strides", C.c_int64 * 4), ("output", C.c_void_p),
         ("workspace", C.c_void_p), ("training", C.c_int), ("dropout_mode", C.c_int),
-        ("keep_masks", c_void_pp), ("seed", C.c_uint64), ("stream", C.c_void_p),
+        ("keep_masks", c_void_pp), ("seed", C.c_uint64), ("stream", C.c_void_p), ("seed_device", C.c_void_p),
     ]
 
 
@@ -50,7 +50,23 @@ class GwnBackwardArgs(C.Structure):
         ("input", C.c_void_p), ("input_strides", C.c_int64 * 4), ("grad_output", C.c_void_p),
         ("workspace", C.c_void_p), ("scratch", C.c_void_p), ("grad_flat", C.c_void_p),
         ("grad_input", C.c_void_p), ("training", C.c_int), ("dropout_mode", C.c_int),
-        ("keep_masks", c_void_pp), ("seed", C.c_uint64), ("stream", C.c_void_p),
+        ("keep_masks", c_void_pp), ("seed", C.c_uint64), ("stream", C.c_void_p), ("seed_device", C.c_void_p),
+    ]
+
+
+class GwnTrainArgs(C.Structure):
+    _fields_ = [
+        ("fwd", GwnForwardArgs), ("scratch", C.c_void_p), ("grad_flat", C.c_void_p), ("target", C.c_void_p),
+        ("target_strides", C.c_int64 * 3), ("scaler_mean", C.c_float), ("scaler_std", C.c_float),
+        ("ctrl", C.c_void_p), ("metrics", C.c_void_p),
+    ]
+
+
+class GwnAdamArgs(C.Structure):
+    _fields_ = [
+        ("param_flat", C.c_void_p), ("grad_flat", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+        ("live4", C.c_void_p), ("n", C.c_int64), ("hyper", C.c_void_p), ("ctrl", C.c_void_p), ("metrics", C.c_void_p),
+        ("stream", C.c_void_p),
     ]
 
 
@@ -64,11 +80,12 @@ class GwnGcnDesc(C.Structure):
 
 # every symbol include/gwnet_b200.h declares (tests check that the library exports them all)
 EXPORTS = [
-    "gwn_last_error", "gwn_abi_version", "gwn_launch_count", "gwn_device_info", "gwn_permute4d",
+    "gwn_last_error", "gwn_abi_version", "gwn_launch_count", "gwn_device_info", "gwn_profile_begin", "gwn_profile_end", "gwn_permute4d",
     "gwn_node_contract", "gwn_tc_error_flag", "gwn_tc_debug_buffer", "gwn_tc_debug_mode", "gwn_nconv_fwd", "gwn_nconv_bwd", "gwn_linear_fwd", "gwn_linear_bwd",
     "gwn_gcn_fwd", "gwn_gcn_bwd_scratch_floats", "gwn_gcn_bwd",
     "gwn_plan_create", "gwn_plan_destroy", "gwn_plan_workspace_bytes", "gwn_plan_param_count",
     "gwn_plan_param_info", "gwn_plan_out_len", "gwn_plan_debug_layout", "gwn_plan_forward", "gwn_plan_backward",
+    "gwn_train_ctrl_bytes", "gwn_train_ctrl_init", "gwn_train_ctrl_read", "gwn_plan_train_fwd_bwd", "gwn_adam_step",
 ]
 
 
@@ -99,6 +116,7 @@ class Lib:
         d.gwn_launch_count.restype = C.c_longlong
         d.gwn_device_info.argtypes = [C.POINTER(C.c_int), C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_int)]
+        d.gwn_profile_end.argtypes = [C.c_char_p, C.c_int]
         i64p = C.POINTER(C.c_int64)
         d.gwn_permute4d.argtypes = [C.c_void_p, i64p, C.c_void_p, i64p, i64p, C.c_void_p]
         d.gwn_node_contract.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
@@ -128,8 +146,13 @@ class Lib:
         d.gwn_plan_debug_layout.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         d.gwn_plan_forward.argtypes = [C.c_void_p, C.POINTER(GwnForwardArgs)]
         d.gwn_plan_backward.argtypes = [C.c_void_p, C.POINTER(GwnBackwardArgs)]
-        if d.gwn_abi_version() != 1:
-            raise GwnError(f"{path}: ABI version {d.gwn_abi_version()} != 1")
+        d.gwn_train_ctrl_bytes.restype = C.c_size_t
+        d.gwn_train_ctrl_init.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
+        d.gwn_train_ctrl_read.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
+        d.gwn_plan_train_fwd_bwd.argtypes = [C.c_void_p, C.POINTER(GwnTrainArgs)]
+        d.gwn_adam_step.argtypes = [C.POINTER(GwnAdamArgs)]
+        if d.gwn_abi_version() != 2:
+            raise GwnError(f"{path}: ABI version {d.gwn_abi_version()} != 2")
 
     def check(self, status: int, what: str = ""):
         if status != 0:

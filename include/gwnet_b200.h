@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GWN_ABI_VERSION 1
+#define GWN_ABI_VERSION 2
 
 typedef enum gwn_status {
   GWN_OK = 0,
@@ -65,6 +65,14 @@ int gwn_abi_version(void);
 long long gwn_launch_count(int reset);
 /* Number of CUDA devices visible; fills name (<=255 chars) and SM count of the current one. */
 int gwn_device_info(int* n_devices, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor);
+
+/* Per-operator device timing for the roofline report (bench.py): between gwn_profile_begin() and
+ * gwn_profile_end() every operator of the plan is bracketed by CUDA events on its launching stream.
+ * gwn_profile_end synchronises the device and writes a JSON array of
+ * {"op", "calls", "ms", "bytes", "flops"} (bytes / flops = algorithmic work).
+ * Do not use while a CUDA graph is being captured.                                                    */
+int gwn_profile_begin(void);
+int gwn_profile_end(char* buf, int len);
 
 /* ------------------------------------------------------------------ layout helpers */
 /* dst[i0,i1,i2,i3] = src[i0,i1,i2,i3] for two arbitrarily strided fp32 4-D tensors
@@ -175,6 +183,7 @@ typedef struct gwn_forward_args {
   const uint8_t* const* keep_masks; /* n_layers pointers [B*L_i*N*C] (GWN_DROPOUT_MASK)     */
   uint64_t seed;                 /* Philox key (GWN_DROPOUT_PHILOX)                         */
   void* stream;
+  const uint64_t* seed_device;   /* optional: read the Philox key from device memory instead (CUDA graphs)  */
 } gwn_forward_args;
 
 int gwn_plan_forward(gwn_plan* p, const gwn_forward_args* a);
@@ -195,9 +204,52 @@ typedef struct gwn_backward_args {
   const uint8_t* const* keep_masks;
   uint64_t seed;
   void* stream;
+  const uint64_t* seed_device;   /* as in the matching forward call                                         */
 } gwn_backward_args;
 
 int gwn_plan_backward(gwn_plan* p, const gwn_backward_args* a);
+
+/* ------------------------------------------------------------------ trainer.train (engine.py:41-58)
+ * One optimisation step as a fixed sequence of launches with no host round trip, so that it can be captured in
+ * a CUDA graph:  gwn_plan_train_fwd_bwd  = forward + inverse_transform + masked MAE/MAPE/RMSE (Utils/util.py:116-117,
+ * 510-552) + backward into the flat gradient buffer;  [the caller's gradient all-reduce for data parallelism];
+ * gwn_adam_step = clip_grad_norm_ (engine.py:53-54) + Adam with L2 weight decay (engine.py:33,55) on flat buffers.
+ * A small device control block (gwn_train_ctrl_bytes) carries the dropout key, the Adam step count and the
+ * reduction accumulators from launch to launch.                                                              */
+size_t gwn_train_ctrl_bytes(void);
+/* Synchronous; (re)initialises the control block: dropout key, Adam step count. */
+int gwn_train_ctrl_init(void* ctrl, uint64_t seed, int64_t step);
+int gwn_train_ctrl_read(const void* ctrl, uint64_t* seed, int64_t* step);
+
+typedef struct gwn_train_args {
+  gwn_forward_args fwd;          /* as for gwn_plan_forward (training = 1); output = caller buffer [B,out_dim,N,T_out];
+                                    seed / seed_device are ignored: the key comes from the control block            */
+  void* scratch;                 /* bwd bytes                                                                       */
+  float* grad_flat;              /* grad_floats floats; written                                                     */
+  const float* target;           /* real_val [B,N,out_dim] fp32, any strides (engine.py:48)                         */
+  int64_t target_strides[3];
+  float scaler_mean, scaler_std; /* StandardScaler.inverse_transform (Utils/util.py:116-117)                        */
+  void* ctrl;                    /* control block                                                                    */
+  float* metrics;                /* device float[4]: masked MAE (the loss), MAPE, RMSE, [3] = gradient norm, written by
+                                    gwn_adam_step                                                                    */
+} gwn_train_args;
+int gwn_plan_train_fwd_bwd(gwn_plan* p, const gwn_train_args* a);
+
+typedef struct gwn_adam_args {
+  float* param_flat;             /* n floats, the layout of the plan's flat gradient buffer; updated in place        */
+  float* grad_flat;              /* n floats; on return holds the (scaled, clipped) gradient, like p.grad           */
+  float* exp_avg;                /* n floats, Adam first moment                                                       */
+  float* exp_avg_sq;             /* n floats, Adam second moment                                                      */
+  const uint8_t* live4;          /* n/4 bytes: 1 = this group of 4 floats belongs to a parameter that has a gradient
+                                    (dead parameters are skipped by clip and Adam alike)                 */
+  int64_t n;                     /* multiple of 4                                                                     */
+  const float* hyper;            /* device float[8]: lr, beta1, beta2, eps, weight_decay, max_norm (<=0: no clip),
+                                    grad_scale (1/world after a summing all-reduce), unused                          */
+  void* ctrl;
+  float* metrics;                /* device float[4] or NULL; [3] receives the total gradient norm                    */
+  void* stream;
+} gwn_adam_args;
+int gwn_adam_step(const gwn_adam_args* a);
 
 #ifdef __cplusplus
 }

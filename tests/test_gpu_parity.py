@@ -343,3 +343,72 @@ def test_tf32_tier_metr_la_full_size(M):
     print(f"[tf32 tier] output rel-L2 {float((out.cpu() - oout.detach()).norm() / oout.detach().norm()):.2e}, "
           f"global grad rel-L2 {gd ** 0.5 / gn:.2e}, worst tensor {worst[1]} {worst[0]:.2e}")
     assert gd ** 0.5 <= TOL_TF32 * gn
+
+
+# ------------------------------------------------------------------------------------------------ fused train step
+def _make_trainer(dev, cfg, sup, state0, dropout, fused, graph, monkeypatch):
+    from graph_wavenet_b200 import engine as E
+    from graph_wavenet_b200.metrics import StandardScaler
+    monkeypatch.setenv("GWNET_B200_FUSED_STEP", "1" if fused else "0")
+    monkeypatch.setenv("GWNET_B200_GRAPH", "1" if graph else "0")
+    tr = E.trainer(StandardScaler(54.0, 20.0), cfg.in_dim, cfg.out_dim, cfg.num_nodes, cfg.residual_channels, dropout,
+                   1e-3, 1e-4, dev, sup, cfg.gcn_bool, cfg.addaptadj, None, cfg.blocks, cfg.layers)
+    tr.model.load_state_dict(state0)
+    return tr
+
+
+def test_fused_graph_step_equals_autograd_step(M, monkeypatch):
+    """One CUDA-graph replay per trainer.train (fused loss / clip / Adam kernels) must track the autograd path
+    (torch loss ops, clip_grad_norm_, torch.optim.Adam) step for step: engine.py:41-58."""
+    dev = torch.device("cuda:0")
+    rec = load_case("dbl_adp")
+    cfg = rec["cfg"]
+    sup = [s.to(dev) for s in rec["supports"]]
+    x, y = rec["x"].to(dev), rec["y"][:, :, : cfg.out_dim].to(dev)
+    y[0, 0, :] = 0.0                                 # exercise the null-value mask
+    runs = {}
+    for mode, (fused, graph) in {"graph": (True, True), "eager-fused": (True, False), "autograd": (False, False)}.items():
+        tr = _make_trainer(dev, cfg, sup, rec["state0"], 0.0, fused, graph, monkeypatch)
+        mets = [tr.train(x.transpose(1, 3).contiguous().transpose(1, 3), y) for _ in range(4)]   # loader-style strided input
+        runs[mode] = (mets, {k: v.detach().clone() for k, v in tr.model.state_dict().items()}, tr)
+    for mode in ("graph", "eager-fused"):
+        for a, b in zip(runs[mode][0], runs["autograd"][0]):
+            for u, v in zip(a, b):
+                assert abs(u - v) <= 1e-4 * abs(v) + 1e-6, (mode, runs[mode][0], runs["autograd"][0])
+        for k, v in runs["autograd"][1].items():
+            assert_close_rel(runs[mode][1][k].float(), v.float(), 2e-3, f"{mode}: state after 4 steps {k}", floor=1e-5)
+    tr = runs["graph"][2]
+    assert tr.optimizer.step_count() == 4
+    assert len(tr._steps) == 1 and next(iter(tr._steps.values())).graph is not None
+    # p.grad keeps reference semantics: the clipped gradient of the last step, None for dead parameters (G4)
+    last = cfg.blocks * cfg.layers - 1
+    for k, p in tr.model.named_parameters():
+        dead = k.startswith("residual_convs.") or k.startswith(f"gconv.{last}.") or k.startswith(f"bn.{last}.")
+        assert (p.grad is None) == dead, k
+    ga = {k: p.grad for k, p in runs["autograd"][2].model.named_parameters() if p.grad is not None}
+    gnorm = sum(float(g.double().pow(2).sum()) for g in ga.values()) ** 0.5
+    for k, p in tr.model.named_parameters():
+        if p.grad is not None:
+            assert_close_rel(p.grad, ga[k], 2e-3, "clipped grad " + k, floor=2e-5 * gnorm)
+
+
+def test_fused_graph_step_draws_fresh_dropout_masks(M, monkeypatch):
+    """The Philox key lives in device memory and advances inside the graph: replays must not repeat masks."""
+    dev = torch.device("cuda:0")
+    rec = load_case("dbl_adp")
+    cfg = rec["cfg"]
+    sup = [s.to(dev) for s in rec["supports"]]
+    x, y = rec["x"].to(dev), rec["y"][:, :, : cfg.out_dim].to(dev)
+    tr = _make_trainer(dev, cfg, sup, rec["state0"], 0.3, True, True, monkeypatch)
+    for g in tr.optimizer.param_groups:
+        g["lr"] = 0.0                                 # frozen weights: the loss can only move through the masks
+        g["weight_decay"] = 0.0
+    losses = [tr.train(x, y)[0] for _ in range(4)]
+    assert len({round(l, 6) for l in losses}) == 4, losses
+    # a learning-rate change reaches the captured graph through the device-side hyper-parameter block
+    before = tr.model.start_conv.weight.detach().clone()
+    tr.train(x, y)
+    assert torch.equal(before, tr.model.start_conv.weight)
+    tr.optimizer.param_groups[0]["lr"] = 1e-2
+    tr.train(x, y)
+    assert not torch.equal(before, tr.model.start_conv.weight)

@@ -97,3 +97,67 @@ def test_emulated_dropout_mask_and_philox(emu):
     o2, _ = r.forward([p.clone() for p in params], rec["supports"], x, training=True, dropout_mode=N.DROPOUT_PHILOX, seed=7)
     o3, _ = r.forward([p.clone() for p in params], rec["supports"], x, training=True, dropout_mode=N.DROPOUT_PHILOX, seed=8)
     assert torch.equal(o1, o2) and not torch.equal(o1, o3)
+
+
+@pytest.mark.parametrize("name", ["dbl_adp", "aptonly"])
+def test_emulated_fused_train_step_matches_reference_trainer(emu, name):
+    """gwn_plan_train_fwd_bwd + gwn_adam_step (loss, metrics, clip, Adam as kernels) against 3 recorded
+    ``engine.trainer.train`` steps of the real reference (metrics 1e-4, state 2e-3 -- see test_gpu_parity)."""
+    import ctypes as C
+    rec = load_case(name)
+    cfg = rec["cfg"]
+    x = rec["x"]                                   # [B, F, N, 12]: the plan folds the trainer's +1 pad
+    y = rec["y"][:, :, : cfg.out_dim].contiguous()
+    r = runner_for(emu, cfg, x.shape[0], x.shape[3])
+    plan = r.plan
+    n = plan.grad_floats
+    flat, grad = torch.zeros(n), torch.zeros(n)
+    m, v = torch.zeros(n), torch.zeros(n)
+    live4 = torch.zeros(n // 4, dtype=torch.uint8)
+    last = cfg.blocks * cfg.layers - 1
+    table = []
+    for k, off, ne in zip(plan.names, plan.grad_offsets, plan.numels):
+        t = rec["state0"][k].clone().contiguous()
+        if off >= 0:
+            flat[off:off + ne] = t.reshape(-1)
+            t = flat[off:off + ne]
+            dead = (k.startswith("residual_convs.") and cfg.gcn_active) or k.startswith(f"gconv.{last}.") or k.startswith(f"bn.{last}.")
+            if not dead:
+                live4[off // 4:(off + ne + 3) // 4] = 1
+        table.append(t)
+    ptab = N.ptr_array([t.data_ptr() for t in table])
+    sup, sptrs, sstr = r._supports(rec["supports"])
+    out = torch.zeros(x.shape[0], cfg.out_dim, cfg.num_nodes, plan.t_out)
+    ws = torch.zeros(plan.fwd_bytes, dtype=torch.uint8)
+    sc = torch.zeros(plan.bwd_bytes, dtype=torch.uint8)
+    ctrl = torch.zeros(int(emu.dll.gwn_train_ctrl_bytes()), dtype=torch.uint8)
+    emu.check(emu.dll.gwn_train_ctrl_init(ctrl.data_ptr(), 1234, 0))
+    metrics = torch.zeros(4)
+    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 1e-4, 5.0, 1.0, 0.0])
+    a = N.GwnTrainArgs()
+    a.fwd.params, a.fwd.supports, a.fwd.support_strides = ptab, sptrs, sstr
+    a.fwd.input = x.data_ptr()
+    for k in range(4):
+        a.fwd.input_strides[k] = x.stride(k)
+    a.fwd.output, a.fwd.workspace, a.fwd.training = out.data_ptr(), ws.data_ptr(), 1
+    a.fwd.dropout_mode = N.DROPOUT_NONE if cfg.dropout == 0 else N.DROPOUT_PHILOX
+    a.scratch, a.grad_flat, a.target = sc.data_ptr(), grad.data_ptr(), y.data_ptr()
+    for k in range(3):
+        a.target_strides[k] = y.stride(k)
+    a.scaler_mean, a.scaler_std, a.ctrl, a.metrics = 54.0, 20.0, ctrl.data_ptr(), metrics.data_ptr()
+    ad = N.GwnAdamArgs()
+    ad.param_flat, ad.grad_flat, ad.exp_avg, ad.exp_avg_sq = flat.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr()
+    ad.live4, ad.n, ad.hyper, ad.ctrl, ad.metrics = live4.data_ptr(), n, hyper.data_ptr(), ctrl.data_ptr(), metrics.data_ptr()
+    assert cfg.dropout == 0, "golden trainer cases are recorded without dropout"
+    want = rec["trainer_metrics"].tolist()
+    for step in range(3):
+        emu.check(emu.dll.gwn_plan_train_fwd_bwd(plan.handle, C.byref(a)), "train_fwd_bwd")
+        emu.check(emu.dll.gwn_adam_step(C.byref(ad)), "adam_step")
+        for got, w in zip(metrics[:3].tolist(), want[step]):
+            assert abs(got - w) <= 1e-4 * abs(w) + 1e-6, (step, metrics.tolist(), want[step])
+    seed, st = C.c_uint64(0), C.c_int64(0)
+    emu.check(emu.dll.gwn_train_ctrl_read(ctrl.data_ptr(), C.byref(seed), C.byref(st)))
+    assert st.value == 3 and seed.value != 1234
+    for k, t in zip(plan.names, table):
+        assert_close_rel(t.float().reshape(rec["state3/" + k].shape), rec["state3/" + k].float(), 2e-3, "state after 3 steps " + k,
+                         floor=1e-5)
