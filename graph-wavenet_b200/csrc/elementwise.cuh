@@ -280,17 +280,18 @@ GWN_GLOBAL bn_bwd_apply_kernel(float* dy, const float* u, const float* ac, const
 // bias_g'[ch] = b_g[ch] + sum_{tap,ci} W_g[ch][ci][tap] * c[ci]      (conv(W, a*u + c) = conv(W*diag(a), u) + W.c)
 GWN_GLOBAL pack_tcn_fwd_kernel(const float* wf, const float* wg, const float* bf, const float* bg, const float* ac, float* Wp,
                                float* bfp, float* bgp, int D, int C) {
-  GWN_FOR_EACH(n, 2 * D) {
+  GWN_FOR_EACH_WARP_ROW(n, 2 * D, lane, WS) {   // one warp per packed output row n = 2*ch + gate
     const int ch = (int)(n >> 1), g = (int)(n & 1);
     const float* w = g ? wg : wf;
     float extra = 0.0f;
-    for (int tap = 0; tap < 2; ++tap)
-      for (int ci = 0; ci < C; ++ci) {
-        const float v = w[((i64)ch * C + ci) * 2 + tap];
-        Wp[n * (2 * C) + tap * C + ci] = ac ? v * ac[ci] : v;
-        if (ac) extra = fmaf(v, ac[C + ci], extra);
-      }
-    (g ? bgp : bfp)[ch] = (g ? bg : bf)[ch] + extra;
+    for (int k = lane; k < 2 * C; k += WS) {
+      const int tap = k / C, ci = k - tap * C;
+      const float v = w[((i64)ch * C + ci) * 2 + tap];
+      Wp[n * (2 * C) + k] = ac ? v * ac[ci] : v;
+      if (ac) extra = fmaf(v, ac[C + ci], extra);
+    }
+    extra = warp_sum(extra);
+    if (lane == 0) (g ? bgp : bfp)[ch] = (g ? bg : bf)[ch] + extra;
   }
 }
 // Gated conv input gradient:  Wd[ci][tap*2D + j] = W_{j&1}[j>>1][ci][tap]

@@ -128,7 +128,9 @@ struct gwn_plan {
   std::vector<gwn::i64> o_g, o_u, o_ac, o_mr, o_sums, o_pack;
   gwn::i64 pk_wp, pk_bf, pk_bg, pk_wd, pk_wt;   // offsets inside a layer's pack region (tf32 tier)
   // backward scratch offsets (floats)
-  gwn::i64 o_rs, o_buf0, o_buf1, o_dh, o_dsegs, o_dg, o_dpre, o_dgh, o_dout, o_de1, o_dskip, o_dA, o_dR, o_bsum, bwd_floats;
+  gwn::i64 o_part, part_floats, o_buf0, o_buf1, o_dh, o_dg, o_dpre, o_dgh, o_dout, o_de1, o_dskip, o_dA, o_dR, o_bsum, bwd_floats;
+  std::vector<gwn::i64> o_dsegs;   // per layer when the support gradient is deferred to ONE launch per backward pass
+  bool defer_dA;
   gwn::i64 P(int i) const { return (gwn::i64)c.batch * L[i] * c.num_nodes; }
   gwn::i64 P0() const { return (gwn::i64)c.batch * L0 * c.num_nodes; }
   gwn::i64 PT() const { return (gwn::i64)c.batch * T_out * c.num_nodes; }
@@ -292,11 +294,21 @@ static int build_plan(gwn_plan* p) {
   for (int i = 0; i < nL; ++i) maxP = std::max(maxP, p->P(i));
   i64 maxPi = 0;
   for (int i = 0; i < nL; ++i) maxPi = std::max(maxPi, p->P(i));
-  p->o_rs = take((i64)2 * C * 2 * D + 2 * D + 64);   // raw gated-conv weight-gradient accumulators (tf32 tier)
+  // tcgen05 reductions (tf32 tier): per-CTA partial results, 160 slots of the largest accumulator tile in use
+  const bool tc_tier = c.precision == GWN_PREC_TF32 && C == 32 && D == 32;
+  p->defer_dA = tc_tier && c.adaptive && c.num_nodes <= 512 && 2 * nL <= TR_MAXSRC;
+  p->part_floats = tc_tier ? (i64)160 * (p->defer_dA ? 512 * 128 : 256 * 64) : 0;
+  p->o_part = take(p->part_floats);
   p->o_buf0 = take(maxP * C);
   p->o_buf1 = take(maxP * C);
   p->o_dh = take(maxPi * C);   // du * dropout keep-mask (gradient wrt the pre-dropout mlp output)
-  p->o_dsegs = take(maxPi * D * p->nseg);
+  p->o_dsegs.assign(nL, 0);
+  if (p->defer_dA) {
+    for (int i = 0; i < nL; ++i) p->o_dsegs[i] = take(p->P(i) * D * p->nseg);   // t tensors stay alive until the dA launch
+  } else {
+    const i64 o_shared = take(maxPi * D * p->nseg);
+    for (int i = 0; i < nL; ++i) p->o_dsegs[i] = o_shared;
+  }
   p->o_dg = take(maxPi * D);
   p->o_dpre = take(maxPi * 2 * D);
   p->o_dgh = take((i64)nL * p->PT() * D);
@@ -448,7 +460,7 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
       int pst = -1;
       if (tcpos_ok(p)) {
         float* pk = ws + p->o_pack[i];
-        GWN_LAUNCH_1D(pack_tcn_fwd_kernel, 2 * D, st, P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw),
+        GWN_LAUNCH_WARP_ROWS(pack_tcn_fwd_kernel, 2 * D, st, P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw),
                       P_<float>(prm, p->li[i].fb), P_<float>(prm, p->li[i].gb), prev_ac, pk + p->pk_wp, pk + p->pk_bf,
                       pk + p->pk_bg, D, C);
         RowGate eg;
@@ -686,8 +698,11 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
   // ---- layers in reverse
   float* cur = sc + p->o_buf0;   // holds d(loss)/d(x_{i+1}) on entry of layer i (unused for the last layer)
   float* oth = sc + p->o_buf1;
-  float* dsegs = sc + p->o_dsegs;
   float* dg = sc + p->o_dg;
+  TcScratch tsc{p->part_floats > 0 ? sc + p->o_part : nullptr, p->part_floats};
+  const float* dA_X[TR_MAXSRC];
+  const float* dA_T[TR_MAXSRC];
+  int dA_slabs[TR_MAXSRC], dA_pairs = 0;
   float* dpre = sc + p->o_dpre;
   for (int i = nL - 1; i >= 0; --i) {
     const bool live = i < nL - 1;   // the last layer's gcn/bn output is discarded (model.py:238)
@@ -696,6 +711,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     const float* prev_ac = i == 0 ? nullptr : ws + p->o_ac[i - 1];
     const float* g = ws + p->o_g[i];
     const float* dgh_i = dgh + (i64)i * PT * D;
+    float* dsegs = sc + p->o_dsegs[i];
     const float* dgp;   // gradient wrt g_i
     if (live) {
       const DropoutSrc ldrop = layer_dropout(p, training, dmode, a->keep_masks, a->seed, i, a->seed_device);
@@ -722,14 +738,24 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
       }
       m.dW = G(c.gcn ? p->li[i].mw : p->li[i].rw);
       m.dbias = G(c.gcn ? p->li[i].mb : p->li[i].rb);
+      m.ts = tsc;
       GWN_TRY(mlp_backward(m, st));
       if (c.gcn) {
         GcnShape gs{B, p->L[i], N, D, C, p->S, c.order};
         float* dsup[MAXSUP];
         i64 ldds[MAXSUP];
         for (int s = 0; s < p->S; ++s) { dsup[s] = nullptr; ldds[s] = p->ld; }
-        if (c.adaptive) dsup[p->S - 1] = sc + p->o_dA;
-        GWN_TRY(gcn_hops_backward(gs, g, g + Pi * D, supB, dsegs, dg, dgh_i, p->T_out, dsup, ldds, st, &tcB));
+        if (c.adaptive && !p->defer_dA) dsup[p->S - 1] = sc + p->o_dA;
+        GWN_TRY(gcn_hops_backward(gs, g, g + Pi * D, supB, dsegs, dg, dgh_i, p->T_out, dsup, ldds, st, &tcB, &tsc));
+        if (c.adaptive && p->defer_dA) {   // (hop input, chained gradient) pairs of the adaptive support, used after the loop
+          const int sA = p->S - 1;
+          for (int k = 1; k <= c.order; ++k) {
+            dA_X[dA_pairs] = (k == 1) ? g : g + (i64)hop_index(gs, sA, k - 1) * Pi * D;
+            dA_T[dA_pairs] = dsegs + (i64)hop_index(gs, sA, k) * Pi * D;
+            dA_slabs[dA_pairs] = B * p->L[i];
+            ++dA_pairs;
+          }
+        }
       } else {
         GWN_LAUNCH_1D(add_window_kernel, Pi * D, st, dg, (const float*)dsegs, dgh_i, B, p->L[i], N, D, p->T_out);
       }
@@ -811,25 +837,24 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     }
     bool wgrad_done = false;
     ProfScope prof_w("gated_tcn_wgrad", st, 4.0 * ((double)Pin * C + (double)Pi * 2 * D), 2.0 * Pi * 2 * D * (2.0 * C + 1));
-    if (tcpos_ok(p)) {   // tcgen05 + TMA reduction over all positions, then fold the BatchNorm affine of the layer below
-      float* R = sc + p->o_rs;
-      float* S = R + (i64)2 * C * 2 * D;
-      GWN_TRY(dev_memset(R, 0, sizeof(float) * ((i64)2 * C * 2 * D + 2 * D), st));
+    if (tcpos_ok(p) && tsc.partial) {   // tcgen05 + TMA reduction over all positions; the slot reduction folds the
+#if !GWN_EMU                            // BatchNorm affine of the layer below and scatters to the four gradients
       TcRedArgs t;
       memset(&t, 0, sizeof(t));
       t.mode = 0; t.na = 2;
-      t.a[0] = TcRedSrc{prev, p->Lin(i) * N, 32, 0, 0};
-      t.a[1] = TcRedSrc{prev, p->Lin(i) * N, 32, 0, p->dil[i] * N};
-      t.b[0] = TcRedSrc{dpre, p->L[i] * N, 2 * D, 0, 0};
-      t.N = 2 * D; t.nb = B; t.rows = p->L[i] * N;
-      t.out.kind = 1; t.out.out = R; t.out.out_bias = S; t.out.nblk_real = 2;
-      int rst = launch_tcred(t, st);
+      t.a[0] = TcRedSrc{prev, p->Lin(i) * N, 32, 0, 0, 0};
+      t.a[1] = TcRedSrc{prev, p->Lin(i) * N, 32, 0, p->dil[i] * N, 0};
+      t.b[0] = TcRedSrc{dpre, p->L[i] * N, 2 * D, 0, 0, 0};
+      t.N = 2 * D; t.nb = B; t.rows = p->L[i] * N; t.partial = tsc.partial; t.partial_floats = tsc.floats;
+      TcRedResult rr;
+      int rst = launch_tcred(t, st, &rr);
       if (rst > 0) return rst;
       if (rst == 0) {
-        GWN_LAUNCH_1D(tcn_wgrad_finalize_kernel, (i64)2 * D * 2 * C + 2 * D, st, (const float*)R, (const float*)S, prev_ac,
-                      G(p->li[i].fw), G(p->li[i].gw), G(p->li[i].fb), G(p->li[i].gb), D, C);
+        tc::SlotTcnOut f{prev_ac, G(p->li[i].fw), G(p->li[i].gw), G(p->li[i].fb), G(p->li[i].gb), C, D};
+        GWN_TRY(launch_slot_reduce(tsc.partial, rr, (i64)2 * C * 2 * D + 2 * D, f, st));
         wgrad_done = true;
       }
+#endif
     }
     if (!wgrad_done) {  // filter / gate weight and bias gradients
       LdCols la;
@@ -847,6 +872,15 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
       GWN_TRY((launch_gemm<TW64>(la, lb, ep, sh, st)));
     }
     std::swap(cur, oth);
+  }
+  // ---- adaptive-support gradient of ALL layers in one tcgen05 reduction (dA sums over 7 layers x 2 hops)
+  if (dA_pairs > 0) {
+    double slabs = 0;
+    for (int q = 0; q < dA_pairs; ++q) slabs += dA_slabs[q];
+    ProfScope prof("nconv_bwd_dA", st, 4.0 * slabs * N * D * 2.0, 2.0 * slabs * N * D * N);
+    int dst = support_grad_tc(dA_X, dA_T, dA_slabs, dA_pairs, sc + p->o_dA, p->ld, N, D, tsc, st);
+    GWN_CHECK_ARG(dst >= 0, "backward: deferred support gradient not eligible for the tcgen05 path");
+    if (dst > 0) return dst;
   }
   // ---- start conv backward: cur = d(loss)/d(x0)
   {
@@ -1205,7 +1239,7 @@ int gwn_plan_debug_layout(const gwn_plan* p, char* buf, int len) {
   put("bwd", "dR", 0, p->o_dR, N * p->ld);
   put("bwd", "buf", 0, p->o_buf0, p->P0() * C);
   put("bwd", "buf", 1, p->o_buf1, p->P0() * C);
-  put("bwd", "dsegs", 0, p->o_dsegs, p->P(0) * D * p->nseg);
+  put("bwd", "dsegs", 0, p->o_dsegs[0], p->P(0) * D * p->nseg);
   put("bwd", "dg", 0, p->o_dg, p->P(0) * D);
   put("bwd", "dpre", 0, p->o_dpre, p->P(0) * 2 * D);
   snprintf(buf, len, "%s", s.c_str());

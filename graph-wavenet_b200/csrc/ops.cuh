@@ -90,21 +90,45 @@ inline int node_gemm(const SupportView* sup, int nsup, bool kcat, const float* c
   return launch_gemm<TBig>(a, b, e, sh, stream);
 }
 
+// Partial-result scratch of the tcgen05 reductions (tcred.cuh); null = not available (op-level calls).
+struct TcScratch {
+  float* partial;
+  i64 floats;
+};
+
+// tcgen05 support gradient over any number of (X, T) pairs with their own slab counts (all layers of a backward pass
+// in ONE launch): dA[v,w] += sum over pairs, slabs, c of X[(slab,v),c] * T[(slab,w),c].  -1 = not eligible.
+inline int support_grad_tc(const float* const* Xp, const float* const* Yp, const int* slabs, int npairs, float* dA, i64 ldda,
+                           int V, int C, const TcScratch& ts, cudaStream_t stream) {
+#if GWN_EMU
+  (void)Xp; (void)Yp; (void)slabs; (void)npairs; (void)dA; (void)ldda; (void)V; (void)C; (void)ts; (void)stream;
+  return -1;
+#else
+  if (C != 32 || npairs < 1 || npairs > TR_MAXSRC || !ts.partial || ldda > 2147483647LL) return -1;
+  TcRedArgs t;
+  memset(&t, 0, sizeof(t));
+  t.mode = 1; t.na = npairs;
+  for (int i = 0; i < npairs; ++i) {
+    t.a[i] = TcRedSrc{Xp[i], V, 32, 0, 0, slabs[i]};
+    t.b[i] = TcRedSrc{Yp[i], V, 32, 0, 0, slabs[i]};
+  }
+  t.rows = V; t.partial = ts.partial; t.partial_floats = ts.floats;
+  TcRedResult r;
+  int st = launch_tcred(t, stream, &r);
+  if (st != 0) return st;
+  tc::SlotSupOut f{dA, (int)ldda, V, r.N, r.n_nt};
+  return launch_slot_reduce(ts.partial, r, (i64)V * V, f, stream);
+#endif
+}
+
 // dA[v,w] += sum over pairs, slabs, c of Xp[(slab,v),c] * Yp[(slab,w),c]
 inline int support_grad_gemm(const float* const* Xp, const float* const* Yp, int npairs, float* dA, i64 ldda, int B, int L,
-                             int V, int C, cudaStream_t stream) {
+                             int V, int C, cudaStream_t stream, const TcScratch* ts = nullptr) {
   GWN_CHECK_ARG(npairs >= 1 && npairs <= MAXSUP, "support_grad: bad pair count %d", npairs);
-  if (current_math() == 1 && C == 32 && V <= 256 && npairs <= TR_MAXSRC && (ldda % 1) == 0) {   // tf32 tier: tcgen05 + TMA
-    TcRedArgs t;
-    memset(&t, 0, sizeof(t));
-    t.mode = 1; t.na = npairs;
-    for (int i = 0; i < npairs; ++i) {
-      t.a[i] = TcRedSrc{Xp[i], V, 32, 0, 0};
-      t.b[i] = TcRedSrc{Yp[i], V, 32, 0, 0};
-    }
-    t.N = round_up(V, 16); t.nb = B * L; t.rows = V;
-    t.out.kind = 2; t.out.out = dA; t.out.ldw = (int)ldda; t.out.V = V;
-    int st = launch_tcred(t, stream);
+  if (current_math() == 1 && ts) {   // tf32 tier: tcgen05 + TMA
+    int slabs[MAXSUP];
+    for (int i = 0; i < npairs; ++i) slabs[i] = B * L;
+    int st = support_grad_tc(Xp, Yp, slabs, npairs, dA, ldda, V, C, *ts, stream);
     if (st >= 0) return st;
   }
   LdSlabK a, b;
@@ -191,6 +215,7 @@ struct MlpBwdArgs {
   float* dW;                  // accumulated (atomic); nullable
   float* dbias;               // accumulated; nullable iff dW is
   const float* WT;            // nullable: W transposed [nseg*D][C_out] -> tcgen05/TMA input-gradient kernel (tf32 tier)
+  TcScratch ts;               // partial-result scratch of the tcgen05 weight-gradient reduction (null: not available)
 };
 inline int mlp_backward(const MlpBwdArgs& m, cudaStream_t stream) {
   GWN_CHECK_ARG(m.nseg >= 1 && m.nseg <= MAXSEG && m.D % 4 == 0 && m.C_out % 4 == 0,
@@ -236,16 +261,22 @@ inline int mlp_backward(const MlpBwdArgs& m, cudaStream_t stream) {
   ProfScope prof_w("gcn_mlp_wgrad", stream, m.dW ? 4.0 * m.P * ((double)Ktot + m.C_out) : 0.0,
                    m.dW ? 2.0 * m.P * (Ktot + 1.0) * m.C_out : 0.0);
   if (m.dW && current_math() == 1 && m.D == 32 && m.C_out == 32 && m.nseg <= 7 && m.drop.mode == GWN_DROPOUT_NONE &&
-      m.P < 2147483647LL) {   // tf32 tier: tcgen05 + TMA reduction (weights and, through the all-ones block, the bias)
+      m.P < 2147483647LL && m.ts.partial) {   // tf32 tier: tcgen05 + TMA reduction (weights and, through the all-ones block, the bias)
+#if !GWN_EMU
     TcRedArgs t;
     memset(&t, 0, sizeof(t));
     t.mode = 0; t.na = m.nseg;
-    for (int q = 0; q < m.nseg; ++q) t.a[q] = TcRedSrc{m.segs[q], (int)m.P, 32, 0, 0};
-    t.b[0] = TcRedSrc{m.dh, (int)m.P, 32, 0, 0};
-    t.N = 32; t.nb = 1; t.rows = (int)m.P;
-    t.out.kind = 0; t.out.out = m.dW; t.out.out_bias = m.dbias; t.out.ldw = Ktot; t.out.nblk_real = m.nseg;
-    int st = launch_tcred(t, stream);
-    if (st >= 0) return st;
+    for (int q = 0; q < m.nseg; ++q) t.a[q] = TcRedSrc{m.segs[q], (int)m.P, 32, 0, 0, 0};
+    t.b[0] = TcRedSrc{m.dh, (int)m.P, 32, 0, 0, 0};
+    t.N = 32; t.nb = 1; t.rows = (int)m.P; t.partial = m.ts.partial; t.partial_floats = m.ts.floats;
+    TcRedResult r;
+    int st = launch_tcred(t, stream, &r);
+    if (st > 0) return st;
+    if (st == 0) {
+      tc::SlotMlpOut f{m.dW, m.dbias, Ktot, m.nseg};
+      return launch_slot_reduce(m.ts.partial, r, (i64)m.nseg * 32 * 32 + 32, f, stream);
+    }
+#endif
   }
   if (m.dW) {
     LdCols a;
@@ -293,7 +324,7 @@ inline int gcn_hops_forward(const GcnShape& g, const float* x, const SupportView
 // dsup[s] (nullable) += sum_k hop_{s,k-1}^T t_{s,k}.
 inline int gcn_hops_backward(const GcnShape& g, const float* x, const float* hops, const SupportView* sup_bwd, float* dsegs,
                              float* dx, const float* add2, int T_out, float* const* dsup, const i64* ldds,
-                             cudaStream_t stream, const TcSupports* tcs = nullptr) {
+                             cudaStream_t stream, const TcSupports* tcs = nullptr, const TcScratch* ts = nullptr) {
   const i64 PD = (i64)g.B * g.L * g.V * g.D;
   {
     ProfScope prof("nconv_bwd_dx_hops", stream, 4.0 * PD * 3.0 * g.S * (g.order - 1), 2.0 * PD * g.V * g.S * (g.order - 1));
@@ -319,7 +350,7 @@ inline int gcn_hops_backward(const GcnShape& g, const float* x, const float* hop
       Xp[k - 1] = (k == 1) ? x : hops + (i64)(hop_index(g, s, k - 1) - 1) * PD;
       Yp[k - 1] = dsegs + (i64)hop_index(g, s, k) * PD;
     }
-    GWN_TRY(support_grad_gemm(Xp, Yp, g.order, dsup[s], ldds[s], g.B, g.L, g.V, g.D, stream));
+    GWN_TRY(support_grad_gemm(Xp, Yp, g.order, dsup[s], ldds[s], g.B, g.L, g.V, g.D, stream, ts));
   }
   {
     ProfScope prof("nconv_bwd_dx_sum", stream, 4.0 * PD * (g.S + 2.0) + 4.0 * PD / g.L * T_out, 2.0 * PD * g.V * g.S);

@@ -56,6 +56,12 @@ struct RowStats32 {
   }
 };
 
+// tanh / sigmoid of the gate on the tf32 tier: ex2.approx-based (2 MUFU + 3 FMA-class instructions each, ~1e-7
+// absolute error) instead of the ~35-instruction tanhf / expf sequences -- with one epilogue warp per scheduler the
+// accurate versions made the gate epilogue, not HBM, the limiter of the gated-conv kernels (ncu r01b).
+__device__ __forceinline__ float gate_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float gate_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+
 // model.py:208-212 -- accumulator columns interleaved (f0,g0,f1,g1,...), N = 64 -> 32 gated outputs.
 struct RowGate {
   static constexpr bool kHasFinish = false;
@@ -68,7 +74,7 @@ struct RowGate {
     const int ch0 = c0 >> 1;
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = tanhf(v[2 * j] + __ldg(bf + ch0 + j)) * sigmoidf_(v[2 * j + 1] + __ldg(bg + ch0 + j));
+    for (int j = 0; j < 8; ++j) o[j] = gate_tanh(v[2 * j] + __ldg(bf + ch0 + j)) * gate_sigmoid(v[2 * j + 1] + __ldg(bg + ch0 + j));
     float* p = y + m * 32 + ch0;
     *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
@@ -93,7 +99,7 @@ struct RowGateBwd {
     float o[16];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float f = tanhf(v[2 * j] + __ldg(bf + ch0 + j)), s = sigmoidf_(v[2 * j + 1] + __ldg(bg + ch0 + j));
+      const float f = gate_tanh(v[2 * j] + __ldg(bf + ch0 + j)), s = gate_sigmoid(v[2 * j + 1] + __ldg(bg + ch0 + j));
       const float gg = g[ch0 + j];
       o[2 * j] = gg * s * (1.0f - f * f);
       o[2 * j + 1] = gg * f * s * (1.0f - s);

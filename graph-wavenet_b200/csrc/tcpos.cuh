@@ -35,6 +35,7 @@ struct TcPosArgs {
   int rows_out;       // output rows per sample
   const float* Wp;    // packed weights [N][nseg*32]
   int N;
+  const float* Wp_lo; // non-null: 3xTF32 (fp32-grade) mode -- Wp holds the tf32-exact high parts, Wp_lo the remainders
 };
 
 // Dummy "tile" for the column-statistics state of row-owner epilogues: 8 slots of 4 columns = 32 columns.
@@ -50,29 +51,39 @@ constexpr int TP_A_BYTES = 128 * 128;   // one A tile: 128 rows x 32 floats
 struct TpMaps {
   CUtensorMap a[TP_MAXSEG];
   CUtensorMap w;
+  CUtensorMap wlo;
 };
 struct TpParams {
   int nseg, nb, rows_out, tiles_per_sample, total_tiles, N, stages;
   int col0[TP_MAXSEG], rshift[TP_MAXSEG];
 };
 
-template <class EP, int NCT>   // NCT > 0: compile-time column count (keeps per-slot epilogue state in registers)
+// X3 = 3xTF32 mode (fp32-grade results on the tf32 tensor pipe): every operand is split into a tf32-exact high part
+// and a remainder, D = A_hi.W_hi + A_hi.W_lo + A_lo.W_hi (the dropped A_lo.W_lo term is ~2^-22 relative).  The weight
+// planes are precomputed; the A remainder is produced in shared memory by two otherwise idle warps (2, 3) from the
+// tile TMA just landed: the element-wise split preserves the swizzled layout.  kind::tf32 ignores the low 13
+// mantissa bits of its operands (probed: tests/tools/tf32_rounding_probe.py), so the fp32 A tile itself serves as A_hi.
+template <class EP, int NCT, bool X3>   // NCT > 0: compile-time column count (keeps per-slot epilogue state in registers)
 __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ TpMaps maps, const TpParams p, const EP ep_in) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const int w_bytes = p.nseg * p.N * 128;                 // resident weights: [seg][N rows][128 B]
-  const uint32_t a0 = base + w_bytes;                     // A stages
-  const uint32_t bar0 = a0 + p.stages * TP_A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + w_bytes + (size_t)p.stages * TP_A_BYTES);
+  constexpr int NPL = X3 ? 2 : 1;                         // operand planes (hi, lo)
+  constexpr int STG = NPL * TP_A_BYTES;                   // bytes per A stage
+  const int w_plane = p.nseg * p.N * 128;                 // resident weights: [plane][seg][N rows][128 B]
+  const int w_bytes = NPL * w_plane;
+  const uint32_t a0 = base + w_bytes;                     // A stages: [A | A_lo]
+  const uint32_t bar0 = a0 + p.stages * STG;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + w_bytes + (size_t)p.stages * STG);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * p.stages + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * p.stages + 2 + a); };
-  const uint32_t w_bar = bar0 + 8u * (2 * p.stages + 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 5);
-  float* red = reinterpret_cast<float*>(bars + 2 * p.stages + 6);   // 64 floats for the statistics reduce
+  auto split_bar = [&](int s) { return bar0 + 8u * (2 * p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * p.stages + 2 + a); };
+  const uint32_t w_bar = bar0 + 8u * (3 * p.stages + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 5);
+  float* red = reinterpret_cast<float*>(bars + 3 * p.stages + 6);   // 64 floats for the statistics reduce
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -83,6 +94,7 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
+      mbar_init(split_bar(s), 64);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -104,6 +116,8 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
     // ===================================================== TMA producer
     mbar_expect_tx(w_bar, (uint32_t)w_bytes);
     for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + s * p.N * 128, &maps.w, w_bar, s * 32, 0);
+    if (X3)
+      for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + w_plane + s * p.N * 128, &maps.wlo, w_bar, s * 32, 0);
     int stage = 0;
     uint32_t phase = 0;
     bool ok = true;
@@ -112,7 +126,7 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
       for (int s = 0; s < p.nseg; ++s) {
         if (!mbar_wait(empty_bar(stage), phase ^ 1u, 11)) { ok = false; break; }
         mbar_expect_tx(full_bar(stage), TP_A_BYTES);
-        tma_load_3d(a0 + stage * TP_A_BYTES, &maps.a[s], full_bar(stage), p.col0[s], rt * 128 + p.rshift[s], b);
+        tma_load_3d(a0 + stage * STG, &maps.a[s], full_bar(stage), p.col0[s], rt * 128 + p.rshift[s], b);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -129,14 +143,19 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
       for (int s = 0; s < p.nseg; ++s) {
         if (!mbar_wait(full_bar(stage), phase, 14)) { ok = false; break; }
+        if (X3 && !mbar_wait(split_bar(stage), phase, 16)) { ok = false; break; }
         tc_fence_after();
-        const uint32_t as = a0 + stage * TP_A_BYTES;
+        const uint32_t as = a0 + stage * STG;
         const uint32_t ws = base + s * p.N * 128;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           // both operands K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart, this k-step 32 B in
-          tc_mma_tf32(d_tmem, make_desc(as + kk * 32, 16, 1024), make_desc(ws + kk * 32, 16, 1024), idesc,
-                      (s > 0 || kk > 0) ? 1u : 0u);
+          const uint64_t ad = make_desc(as + kk * 32, 16, 1024), wd = make_desc(ws + kk * 32, 16, 1024);
+          tc_mma_tf32(d_tmem, ad, wd, idesc, (s > 0 || kk > 0) ? 1u : 0u);
+          if (X3) {
+            tc_mma_tf32(d_tmem, ad, make_desc(ws + w_plane + kk * 32, 16, 1024), idesc, 1u);
+            tc_mma_tf32(d_tmem, make_desc(as + TP_A_BYTES + kk * 32, 16, 1024), wd, idesc, 1u);
+          }
         }
         tc_commit(empty_bar(stage));
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -145,6 +164,32 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
       tc_commit(tfull_bar(acc));
       acc ^= 1;
       if (acc == 0) accphase ^= 1u;
+    }
+  } else if (X3 && (warp == 2 || warp == 3)) {
+    // ===================================================== splitter: A_lo = A - tf32_trunc(A), 64 threads, 16 float4 each
+    const int t64 = threadIdx.x - 64;
+    int stage = 0;
+    uint32_t phase = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+      for (int s = 0; s < p.nseg; ++s) {
+        if (!mbar_wait(full_bar(stage), phase, 17)) { ok = false; break; }
+        const float4* src = reinterpret_cast<const float4*>(smem + w_bytes + (size_t)stage * STG);
+        float4* dst = reinterpret_cast<float4*>(smem + w_bytes + (size_t)stage * STG + TP_A_BYTES);
+#pragma unroll 4
+        for (int i = t64; i < TP_A_BYTES / 16; i += 64) {
+          const float4 v = src[i];
+          float4 r;
+          r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+          r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+          r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          dst[i] = r;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(split_bar(stage));
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue: one position row per thread
@@ -198,8 +243,8 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
 #endif
 
 // Returns 0 after launching; -1 when the shape is not eligible (caller falls back); > 0 on error.
-template <int NCT, class EP>
-int launch_tcpos(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
+template <int NCT, bool X3, class EP>
+int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
 #if GWN_EMU
   (void)a; (void)ep; (void)stream;
   return -1;
@@ -216,8 +261,9 @@ int launch_tcpos(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
   const long long tiles = (long long)p.tiles_per_sample * a.nb;
   if (tiles > 2147483647LL) return -1;
   p.total_tiles = (int)tiles;
-  const int w_bytes = a.nseg * a.N * 128;
-  p.stages = (SMEM_LIMIT - 2048 - w_bytes) / TP_A_BYTES;
+  const int w_bytes = (X3 ? 2 : 1) * a.nseg * a.N * 128;
+  constexpr int STG = (X3 ? 2 : 1) * TP_A_BYTES;
+  p.stages = (SMEM_LIMIT - 2048 - w_bytes) / STG;
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) return -1;
   for (int s = 0; s < a.nseg; ++s) {
@@ -237,9 +283,15 @@ int launch_tcpos(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
     cuuint64_t st[1] = {(cuuint64_t)K * 4};
     cuuint32_t box[2] = {32, (cuuint32_t)a.N};
     GWN_TRY(encode(&maps.w, a.Wp, 2, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    if (X3) {
+      if (reinterpret_cast<uintptr_t>(a.Wp_lo) & 15) return -1;
+      GWN_TRY(encode(&maps.wlo, a.Wp_lo, 2, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    } else {
+      maps.wlo = maps.w;
+    }
   }
-  const int smem_bytes = w_bytes + p.stages * TP_A_BYTES + 1024 + 512;
-  static cudaError_t attr = cudaFuncSetAttribute(tcpos_kernel<EP, NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  const int smem_bytes = w_bytes + p.stages * STG + 1024 + 512;
+  static cudaError_t attr = cudaFuncSetAttribute(tcpos_kernel<EP, NCT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   if (attr != cudaSuccess) {
     set_error("tcpos: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr));
     return GWN_ERR_CUDA;
@@ -251,11 +303,16 @@ int launch_tcpos(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
     return n;
   }();
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  tcpos_kernel<EP, NCT><<<grid, 256, smem_bytes, stream>>>(maps, p, ep);
+  tcpos_kernel<EP, NCT, X3><<<grid, 256, smem_bytes, stream>>>(maps, p, ep);
   GWN_LAUNCH_CHECK();
   count_launch();
   return 0;
 #endif
+}
+
+template <int NCT, class EP>
+int launch_tcpos(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
+  return a.Wp_lo ? launch_tcpos_impl<NCT, true>(a, ep, stream) : launch_tcpos_impl<NCT, false>(a, ep, stream);
 }
 
 }  // namespace gwn

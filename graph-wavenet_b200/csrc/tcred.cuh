@@ -195,23 +195,125 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
   }
 }
 
+// ---------------------------------------------------------------------------- slot reduction
+// out element i = sum over the slots {slot0, slot0 + step, ...} of partial[slot][off(i)] (and optionally a second
+// offset), handed to the functor's store().  Block = 32 outputs x 8 slot groups.
+template <class F>
+__global__ void __launch_bounds__(256) slot_reduce_kernel(const float* __restrict__ partial, int nslots, i64 slot_floats, i64 nout, F f) {
+  __shared__ float sm[2][8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const i64 i = (i64)blockIdx.x * 32 + tx;
+  float s0 = 0.0f, s1 = 0.0f;
+  if (i < nout) {
+    i64 off, off2;
+    int slot0, step;
+    f.where(i, off, off2, slot0, step);
+    for (int slot = slot0 + ty * step; slot < nslots; slot += 8 * step) {
+      const float* q = partial + (size_t)slot * slot_floats;
+      s0 += __ldg(q + off);
+      if (off2 >= 0) s1 += __ldg(q + off2);
+    }
+  }
+  sm[0][ty][tx] = s0;
+  sm[1][ty][tx] = s1;
+  __syncthreads();
+  if (ty == 0 && i < nout) {
+#pragma unroll
+    for (int y = 1; y < 8; ++y) { s0 += sm[0][y][tx]; s1 += sm[1][y][tx]; }
+    f.store(i, s0, s1);
+  }
+}
+
+// gcn mlp weight / bias gradient: slot rows (blk*32 + ci) x 32 columns (n = co); the ones block is row nblk*32.
+struct SlotMlpOut {
+  float* dW; float* db; int ldw, nblk;
+  __device__ __forceinline__ void where(i64 i, i64& off, i64& off2, int& slot0, int& step) const {
+    const i64 nw = (i64)nblk * 32 * 32;
+    off = i < nw ? i : (i64)nblk * 32 * 32 + (i - nw);
+    off2 = -1; slot0 = 0; step = 1;
+  }
+  __device__ __forceinline__ void store(i64 i, float s0, float) const {
+    const i64 nw = (i64)nblk * 32 * 32;
+    if (i < nw) {
+      const int row = (int)(i >> 5), n = (int)(i & 31);
+      dW[(size_t)n * ldw + row] += s0;
+    } else {
+      db[i - nw] += s0;
+    }
+  }
+};
+// gated-conv weight / bias gradient with the BatchNorm affine of the layer below folded in (x = a*u + c):
+// slot rows (tap*32 + ci) x 64 columns j = 2*ch + gate; ones block = row 64.   dW = a[ci]*R + c[ci]*S[j], db = S[j].
+struct SlotTcnOut {
+  const float* ac; float* dwf; float* dwg; float* dbf; float* dbg; int C, D;
+  __device__ __forceinline__ void where(i64 i, i64& off, i64& off2, int& slot0, int& step) const {
+    const i64 nw = (i64)2 * C * 2 * D;
+    if (i < nw) { off = i; off2 = ac ? (i64)2 * C * 2 * D + (i % (2 * D)) : -1; }
+    else { off = (i64)2 * C * 2 * D + (i - nw); off2 = -1; }
+    slot0 = 0; step = 1;
+  }
+  __device__ __forceinline__ void store(i64 i, float s0, float s1) const {
+    const i64 nw = (i64)2 * C * 2 * D;
+    if (i < nw) {
+      const int k = (int)(i / (2 * D)), j = (int)(i - (i64)k * 2 * D);
+      const int tap = k / C, ci = k - tap * C;
+      float v = s0;
+      if (ac) v = ac[ci] * s0 + ac[C + ci] * s1;
+      ((j & 1) ? dwg : dwf)[((size_t)(j >> 1) * C + ci) * 2 + tap] += v;
+    } else {
+      const int j = (int)(i - nw);
+      ((j & 1) ? dbg : dbf)[j >> 1] += s0;
+    }
+  }
+};
+// support gradient: slot rows v x Ntile columns; slot s holds output columns (s % n_nt)*Ntile ...
+struct SlotSupOut {
+  float* dA; int ld, V, Ntile, n_nt;
+  __device__ __forceinline__ void where(i64 i, i64& off, i64& off2, int& slot0, int& step) const {
+    const int v = (int)(i / V), w = (int)(i - (i64)v * V);
+    const int nt = w / Ntile;
+    off = (i64)v * Ntile + (w - nt * Ntile);
+    off2 = -1; slot0 = nt; step = n_nt;
+  }
+  __device__ __forceinline__ void store(i64 i, float s0, float) const {
+    const int v = (int)(i / V), w = (int)(i - (i64)v * V);
+    dA[(size_t)v * ld + w] += s0;
+  }
+};
+
 }  // namespace tc
+
+template <class F>
+inline int launch_slot_reduce(const float* partial, const TcRedResult& r, i64 nout, const F& f, cudaStream_t stream) {
+  if (nout <= 0) return 0;
+  tc::slot_reduce_kernel<F><<<(unsigned)((nout + 31) / 32), 256, 0, stream>>>(partial, r.nslots, r.slot_floats, nout, f);
+  GWN_LAUNCH_CHECK();
+  count_launch();
+  return 0;
+}
 #endif
 
 // 0 = launched, -1 = not eligible (caller falls back), > 0 = error.
-inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream) {
+inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* res) {
 #if GWN_EMU
-  (void)a; (void)stream;
+  (void)a; (void)stream; (void)res;
   return -1;
 #else
   using namespace tc;
   TrMaps maps;
   TrParams p;
   memset(&p, 0, sizeof(p));
-  p.mode = a.mode; p.na = a.na; p.N = a.N; p.nb = a.nb; p.out = a.out;
-  if (a.na < 1 || a.na > TR_MAXSRC || a.nb < 1 || a.rows < 1 || a.N % 16 != 0 || a.N < 16 || a.N > 256) return -1;
+  p.mode = a.mode; p.na = a.na; p.nb = a.nb; p.n_nt = 1;
+  if (a.na < 1 || a.na > TR_MAXSRC || a.rows < 1 || !a.partial || !res) return -1;
+  static int num_sms = [] {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
   if (a.mode == 0) {
-    if (a.na > 7 || (a.N != 32 && a.N != 64)) return -1;
+    if (a.na > 7 || (a.N != 32 && a.N != 64) || a.nb < 1) return -1;
+    p.N = a.N;
     p.nblk = a.na + 1;                       // + the all-ones block
     p.mtiles = (p.nblk + 3) / 4;
     p.nbn = a.N / 32;
@@ -244,48 +346,62 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream) {
     for (int j = a.na; j < TR_MAXSRC; ++j) maps.a[j] = maps.a[0];
     for (int j = 1; j < TR_MAXSRC; ++j) maps.b[j] = maps.b[0];
   } else {
-    if (a.rows > 256) return -1;              // V <= 256 (two 128-row M tiles)
+    // D[v, w] over V x V: mtiles row tiles of 128 live in TMEM side by side, Ntile columns each (mtiles*Ntile <= 512);
+    // n_nt column tiles are spread over the CTAs
     p.nblk = 0;
     p.mtiles = (a.rows + 127) / 128;
+    if (p.mtiles > 4) return -1;              // V <= 512
+    int ntile = (512 / p.mtiles) / 16 * 16;
+    if (ntile > 256) ntile = 256;
+    const int need = round_up(a.rows, 16);
+    if (ntile > need) ntile = need;
+    p.N = ntile;
+    p.n_nt = (a.rows + ntile - 1) / ntile;
     p.a_bytes = p.mtiles * 16384;
-    p.b_bytes = a.N * 128;
+    p.b_bytes = ntile * 128;
     p.tx_bytes = p.a_bytes + p.b_bytes;
-    const long long tot = (long long)a.na * a.nb;
-    if (tot > 2147483647LL) return -1;
-    p.total_chunks = (int)tot;
+    long long tot = 0;
     for (int j = 0; j < a.na; ++j) {
+      const int nbj = a.a[j].nb > 0 ? a.a[j].nb : a.nb;
+      if (nbj < 1) return -1;
+      tot += nbj;
+      if (tot > 2147483647LL) return -1;
+      p.pair_end[j] = (int)tot;
       const TcRedSrc* gs[2] = {&a.a[j], &a.b[j]};
       for (int w = 0; w < 2; ++w) {
         const TcRedSrc& g = *gs[w];
         if ((reinterpret_cast<uintptr_t>(g.src) & 15) || g.row_width != 32) return -1;
-        cuuint64_t d[3] = {32, (cuuint64_t)a.rows, (cuuint64_t)a.nb};
+        cuuint64_t d[3] = {32, (cuuint64_t)a.rows, (cuuint64_t)nbj};
         cuuint64_t st[2] = {128, (cuuint64_t)a.rows * 128};
-        cuuint32_t box[3] = {32, (cuuint32_t)(w == 0 ? 128 : a.N), 1};
+        cuuint32_t box[3] = {32, (cuuint32_t)(w == 0 ? 128 : ntile), 1};
         GWN_TRY(encode(w == 0 ? &maps.a[j] : &maps.b[j], g.src, 3, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B));
       }
     }
-    for (int j = a.na; j < TR_MAXSRC; ++j) { maps.a[j] = maps.a[0]; maps.b[j] = maps.b[0]; }
+    for (int j = a.na; j < TR_MAXSRC; ++j) { p.pair_end[j] = (int)tot; maps.a[j] = maps.a[0]; maps.b[j] = maps.b[0]; }
+    p.total_chunks = (int)tot;
   }
   const int stage_bytes = p.a_bytes + p.b_bytes;
   p.stages = (SMEM_LIMIT - 2048) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) return -1;
+  // grid: a multiple of n_nt, every CTA gets at least one chunk
+  int nk = num_sms / p.n_nt;
+  if (nk > p.total_chunks) nk = p.total_chunks;
+  if (nk < 1) return -1;
+  const int grid = nk * p.n_nt;
+  p.slot_floats = (i64)p.mtiles * 128 * p.N;
+  if ((i64)grid * p.slot_floats > a.partial_floats) return -1;
+  p.partial = a.partial;
   const int smem_bytes = p.stages * stage_bytes + 1024 + 256;
   static cudaError_t attr = cudaFuncSetAttribute(tcred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   if (attr != cudaSuccess) {
     set_error("tcred: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr));
     return GWN_ERR_CUDA;
   }
-  static int num_sms = [] {
-    int dev = 0, n = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-  }();
-  const int grid = p.total_chunks < num_sms ? p.total_chunks : num_sms;
   tcred_kernel<<<grid, 256, smem_bytes, stream>>>(maps, p);
   GWN_LAUNCH_CHECK();
   count_launch();
+  res->nslots = grid; res->mtiles = p.mtiles; res->N = p.N; res->n_nt = p.n_nt; res->slot_floats = p.slot_floats;
   return 0;
 #endif
 }
