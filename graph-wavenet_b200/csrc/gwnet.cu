@@ -466,7 +466,9 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
         RowGate eg;
         memset(&eg, 0, sizeof(eg));
         eg.y = g; eg.bf = pk + p->pk_bf; eg.bg = pk + p->pk_bg;
-        pst = launch_tcpos<64>(tcn_tcpos_args(p, prev, pk + p->pk_wp, i), eg, st);
+        TcPosArgs ta = tcn_tcpos_args(p, prev, pk + p->pk_wp, i);
+        ta.out = g; ta.out_width = D; ta.out_nblk = 1;
+        pst = launch_tcpos<64>(ta, eg, st);
         if (pst > 0) return pst;
       }
       if (pst < 0 && pg_ok(p)) {
@@ -776,7 +778,9 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
         RowGateBwd eg;
         memset(&eg, 0, sizeof(eg));
         eg.dpre = dpre; eg.dg = dgp; eg.bf = pk + p->pk_bf; eg.bg = pk + p->pk_bg;
-        pst = launch_tcpos<64>(tcn_tcpos_args(p, prev, pk + p->pk_wp, i), eg, st);
+        TcPosArgs ta = tcn_tcpos_args(p, prev, pk + p->pk_wp, i);
+        ta.out = dpre; ta.out_width = 2 * D; ta.out_nblk = 2;
+        pst = launch_tcpos<64>(ta, eg, st);
         if (pst > 0) return pst;
       }
       if (pst < 0 && pg_ok(p)) pst = launch_posgemm<TPG, 64>(tcn_arows(p, prev, prev_ac, i), lb, ep, Pi, 2 * D, st);
@@ -813,6 +817,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
         memset(&t, 0, sizeof(t));
         for (int q = 0; q < 4; ++q) t.seg[q] = TcPosSeg{dpre, p->L[i] * N, 2 * D, (q & 1) * 32, -(q >> 1) * p->dil[i] * N};
         t.nseg = 4; t.nb = B; t.rows_out = p->Lin(i) * N; t.Wp = pk + p->pk_wd; t.N = 32;
+        t.out = eg.dx; t.out_width = 32; t.out_nblk = 1;
         pst = launch_tcpos<32>(t, eg, st);
         if (pst > 0) return pst;
       }

@@ -174,6 +174,7 @@ inline int mlp_forward(const MlpFwdArgs& m, cudaStream_t stream) {
     memset(&t, 0, sizeof(t));
     for (int q = 0; q < m.nseg; ++q) t.seg[q] = TcPosSeg{m.segs[q], (int)m.P, 32, 0, 0};
     t.nseg = m.nseg; t.nb = 1; t.rows_out = (int)m.P; t.Wp = m.W; t.N = 32;
+    t.out = m.y; t.out_width = 32; t.out_nblk = 1;
     RowMlp eg;
     memset(&eg, 0, sizeof(eg));
     eg.y = m.y; eg.bias = m.bias; eg.drop = m.drop; eg.res = m.res; eg.rrm = m.rrm; eg.rac = m.rac; eg.stats = m.stats;
@@ -235,6 +236,7 @@ inline int mlp_backward(const MlpBwdArgs& m, cudaStream_t stream) {
       memset(&t, 0, sizeof(t));
       t.seg[0] = TcPosSeg{m.dh, (int)m.P, 32, 0, 0};
       t.nseg = 1; t.nb = 1; t.rows_out = (int)m.P; t.Wp = m.WT; t.N = Ktot;
+      t.out = m.dsegs; t.out_width = 32; t.out_nblk = m.nseg; t.out_blk_dim2 = 1;
       RowSeg rs;
       memset(&rs, 0, sizeof(rs));
       rs.out = m.dsegs; rs.M = m.P;

@@ -1,12 +1,16 @@
 // Row-owner epilogues of the tcgen05 position GEMM (tcpos.cuh): each of the 128 epilogue threads owns one whole
 // position row of the accumulator tile.  Contract:
+//     static constexpr int kAccPerBlock;                   // accumulator columns that make one 32-wide output block
 //     void init();
 //     void prefetch(i64 m, bool valid);                    // issue the global loads of the row's addends (128-bit)
-//     void consume16(i64 m, int c0, const float (&v)[16]); // accumulator columns c0..c0+15 of row m (valid rows only)
+//     void consume16(i64 m, int c0, const float (&v)[16], RowSink& out);   // accumulator columns c0..c0+15 of row m
 //     void finish_rows(float* red, int etid);              // if kHasFinish: block-level reduce of column statistics
 // Addends are fetched as whole 128-byte rows BEFORE the accumulator is waited for (ncu on the first version, which
 // loaded them 4 floats at a time inside the column loop, showed the epilogue stalled on those dependent loads
-// for ~10k cycles per tile); outputs leave as 128-bit stores.  Same arithmetic as the functors of functors.cuh.
+// for ~10k cycles per tile).  Outputs go to a 128B-swizzled shared-memory staging tile that one thread hands to TMA
+// (cp.async.bulk.tensor store): a row-owner thread storing its row straight to global writes 16 bytes per 128-byte
+// line per instruction, and ncu (r01c) showed those kernels bound by L2 sector traffic (L2 72 %, DRAM 22 %).
+// Same arithmetic as the functors of functors.cuh.
 #pragma once
 #include "functors.cuh"
 
@@ -20,10 +24,18 @@ __device__ __forceinline__ void ld_row32(float (&r)[32], const float* p) {
     r[4 * q] = f.x; r[4 * q + 1] = f.y; r[4 * q + 2] = f.z; r[4 * q + 3] = f.w;
   }
 }
-__device__ __forceinline__ void st16(float* p, const float (&o)[16]) {
+// One row (128 bytes = 32 floats) of the staging tile, SWIZZLE_128B: 16-byte chunk j of row r lives at chunk j ^ (r & 7).
+struct RowSink {
+  uint8_t* row;   // staging tile + r * 128
+  uint32_t x;     // r & 7
+  __device__ __forceinline__ void put4(int col, float a, float b, float c, float d) const {   // col: 0..28, multiple of 4
+    *reinterpret_cast<float4*>(row + ((((uint32_t)col >> 2) ^ x) << 4)) = make_float4(a, b, c, d);
+  }
+  __device__ __forceinline__ void put16(int col, const float (&o)[16]) const {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-}
+    for (int q = 0; q < 4; ++q) put4(col + 4 * q, o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+  }
+};
 
 // Per-thread column statistics over 32 columns, reduced across the 128 epilogue threads at the end.
 struct RowStats32 {
@@ -65,19 +77,19 @@ __device__ __forceinline__ float gate_tanh(float x) { return 1.0f - __fdividef(2
 // model.py:208-212 -- accumulator columns interleaved (f0,g0,f1,g1,...), N = 64 -> 32 gated outputs.
 struct RowGate {
   static constexpr bool kHasFinish = false;
-  float* y;          // [P, 32]
+  static constexpr int kAccPerBlock = 64;
+  float* y;          // [P, 32] (written through the kernel's output tensor map)
   const float* bf;
   const float* bg;
   __device__ __forceinline__ void init() {}
   __device__ __forceinline__ void prefetch(i64, bool) {}
-  __device__ __forceinline__ void consume16(i64 m, int c0, const float (&v)[16]) {
+  __device__ __forceinline__ void consume16(i64, int c0, const float (&v)[16], const RowSink& out) {
     const int ch0 = c0 >> 1;
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = gate_tanh(v[2 * j] + __ldg(bf + ch0 + j)) * gate_sigmoid(v[2 * j + 1] + __ldg(bg + ch0 + j));
-    float* p = y + m * 32 + ch0;
-    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    out.put4(ch0, o[0], o[1], o[2], o[3]);
+    out.put4(ch0 + 4, o[4], o[5], o[6], o[7]);
   }
   __device__ __forceinline__ void finish_rows(float*, int) {}
 };
@@ -85,6 +97,7 @@ struct RowGate {
 // Gate backward from recomputed pre-activations: dpre[m][2ch+{0,1}] (interleaved, 64 wide).
 struct RowGateBwd {
   static constexpr bool kHasFinish = false;
+  static constexpr int kAccPerBlock = 32;
   float* dpre;       // [P, 64]
   const float* dg;   // [P, 32]
   const float* bf;
@@ -94,7 +107,7 @@ struct RowGateBwd {
   __device__ __forceinline__ void prefetch(i64 m, bool valid) {
     if (valid) ld_row32(g, dg + m * 32);
   }
-  __device__ __forceinline__ void consume16(i64 m, int c0, const float (&v)[16]) {
+  __device__ __forceinline__ void consume16(i64, int c0, const float (&v)[16], const RowSink& out) {
     const int ch0 = c0 >> 1;
     float o[16];
 #pragma unroll
@@ -104,7 +117,7 @@ struct RowGateBwd {
       o[2 * j] = gg * s * (1.0f - f * f);
       o[2 * j + 1] = gg * f * s * (1.0f - s);
     }
-    st16(dpre + m * 64 + c0, o);
+    out.put16(c0 & 31, o);
   }
   __device__ __forceinline__ void finish_rows(float*, int) {}
 };
@@ -112,6 +125,7 @@ struct RowGateBwd {
 // gcn tail + residual + BatchNorm statistics (model.py:53-54, 234-236), N = 32.
 struct RowMlp {
   static constexpr bool kHasFinish = true;
+  static constexpr int kAccPerBlock = 32;
   float* y;            // [P, 32]
   const float* bias;
   DropoutSrc drop;
@@ -125,7 +139,7 @@ struct RowMlp {
   __device__ __forceinline__ void prefetch(i64 m, bool valid) {
     if (res && valid) ld_row32(rrow, res + rrm(m) * 32);
   }
-  __device__ __forceinline__ void consume16(i64 m, int c0, const float (&v)[16]) {
+  __device__ __forceinline__ void consume16(i64 m, int c0, const float (&v)[16], const RowSink& out) {
     float o[16];
     const i64 e = m * 32 + c0;
 #pragma unroll
@@ -144,7 +158,7 @@ struct RowMlp {
         o[c] = r;
       }
     }
-    st16(y + e, o);
+    out.put16(c0, o);
     if (stats) {
 #pragma unroll
       for (int c = 0; c < 16; ++c) { cs.s1[c0 + c] += o[c]; cs.s2[c0 + c] += o[c] * o[c]; }
@@ -158,20 +172,19 @@ struct RowMlp {
 // mlp input gradient: N = nseg*32 columns scattered to the per-segment tensors out[(q*M + m)*32 + nn].
 struct RowSeg {
   static constexpr bool kHasFinish = false;
+  static constexpr int kAccPerBlock = 32;
   float* out;
   i64 M;
   __device__ __forceinline__ void init() {}
   __device__ __forceinline__ void prefetch(i64, bool) {}
-  __device__ __forceinline__ void consume16(i64 m, int c0, const float (&v)[16]) {
-    const int q = c0 >> 5, nn = c0 & 31;
-    st16(out + ((i64)q * M + m) * 32 + nn, v);
-  }
+  __device__ __forceinline__ void consume16(i64, int c0, const float (&v)[16], const RowSink& o) { o.put16(c0 & 31, v); }
   __device__ __forceinline__ void finish_rows(float*, int) {}
 };
 
 // Gated-conv input gradient + residual path + BatchNorm-backward statistics of the layer below, N = 32.
 struct RowTcnDgrad {
   static constexpr bool kHasFinish = true;
+  static constexpr int kAccPerBlock = 32;
   float* dx;           // [P_in, 32]
   const float* du;     // nullable [P_out, 32]
   int N, L_in, L_out;
@@ -197,11 +210,11 @@ struct RowTcnDgrad {
     }
     if (uprev) ld_row32(urow, uprev + m * 32);
   }
-  __device__ __forceinline__ void consume16(i64 m, int c0, const float (&v)[16]) {
+  __device__ __forceinline__ void consume16(i64, int c0, const float (&v)[16], const RowSink& out) {
     float o[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) o[c] = v[c] + (has_du ? durow[c0 + c] : 0.0f);
-    st16(dx + m * 32 + c0, o);
+    out.put16(c0, o);
     if (uprev) {
 #pragma unroll
       for (int c = 0; c < 16; ++c) {

@@ -36,6 +36,11 @@ struct TcPosArgs {
   const float* Wp;    // packed weights [N][nseg*32]
   int N;
   const float* Wp_lo; // non-null: 3xTF32 (fp32-grade) mode -- Wp holds the tf32-exact high parts, Wp_lo the remainders
+  // output tensor, written by TMA from the swizzled staging tile: out_nblk 32-column blocks per row tile;
+  //   out_blk_dim2 == 0: [nb][rows_out][out_width], block k = columns 32k..32k+31;
+  //   out_blk_dim2 == 1: [out_nblk][rows_out][32] (one tensor per block, nb == 1).
+  float* out;
+  int out_width, out_nblk, out_blk_dim2;
 };
 
 // Dummy "tile" for the column-statistics state of row-owner epilogues: 8 slots of 4 columns = 32 columns.
@@ -52,9 +57,10 @@ struct TpMaps {
   CUtensorMap a[TP_MAXSEG];
   CUtensorMap w;
   CUtensorMap wlo;
+  CUtensorMap out;
 };
 struct TpParams {
-  int nseg, nb, rows_out, tiles_per_sample, total_tiles, N, stages;
+  int nseg, nb, rows_out, tiles_per_sample, total_tiles, N, stages, out_blk_dim2;
   int col0[TP_MAXSEG], rshift[TP_MAXSEG];
 };
 
@@ -74,8 +80,10 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
   const int w_plane = p.nseg * p.N * 128;                 // resident weights: [plane][seg][N rows][128 B]
   const int w_bytes = NPL * w_plane;
   const uint32_t a0 = base + w_bytes;                     // A stages: [A | A_lo]
-  const uint32_t bar0 = a0 + p.stages * STG;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + w_bytes + (size_t)p.stages * STG);
+  const uint32_t so0 = a0 + p.stages * STG;               // output staging ring: 2 x [128 rows][128 B], SWIZZLE_128B
+  uint8_t* so_ptr = smem + w_bytes + (size_t)p.stages * STG;
+  const uint32_t bar0 = so0 + 2 * TP_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(so_ptr + 2 * TP_A_BYTES);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
   auto split_bar = [&](int s) { return bar0 + 8u * (2 * p.stages + s); };
@@ -89,6 +97,7 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[s]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.out) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
     ep.init();
     const int ew = warp - 4;
     int acc = 0;
-    uint32_t accphase = 0;
+    uint32_t accphase = 0, ring = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_sample, rt = tile - b * p.tiles_per_sample;
       const int rl = rt * 128 + ew * 32 + lane;
@@ -208,23 +217,51 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * 256);
       const int ncols = NCT > 0 ? NCT : p.N;
+      constexpr int APB = EP::kAccPerBlock;
+      const int r = ew * 32 + lane;
+      auto do_block = [&](const int blk) {
+        // ring of two staging tiles: the TMA store that read this one two blocks ago must have finished reading
+        if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint8_t* sbuf = so_ptr + (ring & 1u) * TP_A_BYTES;
+        const RowSink sink{sbuf + r * 128, (uint32_t)(r & 7)};
 #pragma unroll
-      for (int c0 = 0; c0 < ncols; c0 += 16) {
-        uint32_t r[16];
-        tc_ld16(taddr + c0, r);
-        tc_wait_ld();
-        if (valid) {
-          float v[16];
+        for (int cc = 0; cc < APB; cc += 16) {
+          const int c0 = blk * APB + cc;
+          uint32_t rr[16];
+          tc_ld16(taddr + c0, rr);
+          tc_wait_ld();
+          if (valid) {
+            float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          ep.consume16(m, c0, v);
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+            ep.consume16(m, c0, v, sink);
+          }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the TMA engine
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 128) {
+          const int c0o = p.out_blk_dim2 ? 0 : 32 * blk, c2o = p.out_blk_dim2 ? blk : b;
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&maps.out),
+                       "r"(so0 + (ring & 1u) * TP_A_BYTES), "r"(c0o), "r"(rt * 128), "r"(c2o)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++ring;
+            };
+      if constexpr (NCT > 0) {   // compile-time block count: the epilogue's per-column register arrays stay in registers
+#pragma unroll
+        for (int blk = 0; blk < NCT / APB; ++blk) do_block(blk);
+      } else {
+#pragma unroll 1
+        for (int blk = 0; blk * APB < ncols; ++blk) do_block(blk);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) accphase ^= 1u;
     }
+    if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output tiles have landed
     if constexpr (EP::kHasFinish) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       ep.finish_rows(red, threadIdx.x - 128);
@@ -263,7 +300,17 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
   p.total_tiles = (int)tiles;
   const int w_bytes = (X3 ? 2 : 1) * a.nseg * a.N * 128;
   constexpr int STG = (X3 ? 2 : 1) * TP_A_BYTES;
-  p.stages = (SMEM_LIMIT - 2048 - w_bytes) / STG;
+  p.stages = (SMEM_LIMIT - 2048 - w_bytes - 2 * TP_A_BYTES) / STG;
+  p.out_blk_dim2 = a.out_blk_dim2;
+  if (!a.out || (reinterpret_cast<uintptr_t>(a.out) & 15) || a.out_width % 4 != 0 || a.out_nblk < 1 ||
+      a.out_nblk * EP::kAccPerBlock != a.N || (a.out_blk_dim2 ? (a.out_width != 32 || a.nb != 1) : (a.out_width < 32 * a.out_nblk)))
+    return -1;
+  {
+    cuuint64_t d[3] = {(cuuint64_t)a.out_width, (cuuint64_t)a.rows_out, (cuuint64_t)(a.out_blk_dim2 ? a.out_nblk : a.nb)};
+    cuuint64_t st[2] = {(cuuint64_t)a.out_width * 4, (cuuint64_t)a.rows_out * a.out_width * 4};
+    cuuint32_t box[3] = {32, 128, 1};
+    GWN_TRY(encode(&maps.out, a.out, 3, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) return -1;
   for (int s = 0; s < a.nseg; ++s) {
@@ -290,7 +337,7 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
       maps.wlo = maps.w;
     }
   }
-  const int smem_bytes = w_bytes + p.stages * STG + 1024 + 512;
+  const int smem_bytes = w_bytes + p.stages * STG + 2 * TP_A_BYTES + 1024 + 512;
   static cudaError_t attr = cudaFuncSetAttribute(tcpos_kernel<EP, NCT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   if (attr != cudaSuccess) {
     set_error("tcpos: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr));
