@@ -115,6 +115,18 @@ GWN_HD void atomic_add_d(double* p, double v) {
 
 GWN_HD float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// Remainder of the 3xTF32 split: tcgen05 kind::tf32 TRUNCATES an fp32 operand to its top 19 bits (probed on B200,
+// tests/tools/tf32_rounding_probe.py), so x itself serves as the high part and x - trunc(x) -- exact in fp32 -- is
+// the low part.
+GWN_HD float tf32_lo(float v) {
+  unsigned u;
+  memcpy(&u, &v, 4);
+  u &= 0xFFFFE000u;
+  float h;
+  memcpy(&h, &u, 4);
+  return v - h;
+}
+
 // Row remap between two BLNC tensors that share (B, N) but differ in time length:
 // position p = (b, t, n) of a tensor with lon_out = L_out*N rows per sample maps to
 // row (b, t + off_t, n) of a tensor with lon_in = L_in*N rows per sample; off = off_t*N.

@@ -279,7 +279,7 @@ GWN_GLOBAL bn_bwd_apply_kernel(float* dy, const float* u, const float* ac, const
 // Gated conv, BatchNorm affine of the layer below folded in:  Wp[2ch+g][tap*C+ci] = W_g[ch][ci][tap] * a[ci];
 // bias_g'[ch] = b_g[ch] + sum_{tap,ci} W_g[ch][ci][tap] * c[ci]      (conv(W, a*u + c) = conv(W*diag(a), u) + W.c)
 GWN_GLOBAL pack_tcn_fwd_kernel(const float* wf, const float* wg, const float* bf, const float* bg, const float* ac, float* Wp,
-                               float* bfp, float* bgp, int D, int C) {
+                               float* bfp, float* bgp, int D, int C, float* Wlo) {
   GWN_FOR_EACH_WARP_ROW(n, 2 * D, lane, WS) {   // one warp per packed output row n = 2*ch + gate
     const int ch = (int)(n >> 1), g = (int)(n & 1);
     const float* w = g ? wg : wf;
@@ -287,7 +287,9 @@ GWN_GLOBAL pack_tcn_fwd_kernel(const float* wf, const float* wg, const float* bf
     for (int k = lane; k < 2 * C; k += WS) {
       const int tap = k / C, ci = k - tap * C;
       const float v = w[((i64)ch * C + ci) * 2 + tap];
-      Wp[n * (2 * C) + k] = ac ? v * ac[ci] : v;
+      const float pv = ac ? v * ac[ci] : v;
+      Wp[n * (2 * C) + k] = pv;
+      if (Wlo) Wlo[n * (2 * C) + k] = tf32_lo(pv);
       if (ac) extra = fmaf(v, ac[C + ci], extra);
     }
     extra = warp_sum(extra);
@@ -295,11 +297,13 @@ GWN_GLOBAL pack_tcn_fwd_kernel(const float* wf, const float* wg, const float* bf
   }
 }
 // Gated conv input gradient:  Wd[ci][tap*2D + j] = W_{j&1}[j>>1][ci][tap]
-GWN_GLOBAL pack_tcn_dgrad_kernel(const float* wf, const float* wg, float* Wd, int D, int C) {
+GWN_GLOBAL pack_tcn_dgrad_kernel(const float* wf, const float* wg, float* Wd, int D, int C, float* Wlo) {
   GWN_FOR_EACH(i, (i64)C * 4 * D) {
     const int ci = (int)(i / (4 * D)), k = (int)(i - (i64)ci * 4 * D);
     const int tap = k / (2 * D), j = k - tap * 2 * D;
-    Wd[i] = ((j & 1) ? wg : wf)[((i64)(j >> 1) * C + ci) * 2 + tap];
+    const float v = ((j & 1) ? wg : wf)[((i64)(j >> 1) * C + ci) * 2 + tap];
+    Wd[i] = v;
+    if (Wlo) Wlo[i] = tf32_lo(v);
   }
 }
 // Gated-conv weight gradient from the raw tcgen05 reduction (tcred.cuh, kind 1): R[(tap*C+ci)*2D + j] = sum_p u[p+tap][ci] dpre[p][j],
@@ -320,11 +324,17 @@ GWN_GLOBAL tcn_wgrad_finalize_kernel(const float* R, const float* S, const float
   }
 }
 // WT[c][r] = W[r][c]
-GWN_GLOBAL transpose_kernel(const float* W, float* WT, int R, int Cc) {
+GWN_GLOBAL transpose_kernel(const float* W, float* WT, int R, int Cc, float* WTlo) {
   GWN_FOR_EACH(i, (i64)R * Cc) {
     const int c = (int)(i / R), r = (int)(i - (i64)c * R);
-    WT[i] = W[(i64)r * Cc + c];
+    const float v = W[(i64)r * Cc + c];
+    WT[i] = v;
+    if (WTlo) WTlo[i] = tf32_lo(v);
   }
+}
+// lo[i] = w[i] - tf32_trunc(w[i])
+GWN_GLOBAL split_lo_kernel(const float* w, float* lo, i64 n) {
+  GWN_FOR_EACH(i, n) { lo[i] = tf32_lo(w[i]); }
 }
 
 // dst[p, c] = (src ? src[p,c] : 0) + (t >= L - T_out ? win[(b, t-(L-T_out), n), c] : 0)

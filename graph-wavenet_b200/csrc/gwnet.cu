@@ -126,7 +126,8 @@ struct gwn_plan {
   // forward workspace offsets (floats)
   gwn::i64 o_sup, o_supT, o_x0, o_skip, o_e1, fwd_floats;
   std::vector<gwn::i64> o_g, o_u, o_ac, o_mr, o_sums, o_pack;
-  gwn::i64 pk_wp, pk_bf, pk_bg, pk_wd, pk_wt;   // offsets inside a layer's pack region (tf32 tier)
+  gwn::i64 pk_wp, pk_bf, pk_bg, pk_wd, pk_wt;   // offsets inside a layer's pack region (tensor-core tiers)
+  gwn::i64 pk_wp_lo, pk_wd_lo, pk_wt_lo, pk_wm_lo;   // 3xTF32 remainders of the packed weights (fp32x3 tier)
   // backward scratch offsets (floats)
   gwn::i64 o_part, part_floats, o_buf0, o_buf1, o_dh, o_dg, o_dpre, o_dgh, o_dout, o_de1, o_dskip, o_dA, o_dR, o_bsum, bwd_floats;
   std::vector<gwn::i64> o_dsegs;   // per layer when the support gradient is deferred to ONE launch per backward pass
@@ -275,7 +276,11 @@ static int build_plan(gwn_plan* p) {
   p->pk_bg = p->pk_bf + align_up(D);
   p->pk_wd = p->pk_bg + align_up(D);
   p->pk_wt = p->pk_wd + align_up((i64)C * 4 * D);
-  const i64 pack_floats = p->pk_wt + align_up((i64)p->nseg * D * C);
+  p->pk_wp_lo = p->pk_wt + align_up((i64)p->nseg * D * C);
+  p->pk_wd_lo = p->pk_wp_lo + align_up((i64)2 * D * 2 * C);
+  p->pk_wt_lo = p->pk_wd_lo + align_up((i64)C * 4 * D);
+  p->pk_wm_lo = p->pk_wt_lo + align_up((i64)p->nseg * D * C);
+  const i64 pack_floats = p->pk_wm_lo + align_up((i64)p->nseg * D * C);
   for (int i = 0; i < nL; ++i) {
     p->o_g[i] = take(p->P(i) * D * p->nseg);  // g_i followed by its hop tensors
     p->o_u[i] = take(p->P(i) * C);
@@ -372,8 +377,10 @@ static ARows tcn_arows(const gwn_plan* p, const float* prev, const float* prev_a
 }
 // tcgen05 + TMA position GEMMs: tf32 tier with the reference's default widths.
 static bool tcpos_ok(const gwn_plan* p) {
-  return p->c.precision == GWN_PREC_TF32 && p->c.residual_channels == 32 && p->c.dilation_channels == 32;
+  return (p->c.precision == GWN_PREC_TF32 || p->c.precision == GWN_PREC_FP32X3) && p->c.residual_channels == 32 &&
+         p->c.dilation_channels == 32;
 }
+static bool x3(const gwn_plan* p) { return p->c.precision == GWN_PREC_FP32X3; }
 static TcPosArgs tcn_tcpos_args(const gwn_plan* p, const float* prev, const float* Wp, int i) {
   TcPosArgs t;
   memset(&t, 0, sizeof(t));
@@ -462,12 +469,13 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
         float* pk = ws + p->o_pack[i];
         GWN_LAUNCH_WARP_ROWS(pack_tcn_fwd_kernel, 2 * D, st, P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw),
                       P_<float>(prm, p->li[i].fb), P_<float>(prm, p->li[i].gb), prev_ac, pk + p->pk_wp, pk + p->pk_bf,
-                      pk + p->pk_bg, D, C);
+                      pk + p->pk_bg, D, C, x3(p) ? pk + p->pk_wp_lo : (float*)nullptr);
         RowGate eg;
         memset(&eg, 0, sizeof(eg));
         eg.y = g; eg.bf = pk + p->pk_bf; eg.bg = pk + p->pk_bg;
         TcPosArgs ta = tcn_tcpos_args(p, prev, pk + p->pk_wp, i);
         ta.out = g; ta.out_width = D; ta.out_nblk = 1;
+        if (x3(p)) ta.Wp_lo = pk + p->pk_wp_lo;
         pst = launch_tcpos<64>(ta, eg, st);
         if (pst > 0) return pst;
       }
@@ -485,6 +493,7 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     MlpFwdArgs m;
     memset(&m, 0, sizeof(m));
     m.tf32_tc = tcpos_ok(p) ? 1 : 0;
+    float* pk_m = ws + p->o_pack[i];
     if (c.gcn) {
       GcnShape gs{B, p->L[i], N, D, C, p->S, c.order};
       GWN_TRY(gcn_hops_forward(gs, g, supF, g + Pi * D, st, &tcF));
@@ -497,10 +506,15 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     m.segs = segs; m.nseg = p->nseg; m.P = Pi; m.D = D; m.C_out = C;
     m.drop = layer_dropout(p, a->training, a->dropout_mode, a->keep_masks, a->seed, i, a->seed_device);
     m.res = prev;
+    m.nb = B; m.rows_per_sample = p->L[i] * N; m.res_rows_src = p->Lin(i) * N; m.res_rshift = (p->Lin(i) - p->L[i]) * N;
     m.rrm = make_remap(p->L[i], p->Lin(i), p->Lin(i) - p->L[i], N);
     m.rac = prev_ac;
     m.stats = a->training ? reinterpret_cast<double*>(ws + p->o_sums[i]) : nullptr;
     m.y = ws + p->o_u[i];
+    if (tcpos_ok(p) && x3(p)) {
+      GWN_LAUNCH_1D(split_lo_kernel, (i64)C * p->nseg * D, st, m.W, pk_m + p->pk_wm_lo, (i64)C * p->nseg * D);
+      m.W_lo = pk_m + p->pk_wm_lo;
+    }
     GWN_TRY(mlp_forward(m, st));
     if (a->training) {
       GWN_LAUNCH_1D(bn_finalize_kernel, C, st, reinterpret_cast<const double*>(ws + p->o_sums[i]), (double)Pi,
@@ -735,8 +749,10 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
       m.dsegs = dsegs;
       if (tcpos_ok(p)) {
         float* pk = const_cast<float*>(ws) + p->o_pack[i];
-        GWN_LAUNCH_1D(transpose_kernel, (i64)C * p->nseg * D, st, m.W, pk + p->pk_wt, C, p->nseg * D);
+        GWN_LAUNCH_1D(transpose_kernel, (i64)C * p->nseg * D, st, m.W, pk + p->pk_wt, C, p->nseg * D,
+                      x3(p) ? pk + p->pk_wt_lo : (float*)nullptr);
         m.WT = pk + p->pk_wt;
+        if (x3(p)) m.WT_lo = pk + p->pk_wt_lo;
       }
       m.dW = G(c.gcn ? p->li[i].mw : p->li[i].rw);
       m.dbias = G(c.gcn ? p->li[i].mb : p->li[i].rb);
@@ -780,6 +796,8 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
         eg.dpre = dpre; eg.dg = dgp; eg.bf = pk + p->pk_bf; eg.bg = pk + p->pk_bg;
         TcPosArgs ta = tcn_tcpos_args(p, prev, pk + p->pk_wp, i);
         ta.out = dpre; ta.out_width = 2 * D; ta.out_nblk = 2;
+        if (x3(p)) ta.Wp_lo = pk + p->pk_wp_lo;
+        ta.addend[0] = TcPosSeg{dgp, p->L[i] * N, 32, 0, 0};
         pst = launch_tcpos<64>(ta, eg, st);
         if (pst > 0) return pst;
       }
@@ -808,7 +826,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
       if (tcpos_ok(p)) {
         float* pk = const_cast<float*>(ws) + p->o_pack[i];
         GWN_LAUNCH_1D(pack_tcn_dgrad_kernel, (i64)C * 4 * D, st, P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw),
-                      pk + p->pk_wd, D, C);
+                      pk + p->pk_wd, D, C, x3(p) ? pk + p->pk_wd_lo : (float*)nullptr);
         RowTcnDgrad eg;
         memset(&eg, 0, sizeof(eg));
         eg.dx = ep.dx; eg.du = ep.du; eg.N = N; eg.L_in = ep.L_in; eg.L_out = ep.L_out;
@@ -818,6 +836,9 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
         for (int q = 0; q < 4; ++q) t.seg[q] = TcPosSeg{dpre, p->L[i] * N, 2 * D, (q & 1) * 32, -(q >> 1) * p->dil[i] * N};
         t.nseg = 4; t.nb = B; t.rows_out = p->Lin(i) * N; t.Wp = pk + p->pk_wd; t.N = 32;
         t.out = eg.dx; t.out_width = 32; t.out_nblk = 1;
+        if (x3(p)) t.Wp_lo = pk + p->pk_wd_lo;
+        if (eg.du) t.addend[0] = TcPosSeg{eg.du, p->L[i] * N, 32, 0, -(p->Lin(i) - p->L[i]) * N};
+        if (eg.uprev) t.addend[1] = TcPosSeg{eg.uprev, p->Lin(i) * N, 32, 0, 0};
         pst = launch_tcpos<32>(t, eg, st);
         if (pst > 0) return pst;
       }
@@ -842,7 +863,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     }
     bool wgrad_done = false;
     ProfScope prof_w("gated_tcn_wgrad", st, 4.0 * ((double)Pin * C + (double)Pi * 2 * D), 2.0 * Pi * 2 * D * (2.0 * C + 1));
-    if (tcpos_ok(p) && tsc.partial) {   // tcgen05 + TMA reduction over all positions; the slot reduction folds the
+    if (tcpos_ok(p) && !x3(p) && tsc.partial) {   // tcgen05 + TMA reduction over all positions; the slot reduction folds the
 #if !GWN_EMU                            // BatchNorm affine of the layer below and scatters to the four gradients
       TcRedArgs t;
       memset(&t, 0, sizeof(t));

@@ -151,6 +151,7 @@ struct MlpFwdArgs {
   i64 P;
   int D, C_out;
   const float* W;            // [C_out, nseg*D]
+  const float* W_lo;         // nullable: 3xTF32 remainders of W (fp32x3 tier on the tcgen05 path)
   const float* bias;
   DropoutSrc drop;
   const float* res;          // nullable residual source
@@ -159,6 +160,9 @@ struct MlpFwdArgs {
   double* stats;             // nullable
   float* y;
   int tf32_tc;               // 1: tf32 tier -> tcgen05/TMA kernel when the shape allows
+  // per-sample geometry of the residual (tcgen05 path): P = nb * rows_per_sample, residual row of output row r of a
+  // sample = row r + res_rshift of a source with res_rows_src rows per sample.  nb == 0: flat positions, no residual.
+  int nb, rows_per_sample, res_rows_src, res_rshift;
 };
 inline int mlp_forward(const MlpFwdArgs& m, cudaStream_t stream) {
   GWN_CHECK_ARG(m.nseg >= 1 && m.nseg <= MAXSEG, "mlp: %d segments (max %d)", m.nseg, MAXSEG);
@@ -169,12 +173,15 @@ inline int mlp_forward(const MlpFwdArgs& m, cudaStream_t stream) {
   LdWK b;
   memset(&b, 0, sizeof(b));
   b.p[0] = m.W; b.set_wd(m.nseg * m.D); b.ldw = m.nseg * m.D;
-  if (m.tf32_tc && m.D == 32 && m.C_out == 32 && m.nseg <= TP_MAXSEG && m.P < 2147483647LL) {   // tcgen05 + TMA path
+  if (m.tf32_tc && m.D == 32 && m.C_out == 32 && m.nseg <= TP_MAXSEG && m.P < 2147483647LL &&
+      (!m.res || (m.nb > 0 && (i64)m.nb * m.rows_per_sample == m.P))) {   // tcgen05 + TMA path
     TcPosArgs t;
     memset(&t, 0, sizeof(t));
-    for (int q = 0; q < m.nseg; ++q) t.seg[q] = TcPosSeg{m.segs[q], (int)m.P, 32, 0, 0};
-    t.nseg = m.nseg; t.nb = 1; t.rows_out = (int)m.P; t.Wp = m.W; t.N = 32;
-    t.out = m.y; t.out_width = 32; t.out_nblk = 1;
+    const int nb = m.nb > 0 ? m.nb : 1, rows = m.nb > 0 ? m.rows_per_sample : (int)m.P;
+    for (int q = 0; q < m.nseg; ++q) t.seg[q] = TcPosSeg{m.segs[q], rows, 32, 0, 0};
+    t.nseg = m.nseg; t.nb = nb; t.rows_out = rows; t.Wp = m.W; t.N = 32;
+    t.out = m.y; t.out_width = 32; t.out_nblk = 1; t.Wp_lo = m.W_lo;
+    if (m.res) t.addend[0] = TcPosSeg{m.res, m.res_rows_src, 32, 0, m.res_rshift};
     RowMlp eg;
     memset(&eg, 0, sizeof(eg));
     eg.y = m.y; eg.bias = m.bias; eg.drop = m.drop; eg.res = m.res; eg.rrm = m.rrm; eg.rac = m.rac; eg.stats = m.stats;
@@ -215,7 +222,8 @@ struct MlpBwdArgs {
   float* dsegs;               // [nseg][P][D] (written); nullable to skip the data gradient
   float* dW;                  // accumulated (atomic); nullable
   float* dbias;               // accumulated; nullable iff dW is
-  const float* WT;            // nullable: W transposed [nseg*D][C_out] -> tcgen05/TMA input-gradient kernel (tf32 tier)
+  const float* WT;            // nullable: W transposed [nseg*D][C_out] -> tcgen05/TMA input-gradient kernel
+  const float* WT_lo;         // nullable: its 3xTF32 remainders (fp32x3 tier)
   TcScratch ts;               // partial-result scratch of the tcgen05 weight-gradient reduction (null: not available)
 };
 inline int mlp_backward(const MlpBwdArgs& m, cudaStream_t stream) {
@@ -236,7 +244,7 @@ inline int mlp_backward(const MlpBwdArgs& m, cudaStream_t stream) {
       memset(&t, 0, sizeof(t));
       t.seg[0] = TcPosSeg{m.dh, (int)m.P, 32, 0, 0};
       t.nseg = 1; t.nb = 1; t.rows_out = (int)m.P; t.Wp = m.WT; t.N = Ktot;
-      t.out = m.dsegs; t.out_width = 32; t.out_nblk = m.nseg; t.out_blk_dim2 = 1;
+      t.out = m.dsegs; t.out_width = 32; t.out_nblk = m.nseg; t.out_blk_dim2 = 1; t.Wp_lo = m.WT_lo;
       RowSeg rs;
       memset(&rs, 0, sizeof(rs));
       rs.out = m.dsegs; rs.M = m.P;

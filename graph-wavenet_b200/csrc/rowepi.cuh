@@ -2,12 +2,14 @@
 // position row of the accumulator tile.  Contract:
 //     static constexpr int kAccPerBlock;                   // accumulator columns that make one 32-wide output block
 //     void init();
-//     void prefetch(i64 m, bool valid);                    // issue the global loads of the row's addends (128-bit)
+//     static constexpr int kAddends;                       // addend tiles TMA stages per row tile (0..2)
+//     void load_addends(const AddendRows& a, bool valid);  // copy the row's addends from the staged tiles to registers
 //     void consume16(i64 m, int c0, const float (&v)[16], RowSink& out);   // accumulator columns c0..c0+15 of row m
 //     void finish_rows(float* red, int etid);              // if kHasFinish: block-level reduce of column statistics
-// Addends are fetched as whole 128-byte rows BEFORE the accumulator is waited for (ncu on the first version, which
-// loaded them 4 floats at a time inside the column loop, showed the epilogue stalled on those dependent loads
-// for ~10k cycles per tile).  Outputs go to a 128B-swizzled shared-memory staging tile that one thread hands to TMA
+// Addends (residual rows, upstream gradients, saved activations) arrive like the GEMM operands: the producer warp
+// TMA-loads them as 128-row tiles one tile ahead, so their HBM latency never sits on the epilogue's critical path
+// (ncu r01c: with per-thread global loads the single epilogue warp per scheduler was latency-bound, "no eligible
+// warp" 81-88 % of cycles).  Outputs go to a 128B-swizzled shared-memory staging tile that one thread hands to TMA
 // (cp.async.bulk.tensor store): a row-owner thread storing its row straight to global writes 16 bytes per 128-byte
 // line per instruction, and ncu (r01c) showed those kernels bound by L2 sector traffic (L2 72 %, DRAM 22 %).
 // Same arithmetic as the functors of functors.cuh.
@@ -24,6 +26,19 @@ __device__ __forceinline__ void ld_row32(float (&r)[32], const float* p) {
     r[4 * q] = f.x; r[4 * q + 1] = f.y; r[4 * q + 2] = f.z; r[4 * q + 3] = f.w;
   }
 }
+// The calling thread's row in up to two staged addend tiles (SWIZZLE_128B, 128 bytes per row).
+struct AddendRows {
+  const uint8_t* row[2];   // tile + r * 128
+  uint32_t x;              // r & 7
+  __device__ __forceinline__ void load(int which, float (&r)[32]) const {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 f = *reinterpret_cast<const float4*>(row[which] + (((uint32_t)q ^ x) << 4));
+      r[4 * q] = f.x; r[4 * q + 1] = f.y; r[4 * q + 2] = f.z; r[4 * q + 3] = f.w;
+    }
+  }
+};
+
 // One row (128 bytes = 32 floats) of the staging tile, SWIZZLE_128B: 16-byte chunk j of row r lives at chunk j ^ (r & 7).
 struct RowSink {
   uint8_t* row;   // staging tile + r * 128
@@ -78,11 +93,12 @@ __device__ __forceinline__ float gate_tanh(float x) { return 1.0f - __fdividef(2
 struct RowGate {
   static constexpr bool kHasFinish = false;
   static constexpr int kAccPerBlock = 64;
+  static constexpr int kAddends = 0;
   float* y;          // [P, 32] (written through the kernel's output tensor map)
   const float* bf;
   const float* bg;
   __device__ __forceinline__ void init() {}
-  __device__ __forceinline__ void prefetch(i64, bool) {}
+  __device__ __forceinline__ void load_addends(const AddendRows&, bool) {}
   __device__ __forceinline__ void consume16(i64, int c0, const float (&v)[16], const RowSink& out) {
     const int ch0 = c0 >> 1;
     float o[8];
@@ -98,14 +114,15 @@ struct RowGate {
 struct RowGateBwd {
   static constexpr bool kHasFinish = false;
   static constexpr int kAccPerBlock = 32;
+  static constexpr int kAddends = 1;   // dg rows
   float* dpre;       // [P, 64]
-  const float* dg;   // [P, 32]
+  const float* dg;   // [P, 32] (addend tile 0)
   const float* bf;
   const float* bg;
   float g[32];
   __device__ __forceinline__ void init() {}
-  __device__ __forceinline__ void prefetch(i64 m, bool valid) {
-    if (valid) ld_row32(g, dg + m * 32);
+  __device__ __forceinline__ void load_addends(const AddendRows& a, bool valid) {
+    if (valid) a.load(0, g);
   }
   __device__ __forceinline__ void consume16(i64, int c0, const float (&v)[16], const RowSink& out) {
     const int ch0 = c0 >> 1;
@@ -126,6 +143,7 @@ struct RowGateBwd {
 struct RowMlp {
   static constexpr bool kHasFinish = true;
   static constexpr int kAccPerBlock = 32;
+  static constexpr int kAddends = 1;   // residual rows (tile 0; staged only when res != nullptr)
   float* y;            // [P, 32]
   const float* bias;
   DropoutSrc drop;
@@ -136,8 +154,8 @@ struct RowMlp {
   float rrow[32];
   RowStats32 cs;
   __device__ __forceinline__ void init() { cs.reset(); }
-  __device__ __forceinline__ void prefetch(i64 m, bool valid) {
-    if (res && valid) ld_row32(rrow, res + rrm(m) * 32);
+  __device__ __forceinline__ void load_addends(const AddendRows& a, bool valid) {
+    if (res && valid) a.load(0, rrow);
   }
   __device__ __forceinline__ void consume16(i64 m, int c0, const float (&v)[16], const RowSink& out) {
     float o[16];
@@ -173,10 +191,11 @@ struct RowMlp {
 struct RowSeg {
   static constexpr bool kHasFinish = false;
   static constexpr int kAccPerBlock = 32;
+  static constexpr int kAddends = 0;
   float* out;
   i64 M;
   __device__ __forceinline__ void init() {}
-  __device__ __forceinline__ void prefetch(i64, bool) {}
+  __device__ __forceinline__ void load_addends(const AddendRows&, bool) {}
   __device__ __forceinline__ void consume16(i64, int c0, const float (&v)[16], const RowSink& o) { o.put16(c0 & 31, v); }
   __device__ __forceinline__ void finish_rows(float*, int) {}
 };
@@ -185,6 +204,7 @@ struct RowSeg {
 struct RowTcnDgrad {
   static constexpr bool kHasFinish = true;
   static constexpr int kAccPerBlock = 32;
+  static constexpr int kAddends = 2;
   float* dx;           // [P_in, 32]
   const float* du;     // nullable [P_out, 32]
   int N, L_in, L_out;
@@ -192,28 +212,19 @@ struct RowTcnDgrad {
   const float* mr;     // mean[32], rstd[32]
   double* bsum;
   float durow[32], urow[32];
-  bool has_du;
   RowStats32 cs;
   __device__ __forceinline__ void init() { cs.reset(); }
-  __device__ __forceinline__ void prefetch(i64 m, bool valid) {
-    has_du = false;
+  // addend tile 0: du rows shifted by (L_in - L_out) time steps (rows before the first step arrive as zeros: TMA
+  // out-of-bounds fill); tile 1: the layer-below pre-BN rows (only staged when uprev != nullptr)
+  __device__ __forceinline__ void load_addends(const AddendRows& a, bool valid) {
     if (!valid) return;
-    if (du) {
-      const unsigned lon = (unsigned)L_in * (unsigned)N;
-      const unsigned b = (unsigned)m / lon, rr = (unsigned)m - b * lon;
-      const int tp = (int)(rr / (unsigned)N), node = (int)(rr - (unsigned)tp * (unsigned)N);
-      const int t = tp - (L_in - L_out);
-      if (t >= 0) {
-        has_du = true;
-        ld_row32(durow, du + (((i64)b * L_out + t) * N + node) * 32);
-      }
-    }
-    if (uprev) ld_row32(urow, uprev + m * 32);
+    if (du) a.load(0, durow);
+    if (uprev) a.load(1, urow);
   }
   __device__ __forceinline__ void consume16(i64, int c0, const float (&v)[16], const RowSink& out) {
     float o[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) o[c] = v[c] + (has_du ? durow[c0 + c] : 0.0f);
+    for (int c = 0; c < 16; ++c) o[c] = v[c] + (du ? durow[c0 + c] : 0.0f);
     out.put16(c0, o);
     if (uprev) {
 #pragma unroll

@@ -41,6 +41,9 @@ struct TcPosArgs {
   //   out_blk_dim2 == 1: [out_nblk][rows_out][32] (one tensor per block, nb == 1).
   float* out;
   int out_width, out_nblk, out_blk_dim2;
+  // epilogue addend tiles (rows of 32 floats, same row tiling as the output, rshift like a segment); addend[k].src may
+  // be null (slot unused); the epilogue functor knows which it reads
+  TcPosSeg addend[2];
 };
 
 // Dummy "tile" for the column-statistics state of row-owner epilogues: 8 slots of 4 columns = 32 columns.
@@ -58,9 +61,11 @@ struct TpMaps {
   CUtensorMap w;
   CUtensorMap wlo;
   CUtensorMap out;
+  CUtensorMap add[2];
 };
 struct TpParams {
   int nseg, nb, rows_out, tiles_per_sample, total_tiles, N, stages, out_blk_dim2;
+  int add_on[2], add_rshift[2], nadd;
   int col0[TP_MAXSEG], rshift[TP_MAXSEG];
 };
 
@@ -82,22 +87,29 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
   const uint32_t a0 = base + w_bytes;                     // A stages: [A | A_lo]
   const uint32_t so0 = a0 + p.stages * STG;               // output staging ring: 2 x [128 rows][128 B], SWIZZLE_128B
   uint8_t* so_ptr = smem + w_bytes + (size_t)p.stages * STG;
-  const uint32_t bar0 = so0 + 2 * TP_A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(so_ptr + 2 * TP_A_BYTES);
+  constexpr int NADD = EP::kAddends;                      // addend ring: 2 x NADD tiles
+  const uint32_t ad0 = so0 + 2 * TP_A_BYTES;
+  const uint8_t* ad_ptr = so_ptr + 2 * TP_A_BYTES;
+  const uint32_t bar0 = ad0 + 2 * NADD * TP_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(so_ptr + (2 + 2 * NADD) * TP_A_BYTES);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
   auto split_bar = [&](int s) { return bar0 + 8u * (2 * p.stages + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * p.stages + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * p.stages + 2 + a); };
   const uint32_t w_bar = bar0 + 8u * (3 * p.stages + 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 5);
-  float* red = reinterpret_cast<float*>(bars + 3 * p.stages + 6);   // 64 floats for the statistics reduce
+  auto efull_bar = [&](int e) { return bar0 + 8u * (3 * p.stages + 5 + e); };
+  auto eempty_bar = [&](int e) { return bar0 + 8u * (3 * p.stages + 7 + e); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 9);
+  float* red = reinterpret_cast<float*>(bars + 3 * p.stages + 10);   // 64 floats for the statistics reduce
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[s]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.out) : "memory");
+    for (int k = 0; k < NADD; ++k)
+      if (p.add_on[k]) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.add[k]) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -110,6 +122,10 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
       mbar_init(tempty_bar(a), 128);
     }
     mbar_init(w_bar, 1);
+    for (int e = 0; e < 2; ++e) {
+      mbar_init(efull_bar(e), 1);
+      mbar_init(eempty_bar(e), 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -127,11 +143,20 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
     for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + s * p.N * 128, &maps.w, w_bar, s * 32, 0);
     if (X3)
       for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + w_plane + s * p.N * 128, &maps.wlo, w_bar, s * 32, 0);
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = 0, eb = 0;
+    uint32_t phase = 0, ephase = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
       const int b = tile / p.tiles_per_sample, rt = tile - b * p.tiles_per_sample;
+      if (NADD > 0 && p.nadd > 0) {   // the epilogue's addend tiles of this row tile
+        if (!mbar_wait(eempty_bar(eb), ephase ^ 1u, 18)) { ok = false; break; }
+        mbar_expect_tx(efull_bar(eb), (uint32_t)p.nadd * TP_A_BYTES);
+        for (int k = 0; k < NADD; ++k)
+          if (p.add_on[k])
+            tma_load_3d(ad0 + (eb * NADD + k) * TP_A_BYTES, &maps.add[k], efull_bar(eb), 0, rt * 128 + p.add_rshift[k], b);
+        eb ^= 1;
+        if (eb == 0) ephase ^= 1u;
+      }
       for (int s = 0; s < p.nseg; ++s) {
         if (!mbar_wait(empty_bar(stage), phase ^ 1u, 11)) { ok = false; break; }
         mbar_expect_tx(full_bar(stage), TP_A_BYTES);
@@ -206,13 +231,25 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
     ep.init();
     const int ew = warp - 4;
     int acc = 0;
-    uint32_t accphase = 0, ring = 0;
+    uint32_t accphase = 0, ring = 0, ephase = 0;
+    int eb = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_sample, rt = tile - b * p.tiles_per_sample;
       const int rl = rt * 128 + ew * 32 + lane;
       const bool valid = rl < p.rows_out;
       const i64 m = (i64)b * p.rows_out + rl;
-      ep.prefetch(m, valid);               // addend rows are in flight while the MMAs of this tile finish
+      if (NADD > 0 && p.nadd > 0) {        // this row's addends: staged tile -> registers, then hand the buffer back
+        if (!mbar_wait(efull_bar(eb), ephase, 19)) break;
+        const int r0 = ew * 32 + lane;
+        AddendRows ar;
+        ar.row[0] = ad_ptr + (size_t)(eb * NADD) * TP_A_BYTES + r0 * 128;
+        ar.row[1] = ad_ptr + (size_t)(eb * NADD + (NADD > 1 ? 1 : 0)) * TP_A_BYTES + r0 * 128;
+        ar.x = (uint32_t)(r0 & 7);
+        ep.load_addends(ar, valid);
+        mbar_arrive(eempty_bar(eb));
+        eb ^= 1;
+        if (eb == 0) ephase ^= 1u;
+      }
       if (!mbar_wait(tfull_bar(acc), accphase, 15)) break;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * 256);
@@ -300,7 +337,20 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
   p.total_tiles = (int)tiles;
   const int w_bytes = (X3 ? 2 : 1) * a.nseg * a.N * 128;
   constexpr int STG = (X3 ? 2 : 1) * TP_A_BYTES;
-  p.stages = (SMEM_LIMIT - 2048 - w_bytes - 2 * TP_A_BYTES) / STG;
+  constexpr int FIXED = (2 + 2 * EP::kAddends) * TP_A_BYTES;   // output staging ring + addend ring
+  p.stages = (SMEM_LIMIT - 2048 - w_bytes - FIXED) / STG;
+  for (int k = 0; k < 2; ++k) {
+    const TcPosSeg& g = a.addend[k];
+    if (!g.src || k >= EP::kAddends) continue;
+    if ((reinterpret_cast<uintptr_t>(g.src) & 15) || g.row_width != 32) return -1;
+    cuuint64_t d[3] = {32, (cuuint64_t)g.rows_src, (cuuint64_t)a.nb};
+    cuuint64_t st[2] = {128, (cuuint64_t)g.rows_src * 128};
+    cuuint32_t box[3] = {32, 128, 1};
+    GWN_TRY(encode(&maps.add[k], g.src, 3, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    p.add_on[k] = 1;
+    p.add_rshift[k] = g.rshift;
+    p.nadd += 1;
+  }
   p.out_blk_dim2 = a.out_blk_dim2;
   if (!a.out || (reinterpret_cast<uintptr_t>(a.out) & 15) || a.out_width % 4 != 0 || a.out_nblk < 1 ||
       a.out_nblk * EP::kAccPerBlock != a.N || (a.out_blk_dim2 ? (a.out_width != 32 || a.nb != 1) : (a.out_width < 32 * a.out_nblk)))
@@ -337,7 +387,9 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
       maps.wlo = maps.w;
     }
   }
-  const int smem_bytes = w_bytes + p.stages * STG + 2 * TP_A_BYTES + 1024 + 512;
+  for (int k = 0; k < 2; ++k)
+    if (!p.add_on[k]) maps.add[k] = maps.out;
+  const int smem_bytes = w_bytes + p.stages * STG + FIXED + 1024 + 512;
   static cudaError_t attr = cudaFuncSetAttribute(tcpos_kernel<EP, NCT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   if (attr != cudaSuccess) {
     set_error("tcpos: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr));
