@@ -124,7 +124,7 @@ struct gwn_plan {
   int i_nv1, i_nv2, i_startw, i_startb, i_e1w, i_e1b, i_e2w, i_e2b;
   gwn::i64 grad_floats;
   // forward workspace offsets (floats)
-  gwn::i64 o_sup, o_supT, o_x0, o_skip, o_e1, fwd_floats;
+  gwn::i64 o_sup, o_supT, o_sup_lo, sup_span, o_x0, o_skip, o_e1, fwd_floats;
   std::vector<gwn::i64> o_g, o_u, o_ac, o_mr, o_sums, o_pack;
   gwn::i64 pk_wp, pk_bf, pk_bg, pk_wd, pk_wt;   // offsets inside a layer's pack region (tensor-core tiers)
   gwn::i64 pk_wp_lo, pk_wd_lo, pk_wt_lo, pk_wm_lo;   // 3xTF32 remainders of the packed weights (fp32x3 tier)
@@ -269,6 +269,8 @@ static int build_plan(gwn_plan* p) {
   };
   p->o_sup = take((i64)std::max(p->S, 1) * N * p->ld);
   p->o_supT = take((i64)std::max(p->S, 1) * N * p->ld);
+  p->sup_span = p->o_supT + (i64)std::max(p->S, 1) * N * p->ld - p->o_sup;   // both packed support regions
+  p->o_sup_lo = take(c.precision == GWN_PREC_FP32X3 ? p->sup_span : 0);        // their 3xTF32 remainders, same layout
   p->o_x0 = take(p->P0() * C);
   p->o_g.resize(nL); p->o_u.resize(nL); p->o_ac.resize(nL); p->o_mr.resize(nL); p->o_sums.resize(nL); p->o_pack.resize(nL);
   p->pk_wp = 0;
@@ -433,7 +435,10 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     supF[s] = support_padded(Ap, p->ld);
     supB[s] = support_padded(ATp, p->ld);
     tcF.S[s] = ATp;   // forward contraction y[w] = sum_v A[v,w] x[v]: K-contiguous rows are those of A^T
+    if (x3(p) && tcpos_ok(p)) tcF.Slo[s] = ws + p->o_sup_lo + (ATp - (ws + p->o_sup));
   }
+  if (x3(p) && tcpos_ok(p) && p->S > 0)
+    GWN_LAUNCH_1D(split_lo_kernel, p->sup_span, st, (const float*)(ws + p->o_sup), ws + p->o_sup_lo, p->sup_span);
   tcF.ld = p->ld;
   tcF.precision = c.precision;
   (void)supB;
@@ -604,6 +609,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
   for (int s = 0; s < p->S; ++s) {
     supB[s] = support_padded(ws + p->o_supT + (i64)s * N * p->ld, p->ld);
     tcB.S[s] = ws + p->o_sup + (i64)s * N * p->ld;   // dx[v] = sum_w A[v,w] dy[w]: K-contiguous rows are those of A
+    if (x3(p) && tcpos_ok(p)) tcB.Slo[s] = ws + p->o_sup_lo + (i64)s * N * p->ld;
   }
   tcB.ld = p->ld;
   tcB.precision = c.precision;

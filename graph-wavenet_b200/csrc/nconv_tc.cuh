@@ -18,6 +18,7 @@ constexpr int TC_MAXSUP = 4;
 struct NodeTcArgs {
   const float* X[TC_MAXSUP];       // slab tensors [nslabs][V][32]
   const float* S[TC_MAXSUP];       // k-major supports [V][ld]
+  const float* Slo[TC_MAXSUP];     // 3xTF32 mode (all non-null): their remainders S - tf32_trunc(S), same layout
   int ld;
   int nsup;
   int kcat;                        // 1: one output, summed over supports; 0: nsup independent outputs

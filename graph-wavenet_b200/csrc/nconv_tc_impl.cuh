@@ -20,6 +20,7 @@ constexpr int ACC_COLS = 256;                             // TMEM columns per ac
 struct Maps {
   CUtensorMap x[TC_MAXSUP];
   CUtensorMap s[TC_MAXSUP];
+  CUtensorMap slo[TC_MAXSUP];
 };
 
 struct Params {
@@ -33,19 +34,27 @@ struct Params {
 };
 
 // ------------------------------------------------------------------------------------------ kernel
+// X3 = 3xTF32 mode (fp32-grade): D = X.S + X.S_lo + X_lo.S with S_lo precomputed in global memory and X_lo produced
+// in shared memory by warps 2 and 3 from the tile TMA just landed (see tcpos.cuh; kind::tf32 truncates, so the fp32
+// tiles themselves are the high parts).  Stage layout: [X | X_lo | S | S_lo].
+template <bool X3>
 __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;           // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
-  const int stage_bytes = X_STAGE_BYTES + p.n_tile * 128;
+  constexpr int NPL = X3 ? 2 : 1;
+  constexpr int XB = NPL * X_STAGE_BYTES;                 // X planes of one stage
+  const int s_tile = p.n_tile * 128;                      // one support plane of one stage
+  const int stage_bytes = XB + NPL * s_tile;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   const uint32_t bar0 = base + p.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * p.stages + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * p.stages + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+  auto split_bar = [&](int s) { return bar0 + 8u * (2 * p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * p.stages + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -53,12 +62,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
     for (int s = 0; s < p.nsup; ++s) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x[s]) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.s[s]) : "memory");
+      if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.slo[s]) : "memory");
     }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
+      mbar_init(split_bar(s), 64);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -89,9 +100,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
         for (int kb = 0; kb < p.nkb; ++kb) {
           if (!mbar_wait(empty_bar(stage), phase ^ 1u, 1)) { ok = false; break; }
           const uint32_t dst = base + stage * stage_bytes;
-          mbar_expect_tx(full_bar(stage), (uint32_t)stage_bytes);
+          mbar_expect_tx(full_bar(stage), (uint32_t)(X_STAGE_BYTES + NPL * s_tile));
           tma_load_3d(dst, &maps.x[s], full_bar(stage), 0, kb * BLOCK_K, jt * SLABS);
-          tma_load_2d(dst + X_STAGE_BYTES, &maps.s[s], full_bar(stage), kb * BLOCK_K, wt * p.n_tile);
+          tma_load_2d(dst + XB, &maps.s[s], full_bar(stage), kb * BLOCK_K, wt * p.n_tile);
+          if (X3) tma_load_2d(dst + XB + s_tile, &maps.slo[s], full_bar(stage), kb * BLOCK_K, wt * p.n_tile);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -111,13 +123,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
       const int nk_total = (p.kcat ? p.nsup : 1) * p.nkb;
       for (int it = 0; it < nk_total; ++it) {
         if (!mbar_wait(full_bar(stage), phase, 3)) { ok = false; break; }
+        if (X3 && !mbar_wait(split_bar(stage), phase, 5)) { ok = false; break; }
         tc_fence_after();
         if (p.dbg && blockIdx.x == 0 && tile == 0 && it == 0) {
           const float* sm = reinterpret_cast<const float*>(smem + (size_t)stage * stage_bytes);
           for (int i = 0; i < stage_bytes / 4; ++i) p.dbg[i] = sm[i];
         }
         const uint32_t xs = base + stage * stage_bytes;
-        const uint32_t bs = xs + X_STAGE_BYTES;
+        const uint32_t bs = xs + XB;
 #pragma unroll
         for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
           // A (X^T, MN-major, 32-byte-atom swizzle): atoms of 4 k-rows x 128 B (SBO = 512 B between them);
@@ -131,6 +144,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
           // B (support, K-major): rows of 128 B (32 k), 8-row groups 1024 B apart; this k-step starts 32 B in
           const uint64_t bdesc = make_desc(bs + kk * (UMMA_K * 4), 16, 1024);
           if (p.mode != 1) tc_mma_tf32(d_tmem, adesc, bdesc, idesc_k, (it > 0 || kk > 0) ? 1u : 0u);
+          if (X3) {
+            tc_mma_tf32(d_tmem, adesc, make_desc(bs + s_tile + kk * (UMMA_K * 4), 16, 1024), idesc_k, 1u);
+            tc_mma_tf32(d_tmem, make_desc(xs + X_STAGE_BYTES + kk * (UMMA_K * 128), BLOCK_K * 128, 4 * 128, 1), bdesc, idesc_k, 1u);
+          }
         }
         tc_commit(empty_bar(stage));     // frees the smem stage once these MMAs have read it
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -139,6 +156,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
       tc_commit(tfull_bar(acc));         // accumulator complete -> epilogue
       acc ^= 1;
       if (acc == 0) accphase ^= 1u;
+    }
+  } else if (X3 && (warp == 2 || warp == 3)) {
+    // ===================================================== splitter: X_lo = X - tf32_trunc(X) (element-wise: layout-preserving)
+    const int t64 = threadIdx.x - 64;
+    int stage = 0;
+    uint32_t phase = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+      const int nk_total = (p.kcat ? p.nsup : 1) * p.nkb;
+      for (int it = 0; it < nk_total; ++it) {
+        if (!mbar_wait(full_bar(stage), phase, 6)) { ok = false; break; }
+        const float4* src = reinterpret_cast<const float4*>(smem + (size_t)stage * stage_bytes);
+        float4* dst = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + X_STAGE_BYTES);
+#pragma unroll 4
+        for (int i = t64; i < X_STAGE_BYTES / 16; i += 64) {
+          const float4 v = src[i];
+          dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(split_bar(stage));
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue: TMEM -> registers -> global
@@ -227,7 +266,8 @@ int tc_error_flag(int reset) {
   return v;
 }
 
-int node_gemm_tc(const NodeTcArgs& a, cudaStream_t stream) {
+template <bool X3>
+static int node_gemm_tc_impl(const NodeTcArgs& a, cudaStream_t stream) {
   using namespace tc;
   if (a.nsup < 1 || a.nsup > TC_MAXSUP) {
     set_error("node_gemm_tc: %d supports (max %d)", a.nsup, TC_MAXSUP);
@@ -247,7 +287,7 @@ int node_gemm_tc(const NodeTcArgs& a, cudaStream_t stream) {
   p.n_wt = (a.V + p.n_tile - 1) / p.n_tile;
   p.n_jt = (int)((nslabs + SLABS - 1) / SLABS);
   p.nkb = (a.V + BLOCK_K - 1) / BLOCK_K;
-  const int stage_bytes = X_STAGE_BYTES + p.n_tile * 128;
+  const int stage_bytes = (X3 ? 2 : 1) * (X_STAGE_BYTES + p.n_tile * 128);
   p.stages = (SMEM_LIMIT - 2048) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) {
@@ -274,8 +314,17 @@ int node_gemm_tc(const NodeTcArgs& a, cudaStream_t stream) {
     cuuint64_t ss[1] = {(cuuint64_t)a.ld * 4};
     cuuint32_t sb[2] = {BLOCK_K, (cuuint32_t)p.n_tile};
     GWN_TRY(encode(&maps.s[s], a.S[s], 2, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_128B));
+    if (X3) {
+      if (!a.Slo[s] || (reinterpret_cast<uintptr_t>(a.Slo[s]) & 15)) {
+        set_error("node_gemm_tc: 3xTF32 mode needs 16-byte aligned support remainders");
+        return GWN_ERR_UNSUPPORTED;
+      }
+      GWN_TRY(encode(&maps.slo[s], a.Slo[s], 2, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_128B));
+    } else {
+      maps.slo[s] = maps.s[s];
+    }
   }
-  for (int s = a.nsup; s < TC_MAXSUP; ++s) { maps.x[s] = maps.x[0]; maps.s[s] = maps.s[0]; }
+  for (int s = a.nsup; s < TC_MAXSUP; ++s) { maps.x[s] = maps.x[0]; maps.s[s] = maps.s[0]; maps.slo[s] = maps.slo[0]; }
   for (int o = 0; o < nout; ++o) {
     p.Y[o] = a.Y[o];
     p.add[o] = a.add[o];
@@ -289,7 +338,7 @@ int node_gemm_tc(const NodeTcArgs& a, cudaStream_t stream) {
   static cudaError_t attr_err = cudaSuccess;
   static int num_sms = 148;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(nconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    attr_err = cudaFuncSetAttribute(nconv_tc_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -299,10 +348,14 @@ int node_gemm_tc(const NodeTcArgs& a, cudaStream_t stream) {
     return GWN_ERR_CUDA;
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  nconv_tc_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(maps, p);
+  nconv_tc_kernel<X3><<<grid, NUM_THREADS, smem_bytes, stream>>>(maps, p);
   GWN_LAUNCH_CHECK();
   count_launch();
   return 0;
+}
+
+int node_gemm_tc(const NodeTcArgs& a, cudaStream_t stream) {
+  return a.Slo[0] ? node_gemm_tc_impl<true>(a, stream) : node_gemm_tc_impl<false>(a, stream);
 }
 
 }  // namespace gwn

@@ -47,6 +47,7 @@ inline void fill_support(LdSupport& l, int idx, const SupportView& s, int M) {
 // `tcs` (nullable): the same supports as K-contiguous padded buffers S[m][k] (ld = tc_ld) for the tcgen05 tier.
 struct TcSupports {
   const float* S[MAXSUP];
+  const float* Slo[MAXSUP];   // fp32x3 tier: remainders S - tf32_trunc(S)
   int ld;
   int precision;   // gwn_precision
 };
@@ -55,12 +56,13 @@ inline int node_gemm(const SupportView* sup, int nsup, bool kcat, const float* c
                      cudaStream_t stream, const TcSupports* tcs = nullptr) {
   GWN_CHECK_ARG(nsup >= 1 && nsup <= MAXSUP, "node_gemm: %d supports (max %d)", nsup, MAXSUP);
   GWN_CHECK_ARG(C % 4 == 0, "node_gemm: channels (%d) must be a multiple of 4", C);
-  if (tcs && tcs->precision == GWN_PREC_TF32) {
+  const bool x3 = tcs && tcs->precision == GWN_PREC_FP32X3 && tcs->Slo[0] && C == 32 && nsup <= TC_MAXSUP;
+  if (tcs && (tcs->precision == GWN_PREC_TF32 || x3)) {
     GWN_CHECK_ARG(C == 32, "node_gemm: the tcgen05 tier needs 32 channels per slab row (got %d)", C);
     GWN_CHECK_ARG(nsup <= TC_MAXSUP, "node_gemm: the tcgen05 tier takes at most %d supports", TC_MAXSUP);
     NodeTcArgs t;
     memset(&t, 0, sizeof(t));
-    for (int s = 0; s < nsup; ++s) { t.X[s] = X[s]; t.S[s] = tcs->S[s]; }
+    for (int s = 0; s < nsup; ++s) { t.X[s] = X[s]; t.S[s] = tcs->S[s]; t.Slo[s] = x3 ? tcs->Slo[s] : nullptr; }
     const int nout = kcat ? 1 : nsup;
     for (int s = 0; s < nout; ++s) { t.Y[s] = Y[s]; t.add[s] = add ? add[s] : nullptr; }
     t.ld = tcs->ld; t.nsup = nsup; t.kcat = kcat ? 1 : 0; t.add2 = add2; t.B = B; t.L = L; t.T_out = T_out; t.V = V;
