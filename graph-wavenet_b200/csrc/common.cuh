@@ -187,6 +187,8 @@ struct DropoutSrc {
   uint64_t seed, stream; // GWN_DROPOUT_PHILOX: key = seed, counter hi = stream (layer id)
   const unsigned long long* seed_dev;   // non-null: the key is read from device memory (CUDA-graph replays draw fresh masks)
   float p, scale;        // scale = 1/(1-p)
+  // One Philox4x32-10 block (128 random bits) serves 8 consecutive elements, 16 bits each: element e takes half-word
+  // (e & 7) of the block with counter e >> 3 and is kept iff  h >= p * 65536  (keep probability exact to 1.5e-5).
   GWN_HD void keep4(i64 e, float (&k)[4]) const {
     if (mode == GWN_DROPOUT_NONE) {
       k[0] = k[1] = k[2] = k[3] = 1.0f;
@@ -195,11 +197,32 @@ struct DropoutSrc {
       for (int i = 0; i < 4; ++i) k[i] = mask[e + i] ? scale : 0.0f;
     } else {
       uint32_t r[4];
-      Philox::gen(seed_dev ? (uint64_t)*seed_dev : seed, (uint64_t)(e >> 2), stream, r);
+      Philox::gen(seed_dev ? (uint64_t)*seed_dev : seed, (uint64_t)(e >> 3), stream, r);
+      const uint32_t thr = (uint32_t)(p * 65536.0f);
+      const int w0 = (int)((e >> 2) & 1) * 2;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float u = (float)(r[i] >> 8) * (1.0f / 16777216.0f);  // [0,1)
-        k[i] = (u >= p) ? scale : 0.0f;
+        const uint32_t h = (r[w0 + (i >> 1)] >> (16 * (i & 1))) & 0xFFFFu;
+        k[i] = (h >= thr) ? scale : 0.0f;
+      }
+    }
+  }
+  // 8 consecutive elements starting at e (e % 8 == 0): one Philox block.
+  GWN_HD void keep8(i64 e, float (&k)[8]) const {
+    if (mode == GWN_DROPOUT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) k[i] = 1.0f;
+    } else if (mode == GWN_DROPOUT_MASK) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) k[i] = mask[e + i] ? scale : 0.0f;
+    } else {
+      uint32_t r[4];
+      Philox::gen(seed_dev ? (uint64_t)*seed_dev : seed, (uint64_t)(e >> 3), stream, r);
+      const uint32_t thr = (uint32_t)(p * 65536.0f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t h = (r[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+        k[i] = (h >= thr) ? scale : 0.0f;
       }
     }
   }

@@ -302,7 +302,7 @@ static int build_plan(gwn_plan* p) {
   i64 maxPi = 0;
   for (int i = 0; i < nL; ++i) maxPi = std::max(maxPi, p->P(i));
   // tcgen05 reductions (tf32 tier): per-CTA partial results, 160 slots of the largest accumulator tile in use
-  const bool tc_tier = c.precision == GWN_PREC_TF32 && C == 32 && D == 32;
+  const bool tc_tier = (c.precision == GWN_PREC_TF32 || c.precision == GWN_PREC_FP32X3) && C == 32 && D == 32;
   p->defer_dA = tc_tier && c.adaptive && c.num_nodes <= 512 && 2 * nL <= TR_MAXSRC;
   p->part_floats = tc_tier ? (i64)160 * (p->defer_dA ? 512 * 128 : 256 * 64) : 0;
   p->o_part = take(p->part_floats);
@@ -721,7 +721,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
   float* cur = sc + p->o_buf0;   // holds d(loss)/d(x_{i+1}) on entry of layer i (unused for the last layer)
   float* oth = sc + p->o_buf1;
   float* dg = sc + p->o_dg;
-  TcScratch tsc{p->part_floats > 0 ? sc + p->o_part : nullptr, p->part_floats};
+  TcScratch tsc{p->part_floats > 0 ? sc + p->o_part : nullptr, p->part_floats, x3(p) ? 1 : 0};
   const float* dA_X[TR_MAXSRC];
   const float* dA_T[TR_MAXSRC];
   int dA_slabs[TR_MAXSRC], dA_pairs = 0;
@@ -869,11 +869,11 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     }
     bool wgrad_done = false;
     ProfScope prof_w("gated_tcn_wgrad", st, 4.0 * ((double)Pin * C + (double)Pi * 2 * D), 2.0 * Pi * 2 * D * (2.0 * C + 1));
-    if (tcpos_ok(p) && !x3(p) && tsc.partial) {   // tcgen05 + TMA reduction over all positions; the slot reduction folds the
+    if (tcpos_ok(p) && tsc.partial) {   // tcgen05 + TMA reduction over all positions; the slot reduction folds the
 #if !GWN_EMU                            // BatchNorm affine of the layer below and scatters to the four gradients
       TcRedArgs t;
       memset(&t, 0, sizeof(t));
-      t.mode = 0; t.na = 2;
+      t.mode = 0; t.na = 2; t.x3 = tsc.x3;
       t.a[0] = TcRedSrc{prev, p->Lin(i) * N, 32, 0, 0, 0};
       t.a[1] = TcRedSrc{prev, p->Lin(i) * N, 32, 0, p->dil[i] * N, 0};
       t.b[0] = TcRedSrc{dpre, p->L[i] * N, 2 * D, 0, 0, 0};

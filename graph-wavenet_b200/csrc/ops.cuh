@@ -96,6 +96,7 @@ inline int node_gemm(const SupportView* sup, int nsup, bool kcat, const float* c
 struct TcScratch {
   float* partial;
   i64 floats;
+  int x3;   // 1: fp32x3 tier (3xTF32 split inside the reduction)
 };
 
 // tcgen05 support gradient over any number of (X, T) pairs with their own slab counts (all layers of a backward pass
@@ -109,7 +110,7 @@ inline int support_grad_tc(const float* const* Xp, const float* const* Yp, const
   if (C != 32 || npairs < 1 || npairs > TR_MAXSRC || !ts.partial || ldda > 2147483647LL) return -1;
   TcRedArgs t;
   memset(&t, 0, sizeof(t));
-  t.mode = 1; t.na = npairs;
+  t.mode = 1; t.na = npairs; t.x3 = ts.x3;
   for (int i = 0; i < npairs; ++i) {
     t.a[i] = TcRedSrc{Xp[i], V, 32, 0, 0, slabs[i]};
     t.b[i] = TcRedSrc{Yp[i], V, 32, 0, 0, slabs[i]};
@@ -127,7 +128,7 @@ inline int support_grad_tc(const float* const* Xp, const float* const* Yp, const
 inline int support_grad_gemm(const float* const* Xp, const float* const* Yp, int npairs, float* dA, i64 ldda, int B, int L,
                              int V, int C, cudaStream_t stream, const TcScratch* ts = nullptr) {
   GWN_CHECK_ARG(npairs >= 1 && npairs <= MAXSUP, "support_grad: bad pair count %d", npairs);
-  if (current_math() == 1 && ts) {   // tf32 tier: tcgen05 + TMA
+  if (current_math() != 0 && ts) {   // tensor-core tiers: tcgen05 + TMA
     int slabs[MAXSUP];
     for (int i = 0; i < npairs; ++i) slabs[i] = B * L;
     int st = support_grad_tc(Xp, Yp, slabs, npairs, dA, ldda, V, C, *ts, stream);
@@ -272,12 +273,12 @@ inline int mlp_backward(const MlpBwdArgs& m, cudaStream_t stream) {
   }
   ProfScope prof_w("gcn_mlp_wgrad", stream, m.dW ? 4.0 * m.P * ((double)Ktot + m.C_out) : 0.0,
                    m.dW ? 2.0 * m.P * (Ktot + 1.0) * m.C_out : 0.0);
-  if (m.dW && current_math() == 1 && m.D == 32 && m.C_out == 32 && m.nseg <= 7 && m.drop.mode == GWN_DROPOUT_NONE &&
+  if (m.dW && current_math() != 0 && m.D == 32 && m.C_out == 32 && m.nseg <= 7 && m.drop.mode == GWN_DROPOUT_NONE &&
       m.P < 2147483647LL && m.ts.partial) {   // tf32 tier: tcgen05 + TMA reduction (weights and, through the all-ones block, the bias)
 #if !GWN_EMU
     TcRedArgs t;
     memset(&t, 0, sizeof(t));
-    t.mode = 0; t.na = m.nseg;
+    t.mode = 0; t.na = m.nseg; t.x3 = m.ts.x3;
     for (int q = 0; q < m.nseg; ++q) t.a[q] = TcRedSrc{m.segs[q], (int)m.P, 32, 0, 0, 0};
     t.b[0] = TcRedSrc{m.dh, (int)m.P, 32, 0, 0, 0};
     t.N = 32; t.nb = 1; t.rows = (int)m.P; t.partial = m.ts.partial; t.partial_floats = m.ts.floats;

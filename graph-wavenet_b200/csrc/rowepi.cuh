@@ -3,6 +3,7 @@
 //     static constexpr int kAccPerBlock;                   // accumulator columns that make one 32-wide output block
 //     void init();
 //     static constexpr int kAddends;                       // addend tiles TMA stages per row tile (0..2)
+//     static constexpr int kGroups;                        // epilogue groups of 4 warps (2 unless registers forbid)
 //     void load_addends(const AddendRows& a, bool valid);  // copy the row's addends from the staged tiles to registers
 //     void consume16(i64 m, int c0, const float (&v)[16], RowSink& out);   // accumulator columns c0..c0+15 of row m
 //     void finish_rows(float* red, int etid);              // if kHasFinish: block-level reduce of column statistics
@@ -30,10 +31,11 @@ __device__ __forceinline__ void ld_row32(float (&r)[32], const float* p) {
 struct AddendRows {
   const uint8_t* row[2];   // tile + r * 128
   uint32_t x;              // r & 7
-  __device__ __forceinline__ void load(int which, float (&r)[32]) const {
+  template <int NF>   // NF floats (multiple of 4) starting at column col (multiple of 4)
+  __device__ __forceinline__ void load(int which, int col, float (&r)[NF]) const {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 f = *reinterpret_cast<const float4*>(row[which] + (((uint32_t)q ^ x) << 4));
+    for (int q = 0; q < NF / 4; ++q) {
+      const float4 f = *reinterpret_cast<const float4*>(row[which] + ((((uint32_t)col >> 2) + q) ^ x) * 16);
       r[4 * q] = f.x; r[4 * q + 1] = f.y; r[4 * q + 2] = f.z; r[4 * q + 3] = f.w;
     }
   }
@@ -59,9 +61,9 @@ struct RowStats32 {
 #pragma unroll
     for (int i = 0; i < 32; ++i) s1[i] = s2[i] = 0.0f;
   }
-  __device__ __forceinline__ void reduce(float* smem, int etid, double* g1, double* g2, int ncols) {
+  __device__ __forceinline__ void reduce(float* smem, int etid, double* g1, double* g2, int ncols, int barid) {
     if (etid < 64) smem[etid] = 0.0f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
 #pragma unroll
     for (int col = 0; col < 32; ++col) {
       float a = s1[col], b = s2[col];
@@ -75,7 +77,7 @@ struct RowStats32 {
         atomicAdd(smem + 32 + col, b);
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
     if (etid < 32 && etid < ncols) {
       atomicAdd(g1 + etid, (double)smem[etid]);
       atomicAdd(g2 + etid, (double)smem[32 + etid]);
@@ -94,6 +96,7 @@ struct RowGate {
   static constexpr bool kHasFinish = false;
   static constexpr int kAccPerBlock = 64;
   static constexpr int kAddends = 0;
+  static constexpr int kGroups = 2;
   float* y;          // [P, 32] (written through the kernel's output tensor map)
   const float* bf;
   const float* bg;
@@ -107,7 +110,7 @@ struct RowGate {
     out.put4(ch0, o[0], o[1], o[2], o[3]);
     out.put4(ch0 + 4, o[4], o[5], o[6], o[7]);
   }
-  __device__ __forceinline__ void finish_rows(float*, int) {}
+  __device__ __forceinline__ void finish_rows(float*, int, int) {}
 };
 
 // Gate backward from recomputed pre-activations: dpre[m][2ch+{0,1}] (interleaved, 64 wide).
@@ -115,6 +118,7 @@ struct RowGateBwd {
   static constexpr bool kHasFinish = false;
   static constexpr int kAccPerBlock = 32;
   static constexpr int kAddends = 1;   // dg rows
+  static constexpr int kGroups = 2;
   float* dpre;       // [P, 64]
   const float* dg;   // [P, 32] (addend tile 0)
   const float* bf;
@@ -122,7 +126,7 @@ struct RowGateBwd {
   float g[32];
   __device__ __forceinline__ void init() {}
   __device__ __forceinline__ void load_addends(const AddendRows& a, bool valid) {
-    if (valid) a.load(0, g);
+    if (valid) a.load<32>(0, 0, g);
   }
   __device__ __forceinline__ void consume16(i64, int c0, const float (&v)[16], const RowSink& out) {
     const int ch0 = c0 >> 1;
@@ -136,7 +140,7 @@ struct RowGateBwd {
     }
     out.put16(c0 & 31, o);
   }
-  __device__ __forceinline__ void finish_rows(float*, int) {}
+  __device__ __forceinline__ void finish_rows(float*, int, int) {}
 };
 
 // gcn tail + residual + BatchNorm statistics (model.py:53-54, 234-236), N = 32.
@@ -144,6 +148,7 @@ struct RowMlp {
   static constexpr bool kHasFinish = true;
   static constexpr int kAccPerBlock = 32;
   static constexpr int kAddends = 1;   // residual rows (tile 0; staged only when res != nullptr)
+  static constexpr int kGroups = 2;
   float* y;            // [P, 32]
   const float* bias;
   DropoutSrc drop;
@@ -155,18 +160,18 @@ struct RowMlp {
   RowStats32 cs;
   __device__ __forceinline__ void init() { cs.reset(); }
   __device__ __forceinline__ void load_addends(const AddendRows& a, bool valid) {
-    if (res && valid) a.load(0, rrow);
+    if (res && valid) a.load<32>(0, 0, rrow);
   }
   __device__ __forceinline__ void consume16(i64 m, int c0, const float (&v)[16], const RowSink& out) {
     float o[16];
     const i64 e = m * 32 + c0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float kp[4];
-      drop.keep4(e + 4 * q, kp);
+    for (int q = 0; q < 2; ++q) {
+      float kp[8];
+      drop.keep8(e + 8 * q, kp);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = 4 * q + i;
+      for (int i = 0; i < 8; ++i) {
+        const int c = 8 * q + i;
         float r = (v[c] + __ldg(bias + c0 + c)) * kp[i];
         if (res) {
           float x = rrow[c0 + c];
@@ -182,8 +187,8 @@ struct RowMlp {
       for (int c = 0; c < 16; ++c) { cs.s1[c0 + c] += o[c]; cs.s2[c0 + c] += o[c] * o[c]; }
     }
   }
-  __device__ __forceinline__ void finish_rows(float* red, int etid) {
-    if (stats) cs.reduce(red, etid, stats, stats + 32, 32);
+  __device__ __forceinline__ void finish_rows(float* red, int etid, int barid) {
+    if (stats) cs.reduce(red, etid, stats, stats + 32, 32, barid);
   }
 };
 
@@ -192,12 +197,13 @@ struct RowSeg {
   static constexpr bool kHasFinish = false;
   static constexpr int kAccPerBlock = 32;
   static constexpr int kAddends = 0;
+  static constexpr int kGroups = 2;
   float* out;
   i64 M;
   __device__ __forceinline__ void init() {}
   __device__ __forceinline__ void load_addends(const AddendRows&, bool) {}
   __device__ __forceinline__ void consume16(i64, int c0, const float (&v)[16], const RowSink& o) { o.put16(c0 & 31, v); }
-  __device__ __forceinline__ void finish_rows(float*, int) {}
+  __device__ __forceinline__ void finish_rows(float*, int, int) {}
 };
 
 // Gated-conv input gradient + residual path + BatchNorm-backward statistics of the layer below, N = 32.
@@ -205,6 +211,7 @@ struct RowTcnDgrad {
   static constexpr bool kHasFinish = true;
   static constexpr int kAccPerBlock = 32;
   static constexpr int kAddends = 2;
+  static constexpr int kGroups = 1;    // 64 addend + 64 statistics registers per thread: one group of 128 threads only
   float* dx;           // [P_in, 32]
   const float* du;     // nullable [P_out, 32]
   int N, L_in, L_out;
@@ -218,8 +225,8 @@ struct RowTcnDgrad {
   // out-of-bounds fill); tile 1: the layer-below pre-BN rows (only staged when uprev != nullptr)
   __device__ __forceinline__ void load_addends(const AddendRows& a, bool valid) {
     if (!valid) return;
-    if (du) a.load(0, durow);
-    if (uprev) a.load(1, urow);
+    if (du) a.load<32>(0, 0, durow);
+    if (uprev) a.load<32>(1, 0, urow);
   }
   __device__ __forceinline__ void consume16(i64, int c0, const float (&v)[16], const RowSink& out) {
     float o[16];
@@ -235,8 +242,8 @@ struct RowTcnDgrad {
       }
     }
   }
-  __device__ __forceinline__ void finish_rows(float* red, int etid) {
-    if (uprev) cs.reduce(red, etid, bsum, bsum + 32, 32);
+  __device__ __forceinline__ void finish_rows(float* red, int etid, int barid) {
+    if (uprev) cs.reduce(red, etid, bsum, bsum + 32, 32, barid);
   }
 };
 #else

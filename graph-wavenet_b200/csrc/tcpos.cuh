@@ -75,7 +75,7 @@ struct TpParams {
 // tile TMA just landed: the element-wise split preserves the swizzled layout.  kind::tf32 ignores the low 13
 // mantissa bits of its operands (probed: tests/tools/tf32_rounding_probe.py), so the fp32 A tile itself serves as A_hi.
 template <class EP, int NCT, bool X3>   // NCT > 0: compile-time column count (keeps per-slot epilogue state in registers)
-__global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ TpMaps maps, const TpParams p, const EP ep_in) {
+__global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const __grid_constant__ TpMaps maps, const TpParams p, const EP ep_in) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -85,13 +85,14 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
   const int w_plane = p.nseg * p.N * 128;                 // resident weights: [plane][seg][N rows][128 B]
   const int w_bytes = NPL * w_plane;
   const uint32_t a0 = base + w_bytes;                     // A stages: [A | A_lo]
-  const uint32_t so0 = a0 + p.stages * STG;               // output staging ring: 2 x [128 rows][128 B], SWIZZLE_128B
+  constexpr int NSO = (EP::kGroups == 1) ? 2 : 2 * ((NCT > 0 && NCT / EP::kAccPerBlock == 1) ? 1 : 2);   // output staging tiles
+  const uint32_t so0 = a0 + p.stages * STG;               // [128 rows][128 B] each, SWIZZLE_128B
   uint8_t* so_ptr = smem + w_bytes + (size_t)p.stages * STG;
-  constexpr int NADD = EP::kAddends;                      // addend ring: 2 x NADD tiles
-  const uint32_t ad0 = so0 + 2 * TP_A_BYTES;
-  const uint8_t* ad_ptr = so_ptr + 2 * TP_A_BYTES;
+  constexpr int NADD = EP::kAddends;                      // addend tiles: 2 buffers (tile parity) x NADD
+  const uint32_t ad0 = so0 + NSO * TP_A_BYTES;
+  const uint8_t* ad_ptr = so_ptr + NSO * TP_A_BYTES;
   const uint32_t bar0 = ad0 + 2 * NADD * TP_A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(so_ptr + (2 + 2 * NADD) * TP_A_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(so_ptr + (NSO + 2 * NADD) * TP_A_BYTES);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
   auto split_bar = [&](int s) { return bar0 + 8u * (2 * p.stages + s); };
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
   auto efull_bar = [&](int e) { return bar0 + 8u * (3 * p.stages + 5 + e); };
   auto eempty_bar = [&](int e) { return bar0 + 8u * (3 * p.stages + 7 + e); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 9);
-  float* red = reinterpret_cast<float*>(bars + 3 * p.stages + 10);   // 64 floats for the statistics reduce
+  float* red = reinterpret_cast<float*>(bars + 3 * p.stages + 10);   // 2 x 64 floats for the statistics reduces
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -226,42 +227,54 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
       }
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue: one position row per thread
+    // ===================================================== epilogue: two groups of 4 warps, one position row per thread.
+    // Group g owns accumulator buffer g, i.e. every other tile of this CTA, so two tiles' epilogues run concurrently:
+    // with a single group the kernels were bound by the latency of ONE warp's instruction stream per scheduler
+    // (ncu r01d: RowMlp ~1100 dependent instructions per tile at ~8 cycles each = 4.5 us per tile vs 2.9 us of HBM time).
     EP ep = ep_in;
     ep.init();
-    const int ew = warp - 4;
-    int acc = 0;
-    uint32_t accphase = 0, ring = 0, ephase = 0;
-    int eb = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    constexpr int NG = EP::kGroups;
+    const int grp = (warp - 4) >> 2, ew = warp & 3;
+    const int barid = 1 + grp;
+    const bool elected = (threadIdx.x & 127) == 0;
+    constexpr int APB = EP::kAccPerBlock;
+    constexpr int RING = (NG == 1 || (NCT > 0 && NCT / APB == 1)) ? (NG == 1 ? 2 : 1) : 2;      // staging tiles per group
+    uint8_t* so_grp = so_ptr + grp * RING * TP_A_BYTES;
+    const uint32_t so_grp32 = so0 + grp * RING * TP_A_BYTES;
+    const int r = ew * 32 + lane;
+    uint32_t ring = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      if (NG == 2 && (it & 1) != grp) continue;
+      const int buf = it & 1;                               // accumulator / addend buffer of this tile
+      const uint32_t bphase = (uint32_t)(it >> 1) & 1u;     // ... and how often it has been used: its barrier parity
       const int b = tile / p.tiles_per_sample, rt = tile - b * p.tiles_per_sample;
-      const int rl = rt * 128 + ew * 32 + lane;
+      const int rl = rt * 128 + r;
       const bool valid = rl < p.rows_out;
       const i64 m = (i64)b * p.rows_out + rl;
-      if (NADD > 0 && p.nadd > 0) {        // this row's addends: staged tile -> registers, then hand the buffer back
-        if (!mbar_wait(efull_bar(eb), ephase, 19)) break;
-        const int r0 = ew * 32 + lane;
+      const bool has_add = NADD > 0 && p.nadd > 0;
+      if (has_add) {        // this row's addends: staged tile -> registers, then hand the buffer back to the producer
+        if (!mbar_wait(efull_bar(buf), bphase, 19)) break;
         AddendRows ar;
-        ar.row[0] = ad_ptr + (size_t)(eb * NADD) * TP_A_BYTES + r0 * 128;
-        ar.row[1] = ad_ptr + (size_t)(eb * NADD + (NADD > 1 ? 1 : 0)) * TP_A_BYTES + r0 * 128;
-        ar.x = (uint32_t)(r0 & 7);
+        ar.row[0] = ad_ptr + (size_t)(buf * NADD) * TP_A_BYTES + r * 128;
+        ar.row[1] = ad_ptr + (size_t)(buf * NADD + (NADD > 1 ? 1 : 0)) * TP_A_BYTES + r * 128;
+        ar.x = (uint32_t)(r & 7);
         ep.load_addends(ar, valid);
-        mbar_arrive(eempty_bar(eb));
-        eb ^= 1;
-        if (eb == 0) ephase ^= 1u;
+        mbar_arrive(eempty_bar(buf));
       }
-      if (!mbar_wait(tfull_bar(acc), accphase, 15)) break;
+      if (!mbar_wait(tfull_bar(buf), bphase, 15)) break;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * 256);
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(buf * 256);
       const int ncols = NCT > 0 ? NCT : p.N;
-      constexpr int APB = EP::kAccPerBlock;
-      const int r = ew * 32 + lane;
       auto do_block = [&](const int blk) {
-        // ring of two staging tiles: the TMA store that read this one two blocks ago must have finished reading
-        if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        uint8_t* sbuf = so_ptr + (ring & 1u) * TP_A_BYTES;
-        const RowSink sink{sbuf + r * 128, (uint32_t)(r & 7)};
+        // staging ring: the TMA store that last read this tile must have finished reading it
+        if (elected) {
+          if (RING == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
+        const uint32_t slot = RING == 2 ? (ring & 1u) : 0u;
+        const RowSink sink{so_grp + slot * TP_A_BYTES + r * 128, (uint32_t)(r & 7)};
 #pragma unroll
         for (int cc = 0; cc < APB; cc += 16) {
           const int c0 = blk * APB + cc;
@@ -276,16 +289,16 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the TMA engine
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 128) {
+        asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
+        if (elected) {
           const int c0o = p.out_blk_dim2 ? 0 : 32 * blk, c2o = p.out_blk_dim2 ? blk : b;
           asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&maps.out),
-                       "r"(so0 + (ring & 1u) * TP_A_BYTES), "r"(c0o), "r"(rt * 128), "r"(c2o)
+                       "r"(so_grp32 + slot * TP_A_BYTES), "r"(c0o), "r"(rt * 128), "r"(c2o)
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         ++ring;
-            };
+      };
       if constexpr (NCT > 0) {   // compile-time block count: the epilogue's per-column register arrays stay in registers
 #pragma unroll
         for (int blk = 0; blk < NCT / APB; ++blk) do_block(blk);
@@ -294,14 +307,12 @@ __global__ void __launch_bounds__(256, 1) tcpos_kernel(const __grid_constant__ T
         for (int blk = 0; blk * APB < ncols; ++blk) do_block(blk);
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
-      acc ^= 1;
-      if (acc == 0) accphase ^= 1u;
+      mbar_arrive(tempty_bar(buf));
     }
-    if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output tiles have landed
+    if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output tiles have landed
     if constexpr (EP::kHasFinish) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      ep.finish_rows(red, threadIdx.x - 128);
+      asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
+      ep.finish_rows(red + 64 * grp, threadIdx.x & 127, barid);
     }
   }
 
@@ -337,7 +348,8 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
   p.total_tiles = (int)tiles;
   const int w_bytes = (X3 ? 2 : 1) * a.nseg * a.N * 128;
   constexpr int STG = (X3 ? 2 : 1) * TP_A_BYTES;
-  constexpr int FIXED = (2 + 2 * EP::kAddends) * TP_A_BYTES;   // output staging ring + addend ring
+  constexpr int NSO = (EP::kGroups == 1) ? 2 : 2 * ((NCT > 0 && NCT / EP::kAccPerBlock == 1) ? 1 : 2);
+  constexpr int FIXED = (NSO + 2 * EP::kAddends) * TP_A_BYTES;   // output staging tiles + addend tiles
   p.stages = (SMEM_LIMIT - 2048 - w_bytes - FIXED) / STG;
   for (int k = 0; k < 2; ++k) {
     const TcPosSeg& g = a.addend[k];
@@ -389,7 +401,7 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
   }
   for (int k = 0; k < 2; ++k)
     if (!p.add_on[k]) maps.add[k] = maps.out;
-  const int smem_bytes = w_bytes + p.stages * STG + FIXED + 1024 + 512;
+  const int smem_bytes = w_bytes + p.stages * STG + FIXED + 1024 + 1024;
   static cudaError_t attr = cudaFuncSetAttribute(tcpos_kernel<EP, NCT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   if (attr != cudaSuccess) {
     set_error("tcpos: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr));
@@ -402,7 +414,7 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
     return n;
   }();
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  tcpos_kernel<EP, NCT, X3><<<grid, 256, smem_bytes, stream>>>(maps, p, ep);
+  tcpos_kernel<EP, NCT, X3><<<grid, 128 + 128 * EP::kGroups, smem_bytes, stream>>>(maps, p, ep);
   GWN_LAUNCH_CHECK();
   count_launch();
   return 0;

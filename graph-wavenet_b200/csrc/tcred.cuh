@@ -26,6 +26,7 @@ struct TcRedSrc {
 };
 struct TcRedArgs {
   int mode;           // 0 = MODE_MN, 1 = MODE_K
+  int x3;             // 1 = 3xTF32 (fp32-grade) mode
   TcRedSrc a[TR_MAXSRC];
   int na;             // MODE_MN: real A blocks (<= 7; the ones block is appended); MODE_K: number of (X, T) pairs
   TcRedSrc b[TR_MAXSRC];   // MODE_MN: b[0] only; MODE_K: one per pair
@@ -57,19 +58,24 @@ struct TrParams {
   i64 slot_floats;
 };
 
+// X3 = 3xTF32 mode (fp32-grade): both operands are activations, so warps 2 and 3 split BOTH tiles of a stage into
+// their remainders (stage layout [A | B | A_lo | B_lo]) and the issuer runs A.B + A.B_lo + A_lo.B (see tcpos.cuh).
+template <bool X3>
 __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ TrMaps maps, const TrParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const int stage_bytes = p.a_bytes + p.b_bytes;
+  const int plane_bytes = p.a_bytes + p.b_bytes;
+  const int stage_bytes = (X3 ? 2 : 1) * plane_bytes;
   const uint32_t st0 = base;
   const uint32_t bar0 = st0 + p.stages * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
-  const uint32_t done_bar = bar0 + 8u * (2 * p.stages);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+  auto split_bar = [&](int s) { return bar0 + 8u * (2 * p.stages + s); };
+  const uint32_t done_bar = bar0 + 8u * (3 * p.stages);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.mode == 0) {
@@ -79,6 +85,10 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       float* blk = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + (size_t)p.na * 4096);
       const int nfill = (p.mtiles * 4 - p.na) * 1024;
       for (int i = threadIdx.x; i < nfill; i += 256) blk[i] = i < 1024 ? 1.0f : 0.0f;
+      if (X3) {   // their remainders are zero
+        float* lo = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + plane_bytes + (size_t)p.na * 4096);
+        for (int i = threadIdx.x; i < nfill; i += 256) lo[i] = 0.0f;
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
   }
@@ -90,6 +100,7 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
+      mbar_init(split_bar(s), 64);
     }
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -138,6 +149,7 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     bool first = true;
     for (int c = c_beg; c < c_end; ++c) {
       if (!mbar_wait(full_bar(stage), phase, 22)) break;
+      if (X3 && !mbar_wait(split_bar(stage), phase, 24)) break;
       tc_fence_after();
       const uint32_t sa = st0 + stage * stage_bytes, sb = sa + p.a_bytes;
 #pragma unroll 1
@@ -155,6 +167,11 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
             bdesc = make_desc(sb + kk * 32, 16, 1024, 2);
           }
           tc_mma_tf32(d_tmem, adesc, bdesc, idesc, (!first || kk > 0) ? 1u : 0u);
+          if (X3) {   // the remainder planes sit plane_bytes further, same layout
+            const uint64_t off = (uint64_t)((uint32_t)plane_bytes >> 4);
+            tc_mma_tf32(d_tmem, adesc, bdesc + off, idesc, 1u);
+            tc_mma_tf32(d_tmem, adesc + off, bdesc, idesc, 1u);
+          }
         }
       }
       first = false;
@@ -162,6 +179,33 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
     tc_commit(done_bar);
+  } else if (X3 && (warp == 2 || warp == 3)) {
+    // ===================================================== splitter: remainders of the TMA-written A blocks and of B
+    const int t64 = threadIdx.x - 64;
+    int stage = 0;
+    uint32_t phase = 0;
+    const int a_live = (p.mode == 0 ? p.na * 4096 : p.a_bytes) / 16, b_live = p.b_bytes / 16;
+    for (int c = c_beg; c < c_end; ++c) {
+      if (!mbar_wait(full_bar(stage), phase, 25)) break;
+      uint8_t* sp = smem + (size_t)stage * stage_bytes;
+      const float4* a_src = reinterpret_cast<const float4*>(sp);
+      float4* a_dst = reinterpret_cast<float4*>(sp + plane_bytes);
+#pragma unroll 4
+      for (int i = t64; i < a_live; i += 64) {
+        const float4 v = a_src[i];
+        a_dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+      }
+      const float4* b_src = reinterpret_cast<const float4*>(sp + p.a_bytes);
+      float4* b_dst = reinterpret_cast<float4*>(sp + plane_bytes + p.a_bytes);
+#pragma unroll 4
+      for (int i = t64; i < b_live; i += 64) {
+        const float4 v = b_src[i];
+        b_dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(split_bar(stage));
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+    }
   } else if (warp >= 4) {
     // ===================================================== epilogue: this CTA's partial result -> its private slot
     // (plain 128-bit stores; a small follow-up kernel sums the slots -- float atomics from 148 CTAs onto the same
@@ -353,8 +397,17 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
     if (p.mtiles > 4) return -1;              // V <= 512
     int ntile = (512 / p.mtiles) / 16 * 16;
     if (ntile > 256) ntile = 256;
+    if (a.x3) {   // two stages of [A | B | A_lo | B_lo] must fit shared memory
+      const int cap = (((SMEM_LIMIT - 2048) / 4 - p.mtiles * 16384) / 128) / 16 * 16;
+      if (cap < 16) return -1;
+      if (ntile > cap) ntile = cap;
+    }
     const int need = round_up(a.rows, 16);
     if (ntile > need) ntile = need;
+    {   // balance the column tiles
+      const int nt = (a.rows + ntile - 1) / ntile;
+      ntile = round_up((a.rows + nt - 1) / nt, 16);
+    }
     p.N = ntile;
     p.n_nt = (a.rows + ntile - 1) / ntile;
     p.a_bytes = p.mtiles * 16384;
@@ -380,7 +433,7 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
     for (int j = a.na; j < TR_MAXSRC; ++j) { p.pair_end[j] = (int)tot; maps.a[j] = maps.a[0]; maps.b[j] = maps.b[0]; }
     p.total_chunks = (int)tot;
   }
-  const int stage_bytes = p.a_bytes + p.b_bytes;
+  const int stage_bytes = (a.x3 ? 2 : 1) * (p.a_bytes + p.b_bytes);
   p.stages = (SMEM_LIMIT - 2048) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) return -1;
@@ -393,12 +446,14 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
   if ((i64)grid * p.slot_floats > a.partial_floats) return -1;
   p.partial = a.partial;
   const int smem_bytes = p.stages * stage_bytes + 1024 + 256;
-  static cudaError_t attr = cudaFuncSetAttribute(tcred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-  if (attr != cudaSuccess) {
-    set_error("tcred: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr));
+  static cudaError_t attr = cudaFuncSetAttribute(tcred_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  static cudaError_t attr3 = cudaFuncSetAttribute(tcred_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  if (attr != cudaSuccess || attr3 != cudaSuccess) {
+    set_error("tcred: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr != cudaSuccess ? attr : attr3));
     return GWN_ERR_CUDA;
   }
-  tcred_kernel<<<grid, 256, smem_bytes, stream>>>(maps, p);
+  if (a.x3) tcred_kernel<true><<<grid, 256, smem_bytes, stream>>>(maps, p);
+  else tcred_kernel<false><<<grid, 256, smem_bytes, stream>>>(maps, p);
   GWN_LAUNCH_CHECK();
   count_launch();
   res->nslots = grid; res->mtiles = p.mtiles; res->N = p.N; res->n_nt = p.n_nt; res->slot_floats = p.slot_floats;
