@@ -740,9 +740,19 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
       const bool use_dh = ldrop.mode != GWN_DROPOUT_NONE;   // materialise du * keep once instead of regenerating masks
       {
       ProfScope prof("bn_bwd_apply", st, 4.0 * Pi * C * (use_dh ? 4.0 : 3.0), 0.0);
-      GWN_LAUNCH_1D(bn_bwd_apply_kernel, Pi * C / 4, st, cur, ws + p->o_u[i], ws + p->o_ac[i], ws + p->o_mr[i],
+#if !GWN_EMU
+      if (C >= 8 && C <= 2048 && (C & (C - 1)) == 0 && (Pi * C) % 8 == 0) {
+        GWN_LAUNCH_1D(bn_bwd_apply8_kernel, Pi * C / 8, st, cur, ws + p->o_u[i], ws + p->o_ac[i], ws + p->o_mr[i],
+                    reinterpret_cast<const double*>(sc + p->o_bsum + (i64)i * 4 * C), (double)Pi, training,
+                    G(p->li[i].bnw), G(p->li[i].bnb), Pi * C / 8, C, use_dh ? sc + p->o_dh : (float*)nullptr, ldrop);
+      } else
+#endif
+      {
+        GWN_LAUNCH_1D(bn_bwd_apply_kernel, Pi * C / 4, st, cur, ws + p->o_u[i], ws + p->o_ac[i], ws + p->o_mr[i],
                     reinterpret_cast<const double*>(sc + p->o_bsum + (i64)i * 4 * C), (double)Pi, training,
                     G(p->li[i].bnw), G(p->li[i].bnb), Pi, C, use_dh ? sc + p->o_dh : (float*)nullptr, ldrop);
+      }
+
       }
       const float* segs[MAXSEG];
       for (int q = 0; q < p->nseg; ++q) segs[q] = g + (i64)q * Pi * D;

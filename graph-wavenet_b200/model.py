@@ -38,7 +38,14 @@ _PRECISIONS = {"fp32": _N.PREC_FP32, "tf32": _N.PREC_TF32, "fp32x3": _N.PREC_FP3
 
 
 def _default_precision() -> int:
-    return _PRECISIONS[os.environ.get("GWNET_B200_PRECISION", "fp32").lower()]
+    """Tier of the whole-network plan: ``fp32x3`` (default) = fp32-grade 3xTF32 on tcgen05 (1e-4 parity), ``tf32`` =
+    single-pass TF32 on tcgen05 (2e-2 tier), ``fp32`` = FMA reference tier."""
+    return _PRECISIONS[os.environ.get("GWNET_B200_PRECISION", "fp32x3").lower()]
+
+
+def _op_precision() -> int:
+    """The stand-alone operators (nconv / gcn / linear) run the fp32 FMA tier of the op-level C ABI."""
+    return _N.PREC_FP32
 
 
 def _require_cuda(t: torch.Tensor, what: str):
@@ -126,7 +133,7 @@ class nconv(nn.Module):
 
     def __init__(self):
         super(nconv, self).__init__()
-        self.precision = _default_precision()
+        self.precision = _op_precision()
 
     def forward(self, x, A):
         return _NconvFn.apply(x, A, self.precision)
@@ -245,7 +252,7 @@ class gcn(nn.Module):
         self.mlp = linear(c_in, c_out)
         self.dropout = dropout
         self.order = order
-        self.precision = _default_precision()
+        self.precision = _op_precision()
         self._keep_mask = None     # test hook: uint8 BLNC keep-mask replacing the Philox draw
 
     def forward(self, x, support):
