@@ -190,15 +190,28 @@ class FusedStep:
         self.graph = None
         self.use_graph = use_graph = bool(use_graph and dev.type == "cuda")
         self.key_ptrs = self._ptr_key()
+        self.graph_tail = None
+        # Under data parallelism the step is captured as TWO graphs with the gradient all-reduce launched between them
+        # by torch.distributed (NCCL's own stream-ordering, no host sync): capturing the collective itself depends on the
+        # NCCL watchdog tolerating stream capture.  GWNET_B200_NCCL_IN_GRAPH=1 captures it into a single graph instead.
+        self.split = trainer.world > 1 and os.environ.get("GWNET_B200_NCCL_IN_GRAPH", "0") != "1"
         if use_graph:
-            if trainer.world > 1:     # NCCL must have built its communicator before capture
+            if trainer.world > 1 and not self.split:     # NCCL must have built its communicator before capture
                 import torch.distributed as dist
                 dist.all_reduce(torch.zeros(1, device=dev))
             torch.cuda.synchronize(dev)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._enqueue()
-            self.graph = g
+            if self.split:
+                g, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue_fwd_bwd()
+                with torch.cuda.graph(g2):
+                    self._enqueue_tail()
+                self.graph, self.graph_tail = g, g2
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue()
+                self.graph = g
 
     def _ptr_key(self):
         return (self.table[0].data_ptr(), self.table[-1].data_ptr(), tuple(s.data_ptr() for s in self.sup),
@@ -235,18 +248,27 @@ class FusedStep:
         a.ctrl, a.metrics = opt.ctrl.data_ptr(), opt.metrics.data_ptr()
         return a
 
-    def _enqueue(self):
-        tr = self.trainer
+    def _enqueue_fwd_bwd(self):
         dev = self.x.device
         with _dev_ctx(dev):
-            stream = _stream(dev)
-            a = self._train_args(stream)
+            a = self._train_args(_stream(dev))
             self.lib.check(self.lib.dll.gwn_plan_train_fwd_bwd(self.plan.handle, C.byref(a)), "gwn_plan_train_fwd_bwd")
-            if tr.world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(self.flat.grad)          # ONE collective per step; 1/world is folded into Adam
+
+    def _allreduce(self):
+        import torch.distributed as dist
+        dist.all_reduce(self.flat.grad)          # ONE collective per step; 1/world is folded into Adam
+
+    def _enqueue_tail(self):
+        tr = self.trainer
+        with _dev_ctx(self.x.device):
             tr.optimizer.launch()
             self.metrics_host.copy_(tr.optimizer.metrics, non_blocking=True)
+
+    def _enqueue(self):
+        self._enqueue_fwd_bwd()
+        if self.trainer.world > 1:
+            self._allreduce()
+        self._enqueue_tail()
 
     def run(self, x: torch.Tensor, y: torch.Tensor):
         tr = self.trainer
@@ -256,7 +278,11 @@ class FusedStep:
         opt.sync_hyper()
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
-        if self.graph is not None:
+        if self.graph is not None and self.graph_tail is not None:
+            self.graph.replay()
+            self._allreduce()
+            self.graph_tail.replay()
+        elif self.graph is not None:
             self.graph.replay()
         else:
             self._enqueue()
