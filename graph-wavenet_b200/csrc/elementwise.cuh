@@ -388,6 +388,40 @@ GWN_GLOBAL transpose_kernel(const float* W, float* WT, int R, int Cc, float* WTl
     if (WTlo) WTlo[i] = tf32_lo(v);
   }
 }
+// Head weights for the tcgen05 position GEMMs (nL skip convs W_i [Sk][D], biases b_i [Sk]):
+//   Wcat[sk][i*D + c] = W_i[sk][c]      (skip sum over the live columns as ONE GEMM with K = nL*D)
+//   WT[(i*D + c)][sk] = W_i[sk][c]      (its input gradient)
+//   bsum[sk] = sum_i b_i[sk]
+struct SkipWeights {
+  const float* w[16];
+  const float* b[16];
+};
+GWN_GLOBAL pack_skip_kernel(SkipWeights sw, int nL, int D, int Sk, float* Wcat, float* Wcat_lo, float* WT, float* WT_lo,
+                            float* bsum) {
+  GWN_FOR_EACH(i, (i64)Sk * nL * D + Sk) {
+    if (i < (i64)Sk * nL * D) {
+      const int sk = (int)(i / (nL * D)), k = (int)(i - (i64)sk * nL * D);
+      const int l = k / D, c = k - l * D;
+      const float v = sw.w[l][(i64)sk * D + c];
+      if (Wcat) { Wcat[i] = v; if (Wcat_lo) Wcat_lo[i] = tf32_lo(v); }
+      if (WT) { WT[(i64)k * Sk + sk] = v; if (WT_lo) WT_lo[(i64)k * Sk + sk] = tf32_lo(v); }
+    } else if (bsum) {
+      const int sk = (int)(i - (i64)Sk * nL * D);
+      float acc = 0.0f;
+      for (int l = 0; l < nL; ++l) acc += sw.b[l][sk];
+      bsum[sk] = acc;
+    }
+  }
+}
+// W2T[e*ldo + o] = W2[o*E + e] (zero for o >= O): the last head layer transposed, rows padded to ldo floats
+GWN_GLOBAL pack_e2t_kernel(const float* W2, float* WT, float* WT_lo, int O, int E, int ldo) {
+  GWN_FOR_EACH(i, (i64)E * ldo) {
+    const int e = (int)(i / ldo), o = (int)(i - (i64)e * ldo);
+    const float v = o < O ? W2[(i64)o * E + e] : 0.0f;
+    WT[i] = v;
+    if (WT_lo) WT_lo[i] = tf32_lo(v);
+  }
+}
 // lo[i] = w[i] - tf32_trunc(w[i])
 GWN_GLOBAL split_lo_kernel(const float* w, float* lo, i64 n) {
   GWN_FOR_EACH(i, n) { lo[i] = tf32_lo(w[i]); }

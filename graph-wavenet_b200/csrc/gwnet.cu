@@ -125,6 +125,10 @@ struct gwn_plan {
   gwn::i64 grad_floats;
   // forward workspace offsets (floats)
   gwn::i64 o_sup, o_supT, o_sup_lo, sup_span, o_x0, o_skip, o_e1, fwd_floats;
+  // packed head weights for the tcgen05 position GEMMs (forward workspace / backward scratch)
+  gwn::i64 o_hk_wcat, o_hk_wcat_lo, o_hk_bsum, o_hk_e1lo, o_hk_e2lo;
+  gwn::i64 o_hb_wt, o_hb_wt_lo, o_hb_w1t, o_hb_w1t_lo, o_hb_w2t, o_hb_w2t_lo;
+  bool head_tc;
   std::vector<gwn::i64> o_g, o_u, o_ac, o_mr, o_sums, o_pack;
   gwn::i64 pk_wp, pk_bf, pk_bg, pk_wd, pk_wt;   // offsets inside a layer's pack region (tensor-core tiers)
   gwn::i64 pk_wp_lo, pk_wd_lo, pk_wt_lo, pk_wm_lo;   // 3xTF32 remainders of the packed weights (fp32x3 tier)
@@ -293,6 +297,18 @@ static int build_plan(gwn_plan* p) {
   }
   p->o_skip = take(p->PT() * Sk);
   p->o_e1 = take(p->PT() * E);
+  // head on tcgen05: default widths only (K segments of 32, column tiles of <= 256)
+  p->head_tc = (c.precision == GWN_PREC_TF32 || c.precision == GWN_PREC_FP32X3) && D == 32 && nL <= TP_MAXSEG &&
+               Sk % 32 == 0 && Sk <= 512 && (Sk <= 128 || Sk % 256 == 0) && E % 32 == 0 && E <= 512 &&
+               (E <= 128 || E % 256 == 0) && c.out_dim <= 16 && (nL * D <= 128 || (nL * D) % 256 == 0);
+  {
+    const bool hx3 = p->head_tc && c.precision == GWN_PREC_FP32X3;
+    p->o_hk_wcat = take(p->head_tc ? (i64)Sk * nL * D : 0);
+    p->o_hk_wcat_lo = take(hx3 ? (i64)Sk * nL * D : 0);
+    p->o_hk_bsum = take(p->head_tc ? Sk : 0);
+    p->o_hk_e1lo = take(hx3 ? (i64)E * Sk : 0);
+    p->o_hk_e2lo = take(hx3 ? (i64)c.out_dim * E : 0);
+  }
   p->fwd_floats = o;
 
   // ---- backward scratch
@@ -325,6 +341,15 @@ static int build_plan(gwn_plan* p) {
   p->o_dA = take(N * p->ld);
   p->o_dR = take(N * p->ld);
   p->o_bsum = take((i64)nL * 4 * C);          // per layer 2*C doubles
+  {
+    const bool hx3 = p->head_tc && c.precision == GWN_PREC_FP32X3;
+    p->o_hb_wt = take(p->head_tc ? (i64)Sk * nL * D : 0);
+    p->o_hb_wt_lo = take(hx3 ? (i64)Sk * nL * D : 0);
+    p->o_hb_w1t = take(p->head_tc ? (i64)E * Sk : 0);
+    p->o_hb_w1t_lo = take(hx3 ? (i64)E * Sk : 0);
+    p->o_hb_w2t = take(p->head_tc ? (i64)E * p->ldo : 0);
+    p->o_hb_w2t_lo = take(hx3 ? (i64)E * p->ldo : 0);
+  }
   p->bwd_floats = o;
   return 0;
 }
@@ -532,6 +557,63 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
   const i64 PT = p->PT();
   ProfScope prof_head("head_fwd", st, 4.0 * PT * ((double)nL * D + 2.0 * Sk + 2.0 * E + c.out_dim),
                       2.0 * PT * ((double)nL * D * Sk + (double)Sk * E + (double)E * c.out_dim));
+  bool head_done = false;
+#if !GWN_EMU
+  if (p->head_tc && PT < 2147483647LL) {   // the three head layers as tcgen05 position GEMMs with streamed weights
+    const bool h3 = x3(p);
+    const int TN = h3 ? 128 : 256;   // output columns per tile: two stages of [A | W blk] (x2 planes in 3xTF32 mode) must fit
+    SkipWeights sw;
+    memset(&sw, 0, sizeof(sw));
+    for (int i = 0; i < nL; ++i) { sw.w[i] = P_<float>(prm, p->li[i].sw); sw.b[i] = P_<float>(prm, p->li[i].sb); }
+    GWN_LAUNCH_1D(pack_skip_kernel, (i64)Sk * nL * D + Sk, st, sw, nL, D, Sk, ws + p->o_hk_wcat,
+                  h3 ? ws + p->o_hk_wcat_lo : (float*)nullptr, (float*)nullptr, (float*)nullptr, ws + p->o_hk_bsum);
+    int hs;
+    {  // skip = relu(sum_i W_i g_i[live columns] + sum_i b_i)
+      TcPosArgs t;
+      memset(&t, 0, sizeof(t));
+      for (int i = 0; i < nL; ++i) t.seg[i] = TcPosSeg{ws + p->o_g[i], p->L[i] * N, 32, 0, (p->L[i] - p->T_out) * N};
+      t.nseg = nL; t.nb = B; t.rows_out = p->T_out * N; t.Wp = ws + p->o_hk_wcat; t.Wp_lo = h3 ? ws + p->o_hk_wcat_lo : nullptr;
+      t.N = Sk <= TN ? Sk : TN; t.wstream = 1; t.N_total = Sk;
+      t.out = ws + p->o_skip; t.out_width = Sk; t.out_nblk = Sk / 32;
+      RowDense ep;
+      memset(&ep, 0, sizeof(ep));
+      ep.bias = ws + p->o_hk_bsum; ep.relu = 1;
+      hs = launch_tcpos<0>(t, ep, st);
+      if (hs > 0) return hs;
+    }
+    if (hs == 0) {  // e1 = relu(W1 skip + b1)
+      if (h3) GWN_LAUNCH_1D(split_lo_kernel, (i64)E * Sk, st, P_<float>(prm, p->i_e1w), ws + p->o_hk_e1lo, (i64)E * Sk);
+      TcPosArgs t;
+      memset(&t, 0, sizeof(t));
+      for (int q = 0; q < Sk / 32; ++q) t.seg[q] = TcPosSeg{ws + p->o_skip, (int)PT, Sk, 32 * q, 0};
+      t.nseg = Sk / 32; t.nb = 1; t.rows_out = (int)PT; t.Wp = P_<float>(prm, p->i_e1w); t.Wp_lo = h3 ? ws + p->o_hk_e1lo : nullptr;
+      t.N = E <= TN ? E : TN; t.wstream = 1; t.N_total = E;
+      t.out = ws + p->o_e1; t.out_width = E; t.out_nblk = E / 32;
+      RowDense ep;
+      memset(&ep, 0, sizeof(ep));
+      ep.bias = P_<float>(prm, p->i_e1b); ep.relu = 1;
+      hs = launch_tcpos<0>(t, ep, st);
+      if (hs > 0) return hs;
+      GWN_CHECK_ARG(hs == 0, "forward: head layer 2 not eligible for the tcgen05 path after layer 1 ran on it");
+    }
+    if (hs == 0) {  // out = W2 e1 + b2, written in the reference's NCHW layout
+      if (h3) GWN_LAUNCH_1D(split_lo_kernel, (i64)c.out_dim * E, st, P_<float>(prm, p->i_e2w), ws + p->o_hk_e2lo, (i64)c.out_dim * E);
+      TcPosArgs t;
+      memset(&t, 0, sizeof(t));
+      for (int q = 0; q < E / 32; ++q) t.seg[q] = TcPosSeg{ws + p->o_e1, (int)PT, E, 32 * q, 0};
+      t.nseg = E / 32; t.nb = 1; t.rows_out = (int)PT; t.Wp = P_<float>(prm, p->i_e2w); t.Wp_lo = h3 ? ws + p->o_hk_e2lo : nullptr;
+      t.N = 16; t.w_rows = c.out_dim;
+      RowNCHW ep;
+      memset(&ep, 0, sizeof(ep));
+      ep.y = a->output; ep.bias = P_<float>(prm, p->i_e2b); ep.O = c.out_dim; ep.N = N; ep.T = p->T_out;
+      hs = launch_tcpos<16>(t, ep, st);
+      if (hs > 0) return hs;
+      GWN_CHECK_ARG(hs == 0, "forward: head layer 3 not eligible for the tcgen05 path after layers 1-2 ran on it");
+      head_done = true;
+    }
+  }
+#endif
+  if (head_done) return 0;
   {
     LdRows la;
     memset(&la, 0, sizeof(la));
@@ -631,7 +713,66 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
   float* dskip = sc + p->o_dskip;
   float* dgh = sc + p->o_dgh;
   GWN_CHECK_ARG(PT < 2147483647LL, "backward: too many output positions");
-  {  // (a) de1 = (dout . W2) * (e1 > 0)
+  bool hb_tc = false;
+#if !GWN_EMU
+  if (p->head_tc) {   // the three input-gradient GEMMs of the head on tcgen05 (weight gradients below stay on the generic kernel)
+    const bool h3 = x3(p);
+    const int TN = h3 ? 128 : 256;
+    GWN_LAUNCH_1D(pack_e2t_kernel, (i64)E * p->ldo, st, P_<float>(prm, p->i_e2w), sc + p->o_hb_w2t,
+                  h3 ? sc + p->o_hb_w2t_lo : (float*)nullptr, O, E, p->ldo);
+    GWN_LAUNCH_1D(transpose_kernel, (i64)E * Sk, st, P_<float>(prm, p->i_e1w), sc + p->o_hb_w1t, E, Sk,
+                  h3 ? sc + p->o_hb_w1t_lo : (float*)nullptr);
+    SkipWeights sw;
+    memset(&sw, 0, sizeof(sw));
+    for (int i = 0; i < nL; ++i) { sw.w[i] = P_<float>(prm, p->li[i].sw); sw.b[i] = P_<float>(prm, p->li[i].sb); }
+    GWN_LAUNCH_1D(pack_skip_kernel, (i64)Sk * nL * D, st, sw, nL, D, Sk, (float*)nullptr, (float*)nullptr, sc + p->o_hb_wt,
+                  h3 ? sc + p->o_hb_wt_lo : (float*)nullptr, (float*)nullptr);
+    int hs;
+    {  // (a) de1 = (dout . W2) * (e1 > 0)
+      TcPosArgs t;
+      memset(&t, 0, sizeof(t));
+      t.seg[0] = TcPosSeg{dout, (int)PT, p->ldo, 0, 0};
+      t.nseg = 1; t.nb = 1; t.rows_out = (int)PT; t.Wp = sc + p->o_hb_w2t; t.Wp_lo = h3 ? sc + p->o_hb_w2t_lo : nullptr;
+      t.N = E <= TN ? E : TN; t.wstream = 1; t.N_total = E; t.w_k = p->ldo;
+      t.out = de1; t.out_width = E; t.out_nblk = E / 32;
+      RowDense ep;
+      memset(&ep, 0, sizeof(ep));
+      ep.gate = e1; ep.ldg = E;
+      hs = launch_tcpos<0>(t, ep, st);
+      if (hs > 0) return hs;
+    }
+    if (hs == 0) {  // (c) dskip = (de1 . W1) * (skip > 0)
+      TcPosArgs t;
+      memset(&t, 0, sizeof(t));
+      for (int q = 0; q < E / 32; ++q) t.seg[q] = TcPosSeg{de1, (int)PT, E, 32 * q, 0};
+      t.nseg = E / 32; t.nb = 1; t.rows_out = (int)PT; t.Wp = sc + p->o_hb_w1t; t.Wp_lo = h3 ? sc + p->o_hb_w1t_lo : nullptr;
+      t.N = Sk <= TN ? Sk : TN; t.wstream = 1; t.N_total = Sk;
+      t.out = dskip; t.out_width = Sk; t.out_nblk = Sk / 32;
+      RowDense ep;
+      memset(&ep, 0, sizeof(ep));
+      ep.gate = skip; ep.ldg = Sk;
+      hs = launch_tcpos<0>(t, ep, st);
+      if (hs > 0) return hs;
+      GWN_CHECK_ARG(hs == 0, "backward: head gradient (c) not eligible for the tcgen05 path");
+    }
+    if (hs == 0) {  // (f) gradient into the live columns of every g_i: dgh[i] = dskip . W_i
+      TcPosArgs t;
+      memset(&t, 0, sizeof(t));
+      for (int q = 0; q < Sk / 32; ++q) t.seg[q] = TcPosSeg{dskip, (int)PT, Sk, 32 * q, 0};
+      t.nseg = Sk / 32; t.nb = 1; t.rows_out = (int)PT; t.Wp = sc + p->o_hb_wt; t.Wp_lo = h3 ? sc + p->o_hb_wt_lo : nullptr;
+      t.N = nL * D <= TN ? nL * D : TN; t.wstream = 1; t.N_total = nL * D;
+      t.out = dgh; t.out_width = 32; t.out_nblk = nL * D / 32; t.out_blk_dim2 = 1;
+      RowSeg ep;
+      memset(&ep, 0, sizeof(ep));
+      ep.out = dgh; ep.M = PT;
+      hs = launch_tcpos<0>(t, ep, st);
+      if (hs > 0) return hs;
+      GWN_CHECK_ARG(hs == 0, "backward: head gradient (f) not eligible for the tcgen05 path");
+      hb_tc = true;
+    }
+  }
+#endif
+  if (!hb_tc) {  // (a) de1 = (dout . W2) * (e1 > 0)
     LdRows la;
     memset(&la, 0, sizeof(la));
     la.p[0] = dout; la.set_wd(p->ldo);
@@ -657,7 +798,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     GemmShape sh{(i64)O, E + 1, (int)PT, pick_ksplit(O, E + 1, PT, TW32::BM, TW32::BN, kTargetBlocks), 1};
     GWN_TRY((launch_gemm<TW32>(la, lb, ep, sh, st)));
   }
-  {  // (c) dskip = (de1 . W1) * (skip > 0)
+  if (!hb_tc) {  // (c) dskip = (de1 . W1) * (skip > 0)
     LdRows la;
     memset(&la, 0, sizeof(la));
     la.p[0] = de1; la.set_wd(E);
@@ -705,15 +846,17 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     GemmShape sh{(i64)Sk, nL * D + 1, (int)PT, pick_ksplit(Sk, nL * D + 1, PT, TBig::BM, TBig::BN, kTargetBlocks), 1};
     GWN_TRY((launch_gemm<TBig>(la, lb, ep, sh, st)));
 
-    LdRows lr;
-    memset(&lr, 0, sizeof(lr));
-    lr.p[0] = dskip; lr.set_wd(Sk);
-    lw.set_wd(D); lw.ldw = D;
-    EpRows es;
-    memset(&es, 0, sizeof(es));
-    es.y = dgh; es.M = PT; es.set_seg(D);
-    GemmShape sh2{PT, nL * D, Sk, 1, 1};
-    GWN_TRY((launch_gemm<TBig>(lr, lw, es, sh2, st)));
+    if (!hb_tc) {
+      LdRows lr;
+      memset(&lr, 0, sizeof(lr));
+      lr.p[0] = dskip; lr.set_wd(Sk);
+      lw.set_wd(D); lw.ldw = D;
+      EpRows es;
+      memset(&es, 0, sizeof(es));
+      es.y = dgh; es.M = PT; es.set_seg(D);
+      GemmShape sh2{PT, nL * D, Sk, 1, 1};
+      GWN_TRY((launch_gemm<TBig>(lr, lw, es, sh2, st)));
+    }
   }
 
   delete prof_hb;

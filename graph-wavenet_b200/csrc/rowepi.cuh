@@ -5,7 +5,8 @@
 //     static constexpr int kAddends;                       // addend tiles TMA stages per row tile (0..2)
 //     static constexpr int kGroups;                        // epilogue groups of 4 warps (2 unless registers forbid)
 //     void load_addends(const AddendRows& a, bool valid);  // copy the row's addends from the staged tiles to registers
-//     void consume16(i64 m, int c0, const float (&v)[16], RowSink& out);   // accumulator columns c0..c0+15 of row m
+//     void consume16(i64 m, int c0, int n0, const float (&v)[16], RowSink& out);   // accumulator columns c0..c0+15 of
+//                                                          // row m in this tile; n0 = the tile's first output column
 //     void finish_rows(float* red, int etid);              // if kHasFinish: block-level reduce of column statistics
 // Addends (residual rows, upstream gradients, saved activations) arrive like the GEMM operands: the producer warp
 // TMA-loads them as 128-row tiles one tile ahead, so their HBM latency never sits on the epilogue's critical path
@@ -97,12 +98,13 @@ struct RowGate {
   static constexpr int kAccPerBlock = 64;
   static constexpr int kAddends = 0;
   static constexpr int kGroups = 2;
+  static constexpr bool kDirectStore = false;
   float* y;          // [P, 32] (written through the kernel's output tensor map)
   const float* bf;
   const float* bg;
   __device__ __forceinline__ void init() {}
   __device__ __forceinline__ void load_addends(const AddendRows&, bool) {}
-  __device__ __forceinline__ void consume16(i64, int c0, const float (&v)[16], const RowSink& out) {
+  __device__ __forceinline__ void consume16(i64, int c0, int, const float (&v)[16], const RowSink& out) {
     const int ch0 = c0 >> 1;
     float o[8];
 #pragma unroll
@@ -119,6 +121,7 @@ struct RowGateBwd {
   static constexpr int kAccPerBlock = 32;
   static constexpr int kAddends = 1;   // dg rows
   static constexpr int kGroups = 2;
+  static constexpr bool kDirectStore = false;
   float* dpre;       // [P, 64]
   const float* dg;   // [P, 32] (addend tile 0)
   const float* bf;
@@ -128,7 +131,7 @@ struct RowGateBwd {
   __device__ __forceinline__ void load_addends(const AddendRows& a, bool valid) {
     if (valid) a.load<32>(0, 0, g);
   }
-  __device__ __forceinline__ void consume16(i64, int c0, const float (&v)[16], const RowSink& out) {
+  __device__ __forceinline__ void consume16(i64, int c0, int, const float (&v)[16], const RowSink& out) {
     const int ch0 = c0 >> 1;
     float o[16];
 #pragma unroll
@@ -149,6 +152,7 @@ struct RowMlp {
   static constexpr int kAccPerBlock = 32;
   static constexpr int kAddends = 1;   // residual rows (tile 0; staged only when res != nullptr)
   static constexpr int kGroups = 2;
+  static constexpr bool kDirectStore = false;
   float* y;            // [P, 32]
   const float* bias;
   DropoutSrc drop;
@@ -162,7 +166,7 @@ struct RowMlp {
   __device__ __forceinline__ void load_addends(const AddendRows& a, bool valid) {
     if (res && valid) a.load<32>(0, 0, rrow);
   }
-  __device__ __forceinline__ void consume16(i64 m, int c0, const float (&v)[16], const RowSink& out) {
+  __device__ __forceinline__ void consume16(i64 m, int c0, int, const float (&v)[16], const RowSink& out) {
     float o[16];
     const i64 e = m * 32 + c0;
 #pragma unroll
@@ -198,11 +202,12 @@ struct RowSeg {
   static constexpr int kAccPerBlock = 32;
   static constexpr int kAddends = 0;
   static constexpr int kGroups = 2;
+  static constexpr bool kDirectStore = false;
   float* out;
   i64 M;
   __device__ __forceinline__ void init() {}
   __device__ __forceinline__ void load_addends(const AddendRows&, bool) {}
-  __device__ __forceinline__ void consume16(i64, int c0, const float (&v)[16], const RowSink& o) { o.put16(c0 & 31, v); }
+  __device__ __forceinline__ void consume16(i64, int c0, int, const float (&v)[16], const RowSink& o) { o.put16(c0 & 31, v); }
   __device__ __forceinline__ void finish_rows(float*, int, int) {}
 };
 
@@ -212,6 +217,7 @@ struct RowTcnDgrad {
   static constexpr int kAccPerBlock = 32;
   static constexpr int kAddends = 2;
   static constexpr int kGroups = 1;    // 64 addend + 64 statistics registers per thread: one group of 128 threads only
+  static constexpr bool kDirectStore = false;
   float* dx;           // [P_in, 32]
   const float* du;     // nullable [P_out, 32]
   int N, L_in, L_out;
@@ -228,7 +234,7 @@ struct RowTcnDgrad {
     if (du) a.load<32>(0, 0, durow);
     if (uprev) a.load<32>(1, 0, urow);
   }
-  __device__ __forceinline__ void consume16(i64, int c0, const float (&v)[16], const RowSink& out) {
+  __device__ __forceinline__ void consume16(i64, int c0, int, const float (&v)[16], const RowSink& out) {
     float o[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) o[c] = v[c] + (du ? durow[c0 + c] : 0.0f);
@@ -246,7 +252,70 @@ struct RowTcnDgrad {
     if (uprev) cs.reduce(red, etid, bsum, bsum + 32, 32, barid);
   }
 };
+// Dense head layers (model.py:216-222, 238-240 and their input gradients): out = act(acc + bias[col]) [* (gate > 0)].
+struct RowDense {
+  static constexpr bool kHasFinish = false;
+  static constexpr int kAccPerBlock = 32;
+  static constexpr int kAddends = 0;
+  static constexpr int kGroups = 2;
+  static constexpr bool kDirectStore = false;
+  const float* bias;   // nullable, indexed by the absolute output column
+  const float* gate;   // nullable [M][ldg]: ReLU mask of the forward activation (backward)
+  int ldg, relu;
+  __device__ __forceinline__ void init() {}
+  __device__ __forceinline__ void load_addends(const AddendRows&, bool) {}
+  __device__ __forceinline__ void consume16(i64 m, int c0, int n0, const float (&v)[16], const RowSink& out) {
+    float o[16];
+    const int ca = n0 + c0;   // absolute output column
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float r = v[j] + (bias ? __ldg(bias + ca + j) : 0.0f);
+      o[j] = relu ? fmaxf(r, 0.0f) : r;
+    }
+    if (gate) {
+      const float4* gp = reinterpret_cast<const float4*>(gate + m * ldg + ca);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 g = __ldg(gp + q);
+        if (!(g.x > 0.0f)) o[4 * q] = 0.0f;
+        if (!(g.y > 0.0f)) o[4 * q + 1] = 0.0f;
+        if (!(g.z > 0.0f)) o[4 * q + 2] = 0.0f;
+        if (!(g.w > 0.0f)) o[4 * q + 3] = 0.0f;
+      }
+    }
+    out.put16(c0 & 31, o);
+  }
+  __device__ __forceinline__ void finish_rows(float*, int, int) {}
+};
+
+// Last head layer (model.py:240): the network output in the reference's NCHW layout [B, O, N, T]; rows are BLNC
+// positions m = (b*T + t)*N + n.  O <= 16 columns, written straight from registers (consecutive threads = consecutive
+// nodes = consecutive addresses for T == 1).
+struct RowNCHW {
+  static constexpr bool kHasFinish = false;
+  static constexpr int kAccPerBlock = 16;
+  static constexpr int kAddends = 0;
+  static constexpr int kGroups = 2;
+  static constexpr bool kDirectStore = true;
+  float* y;
+  const float* bias;
+  int O, N, T;
+  __device__ __forceinline__ void init() {}
+  __device__ __forceinline__ void load_addends(const AddendRows&, bool) {}
+  __device__ __forceinline__ void consume16(i64 m, int c0, int, const float (&v)[16], const RowSink&) {
+    const unsigned nt = (unsigned)N * (unsigned)T;
+    const unsigned b = (unsigned)m / nt, r = (unsigned)m - b * nt;
+    const unsigned t = r / (unsigned)N, n = r - t * (unsigned)N;
+    float* base = y + ((size_t)b * O * N + n) * T + t;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c0 + j < O) base[(size_t)(c0 + j) * N * T] = v[j] + __ldg(bias + c0 + j);
+  }
+  __device__ __forceinline__ void finish_rows(float*, int, int) {}
+};
 #else
+struct RowDense { const float* bias; const float* gate; int ldg, relu; };
+struct RowNCHW { float* y; const float* bias; int O, N, T; };
 struct RowGate { float* y; const float* bf; const float* bg; };
 struct RowGateBwd { float* dpre; const float* dg; const float* bf; const float* bg; };
 struct RowMlp { float* y; const float* bias; DropoutSrc drop; const float* res; Remap rrm; const float* rac; double* stats; };

@@ -33,8 +33,12 @@ struct TcPosArgs {
   int nseg;
   int nb;             // samples
   int rows_out;       // output rows per sample
-  const float* Wp;    // packed weights [N][nseg*32]
-  int N;
+  const float* Wp;    // packed weights [N_total][nseg*32]
+  int N;              // output columns per tile (multiple of 16, <= 256)
+  int wstream;        // 0: the whole [N][K] weight matrix stays resident in shared memory (N_total == N);
+                      // 1: weights too large for that (head GEMMs): the k-block of the tile's N rows is streamed with A
+  int N_total;        // wstream: total output columns (multiple of N); 0 = N
+  int w_k, w_rows;    // actual extent of the weight matrix when smaller than nseg*32 x N_total (rest reads as zero); 0 = full
   const float* Wp_lo; // non-null: 3xTF32 (fp32-grade) mode -- Wp holds the tf32-exact high parts, Wp_lo the remainders
   // output tensor, written by TMA from the swizzled staging tile: out_nblk 32-column blocks per row tile;
   //   out_blk_dim2 == 0: [nb][rows_out][out_width], block k = columns 32k..32k+31;
@@ -64,7 +68,7 @@ struct TpMaps {
   CUtensorMap add[2];
 };
 struct TpParams {
-  int nseg, nb, rows_out, tiles_per_sample, total_tiles, N, stages, out_blk_dim2;
+  int nseg, nb, rows_out, tiles_per_sample, total_tiles, N, stages, out_blk_dim2, wstream, n_nt;
   int add_on[2], add_rshift[2], nadd;
   int col0[TP_MAXSEG], rshift[TP_MAXSEG];
 };
@@ -81,9 +85,10 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   constexpr int NPL = X3 ? 2 : 1;                         // operand planes (hi, lo)
-  constexpr int STG = NPL * TP_A_BYTES;                   // bytes per A stage
-  const int w_plane = p.nseg * p.N * 128;                 // resident weights: [plane][seg][N rows][128 B]
-  const int w_bytes = NPL * w_plane;
+  const int w_blk = p.N * 128;                            // one k-block of weights: [N rows][128 B]
+  const int STG = NPL * TP_A_BYTES + (p.wstream ? NPL * w_blk : 0);   // bytes per stage: [A | A_lo | (W blk | W_lo blk)]
+  const int w_plane = p.nseg * w_blk;                     // resident weights: [plane][seg][N rows][128 B]
+  const int w_bytes = p.wstream ? 0 : NPL * w_plane;
   const uint32_t a0 = base + w_bytes;                     // A stages: [A | A_lo]
   constexpr int NSO = (EP::kGroups == 1) ? 2 : 2 * ((NCT > 0 && NCT / EP::kAccPerBlock == 1) ? 1 : 2);   // output staging tiles
   const uint32_t so0 = a0 + p.stages * STG;               // [128 rows][128 B] each, SWIZZLE_128B
@@ -140,15 +145,18 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
 
   if (warp == 0 && lane == 0) {
     // ===================================================== TMA producer
-    mbar_expect_tx(w_bar, (uint32_t)w_bytes);
-    for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + s * p.N * 128, &maps.w, w_bar, s * 32, 0);
-    if (X3)
-      for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + w_plane + s * p.N * 128, &maps.wlo, w_bar, s * 32, 0);
+    if (!p.wstream) {
+      mbar_expect_tx(w_bar, (uint32_t)w_bytes);
+      for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + s * w_blk, &maps.w, w_bar, s * 32, 0);
+      if (X3)
+        for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + w_plane + s * w_blk, &maps.wlo, w_bar, s * 32, 0);
+    }
     int stage = 0, eb = 0;
     uint32_t phase = 0, ephase = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
-      const int b = tile / p.tiles_per_sample, rt = tile - b * p.tiles_per_sample;
+      const int nt = tile % p.n_nt, rtile = tile / p.n_nt;
+      const int b = rtile / p.tiles_per_sample, rt = rtile - b * p.tiles_per_sample;
       if (NADD > 0 && p.nadd > 0) {   // the epilogue's addend tiles of this row tile
         if (!mbar_wait(eempty_bar(eb), ephase ^ 1u, 18)) { ok = false; break; }
         mbar_expect_tx(efull_bar(eb), (uint32_t)p.nadd * TP_A_BYTES);
@@ -160,8 +168,13 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
       }
       for (int s = 0; s < p.nseg; ++s) {
         if (!mbar_wait(empty_bar(stage), phase ^ 1u, 11)) { ok = false; break; }
-        mbar_expect_tx(full_bar(stage), TP_A_BYTES);
+        mbar_expect_tx(full_bar(stage), TP_A_BYTES + (p.wstream ? NPL * w_blk : 0));
         tma_load_3d(a0 + stage * STG, &maps.a[s], full_bar(stage), p.col0[s], rt * 128 + p.rshift[s], b);
+        if (p.wstream) {
+          const uint32_t wdst = a0 + stage * STG + NPL * TP_A_BYTES;
+          tma_load_2d(wdst, &maps.w, full_bar(stage), s * 32, nt * p.N);
+          if (X3) tma_load_2d(wdst + w_blk, &maps.wlo, full_bar(stage), s * 32, nt * p.N);
+        }
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -170,7 +183,7 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int stage = 0, acc = 0;
     uint32_t phase = 0, accphase = 0;
-    bool ok = mbar_wait(w_bar, 0, 12);
+    bool ok = p.wstream ? true : mbar_wait(w_bar, 0, 12);
     tc_fence_after();
     for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
       if (!mbar_wait(tempty_bar(acc), accphase ^ 1u, 13)) break;
@@ -181,14 +194,15 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
         if (X3 && !mbar_wait(split_bar(stage), phase, 16)) { ok = false; break; }
         tc_fence_after();
         const uint32_t as = a0 + stage * STG;
-        const uint32_t ws = base + s * p.N * 128;
+        const uint32_t ws = p.wstream ? as + NPL * TP_A_BYTES : base + s * w_blk;
+        const uint32_t wlo_off = p.wstream ? (uint32_t)w_blk : (uint32_t)w_plane;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           // both operands K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart, this k-step 32 B in
           const uint64_t ad = make_desc(as + kk * 32, 16, 1024), wd = make_desc(ws + kk * 32, 16, 1024);
           tc_mma_tf32(d_tmem, ad, wd, idesc, (s > 0 || kk > 0) ? 1u : 0u);
           if (X3) {
-            tc_mma_tf32(d_tmem, ad, make_desc(ws + w_plane + kk * 32, 16, 1024), idesc, 1u);
+            tc_mma_tf32(d_tmem, ad, make_desc(ws + wlo_off + kk * 32, 16, 1024), idesc, 1u);
             tc_mma_tf32(d_tmem, make_desc(as + TP_A_BYTES + kk * 32, 16, 1024), wd, idesc, 1u);
           }
         }
@@ -214,12 +228,7 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
 #pragma unroll 4
         for (int i = t64; i < TP_A_BYTES / 16; i += 64) {
           const float4 v = src[i];
-          float4 r;
-          r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-          r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-          r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-          r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-          dst[i] = r;
+          dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         mbar_arrive(split_bar(stage));
@@ -248,7 +257,9 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
       if (NG == 2 && (it & 1) != grp) continue;
       const int buf = it & 1;                               // accumulator / addend buffer of this tile
       const uint32_t bphase = (uint32_t)(it >> 1) & 1u;     // ... and how often it has been used: its barrier parity
-      const int b = tile / p.tiles_per_sample, rt = tile - b * p.tiles_per_sample;
+      const int nt = tile % p.n_nt, rtile = tile / p.n_nt;
+      const int b = rtile / p.tiles_per_sample, rt = rtile - b * p.tiles_per_sample;
+      const int n0 = nt * p.N;                              // first output column of this tile
       const int rl = rt * 128 + r;
       const bool valid = rl < p.rows_out;
       const i64 m = (i64)b * p.rows_out + rl;
@@ -267,6 +278,24 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(buf * 256);
       const int ncols = NCT > 0 ? NCT : p.N;
       auto do_block = [&](const int blk) {
+        if constexpr (EP::kDirectStore) {   // tiny strided outputs (the network's NCHW result): straight from registers
+          const RowSink sink{nullptr, 0u};
+#pragma unroll
+          for (int cc = 0; cc < APB; cc += 16) {
+            const int c0 = blk * APB + cc;
+            if (c0 < ncols) {
+              uint32_t rr[16];
+              tc_ld16(taddr + c0, rr);
+              tc_wait_ld();
+              if (valid) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+                ep.consume16(m, c0, n0, v, sink);
+              }
+            }
+          }
+        } else {
         // staging ring: the TMA store that last read this tile must have finished reading it
         if (elected) {
           if (RING == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -285,19 +314,21 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
-            ep.consume16(m, c0, v, sink);
+            ep.consume16(m, c0, n0, v, sink);
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the TMA engine
         asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
         if (elected) {
-          const int c0o = p.out_blk_dim2 ? 0 : 32 * blk, c2o = p.out_blk_dim2 ? blk : b;
+          const int oblk = n0 / 32 + blk;                   // output block index across column tiles
+          const int c0o = p.out_blk_dim2 ? 0 : 32 * oblk, c2o = p.out_blk_dim2 ? oblk : b;
           asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&maps.out),
                        "r"(so_grp32 + slot * TP_A_BYTES), "r"(c0o), "r"(rt * 128), "r"(c2o)
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         ++ring;
+        }
       };
       if constexpr (NCT > 0) {   // compile-time block count: the epilogue's per-column register arrays stay in registers
 #pragma unroll
@@ -337,17 +368,21 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
   using namespace tc;
   if (NCT > 0 && a.N != NCT) return -1;
   if (a.nseg < 1 || a.nseg > TP_MAXSEG || a.N < 16 || a.N > 256 || a.N % 16 != 0 || a.nb < 1 || a.rows_out < 1) return -1;
+  const int N_total = (a.wstream && a.N_total > 0) ? a.N_total : a.N;
+  if (N_total % a.N != 0) return -1;
   if (reinterpret_cast<uintptr_t>(a.Wp) & 15) return -1;
   TpMaps maps;
   TpParams p;
   memset(&p, 0, sizeof(p));
   p.nseg = a.nseg; p.nb = a.nb; p.rows_out = a.rows_out; p.N = a.N;
+  p.wstream = a.wstream ? 1 : 0;
+  p.n_nt = N_total / a.N;
   p.tiles_per_sample = (a.rows_out + 127) / 128;
-  const long long tiles = (long long)p.tiles_per_sample * a.nb;
+  const long long tiles = (long long)p.tiles_per_sample * a.nb * p.n_nt;
   if (tiles > 2147483647LL) return -1;
   p.total_tiles = (int)tiles;
-  const int w_bytes = (X3 ? 2 : 1) * a.nseg * a.N * 128;
-  constexpr int STG = (X3 ? 2 : 1) * TP_A_BYTES;
+  const int w_bytes = a.wstream ? 0 : (X3 ? 2 : 1) * a.nseg * a.N * 128;
+  const int STG = (X3 ? 2 : 1) * (TP_A_BYTES + (a.wstream ? a.N * 128 : 0));
   constexpr int NSO = (EP::kGroups == 1) ? 2 : 2 * ((NCT > 0 && NCT / EP::kAccPerBlock == 1) ? 1 : 2);
   constexpr int FIXED = (NSO + 2 * EP::kAddends) * TP_A_BYTES;   // output staging tiles + addend tiles
   p.stages = (SMEM_LIMIT - 2048 - w_bytes - FIXED) / STG;
@@ -364,10 +399,13 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
     p.nadd += 1;
   }
   p.out_blk_dim2 = a.out_blk_dim2;
-  if (!a.out || (reinterpret_cast<uintptr_t>(a.out) & 15) || a.out_width % 4 != 0 || a.out_nblk < 1 ||
-      a.out_nblk * EP::kAccPerBlock != a.N || (a.out_blk_dim2 ? (a.out_width != 32 || a.nb != 1) : (a.out_width < 32 * a.out_nblk)))
+  if (!EP::kDirectStore &&
+      (!a.out || (reinterpret_cast<uintptr_t>(a.out) & 15) || a.out_width % 4 != 0 || a.out_nblk < 1 ||
+       a.out_nblk * EP::kAccPerBlock != N_total || (a.out_blk_dim2 ? (a.out_width != 32 || a.nb != 1) : (a.out_width < 32 * a.out_nblk))))
     return -1;
-  {
+  if (EP::kDirectStore) {
+    maps.out = maps.a[0];
+  } else {
     cuuint64_t d[3] = {(cuuint64_t)a.out_width, (cuuint64_t)a.rows_out, (cuuint64_t)(a.out_blk_dim2 ? a.out_nblk : a.nb)};
     cuuint64_t st[2] = {(cuuint64_t)a.out_width * 4, (cuuint64_t)a.rows_out * a.out_width * 4};
     cuuint32_t box[3] = {32, 128, 1};
@@ -377,7 +415,7 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
   if (p.stages < 2) return -1;
   for (int s = 0; s < a.nseg; ++s) {
     const TcPosSeg& g = a.seg[s];
-    if ((reinterpret_cast<uintptr_t>(g.src) & 15) || g.row_width % 4 != 0 || g.col0 + 32 > g.row_width) return -1;
+    if ((reinterpret_cast<uintptr_t>(g.src) & 15) || g.row_width % 4 != 0 || g.col0 >= g.row_width) return -1;   // a box past the row end reads zeros
     cuuint64_t d[3] = {(cuuint64_t)g.row_width, (cuuint64_t)g.rows_src, (cuuint64_t)a.nb};
     cuuint64_t st[2] = {(cuuint64_t)g.row_width * 4, (cuuint64_t)g.rows_src * g.row_width * 4};
     cuuint32_t box[3] = {32, 128, 1};
@@ -387,8 +425,8 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
   }
   for (int s = a.nseg; s < TP_MAXSEG; ++s) maps.a[s] = maps.a[0];
   {
-    const int K = a.nseg * 32;
-    cuuint64_t d[2] = {(cuuint64_t)K, (cuuint64_t)a.N};
+    const int K = a.w_k > 0 ? a.w_k : a.nseg * 32;   // row length of the weight matrix (short rows are zero-filled)
+    cuuint64_t d[2] = {(cuuint64_t)K, (cuuint64_t)(a.w_rows > 0 ? a.w_rows : N_total)};
     cuuint64_t st[1] = {(cuuint64_t)K * 4};
     cuuint32_t box[2] = {32, (cuuint32_t)a.N};
     GWN_TRY(encode(&maps.w, a.Wp, 2, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B));
