@@ -1506,6 +1506,27 @@ int gwn_plan_train_fwd_bwd(gwn_plan* p, const gwn_train_args* a) {
   return plan_backward(p, &ba, true);
 }
 
+int gwn_plan_eval_metrics(gwn_plan* p, const gwn_train_args* a) {
+  GWN_CHECK_ARG(p && a, "eval_metrics: null argument");
+  GWN_CHECK_ARG(a->ctrl && a->metrics && a->target && a->fwd.output, "eval_metrics: null buffer");
+  GWN_TRY(require_device());
+  const gwn_config& c = p->c;
+  cudaStream_t st = (cudaStream_t)a->fwd.stream;
+  TrainCtrl* ctrl = reinterpret_cast<TrainCtrl*>(a->ctrl);
+  GWN_TRY(dev_memset(&ctrl->acc[0], 0, sizeof(double) * 4, st));
+  gwn_forward_args fa = a->fwd;
+  fa.training = 0;
+  fa.dropout_mode = GWN_DROPOUT_NONE;
+  GWN_TRY(plan_forward(p, &fa));
+  const i64 n = (i64)c.batch * c.out_dim * c.num_nodes * p->T_out;
+  ProfScope prof("loss_metrics", st, 4.0 * n * 2.0, 0.0);
+  GWN_LAUNCH_1D(loss_reduce_kernel, n, st, (const float*)a->fwd.output, a->target, (i64)a->target_strides[0],
+                (i64)a->target_strides[1], (i64)a->target_strides[2], a->scaler_mean, a->scaler_std, c.batch, c.out_dim,
+                c.num_nodes, p->T_out, ctrl);
+  GWN_LAUNCH_1D(metrics_finalize_kernel, 1, st, (const TrainCtrl*)ctrl, p->T_out, a->metrics);
+  return 0;
+}
+
 int gwn_adam_step(const gwn_adam_args* a) {
   GWN_CHECK_ARG(a && a->param_flat && a->grad_flat && a->exp_avg && a->exp_avg_sq && a->live4 && a->hyper && a->ctrl,
                 "adam_step: null argument");

@@ -94,6 +94,16 @@ GWN_GLOBAL loss_grad_kernel(const float* out, const float* y, i64 ys0, i64 ys1, 
   }
 }
 
+// metrics = {mae, mape, rmse} from the accumulators alone (trainer.eval: no gradient wanted)
+GWN_GLOBAL metrics_finalize_kernel(const TrainCtrl* c, int T, float* metrics) {
+  GWN_FOR_EACH(i, 1) {
+    const double denom = c->acc[0] * (double)T;
+    metrics[0] = denom > 0.0 ? (float)(c->acc[1] / denom) : 0.0f;
+    metrics[1] = denom > 0.0 ? (float)(c->acc[2] / denom) : 0.0f;
+    metrics[2] = denom > 0.0 ? (float)sqrt(c->acc[3] / denom) : 0.0f;
+  }
+}
+
 // hyper: lr, beta1, beta2, eps, weight_decay, max_norm (<= 0: no clipping), grad_scale (1/world after an all-reduce sum)
 struct AdamHyper {
   float lr, beta1, beta2, eps, wd, max_norm, gscale, pad;

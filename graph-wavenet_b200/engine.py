@@ -82,6 +82,9 @@ class trainer():
         if st is None or not st.valid():
             self._steps = {k: v for k, v in self._steps.items() if v.valid()}
             st = _fused.FusedStep(self, input, real_val, self.use_graph)
+            for v in self._steps.values():      # a new FlatParams re-homes the parameters: captured eval graphs are stale
+                if isinstance(v, _fused.FusedEval) and not v.valid():
+                    v.key = None
             self._steps[key] = st
         return st
 
@@ -115,8 +118,23 @@ class trainer():
         rmse = util.masked_rmse(predict, real, 0.0).item()
         return loss.item(), mape, rmse
 
+    def _fused_eval(self, input, real_val):
+        key = ("eval", tuple(input.shape), tuple(real_val.shape), self.model.precision, bool(self.use_graph))
+        ev = self._steps.get(key)
+        if ev is None or not ev.valid():
+            self.model._table()
+            ws = None
+            for v in self._steps.values():      # share the forward workspace of a train step of the same shape
+                if isinstance(v, _fused.FusedStep) and v.plan is self.model._runner(input.shape[0], input.shape[3]).plan:
+                    ws = v.workspace
+            ev = _fused.FusedEval(self, input, real_val, self.use_graph, ws)
+            self._steps[key] = ev
+        return ev
+
     def eval(self, input, real_val):
         self.model.eval()
+        if self.fused and self.loss is util.masked_mae:
+            return self._fused_eval(input, real_val).run(input, real_val)
         input = nn.functional.pad(input, (1, 0, 0, 0))
         with torch.no_grad():   # the reference builds and discards a graph here; results are identical
             output = self.model(input)

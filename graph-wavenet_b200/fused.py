@@ -292,6 +292,78 @@ class FusedStep:
         return float(m[0]), float(m[1]), float(m[2])
 
 
+class FusedEval:
+    """``trainer.eval`` (engine.py:119-130) for a fixed shape: forward in eval mode + the three masked metrics as one
+    captured launch sequence, one host sync."""
+
+    def __init__(self, trainer, x: torch.Tensor, y: torch.Tensor, use_graph: bool, workspace: Optional[torch.Tensor] = None):
+        model = trainer.model
+        lib = N.get_lib()
+        self.lib, self.trainer = lib, trainer
+        dev = x.device
+        B, F, Nn, T = x.shape
+        runner = model._runner(B, T)
+        self.runner, self.plan = runner, runner.plan
+        cfg = runner.cfg
+        if y.dim() != 3 or y.shape[0] != B or y.shape[1] != Nn or y.shape[2] != cfg.out_dim:
+            raise N.GwnError(f"real_val must be [B={B}, N={Nn}, out_dim={cfg.out_dim}], got {tuple(y.shape)}")
+        self.x = torch.empty((B, T, Nn, F), dtype=torch.float32, device=dev).permute(0, 3, 2, 1)
+        self.y = torch.empty(tuple(y.shape), dtype=torch.float32, device=dev)
+        self.out = torch.empty((B, cfg.out_dim, Nn, self.plan.t_out), dtype=torch.float32, device=dev)
+        self.workspace = workspace if workspace is not None else torch.empty(self.plan.fwd_bytes, dtype=torch.uint8, device=dev)
+        self.ctrl = torch.zeros(int(lib.dll.gwn_train_ctrl_bytes()), dtype=torch.uint8, device=dev)
+        self.metrics = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.metrics_host = _pinned(torch.zeros(4, dtype=torch.float32), dev)
+        self.table = [t.detach() for t in model._table()]
+        self.ptab = runner._param_table(self.table)
+        self.sup, self.sptrs, self.sstrides = runner._supports(model.supports)
+        self.key = (self.table[0].data_ptr(), self.table[-1].data_ptr(), tuple(s.data_ptr() for s in self.sup))
+        self.graph = None
+        if use_graph and dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self.graph = g
+
+    def valid(self) -> bool:
+        m = self.trainer.model
+        if m._entries is None:
+            return False
+        t = m._entries
+        return self.key == (t[0].data_ptr(), t[-1].data_ptr(), tuple(s.data_ptr() for s in (m.supports or [])[:len(self.sup)]))
+
+    def _enqueue(self):
+        dev = self.x.device
+        with _dev_ctx(dev):
+            a = N.GwnTrainArgs()
+            f = a.fwd
+            f.params, f.supports, f.support_strides = self.ptab, self.sptrs, self.sstrides
+            f.input = self.x.data_ptr()
+            for k in range(4):
+                f.input_strides[k] = self.x.stride(k)
+            f.output, f.workspace, f.training, f.dropout_mode = self.out.data_ptr(), self.workspace.data_ptr(), 0, N.DROPOUT_NONE
+            f.stream = _stream(dev)
+            a.target = self.y.data_ptr()
+            for k in range(3):
+                a.target_strides[k] = self.y.stride(k)
+            a.scaler_mean, a.scaler_std = float(self.trainer.scaler.mean), float(self.trainer.scaler.std)
+            a.ctrl, a.metrics = self.ctrl.data_ptr(), self.metrics.data_ptr()
+            self.lib.check(self.lib.dll.gwn_plan_eval_metrics(self.plan.handle, C.byref(a)), "gwn_plan_eval_metrics")
+            self.metrics_host.copy_(self.metrics, non_blocking=True)
+
+    def run(self, x: torch.Tensor, y: torch.Tensor):
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+        _sync(self.x.device)
+        m = self.metrics_host
+        return float(m[0]), float(m[1]), float(m[2])
+
+
 def fused_enabled() -> bool:
     return os.environ.get("GWNET_B200_FUSED_STEP", "1") != "0"
 

@@ -85,7 +85,7 @@ EXPORTS = [
     "gwn_gcn_fwd", "gwn_gcn_bwd_scratch_floats", "gwn_gcn_bwd",
     "gwn_plan_create", "gwn_plan_destroy", "gwn_plan_workspace_bytes", "gwn_plan_param_count",
     "gwn_plan_param_info", "gwn_plan_out_len", "gwn_plan_debug_layout", "gwn_plan_forward", "gwn_plan_backward",
-    "gwn_train_ctrl_bytes", "gwn_train_ctrl_init", "gwn_train_ctrl_read", "gwn_plan_train_fwd_bwd", "gwn_adam_step",
+    "gwn_train_ctrl_bytes", "gwn_train_ctrl_init", "gwn_train_ctrl_read", "gwn_plan_train_fwd_bwd", "gwn_plan_eval_metrics", "gwn_adam_step",
 ]
 
 
@@ -150,6 +150,7 @@ class Lib:
         d.gwn_train_ctrl_init.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
         d.gwn_train_ctrl_read.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
         d.gwn_plan_train_fwd_bwd.argtypes = [C.c_void_p, C.POINTER(GwnTrainArgs)]
+        d.gwn_plan_eval_metrics.argtypes = [C.c_void_p, C.POINTER(GwnTrainArgs)]
         d.gwn_adam_step.argtypes = [C.POINTER(GwnAdamArgs)]
         if d.gwn_abi_version() != 2:
             raise GwnError(f"{path}: ABI version {d.gwn_abi_version()} != 2")

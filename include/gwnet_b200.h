@@ -235,6 +235,11 @@ typedef struct gwn_train_args {
 } gwn_train_args;
 int gwn_plan_train_fwd_bwd(gwn_plan* p, const gwn_train_args* a);
 
+/* trainer.eval (engine.py:119-130): forward in eval mode (BatchNorm running statistics, no dropout) + the three masked
+ * metrics, no backward.  Uses fwd (training is forced to 0), target, target_strides, scaler_*, ctrl and metrics of
+ * gwn_train_args; scratch / grad_flat are ignored.  metrics[0..2] = masked MAE, MAPE, RMSE.                        */
+int gwn_plan_eval_metrics(gwn_plan* p, const gwn_train_args* a);
+
 typedef struct gwn_adam_args {
   float* param_flat;             /* n floats, the layout of the plan's flat gradient buffer; updated in place        */
   float* grad_flat;              /* n floats; on return holds the (scaled, clipped) gradient, like p.grad           */

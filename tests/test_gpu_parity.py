@@ -412,3 +412,35 @@ def test_fused_graph_step_draws_fresh_dropout_masks(M, monkeypatch):
     tr.optimizer.param_groups[0]["lr"] = 1e-2
     tr.train(x, y)
     assert not torch.equal(before, tr.model.start_conv.weight)
+
+
+def test_device_feed_and_fused_eval(M, monkeypatch):
+    """Device-resident batch iterator (feed.py) -> trainer.train / trainer.eval (one CUDA graph each): the loader-layout
+    batches [B,T,N,F] are consumed through the strided view of train.py:245; eval matches the autograd-free torch path."""
+    import numpy as np
+    from graph_wavenet_b200.feed import DataLoader
+    dev = torch.device("cuda:0")
+    rec = load_case("dbl_adp")
+    cfg = rec["cfg"]
+    sup = [s.to(dev) for s in rec["supports"]]
+    x = rec["x"].transpose(1, 3).contiguous().numpy()                  # [B, T, N, F] as generate_training_data.py writes it
+    y = rec["y"][:, :, : cfg.out_dim].permute(0, 2, 1).unsqueeze(-1).contiguous().numpy()    # [B, T, N, 1]
+    B = x.shape[0]
+    loader = DataLoader(np.concatenate([x, x[: B // 2]]), np.concatenate([y, y[: B // 2]]), B, device=dev)
+    assert loader.num_batch == 2
+    runs = {}
+    for mode, fused in (("fused", True), ("torch", False)):
+        tr = _make_trainer(dev, cfg, sup, rec["state0"], 0.0, fused, fused, monkeypatch)
+        out = []
+        for bx, by in loader.get_iterator():
+            trainx, trainy = bx.transpose(1, 3), by.transpose(1, 3)    # train.py:245-247
+            out.append(tr.train(trainx, trainy[:, 0, :, :]))
+        for bx, by in loader.get_iterator():
+            out.append(tr.eval(bx.transpose(1, 3), by.transpose(1, 3)[:, 0, :, :]))
+        runs[mode] = out
+    for a, b in zip(runs["fused"], runs["torch"]):
+        for u, v in zip(a, b):
+            assert abs(u - v) <= 1e-4 * abs(v) + 1e-6, (runs["fused"], runs["torch"])
+    want = rec["trainer_metrics"].tolist()[0]                          # first batch = the golden batch, first step
+    for u, v in zip(runs["fused"][0], want):
+        assert abs(u - v) <= 1e-4 * abs(v) + 1e-6

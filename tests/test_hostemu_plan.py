@@ -155,6 +155,10 @@ def test_emulated_fused_train_step_matches_reference_trainer(emu, name):
         emu.check(emu.dll.gwn_adam_step(C.byref(ad)), "adam_step")
         for got, w in zip(metrics[:3].tolist(), want[step]):
             assert abs(got - w) <= 1e-4 * abs(w) + 1e-6, (step, metrics.tolist(), want[step])
+    # trainer.eval after the three steps (engine.py:119-130): eval-mode forward + the three metrics
+    emu.check(emu.dll.gwn_plan_eval_metrics(plan.handle, C.byref(a)), "eval_metrics")
+    for got, w in zip(metrics[:3].tolist(), want[3]):
+        assert abs(got - w) <= 1e-4 * abs(w) + 1e-6, ("eval", metrics.tolist(), want[3])
     seed, st = C.c_uint64(0), C.c_int64(0)
     emu.check(emu.dll.gwn_train_ctrl_read(ctrl.data_ptr(), C.byref(seed), C.byref(st)))
     assert st.value == 3 and seed.value != 1234
