@@ -320,7 +320,13 @@ static int build_plan(gwn_plan* p) {
   // tcgen05 reductions (tf32 tier): per-CTA partial results, 160 slots of the largest accumulator tile in use
   const bool tc_tier = (c.precision == GWN_PREC_TF32 || c.precision == GWN_PREC_FP32X3) && C == 32 && D == 32;
   p->defer_dA = tc_tier && c.adaptive && c.num_nodes <= 512 && 2 * nL <= TR_MAXSRC;
-  p->part_floats = tc_tier ? (i64)160 * (p->defer_dA ? 512 * 128 : 256 * 64) : 0;
+  {
+    // adaptive support gradient: one slot = at most 512 x 128 accumulator floats; large graphs tile the output into
+    // (V/256) x (V/256) tiles with at least one CTA each
+    const i64 ot = (i64)((N + 255) / 256) * ((N + 255) / 256);
+    const i64 slots = std::max<i64>(160, ot);
+    p->part_floats = tc_tier ? (c.adaptive ? slots * 512 * 128 : (i64)160 * 256 * 64) : 0;
+  }
   p->o_part = take(p->part_floats);
   p->o_buf0 = take(maxP * C);
   p->o_buf1 = take(maxP * C);

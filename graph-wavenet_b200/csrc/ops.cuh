@@ -119,7 +119,7 @@ inline int support_grad_tc(const float* const* Xp, const float* const* Yp, const
   TcRedResult r;
   int st = launch_tcred(t, stream, &r);
   if (st != 0) return st;
-  tc::SlotSupOut f{dA, (int)ldda, V, r.N, r.n_nt};
+  tc::SlotSupOut f{dA, (int)ldda, V, r.N, r.n_nt, r.mtiles * 128, r.n_mg};
   return launch_slot_reduce(ts.partial, r, (i64)V * V, f, stream);
 #endif
 }

@@ -39,7 +39,7 @@ struct TcRedArgs {
 //   MODE_MN: slot layout [mtiles*128 rows = (blk, i)][N]; MODE_K: [mtiles*128 rows = v][Ntile], slot s covers the
 //   output columns (s % n_nt)*Ntile .. +Ntile.
 struct TcRedResult {
-  int nslots, mtiles, N, n_nt;
+  int nslots, mtiles, N, n_nt, n_mg;   // MODE_K: output tiled n_mg (row groups of mtiles*128) x n_nt (column tiles of N)
   i64 slot_floats;
 };
 
@@ -51,7 +51,7 @@ struct TrMaps {
   CUtensorMap b[TR_MAXSRC];
 };
 struct TrParams {
-  int mode, na, nblk, mtiles, N, nbn, nb, chunks_per_sample, total_chunks, stages, a_bytes, b_bytes, tx_bytes, n_nt;
+  int mode, na, nblk, mtiles, N, nbn, nb, chunks_per_sample, total_chunks, stages, a_bytes, b_bytes, tx_bytes, n_nt, n_mg;
   int acol0[TR_MAXSRC], arshift[TR_MAXSRC], bcol0[TR_MAXSRC];
   int pair_end[TR_MAXSRC];   // MODE_K: cumulative chunk (slab) counts per pair
   float* partial;
@@ -115,7 +115,9 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
   const uint32_t tmem_base = *tmem_slot;
 
   // contiguous chunk range of this CTA (MODE_K: CTAs are split over n_nt column tiles of the output)
-  const int ntile = (int)(blockIdx.x % p.n_nt), kslot = (int)(blockIdx.x / p.n_nt), nk = (int)(gridDim.x / p.n_nt);
+  const int n_ot = p.n_nt * p.n_mg;   // output tiles; CTA = (k split, row group, column tile)
+  const int ot = (int)(blockIdx.x % n_ot), ntile = ot % p.n_nt, mg = ot / p.n_nt;
+  const int kslot = (int)(blockIdx.x / n_ot), nk = (int)(gridDim.x / n_ot);
   const int c_beg = (int)((long long)p.total_chunks * kslot / nk);
   const int c_end = (int)((long long)p.total_chunks * (kslot + 1) / nk);
 
@@ -135,7 +137,8 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       } else {
         while (c >= p.pair_end[pair]) ++pair;
         const int slab = c - (pair ? p.pair_end[pair - 1] : 0);
-        for (int t = 0; t < p.mtiles; ++t) tma_load_3d(sa + t * 16384, &maps.a[pair], full_bar(stage), 0, t * 128, slab);
+        for (int t = 0; t < p.mtiles; ++t)
+          tma_load_3d(sa + t * 16384, &maps.a[pair], full_bar(stage), 0, (mg * p.mtiles + t) * 128, slab);
         tma_load_3d(sb, &maps.b[pair], full_bar(stage), 0, ntile * p.N, slab);
       }
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -310,14 +313,15 @@ struct SlotTcnOut {
     }
   }
 };
-// support gradient: slot rows v x Ntile columns; slot s holds output columns (s % n_nt)*Ntile ...
+// support gradient: a slot holds output rows (mg*MR .. +MR) x columns (nt*Ntile .. +Ntile); slot index =
+// (k split * n_mg + mg) * n_nt + nt
 struct SlotSupOut {
-  float* dA; int ld, V, Ntile, n_nt;
+  float* dA; int ld, V, Ntile, n_nt, MR, n_mg;
   __device__ __forceinline__ void where(i64 i, i64& off, i64& off2, int& slot0, int& step) const {
     const int v = (int)(i / V), w = (int)(i - (i64)v * V);
-    const int nt = w / Ntile;
-    off = (i64)v * Ntile + (w - nt * Ntile);
-    off2 = -1; slot0 = nt; step = n_nt;
+    const int nt = w / Ntile, mg = v / MR;
+    off = (i64)(v - mg * MR) * Ntile + (w - nt * Ntile);
+    off2 = -1; slot0 = mg * n_nt + nt; step = n_nt * n_mg;
   }
   __device__ __forceinline__ void store(i64 i, float s0, float) const {
     const int v = (int)(i / V), w = (int)(i - (i64)v * V);
@@ -347,7 +351,7 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
   TrMaps maps;
   TrParams p;
   memset(&p, 0, sizeof(p));
-  p.mode = a.mode; p.na = a.na; p.nb = a.nb; p.n_nt = 1;
+  p.mode = a.mode; p.na = a.na; p.nb = a.nb; p.n_nt = 1; p.n_mg = 1;
   if (a.na < 1 || a.na > TR_MAXSRC || a.rows < 1 || !a.partial || !res) return -1;
   static int num_sms = [] {
     int dev = 0, n = 148;
@@ -394,7 +398,10 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
     // n_nt column tiles are spread over the CTAs
     p.nblk = 0;
     p.mtiles = (a.rows + 127) / 128;
-    if (p.mtiles > 4) return -1;              // V <= 512
+    if (p.mtiles > 4) {                       // large graphs: row groups of 256 as well as column tiles
+      p.n_mg = (p.mtiles + 1) / 2;
+      p.mtiles = 2;
+    }
     int ntile = (512 / p.mtiles) / 16 * 16;
     if (ntile > 256) ntile = 256;
     if (a.x3) {   // two stages of [A | B | A_lo | B_lo] must fit shared memory
@@ -437,11 +444,13 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
   p.stages = (SMEM_LIMIT - 2048) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) return -1;
-  // grid: a multiple of n_nt, every CTA gets at least one chunk
-  int nk = num_sms / p.n_nt;
+  // grid: a multiple of the output tile count, every CTA gets at least one chunk
+  const int n_ot = p.n_nt * p.n_mg;
+  int nk = num_sms / n_ot;
+  if (nk < 1) nk = 1;
   if (nk > p.total_chunks) nk = p.total_chunks;
   if (nk < 1) return -1;
-  const int grid = nk * p.n_nt;
+  const int grid = nk * n_ot;
   p.slot_floats = (i64)p.mtiles * 128 * p.N;
   if ((i64)grid * p.slot_floats > a.partial_floats) return -1;
   p.partial = a.partial;
@@ -456,7 +465,7 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
   else tcred_kernel<false><<<grid, 256, smem_bytes, stream>>>(maps, p);
   GWN_LAUNCH_CHECK();
   count_launch();
-  res->nslots = grid; res->mtiles = p.mtiles; res->N = p.N; res->n_nt = p.n_nt; res->slot_floats = p.slot_floats;
+  res->nslots = grid; res->mtiles = p.mtiles; res->N = p.N; res->n_nt = p.n_nt; res->n_mg = p.n_mg; res->slot_floats = p.slot_floats;
   return 0;
 #endif
 }
