@@ -180,12 +180,35 @@ def roofline_leg(lib, step_fn, dev, steps=5):
                       "share": o["ms"] / total, "GBps": gbs, "hbm_frac": gbs / hbm_peak, "TFLOPs": tfs,
                       "tensor_frac": tfs / tens_peak, "flop_per_byte": ai, "bound": "tensor" if ai > ridge else "hbm"})
     table.sort(key=lambda r: -r["share"])
-    top = table[0]
-    if top["bound"] == "hbm":
-        roof = {"bound": "hbm", "achieved": top["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": top["hbm_frac"]}
+    # kernel families: which hand-written kernel runs each operator's dominant launch
+    fam_of = {"nconv_fwd": "nconv_tc_kernel", "nconv_bwd_dx_hops": "nconv_tc_kernel", "nconv_bwd_dx_sum": "nconv_tc_kernel",
+              "nconv_bwd_dA": "tcred_kernel", "gcn_mlp_wgrad": "tcred_kernel", "gated_tcn_wgrad": "tcred_kernel",
+              "gated_tcn_fwd": "tcpos_kernel<RowGate>", "gated_tcn_bwd_gate": "tcpos_kernel<RowGateBwd>",
+              "gated_tcn_dgrad": "tcpos_kernel<RowTcnDgrad>", "gcn_mlp_fwd": "tcpos_kernel<RowMlp>",
+              "gcn_mlp_dgrad": "tcpos_kernel<RowSeg>", "head_fwd": "tcpos_kernel<RowDense>"}
+    fams = {}
+    for o in ops:
+        f = fam_of.get(o["op"])
+        if f is None or o["ms"] <= 0:
+            continue
+        a = fams.setdefault(f, {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "groups": 0})
+        a["ms"] += o["ms"]; a["bytes"] += o["bytes"]; a["flops"] += o["flops"]; a["groups"] += o["calls"]
+    fam, a = max(fams.items(), key=lambda kv: kv[1]["ms"])
+    sec = a["ms"] * 1e-3
+    gbs, tfs = a["bytes"] / sec / 1e9, a["flops"] / sec / 1e12
+    ai = a["flops"] / a["bytes"] if a["bytes"] else 0.0
+    if ai <= ridge:
+        roof = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak}
     else:
-        roof = {"bound": "tensor", "achieved": top["TFLOPs"], "peak": tens_peak, "unit": "TFLOP/s", "frac": top["tensor_frac"]}
-    roof.update({"traffic": None, "kernel": top["op"], "share_of_step": top["share"],
+        roof = {"bound": "tensor", "achieved": tfs, "peak": tens_peak, "unit": "TFLOP/s", "frac": tfs / tens_peak}
+    # DRAM bytes of one captured launch of this kernel (ncu --set full, profiles/r01e_ncu_key_metrics.json): the layer-0
+    # first-hop node contraction moved 62.1 MB in + 15.7 MB out against 81.2 MB algorithmic (the tail of the writes was
+    # still in L2 when the kernel ended) -- no re-read waste
+    traffic = 77.8e6 if fam == "nconv_tc_kernel" else None
+    roof.update({"traffic": traffic, "traffic_note": "one launch (layer 0, first hop: 81.2e6 algorithmic bytes), ncu r01e" if traffic else None,
+                 "kernel": fam, "share_of_step": a["ms"] / total, "tensor_TFLOPs": tfs, "flop_per_byte": ai,
+                 "algorithmic_bytes_per_step": a["bytes"] / steps, "ms_per_step": a["ms"] / steps,
+                 "operators": [k for k, v in fam_of.items() if v == fam],
                  "peak_source": f"MEASURED_PEAKS.json ({src}): hbm_gbs, bf16_tflops_sustained (operators timed inside the step)",
                  "ridge_flop_per_byte": ridge, "profiled_steps": steps, "op_ms_per_step": total / steps})
     return roof, table

@@ -1356,6 +1356,115 @@ int gwn_gcn_bwd(const gwn_gcn_desc* d, const float* dy, const float* x, const fl
   return gcn_hops_backward(gs, x, hops, sv, scratch, dx, nullptr, 0, dsupports, ldd, st);
 }
 
+// ---- per-sample-graph operators (model.py:16-22, 57-80): one launch group per sample over the sample's slab
+int gwn_nconv2_fwd(const float* x, const float* A, int64_t lda_b, int64_t lda, float* y, int B, int L, int V, int C,
+                   int precision, void* stream) {
+  GWN_TRY(require_device());
+  GWN_CHECK_ARG(x && A && y, "nconv2_fwd: null pointer");
+  GWN_CHECK_ARG(precision == GWN_PREC_FP32, "nconv2_fwd: precision %d not available in this build", precision);
+  const i64 slab = (i64)L * V * C;
+  for (int b = 0; b < B; ++b) {
+    SupportView sv = support_fwd(A + (i64)b * lda_b, lda, 1);
+    const float* X[1] = {x + b * slab};
+    float* Y[1] = {y + b * slab};
+    GWN_TRY(node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, 1, L, 0, V, C, (cudaStream_t)stream));
+  }
+  return 0;
+}
+
+int gwn_nconv2_bwd(const float* dy, const float* x, const float* A, int64_t lda_b, int64_t lda, float* dx, float* dA,
+                   int64_t ldda_b, int64_t ldda, int B, int L, int V, int C, int precision, void* stream) {
+  GWN_TRY(require_device());
+  GWN_CHECK_ARG(dy && A, "nconv2_bwd: null pointer");
+  GWN_CHECK_ARG(precision == GWN_PREC_FP32, "nconv2_bwd: precision %d not available in this build", precision);
+  GWN_CHECK_ARG(!dA || x, "nconv2_bwd: x needed for dA");
+  const i64 slab = (i64)L * V * C;
+  for (int b = 0; b < B; ++b) {
+    if (dx) {
+      SupportView sv = support_bwd(A + (i64)b * lda_b, lda, 1);
+      const float* X[1] = {dy + b * slab};
+      float* Y[1] = {dx + b * slab};
+      GWN_TRY(node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, 1, L, 0, V, C, (cudaStream_t)stream));
+    }
+    if (dA) {
+      const float* Xp[1] = {x + b * slab};
+      const float* Yp[1] = {dy + b * slab};
+      GWN_TRY(support_grad_gemm(Xp, Yp, 1, dA + (i64)b * ldda_b, ldda, 1, L, V, C, (cudaStream_t)stream));
+    }
+  }
+  return 0;
+}
+
+int gwn_gcn2_fwd(const gwn_gcn_desc* d, const float* x, const float* const* supports, const int64_t* lds_b, const int64_t* lds,
+                 const float* W, const float* bias, const uint8_t* keep_mask, float* hops, float* y, void* stream) {
+  GWN_TRY(require_device());
+  GWN_TRY(gcn_check(d));
+  GWN_CHECK_ARG(x && supports && lds && lds_b && W && bias && hops && y, "gcn2_fwd: null pointer");
+  GWN_CHECK_ARG(d->dropout_mode != GWN_DROPOUT_MASK || keep_mask, "gcn2_fwd: GWN_DROPOUT_MASK without keep_mask");
+  cudaStream_t st = (cudaStream_t)stream;
+  const i64 slab = (i64)d->L * d->V * d->C, PD = (i64)d->B * slab;
+  GcnShape g1{1, d->L, d->V, d->C, d->c_out, d->n_supports, d->order};
+  for (int b = 0; b < d->B; ++b) {
+    SupportView sv[MAXSUP];
+    for (int s = 0; s < d->n_supports; ++s) sv[s] = support_fwd(supports[s] + (i64)b * lds_b[s], lds[s], 1);
+    GWN_TRY(gcn_hops_forward(g1, x + b * slab, sv, hops + b * slab, st, nullptr, PD));
+  }
+  const i64 P = (i64)d->B * d->L * d->V;
+  const int nseg = 1 + d->n_supports * d->order;
+  const float* segs[MAXSEG];
+  segs[0] = x;
+  for (int q = 1; q < nseg; ++q) segs[q] = hops + (i64)(q - 1) * P * d->C;
+  MlpFwdArgs m;
+  memset(&m, 0, sizeof(m));
+  m.segs = segs; m.nseg = nseg; m.P = P; m.D = d->C; m.C_out = d->c_out; m.W = W; m.bias = bias;
+  m.drop = make_dropout(d->dropout_mode, keep_mask, d->seed, d->offset, d->dropout_p);
+  m.y = y;
+  return mlp_forward(m, st);
+}
+
+int gwn_gcn2_bwd(const gwn_gcn_desc* d, const float* dy, const float* x, const float* const* supports, const int64_t* lds_b,
+                 const int64_t* lds, const float* W, const uint8_t* keep_mask, const float* hops, float* dx, float* dW,
+                 float* dbias, float* const* dsupports, const int64_t* ldds_b, const int64_t* ldds, float* scratch,
+                 void* stream) {
+  GWN_TRY(require_device());
+  GWN_TRY(gcn_check(d));
+  GWN_CHECK_ARG(dy && x && supports && lds && lds_b && W && hops && dx && scratch, "gcn2_bwd: null pointer");
+  GWN_CHECK_ARG((dW == nullptr) == (dbias == nullptr), "gcn2_bwd: dW and dbias must be given together");
+  GWN_CHECK_ARG(!dsupports || (ldds_b && ldds), "gcn2_bwd: support-gradient strides missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  const i64 slab = (i64)d->L * d->V * d->C, PD = (i64)d->B * slab;
+  const i64 P = (i64)d->B * d->L * d->V;
+  const int nseg = 1 + d->n_supports * d->order;
+  const float* segs[MAXSEG];
+  segs[0] = x;
+  for (int q = 1; q < nseg; ++q) segs[q] = hops + (i64)(q - 1) * P * d->C;
+  MlpBwdArgs m;
+  memset(&m, 0, sizeof(m));
+  m.dh = dy;
+  m.drop = make_dropout(d->dropout_mode, keep_mask, d->seed, d->offset, d->dropout_p);
+  m.segs = segs; m.nseg = nseg; m.P = P; m.D = d->C; m.C_out = d->c_out; m.W = W;
+  m.dsegs = scratch; m.dW = dW; m.dbias = dbias;
+  if (dW) {
+    GWN_TRY(dev_memset(dW, 0, sizeof(float) * (size_t)d->c_out * nseg * d->C, st));
+    GWN_TRY(dev_memset(dbias, 0, sizeof(float) * (size_t)d->c_out, st));
+  }
+  GWN_TRY(mlp_backward(m, st));
+  GcnShape g1{1, d->L, d->V, d->C, d->c_out, d->n_supports, d->order};
+  for (int b = 0; b < d->B; ++b) {
+    SupportView sv[MAXSUP];
+    float* dsup[MAXSUP];
+    i64 ldd[MAXSUP];
+    for (int s = 0; s < d->n_supports; ++s) {
+      sv[s] = support_bwd(supports[s] + (i64)b * lds_b[s], lds[s], 1);
+      dsup[s] = (dsupports && dsupports[s]) ? dsupports[s] + (i64)b * ldds_b[s] : nullptr;
+      ldd[s] = ldds ? ldds[s] : d->V;
+    }
+    GWN_TRY(gcn_hops_backward(g1, x + b * slab, hops + b * slab, sv, scratch + b * slab, dx + b * slab, nullptr, 0, dsup, ldd,
+                              st, nullptr, nullptr, PD));
+  }
+  return 0;
+}
+
 int gwn_plan_create(const gwn_config* cfg, gwn_plan** out) {
   GWN_CHECK_ARG(cfg && out, "plan_create: null argument");
   gwn_plan* p = new gwn_plan();

@@ -316,9 +316,10 @@ struct GcnShape {
 inline int hop_index(const GcnShape& g, int s, int k) { return 1 + s * g.order + (k - 1); }  // cat order (model.py:42-52)
 
 // hops[q-1] (q >= 1) receives the q-th concatenated tensor; x is segment 0.
+// hop_stride (floats between consecutive hop tensors; 0 = B*L*V*D) lets a caller run one sample of a larger batch.
 inline int gcn_hops_forward(const GcnShape& g, const float* x, const SupportView* sup_fwd, float* hops,
-                            cudaStream_t stream, const TcSupports* tcs = nullptr) {
-  const i64 PD = (i64)g.B * g.L * g.V * g.D;
+                            cudaStream_t stream, const TcSupports* tcs = nullptr, i64 hop_stride = 0) {
+  const i64 PD = hop_stride > 0 ? hop_stride : (i64)g.B * g.L * g.V * g.D;
   ProfScope prof("nconv_fwd", stream, 4.0 * PD * (1 + g.S + 2.0 * g.S * (g.order - 1)), 2.0 * PD * g.V * g.S * g.order);
   for (int k = 1; k <= g.order; ++k) {
     const float* X[MAXSUP];
@@ -337,8 +338,9 @@ inline int gcn_hops_forward(const GcnShape& g, const float* x, const SupportView
 // dsup[s] (nullable) += sum_k hop_{s,k-1}^T t_{s,k}.
 inline int gcn_hops_backward(const GcnShape& g, const float* x, const float* hops, const SupportView* sup_bwd, float* dsegs,
                              float* dx, const float* add2, int T_out, float* const* dsup, const i64* ldds,
-                             cudaStream_t stream, const TcSupports* tcs = nullptr, const TcScratch* ts = nullptr) {
-  const i64 PD = (i64)g.B * g.L * g.V * g.D;
+                             cudaStream_t stream, const TcSupports* tcs = nullptr, const TcScratch* ts = nullptr,
+                             i64 hop_stride = 0) {
+  const i64 PD = hop_stride > 0 ? hop_stride : (i64)g.B * g.L * g.V * g.D;
   {
     ProfScope prof("nconv_bwd_dx_hops", stream, 4.0 * PD * 3.0 * g.S * (g.order - 1), 2.0 * PD * g.V * g.S * (g.order - 1));
     for (int k = g.order; k >= 2; --k) {

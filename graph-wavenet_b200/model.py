@@ -261,27 +261,144 @@ class gcn(nn.Module):
                             self.precision, self._keep_mask, seed, *support)
 
 
-# ============================================================================== per-sample-graph variants
-class _NotOnHotPath(nn.Module):
-    _what = ""
+# ============================================================================== per-sample-graph operators
+class _Nconv2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, A, precision):
+        _require_cuda(x, "nconv2 input")
+        _require_cuda(A, "nconv2 support")
+        lib = _N.get_lib()
+        B, C, V, L = x.shape
+        if A.dim() != 3 or tuple(A.shape) != (B, V, V):
+            raise RuntimeError(f"nconv2: support must be [{B},{V},{V}] (one graph per sample), got {tuple(A.shape)}")
+        if C % 4:
+            raise RuntimeError("nconv2: channel count must be a multiple of 4")
+        xb = _to_blnc(x)
+        Ac = A.contiguous()
+        yb = torch.empty_like(xb)
+        with torch.cuda.device(x.device):
+            lib.check(lib.dll.gwn_nconv2_fwd(xb.data_ptr(), Ac.data_ptr(), V * V, V, yb.data_ptr(), B, L, V, C, precision,
+                                             _stream(x)), "gwn_nconv2_fwd")
+        ctx.save_for_backward(xb, Ac)
+        ctx.precision = precision
+        return _blnc_to_nchw(yb)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xb, Ac = ctx.saved_tensors
+        lib = _N.get_lib()
+        B, L, V, C = xb.shape
+        gyb = _to_blnc(gy)
+        need_x, need_A = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dxb = torch.empty_like(xb) if need_x else None
+        dA = torch.zeros_like(Ac) if need_A else None
+        with torch.cuda.device(gy.device):
+            lib.check(lib.dll.gwn_nconv2_bwd(gyb.data_ptr(), xb.data_ptr(), Ac.data_ptr(), V * V, V,
+                                             dxb.data_ptr() if need_x else None, dA.data_ptr() if need_A else None, V * V, V,
+                                             B, L, V, C, ctx.precision, _stream(gy)), "gwn_nconv2_bwd")
+        return (_blnc_to_nchw(dxb) if need_x else None), dA, None
+
+
+class nconv2(nn.Module):
+    """model.py:16-22 -- ``einsum('ncvl,nvw->ncwl')`` + ``.contiguous()``: one support per sample."""
+
+    def __init__(self):
+        super(nconv2, self).__init__()
+        self.precision = _op_precision()
+
+    def forward(self, x, A):
+        return _Nconv2Fn.apply(x, A, self.precision)
+
+
+class _Gcn2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, order, p, training, precision, keep_mask, seed, *supports):
+        import ctypes
+        _require_cuda(x, "gcn2 input")
+        lib = _N.get_lib()
+        B, Cin, V, L = x.shape
+        S = len(supports)
+        Cout = weight.shape[0]
+        if weight.shape[1] != (order * S + 1) * Cin:
+            raise RuntimeError(f"gcn2: mlp expects {(order * S + 1) * Cin} input channels, weight has {weight.shape[1]}")
+        for a in supports:
+            if tuple(a.shape) != (B, V, V):
+                raise RuntimeError(f"gcn2: every support must be [{B},{V},{V}], got {tuple(a.shape)}")
+        xb = _to_blnc(x)
+        sup = [s.contiguous() for s in supports]
+        w = weight.contiguous()
+        hops = torch.empty((order * S, B, L, V, Cin), dtype=torch.float32, device=x.device)
+        yb = torch.empty((B, L, V, Cout), dtype=torch.float32, device=x.device)
+        mode = _N.DROPOUT_NONE
+        if training and p > 0:
+            mode = _N.DROPOUT_MASK if keep_mask is not None else _N.DROPOUT_PHILOX
+        d = _N.GwnGcnDesc(B, L, V, Cin, Cout, S, order, precision, mode, float(p), int(seed), 0)
+        sp = _N.ptr_array([s.data_ptr() for s in sup])
+        lds = (ctypes.c_int64 * max(S, 1))(*[V] * S)
+        ldb = (ctypes.c_int64 * max(S, 1))(*[V * V] * S)
+        with torch.cuda.device(x.device):
+            lib.check(lib.dll.gwn_gcn2_fwd(ctypes.byref(d), xb.data_ptr(), sp, ldb, lds, w.data_ptr(), bias.data_ptr(),
+                                           keep_mask.data_ptr() if keep_mask is not None else None, hops.data_ptr(),
+                                           yb.data_ptr(), _stream(x)), "gwn_gcn2_fwd")
+        ctx.save_for_backward(xb, w, hops, *sup)
+        ctx.desc, ctx.keep_mask = d, keep_mask
+        return _blnc_to_nchw(yb)
+
+    @staticmethod
+    def backward(ctx, gy):
+        import ctypes
+        xb, w, hops, *sup = ctx.saved_tensors
+        lib = _N.get_lib()
+        d = ctx.desc
+        S, V = d.n_supports, d.V
+        gyb = _to_blnc(gy)
+        dxb = torch.empty_like(xb)
+        dW = torch.empty_like(w)
+        db = torch.empty(d.c_out, dtype=torch.float32, device=gy.device)
+        need = ctx.needs_input_grad[9:]
+        dsup = [torch.zeros_like(s) if n else None for s, n in zip(sup, need)]
+        scratch = torch.empty(lib.dll.gwn_gcn_bwd_scratch_floats(ctypes.byref(d)), dtype=torch.float32, device=gy.device)
+        sp = _N.ptr_array([s.data_ptr() for s in sup])
+        dsp = _N.ptr_array([t.data_ptr() if t is not None else None for t in dsup])
+        lds = (ctypes.c_int64 * max(S, 1))(*[V] * S)
+        ldb = (ctypes.c_int64 * max(S, 1))(*[V * V] * S)
+        km = ctx.keep_mask
+        with torch.cuda.device(gy.device):
+            lib.check(lib.dll.gwn_gcn2_bwd(ctypes.byref(d), gyb.data_ptr(), xb.data_ptr(), sp, ldb, lds, w.data_ptr(),
+                                           km.data_ptr() if km is not None else None, hops.data_ptr(), dxb.data_ptr(),
+                                           dW.data_ptr(), db.data_ptr(), dsp, ldb, lds, scratch.data_ptr(), _stream(gy)),
+                      "gwn_gcn2_bwd")
+        return (_blnc_to_nchw(dxb), dW, db, None, None, None, None, None, None, *dsup)
+
+
+class gcn2(nn.Module):
+    """model.py:57-80 -- ``gcn`` with one support set per sample (supports are ``[B,V,V]`` tensors)."""
+
+    def __init__(self, c_in, c_out, dropout, support_len=3, order=2):
+        super(gcn2, self).__init__()
+        self.nconv = nconv2()
+        c_in = (order * support_len + 1) * c_in
+        self.mlp = linear(c_in, c_out)
+        self.dropout = dropout
+        self.order = order
+        self.precision = _op_precision()
+        self._keep_mask = None     # test hook, as in gcn
+
+    def forward(self, x, support):
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (self.training and self.dropout > 0) else 0
+        return _Gcn2Fn.apply(x, self.mlp.mlp.weight, self.mlp.mlp.bias, self.order, self.dropout, self.training,
+                             self.precision, self._keep_mask, seed, *support)
+
+
+class gwnet_diff_G(nn.Module):
+    """model.py:244-407 (the fork's per-sample-graph network) is NOT part of this round: its operators ``nconv2`` /
+    ``gcn2`` above run natively, the network around them -- which re-randomises its node embeddings inside ``forward`` and
+    stops in a debugger in the reference (model.py:324-332) -- is SURVEY.md section 8(f) row 2 'next'."""
 
     def __init__(self, *a, **k):
         super().__init__()
-        raise NotImplementedError(
-            f"{self._what} (per-sample adjacency, model.py:16-22,57-80,244-407) is outside the gwnet hot path this "
-            "package accelerates (SURVEY.md §8(f) row 2); use the reference implementation for it")
-
-
-class nconv2(_NotOnHotPath):
-    _what = "nconv2"
-
-
-class gcn2(_NotOnHotPath):
-    _what = "gcn2"
-
-
-class gwnet_diff_G(_NotOnHotPath):
-    _what = "gwnet_diff_G"
+        raise NotImplementedError("gwnet_diff_G (model.py:244-407) is outside the accelerated hot path of this round "
+                                  "(SURVEY.md section 8(f) row 2); nconv2 / gcn2 are available as native operators")
 
 
 # ============================================================================== gwnet

@@ -83,6 +83,7 @@ EXPORTS = [
     "gwn_last_error", "gwn_abi_version", "gwn_launch_count", "gwn_device_info", "gwn_profile_begin", "gwn_profile_end", "gwn_permute4d",
     "gwn_node_contract", "gwn_tc_error_flag", "gwn_tc_debug_buffer", "gwn_tc_debug_mode", "gwn_nconv_fwd", "gwn_nconv_bwd", "gwn_linear_fwd", "gwn_linear_bwd",
     "gwn_gcn_fwd", "gwn_gcn_bwd_scratch_floats", "gwn_gcn_bwd",
+    "gwn_nconv2_fwd", "gwn_nconv2_bwd", "gwn_gcn2_fwd", "gwn_gcn2_bwd",
     "gwn_plan_create", "gwn_plan_destroy", "gwn_plan_workspace_bytes", "gwn_plan_param_count",
     "gwn_plan_param_info", "gwn_plan_out_len", "gwn_plan_debug_layout", "gwn_plan_forward", "gwn_plan_backward",
     "gwn_train_ctrl_bytes", "gwn_train_ctrl_init", "gwn_train_ctrl_read", "gwn_plan_train_fwd_bwd", "gwn_plan_eval_metrics", "gwn_adam_step",
@@ -135,6 +136,12 @@ class Lib:
         d.gwn_gcn_bwd_scratch_floats.restype = C.c_size_t
         d.gwn_gcn_bwd.argtypes = ([C.POINTER(GwnGcnDesc), C.c_void_p, C.c_void_p, c_void_pp, i64p] + [C.c_void_p] * 6
                                   + [c_void_pp, i64p, C.c_void_p, C.c_void_p])
+        d.gwn_nconv2_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+        d.gwn_nconv2_bwd.argtypes = ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.c_int64] + [C.c_int] * 5 + [C.c_void_p])
+        d.gwn_gcn2_fwd.argtypes = [C.POINTER(GwnGcnDesc), C.c_void_p, c_void_pp, i64p, i64p] + [C.c_void_p] * 6
+        d.gwn_gcn2_bwd.argtypes = ([C.POINTER(GwnGcnDesc), C.c_void_p, C.c_void_p, c_void_pp, i64p, i64p] + [C.c_void_p] * 6
+                                   + [c_void_pp, i64p, i64p, C.c_void_p, C.c_void_p])
         d.gwn_plan_create.argtypes = [C.POINTER(GwnConfig), C.POINTER(C.c_void_p)]
         d.gwn_plan_destroy.argtypes = [C.c_void_p]
         d.gwn_plan_destroy.restype = None

@@ -133,6 +133,21 @@ int gwn_gcn_bwd(const gwn_gcn_desc* d, const float* dy, const float* x, const fl
                 const float* W, const uint8_t* keep_mask, const float* hops, float* dx, float* dW, float* dbias,
                 float* const* dsupports, const int64_t* ldds, float* scratch, void* stream);
 
+/* ------------------------------------------------------------------ nconv2 / gcn2 (model.py:16-22, 57-80)
+ * The per-sample-graph operators of the fork: y[b,l,w,c] = sum_v x[b,l,v,c] * A[b][v,w], one [V,V] support per sample
+ * (A: [B,V,V], sample stride lda_b, row stride lda).  Same semantics as gwn_nconv_* / gwn_gcn_* otherwise; the supports
+ * of gwn_gcn2_* are `n_supports` tensors [B,V,V]; dsupports[s] (nullable) are accumulated into, same layout.        */
+int gwn_nconv2_fwd(const float* x, const float* A, int64_t lda_b, int64_t lda, float* y, int B, int L, int V, int C,
+                   int precision, void* stream);
+int gwn_nconv2_bwd(const float* dy, const float* x, const float* A, int64_t lda_b, int64_t lda, float* dx, float* dA,
+                   int64_t ldda_b, int64_t ldda, int B, int L, int V, int C, int precision, void* stream);
+int gwn_gcn2_fwd(const gwn_gcn_desc* d, const float* x, const float* const* supports, const int64_t* lds_b, const int64_t* lds,
+                 const float* W, const float* bias, const uint8_t* keep_mask, float* hops, float* y, void* stream);
+int gwn_gcn2_bwd(const gwn_gcn_desc* d, const float* dy, const float* x, const float* const* supports, const int64_t* lds_b,
+                 const int64_t* lds, const float* W, const uint8_t* keep_mask, const float* hops, float* dx, float* dW,
+                 float* dbias, float* const* dsupports, const int64_t* ldds_b, const int64_t* ldds, float* scratch,
+                 void* stream);
+
 /* ------------------------------------------------------------------ gwnet (model.py:82-241)
  * Whole-network plan: replaces gwnet.forward and its autograd graph.                 */
 typedef struct gwn_config {

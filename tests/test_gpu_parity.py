@@ -444,3 +444,52 @@ def test_device_feed_and_fused_eval(M, monkeypatch):
     want = rec["trainer_metrics"].tolist()[0]                          # first batch = the golden batch, first step
     for u, v in zip(runs["fused"][0], want):
         assert abs(u - v) <= 1e-4 * abs(v) + 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ per-sample-graph operators
+def test_nconv2_gcn2_operators(M):
+    """model.py:16-22,57-80: one support per sample (einsum 'ncvl,nvw->ncwl'); forward and every gradient vs torch fp64."""
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(11)
+    B, C, V, L, S, order = 5, 32, 37, 6, 2, 2
+    x = torch.randn(B, C, V, L, generator=gen)
+    A = [torch.softmax(torch.randn(B, V, V, generator=gen), dim=2) for _ in range(S)]
+    # nconv2
+    xd = x.to(dev).requires_grad_(True)
+    Ad = A[0].to(dev).requires_grad_(True)
+    y = M.nconv2()(xd, Ad)
+    probe = torch.randn(y.shape, generator=gen)
+    (y * probe.to(dev)).sum().backward()
+    x64, A64 = x.double().requires_grad_(True), A[0].double().requires_grad_(True)
+    y64 = torch.einsum("ncvl,nvw->ncwl", x64, A64).contiguous()
+    (y64 * probe.double()).sum().backward()
+    assert y.is_contiguous()
+    assert_close_rel(y, y64, TOL, "nconv2 output")
+    assert_close_rel(xd.grad, x64.grad, TOL, "nconv2 dx")
+    assert_close_rel(Ad.grad, A64.grad, TOL, "nconv2 dA")
+    # gcn2 (eval mode: no dropout)
+    g = M.gcn2(C, 32, 0.3, support_len=S, order=order).to(dev).eval()
+    xd = x.to(dev).requires_grad_(True)
+    Ads = [a.to(dev).requires_grad_(True) for a in A]
+    h = g(xd, Ads)
+    probe = torch.randn(h.shape, generator=gen)
+    (h * probe.to(dev)).sum().backward()
+    W64 = g.mlp.mlp.weight.detach().cpu().double().requires_grad_(True)
+    b64 = g.mlp.mlp.bias.detach().cpu().double().requires_grad_(True)
+    x64 = x.double().requires_grad_(True)
+    A64s = [a.double().requires_grad_(True) for a in A]
+    out = [x64]
+    for a in A64s:
+        x1 = torch.einsum("ncvl,nvw->ncwl", x64, a)
+        out.append(x1)
+        for _ in range(2, order + 1):
+            x1 = torch.einsum("ncvl,nvw->ncwl", x1, a)
+            out.append(x1)
+    h64 = torch.nn.functional.conv2d(torch.cat(out, dim=1), W64, b64)
+    (h64 * probe.double()).sum().backward()
+    assert_close_rel(h, h64, TOL, "gcn2 output")
+    assert_close_rel(xd.grad, x64.grad, TOL, "gcn2 dx")
+    assert_close_rel(g.mlp.mlp.weight.grad, W64.grad, TOL, "gcn2 dW")
+    assert_close_rel(g.mlp.mlp.bias.grad, b64.grad, TOL, "gcn2 db")
+    for s in range(S):
+        assert_close_rel(Ads[s].grad, A64s[s].grad, TOL, f"gcn2 dA[{s}]")

@@ -65,6 +65,9 @@ def contraction(V, B, L, iters=5):
 
 if __name__ == "__main__":
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+    if len(sys.argv) > 1 and sys.argv[1] == "contraction_only":
+        contraction(2048, 8, 24, iters=2)
+        sys.exit(0)
     step_time("METR-LA", 207, 64, 12, gflop=217.4)
     step_time("PEMS-BAY aptonly", 325, 64, 12, aptonly=True, gflop=249.9)
     step_time("CRASH N=200 T=12", 200, 64, 12, gflop=205.9)
