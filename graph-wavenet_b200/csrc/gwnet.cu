@@ -719,6 +719,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
   float* dskip = sc + p->o_dskip;
   float* dgh = sc + p->o_dgh;
   GWN_CHECK_ARG(PT < 2147483647LL, "backward: too many output positions");
+  TcScratch tsc{p->part_floats > 0 ? sc + p->o_part : nullptr, p->part_floats, x3(p) ? 1 : 0};
   bool hb_tc = false;
 #if !GWN_EMU
   if (p->head_tc) {   // the three input-gradient GEMMs of the head on tcgen05 (weight gradients below stay on the generic kernel)
@@ -791,7 +792,66 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     GemmShape sh{PT, E, O, 1, 1};
     GWN_TRY((launch_gemm<TBig>(la, lb, ep, sh, st)));
   }
-  {  // (b) dW2, db2
+  bool hw_tc = false;   // head weight gradients on the tcgen05 reduction kernel
+#if !GWN_EMU
+  auto head_wgrad_tc = [&](const TcRedSrc* ablk, int na, const TcRedSrc& bsrc, int Ntot, int n_valid, int nb_, int rows_,
+                           float* const* blk, i64 sn, float* const* bias, int nbias) -> int {
+    if (!tsc.partial || na > TR_MAXSRC) return -1;
+    TcRedArgs t;
+    memset(&t, 0, sizeof(t));
+    t.mode = 0; t.na = na; t.x3 = tsc.x3;
+    for (int j = 0; j < na; ++j) t.a[j] = ablk[j];
+    t.b[0] = bsrc;
+    t.ab = tsc.x3 ? 4 : 7;
+    t.N = Ntot <= (tsc.x3 ? 128 : 256) ? Ntot : (tsc.x3 ? 128 : 256);
+    t.N_total = Ntot; t.nb = nb_; t.rows = rows_; t.partial = tsc.partial; t.partial_floats = tsc.floats;
+    TcRedResult r;
+    int rs = launch_tcred(t, st, &r);
+    if (rs != 0) return rs;
+    tc::SlotGridOut f;
+    memset(&f, 0, sizeof(f));
+    for (int j = 0; j < na; ++j) f.blk[j] = blk[j];
+    for (int q = 0; q < nbias; ++q) f.bias[q] = bias[q];
+    f.nbias = nbias; f.na = na; f.ab = t.ab < na ? t.ab : na; f.n_ag = r.n_mg; f.n_bg = r.n_nt; f.Ntile = r.N; f.Ntot = Ntot;
+    f.n_valid = n_valid; f.sn = sn; f.si = 1;
+    return launch_slot_reduce(tsc.partial, r, (i64)na * 32 * Ntot + Ntot, f, st);
+  };
+  if (hb_tc && E % 32 == 0 && E / 32 <= TR_MAXSRC && Sk / 32 <= TR_MAXSRC && O <= 32) {
+    int rs;
+    {  // (b) dW2[o][e] = sum_p dout[p][o] e1[p][e], db2[o] = sum_p dout[p][o]
+      TcRedSrc ab_[TR_MAXSRC];
+      float* blk[TR_MAXSRC];
+      for (int j = 0; j < E / 32; ++j) { ab_[j] = TcRedSrc{e1, (int)PT, E, 32 * j, 0, 0}; blk[j] = G(p->i_e2w) + 32 * j; }
+      float* bias[1] = {G(p->i_e2b)};
+      rs = head_wgrad_tc(ab_, E / 32, TcRedSrc{dout, (int)PT, p->ldo, 0, 0, 0}, 32, O, 1, (int)PT, blk, E, bias, 1);
+      if (rs > 0) return rs;
+    }
+    if (rs == 0) {  // (d) dW1[e][sk] = sum_p de1[p][e] skip[p][sk], db1[e] = sum_p de1[p][e]
+      TcRedSrc ab_[TR_MAXSRC];
+      float* blk[TR_MAXSRC];
+      for (int j = 0; j < Sk / 32; ++j) { ab_[j] = TcRedSrc{skip, (int)PT, Sk, 32 * j, 0, 0}; blk[j] = G(p->i_e1w) + 32 * j; }
+      float* bias[1] = {G(p->i_e1b)};
+      rs = head_wgrad_tc(ab_, Sk / 32, TcRedSrc{de1, (int)PT, E, 0, 0, 0}, E, E, 1, (int)PT, blk, Sk, bias, 1);
+      if (rs > 0) return rs;
+      GWN_CHECK_ARG(rs == 0, "backward: head weight gradient (d) not eligible for the tcgen05 path");
+    }
+    if (rs == 0) {  // (e) dWskip_i[sk][c] = sum_p dskip[p][sk] g_i[live p][c], dbskip_i[sk] = sum_p dskip[p][sk]
+      TcRedSrc ab_[TR_MAXSRC];
+      float* blk[TR_MAXSRC];
+      float* bias[TR_MAXSRC];
+      for (int i = 0; i < nL; ++i) {
+        ab_[i] = TcRedSrc{ws + p->o_g[i], p->L[i] * N, 32, 0, (p->L[i] - p->T_out) * N, 0};
+        blk[i] = G(p->li[i].sw);
+        bias[i] = G(p->li[i].sb);
+      }
+      rs = head_wgrad_tc(ab_, nL, TcRedSrc{dskip, p->T_out * N, Sk, 0, 0, 0}, Sk, Sk, B, p->T_out * N, blk, D, bias, nL);
+      if (rs > 0) return rs;
+      GWN_CHECK_ARG(rs == 0, "backward: head weight gradient (e) not eligible for the tcgen05 path");
+      hw_tc = true;
+    }
+  }
+#endif
+  if (!hw_tc) {  // (b) dW2, db2
     LdCols la;
     memset(&la, 0, sizeof(la));
     la.p[0] = dout; la.set_wd(p->ldo); la.nseg = 1;
@@ -817,7 +877,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     GemmShape sh{PT, Sk, E, 1, 1};
     GWN_TRY((launch_gemm<TBig>(la, lb, ep, sh, st)));
   }
-  {  // (d) dW1, db1
+  if (!hw_tc) {  // (d) dW1, db1
     LdCols la;
     memset(&la, 0, sizeof(la));
     la.p[0] = de1; la.set_wd(E); la.nseg = 1;
@@ -850,7 +910,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     lb.set_wd(D); lb.nseg = nL; lb.use_remap = 1; lb.ones = 1;
     ep.set_wd(D); ep.nseg = nL; ep.ldw = D; ep.nbias = nL;
     GemmShape sh{(i64)Sk, nL * D + 1, (int)PT, pick_ksplit(Sk, nL * D + 1, PT, TBig::BM, TBig::BN, kTargetBlocks), 1};
-    GWN_TRY((launch_gemm<TBig>(la, lb, ep, sh, st)));
+    if (!hw_tc) GWN_TRY((launch_gemm<TBig>(la, lb, ep, sh, st)));
 
     if (!hb_tc) {
       LdRows lr;
@@ -870,7 +930,6 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
   float* cur = sc + p->o_buf0;   // holds d(loss)/d(x_{i+1}) on entry of layer i (unused for the last layer)
   float* oth = sc + p->o_buf1;
   float* dg = sc + p->o_dg;
-  TcScratch tsc{p->part_floats > 0 ? sc + p->o_part : nullptr, p->part_floats, x3(p) ? 1 : 0};
   const float* dA_X[TR_MAXSRC];
   const float* dA_T[TR_MAXSRC];
   int dA_slabs[TR_MAXSRC], dA_pairs = 0;

@@ -30,7 +30,10 @@ struct TcRedArgs {
   TcRedSrc a[TR_MAXSRC];
   int na;             // MODE_MN: real A blocks (<= 7; the ones block is appended); MODE_K: number of (X, T) pairs
   TcRedSrc b[TR_MAXSRC];   // MODE_MN: b[0] only; MODE_K: one per pair
-  int N;              // MODE_MN: 32 or 64; MODE_K: ignored (derived from rows)
+  int N;              // MODE_MN: B columns per CTA tile (multiple of 32, <= 256); MODE_K: ignored (derived from rows)
+  int ab;             // MODE_MN: real A blocks per CTA tile (0 = all `na`, at most 7); the output is tiled
+                      //   ceil(na/ab) block groups x (N_total/N) column groups, each with its own K-split CTAs
+  int N_total;        // MODE_MN: B columns in total (0 = N)
   int nb, rows;       // MODE_MN: samples and B rows per sample; MODE_K: default slabs per pair, rows = V
   float* partial;     // scratch for the per-CTA partial results
   i64 partial_floats; // its capacity
@@ -54,6 +57,7 @@ struct TrParams {
   int mode, na, nblk, mtiles, N, nbn, nb, chunks_per_sample, total_chunks, stages, a_bytes, b_bytes, tx_bytes, n_nt, n_mg;
   int acol0[TR_MAXSRC], arshift[TR_MAXSRC], bcol0[TR_MAXSRC];
   int pair_end[TR_MAXSRC];   // MODE_K: cumulative chunk (slab) counts per pair
+  int ab;                    // MODE_MN: real A blocks per block group
   float* partial;
   i64 slot_floats;
 };
@@ -78,22 +82,27 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // output tile of this CTA: (k split, row/block group mg, column group ntile)
+  const int n_ot = p.n_nt * p.n_mg;
+  const int ot = (int)(blockIdx.x % n_ot), ntile = ot % p.n_nt, mg = ot / p.n_nt;
+  const int kslot = (int)(blockIdx.x / n_ot), nk = (int)(gridDim.x / n_ot);
+  const int na_loc = p.mode == 0 ? min(p.ab, p.na - mg * p.ab) : 0;   // MODE_MN: real A blocks of this block group
   if (p.mode == 0) {
-    // A blocks that TMA never writes: block `na` of every stage is the all-ones block (its accumulator rows become
+    // A blocks that TMA never writes: block `na_loc` of every stage is the all-ones block (its accumulator rows become
     // the column sums of B = the bias gradient); blocks beyond it are zero.
     for (int s = 0; s < p.stages; ++s) {
-      float* blk = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + (size_t)p.na * 4096);
-      const int nfill = (p.mtiles * 4 - p.na) * 1024;
+      float* blk = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + (size_t)na_loc * 4096);
+      const int nfill = (p.mtiles * 4 - na_loc) * 1024;
       for (int i = threadIdx.x; i < nfill; i += 256) blk[i] = i < 1024 ? 1.0f : 0.0f;
       if (X3) {   // their remainders are zero
-        float* lo = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + plane_bytes + (size_t)p.na * 4096);
+        float* lo = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + plane_bytes + (size_t)na_loc * 4096);
         for (int i = threadIdx.x; i < nfill; i += 256) lo[i] = 0.0f;
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
   }
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.na; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[s]) : "memory");
+    for (int s = 0; s < (p.na < TR_MAXSRC ? p.na : TR_MAXSRC); ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[s]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[0]) : "memory");
   }
   if (warp == 1 && lane == 0) {
@@ -115,9 +124,6 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
   const uint32_t tmem_base = *tmem_slot;
 
   // contiguous chunk range of this CTA (MODE_K: CTAs are split over n_nt column tiles of the output)
-  const int n_ot = p.n_nt * p.n_mg;   // output tiles; CTA = (k split, row group, column tile)
-  const int ot = (int)(blockIdx.x % n_ot), ntile = ot % p.n_nt, mg = ot / p.n_nt;
-  const int kslot = (int)(blockIdx.x / n_ot), nk = (int)(gridDim.x / n_ot);
   const int c_beg = (int)((long long)p.total_chunks * kslot / nk);
   const int c_end = (int)((long long)p.total_chunks * (kslot + 1) / nk);
 
@@ -129,11 +135,14 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     for (int c = c_beg; c < c_end; ++c) {
       if (!mbar_wait(empty_bar(stage), phase ^ 1u, 21)) break;
       const uint32_t sa = st0 + stage * stage_bytes, sb = sa + p.a_bytes;
-      mbar_expect_tx(full_bar(stage), (uint32_t)p.tx_bytes);
+      mbar_expect_tx(full_bar(stage), p.mode == 0 ? (uint32_t)((na_loc + p.nbn) * 4096) : (uint32_t)p.tx_bytes);
       if (p.mode == 0) {
         const int b = c / p.chunks_per_sample, r0 = (c - b * p.chunks_per_sample) * 32;
-        for (int j = 0; j < p.na; ++j) tma_load_3d(sa + j * 4096, &maps.a[j], full_bar(stage), p.acol0[j], r0 + p.arshift[j], b);
-        for (int j = 0; j < p.nbn; ++j) tma_load_3d(sb + j * 4096, &maps.b[0], full_bar(stage), p.bcol0[j], r0, b);
+        for (int j = 0; j < na_loc; ++j) {
+          const int jj = mg * p.ab + j;
+          tma_load_3d(sa + j * 4096, &maps.a[jj], full_bar(stage), p.acol0[jj], r0 + p.arshift[jj], b);
+        }
+        for (int j = 0; j < p.nbn; ++j) tma_load_3d(sb + j * 4096, &maps.b[0], full_bar(stage), p.bcol0[0] + ntile * p.N + 32 * j, r0, b);
       } else {
         while (c >= p.pair_end[pair]) ++pair;
         const int slab = c - (pair ? p.pair_end[pair - 1] : 0);
@@ -187,7 +196,7 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     const int t64 = threadIdx.x - 64;
     int stage = 0;
     uint32_t phase = 0;
-    const int a_live = (p.mode == 0 ? p.na * 4096 : p.a_bytes) / 16, b_live = p.b_bytes / 16;
+    const int a_live = (p.mode == 0 ? na_loc * 4096 : p.a_bytes) / 16, b_live = p.b_bytes / 16;
     for (int c = c_beg; c < c_end; ++c) {
       if (!mbar_wait(full_bar(stage), phase, 25)) break;
       uint8_t* sp = smem + (size_t)stage * stage_bytes;
@@ -313,6 +322,39 @@ struct SlotTcnOut {
     }
   }
 };
+// Tiled MODE_MN result (head weight gradients): element (j, i, n) of global A block j -> blk[j][n*sn + i*si]; the ones
+// block of block group 0 delivers the column sums of B to every bias[q][n].  Slot = (k split, block group, column group).
+struct SlotGridOut {
+  float* blk[TR_MAXSRC];
+  float* bias[TR_MAXSRC];
+  int nbias, na, ab, n_ag, n_bg, Ntile, Ntot, n_valid;   // n_valid: B columns that exist (the rest were zero-filled)
+  i64 sn, si;
+  __device__ __forceinline__ void where(i64 i, i64& off, i64& off2, int& slot0, int& step) const {
+    const i64 nw = (i64)na * 32 * Ntot;
+    int lb, ii, n, ga;
+    if (i < nw) {
+      const int j = (int)(i / (32 * Ntot)), r = (int)(i - (i64)j * 32 * Ntot);
+      ii = r / Ntot; n = r - ii * Ntot; ga = j / ab; lb = j - ga * ab;
+    } else {
+      n = (int)(i - nw); ii = 0; ga = 0; lb = ab < na ? ab : na;   // the ones block follows the real blocks of group 0
+    }
+    const int gb = n / Ntile, ln = n - gb * Ntile;
+    off = (i64)(lb * 32 + ii) * Ntile + ln;
+    off2 = -1; slot0 = ga * n_bg + gb; step = n_ag * n_bg;
+  }
+  __device__ __forceinline__ void store(i64 i, float s0, float) const {
+    const i64 nw = (i64)na * 32 * Ntot;
+    if (i < nw) {
+      const int j = (int)(i / (32 * Ntot)), r = (int)(i - (i64)j * 32 * Ntot);
+      const int ii = r / Ntot, n = r - ii * Ntot;
+      if (n < n_valid) blk[j][(size_t)n * sn + (size_t)ii * si] += s0;
+    } else {
+      const int n = (int)(i - nw);
+      if (n < n_valid)
+        for (int q = 0; q < nbias; ++q) bias[q][n] += s0;
+    }
+  }
+};
 // support gradient: a slot holds output rows (mg*MR .. +MR) x columns (nt*Ntile .. +Ntile); slot index =
 // (k split * n_mg + mg) * n_nt + nt
 struct SlotSupOut {
@@ -360,14 +402,20 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
     return n;
   }();
   if (a.mode == 0) {
-    if (a.na > 7 || (a.N != 32 && a.N != 64) || a.nb < 1) return -1;
+    const int ab = a.ab > 0 ? a.ab : a.na;
+    const int Ntot = a.N_total > 0 ? a.N_total : a.N;
+    if (ab > 7 || ab < 1 || a.N % 32 != 0 || a.N < 32 || a.N > 256 || Ntot % a.N != 0 || a.nb < 1) return -1;
     p.N = a.N;
-    p.nblk = a.na + 1;                       // + the all-ones block
+    p.ab = ab;
+    p.n_mg = (a.na + ab - 1) / ab;             // block groups
+    p.n_nt = Ntot / a.N;                       // column groups
+    p.nblk = ab + 1;                           // + the all-ones block
     p.mtiles = (p.nblk + 3) / 4;
+    if (p.mtiles * a.N > 512) return -1;       // TMEM columns
     p.nbn = a.N / 32;
     p.a_bytes = p.mtiles * 16384;
     p.b_bytes = p.nbn * 4096;
-    p.tx_bytes = (a.na + p.nbn) * 4096;
+    p.tx_bytes = (ab + p.nbn) * 4096;
     p.chunks_per_sample = (a.rows + 31) / 32;
     const long long tot = (long long)p.chunks_per_sample * a.nb;
     if (tot > 2147483647LL) return -1;
@@ -384,7 +432,7 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
     }
     {
       const TcRedSrc& g = a.b[0];
-      if ((reinterpret_cast<uintptr_t>(g.src) & 15) || g.row_width % 4 || a.N > g.row_width) return -1;
+      if ((reinterpret_cast<uintptr_t>(g.src) & 15) || g.row_width % 4 || g.col0 >= g.row_width) return -1;   // short rows read zeros
       cuuint64_t d[3] = {(cuuint64_t)g.row_width, (cuuint64_t)g.rows_src, (cuuint64_t)a.nb};
       cuuint64_t st[2] = {(cuuint64_t)g.row_width * 4, (cuuint64_t)g.rows_src * g.row_width * 4};
       cuuint32_t box[3] = {32, 32, 1};
