@@ -123,7 +123,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
       const int nk_total = (p.kcat ? p.nsup : 1) * p.nkb;
       for (int it = 0; it < nk_total; ++it) {
         if (!mbar_wait(full_bar(stage), phase, 3)) { ok = false; break; }
-        if (X3 && !mbar_wait(split_bar(stage), phase, 5)) { ok = false; break; }
         tc_fence_after();
         if (p.dbg && blockIdx.x == 0 && tile == 0 && it == 0) {
           const float* sm = reinterpret_cast<const float*>(smem + (size_t)stage * stage_bytes);
@@ -144,10 +143,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
           // B (support, K-major): rows of 128 B (32 k), 8-row groups 1024 B apart; this k-step starts 32 B in
           const uint64_t bdesc = make_desc(bs + kk * (UMMA_K * 4), 16, 1024);
           if (p.mode != 1) tc_mma_tf32(d_tmem, adesc, bdesc, idesc_k, (it > 0 || kk > 0) ? 1u : 0u);
-          if (X3) {
-            tc_mma_tf32(d_tmem, adesc, make_desc(bs + s_tile + kk * (UMMA_K * 4), 16, 1024), idesc_k, 1u);
-            tc_mma_tf32(d_tmem, make_desc(xs + X_STAGE_BYTES + kk * (UMMA_K * 128), BLOCK_K * 128, 4 * 128, 1), bdesc, idesc_k, 1u);
-          }
+          if (X3) tc_mma_tf32(d_tmem, adesc, make_desc(bs + s_tile + kk * (UMMA_K * 4), 16, 1024), idesc_k, 1u);
+        }
+        if (X3) {   // the X_lo term last: the split of this stage ran while the eight MMAs above were issued
+          if (!mbar_wait(split_bar(stage), phase, 5)) { ok = false; break; }
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+            tc_mma_tf32(d_tmem, make_desc(xs + X_STAGE_BYTES + kk * (UMMA_K * 128), BLOCK_K * 128, 4 * 128, 1),
+                        make_desc(bs + kk * (UMMA_K * 4), 16, 1024), idesc, 1u);
         }
         tc_commit(empty_bar(stage));     // frees the smem stage once these MMAs have read it
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }

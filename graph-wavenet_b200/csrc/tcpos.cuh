@@ -191,7 +191,6 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
       for (int s = 0; s < p.nseg; ++s) {
         if (!mbar_wait(full_bar(stage), phase, 14)) { ok = false; break; }
-        if (X3 && !mbar_wait(split_bar(stage), phase, 16)) { ok = false; break; }
         tc_fence_after();
         const uint32_t as = a0 + stage * STG;
         const uint32_t ws = p.wstream ? as + NPL * TP_A_BYTES : base + s * w_blk;
@@ -201,10 +200,14 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
           // both operands K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart, this k-step 32 B in
           const uint64_t ad = make_desc(as + kk * 32, 16, 1024), wd = make_desc(ws + kk * 32, 16, 1024);
           tc_mma_tf32(d_tmem, ad, wd, idesc, (s > 0 || kk > 0) ? 1u : 0u);
-          if (X3) {
-            tc_mma_tf32(d_tmem, ad, make_desc(ws + wlo_off + kk * 32, 16, 1024), idesc, 1u);
-            tc_mma_tf32(d_tmem, make_desc(as + TP_A_BYTES + kk * 32, 16, 1024), wd, idesc, 1u);
-          }
+          if (X3) tc_mma_tf32(d_tmem, ad, make_desc(ws + wlo_off + kk * 32, 16, 1024), idesc, 1u);
+        }
+        if (X3) {   // the A_lo term last: the split of this stage overlaps the MMAs above
+          if (!mbar_wait(split_bar(stage), phase, 16)) { ok = false; break; }
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            tc_mma_tf32(d_tmem, make_desc(as + TP_A_BYTES + kk * 32, 16, 1024), make_desc(ws + kk * 32, 16, 1024), idesc, 1u);
         }
         tc_commit(empty_bar(stage));
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }

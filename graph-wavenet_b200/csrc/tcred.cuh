@@ -161,26 +161,40 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     bool first = true;
     for (int c = c_beg; c < c_end; ++c) {
       if (!mbar_wait(full_bar(stage), phase, 22)) break;
-      if (X3 && !mbar_wait(split_bar(stage), phase, 24)) break;
       tc_fence_after();
       const uint32_t sa = st0 + stage * stage_bytes, sb = sa + p.a_bytes;
+      auto descs = [&](int t, int kk, uint64_t& adesc, uint64_t& bdesc) {
+        if (p.mode == 0) {
+          // MN-major, 32-byte-atom swizzle: atoms of 4 k-rows x 128 B (SBO 512 B), next 32-wide block 4096 B on (LBO)
+          adesc = make_desc(sa + t * 16384 + kk * 1024, 4096, 512, 1);
+          bdesc = make_desc(sb + kk * 1024, 4096, 512, 1);
+        } else {
+          adesc = make_desc(sa + t * 16384 + kk * 32, 16, 1024, 2);
+          bdesc = make_desc(sb + kk * 32, 16, 1024, 2);
+        }
+      };
 #pragma unroll 1
       for (int t = 0; t < p.mtiles; ++t) {
         const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.N);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           uint64_t adesc, bdesc;
-          if (p.mode == 0) {
-            // MN-major, 32-byte-atom swizzle: atoms of 4 k-rows x 128 B (SBO 512 B), next 32-wide block 4096 B on (LBO)
-            adesc = make_desc(sa + t * 16384 + kk * 1024, 4096, 512, 1);
-            bdesc = make_desc(sb + kk * 1024, 4096, 512, 1);
-          } else {
-            adesc = make_desc(sa + t * 16384 + kk * 32, 16, 1024, 2);
-            bdesc = make_desc(sb + kk * 32, 16, 1024, 2);
-          }
+          descs(t, kk, adesc, bdesc);
           tc_mma_tf32(d_tmem, adesc, bdesc, idesc, (!first || kk > 0) ? 1u : 0u);
-          if (X3) {   // the remainder planes sit plane_bytes further, same layout
-            const uint64_t off = (uint64_t)((uint32_t)plane_bytes >> 4);
+        }
+      }
+      if (X3) {   // remainder terms after the split of this stage (it ran while the MMAs above were issued); the remainder
+                  // planes sit plane_bytes further, same layout
+        if (!mbar_wait(split_bar(stage), phase, 24)) break;
+        tc_fence_after();
+        const uint64_t off = (uint64_t)((uint32_t)plane_bytes >> 4);
+#pragma unroll 1
+        for (int t = 0; t < p.mtiles; ++t) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.N);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            uint64_t adesc, bdesc;
+            descs(t, kk, adesc, bdesc);
             tc_mma_tf32(d_tmem, adesc, bdesc + off, idesc, 1u);
             tc_mma_tf32(d_tmem, adesc + off, bdesc, idesc, 1u);
           }
