@@ -118,6 +118,7 @@ struct LayerIdx {
 struct gwn_plan {
   gwn_config c;
   int nL, S, nseg, nseg_mod, RF, L0, pad, T_out, ld, ldo;
+  int Bs;                          // support sets: 1, or batch with per_sample_supports
   std::vector<int> dil, L;  // per layer dilation and output length
   std::vector<gwn::Entry> entries;
   std::vector<gwn::LayerIdx> li;
@@ -164,18 +165,22 @@ static int build_plan(gwn_plan* p) {
   GWN_CHECK_ARG(!c.gcn || c.gcn_bool, "plan: gcn active without gcn_bool");
   GWN_CHECK_ARG(!c.adaptive || c.gcn, "plan: adaptive adjacency implies an active gcn");
   p->nL = c.blocks * c.layers;
-  const int supports_len = c.n_static_supports + (c.adaptive ? 1 : 0);  // model.py:109-128
+  GWN_CHECK_ARG(!(c.adaptive && c.adaptive_input), "plan: adaptive (parameters) and adaptive_input are exclusive");
+  GWN_CHECK_ARG(!c.adaptive_input || c.per_sample_supports, "plan: adaptive_input implies per_sample_supports");
+  GWN_CHECK_ARG(!c.per_sample_supports || !c.adaptive, "plan: per-sample supports have no trainable adaptive adjacency");
+  const int supports_len = c.n_static_supports + ((c.adaptive || c.adaptive_input) ? 1 : 0);  // model.py:109-128
+  p->Bs = c.per_sample_supports ? c.batch : 1;
   p->S = c.gcn ? supports_len : 0;
   GWN_CHECK_ARG(p->S <= MAXSUP, "plan: too many supports");
   GWN_CHECK_ARG(!c.gcn || p->S >= 1, "plan: gcn enabled without supports");
-  GWN_CHECK_ARG(!c.adaptive || (c.apt_rank >= 1 && c.apt_rank <= 16), "plan: apt_rank must be in [1,16]");
+  GWN_CHECK_ARG(!(c.adaptive || c.adaptive_input) || (c.apt_rank >= 1 && c.apt_rank <= 16), "plan: apt_rank must be in [1,16]");
   p->nseg_mod = 1 + c.order * supports_len;   // c_in multiplier of the gconv modules (model.py:36)
   p->nseg = c.gcn ? p->nseg_mod : 1;
   GWN_CHECK_ARG(p->nseg_mod <= MAXSEG, "plan: too many gcn segments");
   p->dil.clear();
   int rf = 1;
   for (int b = 0; b < c.blocks; ++b) {   // model.py:130-155
-    int d = 1, scope = c.kernel_size - 1;
+    int d = c.dilation_base > 0 ? c.dilation_base : 1, scope = c.kernel_size - 1;
     for (int l = 0; l < c.layers; ++l) {
       p->dil.push_back(d);
       d *= 2;
@@ -271,9 +276,9 @@ static int build_plan(gwn_plan* p) {
     o += align_up(n);
     return r;
   };
-  p->o_sup = take((i64)std::max(p->S, 1) * N * p->ld);
-  p->o_supT = take((i64)std::max(p->S, 1) * N * p->ld);
-  p->sup_span = p->o_supT + (i64)std::max(p->S, 1) * N * p->ld - p->o_sup;   // both packed support regions
+  p->o_sup = take((i64)std::max(p->S, 1) * p->Bs * N * p->ld);     // [support][sample set][N][ld]
+  p->o_supT = take((i64)std::max(p->S, 1) * p->Bs * N * p->ld);
+  p->sup_span = p->o_supT + (i64)std::max(p->S, 1) * p->Bs * N * p->ld - p->o_sup;   // both packed support regions
   p->o_sup_lo = take(c.precision == GWN_PREC_FP32X3 ? p->sup_span : 0);        // their 3xTF32 remainders, same layout
   p->o_x0 = take(p->P0() * C);
   p->o_g.resize(nL); p->o_u.resize(nL); p->o_ac.resize(nL); p->o_mr.resize(nL); p->o_sums.resize(nL); p->o_pack.resize(nL);
@@ -448,25 +453,38 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
   const int nL = p->nL, B = c.batch;
   const void* const* prm = a->params;
 
-  // ---- supports: pack static ones, compute the adaptive one (model.py:185-188)
+  // ---- supports: pack static ones, compute the adaptive one (model.py:185-188); with per-sample graphs one set per
+  // sample (model.py:313,345-346).  Layout of both packed regions: [support][sample set][N][ld].
+  const int Bs = p->Bs;
+  const i64 sup_sz = (i64)N * p->ld;
   SupportView supF[MAXSUP], supB[MAXSUP];
   TcSupports tcF;
   memset(&tcF, 0, sizeof(tcF));
+  const int sstr = c.per_sample_supports ? 3 : 2;
   for (int s = 0; s < p->S; ++s) {
-    float* Ap = ws + p->o_sup + (i64)s * N * p->ld;
-    float* ATp = ws + p->o_supT + (i64)s * N * p->ld;
-    if (s < c.n_static_supports) {
-      GWN_CHECK_ARG(a->supports && a->supports[s] && a->support_strides, "forward: support %d missing", s);
-      GWN_LAUNCH_1D(support_pack_kernel, (i64)N * p->ld, st, a->supports[s], (i64)a->support_strides[2 * s],
-                    (i64)a->support_strides[2 * s + 1], Ap, ATp, N, p->ld);
-    } else {
-      GWN_LAUNCH_WARP_ROWS(adp_fwd_kernel, N, st, P_<float>(prm, p->i_nv1), P_<float>(prm, p->i_nv2), c.apt_rank, Ap, ATp, N,
-                           p->ld);
+    for (int b = 0; b < Bs; ++b) {
+      float* Ap = ws + p->o_sup + ((i64)s * Bs + b) * sup_sz;
+      float* ATp = ws + p->o_supT + ((i64)s * Bs + b) * sup_sz;
+      if (s < c.n_static_supports) {
+        GWN_CHECK_ARG(a->supports && a->supports[s] && a->support_strides, "forward: support %d missing", s);
+        const int64_t* ss = a->support_strides + sstr * s;
+        const float* As = a->supports[s] + (c.per_sample_supports ? (i64)b * ss[0] : 0);
+        GWN_LAUNCH_1D(support_pack_kernel, sup_sz, st, As, (i64)ss[sstr - 2], (i64)ss[sstr - 1], Ap, ATp, N, p->ld);
+      } else if (c.adaptive_input) {
+        GWN_CHECK_ARG(a->apt_e1 && a->apt_e2, "forward: adaptive_input without node embeddings");
+        GWN_LAUNCH_WARP_ROWS(adp_fwd_kernel, N, st, a->apt_e1 + (i64)b * N * c.apt_rank, a->apt_e2 + (i64)b * c.apt_rank * N,
+                             c.apt_rank, Ap, ATp, N, p->ld);
+      } else {
+        GWN_LAUNCH_WARP_ROWS(adp_fwd_kernel, N, st, P_<float>(prm, p->i_nv1), P_<float>(prm, p->i_nv2), c.apt_rank, Ap, ATp, N,
+                             p->ld);
+      }
     }
-    supF[s] = support_padded(Ap, p->ld);
-    supB[s] = support_padded(ATp, p->ld);
-    tcF.S[s] = ATp;   // forward contraction y[w] = sum_v A[v,w] x[v]: K-contiguous rows are those of A^T
-    if (x3(p) && tcpos_ok(p)) tcF.Slo[s] = ws + p->o_sup_lo + (ATp - (ws + p->o_sup));
+    float* Ap0 = ws + p->o_sup + (i64)s * Bs * sup_sz;
+    float* ATp0 = ws + p->o_supT + (i64)s * Bs * sup_sz;
+    supF[s] = support_padded(Ap0, p->ld);
+    supB[s] = support_padded(ATp0, p->ld);
+    tcF.S[s] = ATp0;   // forward contraction y[w] = sum_v A[v,w] x[v]: K-contiguous rows are those of A^T
+    if (x3(p) && tcpos_ok(p)) tcF.Slo[s] = ws + p->o_sup_lo + (ATp0 - (ws + p->o_sup));
   }
   if (x3(p) && tcpos_ok(p) && p->S > 0)
     GWN_LAUNCH_1D(split_lo_kernel, p->sup_span, st, (const float*)(ws + p->o_sup), ws + p->o_sup_lo, p->sup_span);
@@ -531,8 +549,23 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     m.tf32_tc = tcpos_ok(p) ? 1 : 0;
     float* pk_m = ws + p->o_pack[i];
     if (c.gcn) {
-      GcnShape gs{B, p->L[i], N, D, C, p->S, c.order};
-      GWN_TRY(gcn_hops_forward(gs, g, supF, g + Pi * D, st, &tcF));
+      if (!c.per_sample_supports) {
+        GcnShape gs{B, p->L[i], N, D, C, p->S, c.order};
+        GWN_TRY(gcn_hops_forward(gs, g, supF, g + Pi * D, st, &tcF));
+      } else {   // one graph per sample: the sample's slab against its own support set
+        GcnShape g1{1, p->L[i], N, D, C, p->S, c.order};
+        const i64 slab = (i64)p->L[i] * N * D;
+        for (int b = 0; b < B; ++b) {
+          SupportView sf[MAXSUP];
+          TcSupports tb = tcF;
+          for (int s = 0; s < p->S; ++s) {
+            sf[s] = support_padded(supF[s].p + (i64)b * sup_sz, p->ld);
+            tb.S[s] = tcF.S[s] + (i64)b * sup_sz;
+            if (tcF.Slo[s]) tb.Slo[s] = tcF.Slo[s] + (i64)b * sup_sz;
+          }
+          GWN_TRY(gcn_hops_forward(g1, g + b * slab, sf, g + Pi * D + b * slab, st, &tb, Pi * D));
+        }
+      }
       m.W = P_<float>(prm, p->li[i].mw);
       m.bias = P_<float>(prm, p->li[i].mb);
     } else {  // model.py:232
@@ -695,9 +728,9 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
   TcSupports tcB;
   memset(&tcB, 0, sizeof(tcB));
   for (int s = 0; s < p->S; ++s) {
-    supB[s] = support_padded(ws + p->o_supT + (i64)s * N * p->ld, p->ld);
-    tcB.S[s] = ws + p->o_sup + (i64)s * N * p->ld;   // dx[v] = sum_w A[v,w] dy[w]: K-contiguous rows are those of A
-    if (x3(p) && tcpos_ok(p)) tcB.Slo[s] = ws + p->o_sup_lo + (i64)s * N * p->ld;
+    supB[s] = support_padded(ws + p->o_supT + (i64)s * p->Bs * N * p->ld, p->ld);
+    tcB.S[s] = ws + p->o_sup + (i64)s * p->Bs * N * p->ld;   // dx[v] = sum_w A[v,w] dy[w]: K-contiguous rows are those of A
+    if (x3(p) && tcpos_ok(p)) tcB.Slo[s] = ws + p->o_sup_lo + (i64)s * p->Bs * N * p->ld;
   }
   tcB.ld = p->ld;
   tcB.precision = c.precision;
@@ -988,7 +1021,23 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
         i64 ldds[MAXSUP];
         for (int s = 0; s < p->S; ++s) { dsup[s] = nullptr; ldds[s] = p->ld; }
         if (c.adaptive && !p->defer_dA) dsup[p->S - 1] = sc + p->o_dA;
-        GWN_TRY(gcn_hops_backward(gs, g, g + Pi * D, supB, dsegs, dg, dgh_i, p->T_out, dsup, ldds, st, &tcB, &tsc));
+        if (!c.per_sample_supports) {
+          GWN_TRY(gcn_hops_backward(gs, g, g + Pi * D, supB, dsegs, dg, dgh_i, p->T_out, dsup, ldds, st, &tcB, &tsc));
+        } else {   // per-sample graphs: no support gradient (the supports are inputs, model.py:313-329)
+          GcnShape g1{1, p->L[i], N, D, C, p->S, c.order};
+          const i64 slab = (i64)p->L[i] * N * D, sup_sz = (i64)N * p->ld;
+          for (int b = 0; b < B; ++b) {
+            SupportView sb[MAXSUP];
+            TcSupports tb = tcB;
+            for (int s = 0; s < p->S; ++s) {
+              sb[s] = support_padded(supB[s].p + (i64)b * sup_sz, p->ld);
+              tb.S[s] = tcB.S[s] + (i64)b * sup_sz;
+              if (tcB.Slo[s]) tb.Slo[s] = tcB.Slo[s] + (i64)b * sup_sz;
+            }
+            GWN_TRY(gcn_hops_backward(g1, g + b * slab, g + Pi * D + b * slab, sb, dsegs + b * slab, dg + b * slab,
+                                      dgh_i + (i64)b * p->T_out * N * D, p->T_out, nullptr, ldds, st, &tb, &tsc, Pi * D));
+          }
+        }
         if (c.adaptive && p->defer_dA) {   // (hop input, chained gradient) pairs of the adaptive support, used after the loop
           const int sA = p->S - 1;
           for (int k = 1; k <= c.order; ++k) {

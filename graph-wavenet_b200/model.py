@@ -390,17 +390,6 @@ class gcn2(nn.Module):
                              self.precision, self._keep_mask, seed, *support)
 
 
-class gwnet_diff_G(nn.Module):
-    """model.py:244-407 (the fork's per-sample-graph network) is NOT part of this round: its operators ``nconv2`` /
-    ``gcn2`` above run natively, the network around them -- which re-randomises its node embeddings inside ``forward`` and
-    stops in a debugger in the reference (model.py:324-332) -- is SURVEY.md section 8(f) row 2 'next'."""
-
-    def __init__(self, *a, **k):
-        super().__init__()
-        raise NotImplementedError("gwnet_diff_G (model.py:244-407) is outside the accelerated hot path of this round "
-                                  "(SURVEY.md section 8(f) row 2); nconv2 / gcn2 are available as native operators")
-
-
 # ============================================================================== gwnet
 class _GwnetFn(torch.autograd.Function):
     """One autograd node for the whole network: forward and backward are each a single C-ABI call."""
@@ -509,15 +498,26 @@ class gwnet(nn.Module):
     def _gcn_active(self):
         return bool(self.gcn_bool and self.supports is not None)   # model.py:225
 
+    def _plan_flags(self):
+        """Plan switches beyond the reference gwnet (overridden by gwnet_diff_G)."""
+        return dict(dilation_base=0, per_sample_supports=False, adaptive_input=False)
+
+    def _plan_supports(self):
+        return self.supports
+
+    def _plan_apt(self):
+        return None
+
     def _runner(self, batch, seq_len):
-        key = (batch, seq_len, self.precision, self._n_static(), float(self.dropout))
+        flags = self._plan_flags()
+        key = (batch, seq_len, self.precision, self._n_static(), float(self.dropout), self._gcn_active(), tuple(flags.values()))
         r = self._runners.get(key)
         if r is None:
             g = self._geom
             cfg = _make_config(batch=batch, seq_len=seq_len, n_static_supports=self._n_static(), gcn_bool=self.gcn_bool,
                                adaptive=self._adaptive(), gcn=self._gcn_active(), order=2, apt_rank=10,
                                precision=self.precision, dropout=self.dropout, bn_eps=self.bn[0].eps,
-                               bn_momentum=self.bn[0].momentum, **g)
+                               bn_momentum=self.bn[0].momentum, **flags, **g)
             r = _PlanRunner(_N.get_lib(), cfg)
             names = list(self.state_dict(keep_vars=True).keys())
             if names != r.plan.names:
@@ -550,7 +550,7 @@ class gwnet(nn.Module):
         for t in table:
             if not t.is_cuda:
                 raise RuntimeError("gwnet_b200: module parameters must be on a CUDA device (call .to(device))")
-        for s in (self.supports or []):
+        for s in (self._plan_supports() or []):
             _require_cuda(s, "gwnet support")
         training = self.training
         mode, masks, seed = _N.DROPOUT_NONE, None, 0
@@ -560,7 +560,7 @@ class gwnet(nn.Module):
             else:
                 mode, seed = _N.DROPOUT_PHILOX, int(torch.randint(0, 2 ** 62, (1,)).item())
         with torch.cuda.device(inp.device):
-            out, fctx = r.forward(table, self.supports, inp.detach(), training, mode, masks, seed)
+            out, fctx = r.forward(table, self._plan_supports(), inp.detach(), training, mode, masks, seed, apt=self._plan_apt())
         fctx.runner = r
         return out, (fctx if save else None)
 
@@ -587,3 +587,100 @@ class gwnet(nn.Module):
             return _GwnetFn.apply(self, input, *params)
         out, _ = self._run_forward(input, save=False)
         return out
+
+
+# ============================================================================== gwnet_diff_G
+class gwnet_diff_G(gwnet):
+    """model.py:244-407 -- the fork's per-sample-graph network: every sample carries its own supports ``[B,N,N]``
+    (passed to ``forward``), dilations 4, 8 per block, and -- with ``addaptadj`` -- an extra support
+    softmax(relu(E1 E2)) from node embeddings that the reference RE-DRAWS inside every forward (model.py:324-329: they
+    are not registered parameters and receive no update).  Constructor arguments, submodule layout and ``state_dict``
+    keys follow the reference; the embeddings are drawn here with the same two ``torch.randn`` calls, so a run seeded
+    like the reference reproduces it.  The ``aptinit is not None`` branch stops in a debugger in the reference
+    (model.py:332) and is rejected here."""
+
+    def __init__(self, device, num_nodes, dropout=0.3, supports_len=0, gcn_bool=True, addaptadj=True, in_dim=2, out_dim=12,
+                 residual_channels=32, dilation_channels=32, skip_channels=256, end_channels=512, kernel_size=2, blocks=4,
+                 layers=2):
+        nn.Module.__init__(self)
+        self.dropout = dropout
+        self.blocks = blocks
+        self.layers = layers
+        self.gcn_bool = gcn_bool
+        self.addaptadj = addaptadj
+        self.device = device
+        self.num_nodes = num_nodes
+
+        self.filter_convs = nn.ModuleList()
+        self.gate_convs = nn.ModuleList()
+        self.residual_convs = nn.ModuleList()
+        self.skip_convs = nn.ModuleList()
+        self.bn = nn.ModuleList()
+        self.gconv = nn.ModuleList()
+        self.start_conv = nn.Conv2d(in_channels=in_dim, out_channels=residual_channels, kernel_size=(1, 1))
+        receptive_field = 1
+        for b in range(blocks):
+            additional_scope = kernel_size - 1
+            new_dilation = 4
+            for i in range(layers):
+                self.filter_convs.append(nn.Conv2d(residual_channels, dilation_channels, kernel_size=(1, kernel_size),
+                                                   dilation=new_dilation))
+                self.gate_convs.append(nn.Conv2d(residual_channels, dilation_channels, kernel_size=(1, kernel_size),
+                                                 dilation=new_dilation))
+                self.residual_convs.append(nn.Conv2d(dilation_channels, residual_channels, kernel_size=(1, 1)))
+                self.skip_convs.append(nn.Conv2d(dilation_channels, skip_channels, kernel_size=(1, 1)))
+                self.bn.append(nn.BatchNorm2d(residual_channels))
+                new_dilation *= 2
+                receptive_field += additional_scope
+                additional_scope *= 2
+                if self.gcn_bool:
+                    self.gconv.append(gcn2(dilation_channels, residual_channels, dropout, support_len=supports_len))
+        self.end_conv_1 = nn.Conv2d(skip_channels, end_channels, kernel_size=(1, 1), bias=True)
+        self.end_conv_2 = nn.Conv2d(end_channels, out_dim, kernel_size=(1, 1), bias=True)
+        self.receptive_field = receptive_field
+
+        self._geom = dict(num_nodes=num_nodes, in_dim=in_dim, out_dim=out_dim, residual_channels=residual_channels,
+                          dilation_channels=dilation_channels, skip_channels=skip_channels, end_channels=end_channels,
+                          kernel_size=kernel_size, blocks=blocks, layers=layers)
+        self.precision = _default_precision()
+        self._runners = {}
+        self._entries = None
+        self._dropout_masks = None
+        self._static_workspace = None
+        self._flat = None
+        self._supports_len = supports_len
+        self.supports = None          # per call
+        self._apt = None
+
+    # ---- plan hooks
+    def _plan_flags(self):
+        return dict(dilation_base=4, per_sample_supports=True, adaptive_input=self._apt is not None)
+
+    def _plan_apt(self):
+        return self._apt
+
+    def _adaptive(self):
+        return False                  # no trainable adjacency: the embeddings are inputs of the call
+
+    def _gcn_active(self):
+        return bool(self.gcn_bool and self.supports is not None)   # model.py:388
+
+    def forward(self, input, supports, aptinit=None):
+        if aptinit is not None:
+            raise NotImplementedError("gwnet_diff_G: the aptinit branch is unfinished in the reference (model.py:332)")
+        batch = len(input)
+        self._apt = None
+        if self.gcn_bool and self.addaptadj:
+            if supports is None:
+                supports = []
+            # model.py:324-329: drawn on the CPU generator, nodevec1 first, then moved to the device
+            nv1 = torch.randn(batch, self.num_nodes, 10).to(input.device)
+            nv2 = torch.randn(batch, 10, self.num_nodes).to(input.device)
+            self._apt = (nv1.contiguous(), nv2.contiguous())
+        self.supports = [s.contiguous() for s in supports] if supports is not None else None
+        if self._gcn_active() and len(self.supports) + (1 if self._apt is not None else 0) != self._supports_len:
+            raise RuntimeError(f"gwnet_diff_G: built for supports_len={self._supports_len}, called with "
+                               f"{len(self.supports)} supports{' + adaptive' if self._apt is not None else ''}")
+        if not self._gcn_active():
+            self._apt = None
+        return gwnet.forward(self, input)

@@ -32,6 +32,7 @@ class GwnConfig(C.Structure):
         ("n_static_supports", C.c_int), ("gcn_bool", C.c_int), ("adaptive", C.c_int), ("gcn", C.c_int),
         ("order", C.c_int), ("apt_rank", C.c_int), ("precision", C.c_int),
         ("dropout", C.c_float), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
+        ("dilation_base", C.c_int), ("per_sample_supports", C.c_int), ("adaptive_input", C.c_int),
     ]
 
 
@@ -41,6 +42,7 @@ class GwnForwardArgs(C.Structure):
         ("input", C.c_void_p), ("input_strides", C.c_int64 * 4), ("output", C.c_void_p),
         ("workspace", C.c_void_p), ("training", C.c_int), ("dropout_mode", C.c_int),
         ("keep_masks", c_void_pp), ("seed", C.c_uint64), ("stream", C.c_void_p), ("seed_device", C.c_void_p),
+        ("apt_e1", C.c_void_p), ("apt_e2", C.c_void_p),
     ]
 
 
@@ -159,8 +161,8 @@ class Lib:
         d.gwn_plan_train_fwd_bwd.argtypes = [C.c_void_p, C.POINTER(GwnTrainArgs)]
         d.gwn_plan_eval_metrics.argtypes = [C.c_void_p, C.POINTER(GwnTrainArgs)]
         d.gwn_adam_step.argtypes = [C.POINTER(GwnAdamArgs)]
-        if d.gwn_abi_version() != 2:
-            raise GwnError(f"{path}: ABI version {d.gwn_abi_version()} != 2")
+        if d.gwn_abi_version() != 3:
+            raise GwnError(f"{path}: ABI version {d.gwn_abi_version()} != 3")
 
     def check(self, status: int, what: str = ""):
         if status != 0:

@@ -15,10 +15,12 @@ from . import native as N
 
 def make_config(*, batch, num_nodes, seq_len, in_dim, out_dim, residual_channels, dilation_channels, skip_channels,
                 end_channels, kernel_size, blocks, layers, n_static_supports, gcn_bool, adaptive, gcn, order=2,
-                apt_rank=10, precision=N.PREC_FP32, dropout=0.3, bn_eps=1e-5, bn_momentum=0.1) -> N.GwnConfig:
+                apt_rank=10, precision=N.PREC_FP32, dropout=0.3, bn_eps=1e-5, bn_momentum=0.1, dilation_base=0,
+                per_sample_supports=False, adaptive_input=False) -> N.GwnConfig:
     return N.GwnConfig(batch, num_nodes, seq_len, in_dim, out_dim, residual_channels, dilation_channels, skip_channels,
                        end_channels, kernel_size, blocks, layers, n_static_supports, int(gcn_bool), int(adaptive),
-                       int(gcn), order, apt_rank, precision, float(dropout), float(bn_eps), float(bn_momentum))
+                       int(gcn), order, apt_rank, precision, float(dropout), float(bn_eps), float(bn_momentum),
+                       int(dilation_base), int(per_sample_supports), int(adaptive_input))
 
 
 def _stream_of(t: torch.Tensor) -> int:
@@ -58,18 +60,23 @@ class PlanRunner:
         sup = list(supports or [])[:ns]
         if len(sup) != ns:
             raise N.GwnError(f"expected {ns} static supports, got {len(sup)}")
+        nn_ = self.cfg.num_nodes
+        per = bool(self.cfg.per_sample_supports)
+        want = (self.cfg.batch, nn_, nn_) if per else (nn_, nn_)
         for s in sup:
-            if s.dtype != torch.float32 or s.dim() != 2 or s.shape[0] != self.cfg.num_nodes or s.shape[1] != self.cfg.num_nodes:
-                raise N.GwnError(f"support must be fp32 [{self.cfg.num_nodes},{self.cfg.num_nodes}], got {s.dtype} {tuple(s.shape)}")
+            if s.dtype != torch.float32 or tuple(s.shape) != want:
+                raise N.GwnError(f"support must be fp32 {list(want)}, got {s.dtype} {tuple(s.shape)}")
         ptrs = N.ptr_array([s.data_ptr() for s in sup])
-        strides = (C.c_int64 * max(2 * ns, 1))()
+        k = 3 if per else 2
+        strides = (C.c_int64 * max(k * ns, 1))()
         for i, s in enumerate(sup):
-            strides[2 * i], strides[2 * i + 1] = s.stride(0), s.stride(1)
+            for j in range(k):
+                strides[k * i + j] = s.stride(j)
         return sup, ptrs, strides
 
     def forward(self, params: Sequence[torch.Tensor], supports, inp: torch.Tensor, training: bool,
                 dropout_mode: int = N.DROPOUT_PHILOX, masks: Optional[Sequence[torch.Tensor]] = None, seed: int = 0,
-                workspace: Optional[torch.Tensor] = None):
+                workspace: Optional[torch.Tensor] = None, apt=None):
         cfg = self.cfg
         if inp.dtype != torch.float32 or inp.dim() != 4 or tuple(inp.shape) != (cfg.batch, cfg.in_dim, cfg.num_nodes, cfg.seq_len):
             raise N.GwnError(f"input must be fp32 [{cfg.batch},{cfg.in_dim},{cfg.num_nodes},{cfg.seq_len}], got {inp.dtype} {tuple(inp.shape)}")
@@ -102,11 +109,16 @@ class PlanRunner:
             a.keep_masks = mptrs
         a.seed = seed
         a.stream = _stream_of(inp)
+        if cfg.adaptive_input:
+            if apt is None or tuple(apt[0].shape) != (cfg.batch, cfg.num_nodes, cfg.apt_rank) or \
+                    tuple(apt[1].shape) != (cfg.batch, cfg.apt_rank, cfg.num_nodes):
+                raise N.GwnError("adaptive_input: node embeddings [B,N,rank] / [B,rank,N] required")
+            a.apt_e1, a.apt_e2 = apt[0].data_ptr(), apt[1].data_ptr()
         self.plan.forward(a)
         ctx = ForwardCtx()
         ctx.workspace, ctx.input, ctx.supports = workspace, inp, sup
         ctx.training, ctx.dropout_mode, ctx.masks, ctx.seed = bool(training), a.dropout_mode, masks, seed
-        ctx.keep = (ptab, sptrs, sstrides, mptrs, list(params))
+        ctx.keep = (ptab, sptrs, sstrides, mptrs, list(params), apt)
         return out, ctx
 
     def backward(self, ctx: ForwardCtx, params: Sequence[torch.Tensor], grad_out: torch.Tensor, need_input_grad: bool = False):

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GWN_ABI_VERSION 2
+#define GWN_ABI_VERSION 3
 
 typedef enum gwn_status {
   GWN_OK = 0,
@@ -167,6 +167,11 @@ typedef struct gwn_config {
   int precision;           /* gwn_precision                                           */
   float dropout;
   float bn_eps, bn_momentum;
+  /* per-sample-graph variant gwnet_diff_G (model.py:244-407); all 0 for gwnet */
+  int dilation_base;       /* first dilation of every block: 0/1 = gwnet (model.py:132), 4 = gwnet_diff_G (model.py:273) */
+  int per_sample_supports; /* supports are [B,N,N], one graph per sample (model.py:313)                              */
+  int adaptive_input;      /* an extra per-sample support softmax(relu(E1 E2)) from node embeddings passed to forward
+                              (model.py:324-329,345-346: re-drawn every forward, not parameters, no gradient)      */
 } gwn_config;
 
 typedef struct gwn_plan gwn_plan;
@@ -188,7 +193,8 @@ int gwn_plan_debug_layout(const gwn_plan* p, char* buf, int len);
 typedef struct gwn_forward_args {
   const void* const* params;     /* n_entries device pointers, state_dict order            */
   const float* const* supports;  /* n_static_supports device pointers [N,N]                */
-  const int64_t* support_strides;/* 2 per support: (row stride, col stride) in elements    */
+  const int64_t* support_strides;/* 2 per support: (row stride, col stride) in elements; with per_sample_supports
+                                    3 per support: (sample stride, row stride, col stride)  */
   const float* input;            /* [B,in_dim,N,T] fp32, any strides                        */
   int64_t input_strides[4];
   float* output;                 /* [B,out_dim,N,T_out] fp32 contiguous NCHW                */
@@ -199,6 +205,8 @@ typedef struct gwn_forward_args {
   uint64_t seed;                 /* Philox key (GWN_DROPOUT_PHILOX)                         */
   void* stream;
   const uint64_t* seed_device;   /* optional: read the Philox key from device memory instead (CUDA graphs)  */
+  const float* apt_e1;           /* adaptive_input: [B,N,apt_rank] contiguous                                */
+  const float* apt_e2;           /* adaptive_input: [B,apt_rank,N] contiguous                                */
 } gwn_forward_args;
 
 int gwn_plan_forward(gwn_plan* p, const gwn_forward_args* a);

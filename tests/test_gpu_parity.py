@@ -493,3 +493,44 @@ def test_nconv2_gcn2_operators(M):
     assert_close_rel(g.mlp.mlp.bias.grad, b64.grad, TOL, "gcn2 db")
     for s in range(S):
         assert_close_rel(Ads[s].grad, A64s[s].grad, TOL, f"gcn2 dA[{s}]")
+
+
+@pytest.mark.parametrize("tier", ["fp32", "fp32x3"])
+def test_gwnet_diff_G_matches_reference(M, tier):
+    """The fork's per-sample-graph network (model.py:244-407) through the drop-in class: forward, every gradient, BN
+    buffers and eval output against vectors of the real reference (tests/tools/make_golden_diffg.py)."""
+    import numpy as np, os
+    from graph_wavenet_b200 import native as NV
+    dev = torch.device("cuda:0")
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "diffg.npz"))
+    rec = {k: torch.from_numpy(z[k]) if z[k].ndim > 0 else torch.tensor(z[k].item()) for k in z.files}
+    state0 = {k[len("state0/"):]: v.clone() for k, v in rec.items() if k.startswith("state0/")}
+    Nn = int(rec["cfg_N"])
+    m = M.gwnet_diff_G(dev, Nn, dropout=0.0, supports_len=3, skip_channels=int(rec["cfg_skip"]),
+                       end_channels=int(rec["cfg_end"])).to(dev)
+    assert list(m.state_dict().keys()) == list(state0.keys())
+    m.load_state_dict(state0)
+    m.precision = {"fp32": NV.PREC_FP32, "fp32x3": NV.PREC_FP32X3}[tier]
+    sup = [rec["support.0"].to(dev), rec["support.1"].to(dev)]
+    x = rec["x"].to(dev).requires_grad_(True)
+    m.train()
+    torch.manual_seed(int(rec["fwd_seed"]))
+    out = m(x, sup, None)
+    assert_close_rel(out, rec["out_train"], TOL, "diff_G train output")
+    (out * rec["probe"].to(dev)).sum().backward()
+    assert_close_rel(x.grad, rec["grad_input"], TOL, "diff_G grad input")
+    ref = sub(rec, "grad/")
+    gnorm = sum(float(g.double().pow(2).sum()) for g in ref.values()) ** 0.5
+    for k, p in m.named_parameters():
+        if k in ref:
+            assert_close_rel(p.grad, ref[k], TOL, "diff_G grad " + k, floor=2e-6 * gnorm)
+        else:
+            assert p.grad is None, k
+    for k, v in m.state_dict().items():
+        if "buf1/" + k in rec:
+            assert_close_rel(v.float(), rec["buf1/" + k].float(), TOL, "diff_G buffer " + k)
+    m.eval()
+    torch.manual_seed(int(rec["fwd_seed"]) + 1)
+    with torch.no_grad():
+        oe = m(rec["x"].to(dev), sup, None)
+    assert_close_rel(oe, rec["out_eval"], TOL, "diff_G eval output")

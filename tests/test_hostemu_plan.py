@@ -165,3 +165,49 @@ def test_emulated_fused_train_step_matches_reference_trainer(emu, name):
     for k, t in zip(plan.names, table):
         assert_close_rel(t.float().reshape(rec["state3/" + k].shape), rec["state3/" + k].float(), 2e-3, "state after 3 steps " + k,
                          floor=1e-5)
+
+
+def _load_diffg():
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "diffg.npz"))
+    rec = {k: torch.from_numpy(z[k]) if z[k].ndim > 0 else torch.tensor(z[k].item()) for k in z.files}
+    state0 = {k[len("state0/"):]: v.clone() for k, v in rec.items() if k.startswith("state0/")}
+    for k in state0:
+        if k.endswith("num_batches_tracked"):
+            state0[k] = torch.as_tensor(state0[k], dtype=torch.long).reshape(())
+    return rec, state0
+
+
+def test_emulated_per_sample_graph_plan_matches_reference_diff_G(emu):
+    """gwnet_diff_G (model.py:244-407): per-sample supports, dilations 4/8, node embeddings drawn per forward -- the plan
+    with per_sample_supports / adaptive_input / dilation_base against vectors of the real reference."""
+    from oracle import diffg_oracle as DO
+    rec, state0 = _load_diffg()
+    x = rec["x"]
+    B, F_, Nn, T = x.shape
+    sup = [rec["support.0"], rec["support.1"]]
+    c = make_config(batch=B, num_nodes=Nn, seq_len=T, in_dim=F_, out_dim=12, residual_channels=32, dilation_channels=32,
+                    skip_channels=int(rec["cfg_skip"]), end_channels=int(rec["cfg_end"]), kernel_size=2, blocks=4, layers=2,
+                    n_static_supports=2, gcn_bool=True, adaptive=False, gcn=True, order=2, dropout=0.0, dilation_base=4,
+                    per_sample_supports=True, adaptive_input=True)
+    r = PlanRunner(emu, c)
+    assert r.plan.names == list(state0.keys())
+    params = [state0[k].clone().contiguous() for k in r.plan.names]
+    torch.manual_seed(int(rec["fwd_seed"]))
+    apt = DO.draw_node_embeddings(B, Nn)
+    out, ctx = r.forward(params, sup, x, training=True, apt=apt)
+    assert_close_rel(out, rec["out_train"], 2e-5, "diff_G train output")
+    gflat, gin = r.backward(ctx, params, rec["probe"], need_input_grad=True)
+    assert_close_rel(gin, rec["grad_input"], 1e-4, "diff_G grad input")
+    grads = r.split_grads(gflat)
+    ref = sub(rec, "grad/")
+    gnorm = sum(float(g.double().pow(2).sum()) for g in ref.values()) ** 0.5
+    for k, g in ref.items():
+        assert_close_rel(grads[k].reshape(g.shape), g, 1e-4, "diff_G grad " + k, floor=2e-6 * gnorm)
+    for k, t in zip(r.plan.names, params):
+        if "buf1/" + k in rec:
+            assert_close_rel(t.float(), rec["buf1/" + k].float(), 2e-5, "diff_G buffer " + k)
+    torch.manual_seed(int(rec["fwd_seed"]) + 1)
+    apt = DO.draw_node_embeddings(B, Nn)
+    out_e, _ = r.forward(params, sup, x, training=False, apt=apt)
+    assert_close_rel(out_e, rec["out_eval"], 2e-5, "diff_G eval output")
