@@ -8,10 +8,10 @@ import torch.optim as optim
 if __package__:
     from . import metrics as util
     from . import fused as _fused
-    from .model import gwnet
+    from .model import gwnet, gwnet_diff_G
 else:  # top-level import next to ``model`` (the reference's style)
     import importlib as _il
-    from model import gwnet  # noqa: F401
+    from model import gwnet, gwnet_diff_G  # noqa: F401
     util = _il.import_module("graph_wavenet_b200.metrics")
     _fused = _il.import_module("graph_wavenet_b200.fused")
 
@@ -19,17 +19,26 @@ else:  # top-level import next to ``model`` (the reference's style)
 class trainer():
     def __init__(self, scaler, in_dim, seq_length, num_nodes, nhid, dropout, lrate, wdecay, device, supports, gcn_bool,
                  addaptadj, aptinit, blocks=4, layers=2):
-        if type(supports) == dict:
-            raise NotImplementedError("per-sample graphs (gwnet_diff_G, engine.py:14-25) are outside the accelerated "
-                                      "hot path (SURVEY.md §8(f) row 2)")
-        self.model = gwnet(device, num_nodes, dropout, supports=supports, gcn_bool=gcn_bool, addaptadj=addaptadj,
-                           aptinit=aptinit, in_dim=in_dim, out_dim=seq_length, residual_channels=nhid,
-                           dilation_channels=nhid, skip_channels=nhid * 8, end_channels=nhid * 16, blocks=blocks,
-                           layers=layers)
+        per_sample = type(supports) == dict
+        if per_sample:   # engine.py:14-25 -- a different graph for every sample: {'train': [..], 'val': [..], 'test': [..]}
+            supports_len = 0
+            for k in supports:
+                supports_len = len(supports[k])
+                break
+            if gcn_bool and addaptadj:
+                supports_len += 1
+            self.model = gwnet_diff_G(device, num_nodes, dropout, supports_len, gcn_bool=gcn_bool, addaptadj=addaptadj,
+                                      in_dim=in_dim, out_dim=seq_length, residual_channels=nhid, dilation_channels=nhid,
+                                      skip_channels=nhid * 8, end_channels=nhid * 16, blocks=blocks, layers=layers)
+        else:
+            self.model = gwnet(device, num_nodes, dropout, supports=supports, gcn_bool=gcn_bool, addaptadj=addaptadj,
+                               aptinit=aptinit, in_dim=in_dim, out_dim=seq_length, residual_channels=nhid,
+                               dilation_channels=nhid, skip_channels=nhid * 8, end_channels=nhid * 16, blocks=blocks,
+                               layers=layers)
         self.model.to(device)
         # engine.py:33 -- Adam(lr, weight_decay as L2-in-gradient).  The fused step (default) runs clip + Adam as one
         # pass of gwn_adam_step over flat buffers; GWNET_B200_FUSED_STEP=0 keeps torch.optim.Adam on the autograd path.
-        self.fused = _fused.fused_enabled()
+        self.fused = _fused.fused_enabled() and not per_sample     # the captured step is the gwnet / trainer.train path
         self.use_graph = _fused.graph_enabled()
         if self.fused:
             self.optimizer = _fused.FusedAdam(self.model.parameters(), lr=lrate, weight_decay=wdecay)
@@ -67,6 +76,17 @@ class trainer():
             for g in grads:
                 dist.all_reduce(g)
                 g.mul_(1.0 / self.world)
+
+    def set_state(self, state):
+        assert state == 'train' or state == 'val' or state == 'test'
+        self.state = state
+
+    def train_syn(self, *a, **k):
+        raise NotImplementedError("train_syn / eval_syn (engine.py:64-117,132-180: the fork's synthetic F/E pooling task, host-side "
+                                  "python loops over graphTools objects) are outside the accelerated path (SURVEY.md section 2.1); "
+                                  "self.model(input, supports, aptinit) and its autograd are available")
+
+    eval_syn = train_syn
 
     def _bind_flat(self, input):
         m = self.model
