@@ -211,3 +211,70 @@ def test_emulated_per_sample_graph_plan_matches_reference_diff_G(emu):
     apt = DO.draw_node_embeddings(B, Nn)
     out_e, _ = r.forward(params, sup, x, training=False, apt=apt)
     assert_close_rel(out_e, rec["out_eval"], 2e-5, "diff_G eval output")
+
+
+def test_emulated_fused_step_null_labels_and_partial_mask(emu):
+    """Masked-loss edge cases of Utils/util.py:510-552 through the loss kernels: an all-null target (mask empty: the
+    reference turns the 0/0 mask into zeros, loss and metrics are 0, no gradient flows) and a partially null target,
+    each against the oracle trainer."""
+    import ctypes as C
+    from oracle import gwnet_oracle as O
+    rec = load_case("dbl_adp")
+    cfg = rec["cfg"]
+    x = rec["x"]
+    r = runner_for(emu, cfg, x.shape[0], x.shape[3])
+    plan = r.plan
+    for case in ("all_null", "partial"):
+        y = rec["y"][:, :, : cfg.out_dim].clone().contiguous()
+        if case == "all_null":
+            y.zero_()
+        else:
+            y[::2, :, ::3] = 0.0
+        st_o = {k: v.clone() for k, v in rec["state0"].items()}
+        tr = O.OracleTrainer(cfg, st_o, rec["supports"], 54.0, 20.0)
+        want = tr.train(x, y)
+        n = plan.grad_floats
+        flat, grad, m, v = torch.zeros(n), torch.zeros(n), torch.zeros(n), torch.zeros(n)
+        live4 = torch.zeros(n // 4, dtype=torch.uint8)
+        last = cfg.blocks * cfg.layers - 1
+        table = []
+        for k, off, ne in zip(plan.names, plan.grad_offsets, plan.numels):
+            t = rec["state0"][k].clone().contiguous()
+            if off >= 0:
+                flat[off:off + ne] = t.reshape(-1)
+                t = flat[off:off + ne]
+                dead = (k.startswith("residual_convs.") and cfg.gcn_active) or k.startswith(f"gconv.{last}.") or k.startswith(f"bn.{last}.")
+                if not dead:
+                    live4[off // 4:(off + ne + 3) // 4] = 1
+            table.append(t)
+        ptab = N.ptr_array([t.data_ptr() for t in table])
+        sup, sptrs, sstr = r._supports(rec["supports"])
+        out = torch.zeros(x.shape[0], cfg.out_dim, cfg.num_nodes, plan.t_out)
+        ws = torch.zeros(plan.fwd_bytes, dtype=torch.uint8)
+        sc = torch.zeros(plan.bwd_bytes, dtype=torch.uint8)
+        ctrl = torch.zeros(int(emu.dll.gwn_train_ctrl_bytes()), dtype=torch.uint8)
+        emu.check(emu.dll.gwn_train_ctrl_init(ctrl.data_ptr(), 1, 0))
+        metrics = torch.full((4,), float("nan"))
+        hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 1e-4, 5.0, 1.0, 0.0])
+        a = N.GwnTrainArgs()
+        a.fwd.params, a.fwd.supports, a.fwd.support_strides = ptab, sptrs, sstr
+        a.fwd.input = x.data_ptr()
+        for k in range(4):
+            a.fwd.input_strides[k] = x.stride(k)
+        a.fwd.output, a.fwd.workspace, a.fwd.training, a.fwd.dropout_mode = out.data_ptr(), ws.data_ptr(), 1, N.DROPOUT_NONE
+        a.scratch, a.grad_flat, a.target = sc.data_ptr(), grad.data_ptr(), y.data_ptr()
+        for k in range(3):
+            a.target_strides[k] = y.stride(k)
+        a.scaler_mean, a.scaler_std, a.ctrl, a.metrics = 54.0, 20.0, ctrl.data_ptr(), metrics.data_ptr()
+        ad = N.GwnAdamArgs()
+        ad.param_flat, ad.grad_flat, ad.exp_avg, ad.exp_avg_sq = flat.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr()
+        ad.live4, ad.n, ad.hyper, ad.ctrl, ad.metrics = live4.data_ptr(), n, hyper.data_ptr(), ctrl.data_ptr(), metrics.data_ptr()
+        emu.check(emu.dll.gwn_plan_train_fwd_bwd(plan.handle, C.byref(a)), "train_fwd_bwd")
+        emu.check(emu.dll.gwn_adam_step(C.byref(ad)), "adam_step")
+        assert not torch.isnan(metrics).any() and not torch.isnan(flat).any()
+        for got, w in zip(metrics[:3].tolist(), want):
+            assert abs(got - w) <= 1e-4 * abs(w) + 1e-6, (case, metrics.tolist(), want)
+        if case == "all_null":
+            assert metrics[:3].abs().max().item() == 0.0 and grad.abs().max().item() == 0.0
+        for k, t in zip(plan.names, table):
+            assert_close_rel(t.float().reshape(tr.state[k].shape), tr.state[k].detach().float(), 2e-3, f"{case}: state {k}", floor=1e-5)
