@@ -549,10 +549,14 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     m.tf32_tc = tcpos_ok(p) ? 1 : 0;
     float* pk_m = ws + p->o_pack[i];
     if (c.gcn) {
-      if (!c.per_sample_supports) {
+      const bool ps_tc = c.per_sample_supports && tcpos_ok(p);   // tcgen05 tiers: all samples' graphs in one launch
+      if (!c.per_sample_supports || ps_tc) {
         GcnShape gs{B, p->L[i], N, D, C, p->S, c.order};
-        GWN_TRY(gcn_hops_forward(gs, g, supF, g + Pi * D, st, &tcF));
-      } else {   // one graph per sample: the sample's slab against its own support set
+        TcSupports tf = tcF;
+        tf.per_sample = ps_tc ? 1 : 0;
+        tf.batch_stride = sup_sz;
+        GWN_TRY(gcn_hops_forward(gs, g, supF, g + Pi * D, st, &tf));
+      } else {   // fp32 reference tier: the sample's slab against its own support set, one launch group per sample
         GcnShape g1{1, p->L[i], N, D, C, p->S, c.order};
         const i64 slab = (i64)p->L[i] * N * D;
         for (int b = 0; b < B; ++b) {
@@ -1021,9 +1025,13 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
         i64 ldds[MAXSUP];
         for (int s = 0; s < p->S; ++s) { dsup[s] = nullptr; ldds[s] = p->ld; }
         if (c.adaptive && !p->defer_dA) dsup[p->S - 1] = sc + p->o_dA;
-        if (!c.per_sample_supports) {
-          GWN_TRY(gcn_hops_backward(gs, g, g + Pi * D, supB, dsegs, dg, dgh_i, p->T_out, dsup, ldds, st, &tcB, &tsc));
-        } else {   // per-sample graphs: no support gradient (the supports are inputs, model.py:313-329)
+        const bool ps_tc = c.per_sample_supports && tcpos_ok(p);
+        if (!c.per_sample_supports || ps_tc) {
+          TcSupports tb = tcB;
+          tb.per_sample = ps_tc ? 1 : 0;
+          tb.batch_stride = (i64)N * p->ld;
+          GWN_TRY(gcn_hops_backward(gs, g, g + Pi * D, supB, dsegs, dg, dgh_i, p->T_out, dsup, ldds, st, &tb, &tsc));
+        } else {   // fp32 tier; per-sample graphs have no support gradient (the supports are inputs, model.py:313-329)
           GcnShape g1{1, p->L[i], N, D, C, p->S, c.order};
           const i64 slab = (i64)p->L[i] * N * D, sup_sz = (i64)N * p->ld;
           for (int b = 0; b < B; ++b) {

@@ -26,6 +26,8 @@ struct NodeTcArgs {
   const float* add[TC_MAXSUP];     // nullable, same layout as Y
   const float* add2;               // nullable head window [B][T_out][V][32]
   int B, L, T_out, V;
+  int per_sample;                  // 1: one support set per sample (gwnet_diff_G): S[s] points at sample 0's matrix,
+  long long s_batch_stride;        //    consecutive samples s_batch_stride floats apart; tiles never straddle samples
 };
 
 // Returns GWN_ERR_UNSUPPORTED (with a message) when the shape cannot use this kernel.

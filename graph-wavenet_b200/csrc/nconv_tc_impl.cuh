@@ -29,6 +29,7 @@ struct Params {
   const float* add2;
   int nsup, kcat, V, L, T_out, nslabs;
   int n_tile, n_wt, n_jt, nkb, stages, total_tiles;
+  int per_sample, tps;   // per-sample supports: tiles per sample = ceil(L / 4); X is addressed (c, v, l, b), S (k, m, b)
   int mode;     // debug: 0 normal, 1 = TMEM st/ld self-test (no MMA), 2 = A operand := support tile (K-major)
   float* dbg;   // debug: dump of the first pipeline stage (X tile then support tile) by block 0
 };
@@ -101,9 +102,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
           if (!mbar_wait(empty_bar(stage), phase ^ 1u, 1)) { ok = false; break; }
           const uint32_t dst = base + stage * stage_bytes;
           mbar_expect_tx(full_bar(stage), (uint32_t)(X_STAGE_BYTES + NPL * s_tile));
-          tma_load_3d(dst, &maps.x[s], full_bar(stage), 0, kb * BLOCK_K, jt * SLABS);
-          tma_load_2d(dst + XB, &maps.s[s], full_bar(stage), kb * BLOCK_K, wt * p.n_tile);
-          if (X3) tma_load_2d(dst + XB + s_tile, &maps.slo[s], full_bar(stage), kb * BLOCK_K, wt * p.n_tile);
+          if (!p.per_sample) {
+            tma_load_3d(dst, &maps.x[s], full_bar(stage), 0, kb * BLOCK_K, jt * SLABS);
+            tma_load_2d(dst + XB, &maps.s[s], full_bar(stage), kb * BLOCK_K, wt * p.n_tile);
+            if (X3) tma_load_2d(dst + XB + s_tile, &maps.slo[s], full_bar(stage), kb * BLOCK_K, wt * p.n_tile);
+          } else {   // the tile's 4 time steps of ONE sample (steps past L arrive as zeros) against that sample's support
+            const int sb = jt / p.tps, lt = jt - sb * p.tps;
+            tma_load_4d(dst, &maps.x[s], full_bar(stage), 0, kb * BLOCK_K, lt * SLABS, sb);
+            tma_load_3d(dst + XB, &maps.s[s], full_bar(stage), kb * BLOCK_K, wt * p.n_tile, sb);
+            if (X3) tma_load_3d(dst + XB + s_tile, &maps.slo[s], full_bar(stage), kb * BLOCK_K, wt * p.n_tile, sb);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -193,8 +201,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
       const int wt = rem / p.n_jt, jt = rem - wt * p.n_jt;
       if (!mbar_wait(tfull_bar(acc), accphase, 4)) break;
       tc_fence_after();
-      const int slab = jt * SLABS + ew;
-      const bool slab_ok = slab < p.nslabs;
+      int slab = jt * SLABS + ew;
+      bool slab_ok = slab < p.nslabs;
+      if (p.per_sample) {
+        const int sb = jt / p.tps, l = (jt - sb * p.tps) * SLABS + ew;
+        slab = sb * p.L + l;
+        slab_ok = l < p.L;
+        if (!slab_ok) slab = 0;
+      }
       float* y = p.Y[o] + (size_t)slab * p.V * CH + lane;
       const float* ad = p.add[o] ? p.add[o] + (size_t)slab * p.V * CH + lane : nullptr;
       const float* ad2 = nullptr;
@@ -289,7 +303,9 @@ static int node_gemm_tc_impl(const NodeTcArgs& a, cudaStream_t stream) {
   p.nsup = a.nsup; p.kcat = a.kcat; p.V = a.V; p.L = a.L; p.T_out = a.T_out; p.nslabs = (int)nslabs;
   p.n_tile = a.V > 256 ? 256 : round_up(a.V, 16);
   p.n_wt = (a.V + p.n_tile - 1) / p.n_tile;
-  p.n_jt = (int)((nslabs + SLABS - 1) / SLABS);
+  p.per_sample = a.per_sample ? 1 : 0;
+  p.tps = (a.L + SLABS - 1) / SLABS;
+  p.n_jt = a.per_sample ? a.B * p.tps : (int)((nslabs + SLABS - 1) / SLABS);
   p.nkb = (a.V + BLOCK_K - 1) / BLOCK_K;
   const int stage_bytes = (X3 ? 2 : 1) * (X_STAGE_BYTES + p.n_tile * 128);
   p.stages = (SMEM_LIMIT - 2048) / stage_bytes;
@@ -310,20 +326,32 @@ static int node_gemm_tc_impl(const NodeTcArgs& a, cudaStream_t stream) {
       set_error("node_gemm_tc: operands must be 16-byte aligned");
       return GWN_ERR_UNSUPPORTED;
     }
-    cuuint64_t xd[3] = {(cuuint64_t)CH, (cuuint64_t)a.V, (cuuint64_t)nslabs};
-    cuuint64_t xs[2] = {(cuuint64_t)CH * 4, (cuuint64_t)a.V * CH * 4};
-    cuuint32_t xb[3] = {CH, BLOCK_K, SLABS};
-    GWN_TRY(encode(&maps.x[s], a.X[s], 3, xd, xs, xb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-    cuuint64_t sd[2] = {(cuuint64_t)a.V, (cuuint64_t)a.V};
-    cuuint64_t ss[1] = {(cuuint64_t)a.ld * 4};
-    cuuint32_t sb[2] = {BLOCK_K, (cuuint32_t)p.n_tile};
-    GWN_TRY(encode(&maps.s[s], a.S[s], 2, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_128B));
+    cuuint64_t sd[3] = {(cuuint64_t)a.V, (cuuint64_t)a.V, (cuuint64_t)a.B};
+    cuuint64_t ss[2] = {(cuuint64_t)a.ld * 4, (cuuint64_t)a.s_batch_stride * 4};
+    cuuint32_t sb[3] = {BLOCK_K, (cuuint32_t)p.n_tile, 1};
+    const int srank = a.per_sample ? 3 : 2;
+    if (a.per_sample) {
+      if (a.s_batch_stride % 4 != 0) {
+        set_error("node_gemm_tc: per-sample support stride must be a multiple of 4 floats");
+        return GWN_ERR_UNSUPPORTED;
+      }
+      cuuint64_t xd[4] = {(cuuint64_t)CH, (cuuint64_t)a.V, (cuuint64_t)a.L, (cuuint64_t)a.B};
+      cuuint64_t xs[3] = {(cuuint64_t)CH * 4, (cuuint64_t)a.V * CH * 4, (cuuint64_t)a.L * a.V * CH * 4};
+      cuuint32_t xb[4] = {CH, BLOCK_K, SLABS, 1};
+      GWN_TRY(encode(&maps.x[s], a.X[s], 4, xd, xs, xb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    } else {
+      cuuint64_t xd[3] = {(cuuint64_t)CH, (cuuint64_t)a.V, (cuuint64_t)nslabs};
+      cuuint64_t xs[2] = {(cuuint64_t)CH * 4, (cuuint64_t)a.V * CH * 4};
+      cuuint32_t xb[3] = {CH, BLOCK_K, SLABS};
+      GWN_TRY(encode(&maps.x[s], a.X[s], 3, xd, xs, xb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    }
+    GWN_TRY(encode(&maps.s[s], a.S[s], srank, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_128B));
     if (X3) {
       if (!a.Slo[s] || (reinterpret_cast<uintptr_t>(a.Slo[s]) & 15)) {
         set_error("node_gemm_tc: 3xTF32 mode needs 16-byte aligned support remainders");
         return GWN_ERR_UNSUPPORTED;
       }
-      GWN_TRY(encode(&maps.slo[s], a.Slo[s], 2, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_128B));
+      GWN_TRY(encode(&maps.slo[s], a.Slo[s], srank, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_128B));
     } else {
       maps.slo[s] = maps.s[s];
     }

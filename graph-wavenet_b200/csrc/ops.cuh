@@ -50,6 +50,8 @@ struct TcSupports {
   const float* Slo[MAXSUP];   // fp32x3 tier: remainders S - tf32_trunc(S)
   int ld;
   int precision;   // gwn_precision
+  int per_sample;  // 1: S / Slo point at sample 0 of a per-sample support set, samples batch_stride floats apart
+  i64 batch_stride;
 };
 inline int node_gemm(const SupportView* sup, int nsup, bool kcat, const float* const* X,
                      float* const* Y, const float* const* add, const float* add2, int B, int L, int T_out, int V, int C,
@@ -66,8 +68,10 @@ inline int node_gemm(const SupportView* sup, int nsup, bool kcat, const float* c
     const int nout = kcat ? 1 : nsup;
     for (int s = 0; s < nout; ++s) { t.Y[s] = Y[s]; t.add[s] = add ? add[s] : nullptr; }
     t.ld = tcs->ld; t.nsup = nsup; t.kcat = kcat ? 1 : 0; t.add2 = add2; t.B = B; t.L = L; t.T_out = T_out; t.V = V;
+    t.per_sample = tcs->per_sample; t.s_batch_stride = tcs->batch_stride;
     return node_gemm_tc(t, stream);
   }
+  GWN_CHECK_ARG(!(tcs && tcs->per_sample), "node_gemm: per-sample supports need the tcgen05 tiers (the caller loops over samples otherwise)");
   LdSupport a;
   LdSlab b;
   EpSlab e;
