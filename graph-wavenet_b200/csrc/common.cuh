@@ -18,6 +18,7 @@
 #include <vector>
 #include <algorithm>
 #include <type_traits>
+#include <utility>
 
 #include <cuda_runtime.h>
 
@@ -74,6 +75,43 @@ struct ProfScope {
     }                                                                                       \
   } while (0)
 #define GWN_LAUNCH_CHECK() GWN_CUDA(cudaGetLastError())
+#endif
+
+// Programmatic dependent launch (PDL): every kernel of the library is launched with the programmatic-stream-
+// serialization attribute and executes GWN_PDL_ENTRY() (or, in the tcgen05 kernels, pdl_wait() after the
+// barrier/TMEM prologue) before it touches global memory.  `griddepcontrol.wait` returns once the preceding kernel
+// of the stream has completed and flushed, so the memory ordering is that of a plain stream; what overlaps is the
+// launch latency and the prologue of kernel n+1 with the tail of kernel n -- ~180 launches per training step, also
+// inside the captured CUDA graph (programmatic edges).  The trigger comes AFTER the wait (and after the TMEM
+// allocation in the tcgen05 kernels), so at most one dependent grid is resident and waiting and it can never hold
+// tensor memory that its predecessor still has to allocate.  GWNET_B200_PDL=0 turns the attribute off.
+#if GWN_EMU
+#define GWN_PDL_ENTRY() do {} while (0)
+#else
+#define GWN_PDL_ENTRY()                                             \
+  do {                                                              \
+    asm volatile("griddepcontrol.wait;" ::: "memory");              \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  if (pdl_enabled()) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 #endif
 
 // ---------------------------------------------------------------- small device helpers

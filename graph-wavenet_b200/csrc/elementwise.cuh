@@ -39,8 +39,7 @@ inline T warp_max(T v) { return v; }
     if (_n > 0) {                                                                           \
       i64 _b = (_n + 255) / 256;                                                            \
       if (_b > 148 * 32) _b = 148 * 32;                                                     \
-      kernel<<<(unsigned)_b, 256, 0, stream>>>(__VA_ARGS__);                                \
-      GWN_LAUNCH_CHECK();                                                                   \
+      GWN_CUDA(::gwn::launch_kernel(kernel, dim3((unsigned)_b), dim3(256), 0, stream, __VA_ARGS__)); \
       ::gwn::count_launch();                                                                \
     }                                                                                       \
   } while (0)
@@ -50,8 +49,7 @@ inline T warp_max(T v) { return v; }
     if (_n > 0) {                                                                           \
       i64 _b = (_n + 7) / 8;                                                                \
       if (_b > 148 * 16) _b = 148 * 16;                                                     \
-      kernel<<<(unsigned)_b, 256, 0, stream>>>(__VA_ARGS__);                                \
-      GWN_LAUNCH_CHECK();                                                                   \
+      GWN_CUDA(::gwn::launch_kernel(kernel, dim3((unsigned)_b), dim3(256), 0, stream, __VA_ARGS__)); \
       ::gwn::count_launch();                                                                \
     }                                                                                       \
   } while (0)
@@ -78,6 +76,7 @@ struct Sizes4 {
 // dst[i0,i1,i2,i3] = src[i0,i1,i2,i3]; iteration is dst-major over `order` (a permutation of the dims
 // sorted by decreasing dst stride) so writes coalesce.
 GWN_GLOBAL permute4d_kernel(const float* src, Strides4 ss, float* dst, Strides4 ds, Sizes4 sz, Sizes4 ord, i64 total) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(i, total) {
     i64 r = i, idx[4];
 #pragma unroll
@@ -98,6 +97,7 @@ GWN_GLOBAL permute4d_kernel(const float* src, Strides4 ss, float* dst, Strides4 
 
 // Pack a static support into zero-padded row-major A[v*ld + w] and its transpose AT[w*ld + v].
 GWN_GLOBAL support_pack_kernel(const float* A, i64 rs, i64 cs, float* Ap, float* ATp, int N, int ld) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(i, (i64)N * ld) {
     int v = (int)(i / ld), w = (int)(i - (i64)v * ld);
     float val = (w < N) ? A[v * rs + w * cs] : 0.0f;
@@ -109,6 +109,7 @@ GWN_GLOBAL support_pack_kernel(const float* A, i64 rs, i64 cs, float* Ap, float*
 
 // adp = softmax(relu(E1 @ E2), dim=1)   (model.py:187); one warp per row; writes A and A^T (padded).
 GWN_GLOBAL adp_fwd_kernel(const float* E1, const float* E2, int R, float* Ap, float* ATp, int N, int ld) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH_WARP_ROW(v, N, lane, WS) {
     float* row = Ap + v * ld;
     float mx = 0.0f;  // relu output is >= 0
@@ -140,6 +141,7 @@ GWN_GLOBAL adp_fwd_kernel(const float* E1, const float* E2, int R, float* Ap, fl
 // Backward of adp: dR = P*(dP - sum_w dP*P) masked by (E1@E2 > 0); dE1[v,k] = sum_w dR[v,w] E2[k,w].
 GWN_GLOBAL adp_bwd_rows_kernel(const float* dA, const float* Ap, const float* E1, const float* E2, int R, float* dR,
                                float* dE1, int N, int ld) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH_WARP_ROW(v, N, lane, WS) {
     float s = 0.0f;
     for (int w = lane; w < N; w += WS) s = fmaf(dA[v * ld + w], Ap[v * ld + w], s);
@@ -167,6 +169,7 @@ GWN_GLOBAL adp_bwd_rows_kernel(const float* dA, const float* Ap, const float* E1
 }
 // dE2[k,w] = sum_v E1[v,k] dR[v,w]
 GWN_GLOBAL adp_bwd_cols_kernel(const float* dR, const float* E1, int R, float* dE2, int N, int ld) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(i, (i64)R * N) {
     int k = (int)(i / N), w = (int)(i - (i64)k * N);
     float acc = 0.0f;
@@ -179,6 +182,7 @@ GWN_GLOBAL adp_bwd_cols_kernel(const float* dR, const float* E1, int R, float* d
 // x0[b,t,n,c] = bias[c] + sum_f W[c,f] * (t >= pad ? in[b,f,n,t-pad] : 0)
 GWN_GLOBAL start_fwd_kernel(const float* in, Strides4 is, const float* W, const float* bias, float* x0, int B, int F,
                             int N, int L0, int pad, int C) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(i, (i64)B * L0 * N * C) {
     int c = (int)(i % C);
     i64 p = i / C;
@@ -195,6 +199,7 @@ GWN_GLOBAL start_fwd_kernel(const float* in, Strides4 is, const float* W, const 
 // grad wrt the network input, contiguous [B,F,N,T]: gi[b,f,n,t] = sum_c W[c,f] dx0[(b,t+pad,n), c]
 GWN_GLOBAL start_dgrad_kernel(const float* dx0, const float* W, float* gi, int B, int F, int N, int T, int L0, int pad,
                               int C) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(i, (i64)B * F * N * T) {
     int t = (int)(i % T);
     i64 r = i / T;
@@ -213,6 +218,7 @@ GWN_GLOBAL start_dgrad_kernel(const float* dx0, const float* W, float* gi, int B
 // a = gamma*rstd, c = beta - mean*a; running stats with momentum and unbiased var; num_batches_tracked += 1.
 GWN_GLOBAL bn_finalize_kernel(const double* sums, double count, const float* gamma, const float* beta, float* rmean,
                               float* rvar, long long* nbt, float eps, float momentum, float* ac, float* mr, int C) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(c, C) {
     double mean = sums[c] / count;
     double var = sums[C + c] / count - mean * mean;
@@ -232,6 +238,7 @@ GWN_GLOBAL bn_finalize_kernel(const double* sums, double count, const float* gam
 // Eval mode: fold constants from the running statistics.
 GWN_GLOBAL bn_eval_kernel(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps,
                           float* ac, float* mr, int C) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(c, C) {
     float rstd = 1.0f / sqrtf(rvar[c] + eps);
     float a = gamma[c] * rstd;
@@ -248,6 +255,7 @@ GWN_GLOBAL bn_eval_kernel(const float* gamma, const float* beta, const float* rm
 GWN_GLOBAL bn_bwd_apply_kernel(float* dy, const float* u, const float* ac, const float* mr, const double* bsum,
                                double count, int training, float* dgamma, float* dbeta, i64 P, int C, float* dh,
                                DropoutSrc drop) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(i4, P * C / 4) {
     float kp[4] = {1.f, 1.f, 1.f, 1.f};
     if (dh) drop.keep4(i4 * 4, kp);
@@ -285,6 +293,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply8_kernel(float* __restrict__ 
                                                             const double* __restrict__ bsum, double count, int training,
                                                             float* dgamma, float* dbeta, i64 n8, int C, float* __restrict__ dh,
                                                             DropoutSrc drop) {
+  GWN_PDL_ENTRY();
   const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = (int)((t0 * 8) & (i64)(C - 1));
   float a[8], mean[8], rstd[8], m1[8], m2[8];
@@ -336,6 +345,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply8_kernel(float* __restrict__ 
 // bias_g'[ch] = b_g[ch] + sum_{tap,ci} W_g[ch][ci][tap] * c[ci]      (conv(W, a*u + c) = conv(W*diag(a), u) + W.c)
 GWN_GLOBAL pack_tcn_fwd_kernel(const float* wf, const float* wg, const float* bf, const float* bg, const float* ac, float* Wp,
                                float* bfp, float* bgp, int D, int C, float* Wlo) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH_WARP_ROW(n, 2 * D, lane, WS) {   // one warp per packed output row n = 2*ch + gate
     const int ch = (int)(n >> 1), g = (int)(n & 1);
     const float* w = g ? wg : wf;
@@ -354,6 +364,7 @@ GWN_GLOBAL pack_tcn_fwd_kernel(const float* wf, const float* wg, const float* bf
 }
 // Gated conv input gradient:  Wd[ci][tap*2D + j] = W_{j&1}[j>>1][ci][tap]
 GWN_GLOBAL pack_tcn_dgrad_kernel(const float* wf, const float* wg, float* Wd, int D, int C, float* Wlo) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(i, (i64)C * 4 * D) {
     const int ci = (int)(i / (4 * D)), k = (int)(i - (i64)ci * 4 * D);
     const int tap = k / (2 * D), j = k - tap * 2 * D;
@@ -366,6 +377,7 @@ GWN_GLOBAL pack_tcn_dgrad_kernel(const float* wf, const float* wg, float* Wd, in
 // S[j] = sum_p dpre[p][j].  With the BatchNorm affine x = a*u + c of the layer below:  dW = a[ci]*R + c[ci]*S,  db = S.
 GWN_GLOBAL tcn_wgrad_finalize_kernel(const float* R, const float* S, const float* ac, float* dwf, float* dwg, float* dbf,
                                      float* dbg, int D, int C) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(i, (i64)2 * D * 2 * C + 2 * D) {
     if (i < (i64)2 * D * 2 * C) {
       const int j = (int)(i / (2 * C)), k = (int)(i - (i64)j * 2 * C);
@@ -381,6 +393,7 @@ GWN_GLOBAL tcn_wgrad_finalize_kernel(const float* R, const float* S, const float
 }
 // WT[c][r] = W[r][c]
 GWN_GLOBAL transpose_kernel(const float* W, float* WT, int R, int Cc, float* WTlo) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(i, (i64)R * Cc) {
     const int c = (int)(i / R), r = (int)(i - (i64)c * R);
     const float v = W[(i64)r * Cc + c];
@@ -398,6 +411,7 @@ struct SkipWeights {
 };
 GWN_GLOBAL pack_skip_kernel(SkipWeights sw, int nL, int D, int Sk, float* Wcat, float* Wcat_lo, float* WT, float* WT_lo,
                             float* bsum) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(i, (i64)Sk * nL * D + Sk) {
     if (i < (i64)Sk * nL * D) {
       const int sk = (int)(i / (nL * D)), k = (int)(i - (i64)sk * nL * D);
@@ -415,6 +429,7 @@ GWN_GLOBAL pack_skip_kernel(SkipWeights sw, int nL, int D, int Sk, float* Wcat, 
 }
 // W2T[e*ldo + o] = W2[o*E + e] (zero for o >= O): the last head layer transposed, rows padded to ldo floats
 GWN_GLOBAL pack_e2t_kernel(const float* W2, float* WT, float* WT_lo, int O, int E, int ldo) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(i, (i64)E * ldo) {
     const int e = (int)(i / ldo), o = (int)(i - (i64)e * ldo);
     const float v = o < O ? W2[(i64)o * E + e] : 0.0f;
@@ -424,11 +439,13 @@ GWN_GLOBAL pack_e2t_kernel(const float* W2, float* WT, float* WT_lo, int O, int 
 }
 // lo[i] = w[i] - tf32_trunc(w[i])
 GWN_GLOBAL split_lo_kernel(const float* w, float* lo, i64 n) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(i, n) { lo[i] = tf32_lo(w[i]); }
 }
 
 // dst[p, c] = (src ? src[p,c] : 0) + (t >= L - T_out ? win[(b, t-(L-T_out), n), c] : 0)
 GWN_GLOBAL add_window_kernel(float* dst, const float* src, const float* win, int B, int L, int N, int C, int T_out) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(i, (i64)B * L * N * C) {
     i64 p = i / C;
     int c = (int)(i - p * C);

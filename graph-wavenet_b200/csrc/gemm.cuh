@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(T::NT, 512 / T::NT) gemm_kernel(AL al, BL bl, 
   constexpr int ASZ = ANAT ? BM * KI_STRIDE : BK * AS, BSZ = BNAT ? BN * KI_STRIDE : BK * BS;
   __shared__ __align__(16) float As[2][ASZ];
   __shared__ __align__(16) float Bs[2][BSZ];
+  GWN_PDL_ENTRY();
 
   const int tid = threadIdx.x;
   const int bz = blockIdx.z / ksplit, kz = blockIdx.z % ksplit;
@@ -313,9 +314,9 @@ int launch_gemm(const AL& al, const BL& bl, const EP& ep, const GemmShape& s, cu
   GWN_CHECK_ARG(gx <= 2147483647LL && gy <= 65535 && gz <= 65535, "gemm: grid too large (%lld,%lld,%lld)", gx, gy, gz);
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz);
   switch (current_math()) {
-    case 1: gemm_kernel<T, AL, BL, EP, 1><<<grid, T::NT, 0, stream>>>(al, bl, ep, s.M, s.N, s.K, kchunk, ksplit); break;
-    case 3: gemm_kernel<T, AL, BL, EP, 3><<<grid, T::NT, 0, stream>>>(al, bl, ep, s.M, s.N, s.K, kchunk, ksplit); break;
-    default: gemm_kernel<T, AL, BL, EP, 0><<<grid, T::NT, 0, stream>>>(al, bl, ep, s.M, s.N, s.K, kchunk, ksplit); break;
+    case 1: GWN_CUDA(launch_kernel(gemm_kernel<T, AL, BL, EP, 1>, grid, dim3(T::NT), 0, stream, al, bl, ep, s.M, s.N, s.K, kchunk, ksplit)); break;
+    case 3: GWN_CUDA(launch_kernel(gemm_kernel<T, AL, BL, EP, 3>, grid, dim3(T::NT), 0, stream, al, bl, ep, s.M, s.N, s.K, kchunk, ksplit)); break;
+    default: GWN_CUDA(launch_kernel(gemm_kernel<T, AL, BL, EP, 0>, grid, dim3(T::NT), 0, stream, al, bl, ep, s.M, s.N, s.K, kchunk, ksplit)); break;
   }
   GWN_LAUNCH_CHECK();
   count_launch();

@@ -16,6 +16,15 @@ namespace gwn {
 static thread_local char g_err[1024] = "";
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+#if !GWN_EMU
+bool pdl_enabled() {   // GWNET_B200_PDL=0 launches every kernel with plain stream ordering (A/B switch, read once)
+  static const bool on = [] {
+    const char* e = getenv("GWNET_B200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+#endif
 static thread_local int g_math = 0;
 int current_math() { return g_math; }
 void set_current_math(int m) { g_math = m; }
@@ -137,6 +146,8 @@ struct gwn_plan {
   gwn::i64 o_part, part_floats, o_buf0, o_buf1, o_dh, o_dg, o_dpre, o_dgh, o_dout, o_de1, o_dskip, o_dA, o_dR, o_bsum, bwd_floats;
   std::vector<gwn::i64> o_dsegs;   // per layer when the support gradient is deferred to ONE launch per backward pass
   bool defer_dA;
+  std::vector<gwn::i64> o_dpre_l, o_dh_l;   // per layer when the weight gradients are deferred (else all = o_dpre / o_dh)
+  bool defer_wgrad;
   gwn::i64 P(int i) const { return (gwn::i64)c.batch * L[i] * c.num_nodes; }
   gwn::i64 P0() const { return (gwn::i64)c.batch * L0 * c.num_nodes; }
   gwn::i64 PT() const { return (gwn::i64)c.batch * T_out * c.num_nodes; }
@@ -335,7 +346,17 @@ static int build_plan(gwn_plan* p) {
   p->o_part = take(p->part_floats);
   p->o_buf0 = take(maxP * C);
   p->o_buf1 = take(maxP * C);
+  // Weight gradients of all layers in ONE tcgen05 reduction per kind at the end of the backward pass (like the support
+  // gradient): a per-layer launch pays ~10 us of prologue / pipeline fill / slot write plus an ~8 us slot reduction,
+  // 26 launches per step at the METR-LA shape; deferred, dpre_i and dh_i stay alive in per-layer buffers instead.
+  {
+    const char* e = getenv("GWNET_B200_DEFER_WGRAD");
+    p->defer_wgrad = tc_tier && nL >= 2 && p->nseg <= 7 && !(e && e[0] == '0');
+  }
+  p->o_dh_l.assign(nL, 0);
+  p->o_dpre_l.assign(nL, 0);
   p->o_dh = take(maxPi * C);   // du * dropout keep-mask (gradient wrt the pre-dropout mlp output)
+  for (int i = 0; i < nL; ++i) p->o_dh_l[i] = p->defer_wgrad ? take(p->P(i) * C) : p->o_dh;
   p->o_dsegs.assign(nL, 0);
   if (p->defer_dA) {
     for (int i = 0; i < nL; ++i) p->o_dsegs[i] = take(p->P(i) * D * p->nseg);   // t tensors stay alive until the dA launch
@@ -345,6 +366,7 @@ static int build_plan(gwn_plan* p) {
   }
   p->o_dg = take(maxPi * D);
   p->o_dpre = take(maxPi * 2 * D);
+  for (int i = 0; i < nL; ++i) p->o_dpre_l[i] = p->defer_wgrad ? take(p->P(i) * 2 * D) : p->o_dpre;
   p->o_dgh = take((i64)nL * p->PT() * D);
   p->o_dout = take(p->PT() * p->ldo);
   p->o_de1 = take(p->PT() * E);
@@ -970,8 +992,13 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
   const float* dA_X[TR_MAXSRC];
   const float* dA_T[TR_MAXSRC];
   int dA_slabs[TR_MAXSRC], dA_pairs = 0;
-  float* dpre = sc + p->o_dpre;
+  const bool defer_w = !GWN_EMU && p->defer_wgrad && tcpos_ok(p) && tsc.partial != nullptr;
+  struct WJob { int layer; const float* prev; const float* prev_ac; const float* dpre; const float* g; const float* dh; };
+  WJob wj_tcn[64], wj_mlp[64];
+  int n_wj_tcn = 0, n_wj_mlp = 0;
   for (int i = nL - 1; i >= 0; --i) {
+    float* dpre = sc + (defer_w ? p->o_dpre_l[i] : p->o_dpre);
+    float* dh_buf = sc + (defer_w ? p->o_dh_l[i] : p->o_dh);
     const bool live = i < nL - 1;   // the last layer's gcn/bn output is discarded (model.py:238)
     const i64 Pi = p->P(i);
     const float* prev = i == 0 ? ws + p->o_x0 : ws + p->o_u[i - 1];
@@ -982,20 +1009,21 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     const float* dgp;   // gradient wrt g_i
     if (live) {
       const DropoutSrc ldrop = layer_dropout(p, training, dmode, a->keep_masks, a->seed, i, a->seed_device);
-      const bool use_dh = ldrop.mode != GWN_DROPOUT_NONE;   // materialise du * keep once instead of regenerating masks
+      // materialise du * keep once instead of regenerating masks; deferred weight gradients need dh_i kept anyway
+      const bool use_dh = ldrop.mode != GWN_DROPOUT_NONE || (defer_w && nL <= 64);
       {
       ProfScope prof("bn_bwd_apply", st, 4.0 * Pi * C * (use_dh ? 4.0 : 3.0), 0.0);
 #if !GWN_EMU
       if (C >= 8 && C <= 2048 && (C & (C - 1)) == 0 && (Pi * C) % 8 == 0) {
         GWN_LAUNCH_1D(bn_bwd_apply8_kernel, Pi * C / 8, st, cur, ws + p->o_u[i], ws + p->o_ac[i], ws + p->o_mr[i],
                     reinterpret_cast<const double*>(sc + p->o_bsum + (i64)i * 4 * C), (double)Pi, training,
-                    G(p->li[i].bnw), G(p->li[i].bnb), Pi * C / 8, C, use_dh ? sc + p->o_dh : (float*)nullptr, ldrop);
+                    G(p->li[i].bnw), G(p->li[i].bnb), Pi * C / 8, C, use_dh ? dh_buf : (float*)nullptr, ldrop);
       } else
 #endif
       {
         GWN_LAUNCH_1D(bn_bwd_apply_kernel, Pi * C / 4, st, cur, ws + p->o_u[i], ws + p->o_ac[i], ws + p->o_mr[i],
                     reinterpret_cast<const double*>(sc + p->o_bsum + (i64)i * 4 * C), (double)Pi, training,
-                    G(p->li[i].bnw), G(p->li[i].bnb), Pi, C, use_dh ? sc + p->o_dh : (float*)nullptr, ldrop);
+                    G(p->li[i].bnw), G(p->li[i].bnb), Pi, C, use_dh ? dh_buf : (float*)nullptr, ldrop);
       }
 
       }
@@ -1003,7 +1031,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
       for (int q = 0; q < p->nseg; ++q) segs[q] = g + (i64)q * Pi * D;
       MlpBwdArgs m;
       memset(&m, 0, sizeof(m));
-      m.dh = use_dh ? sc + p->o_dh : cur;
+      m.dh = use_dh ? dh_buf : cur;
       m.drop = make_dropout(GWN_DROPOUT_NONE, nullptr, 0, 0, 0.f);
       m.segs = segs; m.nseg = p->nseg; m.P = Pi; m.D = D; m.C_out = C;
       m.W = P_<float>(prm, c.gcn ? p->li[i].mw : p->li[i].rw);
@@ -1017,6 +1045,11 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
       }
       m.dW = G(c.gcn ? p->li[i].mw : p->li[i].rw);
       m.dbias = G(c.gcn ? p->li[i].mb : p->li[i].rb);
+      if (defer_w && nL <= 64 && D == 32 && C == 32 && Pi < 2147483647LL) {   // weight gradient after the layer loop
+        wj_mlp[n_wj_mlp++] = WJob{i, nullptr, nullptr, nullptr, g, m.dh};
+        m.dW = nullptr;
+        m.dbias = nullptr;
+      }
       m.ts = tsc;
       GWN_TRY(mlp_backward(m, st));
       if (c.gcn) {
@@ -1143,8 +1176,13 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
       }
     }
     bool wgrad_done = false;
-    ProfScope prof_w("gated_tcn_wgrad", st, 4.0 * ((double)Pin * C + (double)Pi * 2 * D), 2.0 * Pi * 2 * D * (2.0 * C + 1));
-    if (tcpos_ok(p) && tsc.partial) {   // tcgen05 + TMA reduction over all positions; the slot reduction folds the
+    if (defer_w && nL <= 64) {
+      wj_tcn[n_wj_tcn++] = WJob{i, prev, prev_ac, dpre, nullptr, nullptr};
+      wgrad_done = true;
+    }
+    ProfScope prof_w("gated_tcn_wgrad", st, wgrad_done ? 0.0 : 4.0 * ((double)Pin * C + (double)Pi * 2 * D),
+                     wgrad_done ? 0.0 : 2.0 * Pi * 2 * D * (2.0 * C + 1));
+    if (!wgrad_done && tcpos_ok(p) && tsc.partial) {   // tcgen05 + TMA reduction over all positions; the slot reduction folds the
 #if !GWN_EMU                            // BatchNorm affine of the layer below and scatters to the four gradients
       TcRedArgs t;
       memset(&t, 0, sizeof(t));
@@ -1180,6 +1218,99 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     }
     std::swap(cur, oth);
   }
+#if !GWN_EMU
+  // ---- deferred weight gradients: all layers' gated-conv (then all layers' mlp) reductions as jobs of one launch each
+  for (int kind = 0; kind < 2; ++kind) {
+    const WJob* wj = kind == 0 ? wj_tcn : wj_mlp;
+    const int nj = kind == 0 ? n_wj_tcn : n_wj_mlp;
+    if (nj == 0) continue;
+    double bytes = 0, flops = 0;
+    for (int q = 0; q < nj; ++q) {
+      const int i = wj[q].layer;
+      const double Pi = (double)p->P(i), Pin = (double)B * p->Lin(i) * N;
+      if (kind == 0) { bytes += 4.0 * (Pin * C + Pi * 2 * D); flops += 2.0 * Pi * 2 * D * (2.0 * C + 1); }
+      else { bytes += 4.0 * Pi * ((double)p->nseg * D + C); flops += 2.0 * Pi * (p->nseg * D + 1.0) * C; }
+    }
+    ProfScope prof(kind == 0 ? "gated_tcn_wgrad" : "gcn_mlp_wgrad", st, bytes, flops);
+    for (int q0 = 0; q0 < nj; q0 += TR_MAXJOBS) {
+      const int nq = std::min(TR_MAXJOBS, nj - q0);
+      if (nq == 1) {   // a lone job: the single-reduction launch
+        const WJob& w = wj[q0];
+        const int i = w.layer;
+        TcRedArgs t;
+        memset(&t, 0, sizeof(t));
+        t.mode = 0; t.x3 = tsc.x3; t.partial = tsc.partial; t.partial_floats = tsc.floats;
+        TcRedResult rr;
+        if (kind == 0) {
+          t.na = 2;
+          t.a[0] = TcRedSrc{w.prev, p->Lin(i) * N, 32, 0, 0, 0};
+          t.a[1] = TcRedSrc{w.prev, p->Lin(i) * N, 32, 0, p->dil[i] * N, 0};
+          t.b[0] = TcRedSrc{w.dpre, p->L[i] * N, 2 * D, 0, 0, 0};
+          t.N = 2 * D; t.nb = B; t.rows = p->L[i] * N;
+          int rst = launch_tcred(t, st, &rr);
+          GWN_CHECK_ARG(rst <= 0, "backward: deferred gated-conv weight gradient failed");
+          GWN_CHECK_ARG(rst == 0, "backward: deferred gated-conv weight gradient not eligible for the tcgen05 path");
+          tc::SlotTcnOut f{w.prev_ac, G(p->li[i].fw), G(p->li[i].gw), G(p->li[i].fb), G(p->li[i].gb), C, D};
+          GWN_TRY(launch_slot_reduce(tsc.partial, rr, (i64)2 * C * 2 * D + 2 * D, f, st));
+        } else {
+          t.na = p->nseg;
+          for (int k = 0; k < p->nseg; ++k) t.a[k] = TcRedSrc{w.g + (i64)k * p->P(i) * D, (int)p->P(i), 32, 0, 0, 0};
+          t.b[0] = TcRedSrc{w.dh, (int)p->P(i), 32, 0, 0, 0};
+          t.N = 32; t.nb = 1; t.rows = (int)p->P(i);
+          int rst = launch_tcred(t, st, &rr);
+          GWN_CHECK_ARG(rst == 0, "backward: deferred mlp weight gradient not eligible for the tcgen05 path");
+          tc::SlotMlpOut f{G(c.gcn ? p->li[i].mw : p->li[i].rw), G(c.gcn ? p->li[i].mb : p->li[i].rb), p->nseg * D, p->nseg};
+          GWN_TRY(launch_slot_reduce(tsc.partial, rr, (i64)p->nseg * 32 * 32 + 32, f, st));
+        }
+        continue;
+      }
+      TcRedJobsArgs ja;
+      memset(&ja, 0, sizeof(ja));
+      ja.njobs = nq; ja.x3 = tsc.x3; ja.partial = tsc.partial; ja.partial_floats = tsc.floats;
+      if (kind == 0) { ja.na = 2; ja.N = 2 * D; ja.seg[0] = ja.seg[1] = 0; }
+      else { ja.na = p->nseg; ja.N = 32; for (int k = 0; k < p->nseg; ++k) ja.seg[k] = k; }
+      for (int q = 0; q < nq; ++q) {
+        const WJob& w = wj[q0 + q];
+        const int i = w.layer;
+        TcRedJob& j = ja.job[q];
+        if (kind == 0) {
+          j.a_src = w.prev; j.a_rows_src = p->Lin(i) * N; j.nseg_src = 1; j.a_seg_stride = 0;
+          j.b_src = w.dpre; j.b_width = 2 * D; j.nb = B; j.rows = p->L[i] * N;
+          j.rshift[0] = 0; j.rshift[1] = p->dil[i] * N;
+        } else {
+          j.a_src = w.g; j.a_rows_src = (int)p->P(i); j.nseg_src = p->nseg; j.a_seg_stride = p->P(i) * D;
+          j.b_src = w.dh; j.b_width = 32; j.nb = 1; j.rows = (int)p->P(i);
+        }
+      }
+      TcRedResult rr;
+      int rst = launch_tcred_jobs(ja, st, &rr);
+      if (rst > 0) return rst;
+      GWN_CHECK_ARG(rst == 0, "backward: deferred weight gradients not eligible for the tcgen05 path");
+      if (kind == 0) {
+        tc::SlotJobs<tc::SlotTcnOut> f;
+        memset(&f, 0, sizeof(f));
+        for (int q = 0; q < nq; ++q) {
+          const WJob& w = wj[q0 + q];
+          const int i = w.layer;
+          f.f[q] = tc::SlotTcnOut{w.prev_ac, G(p->li[i].fw), G(p->li[i].gw), G(p->li[i].fb), G(p->li[i].gb), C, D};
+        }
+        for (int q = 0; q <= nq; ++q) f.cta0[q] = rr.job_cta0[q];
+        f.nout_job = (i64)2 * C * 2 * D + 2 * D;
+        GWN_TRY(launch_slot_reduce(tsc.partial, rr, f.nout_job * nq, f, st));
+      } else {
+        tc::SlotJobs<tc::SlotMlpOut> f;
+        memset(&f, 0, sizeof(f));
+        for (int q = 0; q < nq; ++q) {
+          const int i = wj[q0 + q].layer;
+          f.f[q] = tc::SlotMlpOut{G(c.gcn ? p->li[i].mw : p->li[i].rw), G(c.gcn ? p->li[i].mb : p->li[i].rb), p->nseg * D, p->nseg};
+        }
+        for (int q = 0; q <= nq; ++q) f.cta0[q] = rr.job_cta0[q];
+        f.nout_job = (i64)p->nseg * 32 * 32 + 32;
+        GWN_TRY(launch_slot_reduce(tsc.partial, rr, f.nout_job * nq, f, st));
+      }
+    }
+  }
+#endif
   // ---- adaptive-support gradient of ALL layers in one tcgen05 reduction (dA sums over 7 layers x 2 hops)
   if (dA_pairs > 0) {
     double slabs = 0;

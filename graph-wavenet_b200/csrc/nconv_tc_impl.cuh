@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  GWN_PDL_ENTRY();   // prologue above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail
   const int per_out = p.n_jt * p.n_wt;
 
   if (warp == 0 && lane == 0) {
@@ -225,30 +226,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
-      const bool has_ad = ad != nullptr, has_ad2 = ad2 != nullptr;   // warp-uniform
-      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-        // Addends first -- unconditional, clamped addresses so that the 16 loads issue back to back (per-element
-        // predication made each load its own reconvergence block and serialised their latencies) -- then the
-        // accumulator columns, then the stores.
-        float av[16];
+      const bool has_ad = slab_ok && ad != nullptr, has_ad2 = slab_ok && ad2 != nullptr;   // warp-uniform
+      // Columns in groups of 64: all addend loads of a group are issued back to back (unconditional, clamped
+      // addresses: per-element predication made each load its own reconvergence block and serialised their
+      // latencies), then the group's four accumulator reads, then the stores.  With 16-column groups the backward
+      // launches paid one exposed L2/HBM round trip per 16 columns -- 13 per tile -- and ran 1.4-2x longer than the
+      // addend-free forward launches of the same MMA work (ncu launch lists r01c/r01f).
+      constexpr int GC = 64;
+      for (int g0 = 0; g0 < p.n_tile; g0 += GC) {
+        float av[GC];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) av[j] = 0.0f;
-        if (slab_ok && has_ad) {
+        for (int j = 0; j < GC; ++j) av[j] = 0.0f;
+        if (has_ad) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) av[j] = __ldg(ad + (size_t)min(w_base + c0 + j, p.V - 1) * CH);
+          for (int j = 0; j < GC; ++j) av[j] = __ldg(ad + (size_t)min(w_base + g0 + j, p.V - 1) * CH);
         }
-        if (slab_ok && has_ad2) {
+        if (has_ad2) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) av[j] += __ldg(ad2 + (size_t)min(w_base + c0 + j, p.V - 1) * CH);
+          for (int j = 0; j < GC; ++j) av[j] += __ldg(ad2 + (size_t)min(w_base + g0 + j, p.V - 1) * CH);
         }
-        uint32_t r[16];
-        tc_ld16(taddr + c0, r);
-        tc_wait_ld();
-        if (slab_ok) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int w = w_base + c0 + j;
-            if (w < p.V) y[(size_t)w * CH] = __uint_as_float(r[j]) + av[j];
+        for (int cc = 0; cc < GC; cc += 16) {
+          const int c0 = g0 + cc;
+          if (c0 < p.n_tile) {   // warp-uniform
+            uint32_t r[16];
+            tc_ld16(taddr + c0, r);
+            tc_wait_ld();
+            if (slab_ok) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int w = w_base + c0 + j;
+                if (w < p.V) y[(size_t)w * CH] = __uint_as_float(r[j]) + av[cc + j];
+              }
+            }
           }
         }
       }
@@ -284,6 +294,16 @@ int tc_error_flag(int reset) {
   return v;
 }
 
+static int tc_num_sms() {
+  static const int n = [] {
+    int dev = 0, v = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
 template <bool X3>
 static int node_gemm_tc_impl(const NodeTcArgs& a, cudaStream_t stream) {
   using namespace tc;
@@ -301,12 +321,35 @@ static int node_gemm_tc_impl(const NodeTcArgs& a, cudaStream_t stream) {
   Params p;
   memset(&p, 0, sizeof(p));
   p.nsup = a.nsup; p.kcat = a.kcat; p.V = a.V; p.L = a.L; p.T_out = a.T_out; p.nslabs = (int)nslabs;
-  p.n_tile = a.V > 256 ? 256 : round_up(a.V, 16);
-  p.n_wt = (a.V + p.n_tile - 1) / p.n_tile;
   p.per_sample = a.per_sample ? 1 : 0;
   p.tps = (a.L + SLABS - 1) / SLABS;
   p.n_jt = a.per_sample ? a.B * p.tps : (int)((nslabs + SLABS - 1) / SLABS);
   p.nkb = (a.V + BLOCK_K - 1) / BLOCK_K;
+  const int nout = a.kcat ? 1 : a.nsup;
+  p.n_tile = a.V > 256 ? 256 : round_up(a.V, 16);
+  if (a.V <= 256) {
+    // Small graphs: the 4-slab row tiles alone are coarse against 148 SMs (METR-LA, L = 12, K-concatenated sum:
+    // 192 tiles = 1.3 waves, i.e. two rounds at 65 % occupancy; L = 4: 64 tiles on 148 SMs).  Splitting the output
+    // columns into n_wt tiles multiplies the tile count, shrinks the stage (more pipeline stages fit) and costs only
+    // the re-read of the X k-block from L2.  Pick the split with the smallest modelled makespan:
+    //   rounds x (k-steps x (columns + per-k-step fixed cost) + per-tile fill/drain).
+    static const int forced = [] {
+      const char* e = getenv("GWNET_B200_NCONV_NWT");
+      return e ? atoi(e) : 0;
+    }();
+    const int nk_total = (a.kcat ? a.nsup : 1) * p.nkb;
+    long long best = -1;
+    for (int nw = 1; nw <= 4; ++nw) {
+      if (forced > 0 && nw != forced) continue;
+      const int nt = round_up((a.V + nw - 1) / nw, 16);
+      const int nwe = (a.V + nt - 1) / nt;
+      const long long tiles_ = (long long)p.n_jt * nwe * nout;
+      const long long rounds = (tiles_ + tc_num_sms() - 1) / tc_num_sms();
+      const long long cost = rounds * ((long long)nk_total * ((nt < 64 ? 64 : nt) + 16) + 300);
+      if (best < 0 || cost < best) { best = cost; p.n_tile = nt; }
+    }
+  }
+  p.n_wt = (a.V + p.n_tile - 1) / p.n_tile;
   const int stage_bytes = (X3 ? 2 : 1) * (X_STAGE_BYTES + p.n_tile * 128);
   p.stages = (SMEM_LIMIT - 2048) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
@@ -314,7 +357,6 @@ static int node_gemm_tc_impl(const NodeTcArgs& a, cudaStream_t stream) {
     set_error("node_gemm_tc: tile does not fit shared memory");
     return GWN_ERR_UNSUPPORTED;
   }
-  const int nout = a.kcat ? 1 : a.nsup;
   const long long tiles = (long long)p.n_jt * p.n_wt * nout;
   if (tiles > 2147483647LL) {
     set_error("node_gemm_tc: too many tiles");
@@ -368,20 +410,16 @@ static int node_gemm_tc_impl(const NodeTcArgs& a, cudaStream_t stream) {
   const int smem_bytes = p.stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  static int num_sms = 148;
   std::call_once(once, [] {
     attr_err = cudaFuncSetAttribute(nconv_tc_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   });
+  const int num_sms = tc_num_sms();
   if (attr_err != cudaSuccess) {
     set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(attr_err));
     return GWN_ERR_CUDA;
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  nconv_tc_kernel<X3><<<grid, NUM_THREADS, smem_bytes, stream>>>(maps, p);
-  GWN_LAUNCH_CHECK();
+  GWN_CUDA(launch_kernel(nconv_tc_kernel<X3>, dim3(grid), dim3(NUM_THREADS), smem_bytes, stream, maps, p));
   count_launch();
   return 0;
 }

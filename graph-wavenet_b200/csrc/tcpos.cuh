@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  GWN_PDL_ENTRY();   // prologue above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail
 
   if (warp == 0 && lane == 0) {
     // ===================================================== TMA producer
@@ -455,8 +456,7 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
     return n;
   }();
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  tcpos_kernel<EP, NCT, X3><<<grid, 128 + 128 * EP::kGroups, smem_bytes, stream>>>(maps, p, ep);
-  GWN_LAUNCH_CHECK();
+  GWN_CUDA(launch_kernel(tcpos_kernel<EP, NCT, X3>, dim3(grid), dim3(128 + 128 * EP::kGroups), smem_bytes, stream, maps, p, ep));
   count_launch();
   return 0;
 #endif

@@ -38,12 +38,37 @@ struct TcRedArgs {
   float* partial;     // scratch for the per-CTA partial results
   i64 partial_floats; // its capacity
 };
+// Several MODE_MN reductions of the same shape class in ONE launch (the weight gradients of all layers, deferred to
+// the end of the backward pass): job q reduces over its own positions,  D_q[(blk, i), n] = sum_p A_q,blk[p][i] * B_q[p][n].
+// The A blocks of a job are 32-column boxes of ONE 4-D tensor [nseg_src][nb][a_rows_src][32] (block j = segment seg[j],
+// rows shifted by rshift[j]); the CTAs are divided among the jobs in proportion to their K extents.
+constexpr int TR_MAXJOBS = 8;
+struct TcRedJob {
+  const float* a_src;
+  int a_rows_src, nseg_src;
+  i64 a_seg_stride;     // floats between consecutive segments of a_src
+  const float* b_src;   // [nb][rows][b_width]
+  int b_width;
+  int nb, rows;         // samples, B rows per sample
+  int rshift[8];        // per A block: source row = B row + rshift
+};
+struct TcRedJobsArgs {
+  int njobs;
+  TcRedJob job[TR_MAXJOBS];
+  int na;               // real A blocks per job (<= 7; the all-ones block is appended)
+  int seg[8];           // per A block: segment of a_src
+  int N;                // B columns (32 or 64 ... <= 256, multiple of 32)
+  int x3;
+  float* partial;
+  i64 partial_floats;
+};
 // What the launch produced: `nslots` partial results of `slot_floats` floats each.
 //   MODE_MN: slot layout [mtiles*128 rows = (blk, i)][N]; MODE_K: [mtiles*128 rows = v][Ntile], slot s covers the
 //   output columns (s % n_nt)*Ntile .. +Ntile.
 struct TcRedResult {
   int nslots, mtiles, N, n_nt, n_mg;   // MODE_K: output tiled n_mg (row groups of mtiles*128) x n_nt (column tiles of N)
   i64 slot_floats;
+  int job_cta0[TR_MAXJOBS + 1];        // multi-job launches: job q wrote the slots job_cta0[q] .. job_cta0[q+1]-1
 };
 
 #if !GWN_EMU
@@ -60,6 +85,10 @@ struct TrParams {
   int ab;                    // MODE_MN: real A blocks per block group
   float* partial;
   i64 slot_floats;
+  // multi-job MODE_MN (njobs > 1): CTA ranges, K extents and A-block coordinates per job
+  int njobs;
+  int job_cta0[TR_MAXJOBS + 1], job_chunks[TR_MAXJOBS], job_cps[TR_MAXJOBS];
+  int jseg[8], jrshift[TR_MAXJOBS][8];
 };
 
 // X3 = 3xTF32 mode (fp32-grade): both operands are activations, so warps 2 and 3 split BOTH tiles of a stage into
@@ -84,8 +113,19 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // output tile of this CTA: (k split, row/block group mg, column group ntile)
   const int n_ot = p.n_nt * p.n_mg;
-  const int ot = (int)(blockIdx.x % n_ot), ntile = ot % p.n_nt, mg = ot / p.n_nt;
-  const int kslot = (int)(blockIdx.x / n_ot), nk = (int)(gridDim.x / n_ot);
+  int ntile, mg, kslot, nk, job = 0, total_chunks = p.total_chunks, cps = p.chunks_per_sample;
+  if (p.njobs > 1) {   // this CTA's job: one output tile per job, its CTAs split K
+    while (job + 1 < p.njobs && (int)blockIdx.x >= p.job_cta0[job + 1]) ++job;
+    ntile = 0; mg = 0;
+    kslot = (int)blockIdx.x - p.job_cta0[job];
+    nk = p.job_cta0[job + 1] - p.job_cta0[job];
+    total_chunks = p.job_chunks[job];
+    cps = p.job_cps[job];
+  } else {
+    const int ot = (int)(blockIdx.x % n_ot);
+    ntile = ot % p.n_nt; mg = ot / p.n_nt;
+    kslot = (int)(blockIdx.x / n_ot); nk = (int)(gridDim.x / n_ot);
+  }
   const int na_loc = p.mode == 0 ? min(p.ab, p.na - mg * p.ab) : 0;   // MODE_MN: real A blocks of this block group
   if (p.mode == 0) {
     // A blocks that TMA never writes: block `na_loc` of every stage is the all-ones block (its accumulator rows become
@@ -102,8 +142,13 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
   }
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < (p.na < TR_MAXSRC ? p.na : TR_MAXSRC); ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[s]) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[0]) : "memory");
+    if (p.njobs > 1) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[job]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[job]) : "memory");
+    } else {
+      for (int s = 0; s < (p.na < TR_MAXSRC ? p.na : TR_MAXSRC); ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[s]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[0]) : "memory");
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -122,10 +167,11 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  GWN_PDL_ENTRY();   // prologue above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail
 
   // contiguous chunk range of this CTA (MODE_K: CTAs are split over n_nt column tiles of the output)
-  const int c_beg = (int)((long long)p.total_chunks * kslot / nk);
-  const int c_end = (int)((long long)p.total_chunks * (kslot + 1) / nk);
+  const int c_beg = (int)((long long)total_chunks * kslot / nk);
+  const int c_end = (int)((long long)total_chunks * (kslot + 1) / nk);
 
   if (warp == 0 && lane == 0) {
     // ===================================================== TMA producer
@@ -137,12 +183,18 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       const uint32_t sa = st0 + stage * stage_bytes, sb = sa + p.a_bytes;
       mbar_expect_tx(full_bar(stage), p.mode == 0 ? (uint32_t)((na_loc + p.nbn) * 4096) : (uint32_t)p.tx_bytes);
       if (p.mode == 0) {
-        const int b = c / p.chunks_per_sample, r0 = (c - b * p.chunks_per_sample) * 32;
-        for (int j = 0; j < na_loc; ++j) {
-          const int jj = mg * p.ab + j;
-          tma_load_3d(sa + j * 4096, &maps.a[jj], full_bar(stage), p.acol0[jj], r0 + p.arshift[jj], b);
+        const int b = c / cps, r0 = (c - b * cps) * 32;
+        if (p.njobs > 1) {
+          for (int j = 0; j < na_loc; ++j)
+            tma_load_4d(sa + j * 4096, &maps.a[job], full_bar(stage), 0, r0 + p.jrshift[job][j], b, p.jseg[j]);
+          for (int j = 0; j < p.nbn; ++j) tma_load_3d(sb + j * 4096, &maps.b[job], full_bar(stage), 32 * j, r0, b);
+        } else {
+          for (int j = 0; j < na_loc; ++j) {
+            const int jj = mg * p.ab + j;
+            tma_load_3d(sa + j * 4096, &maps.a[jj], full_bar(stage), p.acol0[jj], r0 + p.arshift[jj], b);
+          }
+          for (int j = 0; j < p.nbn; ++j) tma_load_3d(sb + j * 4096, &maps.b[0], full_bar(stage), p.bcol0[0] + ntile * p.N + 32 * j, r0, b);
         }
-        for (int j = 0; j < p.nbn; ++j) tma_load_3d(sb + j * 4096, &maps.b[0], full_bar(stage), p.bcol0[0] + ntile * p.N + 32 * j, r0, b);
       } else {
         while (c >= p.pair_end[pair]) ++pair;
         const int slab = c - (pair ? p.pair_end[pair - 1] : 0);
@@ -271,14 +323,15 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
 template <class F>
 __global__ void __launch_bounds__(256) slot_reduce_kernel(const float* __restrict__ partial, int nslots, i64 slot_floats, i64 nout, F f) {
   __shared__ float sm[2][8][32];
+  GWN_PDL_ENTRY();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const i64 i = (i64)blockIdx.x * 32 + tx;
   float s0 = 0.0f, s1 = 0.0f;
   if (i < nout) {
     i64 off, off2;
-    int slot0, step;
-    f.where(i, off, off2, slot0, step);
-    for (int slot = slot0 + ty * step; slot < nslots; slot += 8 * step) {
+    int slot0, step, send = nslots;
+    f.where(i, off, off2, slot0, step, send);
+    for (int slot = slot0 + ty * step; slot < send; slot += 8 * step) {
       const float* q = partial + (size_t)slot * slot_floats;
       s0 += __ldg(q + off);
       if (off2 >= 0) s1 += __ldg(q + off2);
@@ -297,7 +350,7 @@ __global__ void __launch_bounds__(256) slot_reduce_kernel(const float* __restric
 // gcn mlp weight / bias gradient: slot rows (blk*32 + ci) x 32 columns (n = co); the ones block is row nblk*32.
 struct SlotMlpOut {
   float* dW; float* db; int ldw, nblk;
-  __device__ __forceinline__ void where(i64 i, i64& off, i64& off2, int& slot0, int& step) const {
+  __device__ __forceinline__ void where(i64 i, i64& off, i64& off2, int& slot0, int& step, int&) const {
     const i64 nw = (i64)nblk * 32 * 32;
     off = i < nw ? i : (i64)nblk * 32 * 32 + (i - nw);
     off2 = -1; slot0 = 0; step = 1;
@@ -316,7 +369,7 @@ struct SlotMlpOut {
 // slot rows (tap*32 + ci) x 64 columns j = 2*ch + gate; ones block = row 64.   dW = a[ci]*R + c[ci]*S[j], db = S[j].
 struct SlotTcnOut {
   const float* ac; float* dwf; float* dwg; float* dbf; float* dbg; int C, D;
-  __device__ __forceinline__ void where(i64 i, i64& off, i64& off2, int& slot0, int& step) const {
+  __device__ __forceinline__ void where(i64 i, i64& off, i64& off2, int& slot0, int& step, int&) const {
     const i64 nw = (i64)2 * C * 2 * D;
     if (i < nw) { off = i; off2 = ac ? (i64)2 * C * 2 * D + (i % (2 * D)) : -1; }
     else { off = (i64)2 * C * 2 * D + (i - nw); off2 = -1; }
@@ -343,7 +396,7 @@ struct SlotGridOut {
   float* bias[TR_MAXSRC];
   int nbias, na, ab, n_ag, n_bg, Ntile, Ntot, n_valid;   // n_valid: B columns that exist (the rest were zero-filled)
   i64 sn, si;
-  __device__ __forceinline__ void where(i64 i, i64& off, i64& off2, int& slot0, int& step) const {
+  __device__ __forceinline__ void where(i64 i, i64& off, i64& off2, int& slot0, int& step, int&) const {
     const i64 nw = (i64)na * 32 * Ntot;
     int lb, ii, n, ga;
     if (i < nw) {
@@ -373,7 +426,7 @@ struct SlotGridOut {
 // (k split * n_mg + mg) * n_nt + nt
 struct SlotSupOut {
   float* dA; int ld, V, Ntile, n_nt, MR, n_mg;
-  __device__ __forceinline__ void where(i64 i, i64& off, i64& off2, int& slot0, int& step) const {
+  __device__ __forceinline__ void where(i64 i, i64& off, i64& off2, int& slot0, int& step, int&) const {
     const int v = (int)(i / V), w = (int)(i - (i64)v * V);
     const int nt = w / Ntile, mg = v / MR;
     off = (i64)(v - mg * MR) * Ntile + (w - nt * Ntile);
@@ -385,13 +438,32 @@ struct SlotSupOut {
   }
 };
 
+// The same functor per job of a multi-job launch: output i = (job, element); the job's slots are its CTA range.
+template <class F>
+struct SlotJobs {
+  F f[TR_MAXJOBS];
+  int cta0[TR_MAXJOBS + 1];
+  i64 nout_job;
+  __device__ __forceinline__ void where(i64 i, i64& off, i64& off2, int& slot0, int& step, int& send) const {
+    const int q = (int)(i / nout_job);
+    int dummy = 0;
+    f[q].where(i - (i64)q * nout_job, off, off2, slot0, step, dummy);
+    slot0 += cta0[q];
+    send = cta0[q + 1];
+  }
+  __device__ __forceinline__ void store(i64 i, float s0, float s1) const {
+    const int q = (int)(i / nout_job);
+    f[q].store(i - (i64)q * nout_job, s0, s1);
+  }
+};
+
 }  // namespace tc
 
 template <class F>
 inline int launch_slot_reduce(const float* partial, const TcRedResult& r, i64 nout, const F& f, cudaStream_t stream) {
   if (nout <= 0) return 0;
-  tc::slot_reduce_kernel<F><<<(unsigned)((nout + 31) / 32), 256, 0, stream>>>(partial, r.nslots, r.slot_floats, nout, f);
-  GWN_LAUNCH_CHECK();
+  GWN_CUDA(launch_kernel(tc::slot_reduce_kernel<F>, dim3((unsigned)((nout + 31) / 32)), dim3(256), 0, stream, partial, r.nslots,
+                         r.slot_floats, nout, f));
   count_launch();
   return 0;
 }
@@ -459,24 +531,36 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
     // D[v, w] over V x V: mtiles row tiles of 128 live in TMEM side by side, Ntile columns each (mtiles*Ntile <= 512);
     // n_nt column tiles are spread over the CTAs
     p.nblk = 0;
-    p.mtiles = (a.rows + 127) / 128;
-    if (p.mtiles > 4) {                       // large graphs: row groups of 256 as well as column tiles
-      p.n_mg = (p.mtiles + 1) / 2;
-      p.mtiles = 2;
+    // Tiling of the V x V output over CTAs: mt row tiles of 128 side by side in TMEM per CTA (n_mg row groups), n_nt
+    // column tiles of `ntile`, the rest of the SMs split K.  One tcgen05.mma of 128 x N x 8 (tf32, both operands
+    // from shared memory) costs about 66 + 0.75 N cycles on B200 (measured on the node contraction: N = 112 -> 150,
+    // 208 -> 222, 256 -> 258), i.e. wide instructions are cheaper per column, so the modelled time of a K chunk is
+    // mt x (66 + 0.75 ntile) and a candidate's cost that time divided by its K-split factor.  METR-LA (V = 207):
+    // one row tile x 208 columns per CTA, 2 row groups x 74 K splits (was 2 x 112 columns x 74: 26 % more MMA time).
+    const int rowtiles = (a.rows + 127) / 128;
+    int best_mt = 0, best_nt = 0;
+    double best_cost = 0.0;
+    for (int mt = 1; mt <= 4 && mt <= rowtiles; ++mt) {
+      const int n_mg = (rowtiles + mt - 1) / mt;
+      for (int cnt = 1; cnt <= 64; ++cnt) {
+        const int nt = round_up((a.rows + cnt - 1) / cnt, 16);
+        if (nt > 256 || mt * nt > 512) continue;
+        const int n_nt = (a.rows + nt - 1) / nt;
+        if ((SMEM_LIMIT - 2048) / ((a.x3 ? 2 : 1) * (mt * 16384 + nt * 128)) < 2) continue;   // two pipeline stages
+        int nk = num_sms / (n_nt * n_mg);
+        if (nk < 1) nk = 1;
+        const double rounds = (double)((n_nt * n_mg + num_sms - 1) / num_sms);   // > 1 only when there are more tiles than SMs
+        const double cost = rounds * mt * (66.0 + 0.75 * nt) / nk;
+        if (best_mt == 0 || cost < best_cost * 0.999 || (cost < best_cost * 1.001 && mt > best_mt)) {
+          best_mt = mt; best_nt = nt; best_cost = cost;
+        }
+        if (nt <= 16) break;
+      }
     }
-    int ntile = (512 / p.mtiles) / 16 * 16;
-    if (ntile > 256) ntile = 256;
-    if (a.x3) {   // two stages of [A | B | A_lo | B_lo] must fit shared memory
-      const int cap = (((SMEM_LIMIT - 2048) / 4 - p.mtiles * 16384) / 128) / 16 * 16;
-      if (cap < 16) return -1;
-      if (ntile > cap) ntile = cap;
-    }
-    const int need = round_up(a.rows, 16);
-    if (ntile > need) ntile = need;
-    {   // balance the column tiles
-      const int nt = (a.rows + ntile - 1) / ntile;
-      ntile = round_up((a.rows + nt - 1) / nt, 16);
-    }
+    if (best_mt == 0) return -1;
+    p.mtiles = best_mt;
+    p.n_mg = (rowtiles + best_mt - 1) / best_mt;
+    const int ntile = best_nt;
     p.N = ntile;
     p.n_nt = (a.rows + ntile - 1) / ntile;
     p.a_bytes = p.mtiles * 16384;
@@ -523,11 +607,131 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
     set_error("tcred: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr != cudaSuccess ? attr : attr3));
     return GWN_ERR_CUDA;
   }
-  if (a.x3) tcred_kernel<true><<<grid, 256, smem_bytes, stream>>>(maps, p);
-  else tcred_kernel<false><<<grid, 256, smem_bytes, stream>>>(maps, p);
+  if (a.x3) GWN_CUDA(launch_kernel(tcred_kernel<true>, dim3(grid), dim3(256), smem_bytes, stream, maps, p));
+  else GWN_CUDA(launch_kernel(tcred_kernel<false>, dim3(grid), dim3(256), smem_bytes, stream, maps, p));
   GWN_LAUNCH_CHECK();
   count_launch();
   res->nslots = grid; res->mtiles = p.mtiles; res->N = p.N; res->n_nt = p.n_nt; res->n_mg = p.n_mg; res->slot_floats = p.slot_floats;
+  return 0;
+#endif
+}
+
+// Several same-shaped MODE_MN reductions in one launch (see TcRedJobsArgs).  0 = launched, -1 = not eligible, > 0 = error.
+inline int launch_tcred_jobs(const TcRedJobsArgs& a, cudaStream_t stream, TcRedResult* res) {
+#if GWN_EMU
+  (void)a; (void)stream; (void)res;
+  return -1;
+#else
+  using namespace tc;
+  if (a.njobs < 2 || a.njobs > TR_MAXJOBS || a.na < 1 || a.na > 7 || a.N % 32 != 0 || a.N < 32 || a.N > 256 || !a.partial || !res)
+    return -1;
+  static int num_sms = [] {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  if (a.njobs > num_sms) return -1;
+  TrMaps maps;
+  TrParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = 0; p.na = a.na; p.n_nt = 1; p.n_mg = 1; p.N = a.N; p.ab = a.na;
+  p.nblk = a.na + 1;
+  p.mtiles = (p.nblk + 3) / 4;
+  if (p.mtiles * a.N > 512) return -1;
+  p.nbn = a.N / 32;
+  p.a_bytes = p.mtiles * 16384;
+  p.b_bytes = p.nbn * 4096;
+  p.tx_bytes = (a.na + p.nbn) * 4096;
+  p.njobs = a.njobs;
+  for (int j = 0; j < a.na; ++j) p.jseg[j] = a.seg[j];
+  long long tot = 0;
+  for (int q = 0; q < a.njobs; ++q) {
+    const TcRedJob& g = a.job[q];
+    if (g.nb < 1 || g.rows < 1 || g.nseg_src < 1 || (reinterpret_cast<uintptr_t>(g.a_src) & 15) || (reinterpret_cast<uintptr_t>(g.b_src) & 15) ||
+        g.b_width % 4 != 0 || g.b_width < a.N || g.a_seg_stride % 4 != 0)
+      return -1;
+    for (int j = 0; j < a.na; ++j) {
+      if (a.seg[j] < 0 || a.seg[j] >= g.nseg_src) return -1;
+      p.jrshift[q][j] = g.rshift[j];
+    }
+    p.job_cps[q] = (g.rows + 31) / 32;
+    const long long ch = (long long)p.job_cps[q] * g.nb;
+    if (ch > 2147483647LL) return -1;
+    p.job_chunks[q] = (int)ch;
+    tot += ch;
+    {
+      const i64 segs = g.nseg_src > 1 ? g.a_seg_stride : (i64)g.a_rows_src * g.nb * 32;
+      cuuint64_t d[4] = {32, (cuuint64_t)g.a_rows_src, (cuuint64_t)g.nb, (cuuint64_t)g.nseg_src};
+      cuuint64_t st[3] = {128, (cuuint64_t)g.a_rows_src * 128, (cuuint64_t)segs * 4};
+      cuuint32_t box[4] = {32, 32, 1, 1};
+      GWN_TRY(encode(&maps.a[q], g.a_src, 4, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    }
+    {
+      cuuint64_t d[3] = {(cuuint64_t)g.b_width, (cuuint64_t)g.rows, (cuuint64_t)g.nb};
+      cuuint64_t st[2] = {(cuuint64_t)g.b_width * 4, (cuuint64_t)g.rows * g.b_width * 4};
+      cuuint32_t box[3] = {32, 32, 1};
+      GWN_TRY(encode(&maps.b[q], g.b_src, 3, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    }
+  }
+  for (int q = a.njobs; q < TR_MAXSRC; ++q) { maps.a[q] = maps.a[0]; maps.b[q] = maps.b[0]; }
+  // CTAs per job in proportion to its K extent (at least one, at most one per chunk); leftovers to the most loaded jobs.
+  // A CTA accumulates its whole K range in ONE fp32 TMEM accumulator, and the tensor core's accumulate step truncates:
+  // the error grows linearly with the chain (measured: 147 chunks per CTA -> 1.4e-4 on the first layer's filter
+  // gradient, 34 chunks -> 3e-5), so the grid grows to whole extra rounds of CTAs until a range is <= 48 chunks.
+  const int sms = num_sms;
+  int T = sms;
+  {
+    long long want = (tot + 47) / 48;
+    want = (want + sms - 1) / sms * sms;
+    const long long cap = a.partial_floats / ((i64)p.mtiles * 128 * p.N);
+    if (want > cap) want = cap / sms * sms;
+    if (want > sms) T = (int)want;
+  }
+  int nkq[TR_MAXJOBS], used = 0;
+  for (int q = 0; q < a.njobs; ++q) {
+    long long n = (long long)T * p.job_chunks[q] / tot;
+    if (n < 1) n = 1;
+    if (n > p.job_chunks[q]) n = p.job_chunks[q];
+    nkq[q] = (int)n;
+    used += nkq[q];
+  }
+  while (used > T) {   // the "at least one" floor overshot: take from the least loaded job that has more than one
+    int w = -1;
+    for (int q = 0; q < a.njobs; ++q)
+      if (nkq[q] > 1 && (w < 0 || (double)p.job_chunks[q] / nkq[q] < (double)p.job_chunks[w] / nkq[w])) w = q;
+    if (w < 0) return -1;
+    --nkq[w]; --used;
+  }
+  while (used < T) {
+    int w = -1;
+    for (int q = 0; q < a.njobs; ++q)
+      if (nkq[q] < p.job_chunks[q] && (w < 0 || (double)p.job_chunks[q] / nkq[q] > (double)p.job_chunks[w] / nkq[w])) w = q;
+    if (w < 0) break;
+    ++nkq[w]; ++used;
+  }
+  p.job_cta0[0] = 0;
+  for (int q = 0; q < a.njobs; ++q) p.job_cta0[q + 1] = p.job_cta0[q] + nkq[q];
+  const int grid = p.job_cta0[a.njobs];
+  const int stage_bytes = (a.x3 ? 2 : 1) * (p.a_bytes + p.b_bytes);
+  p.stages = (SMEM_LIMIT - 2048) / stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages < 2) return -1;
+  p.slot_floats = (i64)p.mtiles * 128 * p.N;
+  if ((i64)grid * p.slot_floats > a.partial_floats) return -1;
+  p.partial = a.partial;
+  const int smem_bytes = p.stages * stage_bytes + 1024 + 256;
+  static cudaError_t attr = cudaFuncSetAttribute(tcred_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  static cudaError_t attr3 = cudaFuncSetAttribute(tcred_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  if (attr != cudaSuccess || attr3 != cudaSuccess) {
+    set_error("tcred: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr != cudaSuccess ? attr : attr3));
+    return GWN_ERR_CUDA;
+  }
+  if (a.x3) GWN_CUDA(launch_kernel(tcred_kernel<true>, dim3(grid), dim3(256), smem_bytes, stream, maps, p));
+  else GWN_CUDA(launch_kernel(tcred_kernel<false>, dim3(grid), dim3(256), smem_bytes, stream, maps, p));
+  count_launch();
+  res->nslots = grid; res->mtiles = p.mtiles; res->N = p.N; res->n_nt = 1; res->n_mg = 1; res->slot_floats = p.slot_floats;
+  for (int q = 0; q <= a.njobs; ++q) res->job_cta0[q] = p.job_cta0[q];
   return 0;
 #endif
 }

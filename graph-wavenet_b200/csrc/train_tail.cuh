@@ -28,6 +28,7 @@ GWN_DEV void reduce_add_d(double* dst, double v) {
 }
 
 GWN_GLOBAL train_begin_kernel(TrainCtrl* c) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(i, 1) {
     c->seed += 0x9E3779B97F4A7C15ull;
     for (int k = 0; k < 6; ++k) c->acc[k] = 0.0;
@@ -37,6 +38,7 @@ GWN_GLOBAL train_begin_kernel(TrainCtrl* c) {
 // out: network output [B,O,N,T] contiguous; label(b,n,o) = y[b*ys0 + n*ys1 + o*ys2] broadcast over T (engine.py:46-48).
 GWN_GLOBAL loss_reduce_kernel(const float* out, const float* y, i64 ys0, i64 ys1, i64 ys2, float mean, float std, int B, int O,
                               int N, int T, TrainCtrl* c) {
+  GWN_PDL_ENTRY();
   double cnt = 0.0, sa = 0.0, sm = 0.0, sq = 0.0;
   GWN_FOR_EACH(i, (i64)B * O * N * T) {
     const int t = (int)(i % T);
@@ -68,6 +70,7 @@ GWN_GLOBAL loss_reduce_kernel(const float* out, const float* y, i64 ys0, i64 ys1
 // masked_mae = mean(|d| * mask / mean(mask)) = sum|d| / (count * T): count = unmasked labels, each broadcast over T.
 GWN_GLOBAL loss_grad_kernel(const float* out, const float* y, i64 ys0, i64 ys1, i64 ys2, float mean, float std, int B, int O,
                             int N, int T, int ldo, const TrainCtrl* c, float* dout, float* metrics) {
+  GWN_PDL_ENTRY();
   const double denom = c->acc[0] * (double)T;
   const float gs = denom > 0.0 ? (float)((double)std / denom) : 0.0f;
   GWN_FOR_EACH(i, (i64)B * T * N * ldo) {
@@ -96,6 +99,7 @@ GWN_GLOBAL loss_grad_kernel(const float* out, const float* y, i64 ys0, i64 ys1, 
 
 // metrics = {mae, mape, rmse} from the accumulators alone (trainer.eval: no gradient wanted)
 GWN_GLOBAL metrics_finalize_kernel(const TrainCtrl* c, int T, float* metrics) {
+  GWN_PDL_ENTRY();
   GWN_FOR_EACH(i, 1) {
     const double denom = c->acc[0] * (double)T;
     metrics[0] = denom > 0.0 ? (float)(c->acc[1] / denom) : 0.0f;
@@ -111,6 +115,7 @@ struct AdamHyper {
 
 // sum of squares of the live gradient elements (live4: one byte per 4 floats); also advances the step counter.
 GWN_GLOBAL gradnorm_kernel(const float* g, const uint8_t* live4, i64 n4, TrainCtrl* c) {
+  GWN_PDL_ENTRY();
   double s = 0.0;
   GWN_FOR_EACH(i, n4) {
     if (live4[i]) {
@@ -124,6 +129,7 @@ GWN_GLOBAL gradnorm_kernel(const float* g, const uint8_t* live4, i64 n4, TrainCt
 
 GWN_GLOBAL adam_kernel(float* p, float* g, float* m, float* v, const uint8_t* live4, i64 n4, const AdamHyper* hp,
                        const TrainCtrl* c, float* metrics) {
+  GWN_PDL_ENTRY();
   const AdamHyper h = *hp;
   const float total_norm = (float)sqrt(c->acc[4]) * h.gscale;
   float coef = h.gscale;

@@ -300,9 +300,13 @@ def test_tf32_tier_matches_reference_golden(M, name):
     (out * rec["probe"].to(dev)).sum().backward()
     ref = sub(rec, "grad/")
     gnorm = sum(float(g.double().pow(2).sum()) for g in ref.values()) ** 0.5
+    gd = 0.0
     for k, p in m.named_parameters():
         if k in ref:   # tiny problem (30 positions): single tensors are noisier than at full size, hence the floor
-            assert_close_rel(p.grad, ref[k], TOL_TF32, "tf32 grad " + k, floor=2e-3 * gnorm)
+            assert_close_rel(p.grad, ref[k], TOL_TF32, "tf32 grad " + k, floor=5e-3 * gnorm)
+            gd += float((p.grad.double().cpu() - ref[k].double()).pow(2).sum())
+    # the tier's statement (north star: 2e-2) on the whole gradient vector, without any floor
+    assert gd ** 0.5 <= TOL_TF32 * gnorm, f"tf32 global gradient error {gd ** 0.5 / gnorm:.3e}"
 
 
 def test_tf32_tier_metr_la_full_size(M):
