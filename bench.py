@@ -27,7 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NODES, SEQ, IN_DIM, BATCH = 207, 12, 2, 64
-DROPOUT = 0.3
+DROPOUT = float(os.environ.get("GWNET_B200_BENCH_DROPOUT", "0.3"))   # the override is for diagnostics only
 METRIC = "train samples/sec (fwd+bwd) METR-LA shape"
 WORKLOAD = "gwnet METR-LA shape N=207 seq=12 in_dim=2 batch=64/GPU doubletransition+adaptive, dropout 0.3, full trainer.train step"
 

@@ -148,6 +148,12 @@ struct gwn_plan {
   bool defer_dA;
   std::vector<gwn::i64> o_dpre_l, o_dh_l;   // per layer when the weight gradients are deferred (else all = o_dpre / o_dh)
   bool defer_wgrad;
+  // Side stream for the operand preparation that depends only on parameters / supports (weight packing, 3xTF32
+  // remainders, support packing, adaptive adjacency): forked from the caller's stream at the start of a forward
+  // pass and joined before the first consumer, so ~30 tiny launches leave the critical path (also as parallel
+  // branches of a captured CUDA graph).  Created lazily on the device of the first forward call.
+  cudaStream_t side = nullptr;
+  cudaEvent_t side_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   gwn::i64 P(int i) const { return (gwn::i64)c.batch * L[i] * c.num_nodes; }
   gwn::i64 P0() const { return (gwn::i64)c.batch * L0 * c.num_nodes; }
   gwn::i64 PT() const { return (gwn::i64)c.batch * T_out * c.num_nodes; }
@@ -461,6 +467,44 @@ static DropoutSrc layer_dropout(const gwn_plan* p, int training, int mode, const
                       reinterpret_cast<const unsigned long long*>(seed_dev));
 }
 
+// Fork: returns the stream to launch preparation work on (the caller's own stream when the side stream is disabled).
+static int side_fork(gwn_plan* p, cudaStream_t st, cudaStream_t* out) {
+  *out = st;
+#if !GWN_EMU
+  static const bool off = [] {
+    const char* e = getenv("GWNET_B200_SIDE_STREAM");
+    return e && e[0] == '0';
+  }();
+  if (off) return 0;
+  if (!p->side) {
+    GWN_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+    for (int k = 0; k < 4; ++k) GWN_CUDA(cudaEventCreateWithFlags(&p->side_ev[k], cudaEventDisableTiming));
+  }
+  GWN_CUDA(cudaEventRecord(p->side_ev[0], st));
+  GWN_CUDA(cudaStreamWaitEvent(p->side, p->side_ev[0], 0));
+  *out = p->side;
+#else
+  (void)p;
+#endif
+  return 0;
+}
+static int side_mark(gwn_plan* p, cudaStream_t sd, cudaStream_t st, int k) {   // "everything launched on sd so far"
+#if !GWN_EMU
+  if (sd != st) GWN_CUDA(cudaEventRecord(p->side_ev[k], sd));
+#else
+  (void)p; (void)sd; (void)st; (void)k;
+#endif
+  return 0;
+}
+static int side_join(gwn_plan* p, cudaStream_t sd, cudaStream_t st, int k) {   // st continues after mark k
+#if !GWN_EMU
+  if (sd != st) GWN_CUDA(cudaStreamWaitEvent(st, p->side_ev[k], 0));
+#else
+  (void)p; (void)sd; (void)st; (void)k;
+#endif
+  return 0;
+}
+
 static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
   MathScope math_scope(math_of(p->c.precision));
   GWN_TRY(require_device());
@@ -475,6 +519,15 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
   const int nL = p->nL, B = c.batch;
   const void* const* prm = a->params;
 
+  // ---- preparation that depends only on parameters / supports runs on the plan's side stream (see gwn_plan::side)
+  cudaStream_t sd = st;
+  GWN_TRY(side_fork(p, st, &sd));
+  if (tcpos_ok(p)) {   // layer 0's packed gated-conv weights (no BatchNorm fold below the first layer)
+    float* pk = ws + p->o_pack[0];
+    GWN_LAUNCH_WARP_ROWS(pack_tcn_fwd_kernel, 2 * D, sd, P_<float>(prm, p->li[0].fw), P_<float>(prm, p->li[0].gw),
+                  P_<float>(prm, p->li[0].fb), P_<float>(prm, p->li[0].gb), (const float*)nullptr, pk + p->pk_wp, pk + p->pk_bf,
+                  pk + p->pk_bg, D, C, x3(p) ? pk + p->pk_wp_lo : (float*)nullptr);
+  }
   // ---- supports: pack static ones, compute the adaptive one (model.py:185-188); with per-sample graphs one set per
   // sample (model.py:313,345-346).  Layout of both packed regions: [support][sample set][N][ld].
   const int Bs = p->Bs;
@@ -491,13 +544,13 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
         GWN_CHECK_ARG(a->supports && a->supports[s] && a->support_strides, "forward: support %d missing", s);
         const int64_t* ss = a->support_strides + sstr * s;
         const float* As = a->supports[s] + (c.per_sample_supports ? (i64)b * ss[0] : 0);
-        GWN_LAUNCH_1D(support_pack_kernel, sup_sz, st, As, (i64)ss[sstr - 2], (i64)ss[sstr - 1], Ap, ATp, N, p->ld);
+        GWN_LAUNCH_1D(support_pack_kernel, sup_sz, sd, As, (i64)ss[sstr - 2], (i64)ss[sstr - 1], Ap, ATp, N, p->ld);
       } else if (c.adaptive_input) {
         GWN_CHECK_ARG(a->apt_e1 && a->apt_e2, "forward: adaptive_input without node embeddings");
-        GWN_LAUNCH_WARP_ROWS(adp_fwd_kernel, N, st, a->apt_e1 + (i64)b * N * c.apt_rank, a->apt_e2 + (i64)b * c.apt_rank * N,
+        GWN_LAUNCH_WARP_ROWS(adp_fwd_kernel, N, sd, a->apt_e1 + (i64)b * N * c.apt_rank, a->apt_e2 + (i64)b * c.apt_rank * N,
                              c.apt_rank, Ap, ATp, N, p->ld);
       } else {
-        GWN_LAUNCH_WARP_ROWS(adp_fwd_kernel, N, st, P_<float>(prm, p->i_nv1), P_<float>(prm, p->i_nv2), c.apt_rank, Ap, ATp, N,
+        GWN_LAUNCH_WARP_ROWS(adp_fwd_kernel, N, sd, P_<float>(prm, p->i_nv1), P_<float>(prm, p->i_nv2), c.apt_rank, Ap, ATp, N,
                              p->ld);
       }
     }
@@ -509,7 +562,43 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     if (x3(p) && tcpos_ok(p)) tcF.Slo[s] = ws + p->o_sup_lo + (ATp0 - (ws + p->o_sup));
   }
   if (x3(p) && tcpos_ok(p) && p->S > 0)
-    GWN_LAUNCH_1D(split_lo_kernel, p->sup_span, st, (const float*)(ws + p->o_sup), ws + p->o_sup_lo, p->sup_span);
+    GWN_LAUNCH_1D(split_lo_kernel, p->sup_span, sd, (const float*)(ws + p->o_sup), ws + p->o_sup_lo, p->sup_span);
+  GWN_TRY(side_mark(p, sd, st, 1));   // layer 0's gated conv and the node contractions may start
+  if (tcpos_ok(p)) {
+    if (x3(p)) {   // 3xTF32 remainders of every layer's mlp weights
+      for (int i = 0; i < nL; ++i) {
+        const float* Wm = P_<float>(prm, c.gcn ? p->li[i].mw : p->li[i].rw);
+        GWN_LAUNCH_1D(split_lo_kernel, (i64)C * p->nseg * D, sd, Wm, ws + p->o_pack[i] + p->pk_wm_lo, (i64)C * p->nseg * D);
+      }
+    }
+    GWN_TRY(side_mark(p, sd, st, 2));   // the mlp of layer 0 may start
+#if !GWN_EMU
+    if (p->head_tc) {   // head: concatenated skip weights + summed bias, remainders of the end convs
+      const bool h3 = x3(p);
+      SkipWeights sw;
+      memset(&sw, 0, sizeof(sw));
+      for (int i = 0; i < nL; ++i) { sw.w[i] = P_<float>(prm, p->li[i].sw); sw.b[i] = P_<float>(prm, p->li[i].sb); }
+      GWN_LAUNCH_1D(pack_skip_kernel, (i64)Sk * nL * D + Sk, sd, sw, nL, D, Sk, ws + p->o_hk_wcat,
+                    h3 ? ws + p->o_hk_wcat_lo : (float*)nullptr, (float*)nullptr, (float*)nullptr, ws + p->o_hk_bsum);
+      if (h3) {
+        GWN_LAUNCH_1D(split_lo_kernel, (i64)E * Sk, sd, P_<float>(prm, p->i_e1w), ws + p->o_hk_e1lo, (i64)E * Sk);
+        GWN_LAUNCH_1D(split_lo_kernel, (i64)c.out_dim * E, sd, P_<float>(prm, p->i_e2w), ws + p->o_hk_e2lo, (i64)c.out_dim * E);
+      }
+    }
+#endif
+    // operands of the backward pass that live in the forward workspace: transposed mlp weights, gated-conv dgrad weights
+    for (int i = 0; i < nL; ++i) {
+      float* pk = ws + p->o_pack[i];
+      if (i < nL - 1) {
+        const float* Wm = P_<float>(prm, c.gcn ? p->li[i].mw : p->li[i].rw);
+        GWN_LAUNCH_1D(transpose_kernel, (i64)C * p->nseg * D, sd, Wm, pk + p->pk_wt, C, p->nseg * D,
+                      x3(p) ? pk + p->pk_wt_lo : (float*)nullptr);
+      }
+      GWN_LAUNCH_1D(pack_tcn_dgrad_kernel, (i64)C * 4 * D, sd, P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw),
+                    pk + p->pk_wd, D, C, x3(p) ? pk + p->pk_wd_lo : (float*)nullptr);
+    }
+    GWN_TRY(side_mark(p, sd, st, 3));
+  }
   tcF.ld = p->ld;
   tcF.precision = c.precision;
   (void)supB;
@@ -529,6 +618,7 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     GWN_LAUNCH_1D(start_fwd_kernel, p->P0() * C, st, a->input, is, P_<float>(prm, p->i_startw), P_<float>(prm, p->i_startb),
                   ws + p->o_x0, B, c.in_dim, N, p->L0, p->pad, C);
   }
+  GWN_TRY(side_join(p, sd, st, 1));
   // ---- WaveNet layers (model.py:192-236)
   for (int i = 0; i < nL; ++i) {
     const float* prev = i == 0 ? ws + p->o_x0 : ws + p->o_u[i - 1];
@@ -543,9 +633,10 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
       int pst = -1;
       if (tcpos_ok(p)) {
         float* pk = ws + p->o_pack[i];
-        GWN_LAUNCH_WARP_ROWS(pack_tcn_fwd_kernel, 2 * D, st, P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw),
-                      P_<float>(prm, p->li[i].fb), P_<float>(prm, p->li[i].gb), prev_ac, pk + p->pk_wp, pk + p->pk_bf,
-                      pk + p->pk_bg, D, C, x3(p) ? pk + p->pk_wp_lo : (float*)nullptr);
+        if (i > 0)   // BatchNorm of the layer below folded in (layer 0 was packed on the side stream)
+          GWN_LAUNCH_WARP_ROWS(pack_tcn_fwd_kernel, 2 * D, st, P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw),
+                        P_<float>(prm, p->li[i].fb), P_<float>(prm, p->li[i].gb), prev_ac, pk + p->pk_wp, pk + p->pk_bf,
+                        pk + p->pk_bg, D, C, x3(p) ? pk + p->pk_wp_lo : (float*)nullptr);
         RowGate eg;
         memset(&eg, 0, sizeof(eg));
         eg.y = g; eg.bf = pk + p->pk_bf; eg.bg = pk + p->pk_bg;
@@ -606,10 +697,8 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     m.rac = prev_ac;
     m.stats = a->training ? reinterpret_cast<double*>(ws + p->o_sums[i]) : nullptr;
     m.y = ws + p->o_u[i];
-    if (tcpos_ok(p) && x3(p)) {
-      GWN_LAUNCH_1D(split_lo_kernel, (i64)C * p->nseg * D, st, m.W, pk_m + p->pk_wm_lo, (i64)C * p->nseg * D);
-      m.W_lo = pk_m + p->pk_wm_lo;
-    }
+    if (tcpos_ok(p) && x3(p)) m.W_lo = pk_m + p->pk_wm_lo;   // split on the side stream
+    if (i == 0 && tcpos_ok(p)) GWN_TRY(side_join(p, sd, st, 2));
     GWN_TRY(mlp_forward(m, st));
     if (a->training) {
       GWN_LAUNCH_1D(bn_finalize_kernel, C, st, reinterpret_cast<const double*>(ws + p->o_sums[i]), (double)Pi,
@@ -619,6 +708,7 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     }
   }
   // ---- head: skip sum over the live columns (G5), relu, end convs (model.py:216-222,238-240)
+  if (tcpos_ok(p)) GWN_TRY(side_join(p, sd, st, 3));
   const i64 PT = p->PT();
   ProfScope prof_head("head_fwd", st, 4.0 * PT * ((double)nL * D + 2.0 * Sk + 2.0 * E + c.out_dim),
                       2.0 * PT * ((double)nL * D * Sk + (double)Sk * E + (double)E * c.out_dim));
@@ -627,11 +717,6 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
   if (p->head_tc && PT < 2147483647LL) {   // the three head layers as tcgen05 position GEMMs with streamed weights
     const bool h3 = x3(p);
     const int TN = h3 ? 128 : 256;   // output columns per tile: two stages of [A | W blk] (x2 planes in 3xTF32 mode) must fit
-    SkipWeights sw;
-    memset(&sw, 0, sizeof(sw));
-    for (int i = 0; i < nL; ++i) { sw.w[i] = P_<float>(prm, p->li[i].sw); sw.b[i] = P_<float>(prm, p->li[i].sb); }
-    GWN_LAUNCH_1D(pack_skip_kernel, (i64)Sk * nL * D + Sk, st, sw, nL, D, Sk, ws + p->o_hk_wcat,
-                  h3 ? ws + p->o_hk_wcat_lo : (float*)nullptr, (float*)nullptr, (float*)nullptr, ws + p->o_hk_bsum);
     int hs;
     {  // skip = relu(sum_i W_i g_i[live columns] + sum_i b_i)
       TcPosArgs t;
@@ -647,7 +732,6 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
       if (hs > 0) return hs;
     }
     if (hs == 0) {  // e1 = relu(W1 skip + b1)
-      if (h3) GWN_LAUNCH_1D(split_lo_kernel, (i64)E * Sk, st, P_<float>(prm, p->i_e1w), ws + p->o_hk_e1lo, (i64)E * Sk);
       TcPosArgs t;
       memset(&t, 0, sizeof(t));
       for (int q = 0; q < Sk / 32; ++q) t.seg[q] = TcPosSeg{ws + p->o_skip, (int)PT, Sk, 32 * q, 0};
@@ -662,7 +746,6 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
       GWN_CHECK_ARG(hs == 0, "forward: head layer 2 not eligible for the tcgen05 path after layer 1 ran on it");
     }
     if (hs == 0) {  // out = W2 e1 + b2, written in the reference's NCHW layout
-      if (h3) GWN_LAUNCH_1D(split_lo_kernel, (i64)c.out_dim * E, st, P_<float>(prm, p->i_e2w), ws + p->o_hk_e2lo, (i64)c.out_dim * E);
       TcPosArgs t;
       memset(&t, 0, sizeof(t));
       for (int q = 0; q < E / 32; ++q) t.seg[q] = TcPosSeg{ws + p->o_e1, (int)PT, E, 32 * q, 0};
@@ -1037,9 +1120,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
       m.W = P_<float>(prm, c.gcn ? p->li[i].mw : p->li[i].rw);
       m.dsegs = dsegs;
       if (tcpos_ok(p)) {
-        float* pk = const_cast<float*>(ws) + p->o_pack[i];
-        GWN_LAUNCH_1D(transpose_kernel, (i64)C * p->nseg * D, st, m.W, pk + p->pk_wt, C, p->nseg * D,
-                      x3(p) ? pk + p->pk_wt_lo : (float*)nullptr);
+        float* pk = const_cast<float*>(ws) + p->o_pack[i];   // W^T (+ remainders): packed by the forward pass
         m.WT = pk + p->pk_wt;
         if (x3(p)) m.WT_lo = pk + p->pk_wt_lo;
       }
@@ -1138,9 +1219,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
       }
       int pst = -1;
       if (tcpos_ok(p)) {
-        float* pk = const_cast<float*>(ws) + p->o_pack[i];
-        GWN_LAUNCH_1D(pack_tcn_dgrad_kernel, (i64)C * 4 * D, st, P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw),
-                      pk + p->pk_wd, D, C, x3(p) ? pk + p->pk_wd_lo : (float*)nullptr);
+        float* pk = const_cast<float*>(ws) + p->o_pack[i];   // dgrad weights: packed by the forward pass
         RowTcnDgrad eg;
         memset(&eg, 0, sizeof(eg));
         eg.dx = ep.dx; eg.du = ep.du; eg.N = N; eg.L_in = ep.L_in; eg.L_out = ep.L_out;
@@ -1725,7 +1804,15 @@ int gwn_plan_create(const gwn_config* cfg, gwn_plan** out) {
   return 0;
 }
 
-void gwn_plan_destroy(gwn_plan* p) { delete p; }
+void gwn_plan_destroy(gwn_plan* p) {
+  if (!p) return;
+#if !GWN_EMU
+  for (int k = 0; k < 4; ++k)
+    if (p->side_ev[k]) cudaEventDestroy(p->side_ev[k]);
+  if (p->side) cudaStreamDestroy(p->side);
+#endif
+  delete p;
+}
 
 int gwn_plan_workspace_bytes(const gwn_plan* p, size_t* fwd, size_t* bwd) {
   GWN_CHECK_ARG(p, "null plan");

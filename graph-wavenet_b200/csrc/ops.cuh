@@ -192,6 +192,10 @@ inline int mlp_forward(const MlpFwdArgs& m, cudaStream_t stream) {
     RowMlp eg;
     memset(&eg, 0, sizeof(eg));
     eg.y = m.y; eg.bias = m.bias; eg.drop = m.drop; eg.res = m.res; eg.rrm = m.rrm; eg.rac = m.rac; eg.stats = m.stats;
+    {
+      static const bool nostats = getenv("GWNET_B200_DIAG_NOSTATS") != nullptr;   // timing diagnostics only (wrong results)
+      if (nostats) eg.stats = nullptr;
+    }
     int st = launch_tcpos<32>(t, eg, stream);
     if (st >= 0) return st;
   }

@@ -416,6 +416,13 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
     GWN_TRY(encode(&maps.out, a.out, 3, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   if (p.stages > 8) p.stages = 8;
+  {
+    static const int cap = [] {   // diagnostics: cap the pipeline depth (GWNET_B200_TCPOS_STAGES)
+      const char* e = getenv("GWNET_B200_TCPOS_STAGES");
+      return e ? atoi(e) : 0;
+    }();
+    if (cap >= 2 && p.stages > cap) p.stages = cap;
+  }
   if (p.stages < 2) return -1;
   for (int s = 0; s < a.nseg; ++s) {
     const TcPosSeg& g = a.seg[s];
