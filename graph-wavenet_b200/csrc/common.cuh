@@ -278,6 +278,18 @@ inline DropoutSrc make_dropout(int mode, const uint8_t* mask, uint64_t seed, uin
   return d;
 }
 
+// BatchNorm column statistics (forward sums, backward sums) are accumulated with fp64 atomics by every CTA of the
+// producing GEMM: 296 epilogue groups onto the same 64 addresses serialise in the L2 atomic unit.  The sums therefore
+// live in GWN_STAT_REPL replicas of [2*C] doubles (a CTA adds to replica blockIdx % GWN_STAT_REPL); consumers add
+// the replicas up.
+constexpr int GWN_STAT_REPL = 8;
+GWN_HD double stat_sum(const double* s, int idx, int C) {   // element idx (< 2*C) summed over the replicas
+  double v = 0.0;
+#pragma unroll
+  for (int r = 0; r < GWN_STAT_REPL; ++r) v += s[(size_t)r * 2 * C + idx];
+  return v;
+}
+
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline i64 round_up64(i64 x, i64 m) { return (x + m - 1) / m * m; }
 

@@ -220,8 +220,8 @@ GWN_GLOBAL bn_finalize_kernel(const double* sums, double count, const float* gam
                               float* rvar, long long* nbt, float eps, float momentum, float* ac, float* mr, int C) {
   GWN_PDL_ENTRY();
   GWN_FOR_EACH(c, C) {
-    double mean = sums[c] / count;
-    double var = sums[C + c] / count - mean * mean;
+    double mean = stat_sum(sums, (int)c, C) / count;
+    double var = stat_sum(sums, C + (int)c, C) / count - mean * mean;
     if (var < 0.0) var = 0.0;
     float rstd = (float)(1.0 / sqrt(var + (double)eps));
     float a = gamma[c] * rstd;
@@ -268,7 +268,7 @@ GWN_GLOBAL bn_bwd_apply_kernel(float* dy, const float* u, const float* ac, const
     float r;
     if (training) {
       float xh = (u[i] - mr[c]) * mr[C + c];
-      float m1 = (float)(bsum[c] / count), m2 = (float)(bsum[C + c] / count);
+      float m1 = (float)(stat_sum(bsum, c, C) / count), m2 = (float)(stat_sum(bsum, C + c, C) / count);
       r = a * (g - m1 - xh * m2);
     } else {
       r = a * g;
@@ -276,8 +276,8 @@ GWN_GLOBAL bn_bwd_apply_kernel(float* dy, const float* u, const float* ac, const
     dy[i] = r;
     if (dh) dh[i] = r * kp[j];
     if (i < C) {
-      dgamma[i] = (float)bsum[C + i];
-      dbeta[i] = (float)bsum[i];
+      dgamma[i] = (float)stat_sum(bsum, C + (int)i, C);
+      dbeta[i] = (float)stat_sum(bsum, (int)i, C);
     }
     }
   }
@@ -294,6 +294,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply8_kernel(float* __restrict__ 
                                                             float* dgamma, float* dbeta, i64 n8, int C, float* __restrict__ dh,
                                                             DropoutSrc drop) {
   GWN_PDL_ENTRY();
+  // the replicated backward sums, added up once per block
+  __shared__ double sb[1024];   // [2*C], C <= 512 (checked by the launcher)
+  for (int k = threadIdx.x; k < 2 * C; k += blockDim.x) sb[k] = stat_sum(bsum, k, C);
+  __syncthreads();
   const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = (int)((t0 * 8) & (i64)(C - 1));
   float a[8], mean[8], rstd[8], m1[8], m2[8];
@@ -302,14 +306,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply8_kernel(float* __restrict__ 
     a[j] = ac[c0 + j];
     mean[j] = mr[c0 + j];
     rstd[j] = mr[C + c0 + j];
-    m1[j] = training ? (float)(bsum[c0 + j] / count) : 0.0f;
-    m2[j] = training ? (float)(bsum[C + c0 + j] / count) : 0.0f;
+    m1[j] = training ? (float)(sb[c0 + j] / count) : 0.0f;
+    m2[j] = training ? (float)(sb[C + c0 + j] / count) : 0.0f;
   }
   if (t0 * 8 < C) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      dgamma[c0 + j] = (float)bsum[C + c0 + j];
-      dbeta[c0 + j] = (float)bsum[c0 + j];
+      dgamma[c0 + j] = (float)sb[C + c0 + j];
+      dbeta[c0 + j] = (float)sb[c0 + j];
     }
   }
   for (i64 i8 = t0; i8 < n8; i8 += (i64)gridDim.x * blockDim.x) {

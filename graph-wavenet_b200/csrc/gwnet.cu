@@ -309,12 +309,16 @@ static int build_plan(gwn_plan* p) {
   p->pk_wt_lo = p->pk_wd_lo + align_up((i64)C * 4 * D);
   p->pk_wm_lo = p->pk_wt_lo + align_up((i64)p->nseg * D * C);
   const i64 pack_floats = p->pk_wm_lo + align_up((i64)p->nseg * D * C);
+  {   // BatchNorm forward sums of all layers: contiguous, so one memset clears them
+    const i64 per = (i64)4 * C * GWN_STAT_REPL;   // GWN_STAT_REPL replicas of 2*C doubles
+    const i64 o_s0 = take(per * nL);
+    for (int i = 0; i < nL; ++i) p->o_sums[i] = o_s0 + per * i;
+  }
   for (int i = 0; i < nL; ++i) {
     p->o_g[i] = take(p->P(i) * D * p->nseg);  // g_i followed by its hop tensors
     p->o_u[i] = take(p->P(i) * C);
     p->o_ac[i] = take(2 * C);
     p->o_mr[i] = take(2 * C);
-    p->o_sums[i] = take(4 * C);               // 2*C doubles
     p->o_pack[i] = take(pack_floats);         // K-major packed weights for the tcgen05 position GEMMs
   }
   p->o_skip = take(p->PT() * Sk);
@@ -379,7 +383,7 @@ static int build_plan(gwn_plan* p) {
   p->o_dskip = take(p->PT() * Sk);
   p->o_dA = take(N * p->ld);
   p->o_dR = take(N * p->ld);
-  p->o_bsum = take((i64)nL * 4 * C);          // per layer 2*C doubles
+  p->o_bsum = take((i64)nL * 4 * C * GWN_STAT_REPL);   // per layer GWN_STAT_REPL replicas of 2*C doubles
   {
     const bool hx3 = p->head_tc && c.precision == GWN_PREC_FP32X3;
     p->o_hb_wt = take(p->head_tc ? (i64)Sk * nL * D : 0);
@@ -604,7 +608,7 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
   (void)supB;
   // ---- BN bookkeeping
   if (a->training) {
-    for (int i = 0; i < nL; ++i) GWN_TRY(dev_memset(ws + p->o_sums[i], 0, sizeof(double) * 2 * C, st));
+    GWN_TRY(dev_memset(ws + p->o_sums[0], 0, sizeof(double) * 2 * C * GWN_STAT_REPL * nL, st));
   } else {
     for (int i = 0; i < nL; ++i)
       GWN_LAUNCH_1D(bn_eval_kernel, C, st, P_<float>(prm, p->li[i].bnw), P_<float>(prm, p->li[i].bnb),
@@ -829,7 +833,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
   const int dmode = a->dropout_mode;
 
   GWN_TRY(dev_memset(gf, 0, sizeof(float) * p->grad_floats, st));
-  GWN_TRY(dev_memset(sc + p->o_bsum, 0, sizeof(float) * (i64)nL * 4 * C, st));
+  GWN_TRY(dev_memset(sc + p->o_bsum, 0, sizeof(float) * (i64)nL * 4 * C * GWN_STAT_REPL, st));
   if (c.adaptive) GWN_TRY(dev_memset(sc + p->o_dA, 0, sizeof(float) * (i64)N * p->ld, st));
   if (!dout_ready) GWN_TRY(dev_memset(sc + p->o_dout, 0, sizeof(float) * PT * p->ldo, st));
 
@@ -1097,15 +1101,15 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
       {
       ProfScope prof("bn_bwd_apply", st, 4.0 * Pi * C * (use_dh ? 4.0 : 3.0), 0.0);
 #if !GWN_EMU
-      if (C >= 8 && C <= 2048 && (C & (C - 1)) == 0 && (Pi * C) % 8 == 0) {
+      if (C >= 8 && C <= 512 && (C & (C - 1)) == 0 && (Pi * C) % 8 == 0) {
         GWN_LAUNCH_1D(bn_bwd_apply8_kernel, Pi * C / 8, st, cur, ws + p->o_u[i], ws + p->o_ac[i], ws + p->o_mr[i],
-                    reinterpret_cast<const double*>(sc + p->o_bsum + (i64)i * 4 * C), (double)Pi, training,
+                    reinterpret_cast<const double*>(sc + p->o_bsum + (i64)i * 4 * C * GWN_STAT_REPL), (double)Pi, training,
                     G(p->li[i].bnw), G(p->li[i].bnb), Pi * C / 8, C, use_dh ? dh_buf : (float*)nullptr, ldrop);
       } else
 #endif
       {
         GWN_LAUNCH_1D(bn_bwd_apply_kernel, Pi * C / 4, st, cur, ws + p->o_u[i], ws + p->o_ac[i], ws + p->o_mr[i],
-                    reinterpret_cast<const double*>(sc + p->o_bsum + (i64)i * 4 * C), (double)Pi, training,
+                    reinterpret_cast<const double*>(sc + p->o_bsum + (i64)i * 4 * C * GWN_STAT_REPL), (double)Pi, training,
                     G(p->li[i].bnw), G(p->li[i].bnb), Pi, C, use_dh ? dh_buf : (float*)nullptr, ldrop);
       }
 
@@ -1215,7 +1219,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
       if (i > 0) {
         ep.uprev = ws + p->o_u[i - 1];
         ep.mr = ws + p->o_mr[i - 1];
-        ep.bsum = reinterpret_cast<double*>(sc + p->o_bsum + (i64)(i - 1) * 4 * C);
+        ep.bsum = reinterpret_cast<double*>(sc + p->o_bsum + (i64)(i - 1) * 4 * C * GWN_STAT_REPL);
       }
       int pst = -1;
       if (tcpos_ok(p)) {

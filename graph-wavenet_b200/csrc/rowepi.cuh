@@ -62,27 +62,33 @@ struct RowStats32 {
 #pragma unroll
     for (int i = 0; i < 32; ++i) s1[i] = s2[i] = 0.0f;
   }
+  // Lane-transposing butterfly: after the 5 exchange steps lane L holds the warp total of column L (31 shuffles per
+  // array instead of 160), the four warps meet in shared memory with one conflict-free atomic per lane, and 64
+  // threads add the CTA totals to this CTA's replica of the global sums (GWN_STAT_REPL).
+  __device__ __forceinline__ static float lane_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int j = 0; j < o; ++j) {
+        const float send = up ? v[j] : v[j + o];
+        const float keep = up ? v[j + o] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    return v[0];
+  }
   __device__ __forceinline__ void reduce(float* smem, int etid, double* g1, double* g2, int ncols, int barid) {
     if (etid < 64) smem[etid] = 0.0f;
     asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
-#pragma unroll
-    for (int col = 0; col < 32; ++col) {
-      float a = s1[col], b = s2[col];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        b += __shfl_xor_sync(0xffffffffu, b, o);
-      }
-      if ((etid & 31) == 0) {
-        atomicAdd(smem + col, a);
-        atomicAdd(smem + 32 + col, b);
-      }
-    }
+    const int lane = etid & 31;
+    const float t1 = lane_transpose_sum(s1, lane), t2 = lane_transpose_sum(s2, lane);
+    atomicAdd(smem + lane, t1);
+    atomicAdd(smem + 32 + lane, t2);
     asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
-    if (etid < 32 && etid < ncols) {
-      atomicAdd(g1 + etid, (double)smem[etid]);
-      atomicAdd(g2 + etid, (double)smem[32 + etid]);
-    }
+    const size_t rep = (size_t)(blockIdx.x % GWN_STAT_REPL) * 64;   // replicas of [2*C] doubles, C == 32 here
+    if (etid < 32 && etid < ncols) atomicAdd(g1 + rep + etid, (double)smem[etid]);
+    else if (etid >= 32 && etid < 64 && etid - 32 < ncols) atomicAdd(g2 + rep + (etid - 32), (double)smem[etid]);
   }
 };
 
