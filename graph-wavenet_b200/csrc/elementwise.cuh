@@ -214,6 +214,95 @@ GWN_GLOBAL start_dgrad_kernel(const float* dx0, const float* W, float* gi, int B
   }
 }
 
+#if !GWN_EMU
+// ---- warp-per-position versions of the start conv kernels for C == 32 (lane = channel) ------------------------------
+// The element-per-thread kernels above pay three 64-bit divisions per output float and re-read the strided input
+// C times: 36 us for 22 MB (0.6 TB/s) forward, and the weight gradient ran as an 82 us generic GEMM with K = 172k
+// positions and 3 output columns.  Here a warp owns a position: (b, t, n) is decoded once per warp, the F input
+// features are broadcast loads, the 128-byte channel row is one coalesced access.
+constexpr int START_MAXF = 4;
+__global__ void __launch_bounds__(256) start_fwd32_kernel(const float* __restrict__ in, Strides4 is, const float* __restrict__ W,
+                                                          const float* __restrict__ bias, float* __restrict__ x0, int B, int F,
+                                                          int N, int L0, int pad) {
+  GWN_PDL_ENTRY();
+  const int lane = threadIdx.x & 31;
+  float w[START_MAXF];
+#pragma unroll
+  for (int f = 0; f < START_MAXF; ++f) w[f] = f < F ? W[lane * F + f] : 0.0f;
+  const float bs = bias[lane];
+  const unsigned P = (unsigned)B * (unsigned)L0 * (unsigned)N;
+  const unsigned nw = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned p0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p0 < P; p0 += nw) {
+    const unsigned n = p0 % (unsigned)N, bt = p0 / (unsigned)N;
+    const unsigned t = bt % (unsigned)L0, b = bt / (unsigned)L0;
+    float acc = bs;
+    if ((int)t >= pad) {
+      const float* src = in + (i64)b * is.s[0] + (i64)n * is.s[2] + (i64)((int)t - pad) * is.s[3];
+#pragma unroll
+      for (int f = 0; f < START_MAXF; ++f)
+        if (f < F) acc = fmaf(w[f], __ldg(src + (i64)f * is.s[1]), acc);
+    }
+    x0[(size_t)p0 * 32 + lane] = acc;
+  }
+}
+// dW[c][f] += sum_p dx0[p][c] * in(p, f), db[c] += sum_p dx0[p][c]  (padding positions contribute to db only).
+__global__ void __launch_bounds__(256) start_wgrad32_kernel(const float* __restrict__ dx0, const float* __restrict__ in, Strides4 is,
+                                                            float* dW, float* db, int B, int F, int N, int L0, int pad) {
+  __shared__ float red[8][32][START_MAXF + 1];
+  GWN_PDL_ENTRY();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[START_MAXF + 1];
+#pragma unroll
+  for (int f = 0; f <= START_MAXF; ++f) acc[f] = 0.0f;
+  const unsigned P = (unsigned)B * (unsigned)L0 * (unsigned)N;
+  const unsigned nw = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned p0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p0 < P; p0 += nw) {
+    const unsigned n = p0 % (unsigned)N, bt = p0 / (unsigned)N;
+    const unsigned t = bt % (unsigned)L0, b = bt / (unsigned)L0;
+    const float v = __ldg(dx0 + (size_t)p0 * 32 + lane);
+    acc[START_MAXF] += v;
+    if ((int)t >= pad) {
+      const float* src = in + (i64)b * is.s[0] + (i64)n * is.s[2] + (i64)((int)t - pad) * is.s[3];
+#pragma unroll
+      for (int f = 0; f < START_MAXF; ++f)
+        if (f < F) acc[f] = fmaf(v, __ldg(src + (i64)f * is.s[1]), acc[f]);
+    }
+  }
+#pragma unroll
+  for (int f = 0; f <= START_MAXF; ++f) red[warp][lane][f] = acc[f];
+  __syncthreads();
+  for (int k = threadIdx.x; k < 32 * (START_MAXF + 1); k += blockDim.x) {
+    const int c = k / (START_MAXF + 1), f = k - c * (START_MAXF + 1);
+    float sum = 0.0f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) sum += red[y][c][f];
+    if (f == START_MAXF) atomicAdd(db + c, sum);
+    else if (f < F) atomicAdd(dW + c * F + f, sum);
+  }
+}
+// dE2[k,w] += sum_{v in this block's slice} E1[v,k] dR[v,w]: thread = column w (coalesced dR rows, broadcast E1),
+// blockIdx.y = slice of v; the element-per-output kernel above ran 207-long dependent chains on 9 blocks (38 us).
+__global__ void __launch_bounds__(256) adp_bwd_cols_split_kernel(const float* __restrict__ dR, const float* __restrict__ E1, int R,
+                                                                 float* dE2, int N, int ld, int vchunk) {
+  GWN_PDL_ENTRY();
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= N) return;
+  const int v0 = blockIdx.y * vchunk, v1 = min(N, v0 + vchunk);
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.0f;
+  for (int v = v0; v < v1; ++v) {
+    const float g = __ldg(dR + (size_t)v * ld + w);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < R) acc[k] = fmaf(__ldg(E1 + (size_t)v * R + k), g, acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    if (k < R) atomicAdd(dE2 + (size_t)k * N + w, acc[k]);
+}
+#endif
+
 // BatchNorm2d training-mode finalize (model.py:236): batch mean / biased var -> fold constants
 // a = gamma*rstd, c = beta - mean*a; running stats with momentum and unbiased var; num_batches_tracked += 1.
 GWN_GLOBAL bn_finalize_kernel(const double* sums, double count, const float* gamma, const float* beta, float* rmean,

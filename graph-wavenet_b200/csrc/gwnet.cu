@@ -619,6 +619,14 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     ProfScope prof("start_conv_fwd", st, 4.0 * p->P0() * (c.in_dim + C), 2.0 * p->P0() * c.in_dim * C);
     Strides4 is;
     for (int k = 0; k < 4; ++k) is.s[k] = a->input_strides[k];
+#if !GWN_EMU
+    if (C == 32 && c.in_dim <= START_MAXF && p->P0() < 2147483647LL) {
+      const i64 blocks = std::min<i64>((p->P0() + 7) / 8, 148 * 16);
+      GWN_CUDA(launch_kernel(start_fwd32_kernel, dim3((unsigned)blocks), dim3(256), 0, st, a->input, is, P_<float>(prm, p->i_startw),
+                             P_<float>(prm, p->i_startb), ws + p->o_x0, B, c.in_dim, N, p->L0, p->pad));
+      count_launch();
+    } else
+#endif
     GWN_LAUNCH_1D(start_fwd_kernel, p->P0() * C, st, a->input, is, P_<float>(prm, p->i_startw), P_<float>(prm, p->i_startb),
                   ws + p->o_x0, B, c.in_dim, N, p->L0, p->pad, C);
   }
@@ -1417,8 +1425,21 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     memset(&ep, 0, sizeof(ep));
     ep.dw[0] = G(p->i_startw); ep.db[0] = G(p->i_startb); ep.set_wd(c.in_dim); ep.nseg = 1; ep.ldw = c.in_dim; ep.nbias = 1;
     GWN_CHECK_ARG(p->P0() < 2147483647LL, "backward: too many input positions");
-    GemmShape sh{(i64)C, c.in_dim + 1, (int)p->P0(), pick_ksplit(C, c.in_dim + 1, p->P0(), TW32::BM, TW32::BN, kTargetBlocks), 1};
-    GWN_TRY((launch_gemm<TW32>(la, lb, ep, sh, st)));
+    bool sw_done = false;
+#if !GWN_EMU
+    if (C == 32 && c.in_dim <= START_MAXF && p->P0() < 2147483647LL) {   // warp-per-position reduction (elementwise.cuh)
+      Strides4 is;
+      for (int k = 0; k < 4; ++k) is.s[k] = a->input_strides[k];
+      GWN_CUDA(launch_kernel(start_wgrad32_kernel, dim3(148 * 4), dim3(256), 0, st, (const float*)cur, a->input, is,
+                             G(p->i_startw), G(p->i_startb), B, c.in_dim, N, p->L0, p->pad));
+      count_launch();
+      sw_done = true;
+    }
+#endif
+    if (!sw_done) {
+      GemmShape sh{(i64)C, c.in_dim + 1, (int)p->P0(), pick_ksplit(C, c.in_dim + 1, p->P0(), TW32::BM, TW32::BN, kTargetBlocks), 1};
+      GWN_TRY((launch_gemm<TW32>(la, lb, ep, sh, st)));
+    }
     if (a->grad_input)
       GWN_LAUNCH_1D(start_dgrad_kernel, (i64)B * c.in_dim * N * c.seq_len, st, (const float*)cur, P_<float>(prm, p->i_startw),
                     a->grad_input, B, c.in_dim, N, c.seq_len, p->L0, p->pad, C);
@@ -1428,6 +1449,14 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     const float* Ap = ws + p->o_sup + (i64)(p->S - 1) * N * p->ld;
     GWN_LAUNCH_WARP_ROWS(adp_bwd_rows_kernel, N, st, (const float*)(sc + p->o_dA), Ap, P_<float>(prm, p->i_nv1),
                          P_<float>(prm, p->i_nv2), c.apt_rank, sc + p->o_dR, G(p->i_nv1), N, p->ld);
+#if !GWN_EMU
+    if (c.apt_rank <= 16) {   // G(nv2) was zeroed with the flat gradient buffer: the slices add into it
+      const int slices = 32, vchunk = (N + slices - 1) / slices;
+      GWN_CUDA(launch_kernel(adp_bwd_cols_split_kernel, dim3((unsigned)((N + 63) / 64), (unsigned)slices), dim3(64), 0, st,
+                             (const float*)(sc + p->o_dR), P_<float>(prm, p->i_nv1), c.apt_rank, G(p->i_nv2), N, p->ld, vchunk));
+      count_launch();
+    } else
+#endif
     GWN_LAUNCH_1D(adp_bwd_cols_kernel, (i64)c.apt_rank * N, st, (const float*)(sc + p->o_dR), P_<float>(prm, p->i_nv1),
                   c.apt_rank, G(p->i_nv2), N, p->ld);
   }

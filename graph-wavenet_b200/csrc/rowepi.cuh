@@ -5,6 +5,8 @@
 //     static constexpr int kAddends;                       // addend tiles TMA stages per row tile (0..2)
 //     static constexpr int kGroups;                        // epilogue groups of 4 warps (2 unless registers forbid)
 //     void load_addends(const AddendRows& a, bool valid);  // copy the row's addends from the staged tiles to registers
+//     static constexpr bool kLazyAddends;                  // true: consume16 reads the staged tiles itself (fewer live
+//                                                          // registers); the tiles are handed back after the last block
 //     void consume16(i64 m, int c0, int n0, const float (&v)[16], RowSink& out);   // accumulator columns c0..c0+15 of
 //                                                          // row m in this tile; n0 = the tile's first output column
 //     void finish_rows(float* red, int etid);              // if kHasFinish: block-level reduce of column statistics
@@ -100,6 +102,7 @@ __device__ __forceinline__ float gate_tanh(float x) { return 1.0f - __fdividef(2
 
 // model.py:208-212 -- accumulator columns interleaved (f0,g0,f1,g1,...), N = 64 -> 32 gated outputs.
 struct RowGate {
+  static constexpr bool kLazyAddends = false;
   static constexpr bool kHasFinish = false;
   static constexpr int kAccPerBlock = 64;
   static constexpr int kAddends = 0;
@@ -123,6 +126,7 @@ struct RowGate {
 
 // Gate backward from recomputed pre-activations: dpre[m][2ch+{0,1}] (interleaved, 64 wide).
 struct RowGateBwd {
+  static constexpr bool kLazyAddends = false;
   static constexpr bool kHasFinish = false;
   static constexpr int kAccPerBlock = 32;
   static constexpr int kAddends = 1;   // dg rows
@@ -154,6 +158,7 @@ struct RowGateBwd {
 
 // gcn tail + residual + BatchNorm statistics (model.py:53-54, 234-236), N = 32.
 struct RowMlp {
+  static constexpr bool kLazyAddends = false;
   static constexpr bool kHasFinish = true;
   static constexpr int kAccPerBlock = 32;
   static constexpr int kAddends = 1;   // residual rows (tile 0; staged only when res != nullptr)
@@ -204,6 +209,7 @@ struct RowMlp {
 
 // mlp input gradient: N = nseg*32 columns scattered to the per-segment tensors out[(q*M + m)*32 + nn].
 struct RowSeg {
+  static constexpr bool kLazyAddends = false;
   static constexpr bool kHasFinish = false;
   static constexpr int kAccPerBlock = 32;
   static constexpr int kAddends = 0;
@@ -219,10 +225,11 @@ struct RowSeg {
 
 // Gated-conv input gradient + residual path + BatchNorm-backward statistics of the layer below, N = 32.
 struct RowTcnDgrad {
-  static constexpr bool kHasFinish = true;
-  static constexpr int kAccPerBlock = 32;
+  static constexpr bool kLazyAddends = true;   // du / u_prev rows are read from the staged tiles 16 columns at a time:
+  static constexpr bool kHasFinish = true;     // with them in registers (64) next to the 64 statistics registers only
+  static constexpr int kAccPerBlock = 32;      // one epilogue group fitted and the kernel was epilogue-bound
   static constexpr int kAddends = 2;
-  static constexpr int kGroups = 1;    // 64 addend + 64 statistics registers per thread: one group of 128 threads only
+  static constexpr int kGroups = 2;
   static constexpr bool kDirectStore = false;
   float* dx;           // [P_in, 32]
   const float* du;     // nullable [P_out, 32]
@@ -230,25 +237,30 @@ struct RowTcnDgrad {
   const float* uprev;  // nullable
   const float* mr;     // mean[32], rstd[32]
   double* bsum;
-  float durow[32], urow[32];
+  AddendRows ar;
   RowStats32 cs;
   __device__ __forceinline__ void init() { cs.reset(); }
   // addend tile 0: du rows shifted by (L_in - L_out) time steps (rows before the first step arrive as zeros: TMA
   // out-of-bounds fill); tile 1: the layer-below pre-BN rows (only staged when uprev != nullptr)
-  __device__ __forceinline__ void load_addends(const AddendRows& a, bool valid) {
-    if (!valid) return;
-    if (du) a.load<32>(0, 0, durow);
-    if (uprev) a.load<32>(1, 0, urow);
-  }
+  __device__ __forceinline__ void load_addends(const AddendRows& a, bool) { ar = a; }
   __device__ __forceinline__ void consume16(i64, int c0, int, const float (&v)[16], const RowSink& out) {
     float o[16];
+    if (du) {
+      float d[16];
+      ar.load<16>(0, c0, d);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) o[c] = v[c] + (du ? durow[c0 + c] : 0.0f);
+      for (int c = 0; c < 16; ++c) o[c] = v[c] + d[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) o[c] = v[c];
+    }
     out.put16(c0, o);
     if (uprev) {
+      float ur[16];
+      ar.load<16>(1, c0, ur);
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
-        const float xh = (urow[c0 + c] - __ldg(mr + c0 + c)) * __ldg(mr + 32 + c0 + c);
+        const float xh = (ur[c] - __ldg(mr + c0 + c)) * __ldg(mr + 32 + c0 + c);
         cs.s1[c0 + c] += o[c];
         cs.s2[c0 + c] += o[c] * xh;
       }
@@ -260,6 +272,7 @@ struct RowTcnDgrad {
 };
 // Dense head layers (model.py:216-222, 238-240 and their input gradients): out = act(acc + bias[col]) [* (gate > 0)].
 struct RowDense {
+  static constexpr bool kLazyAddends = false;
   static constexpr bool kHasFinish = false;
   static constexpr int kAccPerBlock = 32;
   static constexpr int kAddends = 0;
@@ -298,6 +311,7 @@ struct RowDense {
 // positions m = (b*T + t)*N + n.  O <= 16 columns, written straight from registers (consecutive threads = consecutive
 // nodes = consecutive addresses for T == 1).
 struct RowNCHW {
+  static constexpr bool kLazyAddends = false;
   static constexpr bool kHasFinish = false;
   static constexpr int kAccPerBlock = 16;
   static constexpr int kAddends = 0;

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
         ar.row[1] = ad_ptr + (size_t)(buf * NADD + (NADD > 1 ? 1 : 0)) * TP_A_BYTES + r * 128;
         ar.x = (uint32_t)(r & 7);
         ep.load_addends(ar, valid);
-        mbar_arrive(eempty_bar(buf));
+        if constexpr (!EP::kLazyAddends) mbar_arrive(eempty_bar(buf));
       }
       if (!mbar_wait(tfull_bar(buf), bphase, 15)) break;
       tc_fence_after();
@@ -340,6 +340,9 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
       } else {
 #pragma unroll 1
         for (int blk = 0; blk * APB < ncols; ++blk) do_block(blk);
+      }
+      if constexpr (EP::kLazyAddends) {   // consume16 read the staged addend tiles: hand them back only now
+        if (has_add) mbar_arrive(eempty_bar(buf));
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
