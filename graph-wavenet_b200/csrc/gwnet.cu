@@ -1110,9 +1110,14 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
       ProfScope prof("bn_bwd_apply", st, 4.0 * Pi * C * (use_dh ? 4.0 : 3.0), 0.0);
 #if !GWN_EMU
       if (C >= 8 && C <= 512 && (C & (C - 1)) == 0 && (Pi * C) % 8 == 0) {
-        GWN_LAUNCH_1D(bn_bwd_apply8_kernel, Pi * C / 8, st, cur, ws + p->o_u[i], ws + p->o_ac[i], ws + p->o_mr[i],
-                    reinterpret_cast<const double*>(sc + p->o_bsum + (i64)i * 4 * C * GWN_STAT_REPL), (double)Pi, training,
-                    G(p->li[i].bnw), G(p->li[i].bnb), Pi * C / 8, C, use_dh ? dh_buf : (float*)nullptr, ldrop);
+        // 8 resident blocks per SM, grid-stride: the per-block prologue (replica sums, channel constants) is paid once
+        const i64 n8 = Pi * C / 8;
+        const i64 blocks = std::min<i64>((n8 + 255) / 256, 148 * 8);
+        GWN_CUDA(launch_kernel(bn_bwd_apply8_kernel, dim3((unsigned)blocks), dim3(256), 0, st, cur, (const float*)(ws + p->o_u[i]),
+                               (const float*)(ws + p->o_ac[i]), (const float*)(ws + p->o_mr[i]),
+                               reinterpret_cast<const double*>(sc + p->o_bsum + (i64)i * 4 * C * GWN_STAT_REPL), (double)Pi, training,
+                               G(p->li[i].bnw), G(p->li[i].bnb), n8, C, use_dh ? dh_buf : (float*)nullptr, ldrop));
+        count_launch();
       } else
 #endif
       {
@@ -1430,7 +1435,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     if (C == 32 && c.in_dim <= START_MAXF && p->P0() < 2147483647LL) {   // warp-per-position reduction (elementwise.cuh)
       Strides4 is;
       for (int k = 0; k < 4; ++k) is.s[k] = a->input_strides[k];
-      GWN_CUDA(launch_kernel(start_wgrad32_kernel, dim3(148 * 4), dim3(256), 0, st, (const float*)cur, a->input, is,
+      GWN_CUDA(launch_kernel(start_wgrad32_kernel, dim3(148 * 8), dim3(256), 0, st, (const float*)cur, a->input, is,
                              G(p->i_startw), G(p->i_startb), B, c.in_dim, N, p->L0, p->pad));
       count_launch();
       sw_done = true;
