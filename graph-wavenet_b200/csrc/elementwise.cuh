@@ -327,24 +327,34 @@ __global__ void __launch_bounds__(256) adp_bwd_cols_split_kernel(const float* __
 
 // BatchNorm2d training-mode finalize (model.py:236): batch mean / biased var -> fold constants
 // a = gamma*rstd, c = beta - mean*a; running stats with momentum and unbiased var; num_batches_tracked += 1.
+// batch statistics of channel c -> mean, biased variance, rstd and the fold constants a = gamma*rstd, cc = beta - mean*a
+GWN_HD void bn_consts(const double* sums, double count, const float* gamma, const float* beta, float eps, int c, int C,
+                      double& mean, double& var, float& rstd, float& a, float& cc) {
+  mean = stat_sum(sums, c, C) / count;
+  var = stat_sum(sums, C + c, C) / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+  a = gamma[c] * rstd;
+  cc = beta[c] - (float)mean * a;
+}
+GWN_HD void bn_finalize_channel(const double* sums, double count, const float* gamma, const float* beta, float* rmean,
+                                float* rvar, long long* nbt, float eps, float momentum, float* ac, float* mr, int C, int c) {
+  double mean, var;
+  float rstd, a, cc;
+  bn_consts(sums, count, gamma, beta, eps, c, C, mean, var, rstd, a, cc);
+  ac[c] = a;
+  ac[C + c] = cc;
+  mr[c] = (float)mean;
+  mr[C + c] = rstd;
+  double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+  rmean[c] = (1.0f - momentum) * rmean[c] + momentum * (float)mean;
+  rvar[c] = (1.0f - momentum) * rvar[c] + momentum * (float)unbiased;
+  if (c == 0) nbt[0] += 1;
+}
 GWN_GLOBAL bn_finalize_kernel(const double* sums, double count, const float* gamma, const float* beta, float* rmean,
                               float* rvar, long long* nbt, float eps, float momentum, float* ac, float* mr, int C) {
   GWN_PDL_ENTRY();
-  GWN_FOR_EACH(c, C) {
-    double mean = stat_sum(sums, (int)c, C) / count;
-    double var = stat_sum(sums, C + (int)c, C) / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    float a = gamma[c] * rstd;
-    ac[c] = a;
-    ac[C + c] = beta[c] - (float)mean * a;
-    mr[c] = (float)mean;
-    mr[C + c] = rstd;
-    double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    rmean[c] = (1.0f - momentum) * rmean[c] + momentum * (float)mean;
-    rvar[c] = (1.0f - momentum) * rvar[c] + momentum * (float)unbiased;
-    if (c == 0) nbt[0] += 1;
-  }
+  GWN_FOR_EACH(c, C) { bn_finalize_channel(sums, count, gamma, beta, rmean, rvar, nbt, eps, momentum, ac, mr, C, (int)c); }
 }
 // Eval mode: fold constants from the running statistics.
 GWN_GLOBAL bn_eval_kernel(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps,
@@ -475,6 +485,38 @@ GWN_GLOBAL pack_tcn_fwd_kernel(const float* wf, const float* wg, const float* bf
     }
     extra = warp_sum(extra);
     if (lane == 0) (g ? bgp : bfp)[ch] = (g ? bg : bf)[ch] + extra;
+  }
+}
+// BatchNorm finalize of layer i AND the packed gated-conv weights of layer i+1 (which fold that BatchNorm) in one
+// launch -- two tiny kernels less on the critical path of every layer.  Warp rows 0..2D-1 pack (each recomputes the
+// fold constants of the channels it touches from the sums: same arithmetic as bn_consts, hence the same bits as
+// ac[] below), warp row 2D does the finalize duties.
+GWN_GLOBAL bn_finalize_pack_kernel(const double* sums, double count, const float* gamma, const float* beta, float* rmean,
+                                   float* rvar, long long* nbt, float eps, float momentum, float* ac, float* mr, int C,
+                                   const float* wf, const float* wg, const float* bf, const float* bg, float* Wp, float* bfp,
+                                   float* bgp, int D, float* Wlo) {
+  GWN_PDL_ENTRY();
+  GWN_FOR_EACH_WARP_ROW(n, 2 * D + 1, lane, WS) {
+    if (n == 2 * D) {
+      for (int c = lane; c < C; c += WS) bn_finalize_channel(sums, count, gamma, beta, rmean, rvar, nbt, eps, momentum, ac, mr, C, c);
+    } else {
+      const int ch = (int)(n >> 1), g = (int)(n & 1);
+      const float* w = g ? wg : wf;
+      float extra = 0.0f;
+      for (int k = lane; k < 2 * C; k += WS) {
+        const int tap = k / C, ci = k - tap * C;
+        double mean, var;
+        float rstd, a, cc;
+        bn_consts(sums, count, gamma, beta, eps, ci, C, mean, var, rstd, a, cc);
+        const float v = w[((i64)ch * C + ci) * 2 + tap];
+        const float pv = v * a;
+        Wp[n * (2 * C) + k] = pv;
+        if (Wlo) Wlo[n * (2 * C) + k] = tf32_lo(pv);
+        extra = fmaf(v, cc, extra);
+      }
+      extra = warp_sum(extra);
+      if (lane == 0) (g ? bgp : bfp)[ch] = (g ? bg : bf)[ch] + extra;
+    }
   }
 }
 // Gated conv input gradient:  Wd[ci][tap*2D + j] = W_{j&1}[j>>1][ci][tap]

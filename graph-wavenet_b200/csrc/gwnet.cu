@@ -632,6 +632,7 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
   }
   GWN_TRY(side_join(p, sd, st, 1));
   // ---- WaveNet layers (model.py:192-236)
+  bool packed_next = false;
   for (int i = 0; i < nL; ++i) {
     const float* prev = i == 0 ? ws + p->o_x0 : ws + p->o_u[i - 1];
     const float* prev_ac = i == 0 ? nullptr : ws + p->o_ac[i - 1];
@@ -645,7 +646,7 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
       int pst = -1;
       if (tcpos_ok(p)) {
         float* pk = ws + p->o_pack[i];
-        if (i > 0)   // BatchNorm of the layer below folded in (layer 0 was packed on the side stream)
+        if (i > 0 && !packed_next)   // BatchNorm of the layer below folded in (layer 0 was packed on the side stream)
           GWN_LAUNCH_WARP_ROWS(pack_tcn_fwd_kernel, 2 * D, st, P_<float>(prm, p->li[i].fw), P_<float>(prm, p->li[i].gw),
                         P_<float>(prm, p->li[i].fb), P_<float>(prm, p->li[i].gb), prev_ac, pk + p->pk_wp, pk + p->pk_bf,
                         pk + p->pk_bg, D, C, x3(p) ? pk + p->pk_wp_lo : (float*)nullptr);
@@ -712,7 +713,17 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     if (tcpos_ok(p) && x3(p)) m.W_lo = pk_m + p->pk_wm_lo;   // split on the side stream
     if (i == 0 && tcpos_ok(p)) GWN_TRY(side_join(p, sd, st, 2));
     GWN_TRY(mlp_forward(m, st));
-    if (a->training) {
+    packed_next = false;
+    if (a->training && tcpos_ok(p) && i + 1 < nL) {   // finalize + the next layer's packed gated-conv weights
+      float* pk = ws + p->o_pack[i + 1];
+      GWN_LAUNCH_WARP_ROWS(bn_finalize_pack_kernel, 2 * D + 1, st, reinterpret_cast<const double*>(ws + p->o_sums[i]), (double)Pi,
+                    P_<float>(prm, p->li[i].bnw), P_<float>(prm, p->li[i].bnb), const_cast<float*>(P_<float>(prm, p->li[i].bnm)),
+                    const_cast<float*>(P_<float>(prm, p->li[i].bnv)), const_cast<long long*>(P_<long long>(prm, p->li[i].bnt)),
+                    c.bn_eps, c.bn_momentum, ws + p->o_ac[i], ws + p->o_mr[i], C, P_<float>(prm, p->li[i + 1].fw),
+                    P_<float>(prm, p->li[i + 1].gw), P_<float>(prm, p->li[i + 1].fb), P_<float>(prm, p->li[i + 1].gb),
+                    pk + p->pk_wp, pk + p->pk_bf, pk + p->pk_bg, D, x3(p) ? pk + p->pk_wp_lo : (float*)nullptr);
+      packed_next = true;
+    } else if (a->training) {
       GWN_LAUNCH_1D(bn_finalize_kernel, C, st, reinterpret_cast<const double*>(ws + p->o_sums[i]), (double)Pi,
                     P_<float>(prm, p->li[i].bnw), P_<float>(prm, p->li[i].bnb), const_cast<float*>(P_<float>(prm, p->li[i].bnm)),
                     const_cast<float*>(P_<float>(prm, p->li[i].bnv)), const_cast<long long*>(P_<long long>(prm, p->li[i].bnt)),

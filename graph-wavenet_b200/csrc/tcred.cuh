@@ -89,6 +89,11 @@ struct TrParams {
   int njobs;
   int job_cta0[TR_MAXJOBS + 1], job_chunks[TR_MAXJOBS], job_cps[TR_MAXJOBS];
   int jseg[8], jrshift[TR_MAXJOBS][8];
+  // drain > 0 (only when mtiles * N <= 64): the issuer hands the accumulator to the epilogue warps every `drain`
+  // chunks (two TMEM buffers, alternating); they add it to fp32 registers with round-to-nearest and write the slot at
+  // the end.  Keeps every tensor-core accumulation chain short: the MMA's own accumulate step truncates, so a chain of
+  // ~150 chunks cost 1.4e-4 of relative error on the first layer's filter gradient.
+  int drain;
 };
 
 // X3 = 3xTF32 mode (fp32-grade): both operands are activations, so warps 2 and 3 split BOTH tiles of a stage into
@@ -108,7 +113,9 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
   auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
   auto split_bar = [&](int s) { return bar0 + 8u * (2 * p.stages + s); };
   const uint32_t done_bar = bar0 + 8u * (3 * p.stages);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * p.stages + 1 + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * p.stages + 3 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // output tile of this CTA: (k split, row/block group mg, column group ntile)
@@ -157,6 +164,10 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       mbar_init(split_bar(s), 64);
     }
     mbar_init(done_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -211,8 +222,19 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     int stage = 0;
     uint32_t phase = 0;
     bool first = true;
+    int acc = 0, in_acc = 0;                 // drain mode: current TMEM buffer, chunks accumulated in it
+    uint32_t accphase[2] = {0u, 0u};
+    const uint32_t acc_cols = (uint32_t)(p.mtiles * p.N);
+    uint32_t tm0 = tmem_base;
+    bool ok = true;
     for (int c = c_beg; c < c_end; ++c) {
-      if (!mbar_wait(full_bar(stage), phase, 22)) break;
+      if (p.drain > 0 && in_acc == 0) {      // a fresh buffer: wait until the epilogue has drained its previous use
+        if (!mbar_wait(tempty_bar(acc), accphase[acc] ^ 1u, 26)) { ok = false; break; }
+        tc_fence_after();
+        tm0 = tmem_base + (uint32_t)acc * acc_cols;
+        first = true;
+      }
+      if (!mbar_wait(full_bar(stage), phase, 22)) { ok = false; break; }
       tc_fence_after();
       const uint32_t sa = st0 + stage * stage_bytes, sb = sa + p.a_bytes;
       auto descs = [&](int t, int kk, uint64_t& adesc, uint64_t& bdesc) {
@@ -227,7 +249,7 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       };
 #pragma unroll 1
       for (int t = 0; t < p.mtiles; ++t) {
-        const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.N);
+        const uint32_t d_tmem = tm0 + (uint32_t)(t * p.N);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           uint64_t adesc, bdesc;
@@ -237,12 +259,12 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       }
       if (X3) {   // remainder terms after the split of this stage (it ran while the MMAs above were issued); the remainder
                   // planes sit plane_bytes further, same layout
-        if (!mbar_wait(split_bar(stage), phase, 24)) break;
+        if (!mbar_wait(split_bar(stage), phase, 24)) { ok = false; break; }
         tc_fence_after();
         const uint64_t off = (uint64_t)((uint32_t)plane_bytes >> 4);
 #pragma unroll 1
         for (int t = 0; t < p.mtiles; ++t) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.N);
+          const uint32_t d_tmem = tm0 + (uint32_t)(t * p.N);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             uint64_t adesc, bdesc;
@@ -255,8 +277,14 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       first = false;
       tc_commit(empty_bar(stage));
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      if (p.drain > 0 && (++in_acc == p.drain || c + 1 == c_end)) {   // hand this buffer to the epilogue warps
+        tc_commit(tfull_bar(acc));
+        accphase[acc] ^= 1u;
+        acc ^= 1;
+        in_acc = 0;
+      }
     }
-    tc_commit(done_bar);
+    if (p.drain == 0 && ok) tc_commit(done_bar);
   } else if (X3 && (warp == 2 || warp == 3)) {
     // ===================================================== splitter: remainders of the TMA-written A blocks and of B
     const int t64 = threadIdx.x - 64;
@@ -288,7 +316,48 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     // ===================================================== epilogue: this CTA's partial result -> its private slot
     // (plain 128-bit stores; a small follow-up kernel sums the slots -- float atomics from 148 CTAs onto the same
     // few thousand addresses cost ~35-85 us per launch, ncu r01b)
-    if (c_end > c_beg && mbar_wait(done_bar, 0, 23)) {
+    if (p.drain > 0) {
+      const int ew = warp - 4;
+      const int row = ew * 32 + lane;
+      float* slot = p.partial + (size_t)blockIdx.x * p.slot_floats;
+      const int ngrp = p.mtiles * p.N / 16;          // 16-column groups of the accumulator (<= 4), g -> (row tile, column)
+      const int gpt = p.N / 16;
+      float sum[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) sum[i] = 0.0f;
+      const int ndrain = (c_end - c_beg + p.drain - 1) / p.drain;
+      bool ok = true;
+      for (int d = 0; d < ndrain && ok; ++d) {
+        const int buf = d & 1;
+        if (!mbar_wait(tfull_bar(buf), (uint32_t)(d >> 1) & 1u, 27)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(buf * p.mtiles * p.N);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g < ngrp) {
+            uint32_t r[16];
+            tc_ld16(taddr + (uint32_t)((g / gpt) * p.N + (g % gpt) * 16), r);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sum[g * 16 + j] += __uint_as_float(r[j]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(buf));
+      }
+      if (ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g < ngrp) {
+            float* orow = slot + (size_t)((g / gpt) * 128 + row) * p.N + (g % gpt) * 16;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<float4*>(orow + 4 * q) = make_float4(sum[g * 16 + 4 * q], sum[g * 16 + 4 * q + 1], sum[g * 16 + 4 * q + 2],
+                                                                      sum[g * 16 + 4 * q + 3]);
+          }
+        }
+      }
+    } else if (c_end > c_beg && mbar_wait(done_bar, 0, 23)) {
       tc_fence_after();
       const int ew = warp - 4;
       const int row = ew * 32 + lane;
@@ -600,6 +669,7 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
   p.slot_floats = (i64)p.mtiles * 128 * p.N;
   if ((i64)grid * p.slot_floats > a.partial_floats) return -1;
   p.partial = a.partial;
+  if (a.mode == 0 && p.mtiles * p.N <= 64) p.drain = 16;
   const int smem_bytes = p.stages * stage_bytes + 1024 + 256;
   static cudaError_t attr = cudaFuncSetAttribute(tcred_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   static cudaError_t attr3 = cudaFuncSetAttribute(tcred_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
@@ -678,10 +748,13 @@ inline int launch_tcred_jobs(const TcRedJobsArgs& a, cudaStream_t stream, TcRedR
   // CTAs per job in proportion to its K extent (at least one, at most one per chunk); leftovers to the most loaded jobs.
   // A CTA accumulates its whole K range in ONE fp32 TMEM accumulator, and the tensor core's accumulate step truncates:
   // the error grows linearly with the chain (measured: 147 chunks per CTA -> 1.4e-4 on the first layer's filter
-  // gradient, 34 chunks -> 3e-5), so the grid grows to whole extra rounds of CTAs until a range is <= 48 chunks.
+  // gradient, 34 chunks -> 3e-5).  Small accumulators (<= 64 columns) are drained into registers every 16 chunks
+  // (TrParams::drain); otherwise the grid grows to whole extra rounds of CTAs until a range is <= 48 chunks.
   const int sms = num_sms;
   int T = sms;
-  {
+  if (p.mtiles * p.N <= 64) {
+    p.drain = 16;   // short chains by draining into registers: one round of CTAs is enough
+  } else {
     long long want = (tot + 47) / 48;
     want = (want + sms - 1) / sms * sms;
     const long long cap = a.partial_floats / ((i64)p.mtiles * 128 * p.N);
