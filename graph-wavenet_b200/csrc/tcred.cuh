@@ -94,10 +94,17 @@ struct TrParams {
   // the end.  Keeps every tensor-core accumulation chain short: the MMA's own accumulate step truncates, so a chain of
   // ~150 chunks cost 1.4e-4 of relative error on the first layer's filter gradient.
   int drain;
+  int lo_stages;   // 3xTF32: buffers of the remainder ring (0 otherwise)
+  int diag;        // timing diagnostics (wrong results): 1 = splitter skips its work, 2 = issuer skips the MMAs
+  int abox;        // multi-job: the job's A blocks are the consecutive segments 0..na-1, unshifted: ONE 4-D TMA box
 };
 
 // X3 = 3xTF32 mode (fp32-grade): both operands are activations, so warps 2 and 3 split BOTH tiles of a stage into
-// their remainders (stage layout [A | B | A_lo | B_lo]) and the issuer runs A.B + A.B_lo + A_lo.B (see tcpos.cuh).
+// their remainders and the issuer runs A.B + A.B_lo + A_lo.B (see tcpos.cuh).  The remainder tiles live in their OWN
+// ring of p.lo_stages (2) buffers [A_lo | B_lo], separate from the p.stages TMA-written stages [A | B]: only the raw
+// stages hold bytes in flight, and with remainders inside every stage a 227 KB CTA had just two or three of them --
+// 64 KB in flight per SM, ~3 TB/s on the whole GPU whatever the MMA cost.  A remainder buffer is busy from the split
+// until its MMAs retire (commit -> loempty), a raw stage from the TMA until the same commit (-> empty).
 template <bool X3>
 __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ TrMaps maps, const TrParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -105,17 +112,22 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const int plane_bytes = p.a_bytes + p.b_bytes;
-  const int stage_bytes = (X3 ? 2 : 1) * plane_bytes;
+  const int stage_bytes = plane_bytes;                 // raw stage [A | B]; remainder buffer [A_lo | B_lo], same size
+  const int LQ = X3 ? p.lo_stages : 0;
   const uint32_t st0 = base;
-  const uint32_t bar0 = st0 + p.stages * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  const uint32_t lo0 = st0 + p.stages * stage_bytes;   // remainder ring
+  uint8_t* lo_ptr = smem + (size_t)p.stages * stage_bytes;
+  const uint32_t bar0 = lo0 + LQ * plane_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lo_ptr + (size_t)LQ * plane_bytes);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
-  auto split_bar = [&](int s) { return bar0 + 8u * (2 * p.stages + s); };
-  const uint32_t done_bar = bar0 + 8u * (3 * p.stages);
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * p.stages + 1 + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * p.stages + 3 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 5);
+  const int nb2 = 2 * p.stages;
+  auto split_bar = [&](int l) { return bar0 + 8u * (nb2 + l); };          // remainder buffer l filled
+  auto loempty_bar = [&](int l) { return bar0 + 8u * (nb2 + 2 + l); };    // ... and consumed (LQ <= 2)
+  const uint32_t done_bar = bar0 + 8u * (nb2 + 4);
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (nb2 + 5 + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (nb2 + 7 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + nb2 + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // output tile of this CTA: (k split, row/block group mg, column group ntile)
@@ -141,10 +153,11 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       float* blk = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + (size_t)na_loc * 4096);
       const int nfill = (p.mtiles * 4 - na_loc) * 1024;
       for (int i = threadIdx.x; i < nfill; i += 256) blk[i] = i < 1024 ? 1.0f : 0.0f;
-      if (X3) {   // their remainders are zero
-        float* lo = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + plane_bytes + (size_t)na_loc * 4096);
-        for (int i = threadIdx.x; i < nfill; i += 256) lo[i] = 0.0f;
-      }
+    }
+    for (int l = 0; l < LQ; ++l) {   // their remainders are zero
+      float* lo = reinterpret_cast<float*>(lo_ptr + (size_t)l * plane_bytes + (size_t)na_loc * 4096);
+      const int nfill = (p.mtiles * 4 - na_loc) * 1024;
+      for (int i = threadIdx.x; i < nfill; i += 256) lo[i] = 0.0f;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
   }
@@ -161,7 +174,10 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(split_bar(s), 64);
+    }
+    for (int l = 0; l < 2; ++l) {
+      mbar_init(split_bar(l), (p.drain > 0) ? 64 : 192);
+      mbar_init(loempty_bar(l), 1);
     }
     mbar_init(done_bar, 1);
     for (int a = 0; a < 2; ++a) {
@@ -196,8 +212,12 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       if (p.mode == 0) {
         const int b = c / cps, r0 = (c - b * cps) * 32;
         if (p.njobs > 1) {
-          for (int j = 0; j < na_loc; ++j)
-            tma_load_4d(sa + j * 4096, &maps.a[job], full_bar(stage), 0, r0 + p.jrshift[job][j], b, p.jseg[j]);
+          if (p.abox) {   // all segments in one instruction (8 TMA issues per 32-position chunk kept the producer busy)
+            tma_load_4d(sa, &maps.a[job], full_bar(stage), 0, r0, b, 0);
+          } else {
+            for (int j = 0; j < na_loc; ++j)
+              tma_load_4d(sa + j * 4096, &maps.a[job], full_bar(stage), 0, r0 + p.jrshift[job][j], b, p.jseg[j]);
+          }
           for (int j = 0; j < p.nbn; ++j) tma_load_3d(sb + j * 4096, &maps.b[job], full_bar(stage), 32 * j, r0, b);
         } else {
           for (int j = 0; j < na_loc; ++j) {
@@ -219,8 +239,8 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     // ===================================================== MMA issuer
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (p.mode == 0 ? ((1u << 15) | (1u << 16)) : 0u) |
                            ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = 0, lq = 0;
+    uint32_t phase = 0, lphase = 0;
     bool first = true;
     int acc = 0, in_acc = 0;                 // drain mode: current TMEM buffer, chunks accumulated in it
     uint32_t accphase[2] = {0u, 0u};
@@ -254,14 +274,15 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
         for (int kk = 0; kk < 4; ++kk) {
           uint64_t adesc, bdesc;
           descs(t, kk, adesc, bdesc);
-          tc_mma_tf32(d_tmem, adesc, bdesc, idesc, (!first || kk > 0) ? 1u : 0u);
+          if (p.diag != 2) tc_mma_tf32(d_tmem, adesc, bdesc, idesc, (!first || kk > 0) ? 1u : 0u);
         }
       }
       if (X3) {   // remainder terms after the split of this stage (it ran while the MMAs above were issued); the remainder
                   // planes sit plane_bytes further, same layout
-        if (!mbar_wait(split_bar(stage), phase, 24)) { ok = false; break; }
+        if (!mbar_wait(split_bar(lq), lphase, 24)) { ok = false; break; }
         tc_fence_after();
-        const uint64_t off = (uint64_t)((uint32_t)plane_bytes >> 4);
+        // remainder buffer lq relative to raw stage `stage` (descriptor start addresses are in 16-byte units)
+        const uint64_t off = (uint64_t)(((lo0 + (uint32_t)lq * plane_bytes) - sa) >> 4);
 #pragma unroll 1
         for (int t = 0; t < p.mtiles; ++t) {
           const uint32_t d_tmem = tm0 + (uint32_t)(t * p.N);
@@ -269,13 +290,17 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
           for (int kk = 0; kk < 4; ++kk) {
             uint64_t adesc, bdesc;
             descs(t, kk, adesc, bdesc);
-            tc_mma_tf32(d_tmem, adesc, bdesc + off, idesc, 1u);
-            tc_mma_tf32(d_tmem, adesc + off, bdesc, idesc, 1u);
+            if (p.diag != 2) tc_mma_tf32(d_tmem, adesc, bdesc + off, idesc, 1u);
+            if (p.diag != 2) tc_mma_tf32(d_tmem, adesc + off, bdesc, idesc, 1u);
           }
         }
       }
       first = false;
       tc_commit(empty_bar(stage));
+      if (X3) {
+        tc_commit(loempty_bar(lq));
+        if (++lq == LQ) { lq = 0; lphase ^= 1u; }
+      }
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       if (p.drain > 0 && (++in_acc == p.drain || c + 1 == c_end)) {   // hand this buffer to the epilogue warps
         tc_commit(tfull_bar(acc));
@@ -285,34 +310,45 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       }
     }
     if (p.drain == 0 && ok) tc_commit(done_bar);
-  } else if (X3 && (warp == 2 || warp == 3)) {
-    // ===================================================== splitter: remainders of the TMA-written A blocks and of B
+  }
+  // ===================================================== splitter: remainders of the TMA-written A blocks and of B.
+  // Warps 2-3, joined by the four epilogue warps when those would otherwise idle until the end (no drain): the
+  // support gradient splits 58 KB per chunk and was bound by two splitter warps (200 us -> 112 us with the split
+  // disabled, against 182 us with the MMAs disabled).
+  const int nsplit = (p.drain > 0) ? 64 : 192;
+  if (X3 && (warp == 2 || warp == 3 || (warp >= 4 && p.drain == 0))) {
     const int t64 = threadIdx.x - 64;
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = 0, lq = 0;
+    uint32_t phase = 0, lphase = 0;
     const int a_live = (p.mode == 0 ? na_loc * 4096 : p.a_bytes) / 16, b_live = p.b_bytes / 16;
     for (int c = c_beg; c < c_end; ++c) {
+      if (!mbar_wait(loempty_bar(lq), lphase ^ 1u, 28)) break;   // the MMAs that read this remainder buffer have retired
       if (!mbar_wait(full_bar(stage), phase, 25)) break;
       uint8_t* sp = smem + (size_t)stage * stage_bytes;
+      uint8_t* lp = lo_ptr + (size_t)lq * plane_bytes;
       const float4* a_src = reinterpret_cast<const float4*>(sp);
-      float4* a_dst = reinterpret_cast<float4*>(sp + plane_bytes);
+      float4* a_dst = reinterpret_cast<float4*>(lp);
+      if (p.diag != 1) {
 #pragma unroll 4
-      for (int i = t64; i < a_live; i += 64) {
+      for (int i = t64; i < a_live; i += nsplit) {
         const float4 v = a_src[i];
         a_dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
       }
       const float4* b_src = reinterpret_cast<const float4*>(sp + p.a_bytes);
-      float4* b_dst = reinterpret_cast<float4*>(sp + plane_bytes + p.a_bytes);
+      float4* b_dst = reinterpret_cast<float4*>(lp + p.a_bytes);
 #pragma unroll 4
-      for (int i = t64; i < b_live; i += 64) {
+      for (int i = t64; i < b_live; i += nsplit) {
         const float4 v = b_src[i];
         b_dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
       }
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(split_bar(stage));
+      mbar_arrive(split_bar(lq));
+      if (++lq == LQ) { lq = 0; lphase ^= 1u; }
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
-  } else if (warp >= 4) {
+  }
+  if (warp >= 4) {
     // ===================================================== epilogue: this CTA's partial result -> its private slot
     // (plain 128-bit stores; a small follow-up kernel sums the slots -- float atomics from 148 CTAs onto the same
     // few thousand addresses cost ~35-85 us per launch, ncu r01b)
@@ -655,8 +691,16 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
     for (int j = a.na; j < TR_MAXSRC; ++j) { p.pair_end[j] = (int)tot; maps.a[j] = maps.a[0]; maps.b[j] = maps.b[0]; }
     p.total_chunks = (int)tot;
   }
-  const int stage_bytes = (a.x3 ? 2 : 1) * (p.a_bytes + p.b_bytes);
-  p.stages = (SMEM_LIMIT - 2048) / stage_bytes;
+  {
+    static const int diag = [] {
+      const char* e = getenv("GWNET_B200_TCRED_DIAG");
+      return e ? atoi(e) : 0;
+    }();
+    p.diag = diag;
+  }
+  const int stage_bytes = p.a_bytes + p.b_bytes;          // raw stage; the 3xTF32 remainder ring has 2 buffers of the same size
+  p.lo_stages = a.x3 ? 2 : 0;
+  p.stages = (SMEM_LIMIT - 2048 - p.lo_stages * stage_bytes) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) return -1;
   // grid: a multiple of the output tile count, every CTA gets at least one chunk
@@ -670,7 +714,7 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
   if ((i64)grid * p.slot_floats > a.partial_floats) return -1;
   p.partial = a.partial;
   if (a.mode == 0 && p.mtiles * p.N <= 64) p.drain = 16;
-  const int smem_bytes = p.stages * stage_bytes + 1024 + 256;
+  const int smem_bytes = (p.stages + p.lo_stages) * stage_bytes + 1024 + 256;
   static cudaError_t attr = cudaFuncSetAttribute(tcred_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   static cudaError_t attr3 = cudaFuncSetAttribute(tcred_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   if (attr != cudaSuccess || attr3 != cudaSuccess) {
@@ -715,6 +759,14 @@ inline int launch_tcred_jobs(const TcRedJobsArgs& a, cudaStream_t stream, TcRedR
   p.tx_bytes = (a.na + p.nbn) * 4096;
   p.njobs = a.njobs;
   for (int j = 0; j < a.na; ++j) p.jseg[j] = a.seg[j];
+  p.abox = 1;
+  for (int j = 0; j < a.na; ++j)
+    if (a.seg[j] != j) p.abox = 0;
+  for (int q = 0; q < a.njobs; ++q) {
+    if (a.job[q].nseg_src < a.na) p.abox = 0;
+    for (int j = 0; j < a.na; ++j)
+      if (a.job[q].rshift[j] != 0) p.abox = 0;
+  }
   long long tot = 0;
   for (int q = 0; q < a.njobs; ++q) {
     const TcRedJob& g = a.job[q];
@@ -734,7 +786,7 @@ inline int launch_tcred_jobs(const TcRedJobsArgs& a, cudaStream_t stream, TcRedR
       const i64 segs = g.nseg_src > 1 ? g.a_seg_stride : (i64)g.a_rows_src * g.nb * 32;
       cuuint64_t d[4] = {32, (cuuint64_t)g.a_rows_src, (cuuint64_t)g.nb, (cuuint64_t)g.nseg_src};
       cuuint64_t st[3] = {128, (cuuint64_t)g.a_rows_src * 128, (cuuint64_t)segs * 4};
-      cuuint32_t box[4] = {32, 32, 1, 1};
+      cuuint32_t box[4] = {32, 32, 1, (cuuint32_t)(p.abox ? a.na : 1)};
       GWN_TRY(encode(&maps.a[q], g.a_src, 4, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     }
     {
@@ -786,14 +838,22 @@ inline int launch_tcred_jobs(const TcRedJobsArgs& a, cudaStream_t stream, TcRedR
   p.job_cta0[0] = 0;
   for (int q = 0; q < a.njobs; ++q) p.job_cta0[q + 1] = p.job_cta0[q] + nkq[q];
   const int grid = p.job_cta0[a.njobs];
-  const int stage_bytes = (a.x3 ? 2 : 1) * (p.a_bytes + p.b_bytes);
-  p.stages = (SMEM_LIMIT - 2048) / stage_bytes;
+  {
+    static const int diag = [] {
+      const char* e = getenv("GWNET_B200_TCRED_DIAG");
+      return e ? atoi(e) : 0;
+    }();
+    p.diag = diag;
+  }
+  const int stage_bytes = p.a_bytes + p.b_bytes;          // raw stage; the 3xTF32 remainder ring has 2 buffers of the same size
+  p.lo_stages = a.x3 ? 2 : 0;
+  p.stages = (SMEM_LIMIT - 2048 - p.lo_stages * stage_bytes) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) return -1;
   p.slot_floats = (i64)p.mtiles * 128 * p.N;
   if ((i64)grid * p.slot_floats > a.partial_floats) return -1;
   p.partial = a.partial;
-  const int smem_bytes = p.stages * stage_bytes + 1024 + 256;
+  const int smem_bytes = (p.stages + p.lo_stages) * stage_bytes + 1024 + 256;
   static cudaError_t attr = cudaFuncSetAttribute(tcred_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   static cudaError_t attr3 = cudaFuncSetAttribute(tcred_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   if (attr != cudaSuccess || attr3 != cudaSuccess) {
