@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
   auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * p.stages + 2 + a); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nsup; ++s) {
@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
   GWN_PDL_ENTRY();   // prologue above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail
   const int per_out = p.n_jt * p.n_wt;
 
-  if (warp == 0 && lane == 0) {
-    // ===================================================== TMA producer
+  if (warp == 0) {
+    // ===================================================== TMA producer (whole warp loops, one elected lane issues)
     int stage = 0;
     uint32_t phase = 0;
     bool ok = true;
@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
       const int s0 = p.kcat ? 0 : o, s1 = p.kcat ? p.nsup : o + 1;
       for (int s = s0; s < s1 && ok; ++s) {
         for (int kb = 0; kb < p.nkb; ++kb) {
-          if (!mbar_wait(empty_bar(stage), phase ^ 1u, 1)) { ok = false; break; }
+          if (!mbar_wait_warp(empty_bar(stage), phase ^ 1u, 1)) { ok = false; break; }
           const uint32_t dst = base + stage * stage_bytes;
+          if (elect_one()) {
           mbar_expect_tx(full_bar(stage), (uint32_t)(X_STAGE_BYTES + NPL * s_tile));
           if (!p.per_sample) {
             tma_load_3d(dst, &maps.x[s], full_bar(stage), 0, kb * BLOCK_K, jt * SLABS);
@@ -113,12 +114,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
             tma_load_3d(dst + XB, &maps.s[s], full_bar(stage), kb * BLOCK_K, wt * p.n_tile, sb);
             if (X3) tma_load_3d(dst + XB + s_tile, &maps.slo[s], full_bar(stage), kb * BLOCK_K, wt * p.n_tile, sb);
           }
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================================================== MMA issuer (one thread)
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (whole warp loops, one elected lane issues)
     // instruction descriptor: D=f32, A=B=tf32, A MN-major, B K-major, N = n_tile, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(p.n_tile >> 3) << 17) |
                            ((uint32_t)(BLOCK_M >> 4) << 24);
@@ -126,19 +129,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
     uint32_t phase = 0, accphase = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
-      if (!mbar_wait(tempty_bar(acc), accphase ^ 1u, 2)) break;
+      if (!mbar_wait_warp(tempty_bar(acc), accphase ^ 1u, 2)) break;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
       const int nk_total = (p.kcat ? p.nsup : 1) * p.nkb;
       for (int it = 0; it < nk_total; ++it) {
-        if (!mbar_wait(full_bar(stage), phase, 3)) { ok = false; break; }
+        if (!mbar_wait_warp(full_bar(stage), phase, 3)) { ok = false; break; }
         tc_fence_after();
-        if (p.dbg && blockIdx.x == 0 && tile == 0 && it == 0) {
+        if (p.dbg && blockIdx.x == 0 && tile == 0 && it == 0 && lane == 0) {
           const float* sm = reinterpret_cast<const float*>(smem + (size_t)stage * stage_bytes);
           for (int i = 0; i < stage_bytes / 4; ++i) p.dbg[i] = sm[i];
         }
         const uint32_t xs = base + stage * stage_bytes;
         const uint32_t bs = xs + XB;
+        if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
           // A (X^T, MN-major, 32-byte-atom swizzle): atoms of 4 k-rows x 128 B (SBO = 512 B between them);
@@ -154,19 +158,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
           if (p.mode != 1) tc_mma_tf32(d_tmem, adesc, bdesc, idesc_k, (it > 0 || kk > 0) ? 1u : 0u);
           if (X3) tc_mma_tf32(d_tmem, adesc, make_desc(bs + s_tile + kk * (UMMA_K * 4), 16, 1024), idesc_k, 1u);
         }
+        }
+        __syncwarp();
         if (X3) {   // the X_lo term last: the split of this stage ran while the eight MMAs above were issued
-          if (!mbar_wait(split_bar(stage), phase, 5)) { ok = false; break; }
+          if (!mbar_wait_warp(split_bar(stage), phase, 5)) { ok = false; break; }
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
             tc_mma_tf32(d_tmem, make_desc(xs + X_STAGE_BYTES + kk * (UMMA_K * 128), BLOCK_K * 128, 4 * 128, 1),
                         make_desc(bs + kk * (UMMA_K * 4), 16, 1024), idesc, 1u);
+          }
+          __syncwarp();
         }
-        tc_commit(empty_bar(stage));     // frees the smem stage once these MMAs have read it
+        if (elect_one()) tc_commit(empty_bar(stage));     // frees the smem stage once these MMAs have read it
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
       if (!ok) break;
-      tc_commit(tfull_bar(acc));         // accumulator complete -> epilogue
+      if (elect_one()) tc_commit(tfull_bar(acc));         // accumulator complete -> epilogue
+      __syncwarp();
       acc ^= 1;
       if (acc == 0) accphase ^= 1u;
     }

@@ -51,6 +51,26 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int cod
   }
   return true;
 }
+// Warp-uniform role code.  tcgen05.mma / TMA / tcgen05.commit take their operands from UNIFORM registers; issued from
+// a branch the compiler cannot prove warp-uniform (`if (warp == 1 && lane == 0)` with warp = threadIdx.x >> 5) every
+// one of them was wrapped in an ELECT / R2UR / BRA.U.ANY waterfall -- ~30 SASS instructions per MMA, and the single
+// issuing thread, not the tensor pipe, set the pace (one extra compare per MMA cost the weight-gradient kernel 24 %).
+// The role warps therefore run their loops with all 32 lanes (warp id broadcast with a shuffle, barrier-wait results
+// voted) and only the instruction itself sits under elect.sync.
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity, int code) {   // all 32 lanes, uniform result
+  const bool ok = mbar_wait(bar, parity, code);
+  return __all_sync(0xffffffffu, ok) != 0;
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
@@ -131,9 +151,14 @@ static int encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* d
     return GWN_ERR_CUDA;
   }
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  static const CUtensorMapL2promotion promo = [] {   // GWNET_B200_L2PROMO = 0 | 64 | 128 (default) | 256
+    const char* e = getenv("GWNET_B200_L2PROMO");
+    const int v = e ? atoi(e) : 128;
+    return v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                    : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
+  }();
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
     return GWN_ERR_CUDA;

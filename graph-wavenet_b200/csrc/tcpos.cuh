@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 9);
   float* red = reinterpret_cast<float*>(bars + 3 * p.stages + 10);   // 2 x 64 floats for the statistics reduces
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[s]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
@@ -144,13 +144,16 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
   const uint32_t tmem_base = *tmem_slot;
   GWN_PDL_ENTRY();   // prologue above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail
 
-  if (warp == 0 && lane == 0) {
-    // ===================================================== TMA producer
+  if (warp == 0) {
+    // ===================================================== TMA producer (whole warp loops, one elected lane issues)
     if (!p.wstream) {
-      mbar_expect_tx(w_bar, (uint32_t)w_bytes);
-      for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + s * w_blk, &maps.w, w_bar, s * 32, 0);
-      if (X3)
-        for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + w_plane + s * w_blk, &maps.wlo, w_bar, s * 32, 0);
+      if (elect_one()) {
+        mbar_expect_tx(w_bar, (uint32_t)w_bytes);
+        for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + s * w_blk, &maps.w, w_bar, s * 32, 0);
+        if (X3)
+          for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + w_plane + s * w_blk, &maps.wlo, w_bar, s * 32, 0);
+      }
+      __syncwarp();
     }
     int stage = 0, eb = 0;
     uint32_t phase = 0, ephase = 0;
@@ -159,62 +162,77 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
       const int nt = tile % p.n_nt, rtile = tile / p.n_nt;
       const int b = rtile / p.tiles_per_sample, rt = rtile - b * p.tiles_per_sample;
       if (NADD > 0 && p.nadd > 0) {   // the epilogue's addend tiles of this row tile
-        if (!mbar_wait(eempty_bar(eb), ephase ^ 1u, 18)) { ok = false; break; }
-        mbar_expect_tx(efull_bar(eb), (uint32_t)p.nadd * TP_A_BYTES);
-        for (int k = 0; k < NADD; ++k)
-          if (p.add_on[k])
-            tma_load_3d(ad0 + (eb * NADD + k) * TP_A_BYTES, &maps.add[k], efull_bar(eb), 0, rt * 128 + p.add_rshift[k], b);
+        if (!mbar_wait_warp(eempty_bar(eb), ephase ^ 1u, 18)) { ok = false; break; }
+        if (elect_one()) {
+          mbar_expect_tx(efull_bar(eb), (uint32_t)p.nadd * TP_A_BYTES);
+          for (int k = 0; k < NADD; ++k)
+            if (p.add_on[k])
+              tma_load_3d(ad0 + (eb * NADD + k) * TP_A_BYTES, &maps.add[k], efull_bar(eb), 0, rt * 128 + p.add_rshift[k], b);
+        }
+        __syncwarp();
         eb ^= 1;
         if (eb == 0) ephase ^= 1u;
       }
       for (int s = 0; s < p.nseg; ++s) {
-        if (!mbar_wait(empty_bar(stage), phase ^ 1u, 11)) { ok = false; break; }
-        mbar_expect_tx(full_bar(stage), TP_A_BYTES + (p.wstream ? NPL * w_blk : 0));
-        tma_load_3d(a0 + stage * STG, &maps.a[s], full_bar(stage), p.col0[s], rt * 128 + p.rshift[s], b);
-        if (p.wstream) {
-          const uint32_t wdst = a0 + stage * STG + NPL * TP_A_BYTES;
-          tma_load_2d(wdst, &maps.w, full_bar(stage), s * 32, nt * p.N);
-          if (X3) tma_load_2d(wdst + w_blk, &maps.wlo, full_bar(stage), s * 32, nt * p.N);
+        if (!mbar_wait_warp(empty_bar(stage), phase ^ 1u, 11)) { ok = false; break; }
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(stage), TP_A_BYTES + (p.wstream ? NPL * w_blk : 0));
+          tma_load_3d(a0 + stage * STG, &maps.a[s], full_bar(stage), p.col0[s], rt * 128 + p.rshift[s], b);
+          if (p.wstream) {
+            const uint32_t wdst = a0 + stage * STG + NPL * TP_A_BYTES;
+            tma_load_2d(wdst, &maps.w, full_bar(stage), s * 32, nt * p.N);
+            if (X3) tma_load_2d(wdst + w_blk, &maps.wlo, full_bar(stage), s * 32, nt * p.N);
+          }
         }
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================================================== MMA issuer: D[128 x N] += A[128 x 32] . Wseg[N x 32]^T
+    // (whole warp loops, one elected lane issues)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int stage = 0, acc = 0;
     uint32_t phase = 0, accphase = 0;
-    bool ok = p.wstream ? true : mbar_wait(w_bar, 0, 12);
+    bool ok = p.wstream ? true : mbar_wait_warp(w_bar, 0, 12);
     tc_fence_after();
     for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
-      if (!mbar_wait(tempty_bar(acc), accphase ^ 1u, 13)) break;
+      if (!mbar_wait_warp(tempty_bar(acc), accphase ^ 1u, 13)) break;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
       for (int s = 0; s < p.nseg; ++s) {
-        if (!mbar_wait(full_bar(stage), phase, 14)) { ok = false; break; }
+        if (!mbar_wait_warp(full_bar(stage), phase, 14)) { ok = false; break; }
         tc_fence_after();
         const uint32_t as = a0 + stage * STG;
         const uint32_t ws = p.wstream ? as + NPL * TP_A_BYTES : base + s * w_blk;
         const uint32_t wlo_off = p.wstream ? (uint32_t)w_blk : (uint32_t)w_plane;
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          // both operands K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart, this k-step 32 B in
-          const uint64_t ad = make_desc(as + kk * 32, 16, 1024), wd = make_desc(ws + kk * 32, 16, 1024);
-          tc_mma_tf32(d_tmem, ad, wd, idesc, (s > 0 || kk > 0) ? 1u : 0u);
-          if (X3) tc_mma_tf32(d_tmem, ad, make_desc(ws + wlo_off + kk * 32, 16, 1024), idesc, 1u);
+          for (int kk = 0; kk < 4; ++kk) {
+            // both operands K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart, this k-step 32 B in
+            const uint64_t ad = make_desc(as + kk * 32, 16, 1024), wd = make_desc(ws + kk * 32, 16, 1024);
+            tc_mma_tf32(d_tmem, ad, wd, idesc, (s > 0 || kk > 0) ? 1u : 0u);
+            if (X3) tc_mma_tf32(d_tmem, ad, make_desc(ws + wlo_off + kk * 32, 16, 1024), idesc, 1u);
+          }
         }
+        __syncwarp();
         if (X3) {   // the A_lo term last: the split of this stage overlaps the MMAs above
-          if (!mbar_wait(split_bar(stage), phase, 16)) { ok = false; break; }
+          if (!mbar_wait_warp(split_bar(stage), phase, 16)) { ok = false; break; }
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            tc_mma_tf32(d_tmem, make_desc(as + TP_A_BYTES + kk * 32, 16, 1024), make_desc(ws + kk * 32, 16, 1024), idesc, 1u);
+            for (int kk = 0; kk < 4; ++kk)
+              tc_mma_tf32(d_tmem, make_desc(as + TP_A_BYTES + kk * 32, 16, 1024), make_desc(ws + kk * 32, 16, 1024), idesc, 1u);
+          }
+          __syncwarp();
         }
-        tc_commit(empty_bar(stage));
+        if (elect_one()) tc_commit(empty_bar(stage));
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
       if (!ok) break;
-      tc_commit(tfull_bar(acc));
+      if (elect_one()) tc_commit(tfull_bar(acc));
+      __syncwarp();
       acc ^= 1;
       if (acc == 0) accphase ^= 1u;
     }

@@ -95,7 +95,7 @@ struct TrParams {
   // ~150 chunks cost 1.4e-4 of relative error on the first layer's filter gradient.
   int drain;
   int lo_stages;   // 3xTF32: buffers of the remainder ring (0 otherwise)
-  int diag;        // timing diagnostics (wrong results): 1 = splitter skips its work, 2 = issuer skips the MMAs
+  int interleave;  // K chunks dealt round-robin to the CTAs of an output tile instead of in contiguous ranges
   int abox;        // multi-job: the job's A blocks are the consecutive segments 0..na-1, unshifted: ONE 4-D TMA box
 };
 
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
   auto tempty_bar = [&](int a) { return bar0 + 8u * (nb2 + 7 + a); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + nb2 + 9);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   // output tile of this CTA: (k split, row/block group mg, column group ntile)
   const int n_ot = p.n_nt * p.n_mg;
   int ntile, mg, kslot, nk, job = 0, total_chunks = p.total_chunks, cps = p.chunks_per_sample;
@@ -197,17 +197,27 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
   GWN_PDL_ENTRY();   // prologue above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail
 
   // contiguous chunk range of this CTA (MODE_K: CTAs are split over n_nt column tiles of the output)
-  const int c_beg = (int)((long long)total_chunks * kslot / nk);
-  const int c_end = (int)((long long)total_chunks * (kslot + 1) / nk);
+  // This CTA's K chunks: kslot, kslot + nk, kslot + 2 nk, ... -- interleaved with the other CTAs of the same output
+  // tile, so that at any moment they read ADJACENT 4 KB pieces of every operand stream (contiguous ranges per CTA
+  // made ~1000 far-apart DRAM streams: 2.9 TB/s with neither the MMAs nor the split nor the TMA issue rate binding).
+  // c_lin = index in this CTA's sequence, c = c_beg + c_lin * c_step the global chunk.
+  const int c_step = p.interleave ? nk : 1;
+  const int c_beg = p.interleave ? kslot : (int)((long long)total_chunks * kslot / nk);
+  const int n_my = p.interleave ? (kslot < total_chunks ? (total_chunks - kslot + nk - 1) / nk : 0)
+                                : (int)((long long)total_chunks * (kslot + 1) / nk) - c_beg;
+  const int c_end = c_beg + n_my * c_step;   // exclusive bound of the strided sequence
 
-  if (warp == 0 && lane == 0) {
-    // ===================================================== TMA producer
+  if (warp == 0) {
+    // ===================================================== TMA producer (whole warp loops, one elected lane issues)
     int stage = 0;
     uint32_t phase = 0;
     int pair = 0;
-    for (int c = c_beg; c < c_end; ++c) {
-      if (!mbar_wait(empty_bar(stage), phase ^ 1u, 21)) break;
+    for (int c = c_beg; c < c_end; c += c_step) {
+      if (!mbar_wait_warp(empty_bar(stage), phase ^ 1u, 21)) break;
       const uint32_t sa = st0 + stage * stage_bytes, sb = sa + p.a_bytes;
+      if (p.mode != 0)
+        while (c >= p.pair_end[pair]) ++pair;
+      if (elect_one()) {
       mbar_expect_tx(full_bar(stage), p.mode == 0 ? (uint32_t)((na_loc + p.nbn) * 4096) : (uint32_t)p.tx_bytes);
       if (p.mode == 0) {
         const int b = c / cps, r0 = (c - b * cps) * 32;
@@ -227,16 +237,17 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
           for (int j = 0; j < p.nbn; ++j) tma_load_3d(sb + j * 4096, &maps.b[0], full_bar(stage), p.bcol0[0] + ntile * p.N + 32 * j, r0, b);
         }
       } else {
-        while (c >= p.pair_end[pair]) ++pair;
         const int slab = c - (pair ? p.pair_end[pair - 1] : 0);
         for (int t = 0; t < p.mtiles; ++t)
           tma_load_3d(sa + t * 16384, &maps.a[pair], full_bar(stage), 0, (mg * p.mtiles + t) * 128, slab);
         tma_load_3d(sb, &maps.b[pair], full_bar(stage), 0, ntile * p.N, slab);
       }
+      }
+      __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================================================== MMA issuer
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (whole warp loops, one elected lane issues)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (p.mode == 0 ? ((1u << 15) | (1u << 16)) : 0u) |
                            ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int stage = 0, lq = 0;
@@ -247,14 +258,14 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     const uint32_t acc_cols = (uint32_t)(p.mtiles * p.N);
     uint32_t tm0 = tmem_base;
     bool ok = true;
-    for (int c = c_beg; c < c_end; ++c) {
+    for (int c = c_beg; c < c_end; c += c_step) {
       if (p.drain > 0 && in_acc == 0) {      // a fresh buffer: wait until the epilogue has drained its previous use
-        if (!mbar_wait(tempty_bar(acc), accphase[acc] ^ 1u, 26)) { ok = false; break; }
+        if (!mbar_wait_warp(tempty_bar(acc), accphase[acc] ^ 1u, 26)) { ok = false; break; }
         tc_fence_after();
         tm0 = tmem_base + (uint32_t)acc * acc_cols;
         first = true;
       }
-      if (!mbar_wait(full_bar(stage), phase, 22)) { ok = false; break; }
+      if (!mbar_wait_warp(full_bar(stage), phase, 22)) { ok = false; break; }
       tc_fence_after();
       const uint32_t sa = st0 + stage * stage_bytes, sb = sa + p.a_bytes;
       auto descs = [&](int t, int kk, uint64_t& adesc, uint64_t& bdesc) {
@@ -267,6 +278,7 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
           bdesc = make_desc(sb + kk * 32, 16, 1024, 2);
         }
       };
+      if (elect_one()) {
 #pragma unroll 1
       for (int t = 0; t < p.mtiles; ++t) {
         const uint32_t d_tmem = tm0 + (uint32_t)(t * p.N);
@@ -274,15 +286,18 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
         for (int kk = 0; kk < 4; ++kk) {
           uint64_t adesc, bdesc;
           descs(t, kk, adesc, bdesc);
-          if (p.diag != 2) tc_mma_tf32(d_tmem, adesc, bdesc, idesc, (!first || kk > 0) ? 1u : 0u);
+          tc_mma_tf32(d_tmem, adesc, bdesc, idesc, (!first || kk > 0) ? 1u : 0u);
         }
       }
+      }
+      __syncwarp();
       if (X3) {   // remainder terms after the split of this stage (it ran while the MMAs above were issued); the remainder
                   // planes sit plane_bytes further, same layout
-        if (!mbar_wait(split_bar(lq), lphase, 24)) { ok = false; break; }
+        if (!mbar_wait_warp(split_bar(lq), lphase, 24)) { ok = false; break; }
         tc_fence_after();
         // remainder buffer lq relative to raw stage `stage` (descriptor start addresses are in 16-byte units)
         const uint64_t off = (uint64_t)(((lo0 + (uint32_t)lq * plane_bytes) - sa) >> 4);
+        if (elect_one()) {
 #pragma unroll 1
         for (int t = 0; t < p.mtiles; ++t) {
           const uint32_t d_tmem = tm0 + (uint32_t)(t * p.N);
@@ -290,26 +305,39 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
           for (int kk = 0; kk < 4; ++kk) {
             uint64_t adesc, bdesc;
             descs(t, kk, adesc, bdesc);
-            if (p.diag != 2) tc_mma_tf32(d_tmem, adesc, bdesc + off, idesc, 1u);
-            if (p.diag != 2) tc_mma_tf32(d_tmem, adesc + off, bdesc, idesc, 1u);
+            tc_mma_tf32(d_tmem, adesc, bdesc + off, idesc, 1u);
+            tc_mma_tf32(d_tmem, adesc + off, bdesc, idesc, 1u);
           }
         }
+        }
+        __syncwarp();
       }
       first = false;
-      tc_commit(empty_bar(stage));
+      const bool hand_over = p.drain > 0 && (in_acc + 1 == p.drain || c + c_step >= c_end);
+      if (elect_one()) {
+        tc_commit(empty_bar(stage));
+        if (X3) tc_commit(loempty_bar(lq));
+        if (hand_over) tc_commit(tfull_bar(acc));   // hand this accumulator buffer to the epilogue warps
+      }
+      __syncwarp();
       if (X3) {
-        tc_commit(loempty_bar(lq));
         if (++lq == LQ) { lq = 0; lphase ^= 1u; }
       }
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-      if (p.drain > 0 && (++in_acc == p.drain || c + 1 == c_end)) {   // hand this buffer to the epilogue warps
-        tc_commit(tfull_bar(acc));
-        accphase[acc] ^= 1u;
-        acc ^= 1;
-        in_acc = 0;
+      if (p.drain > 0) {
+        if (hand_over) {
+          accphase[acc] ^= 1u;
+          acc ^= 1;
+          in_acc = 0;
+        } else {
+          ++in_acc;
+        }
       }
     }
-    if (p.drain == 0 && ok) tc_commit(done_bar);
+    if (p.drain == 0 && ok) {
+      if (elect_one()) tc_commit(done_bar);
+      __syncwarp();
+    }
   }
   // ===================================================== splitter: remainders of the TMA-written A blocks and of B.
   // Warps 2-3, joined by the four epilogue warps when those would otherwise idle until the end (no drain): the
@@ -321,14 +349,13 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     int stage = 0, lq = 0;
     uint32_t phase = 0, lphase = 0;
     const int a_live = (p.mode == 0 ? na_loc * 4096 : p.a_bytes) / 16, b_live = p.b_bytes / 16;
-    for (int c = c_beg; c < c_end; ++c) {
+    for (int c = c_beg; c < c_end; c += c_step) {
       if (!mbar_wait(loempty_bar(lq), lphase ^ 1u, 28)) break;   // the MMAs that read this remainder buffer have retired
       if (!mbar_wait(full_bar(stage), phase, 25)) break;
       uint8_t* sp = smem + (size_t)stage * stage_bytes;
       uint8_t* lp = lo_ptr + (size_t)lq * plane_bytes;
       const float4* a_src = reinterpret_cast<const float4*>(sp);
       float4* a_dst = reinterpret_cast<float4*>(lp);
-      if (p.diag != 1) {
 #pragma unroll 4
       for (int i = t64; i < a_live; i += nsplit) {
         const float4 v = a_src[i];
@@ -340,7 +367,6 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       for (int i = t64; i < b_live; i += nsplit) {
         const float4 v = b_src[i];
         b_dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
-      }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(split_bar(lq));
@@ -361,7 +387,7 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       float sum[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) sum[i] = 0.0f;
-      const int ndrain = (c_end - c_beg + p.drain - 1) / p.drain;
+      const int ndrain = (n_my + p.drain - 1) / p.drain;
       bool ok = true;
       for (int d = 0; d < ndrain && ok; ++d) {
         const int buf = d & 1;
@@ -692,11 +718,11 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
     p.total_chunks = (int)tot;
   }
   {
-    static const int diag = [] {
-      const char* e = getenv("GWNET_B200_TCRED_DIAG");
-      return e ? atoi(e) : 0;
+    static const int inter = [] {
+      const char* e = getenv("GWNET_B200_TCRED_INTERLEAVE");
+      return e ? atoi(e) : 1;
     }();
-    p.diag = diag;
+    p.interleave = inter;
   }
   const int stage_bytes = p.a_bytes + p.b_bytes;          // raw stage; the 3xTF32 remainder ring has 2 buffers of the same size
   p.lo_stages = a.x3 ? 2 : 0;
@@ -839,11 +865,11 @@ inline int launch_tcred_jobs(const TcRedJobsArgs& a, cudaStream_t stream, TcRedR
   for (int q = 0; q < a.njobs; ++q) p.job_cta0[q + 1] = p.job_cta0[q] + nkq[q];
   const int grid = p.job_cta0[a.njobs];
   {
-    static const int diag = [] {
-      const char* e = getenv("GWNET_B200_TCRED_DIAG");
-      return e ? atoi(e) : 0;
+    static const int inter = [] {
+      const char* e = getenv("GWNET_B200_TCRED_INTERLEAVE");
+      return e ? atoi(e) : 1;
     }();
-    p.diag = diag;
+    p.interleave = inter;
   }
   const int stage_bytes = p.a_bytes + p.b_bytes;          // raw stage; the 3xTF32 remainder ring has 2 buffers of the same size
   p.lo_stages = a.x3 ? 2 : 0;
