@@ -193,10 +193,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
         if (!mbar_wait(full_bar(stage), phase, 6)) { ok = false; break; }
         const float4* src = reinterpret_cast<const float4*>(smem + (size_t)stage * stage_bytes);
         float4* dst = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + X_STAGE_BYTES);
-#pragma unroll 4
-        for (int i = t64; i < X_STAGE_BYTES / 16; i += 64) {
-          const float4 v = src[i];
-          dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+        {   // 16 float4 per thread: all loads in flight before the first use (with 4 at a time the two splitter
+            // warps were busy ~100 % of the time, stalled on LDS results: ncu source page of the reduction kernel)
+          static_assert(X_STAGE_BYTES / 16 == 64 * 16, "splitter: 16 float4 per thread");
+          float4 v[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) v[u] = src[t64 + 64 * u];
+#pragma unroll
+          for (int u = 0; u < 16; ++u)
+            dst[t64 + 64 * u] = make_float4(tf32_lo(v[u].x), tf32_lo(v[u].y), tf32_lo(v[u].z), tf32_lo(v[u].w));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(split_bar(stage));

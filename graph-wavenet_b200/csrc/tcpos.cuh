@@ -247,10 +247,15 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
         if (!mbar_wait(full_bar(stage), phase, 17)) { ok = false; break; }
         const float4* src = reinterpret_cast<const float4*>(smem + w_bytes + (size_t)stage * STG);
         float4* dst = reinterpret_cast<float4*>(smem + w_bytes + (size_t)stage * STG + TP_A_BYTES);
-#pragma unroll 4
-        for (int i = t64; i < TP_A_BYTES / 16; i += 64) {
-          const float4 v = src[i];
-          dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+        {   // 16 float4 per thread: all loads in flight before the first use (with 4 at a time the two splitter
+            // warps were busy ~100 % of the time, stalled on LDS results: ncu source page of the reduction kernel)
+          static_assert(TP_A_BYTES / 16 == 64 * 16, "splitter: 16 float4 per thread");
+          float4 v[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) v[u] = src[t64 + 64 * u];
+#pragma unroll
+          for (int u = 0; u < 16; ++u)
+            dst[t64 + 64 * u] = make_float4(tf32_lo(v[u].x), tf32_lo(v[u].y), tf32_lo(v[u].z), tf32_lo(v[u].w));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         mbar_arrive(split_bar(stage));

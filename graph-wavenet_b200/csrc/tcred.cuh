@@ -356,14 +356,14 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       uint8_t* lp = lo_ptr + (size_t)lq * plane_bytes;
       const float4* a_src = reinterpret_cast<const float4*>(sp);
       float4* a_dst = reinterpret_cast<float4*>(lp);
-#pragma unroll 4
+#pragma unroll 8
       for (int i = t64; i < a_live; i += nsplit) {
         const float4 v = a_src[i];
         a_dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
       }
       const float4* b_src = reinterpret_cast<const float4*>(sp + p.a_bytes);
       float4* b_dst = reinterpret_cast<float4*>(lp + p.a_bytes);
-#pragma unroll 4
+#pragma unroll 8
       for (int i = t64; i < b_live; i += nsplit) {
         const float4 v = b_src[i];
         b_dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
