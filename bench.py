@@ -148,6 +148,9 @@ def cpu_baseline_leg(steps=3):
             "sample": f"{steps} full trainer.train steps at batch 64 after 1 warm-up (oracle port, torch CPU ops, {cores} threads)"}
 
 
+PRECISION_FOR_NOTE = ["fp32x3"]   # set by run_native: the tier the roofline leg is profiling
+
+
 def roofline_leg(lib, step_fn, dev, steps=5):
     """Per-operator device timing of the same train step (CUDA events on the launching stream, recorded by
     the library around every operator of the plan: gwn_profile_begin/end) -> achieved GB/s and TFLOP/s per
@@ -201,11 +204,16 @@ def roofline_leg(lib, step_fn, dev, steps=5):
         roof = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak}
     else:
         roof = {"bound": "tensor", "achieved": tfs, "peak": tens_peak, "unit": "TFLOP/s", "frac": tfs / tens_peak}
-    # DRAM bytes of one captured launch of this kernel (ncu --set full, profiles/r01e_ncu_key_metrics.json): the layer-0
-    # first-hop node contraction moved 62.1 MB in + 15.7 MB out against 81.2 MB algorithmic (the tail of the writes was
+    # DRAM bytes of one captured launch of this kernel (ncu --set full, profiles/r01g_ncu_key_metrics.json): the layer-0
+    # second-hop node contraction moved 62.1 MB in + 14.5 MB out against 81.2 MB algorithmic (the tail of the writes was
     # still in L2 when the kernel ended) -- no re-read waste
-    traffic = 77.8e6 if fam == "nconv_tc_kernel" else None
-    roof.update({"traffic": traffic, "traffic_note": "one launch (layer 0, first hop: 81.2e6 algorithmic bytes), ncu r01e" if traffic else None,
+    traffic = 76.6e6 if fam == "nconv_tc_kernel" else None
+    # the fp32x3 tier issues 3 tf32 MMAs per algorithmic one: the tensor pipe, not HBM, is what this kernel runs
+    # against at N ~ 200 (ncu: tensor pipe active 44 %, DRAM 8-22 %); stated beside the contract's algorithmic figures
+    tf32_peak = tens_peak / 2.0
+    issued = 3.0 if "3xTF32" in TIER_TEXT.get(PRECISION_FOR_NOTE[0], "") else 1.0
+    roof.update({"traffic": traffic, "traffic_note": "one launch (layer 0, second hop: 81.2e6 algorithmic bytes), ncu r01g" if traffic else None,
+                 "issued_tf32_TFLOPs": tfs * issued, "issued_tf32_frac_of_half_bf16_peak": tfs * issued / tf32_peak,
                  "kernel": fam, "share_of_step": a["ms"] / total, "tensor_TFLOPs": tfs, "flop_per_byte": ai,
                  "algorithmic_bytes_per_step": a["bytes"] / steps, "ms_per_step": a["ms"] / steps,
                  "operators": [k for k, v in fam_of.items() if v == fam],
@@ -238,6 +246,7 @@ def run_native(args):
     torch.manual_seed(999)
     tr = E.trainer(StandardScaler(54.0, 20.0), IN_DIM, SEQ, NODES, 32, DROPOUT, 1e-3, 1e-4, dev, sup, True, True, None)
     tr.model.precision = {"fp32": NV.PREC_FP32, "tf32": NV.PREC_TF32, "fp32x3": NV.PREC_FP32X3}[args.precision]
+    PRECISION_FOR_NOTE[0] = args.precision
     if world > 1:
         tr.enable_data_parallel()
     gen = torch.Generator().manual_seed(100 + rank)
@@ -328,7 +337,7 @@ def run_native(args):
                 "config": {"workload": WORKLOAD, "global_batch": BATCH * world,
                            "parallelism": f"dp{world}" if world > 1 else "single",
                            "precision_tier": TIER_TEXT[args.precision],
-                           "step": ("one CUDA graph per step: forward + masked-MAE loss + backward + clip + Adam + metrics" if graph_mode
+                           "step": (("one CUDA graph per step: forward + masked-MAE loss + backward + clip + Adam + metrics" if world == 1 else "two CUDA graphs per step around the NCCL gradient all-reduce") if graph_mode
                                     else "eager launches of the same fused step"),
                            "l2_policy": "per-step working set (~0.9 GB of saved activations) exceeds the 126 MB L2; 4 rotating input batches"},
                 "e2e": {"value": BATCH * world / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
