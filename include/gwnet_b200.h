@@ -13,9 +13,19 @@
  *     gwn_last_error() returns a thread-local message.  Nothing throws or exits.
  *   - the caller owns every buffer (parameters, activations, workspace); the
  *     library allocates no device memory.
- *   - all work is enqueued on the cudaStream_t passed as `stream` (void*), on the
+ *   - all work is ordered on the cudaStream_t passed as `stream` (void*), on the
  *     caller's current device; no implicit synchronisation; re-entrant (forward
  *     is called from the main thread, backward from PyTorch's autograd thread).
+ *     A plan additionally owns ONE internal non-blocking stream (+ four events,
+ *     created at the first gwn_plan_forward, released by gwn_plan_destroy): the
+ *     forward pass forks it from `stream` with an event, runs its parameter- and
+ *     support-only operand preparation there, and joins it back with events
+ *     before the first consumer and before it returns.  To the caller the call
+ *     behaves as if everything ran on `stream` (also under stream capture, where
+ *     the preparation becomes parallel graph branches); GWNET_B200_SIDE_STREAM=0
+ *     keeps every launch on `stream`.  Kernels are launched with programmatic
+ *     stream serialization and wait (griddepcontrol.wait) for the previous kernel
+ *     of the stream before touching memory; GWNET_B200_PDL=0 turns that off.
  *   - activation tensors are fp32 in the "BLNC" physical layout
  *         x[b][l][n][c]   (batch, time, node, channel; channel innermost)
  *     which is the reference's logical NCHW tensor [B,C,N,L] viewed with strides

@@ -209,6 +209,13 @@ def test_pems_bay_aptonly_full_size(M, tier):
     _fullsize(M, O.GwnetConfig(num_nodes=325, dropout=0.0, n_static_supports=0, has_supports=False), 16, 0.05, tier)
 
 
+@pytest.mark.parametrize("blocks,layers", [(3, 3), (5, 2)])
+def test_deep_stacks_deferred_weight_gradients(M, blocks, layers):
+    """More than 8 layers: the deferred weight-gradient reductions run as several multi-job launches (groups of 8) and,
+    for 9 layers, a lone single-job launch; dilations up to 4 (layers=3) and a receptive field longer than the input."""
+    _fullsize(M, O.GwnetConfig(num_nodes=80, dropout=0.0, n_static_supports=2, blocks=blocks, layers=layers), 8, 0.1, "fp32x3")
+
+
 def test_crash_shape_long_sequence(M):
     """BASELINE config 3 secondary: N=200, seq 48 -> T_out = 37, out_dim 48 (skip slicing with T_out > 1)."""
     dev = torch.device("cuda:0")
