@@ -967,7 +967,7 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     t.mode = 0; t.na = na; t.x3 = tsc.x3;
     for (int j = 0; j < na; ++j) t.a[j] = ablk[j];
     t.b[0] = bsrc;
-    t.ab = tsc.x3 ? 4 : 7;
+    t.ab = tsc.x3 ? 3 : 7;   // 3 real blocks + the all-ones block = ONE 128-row tile (4 + ones made two, 3/8 of the MMA rows zero)
     t.N = Ntot <= (tsc.x3 ? 128 : 256) ? Ntot : (tsc.x3 ? 128 : 256);
     t.N_total = Ntot; t.nb = nb_; t.rows = rows_; t.partial = tsc.partial; t.partial_floats = tsc.floats;
     TcRedResult r;
