@@ -85,6 +85,11 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   constexpr int NPL = X3 ? 2 : 1;                         // operand planes (hi, lo)
+  // N-concatenated remainder product (3xTF32, resident weights, compile-time N <= 64): W_lo's k-block sits right behind
+  // W's, so A.[W | W_lo] is ONE instruction of twice the width into accumulator columns [0,N) and [N,2N) that the
+  // epilogue adds; with the measured 66 + 0.75 N cycles per tcgen05.mma two N = 32 instructions (180 cycles) become
+  // one N = 64 instruction (114).  Per k-step: 2 instructions instead of 3.
+  constexpr bool NCAT = X3 && NCT > 0 && NCT <= 64 && !EP::kDirectStore;
   const int w_blk = p.N * 128;                            // one k-block of weights: [N rows][128 B]
   const int STG = NPL * TP_A_BYTES + (p.wstream ? NPL * w_blk : 0);   // bytes per stage: [A | A_lo | (W blk | W_lo blk)]
   const int w_plane = p.nseg * w_blk;                     // resident weights: [plane][seg][N rows][128 B]
@@ -149,9 +154,16 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
     if (!p.wstream) {
       if (elect_one()) {
         mbar_expect_tx(w_bar, (uint32_t)w_bytes);
-        for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + s * w_blk, &maps.w, w_bar, s * 32, 0);
-        if (X3)
-          for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + w_plane + s * w_blk, &maps.wlo, w_bar, s * 32, 0);
+        if (NCAT) {   // [seg][W blk | W_lo blk]
+          for (int s = 0; s < p.nseg; ++s) {
+            tma_load_2d(base + s * 2 * w_blk, &maps.w, w_bar, s * 32, 0);
+            tma_load_2d(base + s * 2 * w_blk + w_blk, &maps.wlo, w_bar, s * 32, 0);
+          }
+        } else {
+          for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + s * w_blk, &maps.w, w_bar, s * 32, 0);
+          if (X3)
+            for (int s = 0; s < p.nseg; ++s) tma_load_2d(base + w_plane + s * w_blk, &maps.wlo, w_bar, s * 32, 0);
+        }
       }
       __syncwarp();
     }
@@ -204,15 +216,20 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
         if (!mbar_wait_warp(full_bar(stage), phase, 14)) { ok = false; break; }
         tc_fence_after();
         const uint32_t as = a0 + stage * STG;
-        const uint32_t ws = p.wstream ? as + NPL * TP_A_BYTES : base + s * w_blk;
+        const uint32_t ws = p.wstream ? as + NPL * TP_A_BYTES : (NCAT ? base + s * 2 * w_blk : base + s * w_blk);
         const uint32_t wlo_off = p.wstream ? (uint32_t)w_blk : (uint32_t)w_plane;
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             // both operands K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart, this k-step 32 B in
             const uint64_t ad = make_desc(as + kk * 32, 16, 1024), wd = make_desc(ws + kk * 32, 16, 1024);
-            tc_mma_tf32(d_tmem, ad, wd, idesc, (s > 0 || kk > 0) ? 1u : 0u);
-            if (X3) tc_mma_tf32(d_tmem, ad, make_desc(ws + wlo_off + kk * 32, 16, 1024), idesc, 1u);
+            if (NCAT) {   // A.[W | W_lo]: 2N columns
+              const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * p.N) >> 3) << 17);
+              tc_mma_tf32(d_tmem, ad, wd, idesc2, (s > 0 || kk > 0) ? 1u : 0u);
+            } else {
+              tc_mma_tf32(d_tmem, ad, wd, idesc, (s > 0 || kk > 0) ? 1u : 0u);
+              if (X3) tc_mma_tf32(d_tmem, ad, make_desc(ws + wlo_off + kk * 32, 16, 1024), idesc, 1u);
+            }
           }
         }
         __syncwarp();
@@ -336,7 +353,15 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
           const int c0 = blk * APB + cc;
           uint32_t rr[16];
           tc_ld16(taddr + c0, rr);
-          tc_wait_ld();
+          if (NCAT) {   // + the A.W_lo half of the accumulator
+            uint32_t r2[16];
+            tc_ld16(taddr + ncols + c0, r2);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(__uint_as_float(rr[j]) + __uint_as_float(r2[j]));
+          } else {
+            tc_wait_ld();
+          }
           if (valid) {
             float v[16];
 #pragma unroll
