@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
   // W's, so A.[W | W_lo] is ONE instruction of twice the width into accumulator columns [0,N) and [N,2N) that the
   // epilogue adds; with the measured 66 + 0.75 N cycles per tcgen05.mma two N = 32 instructions (180 cycles) become
   // one N = 64 instruction (114).  Per k-step: 2 instructions instead of 3.
-  constexpr bool NCAT = X3 && NCT > 0 && NCT <= 64 && !EP::kDirectStore;
+  // Streamed weights (head layers, N <= 128 per tile) keep W_lo's k-block behind W's inside every stage: same trick.
+  const bool NCAT = X3 && !EP::kDirectStore && (NCT > 0 ? NCT <= 64 : (p.wstream != 0 && p.N <= 128));
   const int w_blk = p.N * 128;                            // one k-block of weights: [N rows][128 B]
   const int STG = NPL * TP_A_BYTES + (p.wstream ? NPL * w_blk : 0);   // bytes per stage: [A | A_lo | (W blk | W_lo blk)]
   const int w_plane = p.nseg * w_blk;                     // resident weights: [plane][seg][N rows][128 B]
