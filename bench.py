@@ -205,9 +205,9 @@ def roofline_leg(lib, step_fn, dev, steps=5):
     else:
         roof = {"bound": "tensor", "achieved": tfs, "peak": tens_peak, "unit": "TFLOP/s", "frac": tfs / tens_peak}
     # DRAM bytes of one captured launch of this kernel (ncu --set full, profiles/r01g_ncu_key_metrics.json): the layer-0
-    # second-hop node contraction moved 62.1 MB in + 14.5 MB out against 81.2 MB algorithmic (the tail of the writes was
+    # second-hop node contraction moved 62.1 MB in + 14.1 MB out against 81.2 MB algorithmic (the tail of the writes was
     # still in L2 when the kernel ended) -- no re-read waste
-    traffic = 76.6e6 if fam == "nconv_tc_kernel" else None
+    traffic = 76.2e6 if fam == "nconv_tc_kernel" else None
     # the fp32x3 tier issues 3 tf32 MMAs per algorithmic one: the tensor pipe, not HBM, is what this kernel runs
     # against at N ~ 200 (ncu: tensor pipe active 44 %, DRAM 8-22 %); stated beside the contract's algorithmic figures
     tf32_peak = tens_peak / 2.0
