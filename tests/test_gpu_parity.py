@@ -545,3 +545,17 @@ def test_gwnet_diff_G_matches_reference(M, tier):
     with torch.no_grad():
         oe = m(rec["x"].to(dev), sup, None)
     assert_close_rel(oe, rec["out_eval"], TOL, "diff_G eval output")
+
+
+def test_launch_switches_off_still_match_the_oracle():
+    """The three launch-level mechanisms (programmatic dependent launch, the plan's side stream, deferred multi-job weight
+    gradients) are read from the environment once per process: run the smoke check (forward + backward vs the oracle)
+    in a child process with all of them switched off, i.e. through the plain single-stream / per-layer code paths."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GWNET_B200_PDL="0", GWNET_B200_SIDE_STREAM="0", GWNET_B200_DEFER_WGRAD="0")
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "[smoke]" in r.stdout
+
