@@ -979,7 +979,10 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     for (int q = 0; q < nbias; ++q) f.bias[q] = bias[q];
     f.nbias = nbias; f.na = na; f.ab = t.ab < na ? t.ab : na; f.n_ag = r.n_mg; f.n_bg = r.n_nt; f.Ntile = r.N; f.Ntot = Ntot;
     f.n_valid = n_valid; f.sn = sn; f.si = 1;
-    return launch_slot_reduce(tsc.partial, r, (i64)na * 32 * Ntot + Ntot, f, st);
+    const i64 nout = (i64)na * 32 * Ntot + Ntot;
+    if (Ntot % 4 == 0 && r.N % 4 == 0 && r.slot_floats % 4 == 0 && (reinterpret_cast<uintptr_t>(tsc.partial) & 15) == 0)
+      return launch_slot_reduce4(tsc.partial, r, nout, f, st);
+    return launch_slot_reduce(tsc.partial, r, nout, f, st);
   };
   if (hb_tc && E % 32 == 0 && E / 32 <= TR_MAXSRC && Sk / 32 <= TR_MAXSRC && O <= 32) {
     int rs;
