@@ -120,7 +120,7 @@ def run_reference(args):
     v = BATCH / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "device": "host CPU"},
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "global_batch": BATCH, "parallelism": "single"},
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": f"{steps} full trainer.train steps at batch 64 (oracle port of model.py/engine.py, torch CPU ops)"},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -160,7 +160,12 @@ def roofline_leg(lib, step_fn, dev, steps=5):
     import torch
     pk, src = peaks()
     hbm_peak = pk.get("hbm_gbs", 6650.0)
-    tens_peak = pk.get("bf16_tflops_sustained", 1400.0)       # kernels timed inside a long step
+    bf16_peak = pk.get("bf16_tflops_sustained", 1400.0)       # kernels timed inside a long step
+    # tensor roof of the tier the step runs in: kind::tf32 issues at half the bf16 rate, the 3xTF32
+    # split spends three tf32 MMAs per algorithmic one; the fp32 tier runs on the FMA pipe (148 SMs x 128 lanes x 2 x 1.965 GHz)
+    tier = PRECISION_FOR_NOTE[0]
+    tier_factor = {"tf32": 0.5, "fp32x3": 1.0 / 6.0}.get(tier)
+    tens_peak = bf16_peak * tier_factor if tier_factor else 74.4
     for i in range(2):
         step_fn(i)
     torch.cuda.synchronize(dev)
@@ -171,7 +176,7 @@ def roofline_leg(lib, step_fn, dev, steps=5):
     lib.check(lib.dll.gwn_profile_end(buf, len(buf)), "gwn_profile_end")
     ops = json.loads(buf.value.decode())
     total = sum(o["ms"] for o in ops) or 1.0
-    ridge = tens_peak * 1e12 / (hbm_peak * 1e9)               # flop/byte where the bf16 tensor roof meets the HBM roof
+    ridge = tens_peak * 1e12 / (hbm_peak * 1e9)               # flop/byte where this tier's tensor roof meets the HBM roof
     table = []
     for o in ops:
         sec = o["ms"] * 1e-3
@@ -204,22 +209,140 @@ def roofline_leg(lib, step_fn, dev, steps=5):
         roof = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak}
     else:
         roof = {"bound": "tensor", "achieved": tfs, "peak": tens_peak, "unit": "TFLOP/s", "frac": tfs / tens_peak}
-    # DRAM bytes of one captured launch of this kernel (ncu --set full, profiles/r01g_ncu_key_metrics.json): the layer-0
-    # second-hop node contraction moved 62.1 MB in + 14.1 MB out against 81.2 MB algorithmic (the tail of the writes was
-    # still in L2 when the kernel ended) -- no re-read waste
-    traffic = 76.2e6 if fam == "nconv_tc_kernel" else None
-    # the fp32x3 tier issues 3 tf32 MMAs per algorithmic one: the tensor pipe, not HBM, is what this kernel runs
-    # against at N ~ 200 (ncu: tensor pipe active 44 %, DRAM 8-22 %); stated beside the contract's algorithmic figures
-    tf32_peak = tens_peak / 2.0
-    issued = 3.0 if "3xTF32" in TIER_TEXT.get(PRECISION_FOR_NOTE[0], "") else 1.0
-    roof.update({"traffic": traffic, "traffic_note": "one launch (layer 0, second hop: 81.2e6 algorithmic bytes), ncu r01g" if traffic else None,
-                 "issued_tf32_TFLOPs": tfs * issued, "issued_tf32_frac_of_half_bf16_peak": tfs * issued / tf32_peak,
+    # DRAM bytes of one captured launch of this kernel: read from the committed ncu summary (profiles/roofline_traffic.json,
+    # written from an `ncu --set full` capture; per launch like `achieved`), never a constant in this file
+    traffic, traffic_note = None, None
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["kernels"].get(fam)
+        if rec:
+            traffic = float(rec["dram_bytes_per_launch"])
+            traffic_note = (f"{rec['launch']}: dram__bytes_read+write = {traffic / 1e6:.1f} MB vs {rec['algorithmic_bytes_per_launch'] / 1e6:.1f} MB "
+                            f"algorithmic ({rec['source']})")
+    except Exception:
+        pass
+    issued = 3.0 if tier == "fp32x3" else 1.0
+    roof.update({"traffic": traffic, "traffic_note": traffic_note, "tier": tier,
+                 "issued_tf32_TFLOPs": tfs * issued, "issued_tf32_frac_of_half_bf16_peak": tfs * issued / (bf16_peak / 2.0),
                  "kernel": fam, "share_of_step": a["ms"] / total, "tensor_TFLOPs": tfs, "flop_per_byte": ai,
+                 "hbm_frac": gbs / hbm_peak, "tensor_frac_of_tier_peak": tfs / tens_peak,
                  "algorithmic_bytes_per_step": a["bytes"] / steps, "ms_per_step": a["ms"] / steps,
                  "operators": [k for k, v in fam_of.items() if v == fam],
-                 "peak_source": f"MEASURED_PEAKS.json ({src}): hbm_gbs, bf16_tflops_sustained (operators timed inside the step)",
+                 "peak_source": f"MEASURED_PEAKS.json ({src}): hbm_gbs; tensor roof = bf16_tflops_sustained x "
+                                f"{'1/2 (tf32)' if tier == 'tf32' else '1/6 (3xTF32)' if tier == 'fp32x3' else 'n/a (FMA pipe 74.4)'}",
                  "ridge_flop_per_byte": ridge, "profiled_steps": steps, "op_ms_per_step": total / steps})
     return roof, table
+
+
+def contraction_leg(lib, NV, dev):
+    """BASELINE metric, second half: "gcn TFLOP/s vs peak" -- the node contraction of model.py:13 alone at N = 2048 / 4096
+    (config 4's graph sizes; X and Y are 100 MB each, beyond the 126 MB L2 together), both tensor-core tiers, CUDA events."""
+    import torch
+    pk, src = peaks()
+    burst = pk.get("bf16_tflops", 1590.0)
+    out = []
+    st = torch.cuda.current_stream(dev).cuda_stream
+    for V, B, L in ((2048, 16, 24), (4096, 8, 24)):
+        gen = torch.Generator().manual_seed(V)
+        S = torch.softmax(torch.randn(V, V, generator=gen), dim=1).to(dev).contiguous()
+        Slo = torch.empty_like(S)
+        lib.check(lib.dll.gwn_split_lo(S.data_ptr(), Slo.data_ptr(), S.numel(), st), "gwn_split_lo")
+        x = torch.randn(B, L, V, 32, generator=gen).to(dev)
+        y = torch.empty_like(x)
+        flop = 2.0 * B * L * 32 * V * V
+
+        def call(tier):
+            if tier == "tf32":
+                lib.check(lib.dll.gwn_node_contract(x.data_ptr(), S.data_ptr(), V, y.data_ptr(), B, L, V, 32, NV.PREC_TF32, st))
+            else:
+                lib.check(lib.dll.gwn_node_contract_x3(x.data_ptr(), S.data_ptr(), Slo.data_ptr(), V, y.data_ptr(), B, L, V, 32, st))
+        for tier, factor in (("tf32", 0.5), ("fp32x3", 1.0 / 6.0)):
+            for _ in range(3):
+                call(tier)
+            iters = 10
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                call(tier)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            tf = flop / ms / 1e9
+            out.append({"nodes": V, "slabs_B_x_L": [B, L], "channels": 32, "tier": tier, "us_per_launch": ms * 1e3,
+                        "TFLOPs": tf, "frac_of_bf16_burst": tf / burst, "tier_factor": factor,
+                        "frac_of_tier_peak": tf / (burst * factor), "peak": f"bf16_tflops burst {burst} ({src}) x tier factor"})
+        del x, y, S, Slo
+    torch.cuda.empty_cache()
+    return out
+
+
+def config4_leg(E, NV, StandardScaler, O, dev):
+    """Full trainer.train step of BASELINE config 4 (N = 2048, residual 32, skip 256, 8 blocks x 2 layers, batch 64)."""
+    import torch
+    recs = []
+    N4, B4 = 2048, 64
+    gen = torch.Generator().manual_seed(0)
+    sup = [s.to(dev) for s in O.synthetic_supports(N4, 16.0 / N4, gen)]
+    x, y = O.synthetic_batch(B4, N4, SEQ, IN_DIM, gen)
+    x, y = x.to(dev), y.to(dev)
+    for tier in ("fp32x3", "tf32"):
+        torch.manual_seed(999)
+        tr = E.trainer(StandardScaler(54.0, 20.0), IN_DIM, SEQ, N4, 32, DROPOUT, 1e-3, 1e-4, dev, sup, True, True, None, 8, 2)
+        tr.model.precision = {"tf32": NV.PREC_TF32, "fp32x3": NV.PREC_FP32X3}[tier]
+        for _ in range(2):
+            tr.train(x, y)
+        steps = 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            tr.train(x, y)
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        recs.append({"workload": "gwnet large graph N=2048 batch=64 8 blocks x 2 layers (config 4), full trainer.train step", "tier": tier,
+                     "ms_per_step": ms, "samples_per_s": B4 / ms * 1e3, "model_TFLOPs": 51131.0 / ms,
+                     "peak_mem_GB": torch.cuda.max_memory_allocated(dev) / 1e9})
+        del tr
+        torch.cuda.empty_cache()
+    return recs
+
+
+def gpu_eager_leg(O, dev):
+    """The bar the reference itself sets on this box: the reference's own torch ops (oracle
+    port of model.py / engine.py: einsum, conv2d, batch_norm, dropout, torch.optim.Adam) run by PyTorch EAGER on the B200
+    through cuBLAS / cuDNN -- full trainer.train step, METR-LA shape, fp32 convs and the reference's default (TF32 convs)."""
+    import torch
+    out = []
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for allow_tf32 in (False, True):
+            torch.backends.cudnn.allow_tf32 = allow_tf32          # reference default: True (SURVEY G6)
+            torch.backends.cuda.matmul.allow_tf32 = False         # reference default
+            cfg = O.GwnetConfig(num_nodes=NODES, dropout=DROPOUT, n_static_supports=2)
+            gen = torch.Generator().manual_seed(0)
+            sup = [s.to(dev) for s in O.synthetic_supports(NODES, 0.05, gen)]
+            torch.manual_seed(999)
+            st = {k: v.to(dev) for k, v in O.init_state(cfg).items()}
+            tr = O.OracleTrainer(cfg, st, sup, 54.0, 20.0)
+            x, y = O.synthetic_batch(BATCH, NODES, SEQ, IN_DIM, gen)
+            x, y = x.to(dev), y.to(dev)
+            for _ in range(5):
+                tr.train(x, y)
+            torch.cuda.synchronize(dev)
+            n = 20
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                tr.train(x, y)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / n
+            out.append({"what": "reference ops (oracle port), torch eager on this B200, cuBLAS/cuDNN", "cudnn_allow_tf32": allow_tf32,
+                        "matmul_allow_tf32": False, "ms_per_step": ms, "samples_per_s": BATCH / ms * 1e3, "steps": n})
+            del tr, st
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_native(args):
@@ -348,6 +471,12 @@ def run_native(args):
             line["other_tiers"] = tiers
         if roof is not None:
             line["roofline"], line["operators"] = roof
+        if world == 1 and not args.skip_extras:
+            del tr
+            torch.cuda.empty_cache()
+            line["gcn_contraction"] = contraction_leg(lib, NV, dev)
+            line["gpu_eager_reference"] = gpu_eager_leg(O, dev)
+            line["config4_large_graph"] = config4_leg(E, NV, StandardScaler, O, dev)
         if world == 1 and not args.skip_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line), flush=True)
@@ -369,6 +498,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the fused step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only")
     ap.add_argument("--skip-roofline", action="store_true", help="profiling runs only")
+    ap.add_argument("--skip-extras", action="store_true",
+                    help="skip the N=1 context records (gcn contraction at N=2048/4096, reference eager on the GPU, config-4 step)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

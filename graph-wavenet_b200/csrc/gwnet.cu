@@ -1596,6 +1596,28 @@ int gwn_node_contract(const float* x, const float* S, int64_t ld, float* y, int 
   return node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, B, L, 0, V, C, (cudaStream_t)stream, &tcs);
 }
 
+int gwn_split_lo(const float* src, float* lo, int64_t n, void* stream) {
+  GWN_TRY(require_device());
+  GWN_CHECK_ARG(src && lo && n >= 0, "split_lo: bad argument");
+  if (n == 0) return 0;
+  GWN_LAUNCH_1D(split_lo_kernel, (i64)n, (cudaStream_t)stream, src, lo, (i64)n);
+  return 0;
+}
+
+int gwn_node_contract_x3(const float* x, const float* S, const float* S_lo, int64_t ld, float* y, int B, int L, int V, int C,
+                         void* stream) {
+  GWN_TRY(require_device());
+  GWN_CHECK_ARG(x && S && S_lo && y, "node_contract_x3: null pointer");
+  MathScope math_scope(math_of(GWN_PREC_FP32X3));
+  SupportView sv = SupportView{S, 1, ld, 0};
+  TcSupports tcs;
+  memset(&tcs, 0, sizeof(tcs));
+  tcs.S[0] = S; tcs.Slo[0] = S_lo; tcs.ld = (int)ld; tcs.precision = GWN_PREC_FP32X3;
+  const float* X[1] = {x};
+  float* Y[1] = {y};
+  return node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, B, L, 0, V, C, (cudaStream_t)stream, &tcs);
+}
+
 int gwn_nconv_fwd(const float* x, const float* A, int64_t lda, float* y, int B, int L, int V, int C, int precision,
                   void* stream) {
   GWN_TRY(require_device());

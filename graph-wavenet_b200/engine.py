@@ -81,23 +81,88 @@ class trainer():
         assert state == 'train' or state == 'val' or state == 'test'
         self.state = state
 
-    def train_syn(self, *a, **k):
-        raise NotImplementedError("train_syn / eval_syn (engine.py:64-117,132-180: the fork's synthetic F/E pooling task, host-side "
-                                  "python loops over graphTools objects) are outside the accelerated path (SURVEY.md section 2.1); "
-                                  "self.model(input, supports, aptinit) and its autograd are available")
+    # ---- the fork's synthetic multi-graph task (engine.py:64-117,132-180): the network predicts the fine signal, from
+    # which a time-pooled signal F (mean over windows of F_t steps) and a cluster-pooled signal E (mean over the node
+    # clusters of the sample's graph) are derived and compared with `real`.  The network runs on the native plan through
+    # the autograd node of gwnet / gwnet_diff_G; the pooling is a handful of index ops on the [B,1,N,T] prediction.
+    def _syn_forward(self, input, adj_idx):
+        input = nn.functional.pad(input, (1, 0, 0, 0))
+        if adj_idx is None:
+            return self.model(input)
+        assert self.state is not None, 'set train/val/test state first'
+        supports = [s[adj_idx] for s in self.supports[self.state]]
+        aptinit = self.aptinit[self.state] if self.aptinit is not None else None
+        if aptinit is not None:
+            aptinit = aptinit[adj_idx]
+        return self.model(input, supports, aptinit)
 
-    eval_syn = train_syn
+    @staticmethod
+    def _syn_pool(predict, F_t, G, adj_idx, pooltype):
+        if pooltype != 'avg':
+            raise NotImplementedError("pooltype 'subsample' is a TODO in the reference (engine.py:108-109)")
+        lead = predict.shape[:-1]
+        # F: window means over time, repeated back to full length
+        F = predict.reshape(*lead, -1, F_t).mean(-1, keepdim=True).expand(*lead, predict.shape[-1] // F_t, F_t).reshape(*lead, -1)
+        # E: cluster means over nodes, written back to the member nodes (clusters in dictionary order, like the reference)
+        per_sample = type(G) == list
+        parts = []
+        for sample in (range(len(predict)) if per_sample else [None]):
+            assign = (G[adj_idx[sample]] if per_sample else G).assign_dict
+            e = predict[sample:sample + 1] if per_sample else predict
+            for k in range(len(assign)):
+                idx = torch.as_tensor(assign[k], dtype=torch.long, device=predict.device)
+                e = e.index_copy(2, idx, e.index_select(2, idx).mean(2, keepdim=True).expand(-1, -1, idx.numel(), -1))
+            parts.append(e)
+        E = torch.cat(parts, 0) if per_sample else parts[0]
+        return F, E
+
+    def train_syn(self, input, real, F_t, G, adj_idx=None, pooltype='avg'):
+        self.model.train()
+        if isinstance(self.optimizer, _fused.FusedAdam):
+            self._bind_flat(input)
+            self.optimizer.zero_grad(set_to_none=False)
+            self.optimizer.max_norm, self.optimizer.grad_scale = 0.0, 1.0
+        else:
+            self.optimizer.zero_grad()
+        output = self._syn_forward(input, adj_idx).transpose(1, 3)
+        predict = self.scaler.inverse_transform(output)
+        F, predict = self._syn_pool(predict, F_t, G, adj_idx, pooltype)
+        loss = self.loss(torch.cat((F, predict), 1), real, 0.0)
+        loss.backward()
+        if self.world > 1:
+            self._allreduce_grads()
+        if self.clip is not None:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip)
+        self.optimizer.step()
+        mape = util.masked_mape(predict, real, 0.0).item()
+        rmse = util.masked_rmse(predict, real, 0.0).item()
+        return loss.item(), mape, rmse
+
+    def eval_syn(self, input, real, F_t, G, adj_idx=None, pooltype='avg'):
+        assert type(G) != list or adj_idx is not None, 'adj index needed.'
+        self.model.eval()
+        with torch.no_grad():
+            output = self._syn_forward(input, adj_idx if type(G) == list else None).transpose(1, 3)
+            predict = self.scaler.inverse_transform(output)
+            F, predict = self._syn_pool(predict, F_t, G, adj_idx, pooltype)
+            loss = self.loss(torch.cat((F, predict), 1), real, 0.0)
+            mape = util.masked_mape(predict, real, 0.0).item()
+            rmse = util.masked_rmse(predict, real, 0.0).item()
+        return loss.item(), mape, rmse, F, predict
 
     def _bind_flat(self, input):
         m = self.model
         if m._flat is None or not m._flat.intact():
-            m._flat = _fused.FlatParams(m, m._runner(input.shape[0], input.shape[3]).plan)
+            # the plan the forward below will use: the input is padded by one column first (engine.py:44)
+            m._flat = _fused.FlatParams(m, m._runner(input.shape[0], input.shape[3] + 1).plan)
             self.optimizer._flat = None
         if not self.optimizer.bound:
             self.optimizer.bind(m._flat, int(torch.randint(0, 2 ** 62, (1,)).item()))
 
     def _fused_step(self, input, real_val):
-        key = (tuple(input.shape), tuple(real_val.shape), self.model.precision, bool(self.use_graph), float(self.model.dropout))
+        # scaler mean/std are baked into the captured launches by value: they are part of the key
+        key = (tuple(input.shape), tuple(real_val.shape), self.model.precision, bool(self.use_graph), float(self.model.dropout),
+               float(self.scaler.mean), float(self.scaler.std))
         st = self._steps.get(key)
         if st is None or not st.valid():
             self._steps = {k: v for k, v in self._steps.items() if v.valid()}
@@ -139,13 +204,14 @@ class trainer():
         return loss.item(), mape, rmse
 
     def _fused_eval(self, input, real_val):
-        key = ("eval", tuple(input.shape), tuple(real_val.shape), self.model.precision, bool(self.use_graph))
+        key = ("eval", tuple(input.shape), tuple(real_val.shape), self.model.precision, bool(self.use_graph),
+               float(self.scaler.mean), float(self.scaler.std))
         ev = self._steps.get(key)
         if ev is None or not ev.valid():
             self.model._table()
             ws = None
             for v in self._steps.values():      # share the forward workspace of a train step of the same shape
-                if isinstance(v, _fused.FusedStep) and v.plan is self.model._runner(input.shape[0], input.shape[3]).plan:
+                if isinstance(v, _fused.FusedStep) and v.plan is self.model._runner(input.shape[0], input.shape[3] + 1).plan:
                     ws = v.workspace
             ev = _fused.FusedEval(self, input, real_val, self.use_graph, ws)
             self._steps[key] = ev

@@ -103,9 +103,61 @@ class FusedAdam(torch.optim.Optimizer):
             lib.check(lib.dll.gwn_train_ctrl_init(self.ctrl.data_ptr(), int(seed) & (2 ** 64 - 1), 0), "gwn_train_ctrl_init")
         self._hyper_cached = None
 
+        pend, self._pending = getattr(self, "_pending", None), None
+        if pend is not None:      # a load_state_dict that arrived before the optimizer was bound
+            self._restore(pend)
+
     @property
     def bound(self):
         return self._flat is not None
+
+    # -- checkpointing: the moments and the step count live in flat device buffers / the control block, not in
+    # Optimizer.state; state_dict()/load_state_dict() carry them under the extra key "fused" so that a resumed run
+    # continues Adam where it stopped (torch.optim.Adam semantics)
+    def state_dict(self):
+        sd = super().state_dict()
+        if self.bound:
+            seed = C.c_uint64(0)
+            step = C.c_int64(0)
+            _sync(self._flat.param.device)
+            self._lib.check(self._lib.dll.gwn_train_ctrl_read(self.ctrl.data_ptr(), C.byref(seed), C.byref(step)))
+            sd["fused"] = {"exp_avg": self.exp_avg.detach().clone(), "exp_avg_sq": self.exp_avg_sq.detach().clone(),
+                           "step": int(step.value), "seed": int(seed.value)}
+        elif getattr(self, "_pending", None) is not None:
+            sd["fused"] = self._pending
+        return sd
+
+    def load_state_dict(self, state_dict):
+        sd = dict(state_dict)
+        fused = sd.pop("fused", None)
+        super().load_state_dict(sd)
+        self._hyper_cached = None
+        if fused is not None:
+            if self.bound:
+                self._restore(fused)
+            else:
+                self._pending = fused
+
+    def _restore(self, fused):
+        f = self._flat
+        if fused["exp_avg"].numel() != f.n:
+            raise N.GwnError("FusedAdam.load_state_dict: moment buffers do not match this model's flat layout")
+        dev = f.param.device
+        with torch.no_grad():
+            self.exp_avg.copy_(fused["exp_avg"].to(dev))
+            self.exp_avg_sq.copy_(fused["exp_avg_sq"].to(dev))
+        with _dev_ctx(dev):
+            _sync(dev)
+            self._lib.check(self._lib.dll.gwn_train_ctrl_init(self.ctrl.data_ptr(), int(fused.get("seed", 0)) & (2 ** 64 - 1),
+                                                              int(fused["step"])), "gwn_train_ctrl_init")
+
+    def zero_grad(self, set_to_none: bool = False):
+        """p.grad are views of the flat gradient buffer: zero the buffer and keep the views (set_to_none would detach
+        them and leave p.grad None after fused steps)."""
+        if self.bound:
+            self._flat.grad.zero_()
+        else:
+            super().zero_grad(set_to_none=set_to_none)
 
     def step_count(self) -> int:
         seed, step = C.c_uint64(0), C.c_int64(0)
@@ -163,7 +215,10 @@ class FusedStep:
         self.lib, self.trainer = lib, trainer
         dev = x.device
         B, F, Nn, T = x.shape
-        runner = model._runner(B, T)
+        # engine.py:44 left-pads the input by one zero column BEFORE gwnet.forward, and model.py:176-180 pads to the
+        # receptive field only when the padded length is still shorter: the plan is built for T+1 and reads the zero
+        # column from the static input buffer (for T+1 <= RF the two pads coincide; for T >= RF they do not)
+        runner = model._runner(B, T + 1)
         self.runner, self.plan = runner, runner.plan
         if model._flat is None or not model._flat.intact():
             model._flat = FlatParams(model, runner.plan)
@@ -173,7 +228,8 @@ class FusedStep:
         self.flat = model._flat
         cfg = runner.cfg
         # static buffers (the graph bakes their addresses)
-        self.x = torch.empty((B, T, Nn, F), dtype=torch.float32, device=dev).permute(0, 3, 2, 1)   # loader layout [B,T,N,F]
+        self.x = torch.zeros((B, T + 1, Nn, F), dtype=torch.float32, device=dev).permute(0, 3, 2, 1)   # loader layout [B,T,N,F]
+        self.x_in = self.x[:, :, :, 1:]      # column 0 stays zero: the trainer's pad
         self.y = torch.empty(tuple(y.shape), dtype=torch.float32, device=dev)
         self.out = torch.empty((B, cfg.out_dim, Nn, self.plan.t_out), dtype=torch.float32, device=dev)
         self.workspace = torch.empty(self.plan.fwd_bytes, dtype=torch.uint8, device=dev)
@@ -276,7 +332,7 @@ class FusedStep:
         opt.max_norm = float(tr.clip) if tr.clip is not None else 0.0
         opt.grad_scale = 1.0 / tr.world
         opt.sync_hyper()
-        self.x.copy_(x, non_blocking=True)
+        self.x_in.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
         if self.graph is not None and self.graph_tail is not None:
             self.graph.replay()
@@ -302,12 +358,13 @@ class FusedEval:
         self.lib, self.trainer = lib, trainer
         dev = x.device
         B, F, Nn, T = x.shape
-        runner = model._runner(B, T)
+        runner = model._runner(B, T + 1)     # engine.py:121: the +1 left pad is part of the network input (see FusedStep)
         self.runner, self.plan = runner, runner.plan
         cfg = runner.cfg
         if y.dim() != 3 or y.shape[0] != B or y.shape[1] != Nn or y.shape[2] != cfg.out_dim:
             raise N.GwnError(f"real_val must be [B={B}, N={Nn}, out_dim={cfg.out_dim}], got {tuple(y.shape)}")
-        self.x = torch.empty((B, T, Nn, F), dtype=torch.float32, device=dev).permute(0, 3, 2, 1)
+        self.x = torch.zeros((B, T + 1, Nn, F), dtype=torch.float32, device=dev).permute(0, 3, 2, 1)
+        self.x_in = self.x[:, :, :, 1:]
         self.y = torch.empty(tuple(y.shape), dtype=torch.float32, device=dev)
         self.out = torch.empty((B, cfg.out_dim, Nn, self.plan.t_out), dtype=torch.float32, device=dev)
         self.workspace = workspace if workspace is not None else torch.empty(self.plan.fwd_bytes, dtype=torch.uint8, device=dev)
@@ -353,7 +410,7 @@ class FusedEval:
             self.metrics_host.copy_(self.metrics, non_blocking=True)
 
     def run(self, x: torch.Tensor, y: torch.Tensor):
-        self.x.copy_(x, non_blocking=True)
+        self.x_in.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
         if self.graph is not None:
             self.graph.replay()

@@ -83,7 +83,7 @@ class GwnGcnDesc(C.Structure):
 # every symbol include/gwnet_b200.h declares (tests check that the library exports them all)
 EXPORTS = [
     "gwn_last_error", "gwn_abi_version", "gwn_launch_count", "gwn_device_info", "gwn_profile_begin", "gwn_profile_end", "gwn_permute4d",
-    "gwn_node_contract", "gwn_tc_error_flag", "gwn_tc_debug_buffer", "gwn_tc_debug_mode", "gwn_nconv_fwd", "gwn_nconv_bwd", "gwn_linear_fwd", "gwn_linear_bwd",
+    "gwn_node_contract", "gwn_node_contract_x3", "gwn_split_lo", "gwn_tc_error_flag", "gwn_tc_debug_buffer", "gwn_tc_debug_mode", "gwn_nconv_fwd", "gwn_nconv_bwd", "gwn_linear_fwd", "gwn_linear_bwd",
     "gwn_gcn_fwd", "gwn_gcn_bwd_scratch_floats", "gwn_gcn_bwd",
     "gwn_nconv2_fwd", "gwn_nconv2_bwd", "gwn_gcn2_fwd", "gwn_gcn2_bwd",
     "gwn_plan_create", "gwn_plan_destroy", "gwn_plan_workspace_bytes", "gwn_plan_param_count",
@@ -123,6 +123,8 @@ class Lib:
         i64p = C.POINTER(C.c_int64)
         d.gwn_permute4d.argtypes = [C.c_void_p, i64p, C.c_void_p, i64p, i64p, C.c_void_p]
         d.gwn_node_contract.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+        d.gwn_node_contract_x3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
+        d.gwn_split_lo.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         d.gwn_tc_error_flag.argtypes = [C.c_int]
         d.gwn_tc_debug_buffer.argtypes = [C.c_void_p]
         d.gwn_tc_debug_buffer.restype = None

@@ -53,13 +53,14 @@ typedef enum gwn_status {
   GWN_ERR_NO_DEVICE = 10004    /* no CUDA device: there is no CPU fallback */
 } gwn_status;
 
-/* Precision of the contractions (storage is always fp32). */
+/* Precision tier of the contractions (activations, parameters and gradients are stored in fp32 in every tier). */
 typedef enum gwn_precision {
-  GWN_PREC_FP32 = 0,  /* fp32 FMA everywhere: the 1e-4 parity tier                 */
-  GWN_PREC_TF32 = 1,  /* node contraction on tcgen05 kind::tf32, other contractions
-                         single-pass TF32 mma.sync; fp32 accumulate (2e-2 tier)     */
-  GWN_PREC_BF16 = 2,  /* reserved: bf16 operands (not in this build)                 */
-  GWN_PREC_FP32X3 = 3 /* fp32-grade on the tensor cores: 3xTF32 split (mma.sync)     */
+  GWN_PREC_FP32 = 0,  /* fp32 FMA everywhere (generic SIMT kernels): reference tier, 1e-4 parity             */
+  GWN_PREC_TF32 = 1,  /* every contraction on tcgen05 kind::tf32 (operands truncated to TF32 by the tensor
+                         core), fp32 accumulate in TMEM: the 2e-2 tier (measured ~2e-4 output error)          */
+  GWN_PREC_BF16 = 2,  /* reserved: bf16 operands (not in this build; entry points reject it)                  */
+  GWN_PREC_FP32X3 = 3 /* DEFAULT.  fp32-grade on tcgen05: every contraction as a 3xTF32 split
+                         (A.B + A.B_lo + A_lo.B, remainders exact in fp32), fp32 accumulate: 1e-4 parity      */
 } gwn_precision;
 
 /* Dropout source for gcn (model.py:54). */
@@ -95,6 +96,11 @@ int gwn_permute4d(const float* src, const int64_t src_strides[4], float* dst, co
  * tcgen05/TMEM/TMA kernel (needs C == 32, ld % 4 == 0, 16-byte aligned pointers); GWN_PREC_FP32 the FMA tier. */
 int gwn_node_contract(const float* x, const float* S, int64_t ld, float* y, int B, int L, int V, int C, int precision,
                       void* stream);
+/* The same contraction in the fp32-grade 3xTF32 tier (GWN_PREC_FP32X3): S_lo = S - tf32_trunc(S) from gwn_split_lo. */
+int gwn_node_contract_x3(const float* x, const float* S, const float* S_lo, int64_t ld, float* y, int B, int L, int V, int C,
+                         void* stream);
+/* lo[i] = src[i] - tf32_trunc(src[i]) (exact in fp32): the remainder plane of a 3xTF32 operand. */
+int gwn_split_lo(const float* src, float* lo, int64_t n, void* stream);
 /* First pipeline time-out recorded by the tcgen05 kernels (0 = none); synchronises the device. Debug aid. */
 int gwn_tc_error_flag(int reset);
 /* Debug aid: device buffer that receives a dump of the first pipeline stage of subsequent tcgen05 launches (NULL = off). */

@@ -1,5 +1,6 @@
 """TEST INFRASTRUCTURE ONLY -- numpy restatement of the reference's batch iterator (Utils/util.py:14-54), the oracle of the
-device-resident feed in graph-wavenet_b200/feed.py.  Imported by tests/ only."""
+device-resident feed in graph-wavenet_b200/feed.py.  Pinned: tests/golden/feed_order.json holds sample orders recorded from the REAL
+reference loader (tests/tools/make_golden_feed.py); tests/test_feed.py checks this restatement against them.  Imported by tests/ only."""
 import numpy as np
 
 

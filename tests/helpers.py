@@ -8,7 +8,10 @@ import torch
 from oracle import gwnet_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-CASES = ["dbl_adp", "aptonly", "static_only", "nogcn", "long_seq", "aptinit", "c32"]
+CASES = ["dbl_adp", "aptonly", "static_only", "nogcn", "long_seq", "aptinit", "c32", "tr_long", "tr_c32"]
+# cases recorded with the trainer's widths (skip = 8 nhid, end = 16 nhid): 3 engine.trainer.train steps + 1 eval of the real
+# reference; tr_long / tr_c32 have inputs LONGER than the receptive field (T_out = 7)
+TRAINER_CASES = ["dbl_adp", "aptonly", "tr_long", "tr_c32"]
 
 
 def load_case(name):

@@ -33,3 +33,24 @@ def test_feed_matches_reference_iterator(n, bs, pad):
             v = gx.transpose(1, 3)                      # train.py:245 -- the strided view the model consumes
             assert tuple(v.shape) == (wx.shape[0], 2, 9, 12)
         assert np.array_equal(ours.xs.numpy(), ref.xs)
+
+
+def test_feed_oracle_is_pinned_to_the_real_reference_loader():
+    """oracle/feed_oracle.py (and the product feed) against sample orders recorded from the REAL ``Utils/util.py``
+    DataLoader by tests/tools/make_golden_feed.py: padding, batch count and three epochs of shuffled order."""
+    import json, os
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "feed_order.json")))
+    assert len(cases) == 5
+    for c in cases:
+        n, bs, pad = c["n"], c["batch_size"], c["pad"]
+        xs = np.arange(n, dtype=np.float32).reshape(n, 1, 1, 1)
+        for make in (DataLoaderOracle, DataLoader):
+            dl = make(xs, -xs, bs, pad)
+            assert (int(dl.size), int(dl.num_batch)) == (c["size"], c["num_batch"])
+            for epoch, want in enumerate(c["epochs"]):
+                if epoch:
+                    np.random.seed(100 + epoch)
+                    dl.shuffle()
+                it = dl.batches() if make is DataLoaderOracle else dl.get_iterator()
+                got = [[int(v) for v in np.asarray(bx).reshape(-1)] for bx, _ in it]
+                assert got == want, (make.__name__, n, bs, pad, epoch)

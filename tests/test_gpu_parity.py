@@ -6,7 +6,7 @@ import torch
 
 import __graft_entry__ as ge
 from oracle import gwnet_oracle as O
-from helpers import CASES, load_case, sub, assert_close_rel
+from helpers import CASES, TRAINER_CASES, load_case, sub, assert_close_rel
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -60,7 +60,7 @@ def test_gwnet_matches_reference_golden(M, name, tier):
             assert_close_rel(v.float(), rec["buf1/" + k].float(), TOL, "buffer " + k)
 
 
-@pytest.mark.parametrize("name", ["dbl_adp", "aptonly"])
+@pytest.mark.parametrize("name", TRAINER_CASES)
 def test_trainer_steps_match_reference(M, name):
     from graph_wavenet_b200 import engine as E
     from graph_wavenet_b200.metrics import StandardScaler
@@ -203,10 +203,10 @@ def test_metr_la_full_size(M, tier):
         assert abs(a - b) <= 1e-4 * max(abs(b), 0.05), (got, rep["out_first8"])
 
 
-@pytest.mark.parametrize("tier", ["fp32", "fp32x3"])
-def test_pems_bay_aptonly_full_size(M, tier):
-    """BASELINE config 2 (N=325, adaptive adjacency only)."""
-    _fullsize(M, O.GwnetConfig(num_nodes=325, dropout=0.0, n_static_supports=0, has_supports=False), 16, 0.05, tier)
+@pytest.mark.parametrize("tier,batch", [("fp32", 16), ("fp32x3", 16), ("fp32x3", 64)])
+def test_pems_bay_aptonly_full_size(M, tier, batch):
+    """BASELINE config 2 (N=325, adaptive adjacency only); batch 64 = the config as written, in the default tier."""
+    _fullsize(M, O.GwnetConfig(num_nodes=325, dropout=0.0, n_static_supports=0, has_supports=False), batch, 0.05, tier)
 
 
 @pytest.mark.parametrize("blocks,layers", [(3, 3), (5, 2)])
@@ -230,8 +230,20 @@ def test_crash_shape_long_sequence(M):
     m.train()
     out = m(x.to(dev))
     assert tuple(out.shape) == (4, 48, 200, 37)
+    probe = torch.randn(out.shape, generator=gen) * O.relu_safe_positions(state, cfg, x, sup, True)
+    (out * probe.to(dev)).sum().backward()
+    pk = [k for k in state if not O.is_buffer(k)]
+    for k in pk:
+        state[k].requires_grad_(True)
     oout = O.forward(state, cfg, x, sup, True)
-    assert_close_rel(out, oout, TOL, "T_out=37 output")
+    (oout * probe).sum().backward()
+    assert_close_rel(out, oout.detach(), TOL, "T_out=37 output")
+    gn = sum(float(state[k].grad.double().pow(2).sum()) for k in pk if state[k].grad is not None) ** 0.5
+    for k, p in m.named_parameters():     # every gradient with T_out = 37 live skip columns per layer
+        if state[k].grad is None:
+            assert p.grad is None, k
+            continue
+        assert_close_rel(p.grad, state[k].grad, TOL, "T_out=37 grad " + k, floor=2e-6 * gn)
 
 
 def test_dropout_statistics_and_determinism(M):
@@ -368,11 +380,13 @@ def _make_trainer(dev, cfg, sup, state0, dropout, fused, graph, monkeypatch):
     return tr
 
 
-def test_fused_graph_step_equals_autograd_step(M, monkeypatch):
+@pytest.mark.parametrize("name", ["dbl_adp", "tr_c32"])
+def test_fused_graph_step_equals_autograd_step(M, monkeypatch, name):
     """One CUDA-graph replay per trainer.train (fused loss / clip / Adam kernels) must track the autograd path
-    (torch loss ops, clip_grad_norm_, torch.optim.Adam) step for step: engine.py:41-58."""
+    (torch loss ops, clip_grad_norm_, torch.optim.Adam) step for step: engine.py:41-58.  tr_c32: input longer than the
+    receptive field (the trainer's +1 pad is a real column, T_out = 7) on the tcgen05 kernels."""
     dev = torch.device("cuda:0")
-    rec = load_case("dbl_adp")
+    rec = load_case(name)
     cfg = rec["cfg"]
     sup = [s.to(dev) for s in rec["supports"]]
     x, y = rec["x"].to(dev), rec["y"][:, :, : cfg.out_dim].to(dev)
@@ -559,3 +573,176 @@ def test_launch_switches_off_still_match_the_oracle():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "[smoke]" in r.stdout
 
+
+
+# ------------------------------------------------------------------------------------------------ round-2 parity additions
+@pytest.mark.parametrize("tier", ["fp32x3", "tf32"])
+def test_large_graph_config4_reduced_batch(M, tier):
+    """BASELINE config 4 (N = 2048, residual 32, skip 256, 8 blocks x 2 layers: RF = 25, 16 layers) at batch 2 so that the
+    CPU oracle finishes in seconds: output and every gradient; exercises the V > 256 column-tiled contraction (the 2-CTA
+    cta_group::2 kernel), the tiled support gradient and 16-layer deferred weight gradients."""
+    from graph_wavenet_b200 import native as NV
+    dev = torch.device("cuda:0")
+    Nn, B = 2048, 2
+    cfg = O.GwnetConfig(num_nodes=Nn, dropout=0.0, n_static_supports=2, blocks=8, layers=2)
+    gen = torch.Generator().manual_seed(4)
+    sup = O.synthetic_supports(Nn, 16.0 / Nn, gen)
+    x, _ = O.synthetic_batch(B, Nn, 12, cfg.in_dim, gen)
+    x = torch.nn.functional.pad(x, (1, 0, 0, 0))
+    torch.manual_seed(999)
+    m = build_model(M, cfg, sup, dev)
+    m.precision = {"fp32x3": NV.PREC_FP32X3, "tf32": NV.PREC_TF32}[tier]
+    state = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    m.train()
+    out = m(x.to(dev))
+    tau = 1e-4 if tier == "fp32x3" else 1e-2
+    probe = torch.randn(out.shape, generator=gen) * O.relu_safe_positions(state, cfg, x, sup, True, tau=tau)
+    (out * probe.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert NV.get_lib().dll.gwn_tc_error_flag(1) == 0
+    pk = [k for k in state if not O.is_buffer(k)]
+    for k in pk:
+        state[k].requires_grad_(True)
+    oout = O.forward(state, cfg, x, sup, True)
+    (oout * probe).sum().backward()
+    tol = TOL if tier == "fp32x3" else TOL_TF32
+    assert_close_rel(out, oout.detach(), tol, f"config 4 {tier} output")
+    gn = sum(float(state[k].grad.double().pow(2).sum()) for k in pk if state[k].grad is not None) ** 0.5
+    gd = 0.0
+    for k, p in m.named_parameters():
+        if state[k].grad is None:
+            assert p.grad is None, k
+            continue
+        if tier == "fp32x3":
+            assert_close_rel(p.grad, state[k].grad, tol, f"config 4 {tier} grad " + k, floor=2e-6 * gn)
+        gd += float((p.grad.cpu() - state[k].grad).double().pow(2).sum())
+    print(f"[config 4, {tier}] output rel-L2 {float((out.cpu() - oout.detach()).norm() / oout.detach().norm()):.2e}, "
+          f"global grad rel-L2 {gd ** 0.5 / gn:.2e}")
+    assert gd ** 0.5 <= tol * gn
+
+
+def test_fused_step_with_injected_dropout_masks_matches_oracle(M, monkeypatch):
+    """trainer.train at dropout 0.3 -- the benchmarked configuration -- through the fused CUDA-graph step with the keep
+    masks INJECTED, against OracleTrainer.train(keep_masks=...) fed the same masks: 3 steps, metrics at 1e-4."""
+    dev = torch.device("cuda:0")
+    rec = load_case("tr_c32")
+    cfg = rec["cfg"]
+    p = 0.3
+    sup = [s.to(dev) for s in rec["supports"]]
+    x, y = rec["x"], rec["y"][:, :, : cfg.out_dim]
+    B, Nn, C = x.shape[0], cfg.num_nodes, cfg.residual_channels
+    gen = torch.Generator().manual_seed(21)
+    Ls, L = [], max(x.shape[3] + 1, cfg.receptive_field)
+    for d in cfg.dilations():
+        L -= d
+        Ls.append(L)
+    masks = [(torch.rand(B, l, Nn, C, generator=gen) >= p).to(torch.uint8) for l in Ls]          # BLNC
+    tr = _make_trainer(dev, cfg, sup, rec["state0"], p, True, True, monkeypatch)
+    tr.model._dropout_masks = [m.to(dev) for m in masks]
+    got = [tr.train(x.to(dev), y.to(dev)) for _ in range(3)]
+    cfg_o = O.GwnetConfig(**{**cfg.to_dict(), "dropout": p})
+    otr = O.OracleTrainer(cfg_o, {k: v.clone() for k, v in rec["state0"].items()}, rec["supports"], 54.0, 20.0)
+    keep = [m.permute(0, 3, 2, 1).float() / (1 - p) for m in masks]                              # NCHW, scaled
+    want = [otr.train(x, y, keep_masks=keep) for _ in range(3)]
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            assert abs(a - b) <= 1e-4 * abs(b) + 1e-6, (got, want)
+    st = next(iter(tr._steps.values()))
+    assert st.graph is not None and st.masks is not None
+    for k, v in tr.model.state_dict().items():
+        assert_close_rel(v.float(), otr.state[k].detach().float(), 2e-3, "masked-dropout state after 3 steps " + k, floor=1e-5)
+
+
+def test_fused_adam_state_dict_round_trip(M, monkeypatch):
+    """optimizer.state_dict() / load_state_dict() carry the flat Adam moments and the step count: a trainer
+    resumed from a checkpoint after 2 steps continues exactly like the one that never stopped."""
+    dev = torch.device("cuda:0")
+    rec = load_case("dbl_adp")
+    cfg = rec["cfg"]
+    sup = [s.to(dev) for s in rec["supports"]]
+    x, y = rec["x"].to(dev), rec["y"][:, :, : cfg.out_dim].to(dev)
+    a = _make_trainer(dev, cfg, sup, rec["state0"], 0.0, True, True, monkeypatch)
+    for _ in range(2):
+        a.train(x, y)
+    ck_model = {k: v.detach().clone() for k, v in a.model.state_dict().items()}
+    ck_opt = a.optimizer.state_dict()
+    assert ck_opt["fused"]["step"] == 2
+    b = _make_trainer(dev, cfg, sup, ck_model, 0.0, True, True, monkeypatch)
+    b.optimizer.load_state_dict(ck_opt)          # before the optimizer is bound: applied at the first step
+    ma, mb = a.train(x, y), b.train(x, y)
+    assert b.optimizer.step_count() == 3
+    for u, v in zip(ma, mb):
+        assert abs(u - v) <= 1e-6 * abs(v) + 1e-7, (ma, mb)
+    for k, v in a.model.state_dict().items():
+        assert_close_rel(b.model.state_dict()[k].float(), v.float(), 1e-6, "resumed state " + k, floor=1e-7)
+    # zero_grad keeps p.grad as views of the flat buffer
+    b.optimizer.zero_grad()
+    g = b.model.start_conv.weight.grad
+    assert g is not None and float(g.abs().max()) == 0.0
+    b.train(x, y)
+    assert float(b.model.start_conv.weight.grad.abs().max()) > 0.0
+
+
+def test_trainer_train_syn_eval_syn_per_sample_graphs(M, monkeypatch):
+    """engine.py:64-117,132-180 on the per-sample-graph network: trainer(dict supports) -> gwnet_diff_G on the native plan,
+    F / E pooling and the loss as torch ops; against the same computation on the diff_G oracle (vectors of the real
+    reference pin that oracle) with torch autograd, clip and Adam."""
+    import numpy as np, os, types
+    from oracle import diffg_oracle as DO
+    from graph_wavenet_b200 import engine as E
+    from graph_wavenet_b200.metrics import StandardScaler, masked_mae, masked_mape, masked_rmse
+    dev = torch.device("cuda:0")
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "diffg.npz"))
+    rec = {k: torch.from_numpy(z[k]) if z[k].ndim > 0 else torch.tensor(z[k].item()) for k in z.files}
+    Nn, B = int(rec["cfg_N"]), rec["x"].shape[0]
+    x = rec["x"][:, :, :, 1:]                     # T = 48: the trainer pads to 49
+    sup_all = [rec["support.0"], rec["support.1"]]
+    monkeypatch.setenv("GWNET_B200_FUSED_STEP", "1")
+    torch.manual_seed(5)
+    tr = E.trainer(StandardScaler(3.0, 2.0), 2, 12, Nn, 32, 0.0, 1e-3, 1e-4, dev,
+                   {"train": [s.to(dev) for s in sup_all], "val": [s.to(dev) for s in sup_all]}, True, True,
+                   {"train": None, "val": None}, 4, 2)
+    state0 = {k: v.detach().cpu().clone() for k, v in tr.model.state_dict().items()}
+    F_t = 3
+    clusters = {0: list(range(0, 7)), 1: list(range(7, 12)), 2: list(range(12, Nn))}
+    G = [types.SimpleNamespace(assign_dict=clusters), types.SimpleNamespace(assign_dict={0: list(range(0, Nn, 2)), 1: list(range(1, Nn, 2))})]
+    adj_idx = torch.tensor([1, 0, 1, 0])          # sample -> graph; also indexes the per-sample supports
+    gen = torch.Generator().manual_seed(8)
+    real = torch.rand(B, 2, Nn, 12, generator=gen) * 5.0 + 1.0
+    tr.set_state("train")
+    torch.manual_seed(123)
+    got = tr.train_syn(x.to(dev), real.to(dev), F_t, G, adj_idx=adj_idx.to(dev))
+    # ---- the same step on the oracle
+    st = {k: v.clone() for k, v in state0.items()}
+    params = [k for k in st if not ("running" in k or "num_batches" in k)]
+    for k in params:
+        st[k].requires_grad_(True)
+    opt = torch.optim.Adam([st[k] for k in params], lr=1e-3, weight_decay=1e-4)
+    torch.manual_seed(123)
+    nv = DO.draw_node_embeddings(B, Nn)
+    out = DO.forward(st, torch.nn.functional.pad(x, (1, 0, 0, 0)), [s[adj_idx] for s in sup_all], nv, dropout=0.0, training=True)
+    predict = out.transpose(1, 3) * 2.0 + 3.0
+    Fp = predict.reshape(*predict.shape[:-1], -1, F_t).mean(-1)
+    Fp = Fp.unsqueeze(-1).repeat(*[1] * len(Fp.shape), F_t)
+    Fp = Fp.view(*Fp.shape[:-2], -1)
+    rows = []
+    for smp in range(B):                          # the reference's in-place cluster pooling (engine.py:98-105) on a copy
+        e = predict[smp:smp + 1].clone()
+        for k, idx in G[int(adj_idx[smp])].assign_dict.items():
+            e[:, :, idx, :] = e[:, :, idx, :].mean(2, keepdim=True).repeat(1, 1, len(idx), 1)
+        rows.append(e)
+    Ep = torch.cat(rows, 0)
+    loss = masked_mae(torch.cat((Fp, Ep), 1), real, 0.0)
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_([st[k] for k in params], 5)
+    opt.step()
+    want = (loss.item(), masked_mape(Ep, real, 0.0).item(), masked_rmse(Ep, real, 0.0).item())
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 1e-4 * abs(b) + 1e-6, (got, want)
+    for k, v in tr.model.state_dict().items():
+        assert_close_rel(v.float(), st[k].detach().float(), 2e-3, "train_syn state " + k, floor=1e-5)
+    tr.set_state("val")
+    torch.manual_seed(124)
+    ev = tr.eval_syn(x.to(dev), real.to(dev), F_t, G, adj_idx=adj_idx.to(dev))
+    assert len(ev) == 5 and tuple(ev[3].shape) == (B, 1, Nn, 12) and tuple(ev[4].shape) == (B, 1, Nn, 12)
+    assert all(v == v for v in ev[:3])

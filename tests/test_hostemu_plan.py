@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import __graft_entry__ as ge
-from helpers import CASES, load_case, sub, assert_close_rel
+from helpers import CASES, TRAINER_CASES, load_case, sub, assert_close_rel
 
 pkg = ge.load_package()
 from graph_wavenet_b200 import native as N          # noqa: E402
@@ -99,17 +99,20 @@ def test_emulated_dropout_mask_and_philox(emu):
     assert torch.equal(o1, o2) and not torch.equal(o1, o3)
 
 
-@pytest.mark.parametrize("name", ["dbl_adp", "aptonly"])
+@pytest.mark.parametrize("name", TRAINER_CASES)
 def test_emulated_fused_train_step_matches_reference_trainer(emu, name):
     """gwn_plan_train_fwd_bwd + gwn_adam_step (loss, metrics, clip, Adam as kernels) against 3 recorded
     ``engine.trainer.train`` steps of the real reference (metrics 1e-4, state 2e-3 -- see test_gpu_parity)."""
     import ctypes as C
     rec = load_case(name)
     cfg = rec["cfg"]
-    x = rec["x"]                                   # [B, F, N, 12]: the plan folds the trainer's +1 pad
+    # engine.py:44: the trainer left-pads by one zero column before gwnet.forward -- like fused.FusedStep, the plan is
+    # built for T+1 and reads the zero column from the input buffer (tr_long / tr_c32: T+1 > RF, so it is a real column)
+    x = torch.nn.functional.pad(rec["x"], (1, 0, 0, 0)).contiguous()
     y = rec["y"][:, :, : cfg.out_dim].contiguous()
     r = runner_for(emu, cfg, x.shape[0], x.shape[3])
     plan = r.plan
+    assert plan.t_out == max(x.shape[3], cfg.receptive_field) - cfg.receptive_field + 1
     n = plan.grad_floats
     flat, grad = torch.zeros(n), torch.zeros(n)
     m, v = torch.zeros(n), torch.zeros(n)

@@ -110,6 +110,12 @@ CASES = {
                      skip_channels=16, end_channels=32, out_dim=12), 2, 12, 16),
     "c32": (dict(num_nodes=15, dropout=0.0, n_static_supports=2, residual_channels=32, dilation_channels=32,
                  skip_channels=64, end_channels=64, out_dim=12, blocks=2, layers=2), 2, 12, 17),
+    # trainer-width cases (skip = 8 nhid, end = 16 nhid) whose input is LONGER than the receptive field (RF = 7): the
+    # trainer's +1 pad (engine.py:44) is then a real extra column and T_out = 13 - 7 + 1 = 7 (fused.py)
+    "tr_long": (dict(num_nodes=10, dropout=0.0, n_static_supports=2, residual_channels=8, dilation_channels=8,
+                     skip_channels=64, end_channels=128, out_dim=12, blocks=2, layers=2), 3, 12, 18),
+    "tr_c32": (dict(num_nodes=15, dropout=0.0, n_static_supports=2, residual_channels=32, dilation_channels=32,
+                    skip_channels=256, end_channels=512, out_dim=12, blocks=2, layers=2), 2, 12, 19),
 }
 
 
@@ -246,9 +252,11 @@ def main():
     torch.set_num_threads(os.cpu_count())
     os.makedirs(OUT, exist_ok=True)
     ref_model, ref_engine = load_reference()
-    for name in CASES:
+    only = sys.argv[1:]          # optional: case names to (re)generate; default = everything + the full-size report
+    for name in (only or CASES):
         make_case(name, ref_model, ref_engine)
-    fullsize_report(ref_model)
+    if not only:
+        fullsize_report(ref_model)
 
 
 if __name__ == "__main__":
