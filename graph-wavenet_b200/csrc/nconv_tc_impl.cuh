@@ -440,7 +440,23 @@ static int node_gemm_tc_impl(const NodeTcArgs& a, cudaStream_t stream) {
   return 0;
 }
 
+}  // namespace gwn
+
+#include "nconv_tc2.cuh"
+
+namespace gwn {
+
 int node_gemm_tc(const NodeTcArgs& a, cudaStream_t stream) {
+  // large graphs: CTA pairs (cta_group::2, nconv_tc2.cuh); GWNET_B200_NCONV_2CTA=0 keeps the one-CTA kernel (A/B runs)
+  static const bool two_cta = [] {
+    const char* e = getenv("GWNET_B200_NCONV_2CTA");
+    return !(e && e[0] == '0');
+  }();
+  if (two_cta && !a.per_sample && a.V > 256 && a.nsup >= 1 && a.nsup <= TC_MAXSUP && a.ld % 4 == 0 && a.ld >= a.V &&
+      (long long)a.B * a.L > 0) {
+    const int st = a.Slo[0] ? node_gemm_tc2_impl<true>(a, stream) : node_gemm_tc2_impl<false>(a, stream);
+    if (st >= 0) return st;
+  }
   return a.Slo[0] ? node_gemm_tc_impl<true>(a, stream) : node_gemm_tc_impl<false>(a, stream);
 }
 

@@ -673,8 +673,16 @@ def test_fused_adam_state_dict_round_trip(M, monkeypatch):
     assert b.optimizer.step_count() == 3
     for u, v in zip(ma, mb):
         assert abs(u - v) <= 1e-6 * abs(v) + 1e-7, (ma, mb)
+    # (BatchNorm sums use atomics: two runs differ in the last bits, which Adam amplifies for the mathematically-zero
+    # gradients of SURVEY G3 -- the same 2e-3 / 1e-5 as the other after-N-steps state comparisons; a run resumed WITHOUT
+    # its moments restarts the bias correction and moves every parameter by ~lr, three orders of magnitude more)
     for k, v in a.model.state_dict().items():
-        assert_close_rel(b.model.state_dict()[k].float(), v.float(), 1e-6, "resumed state " + k, floor=1e-7)
+        assert_close_rel(b.model.state_dict()[k].float(), v.float(), 2e-3, "resumed state " + k, floor=1e-5)
+    c = _make_trainer(dev, cfg, sup, ck_model, 0.0, True, True, monkeypatch)     # control: no optimizer state restored
+    c.train(x, y)
+    moved = sum(float((c.model.state_dict()[k].float() - v.float()).norm()) for k, v in a.model.state_dict().items())
+    kept = sum(float((b.model.state_dict()[k].float() - v.float()).norm()) for k, v in a.model.state_dict().items())
+    assert moved > 20 * kept, (moved, kept)
     # zero_grad keeps p.grad as views of the flat buffer
     b.optimizer.zero_grad()
     g = b.model.start_conv.weight.grad
