@@ -595,6 +595,17 @@ GWN_GLOBAL pack_e2t_kernel(const float* W2, float* WT, float* WT_lo, int O, int 
   }
 }
 // lo[i] = w[i] - tf32_trunc(w[i])
+// dst[e] = src[e] * dropout keep-scale of flat element e (n % 4 == 0): the gradient wrt a pre-dropout tensor
+GWN_GLOBAL apply_dropout_kernel(const float* src, float* dst, i64 n, DropoutSrc drop) {
+  GWN_PDL_ENTRY();
+  GWN_FOR_EACH(i4, n / 4) {
+    float kp[4];
+    drop.keep4(i4 * 4, kp);
+    const float4 v = ld4(src + i4 * 4);
+    st4(dst + i4 * 4, make_float4(v.x * kp[0], v.y * kp[1], v.z * kp[2], v.w * kp[3]));
+  }
+}
+
 GWN_GLOBAL split_lo_kernel(const float* w, float* lo, i64 n) {
   GWN_PDL_ENTRY();
   GWN_FOR_EACH(i, n) { lo[i] = tf32_lo(w[i]); }

@@ -1618,33 +1618,127 @@ int gwn_node_contract_x3(const float* x, const float* S, const float* S_lo, int6
   return node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, B, L, 0, V, C, (cudaStream_t)stream, &tcs);
 }
 
+// ---- tensor-core tiers of the stand-alone operators: operand preparation in the caller's workspace
+namespace gwn {
+static bool tc_tier(int precision) { return precision == GWN_PREC_TF32 || precision == GWN_PREC_FP32X3; }
+static i64 op_part_floats(int V) {   // partial-result slots of the tcgen05 reductions (as in build_plan)
+  const i64 ot = (i64)((V + 255) / 256) * ((V + 255) / 256);
+  return std::max<i64>(160, ot) * 512 * 128;
+}
+// Packed supports of one operator call: [set][support] matrices A (ld-padded) and A^T, then their 3xTF32 remainders.
+struct OpSupports {
+  float *Ap, *ATp, *lo;   // lo = remainders of [Ap | ATp] (fp32x3) or nullptr
+  i64 mat, span;          // floats per matrix, floats of Ap + ATp
+  int ld;
+};
+static i64 op_support_floats(int nsets, int nsup, int V, int precision) {
+  const i64 mat = align_up((i64)V * round_up(V, 4));
+  return (i64)nsets * nsup * mat * 2 * (precision == GWN_PREC_FP32X3 ? 2 : 1);
+}
+// supports[s]: [nsets][V][V] with sample stride lds_b[s] (ignored for nsets == 1) and row stride lds[s]
+static int op_pack_supports(float* ws, const float* const* supports, const int64_t* lds_b, const int64_t* lds, int nsets, int nsup,
+                            int V, int precision, cudaStream_t st, OpSupports* o) {
+  o->ld = round_up(V, 4);
+  o->mat = align_up((i64)V * o->ld);
+  o->span = (i64)nsets * nsup * o->mat * 2;
+  o->Ap = ws;
+  o->ATp = ws + (i64)nsets * nsup * o->mat;
+  o->lo = precision == GWN_PREC_FP32X3 ? ws + o->span : nullptr;
+  for (int s = 0; s < nsup; ++s)
+    for (int b = 0; b < nsets; ++b) {
+      const float* A = supports[s] + (nsets > 1 ? (i64)b * lds_b[s] : 0);
+      const i64 off = ((i64)s * nsets + b) * o->mat;
+      GWN_LAUNCH_1D(support_pack_kernel, (i64)V * o->ld, st, A, (i64)lds[s], (i64)1, o->Ap + off, o->ATp + off, V, o->ld);
+    }
+  if (o->lo) GWN_LAUNCH_1D(split_lo_kernel, o->span, st, (const float*)ws, o->lo, o->span);
+  return 0;
+}
+// forward = true: y[w] = sum_v A[v,w] x[v] (K-contiguous rows are those of A^T); false: dx[v] = sum_w A[v,w] dy[w]
+static TcSupports op_tc_supports(const OpSupports& o, int nsets, int nsup, bool forward, int precision) {
+  TcSupports t;
+  memset(&t, 0, sizeof(t));
+  for (int s = 0; s < nsup; ++s) {
+    const i64 off = (i64)s * nsets * o.mat;
+    t.S[s] = (forward ? o.ATp : o.Ap) + off;
+    if (o.lo) t.Slo[s] = o.lo + ((forward ? o.ATp : o.Ap) - o.Ap) + off;
+  }
+  t.ld = o.ld; t.precision = precision; t.per_sample = nsets > 1 ? 1 : 0; t.batch_stride = o.mat;
+  return t;
+}
+}  // namespace gwn
+
+size_t gwn_nconv_workspace_floats(int n_sets, int V, int precision, int support_grad) {
+  if (!tc_tier(precision) || V <= 0 || n_sets <= 0) return 0;
+  return (size_t)(op_support_floats(n_sets, 1, V, precision) + (support_grad ? op_part_floats(V) : 0));
+}
+
+static int nconv_tc_args_ok(const char* what, int C, int precision, const void* workspace) {
+  GWN_CHECK_ARG(precision == GWN_PREC_FP32 || tc_tier(precision), "%s: precision %d not available in this build", what, precision);
+  if (!tc_tier(precision)) return 0;
+  GWN_CHECK_ARG(C == 32, "%s: the tcgen05 tiers need 32 channels per node row (got %d); use GWN_PREC_FP32", what, C);
+  GWN_CHECK_ARG(workspace && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+                "%s: the tcgen05 tiers need a 16-byte aligned workspace of gwn_nconv_workspace_floats() floats", what);
+  return 0;
+}
+
 int gwn_nconv_fwd(const float* x, const float* A, int64_t lda, float* y, int B, int L, int V, int C, int precision,
-                  void* stream) {
+                  void* workspace, void* stream) {
   GWN_TRY(require_device());
   GWN_CHECK_ARG(x && A && y, "nconv_fwd: null pointer");
-  GWN_CHECK_ARG(precision == GWN_PREC_FP32, "nconv_fwd: precision %d not available in this build", precision);
+  GWN_TRY(nconv_tc_args_ok("nconv_fwd", C, precision, workspace));
+  cudaStream_t st = (cudaStream_t)stream;
   SupportView sv = support_fwd(A, lda, 1);
   const float* X[1] = {x};
   float* Y[1] = {y};
-  return node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, B, L, 0, V, C, (cudaStream_t)stream);
+  if (tc_tier(precision)) {
+    MathScope math_scope(math_of(precision));
+    OpSupports os;
+    const int64_t zero = 0;
+    GWN_TRY(op_pack_supports(reinterpret_cast<float*>(workspace), &A, &zero, &lda, 1, 1, V, precision, st, &os));
+    TcSupports tcs = op_tc_supports(os, 1, 1, true, precision);
+    return node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, B, L, 0, V, C, st, &tcs);
+  }
+  return node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, B, L, 0, V, C, st);
 }
 
 int gwn_nconv_bwd(const float* dy, const float* x, const float* A, int64_t lda, float* dx, float* dA, int64_t ldda, int B,
-                  int L, int V, int C, int precision, void* stream) {
+                  int L, int V, int C, int precision, void* workspace, void* stream) {
   GWN_TRY(require_device());
   GWN_CHECK_ARG(dy && A, "nconv_bwd: null pointer");
-  GWN_CHECK_ARG(precision == GWN_PREC_FP32, "nconv_bwd: precision %d not available in this build", precision);
+  GWN_TRY(nconv_tc_args_ok("nconv_bwd", C, precision, workspace));
+  GWN_CHECK_ARG(!dA || x, "nconv_bwd: x needed for dA");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tc_tier(precision)) {
+    MathScope math_scope(math_of(precision));
+    float* ws = reinterpret_cast<float*>(workspace);
+    OpSupports os;
+    const int64_t zero = 0;
+    GWN_TRY(op_pack_supports(ws, &A, &zero, &lda, 1, 1, V, precision, st, &os));
+    if (dx) {
+      TcSupports tcs = op_tc_supports(os, 1, 1, false, precision);
+      SupportView sv = support_bwd(A, lda, 1);
+      const float* X[1] = {dy};
+      float* Y[1] = {dx};
+      GWN_TRY(node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, B, L, 0, V, C, st, &tcs));
+    }
+    if (dA) {   // caller sized the workspace with support_grad = 1
+      TcScratch ts{ws + op_support_floats(1, 1, V, precision), op_part_floats(V), precision == GWN_PREC_FP32X3 ? 1 : 0};
+      const float* Xp[1] = {x};
+      const float* Yp[1] = {dy};
+      GWN_TRY(support_grad_gemm(Xp, Yp, 1, dA, ldda, B, L, V, C, st, &ts));
+    }
+    return 0;
+  }
   if (dx) {
     SupportView sv = support_bwd(A, lda, 1);
     const float* X[1] = {dy};
     float* Y[1] = {dx};
-    GWN_TRY(node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, B, L, 0, V, C, (cudaStream_t)stream));
+    GWN_TRY(node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, B, L, 0, V, C, st));
   }
   if (dA) {
-    GWN_CHECK_ARG(x != nullptr, "nconv_bwd: x needed for dA");
     const float* Xp[1] = {x};
     const float* Yp[1] = {dy};
-    GWN_TRY(support_grad_gemm(Xp, Yp, 1, dA, ldda, B, L, V, C, (cudaStream_t)stream));
+    GWN_TRY(support_grad_gemm(Xp, Yp, 1, dA, ldda, B, L, V, C, st));
   }
   return 0;
 }
@@ -1688,129 +1782,69 @@ static int gcn_check(const gwn_gcn_desc* d) {
   GWN_CHECK_ARG(d->n_supports >= 1 && d->n_supports <= MAXSUP && d->order >= 1 && d->order <= MAXSUP &&
                     1 + d->n_supports * d->order <= MAXSEG,
                 "gcn: bad support count / order");
-  GWN_CHECK_ARG(d->precision == GWN_PREC_FP32, "gcn: precision %d not available in this build", d->precision);
+  GWN_CHECK_ARG(d->precision == GWN_PREC_FP32 || tc_tier(d->precision), "gcn: precision %d not available in this build", d->precision);
+  GWN_CHECK_ARG(!tc_tier(d->precision) || (d->C == 32 && d->c_out == 32 && d->n_supports <= TC_MAXSUP && 1 + d->n_supports * d->order <= 7),
+                "gcn: the tcgen05 tiers need c_in = c_out = 32 and at most 7 concatenated segments; use GWN_PREC_FP32");
   GWN_CHECK_ARG(d->dropout_p >= 0.f && d->dropout_p < 1.f, "gcn: dropout must be in [0,1)");
   return 0;
 }
 
-int gwn_gcn_fwd(const gwn_gcn_desc* d, const float* x, const float* const* supports, const int64_t* lds, const float* W,
-                const float* bias, const uint8_t* keep_mask, float* hops, float* y, void* stream) {
-  GWN_TRY(require_device());
-  GWN_TRY(gcn_check(d));
-  GWN_CHECK_ARG(x && supports && lds && W && bias && hops && y, "gcn_fwd: null pointer");
-  GWN_CHECK_ARG(d->dropout_mode != GWN_DROPOUT_MASK || keep_mask, "gcn_fwd: GWN_DROPOUT_MASK without keep_mask");
-  cudaStream_t st = (cudaStream_t)stream;
-  GcnShape gs{d->B, d->L, d->V, d->C, d->c_out, d->n_supports, d->order};
-  SupportView sv[MAXSUP];
-  for (int s = 0; s < d->n_supports; ++s) sv[s] = support_fwd(supports[s], lds[s], 1);
-  GWN_TRY(gcn_hops_forward(gs, x, sv, hops, st));
-  const i64 P = (i64)d->B * d->L * d->V;
-  const int nseg = 1 + d->n_supports * d->order;
-  const float* segs[MAXSEG];
-  segs[0] = x;
-  for (int q = 1; q < nseg; ++q) segs[q] = hops + (i64)(q - 1) * P * d->C;
-  MlpFwdArgs m;
-  memset(&m, 0, sizeof(m));
-  m.segs = segs; m.nseg = nseg; m.P = P; m.D = d->C; m.C_out = d->c_out; m.W = W; m.bias = bias;
-  m.drop = make_dropout(d->dropout_mode, keep_mask, d->seed, d->offset, d->dropout_p);
-  m.y = y;
-  return mlp_forward(m, st);
+// Workspace layout of the gcn operators in the tensor-core tiers (floats):
+//   [packed supports (+ remainders)] [W_lo] [W^T] [W^T_lo] [dh * keep-mask (backward)] [reduction slots (backward)]
+namespace gwn {
+struct GcnOpWs {
+  i64 o_sup, o_wlo, o_wt, o_wtlo, o_dh, o_part, total;
+};
+static GcnOpWs gcn_op_ws(const gwn_gcn_desc* d, int nsets, bool backward) {
+  GcnOpWs w;
+  const i64 nw = align_up((i64)d->c_out * (1 + d->n_supports * d->order) * d->C);
+  i64 o = 0;
+  w.o_sup = o; o += op_support_floats(nsets, d->n_supports, d->V, d->precision);
+  w.o_wlo = o; o += nw;
+  w.o_wt = o; o += nw;
+  w.o_wtlo = o; o += nw;
+  w.o_dh = o; o += backward ? align_up((i64)d->B * d->L * d->V * d->c_out) : 0;
+  w.o_part = o; o += backward ? op_part_floats(d->V) : 0;
+  w.total = o;
+  return w;
 }
 
-size_t gwn_gcn_bwd_scratch_floats(const gwn_gcn_desc* d) {
-  if (!d) return 0;
-  return (size_t)(1 + d->n_supports * d->order) * d->B * d->L * d->V * d->C;
-}
-
-int gwn_gcn_bwd(const gwn_gcn_desc* d, const float* dy, const float* x, const float* const* supports, const int64_t* lds,
-                const float* W, const uint8_t* keep_mask, const float* hops, float* dx, float* dW, float* dbias,
-                float* const* dsupports, const int64_t* ldds, float* scratch, void* stream) {
-  GWN_TRY(require_device());
-  GWN_TRY(gcn_check(d));
-  GWN_CHECK_ARG(dy && x && supports && lds && W && hops && dx && scratch, "gcn_bwd: null pointer");
-  GWN_CHECK_ARG((dW == nullptr) == (dbias == nullptr), "gcn_bwd: dW and dbias must be given together");
-  cudaStream_t st = (cudaStream_t)stream;
-  GcnShape gs{d->B, d->L, d->V, d->C, d->c_out, d->n_supports, d->order};
-  const i64 P = (i64)d->B * d->L * d->V;
-  const int nseg = 1 + d->n_supports * d->order;
-  const float* segs[MAXSEG];
-  segs[0] = x;
-  for (int q = 1; q < nseg; ++q) segs[q] = hops + (i64)(q - 1) * P * d->C;
-  MlpBwdArgs m;
-  memset(&m, 0, sizeof(m));
-  m.dh = dy;
-  m.drop = make_dropout(d->dropout_mode, keep_mask, d->seed, d->offset, d->dropout_p);
-  m.segs = segs; m.nseg = nseg; m.P = P; m.D = d->C; m.C_out = d->c_out; m.W = W;
-  m.dsegs = scratch; m.dW = dW; m.dbias = dbias;
-  if (dW) {
-    GWN_TRY(dev_memset(dW, 0, sizeof(float) * (size_t)d->c_out * nseg * d->C, st));
-    GWN_TRY(dev_memset(dbias, 0, sizeof(float) * (size_t)d->c_out, st));
-  }
-  GWN_TRY(mlp_backward(m, st));
-  SupportView sv[MAXSUP];
-  i64 ldd[MAXSUP];
-  for (int s = 0; s < d->n_supports; ++s) {
-    sv[s] = support_bwd(supports[s], lds[s], 1);
-    ldd[s] = ldds ? ldds[s] : d->V;
-  }
-  return gcn_hops_backward(gs, x, hops, sv, scratch, dx, nullptr, 0, dsupports, ldd, st);
-}
-
-// ---- per-sample-graph operators (model.py:16-22, 57-80): one launch group per sample over the sample's slab
-int gwn_nconv2_fwd(const float* x, const float* A, int64_t lda_b, int64_t lda, float* y, int B, int L, int V, int C,
-                   int precision, void* stream) {
-  GWN_TRY(require_device());
-  GWN_CHECK_ARG(x && A && y, "nconv2_fwd: null pointer");
-  GWN_CHECK_ARG(precision == GWN_PREC_FP32, "nconv2_fwd: precision %d not available in this build", precision);
-  const i64 slab = (i64)L * V * C;
-  for (int b = 0; b < B; ++b) {
-    SupportView sv = support_fwd(A + (i64)b * lda_b, lda, 1);
-    const float* X[1] = {x + b * slab};
-    float* Y[1] = {y + b * slab};
-    GWN_TRY(node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, 1, L, 0, V, C, (cudaStream_t)stream));
-  }
-  return 0;
-}
-
-int gwn_nconv2_bwd(const float* dy, const float* x, const float* A, int64_t lda_b, int64_t lda, float* dx, float* dA,
-                   int64_t ldda_b, int64_t ldda, int B, int L, int V, int C, int precision, void* stream) {
-  GWN_TRY(require_device());
-  GWN_CHECK_ARG(dy && A, "nconv2_bwd: null pointer");
-  GWN_CHECK_ARG(precision == GWN_PREC_FP32, "nconv2_bwd: precision %d not available in this build", precision);
-  GWN_CHECK_ARG(!dA || x, "nconv2_bwd: x needed for dA");
-  const i64 slab = (i64)L * V * C;
-  for (int b = 0; b < B; ++b) {
-    if (dx) {
-      SupportView sv = support_bwd(A + (i64)b * lda_b, lda, 1);
-      const float* X[1] = {dy + b * slab};
-      float* Y[1] = {dx + b * slab};
-      GWN_TRY(node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, 1, L, 0, V, C, (cudaStream_t)stream));
-    }
-    if (dA) {
-      const float* Xp[1] = {x + b * slab};
-      const float* Yp[1] = {dy + b * slab};
-      GWN_TRY(support_grad_gemm(Xp, Yp, 1, dA + (i64)b * ldda_b, ldda, 1, L, V, C, (cudaStream_t)stream));
-    }
-  }
-  return 0;
-}
-
-int gwn_gcn2_fwd(const gwn_gcn_desc* d, const float* x, const float* const* supports, const int64_t* lds_b, const int64_t* lds,
-                 const float* W, const float* bias, const uint8_t* keep_mask, float* hops, float* y, void* stream) {
-  GWN_TRY(require_device());
-  GWN_TRY(gcn_check(d));
-  GWN_CHECK_ARG(x && supports && lds && lds_b && W && bias && hops && y, "gcn2_fwd: null pointer");
-  GWN_CHECK_ARG(d->dropout_mode != GWN_DROPOUT_MASK || keep_mask, "gcn2_fwd: GWN_DROPOUT_MASK without keep_mask");
-  cudaStream_t st = (cudaStream_t)stream;
+// nsets = 1: supports shared by all samples (gcn); nsets = B: one set per sample (gcn2)
+static int gcn_op_fwd(const gwn_gcn_desc* d, int nsets, const float* x, const float* const* supports, const int64_t* lds_b,
+                      const int64_t* lds, const float* W, const float* bias, const uint8_t* keep_mask, float* hops, float* y,
+                      void* workspace, cudaStream_t st) {
+  MathScope math_scope(math_of(d->precision));
+  const bool tc = tc_tier(d->precision);
+  GWN_CHECK_ARG(!tc || (workspace && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0),
+                "gcn_fwd: the tcgen05 tiers need a 16-byte aligned workspace of gwn_gcn_workspace_floats() floats");
   const i64 slab = (i64)d->L * d->V * d->C, PD = (i64)d->B * slab;
-  GcnShape g1{1, d->L, d->V, d->C, d->c_out, d->n_supports, d->order};
-  for (int b = 0; b < d->B; ++b) {
+  const i64 P = (i64)d->B * d->L * d->V;
+  const int nseg = 1 + d->n_supports * d->order;
+  float* ws = reinterpret_cast<float*>(workspace);
+  const GcnOpWs w = gcn_op_ws(d, nsets, false);
+  if (tc) {
+    OpSupports os;
+    GWN_TRY(op_pack_supports(ws + w.o_sup, supports, lds_b, lds, nsets, d->n_supports, d->V, d->precision, st, &os));
+    TcSupports tcs = op_tc_supports(os, nsets, d->n_supports, true, d->precision);
+    GcnShape gs{d->B, d->L, d->V, d->C, d->c_out, d->n_supports, d->order};
     SupportView sv[MAXSUP];
-    for (int s = 0; s < d->n_supports; ++s) sv[s] = support_fwd(supports[s] + (i64)b * lds_b[s], lds[s], 1);
-    GWN_TRY(gcn_hops_forward(g1, x + b * slab, sv, hops + b * slab, st, nullptr, PD));
+    for (int s = 0; s < d->n_supports; ++s) sv[s] = support_fwd(supports[s], lds[s], 1);
+    GWN_TRY(gcn_hops_forward(gs, x, sv, hops, st, &tcs));
+    if (d->precision == GWN_PREC_FP32X3)
+      GWN_LAUNCH_1D(split_lo_kernel, (i64)d->c_out * nseg * d->C, st, W, ws + w.o_wlo, (i64)d->c_out * nseg * d->C);
+  } else if (nsets == 1) {
+    GcnShape gs{d->B, d->L, d->V, d->C, d->c_out, d->n_supports, d->order};
+    SupportView sv[MAXSUP];
+    for (int s = 0; s < d->n_supports; ++s) sv[s] = support_fwd(supports[s], lds[s], 1);
+    GWN_TRY(gcn_hops_forward(gs, x, sv, hops, st));
+  } else {   // fp32 tier, per-sample graphs: one launch group per sample over the sample's slab
+    GcnShape g1{1, d->L, d->V, d->C, d->c_out, d->n_supports, d->order};
+    for (int b = 0; b < d->B; ++b) {
+      SupportView sv[MAXSUP];
+      for (int s = 0; s < d->n_supports; ++s) sv[s] = support_fwd(supports[s] + (i64)b * lds_b[s], lds[s], 1);
+      GWN_TRY(gcn_hops_forward(g1, x + b * slab, sv, hops + b * slab, st, nullptr, PD));
+    }
   }
-  const i64 P = (i64)d->B * d->L * d->V;
-  const int nseg = 1 + d->n_supports * d->order;
   const float* segs[MAXSEG];
   segs[0] = x;
   for (int q = 1; q < nseg; ++q) segs[q] = hops + (i64)(q - 1) * P * d->C;
@@ -1819,36 +1853,89 @@ int gwn_gcn2_fwd(const gwn_gcn_desc* d, const float* x, const float* const* supp
   m.segs = segs; m.nseg = nseg; m.P = P; m.D = d->C; m.C_out = d->c_out; m.W = W; m.bias = bias;
   m.drop = make_dropout(d->dropout_mode, keep_mask, d->seed, d->offset, d->dropout_p);
   m.y = y;
+  if (tc) {
+    m.tf32_tc = 1;
+    if (d->precision == GWN_PREC_FP32X3) m.W_lo = ws + w.o_wlo;
+  }
   return mlp_forward(m, st);
 }
 
-int gwn_gcn2_bwd(const gwn_gcn_desc* d, const float* dy, const float* x, const float* const* supports, const int64_t* lds_b,
-                 const int64_t* lds, const float* W, const uint8_t* keep_mask, const float* hops, float* dx, float* dW,
-                 float* dbias, float* const* dsupports, const int64_t* ldds_b, const int64_t* ldds, float* scratch,
-                 void* stream) {
-  GWN_TRY(require_device());
-  GWN_TRY(gcn_check(d));
-  GWN_CHECK_ARG(dy && x && supports && lds && lds_b && W && hops && dx && scratch, "gcn2_bwd: null pointer");
-  GWN_CHECK_ARG((dW == nullptr) == (dbias == nullptr), "gcn2_bwd: dW and dbias must be given together");
-  GWN_CHECK_ARG(!dsupports || (ldds_b && ldds), "gcn2_bwd: support-gradient strides missing");
-  cudaStream_t st = (cudaStream_t)stream;
+static int gcn_op_bwd(const gwn_gcn_desc* d, int nsets, const float* dy, const float* x, const float* const* supports,
+                      const int64_t* lds_b, const int64_t* lds, const float* W, const uint8_t* keep_mask, const float* hops,
+                      float* dx, float* dW, float* dbias, float* const* dsupports, const int64_t* ldds_b, const int64_t* ldds,
+                      float* scratch, cudaStream_t st) {
+  MathScope math_scope(math_of(d->precision));
+  const bool tc = tc_tier(d->precision);
   const i64 slab = (i64)d->L * d->V * d->C, PD = (i64)d->B * slab;
   const i64 P = (i64)d->B * d->L * d->V;
   const int nseg = 1 + d->n_supports * d->order;
   const float* segs[MAXSEG];
   segs[0] = x;
   for (int q = 1; q < nseg; ++q) segs[q] = hops + (i64)(q - 1) * P * d->C;
+  // scratch: [nseg][P][C] segment gradients, then (tensor-core tiers) the operator workspace
+  float* ws = scratch + (i64)nseg * P * d->C;
+  const GcnOpWs w = gcn_op_ws(d, nsets, true);
   MlpBwdArgs m;
   memset(&m, 0, sizeof(m));
   m.dh = dy;
   m.drop = make_dropout(d->dropout_mode, keep_mask, d->seed, d->offset, d->dropout_p);
   m.segs = segs; m.nseg = nseg; m.P = P; m.D = d->C; m.C_out = d->c_out; m.W = W;
   m.dsegs = scratch; m.dW = dW; m.dbias = dbias;
+  OpSupports os;
+  TcScratch tsc{nullptr, 0, 0};
+  if (tc) {
+    GWN_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "gcn_bwd: scratch must be 16-byte aligned");
+    GWN_TRY(op_pack_supports(ws + w.o_sup, supports, lds_b, lds, nsets, d->n_supports, d->V, d->precision, st, &os));
+    const bool x3_ = d->precision == GWN_PREC_FP32X3;
+    GWN_LAUNCH_1D(transpose_kernel, (i64)d->c_out * nseg * d->C, st, W, ws + w.o_wt, d->c_out, nseg * d->C,
+                  x3_ ? ws + w.o_wtlo : (float*)nullptr);
+    m.WT = ws + w.o_wt;
+    if (x3_) m.WT_lo = ws + w.o_wtlo;
+    tsc = TcScratch{ws + w.o_part, op_part_floats(d->V), x3_ ? 1 : 0};
+    m.ts = tsc;
+    if (m.drop.mode != GWN_DROPOUT_NONE) {   // dh = dy * keep / (1 - p) once, so that the tcgen05 kernels see a plain operand
+      GWN_LAUNCH_1D(apply_dropout_kernel, P * d->c_out, st, dy, ws + w.o_dh, P * d->c_out, m.drop);
+      m.dh = ws + w.o_dh;
+      m.drop = make_dropout(GWN_DROPOUT_NONE, nullptr, 0, 0, 0.f);
+    }
+  }
   if (dW) {
     GWN_TRY(dev_memset(dW, 0, sizeof(float) * (size_t)d->c_out * nseg * d->C, st));
     GWN_TRY(dev_memset(dbias, 0, sizeof(float) * (size_t)d->c_out, st));
   }
   GWN_TRY(mlp_backward(m, st));
+  if (tc || nsets == 1) {
+    GcnShape gs{d->B, d->L, d->V, d->C, d->c_out, d->n_supports, d->order};
+    SupportView sv[MAXSUP];
+    float* dsup[MAXSUP];
+    i64 ldd[MAXSUP];
+    for (int s = 0; s < d->n_supports; ++s) {
+      sv[s] = support_bwd(supports[s], lds[s], 1);
+      dsup[s] = (dsupports && nsets == 1) ? dsupports[s] : nullptr;
+      ldd[s] = ldds ? ldds[s] : d->V;
+    }
+    if (tc) {
+      TcSupports tcs = op_tc_supports(os, nsets, d->n_supports, false, d->precision);
+      GWN_TRY(gcn_hops_backward(gs, x, hops, sv, scratch, dx, nullptr, 0, dsup, ldd, st, &tcs, &tsc));
+      if (nsets > 1 && dsupports) {   // per-sample support gradients: one tcgen05 reduction per (sample, support)
+        GWN_CHECK_ARG(d->order <= MAXSUP, "gcn2 bwd: order too large");
+        for (int s = 0; s < d->n_supports; ++s) {
+          if (!dsupports[s]) continue;
+          for (int b = 0; b < d->B; ++b) {
+            const float* Xp[MAXSUP];
+            const float* Yp[MAXSUP];
+            for (int k = 1; k <= d->order; ++k) {
+              Xp[k - 1] = ((k == 1) ? x : hops + (i64)(hop_index(gs, s, k - 1) - 1) * PD) + b * slab;
+              Yp[k - 1] = scratch + (i64)hop_index(gs, s, k) * PD + b * slab;
+            }
+            GWN_TRY(support_grad_gemm(Xp, Yp, d->order, dsupports[s] + (i64)b * ldds_b[s], ldd[s], 1, d->L, d->V, d->C, st, &tsc));
+          }
+        }
+      }
+      return 0;
+    }
+    return gcn_hops_backward(gs, x, hops, sv, scratch, dx, nullptr, 0, dsup, ldd, st);
+  }
   GcnShape g1{1, d->L, d->V, d->C, d->c_out, d->n_supports, d->order};
   for (int b = 0; b < d->B; ++b) {
     SupportView sv[MAXSUP];
@@ -1863,6 +1950,136 @@ int gwn_gcn2_bwd(const gwn_gcn_desc* d, const float* dy, const float* x, const f
                               st, nullptr, nullptr, PD));
   }
   return 0;
+}
+}  // namespace gwn
+
+size_t gwn_gcn_workspace_floats(const gwn_gcn_desc* d, int per_sample_supports) {
+  if (!d || !tc_tier(d->precision)) return 0;
+  return (size_t)gcn_op_ws(d, per_sample_supports ? d->B : 1, false).total;
+}
+
+int gwn_gcn_fwd(const gwn_gcn_desc* d, const float* x, const float* const* supports, const int64_t* lds, const float* W,
+                const float* bias, const uint8_t* keep_mask, float* hops, float* y, void* workspace, void* stream) {
+  GWN_TRY(require_device());
+  GWN_TRY(gcn_check(d));
+  GWN_CHECK_ARG(x && supports && lds && W && bias && hops && y, "gcn_fwd: null pointer");
+  GWN_CHECK_ARG(d->dropout_mode != GWN_DROPOUT_MASK || keep_mask, "gcn_fwd: GWN_DROPOUT_MASK without keep_mask");
+  return gcn_op_fwd(d, 1, x, supports, lds, lds, W, bias, keep_mask, hops, y, workspace, (cudaStream_t)stream);
+}
+
+size_t gwn_gcn_bwd_scratch_floats(const gwn_gcn_desc* d) {
+  if (!d) return 0;
+  const size_t segs = (size_t)(1 + d->n_supports * d->order) * d->B * d->L * d->V * d->C;
+  if (!tc_tier(d->precision)) return segs;
+  return segs + (size_t)gcn_op_ws(d, d->B, true).total;   // sized for per-sample supports too (gwn_gcn2_bwd)
+}
+
+int gwn_gcn_bwd(const gwn_gcn_desc* d, const float* dy, const float* x, const float* const* supports, const int64_t* lds,
+                const float* W, const uint8_t* keep_mask, const float* hops, float* dx, float* dW, float* dbias,
+                float* const* dsupports, const int64_t* ldds, float* scratch, void* stream) {
+  GWN_TRY(require_device());
+  GWN_TRY(gcn_check(d));
+  GWN_CHECK_ARG(dy && x && supports && lds && W && hops && dx && scratch, "gcn_bwd: null pointer");
+  GWN_CHECK_ARG((dW == nullptr) == (dbias == nullptr), "gcn_bwd: dW and dbias must be given together");
+  return gcn_op_bwd(d, 1, dy, x, supports, lds, lds, W, keep_mask, hops, dx, dW, dbias, dsupports, ldds, ldds, scratch,
+                    (cudaStream_t)stream);
+}
+
+// ---- per-sample-graph operators (model.py:16-22, 57-80).  fp32 tier: one launch group per sample over the sample's
+// slab; tensor-core tiers: all samples' graphs in one launch (batched tensor maps of nconv_tc_kernel)
+int gwn_nconv2_fwd(const float* x, const float* A, int64_t lda_b, int64_t lda, float* y, int B, int L, int V, int C,
+                   int precision, void* workspace, void* stream) {
+  GWN_TRY(require_device());
+  GWN_CHECK_ARG(x && A && y, "nconv2_fwd: null pointer");
+  GWN_TRY(nconv_tc_args_ok("nconv2_fwd", C, precision, workspace));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tc_tier(precision)) {
+    MathScope math_scope(math_of(precision));
+    OpSupports os;
+    GWN_TRY(op_pack_supports(reinterpret_cast<float*>(workspace), &A, &lda_b, &lda, B, 1, V, precision, st, &os));
+    TcSupports tcs = op_tc_supports(os, B, 1, true, precision);
+    SupportView sv = support_fwd(A, lda, 1);
+    const float* X[1] = {x};
+    float* Y[1] = {y};
+    return node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, B, L, 0, V, C, st, &tcs);
+  }
+  const i64 slab = (i64)L * V * C;
+  for (int b = 0; b < B; ++b) {
+    SupportView sv = support_fwd(A + (i64)b * lda_b, lda, 1);
+    const float* X[1] = {x + b * slab};
+    float* Y[1] = {y + b * slab};
+    GWN_TRY(node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, 1, L, 0, V, C, st));
+  }
+  return 0;
+}
+
+int gwn_nconv2_bwd(const float* dy, const float* x, const float* A, int64_t lda_b, int64_t lda, float* dx, float* dA,
+                   int64_t ldda_b, int64_t ldda, int B, int L, int V, int C, int precision, void* workspace, void* stream) {
+  GWN_TRY(require_device());
+  GWN_CHECK_ARG(dy && A, "nconv2_bwd: null pointer");
+  GWN_TRY(nconv_tc_args_ok("nconv2_bwd", C, precision, workspace));
+  GWN_CHECK_ARG(!dA || x, "nconv2_bwd: x needed for dA");
+  cudaStream_t st = (cudaStream_t)stream;
+  const i64 slab = (i64)L * V * C;
+  if (tc_tier(precision)) {
+    MathScope math_scope(math_of(precision));
+    float* ws = reinterpret_cast<float*>(workspace);
+    OpSupports os;
+    GWN_TRY(op_pack_supports(ws, &A, &lda_b, &lda, B, 1, V, precision, st, &os));
+    if (dx) {
+      TcSupports tcs = op_tc_supports(os, B, 1, false, precision);
+      SupportView sv = support_bwd(A, lda, 1);
+      const float* X[1] = {dy};
+      float* Y[1] = {dx};
+      GWN_TRY(node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, B, L, 0, V, C, st, &tcs));
+    }
+    if (dA) {
+      TcScratch ts{ws + op_support_floats(B, 1, V, precision), op_part_floats(V), precision == GWN_PREC_FP32X3 ? 1 : 0};
+      for (int b = 0; b < B; ++b) {
+        const float* Xp[1] = {x + b * slab};
+        const float* Yp[1] = {dy + b * slab};
+        GWN_TRY(support_grad_gemm(Xp, Yp, 1, dA + (i64)b * ldda_b, ldda, 1, L, V, C, st, &ts));
+      }
+    }
+    return 0;
+  }
+  for (int b = 0; b < B; ++b) {
+    if (dx) {
+      SupportView sv = support_bwd(A + (i64)b * lda_b, lda, 1);
+      const float* X[1] = {dy + b * slab};
+      float* Y[1] = {dx + b * slab};
+      GWN_TRY(node_gemm(&sv, 1, false, X, Y, nullptr, nullptr, 1, L, 0, V, C, st));
+    }
+    if (dA) {
+      const float* Xp[1] = {x + b * slab};
+      const float* Yp[1] = {dy + b * slab};
+      GWN_TRY(support_grad_gemm(Xp, Yp, 1, dA + (i64)b * ldda_b, ldda, 1, L, V, C, st));
+    }
+  }
+  return 0;
+}
+
+int gwn_gcn2_fwd(const gwn_gcn_desc* d, const float* x, const float* const* supports, const int64_t* lds_b, const int64_t* lds,
+                 const float* W, const float* bias, const uint8_t* keep_mask, float* hops, float* y, void* workspace,
+                 void* stream) {
+  GWN_TRY(require_device());
+  GWN_TRY(gcn_check(d));
+  GWN_CHECK_ARG(x && supports && lds && lds_b && W && bias && hops && y, "gcn2_fwd: null pointer");
+  GWN_CHECK_ARG(d->dropout_mode != GWN_DROPOUT_MASK || keep_mask, "gcn2_fwd: GWN_DROPOUT_MASK without keep_mask");
+  return gcn_op_fwd(d, d->B, x, supports, lds_b, lds, W, bias, keep_mask, hops, y, workspace, (cudaStream_t)stream);
+}
+
+int gwn_gcn2_bwd(const gwn_gcn_desc* d, const float* dy, const float* x, const float* const* supports, const int64_t* lds_b,
+                 const int64_t* lds, const float* W, const uint8_t* keep_mask, const float* hops, float* dx, float* dW,
+                 float* dbias, float* const* dsupports, const int64_t* ldds_b, const int64_t* ldds, float* scratch,
+                 void* stream) {
+  GWN_TRY(require_device());
+  GWN_TRY(gcn_check(d));
+  GWN_CHECK_ARG(dy && x && supports && lds && lds_b && W && hops && dx && scratch, "gcn2_bwd: null pointer");
+  GWN_CHECK_ARG((dW == nullptr) == (dbias == nullptr), "gcn2_bwd: dW and dbias must be given together");
+  GWN_CHECK_ARG(!dsupports || (ldds_b && ldds), "gcn2_bwd: support-gradient strides missing");
+  return gcn_op_bwd(d, d->B, dy, x, supports, lds_b, lds, W, keep_mask, hops, dx, dW, dbias, dsupports, ldds_b, ldds, scratch,
+                    (cudaStream_t)stream);
 }
 
 int gwn_plan_create(const gwn_config* cfg, gwn_plan** out) {

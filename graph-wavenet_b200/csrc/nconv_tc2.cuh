@@ -1,4 +1,5 @@
-// Node contraction for LARGE graphs (V > 256) on CTA pairs: tcgen05.mma.cta_group::2 (model.py:13 and its autograd).
+// Node contraction on CTA pairs: tcgen05.mma.cta_group::2 (model.py:13 and its autograd).  Written for large graphs
+// (V > 256, column tiles of 256 nodes); small graphs (V <= 256) use it with 1-4 narrower column tiles.
 //
 //   D[j, m] = sum_s sum_k X_s[k, j] * S_s[m, k]          j = (slab, channel) row, m = output node
 //
@@ -15,10 +16,10 @@
 //   full[s]   L  1 arrival + tx bytes: the leader's producer arms it for BOTH CTAs' bytes, every TMA of either CTA
 //                (cp.async.bulk.tensor ... .cta_group::2) completes on it
 //   xfull[s]  E  3xTF32 mode only: the CTA's own X tile landed (its splitter warps wait on it)
-//   split[s]  L  3xTF32 mode only: 128 arrivals = 64 splitter threads per CTA, after X_lo is written and fenced
+//   split[s]  L  3xTF32 mode only: 2 arrivals = one per CTA, after its 64 splitter threads have written and fenced X_lo
 //   empty[s]  E  tcgen05.commit.cta_group::2 ... multicast -> both CTAs: the MMAs reading stage s have completed
 //   tfull[a]  E  commit multicast: accumulator a is complete in both CTAs' tensor memory
-//   tempty[a] L  256 arrivals = the 128 epilogue threads of each CTA have drained accumulator a
+//   tempty[a] L  8 arrivals = the 4 epilogue warps of each CTA have drained accumulator a
 #pragma once
 #include "nconv_tc.cuh"
 #include "tc_common.cuh"
@@ -34,11 +35,9 @@ using tc::tc_ld16; using tc::tc_wait_ld; using tc::make_desc;
 
 constexpr int SLABS = 4, CH = 32, BLOCK_K = 32, UMMA_K = 8;
 constexpr int X_BYTES = SLABS * BLOCK_K * CH * 4;   // 16 KB: this CTA's 128 rows of the A operand, one k-block
-constexpr int S_ROWS = 128;                         // this CTA's half of the 256-column B tile
-constexpr int S_BYTES = S_ROWS * BLOCK_K * 4;       // 16 KB
-constexpr int N_TILE = 256;
+constexpr int ACC_COLS = 256;                       // TMEM columns per accumulator buffer (2 buffers)
 constexpr int NUM_THREADS = 256;
-constexpr int MAXSTAGES = 6;
+constexpr int MAXSTAGES = 8;
 
 struct Maps {
   CUtensorMap x[TC_MAXSUP];
@@ -52,6 +51,7 @@ struct Params {
   const float* add2;
   int nsup, kcat, V, L, T_out, nslabs;
   int n_wt, n_jt, nkb, stages, total_tiles;
+  int n_tile;    // output nodes per tile (MMA N, multiple of 16, <= 256); each CTA stages n_tile / 2 support rows
 };
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -66,6 +66,11 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t ran
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// No ordering of the caller's earlier global stores is needed (the consumer only re-uses tensor memory that was read
+// with tcgen05.ld + wait::ld before): a release at cluster scope would wait for those stores to drain.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");   // default: release at CTA scope
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -108,7 +113,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) ncon
   uint8_t* smem = smem_raw + (base - raw);
   constexpr int NPL = X3 ? 2 : 1;
   constexpr int XB = NPL * X_BYTES;
-  constexpr int STAGE = NPL * (X_BYTES + S_BYTES);
+  const int N_TILE = p.n_tile, S_ROWS = N_TILE >> 1;   // this CTA's half of the B tile
+  const int S_BYTES = S_ROWS * BLOCK_K * 4;
+  const int STAGE = NPL * (X_BYTES + S_BYTES);
   const int stages = p.stages;
   const uint32_t bar0 = base + stages * STAGE;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -135,11 +142,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) ncon
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
       mbar_init(xfull_bar(s), 1);
-      mbar_init(split_bar(s), 128);
+      mbar_init(split_bar(s), 2);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 256);
+      mbar_init(tempty_bar(a), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -192,14 +199,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) ncon
   } else if (warp == 1 && leader) {
     // ===================================================== MMA issuer (leader CTA only): M = 256 over the pair, N = 256
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(N_TILE >> 3) << 17) |
-                           ((uint32_t)(256 >> 4) << 24);
+                           ((uint32_t)(256 >> 4) << 24);   // M = 256: 128 rows in each CTA's tensor memory
     int stage = 0, acc = 0;
     uint32_t phase = 0, accphase = 0;
     bool ok = true;
     for (int tile = cl; tile < p.total_tiles && ok; tile += ncl) {
       if (!mbar_wait_warp(tempty_bar(acc), accphase ^ 1u, 2)) break;
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
       const int nk_total = (p.kcat ? p.nsup : 1) * p.nkb;
       for (int it = 0; it < nk_total; ++it) {
         if (!mbar_wait_warp(full_bar(stage), phase, 3)) { ok = false; break; }
@@ -249,7 +256,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) ncon
         for (int u = 0; u < 16; ++u)
           dst[t64 + 64 * u] = make_float4(tf32_lo(v[u].x), tf32_lo(v[u].y), tf32_lo(v[u].z), tf32_lo(v[u].w));
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive_cluster(map_to_cta(split_bar(stage), 0));
+        asm volatile("bar.sync 1, 64;" ::: "memory");     // the 64 splitter threads; then ONE release-arrive per CTA
+        if (t64 == 0) mbar_arrive_cluster(map_to_cta(split_bar(stage), 0));
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -273,7 +281,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) ncon
         const int b = slab / p.L, l = slab - b * p.L;
         if (l >= p.L - p.T_out) ad2 = p.add2 + ((size_t)(b * p.T_out + (l - (p.L - p.T_out))) * p.V) * CH + lane;
       }
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * N_TILE);
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * ACC_COLS);
       const int w_base = wt * N_TILE;
       const bool has_ad = slab_ok && ad != nullptr, has_ad2 = slab_ok && ad2 != nullptr;   // warp-uniform
       constexpr int GC = 64;
@@ -292,20 +300,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) ncon
         }
 #pragma unroll
         for (int cc = 0; cc < GC; cc += 16) {
-          uint32_t r[16];
-          tc_ld16(taddr + g0 + cc, r);
-          tc_wait_ld();
-          if (slab_ok) {
+          if (g0 + cc < N_TILE) {   // warp-uniform
+            uint32_t r[16];
+            tc_ld16(taddr + g0 + cc, r);
+            tc_wait_ld();
+            if (slab_ok) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int w = w_base + g0 + cc + j;
-              if (w < p.V) y[(size_t)w * CH] = __uint_as_float(r[j]) + av[cc + j];
+              for (int j = 0; j < 16; ++j) {
+                const int w = w_base + g0 + cc + j;
+                if (w < p.V) y[(size_t)w * CH] = __uint_as_float(r[j]) + av[cc + j];
+              }
             }
           }
         }
       }
       tc_fence_before();
-      mbar_arrive_cluster(map_to_cta(tempty_bar(acc), 0));
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(map_to_cta(tempty_bar(acc), 0));
       acc ^= 1;
       if (acc == 0) accphase ^= 1u;
     }
@@ -321,7 +332,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) ncon
 
 }  // namespace tc2
 
-// Eligible: batched or K-concatenated supports shared by all samples, V > 256.  Returns -1 when not eligible.
+// Eligible: batched or K-concatenated supports shared by all samples.  Returns -1 when not eligible.
 template <bool X3>
 static int node_gemm_tc2_impl(const NodeTcArgs& a, cudaStream_t stream) {
   using namespace tc2;
@@ -331,9 +342,32 @@ static int node_gemm_tc2_impl(const NodeTcArgs& a, cudaStream_t stream) {
   memset(&p, 0, sizeof(p));
   p.nsup = a.nsup; p.kcat = a.kcat; p.V = a.V; p.L = a.L; p.T_out = a.T_out; p.nslabs = (int)nslabs;
   p.n_jt = (int)((nslabs + 2 * SLABS - 1) / (2 * SLABS));
-  p.n_wt = (a.V + N_TILE - 1) / N_TILE;
   p.nkb = (a.V + BLOCK_K - 1) / BLOCK_K;
   const int nout = a.kcat ? 1 : a.nsup;
+  const int n_clusters = (tc_num_sms() & ~1) / 2;
+  p.n_tile = 256;
+  if (a.V <= 256) {
+    // Small graphs: 8-slab row tiles alone are coarse against 74 clusters (METR-LA, K-concatenated dX sum at L = 12:
+    // 96 tiles = 1.3 rounds).  Splitting the output columns multiplies the tile count at the price of narrower (per
+    // column more expensive) MMAs; pick the split with the smallest modelled makespan, as the one-CTA kernel does.
+    static const int forced = [] {
+      const char* e = getenv("GWNET_B200_NCONV2_NWT");
+      return e ? atoi(e) : 0;
+    }();
+    const int nk_total = (a.kcat ? a.nsup : 1) * p.nkb;
+    long long best = -1;
+    for (int nw = 1; nw <= 4; ++nw) {
+      if (forced > 0 && nw != forced) continue;
+      const int nt = round_up((a.V + nw - 1) / nw, 16);
+      const int nwe = (a.V + nt - 1) / nt;
+      const long long tiles_ = (long long)p.n_jt * nwe * nout;
+      const long long rounds = (tiles_ + n_clusters - 1) / n_clusters;
+      const long long cost = rounds * ((long long)nk_total * ((nt < 64 ? 64 : nt) + 48) + 400);
+      if (best < 0 || cost < best) { best = cost; p.n_tile = nt; }
+    }
+  }
+  p.n_wt = (a.V + p.n_tile - 1) / p.n_tile;
+  const int S_BYTES = (p.n_tile / 2) * BLOCK_K * 4;
   const int stage_bytes = (X3 ? 2 : 1) * (X_BYTES + S_BYTES);
   p.stages = (tc::SMEM_LIMIT - 2048) / stage_bytes;
   if (p.stages > MAXSTAGES) p.stages = MAXSTAGES;
@@ -351,7 +385,7 @@ static int node_gemm_tc2_impl(const NodeTcArgs& a, cudaStream_t stream) {
     GWN_TRY(tc::encode(&maps.x[s], a.X[s], 3, xd, xs, xb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     cuuint64_t sd[2] = {(cuuint64_t)a.V, (cuuint64_t)a.V};
     cuuint64_t ss[1] = {(cuuint64_t)a.ld * 4};
-    cuuint32_t sb[2] = {BLOCK_K, S_ROWS};
+    cuuint32_t sb[2] = {BLOCK_K, (cuuint32_t)(p.n_tile / 2)};
     GWN_TRY(tc::encode(&maps.s[s], a.S[s], 2, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_128B));
     if (X3) {
       if (!a.Slo[s] || (reinterpret_cast<uintptr_t>(a.Slo[s]) & 15)) {

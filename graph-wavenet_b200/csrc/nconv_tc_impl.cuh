@@ -452,7 +452,14 @@ int node_gemm_tc(const NodeTcArgs& a, cudaStream_t stream) {
     const char* e = getenv("GWNET_B200_NCONV_2CTA");
     return !(e && e[0] == '0');
   }();
-  if (two_cta && !a.per_sample && a.V > 256 && a.nsup >= 1 && a.nsup <= TC_MAXSUP && a.ld % 4 == 0 && a.ld >= a.V &&
+  // Smallest graph that takes the CTA-pair kernel (GWNET_B200_NCONV_2CTA_MINV for A/B runs).  Default V > 256: at
+  // V ~ 200 a tile has only 7 k-blocks and the pair kernel measured 3-5 % SLOWER than the one-CTA kernel in both
+  // tiers (r02c/r02d sweeps, METR-LA step 2.82-2.89 vs 2.74 ms) -- neither kernel is paced by MMA issue there.
+  static const int min_v = [] {
+    const char* e = getenv("GWNET_B200_NCONV_2CTA_MINV");
+    return e ? atoi(e) : 257;
+  }();
+  if (two_cta && !a.per_sample && a.V >= min_v && a.V >= 16 && a.nsup >= 1 && a.nsup <= TC_MAXSUP && a.ld % 4 == 0 && a.ld >= a.V &&
       (long long)a.B * a.L > 0) {
     const int st = a.Slo[0] ? node_gemm_tc2_impl<true>(a, stream) : node_gemm_tc2_impl<false>(a, stream);
     if (st >= 0) return st;

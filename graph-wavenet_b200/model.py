@@ -44,8 +44,34 @@ def _default_precision() -> int:
 
 
 def _op_precision() -> int:
-    """The stand-alone operators (nconv / gcn / linear) run the fp32 FMA tier of the op-level C ABI."""
+    """Tier of the stand-alone operators (nconv / gcn / nconv2 / gcn2): the same default as the whole-network plan.  The
+    tensor-core tiers need 32 channels per node row (the reference's --nhid default); other widths run the fp32 FMA tier
+    of the same C ABI (see ``_op_tier``)."""
+    return _default_precision()
+
+
+_warned_widths = set()
+
+
+def _op_tier(precision: int, *channels) -> int:
+    """tcgen05 kernels exist for 32-channel rows only: anything else runs the fp32 FMA tier -- say so once per width
+    instead of a silent 5x slowdown."""
+    if precision == _N.PREC_FP32 or all(c == 32 for c in channels):
+        return precision
+    if channels not in _warned_widths:
+        _warned_widths.add(channels)
+        import warnings
+        warnings.warn(f"gwnet_b200: channel width(s) {channels} != 32: this operator runs the fp32 FMA kernels, not the tcgen05 "
+                      "tensor-core tier (several times slower)", RuntimeWarning, stacklevel=3)
     return _N.PREC_FP32
+
+
+def _workspace(floats: int, device):
+    return torch.empty(max(int(floats), 4), dtype=torch.float32, device=device) if floats else None
+
+
+def _wp(t):
+    return t.data_ptr() if t is not None else None
 
 
 def _require_cuda(t: torch.Tensor, what: str):
@@ -102,11 +128,13 @@ class _NconvFn(torch.autograd.Function):
             raise RuntimeError(f"nconv: support must be [{V},{V}], got {tuple(A.shape)}")
         if C % 4:
             raise RuntimeError("nconv: channel count must be a multiple of 4")
+        precision = _op_tier(precision, C)
         xb = _to_blnc(x)
         Ac = A.contiguous()
         yb = torch.empty_like(xb)
+        ws = _workspace(lib.dll.gwn_nconv_workspace_floats(1, V, precision, 0), x.device)
         with torch.cuda.device(x.device):
-            lib.check(lib.dll.gwn_nconv_fwd(xb.data_ptr(), Ac.data_ptr(), V, yb.data_ptr(), B, L, V, C, precision,
+            lib.check(lib.dll.gwn_nconv_fwd(xb.data_ptr(), Ac.data_ptr(), V, yb.data_ptr(), B, L, V, C, precision, _wp(ws),
                                             _stream(x)), "gwn_nconv_fwd")
         ctx.save_for_backward(xb, Ac)
         ctx.precision = precision
@@ -121,10 +149,11 @@ class _NconvFn(torch.autograd.Function):
         need_x, need_A = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dxb = torch.empty_like(xb) if need_x else None
         dA = torch.zeros_like(Ac) if need_A else None
+        ws = _workspace(lib.dll.gwn_nconv_workspace_floats(1, V, ctx.precision, int(need_A)), gy.device)
         with torch.cuda.device(gy.device):
             lib.check(lib.dll.gwn_nconv_bwd(gyb.data_ptr(), xb.data_ptr(), Ac.data_ptr(), V,
                                             dxb.data_ptr() if need_x else None, dA.data_ptr() if need_A else None, V,
-                                            B, L, V, C, ctx.precision, _stream(gy)), "gwn_nconv_bwd")
+                                            B, L, V, C, ctx.precision, _wp(ws), _stream(gy)), "gwn_nconv_bwd")
         return (_blnc_to_nchw(dxb) if need_x else None), dA, None
 
 
@@ -205,13 +234,15 @@ class _GcnFn(torch.autograd.Function):
         mode = _N.DROPOUT_NONE
         if training and p > 0:
             mode = _N.DROPOUT_MASK if keep_mask is not None else _N.DROPOUT_PHILOX
+        precision = _op_tier(precision, Cin, Cout) if (S <= 4 and 1 + order * S <= 7) else _N.PREC_FP32
         d = _N.GwnGcnDesc(B, L, V, Cin, Cout, S, order, precision, mode, float(p), int(seed), 0)
         sp = _N.ptr_array([s.data_ptr() for s in sup])
         lds = (ctypes.c_int64 * max(S, 1))(*[V] * S)
+        ws = _workspace(lib.dll.gwn_gcn_workspace_floats(ctypes.byref(d), 0), x.device)
         with torch.cuda.device(x.device):
             lib.check(lib.dll.gwn_gcn_fwd(ctypes.byref(d), xb.data_ptr(), sp, lds, w.data_ptr(), bias.data_ptr(),
                                           keep_mask.data_ptr() if keep_mask is not None else None, hops.data_ptr(),
-                                          yb.data_ptr(), _stream(x)), "gwn_gcn_fwd")
+                                          yb.data_ptr(), _wp(ws), _stream(x)), "gwn_gcn_fwd")
         ctx.save_for_backward(xb, w, hops, *sup)
         ctx.desc, ctx.keep_mask = d, keep_mask
         return _blnc_to_nchw(yb)
@@ -273,12 +304,14 @@ class _Nconv2Fn(torch.autograd.Function):
             raise RuntimeError(f"nconv2: support must be [{B},{V},{V}] (one graph per sample), got {tuple(A.shape)}")
         if C % 4:
             raise RuntimeError("nconv2: channel count must be a multiple of 4")
+        precision = _op_tier(precision, C)
         xb = _to_blnc(x)
         Ac = A.contiguous()
         yb = torch.empty_like(xb)
+        ws = _workspace(lib.dll.gwn_nconv_workspace_floats(B, V, precision, 0), x.device)
         with torch.cuda.device(x.device):
             lib.check(lib.dll.gwn_nconv2_fwd(xb.data_ptr(), Ac.data_ptr(), V * V, V, yb.data_ptr(), B, L, V, C, precision,
-                                             _stream(x)), "gwn_nconv2_fwd")
+                                             _wp(ws), _stream(x)), "gwn_nconv2_fwd")
         ctx.save_for_backward(xb, Ac)
         ctx.precision = precision
         return _blnc_to_nchw(yb)
@@ -292,10 +325,11 @@ class _Nconv2Fn(torch.autograd.Function):
         need_x, need_A = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dxb = torch.empty_like(xb) if need_x else None
         dA = torch.zeros_like(Ac) if need_A else None
+        ws = _workspace(lib.dll.gwn_nconv_workspace_floats(B, V, ctx.precision, int(need_A)), gy.device)
         with torch.cuda.device(gy.device):
             lib.check(lib.dll.gwn_nconv2_bwd(gyb.data_ptr(), xb.data_ptr(), Ac.data_ptr(), V * V, V,
                                              dxb.data_ptr() if need_x else None, dA.data_ptr() if need_A else None, V * V, V,
-                                             B, L, V, C, ctx.precision, _stream(gy)), "gwn_nconv2_bwd")
+                                             B, L, V, C, ctx.precision, _wp(ws), _stream(gy)), "gwn_nconv2_bwd")
         return (_blnc_to_nchw(dxb) if need_x else None), dA, None
 
 
@@ -332,14 +366,16 @@ class _Gcn2Fn(torch.autograd.Function):
         mode = _N.DROPOUT_NONE
         if training and p > 0:
             mode = _N.DROPOUT_MASK if keep_mask is not None else _N.DROPOUT_PHILOX
+        precision = _op_tier(precision, Cin, Cout) if (S <= 4 and 1 + order * S <= 7) else _N.PREC_FP32
         d = _N.GwnGcnDesc(B, L, V, Cin, Cout, S, order, precision, mode, float(p), int(seed), 0)
         sp = _N.ptr_array([s.data_ptr() for s in sup])
         lds = (ctypes.c_int64 * max(S, 1))(*[V] * S)
         ldb = (ctypes.c_int64 * max(S, 1))(*[V * V] * S)
+        ws = _workspace(lib.dll.gwn_gcn_workspace_floats(ctypes.byref(d), 1), x.device)
         with torch.cuda.device(x.device):
             lib.check(lib.dll.gwn_gcn2_fwd(ctypes.byref(d), xb.data_ptr(), sp, ldb, lds, w.data_ptr(), bias.data_ptr(),
                                            keep_mask.data_ptr() if keep_mask is not None else None, hops.data_ptr(),
-                                           yb.data_ptr(), _stream(x)), "gwn_gcn2_fwd")
+                                           yb.data_ptr(), _wp(ws), _stream(x)), "gwn_gcn2_fwd")
         ctx.save_for_backward(xb, w, hops, *sup)
         ctx.desc, ctx.keep_mask = d, keep_mask
         return _blnc_to_nchw(yb)
@@ -514,6 +550,12 @@ class gwnet(nn.Module):
         r = self._runners.get(key)
         if r is None:
             g = self._geom
+            if self.precision != _N.PREC_FP32 and (g["residual_channels"] != 32 or g["dilation_channels"] != 32):
+                # train.py:32 --nhid other than 32: no tcgen05 kernels for those widths -- say so instead of a silent slowdown
+                import warnings
+                warnings.warn(f"gwnet_b200: residual/dilation channels {g['residual_channels']}/{g['dilation_channels']} != 32: "
+                              "the tcgen05 kernels need 32-channel rows; this model runs the generic mma.sync / FMA kernels "
+                              "(about 5x slower than the tensor-core tier)", RuntimeWarning, stacklevel=3)
             cfg = _make_config(batch=batch, seq_len=seq_len, n_static_supports=self._n_static(), gcn_bool=self.gcn_bool,
                                adaptive=self._adaptive(), gcn=self._gcn_active(), order=2, apt_rank=10,
                                precision=self.precision, dropout=self.dropout, bn_eps=self.bn[0].eps,

@@ -83,8 +83,8 @@ class GwnGcnDesc(C.Structure):
 # every symbol include/gwnet_b200.h declares (tests check that the library exports them all)
 EXPORTS = [
     "gwn_last_error", "gwn_abi_version", "gwn_launch_count", "gwn_device_info", "gwn_profile_begin", "gwn_profile_end", "gwn_permute4d",
-    "gwn_node_contract", "gwn_node_contract_x3", "gwn_split_lo", "gwn_tc_error_flag", "gwn_tc_debug_buffer", "gwn_tc_debug_mode", "gwn_nconv_fwd", "gwn_nconv_bwd", "gwn_linear_fwd", "gwn_linear_bwd",
-    "gwn_gcn_fwd", "gwn_gcn_bwd_scratch_floats", "gwn_gcn_bwd",
+    "gwn_node_contract", "gwn_node_contract_x3", "gwn_split_lo", "gwn_tc_error_flag", "gwn_tc_debug_buffer", "gwn_tc_debug_mode", "gwn_nconv_workspace_floats", "gwn_nconv_fwd", "gwn_nconv_bwd", "gwn_linear_fwd", "gwn_linear_bwd",
+    "gwn_gcn_workspace_floats", "gwn_gcn_fwd", "gwn_gcn_bwd_scratch_floats", "gwn_gcn_bwd",
     "gwn_nconv2_fwd", "gwn_nconv2_bwd", "gwn_gcn2_fwd", "gwn_gcn2_bwd",
     "gwn_plan_create", "gwn_plan_destroy", "gwn_plan_workspace_bytes", "gwn_plan_param_count",
     "gwn_plan_param_info", "gwn_plan_out_len", "gwn_plan_debug_layout", "gwn_plan_forward", "gwn_plan_backward",
@@ -130,20 +130,25 @@ class Lib:
         d.gwn_tc_debug_buffer.restype = None
         d.gwn_tc_debug_mode.argtypes = [C.c_int]
         d.gwn_tc_debug_mode.restype = None
-        d.gwn_nconv_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+        d.gwn_nconv_workspace_floats.argtypes = [C.c_int] * 4
+        d.gwn_nconv_workspace_floats.restype = C.c_size_t
+        d.gwn_nconv_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]
         d.gwn_nconv_bwd.argtypes = ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
-                                    + [C.c_int] * 5 + [C.c_void_p])
+                                    + [C.c_int] * 5 + [C.c_void_p, C.c_void_p])
         d.gwn_linear_fwd.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int, C.c_int, C.c_void_p]
         d.gwn_linear_bwd.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_int, C.c_int, C.c_void_p]
-        d.gwn_gcn_fwd.argtypes = [C.POINTER(GwnGcnDesc), C.c_void_p, c_void_pp, i64p] + [C.c_void_p] * 6
+        d.gwn_gcn_workspace_floats.argtypes = [C.POINTER(GwnGcnDesc), C.c_int]
+        d.gwn_gcn_workspace_floats.restype = C.c_size_t
+        d.gwn_gcn_fwd.argtypes = [C.POINTER(GwnGcnDesc), C.c_void_p, c_void_pp, i64p] + [C.c_void_p] * 7
         d.gwn_gcn_bwd_scratch_floats.argtypes = [C.POINTER(GwnGcnDesc)]
         d.gwn_gcn_bwd_scratch_floats.restype = C.c_size_t
         d.gwn_gcn_bwd.argtypes = ([C.POINTER(GwnGcnDesc), C.c_void_p, C.c_void_p, c_void_pp, i64p] + [C.c_void_p] * 6
                                   + [c_void_pp, i64p, C.c_void_p, C.c_void_p])
-        d.gwn_nconv2_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+        d.gwn_nconv2_fwd.argtypes = ([C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p] + [C.c_int] * 5
+                                     + [C.c_void_p, C.c_void_p])
         d.gwn_nconv2_bwd.argtypes = ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
-                                      C.c_int64] + [C.c_int] * 5 + [C.c_void_p])
-        d.gwn_gcn2_fwd.argtypes = [C.POINTER(GwnGcnDesc), C.c_void_p, c_void_pp, i64p, i64p] + [C.c_void_p] * 6
+                                      C.c_int64] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p])
+        d.gwn_gcn2_fwd.argtypes = [C.POINTER(GwnGcnDesc), C.c_void_p, c_void_pp, i64p, i64p] + [C.c_void_p] * 7
         d.gwn_gcn2_bwd.argtypes = ([C.POINTER(GwnGcnDesc), C.c_void_p, C.c_void_p, c_void_pp, i64p, i64p] + [C.c_void_p] * 6
                                    + [c_void_pp, i64p, i64p, C.c_void_p, C.c_void_p])
         d.gwn_plan_create.argtypes = [C.POINTER(GwnConfig), C.POINTER(C.c_void_p)]
@@ -163,8 +168,8 @@ class Lib:
         d.gwn_plan_train_fwd_bwd.argtypes = [C.c_void_p, C.POINTER(GwnTrainArgs)]
         d.gwn_plan_eval_metrics.argtypes = [C.c_void_p, C.POINTER(GwnTrainArgs)]
         d.gwn_adam_step.argtypes = [C.POINTER(GwnAdamArgs)]
-        if d.gwn_abi_version() != 3:
-            raise GwnError(f"{path}: ABI version {d.gwn_abi_version()} != 3")
+        if d.gwn_abi_version() != 4:
+            raise GwnError(f"{path}: ABI version {d.gwn_abi_version()} != 4")
 
     def check(self, status: int, what: str = ""):
         if status != 0:

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define GWN_ABI_VERSION 3
+#define GWN_ABI_VERSION 4
 
 typedef enum gwn_status {
   GWN_OK = 0,
@@ -107,18 +107,27 @@ int gwn_tc_error_flag(int reset);
 void gwn_tc_debug_buffer(float* p);
 void gwn_tc_debug_mode(int mode);   /* 0 = normal; non-zero = kernel self-test modes (development only) */
 
+/* ------------------------------------------------------------------ stand-alone operators
+ * nconv / gcn / nconv2 / gcn2 run in any tier.  GWN_PREC_FP32 needs no workspace (pass NULL).  The tensor-core tiers
+ * (GWN_PREC_FP32X3, GWN_PREC_TF32: tcgen05 + TMA kernels, c_in = c_out = 32) prepare their operands -- zero-padded
+ * K-contiguous supports A / A^T, 3xTF32 remainders, transposed weights, partial-result slots of the reductions -- in a
+ * caller-owned, 16-byte aligned workspace whose size the *_workspace_floats / *_scratch_floats functions return.      */
+
 /* ------------------------------------------------------------------ nconv (model.py:8-14)
  * y[b,l,w,c] = sum_v x[b,l,v,c] * A[v,w].   x,y: BLNC [B,L,V,C]; A: [V,V] row-major, ld = lda.
  * Replaces torch.einsum('ncvl,vw->ncwl') + .contiguous().                          */
+/* floats of workspace for gwn_nconv_* (n_sets = 1) / gwn_nconv2_* (n_sets = B); support_grad = 1 when dA is wanted. */
+size_t gwn_nconv_workspace_floats(int n_sets, int V, int precision, int support_grad);
 int gwn_nconv_fwd(const float* x, const float* A, int64_t lda, float* y, int B, int L, int V, int C,
-                  int precision, void* stream);
+                  int precision, void* workspace, void* stream);
 /* Autograd of nconv: dx = dy . A^T ; dA += x^T dy summed over (b,l,c) when dA != NULL
  * (dA is accumulated into -- zero it first).                                        */
 int gwn_nconv_bwd(const float* dy, const float* x, const float* A, int64_t lda, float* dx, float* dA, int64_t ldda,
-                  int B, int L, int V, int C, int precision, void* stream);
+                  int B, int L, int V, int C, int precision, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------ linear (model.py:24-30)
- * 1x1 Conv2d with bias: y[p,co] = sum_ci W[co,ci] x[p,ci] + b[co], p over B*L*N positions. */
+ * 1x1 Conv2d with bias: y[p,co] = sum_ci W[co,ci] x[p,ci] + b[co], p over B*L*N positions (fp32 FMA kernels; inside
+ * gcn and gwnet the same contraction runs on tcgen05). */
 int gwn_linear_fwd(const float* x, const float* W, const float* bias, float* y, int64_t positions, int c_in, int c_out,
                    void* stream);
 int gwn_linear_bwd(const float* dy, const float* x, const float* W, float* dx, float* dW, float* dbias,
@@ -140,10 +149,13 @@ typedef struct gwn_gcn_desc {
   uint64_t offset;         /* Philox stream offset (layer id)                        */
 } gwn_gcn_desc;
 
+/* floats of forward workspace (0 in the fp32 tier); per_sample_supports = 1 for gwn_gcn2_fwd. */
+size_t gwn_gcn_workspace_floats(const gwn_gcn_desc* d, int per_sample_supports);
 int gwn_gcn_fwd(const gwn_gcn_desc* d, const float* x, const float* const* supports, const int64_t* lds,
-                const float* W, const float* bias, const uint8_t* keep_mask, float* hops, float* y, void* stream);
+                const float* W, const float* bias, const uint8_t* keep_mask, float* hops, float* y, void* workspace,
+                void* stream);
 /* dsupports[s] may be NULL (no gradient wanted for that support); non-NULL ones are accumulated into.
- * scratch: caller buffer of gwn_gcn_bwd_scratch_floats(d) floats.                    */
+ * scratch: caller buffer of gwn_gcn_bwd_scratch_floats(d) floats (16-byte aligned; covers gwn_gcn_bwd and gwn_gcn2_bwd). */
 size_t gwn_gcn_bwd_scratch_floats(const gwn_gcn_desc* d);
 int gwn_gcn_bwd(const gwn_gcn_desc* d, const float* dy, const float* x, const float* const* supports, const int64_t* lds,
                 const float* W, const uint8_t* keep_mask, const float* hops, float* dx, float* dW, float* dbias,
@@ -152,13 +164,15 @@ int gwn_gcn_bwd(const gwn_gcn_desc* d, const float* dy, const float* x, const fl
 /* ------------------------------------------------------------------ nconv2 / gcn2 (model.py:16-22, 57-80)
  * The per-sample-graph operators of the fork: y[b,l,w,c] = sum_v x[b,l,v,c] * A[b][v,w], one [V,V] support per sample
  * (A: [B,V,V], sample stride lda_b, row stride lda).  Same semantics as gwn_nconv_* / gwn_gcn_* otherwise; the supports
- * of gwn_gcn2_* are `n_supports` tensors [B,V,V]; dsupports[s] (nullable) are accumulated into, same layout.        */
+ * of gwn_gcn2_* are `n_supports` tensors [B,V,V]; dsupports[s] (nullable) are accumulated into, same layout.  In the
+ * tensor-core tiers all samples' graphs go through one launch (batched tensor maps).                                */
 int gwn_nconv2_fwd(const float* x, const float* A, int64_t lda_b, int64_t lda, float* y, int B, int L, int V, int C,
-                   int precision, void* stream);
+                   int precision, void* workspace, void* stream);
 int gwn_nconv2_bwd(const float* dy, const float* x, const float* A, int64_t lda_b, int64_t lda, float* dx, float* dA,
-                   int64_t ldda_b, int64_t ldda, int B, int L, int V, int C, int precision, void* stream);
+                   int64_t ldda_b, int64_t ldda, int B, int L, int V, int C, int precision, void* workspace, void* stream);
 int gwn_gcn2_fwd(const gwn_gcn_desc* d, const float* x, const float* const* supports, const int64_t* lds_b, const int64_t* lds,
-                 const float* W, const float* bias, const uint8_t* keep_mask, float* hops, float* y, void* stream);
+                 const float* W, const float* bias, const uint8_t* keep_mask, float* hops, float* y, void* workspace,
+                 void* stream);
 int gwn_gcn2_bwd(const gwn_gcn_desc* d, const float* dy, const float* x, const float* const* supports, const int64_t* lds_b,
                  const int64_t* lds, const float* W, const uint8_t* keep_mask, const float* hops, float* dx, float* dW,
                  float* dbias, float* const* dsupports, const int64_t* ldds_b, const int64_t* ldds, float* scratch,

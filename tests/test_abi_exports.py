@@ -54,5 +54,5 @@ def test_no_cpu_fallback():
         m(torch.zeros(1, 2, 7, 13))
     lib = N.Lib(N.LIB_PATH)
     x = torch.zeros(1, 1, 4, 4)
-    st = lib.dll.gwn_nconv_fwd(x.data_ptr(), x.data_ptr(), 4, x.data_ptr(), 1, 1, 4, 4, 0, None)
+    st = lib.dll.gwn_nconv_fwd(x.data_ptr(), x.data_ptr(), 4, x.data_ptr(), 1, 1, 4, 4, 0, None, None)
     assert st == 10004
