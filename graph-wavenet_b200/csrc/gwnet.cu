@@ -3,6 +3,7 @@
 #include "ops.cuh"
 #include "nconv_tc_impl.cuh"
 #include "train_tail.cuh"
+#include "p2p_allreduce.cuh"
 
 #include <atomic>
 #include <cstdarg>
@@ -2278,8 +2279,115 @@ int gwn_adam_step(const gwn_adam_args* a) {
   GWN_TRY(dev_memset(&ctrl->acc[4], 0, sizeof(double), st));
   GWN_LAUNCH_1D(gradnorm_kernel, a->n / 4, st, (const float*)a->grad_flat, a->live4, a->n / 4, ctrl);
   GWN_LAUNCH_1D(adam_kernel, a->n / 4, st, a->param_flat, a->grad_flat, a->exp_avg, a->exp_avg_sq, a->live4, a->n / 4,
-                reinterpret_cast<const AdamHyper*>(a->hyper), (const TrainCtrl*)ctrl, a->metrics);
+                reinterpret_cast<const AdamHyper*>(a->hyper), (const TrainCtrl*)ctrl, a->metrics, (const float*)nullptr);
   return 0;
+}
+
+// ---- data-parallel step tail over NVLink peer memory (p2p_allreduce.cuh)
+size_t gwn_p2p_header_bytes(void) {
+#if GWN_EMU
+  return 4096;
+#else
+  return P2P_FLAG_BYTES;
+#endif
+}
+
+int gwn_p2p_alloc(size_t bytes, void** base, unsigned char* handle64) {
+  GWN_CHECK_ARG(base && handle64 && bytes > 0, "p2p_alloc: bad argument");
+#if GWN_EMU
+  set_error("p2p: not part of the host emulation");
+  return GWN_ERR_UNSUPPORTED;
+#else
+  GWN_TRY(require_device());
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  GWN_CUDA(cudaMalloc(&p, bytes));
+  GWN_CUDA(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return GWN_ERR_CUDA;
+  }
+  memcpy(handle64, &h, 64);
+  *base = p;
+  return 0;
+#endif
+}
+
+int gwn_p2p_open(const unsigned char* handle64, void** base) {
+  GWN_CHECK_ARG(base && handle64, "p2p_open: bad argument");
+#if GWN_EMU
+  set_error("p2p: not part of the host emulation");
+  return GWN_ERR_UNSUPPORTED;
+#else
+  GWN_TRY(require_device());
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    set_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return GWN_ERR_CUDA;
+  }
+  *base = p;
+  return 0;
+#endif
+}
+
+int gwn_p2p_close(void* base) {
+#if !GWN_EMU
+  if (base) cudaIpcCloseMemHandle(base);
+#else
+  (void)base;
+#endif
+  return 0;
+}
+
+int gwn_p2p_free(void* base) {
+#if !GWN_EMU
+  if (base) cudaFree(base);
+#else
+  (void)base;
+#endif
+  return 0;
+}
+
+int gwn_allreduce_adam_step(const gwn_adam_args* a, const gwn_p2p_args* p) {
+  GWN_CHECK_ARG(a && p && a->param_flat && a->grad_flat && a->exp_avg && a->exp_avg_sq && a->live4 && a->hyper && a->ctrl,
+                "allreduce_adam_step: null argument");
+  GWN_CHECK_ARG(a->n > 0 && a->n % 4 == 0, "allreduce_adam_step: n must be a positive multiple of 4");
+#if GWN_EMU
+  set_error("p2p: not part of the host emulation");
+  return GWN_ERR_UNSUPPORTED;
+#else
+  GWN_CHECK_ARG(p->world >= 2 && p->world <= P2P_MAXRANKS && p->rank >= 0 && p->rank < p->world && p->sum_out,
+                "allreduce_adam_step: world must be in [2,%d]", P2P_MAXRANKS);
+  GWN_TRY(require_device());
+  cudaStream_t st = (cudaStream_t)a->stream;
+  TrainCtrl* ctrl = reinterpret_cast<TrainCtrl*>(a->ctrl);
+  P2PArgs k;
+  memset(&k, 0, sizeof(k));
+  for (int q = 0; q < p->world; ++q) {
+    GWN_CHECK_ARG(p->base[q] != nullptr, "allreduce_adam_step: rank %d's buffer is not mapped", q);
+    k.flags[q] = reinterpret_cast<unsigned*>(p->base[q]);
+    k.grad[q] = reinterpret_cast<const float*>(reinterpret_cast<const char*>(p->base[q]) + P2P_FLAG_BYTES);
+  }
+  GWN_CHECK_ARG(k.grad[p->rank] == a->grad_flat, "allreduce_adam_step: grad_flat must be this rank's p2p gradient buffer");
+  k.out = p->sum_out; k.live4 = a->live4; k.n4 = a->n / 4; k.c = ctrl; k.rank = p->rank; k.world = p->world;
+  ProfScope prof("p2p_allreduce_clip_adam", st, 4.0 * a->n * (8.0 + p->world), 0.0);
+  GWN_TRY(dev_memset(&ctrl->acc[4], 0, sizeof(double), st));
+  const i64 want = (k.n4 + P2P_THREADS - 1) / P2P_THREADS;
+  const int grid = (int)std::min<i64>(want, 148);      // all blocks co-resident: they wait for one another's peers
+  GWN_CUDA(launch_kernel(p2p_allreduce_gradnorm_kernel, dim3((unsigned)grid), dim3(P2P_THREADS), 0, st, k));
+  count_launch();
+  GWN_LAUNCH_1D(adam_kernel, a->n / 4, st, a->param_flat, a->grad_flat, a->exp_avg, a->exp_avg_sq, a->live4, a->n / 4,
+                reinterpret_cast<const AdamHyper*>(a->hyper), (const TrainCtrl*)ctrl, a->metrics, (const float*)p->sum_out);
+  return 0;
+#endif
 }
 
 }  // extern "C"

@@ -143,8 +143,10 @@ GWN_GLOBAL gradnorm_kernel(const float* g, const uint8_t* live4, i64 n4, TrainCt
   reduce_add_d(&c->acc[4], s);
 }
 
+// gin (nullable): read the gradient from here instead of g (the all-reduced sum of the data-parallel step); g always
+// receives the clipped gradient.
 GWN_GLOBAL adam_kernel(float* p, float* g, float* m, float* v, const uint8_t* live4, i64 n4, const AdamHyper* hp,
-                       const TrainCtrl* c, float* metrics) {
+                       const TrainCtrl* c, float* metrics, const float* gin) {
   GWN_PDL_ENTRY();
   const AdamHyper h = *hp;
   const float total_norm = (float)sqrt(c->acc[4]) * h.gscale;
@@ -157,7 +159,7 @@ GWN_GLOBAL adam_kernel(float* p, float* g, float* m, float* v, const uint8_t* li
   GWN_FOR_EACH(i, n4) {
     if (i == 0 && metrics) metrics[3] = total_norm;
     if (!live4[i]) continue;
-    float4 pp = ld4(p + 4 * i), gg = ld4(g + 4 * i), mm = ld4(m + 4 * i), vv = ld4(v + 4 * i);
+    float4 pp = ld4(p + 4 * i), gg = ld4((gin ? gin : g) + 4 * i), mm = ld4(m + 4 * i), vv = ld4(v + 4 * i);
     float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {

@@ -52,15 +52,34 @@ class trainer():
         self.aptinit = aptinit
         self.state = None
         self.world = 1
+        self.rank = 0
+        self.p2p = False
+        self._p2p_comm = None
 
     # ---- data parallelism (no reference counterpart): one process per GPU, batch sharded,
     # parameters replicated, ONE NCCL all-reduce per step over the flat gradient buffer the backward call fills.
     def enable_data_parallel(self):
         import torch.distributed as dist
         self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        # gradient exchange of the fused step: a peer-memory kernel over NVLink (fused.P2PComm) when every rank can map
+        # its peers' buffers (one node, <= 8 GPUs); otherwise ONE NCCL all-reduce of the flat buffer between two graphs
+        self.p2p = _fused.p2p_enabled() and self.fused and 2 <= self.world <= 8 and dist.get_backend() == "nccl"
+        self._p2p_comm = None
         with torch.no_grad():
             for t in self.model.state_dict().values():
                 dist.broadcast(t, src=0)
+
+    def p2p_comm(self, grad_floats, dev):
+        """This rank's peer-mapped gradient buffer (None -- and the NCCL path from then on -- if IPC mapping fails)."""
+        if self._p2p_comm is None and self.p2p:
+            try:
+                self._p2p_comm = _fused.P2PComm(grad_floats, dev, self.rank, self.world)
+            except Exception as e:      # every rank raises together (see P2PComm)
+                import warnings
+                warnings.warn(f"gwnet_b200: {e}; using the NCCL all-reduce path", RuntimeWarning)
+                self.p2p = False
+        return self._p2p_comm
 
     def _allreduce_grads(self):
         import torch.distributed as dist

@@ -37,10 +37,80 @@ def _pinned(t, dev):
     return t.pin_memory() if dev.type == "cuda" else t
 
 
+class _DeviceMemory:
+    """``torch.as_tensor`` view of device memory owned by the library (CUDA array interface, no copy)."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class P2PComm:
+    """Every rank's ``[flags | flat gradient]`` allocation, mapped into every process of the node (``gwn_p2p_alloc`` /
+    ``gwn_p2p_open``; the 64-byte IPC handles travel through ``torch.distributed``).  ``grad`` is this rank's gradient
+    buffer as a torch tensor: the backward pass writes it, the peers read it over NVLink inside
+    ``gwn_allreduce_adam_step``."""
+
+    def __init__(self, n_floats: int, dev, rank: int, world: int):
+        import torch.distributed as dist
+        lib = N.get_lib()
+        self.lib, self.rank, self.world, self.n = lib, rank, world, int(n_floats)
+        self.bases, self.own = [None] * world, None
+        hdr = int(lib.dll.gwn_p2p_header_bytes())
+        ok, err = 1, ""
+        handle = C.create_string_buffer(64)
+        with _dev_ctx(dev):
+            base = C.c_void_p()
+            if lib.dll.gwn_p2p_alloc(hdr + 4 * self.n, C.byref(base), handle) != 0:
+                ok, err = 0, lib.dll.gwn_last_error().decode()
+            else:
+                self.own = base.value
+            handles = [None] * world
+            dist.all_gather_object(handles, (ok, bytes(handle.raw)))
+            if all(h[0] for h in handles):
+                for q in range(world):
+                    if q == rank:
+                        self.bases[q] = self.own
+                        continue
+                    p = C.c_void_p()
+                    if lib.dll.gwn_p2p_open(handles[q][1], C.byref(p)) != 0:
+                        ok, err = 0, lib.dll.gwn_last_error().decode()
+                        break
+                    self.bases[q] = p.value
+            else:
+                ok = 0
+            flag = torch.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # all ranks take the same path
+            if int(flag.item()) == 0:
+                self.close()
+                raise N.GwnError("peer-memory gradient exchange unavailable" + (": " + err if err else ""))
+            self.grad = torch.as_tensor(_DeviceMemory(self.own + hdr, self.n), device=dev)
+            dist.barrier()
+
+    def args(self, sum_out: torch.Tensor) -> N.GwnP2PArgs:
+        a = N.GwnP2PArgs()
+        for q in range(self.world):
+            a.base[q] = self.bases[q]
+        a.rank, a.world, a.sum_out = self.rank, self.world, sum_out.data_ptr()
+        return a
+
+    def close(self):
+        for q, b in enumerate(self.bases):
+            if b is not None and q != self.rank:
+                self.lib.dll.gwn_p2p_close(b)
+        self.bases = [None] * self.world
+        if self.own is not None:
+            self.lib.dll.gwn_p2p_free(self.own)
+            self.own = None
+
+
+def p2p_enabled() -> bool:
+    return os.environ.get("GWNET_B200_P2P_ALLREDUCE", "1") != "0"
+
+
 class FlatParams:
     """Parameters and gradients of one ``gwnet`` as views of flat buffers (offsets = the plan's gradient layout)."""
 
-    def __init__(self, model, plan):
+    def __init__(self, model, plan, p2p: Optional["P2PComm"] = None):
         named = list(model.named_parameters())
         offs = [o for o in plan.grad_offsets if o >= 0]
         nums = [n for n, o in zip(plan.numels, plan.grad_offsets) if o >= 0]
@@ -51,7 +121,10 @@ class FlatParams:
         if self.n % 4:
             raise N.GwnError("flat gradient buffer must be a multiple of 4 floats")
         self.param = torch.zeros(self.n, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.p2p = p2p        # data parallel: the gradient buffer is the rank's peer-mapped allocation
+        self.grad = p2p.grad if p2p is not None else torch.zeros(self.n, dtype=torch.float32, device=dev)
+        if self.grad.numel() != self.n:
+            raise N.GwnError("peer-memory gradient buffer does not match the plan's flat layout")
         live4 = torch.zeros(self.n // 4, dtype=torch.uint8)
         with torch.no_grad():
             for (name, p), off, ne in zip(named, offs, nums):
@@ -188,6 +261,13 @@ class FusedAdam(torch.optim.Optimizer):
         a = self.adam_args(_stream(dev))
         self._lib.check(self._lib.dll.gwn_adam_step(C.byref(a)), "gwn_adam_step")
 
+    def launch_p2p(self, sum_out: torch.Tensor):
+        """Data parallel: gradient all-reduce over NVLink peer memory fused with the norm pass, then Adam (capturable)."""
+        dev = self._flat.param.device
+        a = self.adam_args(_stream(dev))
+        p = self._flat.p2p.args(sum_out)
+        self._lib.check(self._lib.dll.gwn_allreduce_adam_step(C.byref(a), C.byref(p)), "gwn_allreduce_adam_step")
+
     @torch.no_grad()
     def step(self, closure=None):
         """Eager use (``loss.backward(); optimizer.step()``): gradients must live in the bound flat buffer."""
@@ -220,12 +300,16 @@ class FusedStep:
         # column from the static input buffer (for T+1 <= RF the two pads coincide; for T >= RF they do not)
         runner = model._runner(B, T + 1)
         self.runner, self.plan = runner, runner.plan
-        if model._flat is None or not model._flat.intact():
-            model._flat = FlatParams(model, runner.plan)
+        want_p2p = trainer.world > 1 and getattr(trainer, "p2p", False) and dev.type == "cuda"
+        if model._flat is None or not model._flat.intact() or (want_p2p and model._flat.p2p is None):
+            model._flat = FlatParams(model, runner.plan, trainer.p2p_comm(runner.plan.grad_floats, dev) if want_p2p else None)
             opt._flat = None
         if not opt.bound:
             opt.bind(model._flat, int(torch.randint(0, 2 ** 62, (1,)).item()))
         self.flat = model._flat
+        # the peer-memory exchange: one kernel inside the step's single graph; else NCCL between two graphs (below)
+        self.p2p = self.flat.p2p if trainer.world > 1 else None
+        self.gsum = torch.empty(self.flat.n, dtype=torch.float32, device=dev) if self.p2p is not None else None
         cfg = runner.cfg
         # static buffers (the graph bakes their addresses)
         self.x = torch.zeros((B, T + 1, Nn, F), dtype=torch.float32, device=dev).permute(0, 3, 2, 1)   # loader layout [B,T,N,F]
@@ -250,9 +334,9 @@ class FusedStep:
         # Under data parallelism the step is captured as TWO graphs with the gradient all-reduce launched between them
         # by torch.distributed (NCCL's own stream-ordering, no host sync): capturing the collective itself depends on the
         # NCCL watchdog tolerating stream capture.  GWNET_B200_NCCL_IN_GRAPH=1 captures it into a single graph instead.
-        self.split = trainer.world > 1 and os.environ.get("GWNET_B200_NCCL_IN_GRAPH", "0") != "1"
+        self.split = trainer.world > 1 and self.p2p is None and os.environ.get("GWNET_B200_NCCL_IN_GRAPH", "0") != "1"
         if use_graph:
-            if trainer.world > 1 and not self.split:     # NCCL must have built its communicator before capture
+            if trainer.world > 1 and not self.split and self.p2p is None:     # NCCL must have built its communicator before capture
                 import torch.distributed as dist
                 dist.all_reduce(torch.zeros(1, device=dev))
             torch.cuda.synchronize(dev)
@@ -322,6 +406,12 @@ class FusedStep:
 
     def _enqueue(self):
         self._enqueue_fwd_bwd()
+        if self.p2p is not None:
+            tr = self.trainer
+            with _dev_ctx(self.x.device):
+                tr.optimizer.launch_p2p(self.gsum)
+                self.metrics_host.copy_(tr.optimizer.metrics, non_blocking=True)
+            return
         if self.trainer.world > 1:
             self._allreduce()
         self._enqueue_tail()

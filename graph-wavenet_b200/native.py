@@ -72,6 +72,10 @@ class GwnAdamArgs(C.Structure):
     ]
 
 
+class GwnP2PArgs(C.Structure):
+    _fields_ = [("base", C.c_void_p * 8), ("rank", C.c_int), ("world", C.c_int), ("sum_out", C.c_void_p)]
+
+
 class GwnGcnDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int), ("L", C.c_int), ("V", C.c_int), ("C", C.c_int), ("c_out", C.c_int),
@@ -89,6 +93,7 @@ EXPORTS = [
     "gwn_plan_create", "gwn_plan_destroy", "gwn_plan_workspace_bytes", "gwn_plan_param_count",
     "gwn_plan_param_info", "gwn_plan_out_len", "gwn_plan_debug_layout", "gwn_plan_forward", "gwn_plan_backward",
     "gwn_train_ctrl_bytes", "gwn_train_ctrl_init", "gwn_train_ctrl_read", "gwn_plan_train_fwd_bwd", "gwn_plan_eval_metrics", "gwn_adam_step",
+    "gwn_p2p_header_bytes", "gwn_p2p_alloc", "gwn_p2p_open", "gwn_p2p_close", "gwn_p2p_free", "gwn_allreduce_adam_step",
 ]
 
 
@@ -168,6 +173,12 @@ class Lib:
         d.gwn_plan_train_fwd_bwd.argtypes = [C.c_void_p, C.POINTER(GwnTrainArgs)]
         d.gwn_plan_eval_metrics.argtypes = [C.c_void_p, C.POINTER(GwnTrainArgs)]
         d.gwn_adam_step.argtypes = [C.POINTER(GwnAdamArgs)]
+        d.gwn_p2p_header_bytes.restype = C.c_size_t
+        d.gwn_p2p_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+        d.gwn_p2p_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        d.gwn_p2p_close.argtypes = [C.c_void_p]
+        d.gwn_p2p_free.argtypes = [C.c_void_p]
+        d.gwn_allreduce_adam_step.argtypes = [C.POINTER(GwnAdamArgs), C.POINTER(GwnP2PArgs)]
         if d.gwn_abi_version() != 4:
             raise GwnError(f"{path}: ABI version {d.gwn_abi_version()} != 4")
 

@@ -309,6 +309,28 @@ typedef struct gwn_adam_args {
 } gwn_adam_args;
 int gwn_adam_step(const gwn_adam_args* a);
 
+/* ------------------------------------------------------------------ data-parallel step tail over NVLink peer memory
+ * (no reference counterpart: SURVEY.md section 8(e)).  One process per GPU; every rank's flat gradient buffer lives in an
+ * allocation made by gwn_p2p_alloc -- gwn_p2p_header_bytes() of flags followed by the gradient floats, which is what the
+ * rank passes as grad_flat to gwn_plan_train_fwd_bwd -- and is mapped into its peers with gwn_p2p_open from the 64-byte
+ * IPC handle (exchanged by the host code, e.g. through torch.distributed).  gwn_allreduce_adam_step then replaces
+ * [all-reduce; gwn_adam_step]: ONE kernel sums all ranks' gradients over peer memory (rank order: bit-identical on every
+ * rank), writes the sum to sum_out and accumulates its squared norm; the Adam kernel reads sum_out (grad_scale = 1/world
+ * averages) and leaves the clipped gradient in grad_flat.  Capturable in a CUDA graph.  All ranks must call it the same
+ * number of times (the protocol's epoch is the Adam step count of the control block).  These are the only entry points
+ * that allocate device memory; the caller frees it with gwn_p2p_close (peers) / gwn_p2p_free (own).                   */
+size_t gwn_p2p_header_bytes(void);
+int gwn_p2p_alloc(size_t bytes, void** base, unsigned char* handle64);
+int gwn_p2p_open(const unsigned char* handle64, void** base);
+int gwn_p2p_close(void* base);
+int gwn_p2p_free(void* base);
+typedef struct gwn_p2p_args {
+  void* base[8];                 /* every rank's allocation as mapped in this process (base[rank] = own)               */
+  int rank, world;               /* world in [2, 8]                                                                    */
+  float* sum_out;                /* n floats, local                                                                    */
+} gwn_p2p_args;
+int gwn_allreduce_adam_step(const gwn_adam_args* a, const gwn_p2p_args* p);
+
 #ifdef __cplusplus
 }
 #endif
