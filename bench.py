@@ -460,7 +460,9 @@ def run_native(args):
                 "config": {"workload": WORKLOAD, "global_batch": BATCH * world,
                            "parallelism": f"dp{world}" if world > 1 else "single",
                            "precision_tier": TIER_TEXT[args.precision],
-                           "step": (("one CUDA graph per step: forward + masked-MAE loss + backward + clip + Adam + metrics" if world == 1 else "two CUDA graphs per step around the NCCL gradient all-reduce") if graph_mode
+                           "step": (("one CUDA graph per step: forward + masked-MAE loss + backward + clip + Adam + metrics" if world == 1 else
+                                     ("one CUDA graph per step; gradient all-reduce + clip norm = ONE peer-memory kernel over NVLink (gwn_allreduce_adam_step)"
+                                      if getattr(tr, "_p2p_comm", None) is not None else "two CUDA graphs per step around the NCCL gradient all-reduce")) if graph_mode
                                     else "eager launches of the same fused step"),
                            "l2_policy": "per-step working set (~0.9 GB of saved activations) exceeds the 126 MB L2; 4 rotating input batches"},
                 "e2e": {"value": BATCH * world / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,

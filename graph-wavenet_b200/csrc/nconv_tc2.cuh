@@ -33,8 +33,7 @@ using tc::smem_u32; using tc::mbar_init; using tc::mbar_expect_tx; using tc::mba
 using tc::elect_one; using tc::uniform_warp_id; using tc::tma_load_3d; using tc::tc_fence_before; using tc::tc_fence_after;
 using tc::tc_ld16; using tc::tc_wait_ld; using tc::make_desc;
 
-constexpr int SLABS = 4, CH = 32, BLOCK_K = 32, UMMA_K = 8;
-constexpr int X_BYTES = SLABS * BLOCK_K * CH * 4;   // 16 KB: this CTA's 128 rows of the A operand, one k-block
+constexpr int SLABS = 4, CH = 32, UMMA_K = 8;
 constexpr int ACC_COLS = 256;                       // TMEM columns per accumulator buffer (2 buffers)
 constexpr int NUM_THREADS = 256;
 constexpr int MAXSTAGES = 8;
@@ -105,8 +104,13 @@ __device__ __forceinline__ void tc2_mma_tf32(uint32_t d_tmem, uint64_t adesc, ui
 }
 
 // X3 = 3xTF32 mode: D = X.S + X.S_lo + X_lo.S; stage layout per CTA [X | X_lo | S half | S_lo half].
-template <bool X3>
+// BLOCK_K = nodes per pipeline stage: 32 (support rows of 128 B, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B: twice
+// the stages in the same shared memory, see nconv_tc_impl.cuh).
+template <bool X3, int BLOCK_K>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) nconv_tc2_kernel(const __grid_constant__ Maps maps, const Params p) {
+  constexpr int X_BYTES = SLABS * BLOCK_K * CH * 4;   // this CTA's 128 rows of the A operand, one k-block
+  constexpr uint32_t S_LAYOUT = BLOCK_K == 32 ? 2u : 4u;
+  constexpr uint32_t S_SBO = 8 * BLOCK_K * 4;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;   // same offset in both CTAs: the dynamic shared window starts at the same address
@@ -114,7 +118,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) ncon
   constexpr int NPL = X3 ? 2 : 1;
   constexpr int XB = NPL * X_BYTES;
   const int N_TILE = p.n_tile, S_ROWS = N_TILE >> 1;   // this CTA's half of the B tile
-  const int S_BYTES = S_ROWS * BLOCK_K * 4;
+  const int S_TX = S_ROWS * BLOCK_K * 4;                 // bytes one support TMA delivers
+  const int S_BYTES = (S_TX + 1023) & ~1023;             // its plane in the stage: the next X tile must stay 1024-byte aligned
   const int STAGE = NPL * (X_BYTES + S_BYTES);
   const int stages = p.stages;
   const uint32_t bar0 = base + stages * STAGE;
@@ -182,11 +187,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) ncon
             if (X3) {
               mbar_expect_tx(xfull_bar(stage), (uint32_t)X_BYTES);
               tma_load_3d(dst, &maps.x[s], xfull_bar(stage), 0, kb * BLOCK_K, slab0);
-              if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)(4 * S_BYTES));
+              if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)(4 * S_TX));
               tma2_load_2d(dst + XB, &maps.s[s], lfull, kb * BLOCK_K, row0);
               tma2_load_2d(dst + XB + S_BYTES, &maps.slo[s], lfull, kb * BLOCK_K, row0);
             } else {
-              if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)(2 * (X_BYTES + S_BYTES)));
+              if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)(2 * (X_BYTES + S_TX)));
               tma2_load_3d(dst, &maps.x[s], lfull, 0, kb * BLOCK_K, slab0);
               tma2_load_2d(dst + XB, &maps.s[s], lfull, kb * BLOCK_K, row0);
             }
@@ -218,10 +223,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) ncon
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
             const uint64_t adesc = make_desc(xs + kk * (UMMA_K * 128), BLOCK_K * 128, 4 * 128, 1);
-            const uint64_t bdesc = make_desc(bs + kk * (UMMA_K * 4), 16, 1024);
+            const uint64_t bdesc = make_desc(bs + kk * (UMMA_K * 4), 16, S_SBO, S_LAYOUT);
             tc2_mma_tf32(d_tmem, adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
             if (X3) {
-              tc2_mma_tf32(d_tmem, adesc, make_desc(bs + S_BYTES + kk * (UMMA_K * 4), 16, 1024), idesc, 1u);
+              tc2_mma_tf32(d_tmem, adesc, make_desc(bs + S_BYTES + kk * (UMMA_K * 4), 16, S_SBO, S_LAYOUT), idesc, 1u);
               tc2_mma_tf32(d_tmem, make_desc(xs + X_BYTES + kk * (UMMA_K * 128), BLOCK_K * 128, 4 * 128, 1), bdesc, idesc, 1u);
             }
           }
@@ -248,16 +253,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) ncon
         if (!mbar_wait(xfull_bar(stage), phase, 6)) { ok = false; break; }
         const float4* src = reinterpret_cast<const float4*>(smem + (size_t)stage * STAGE);
         float4* dst = reinterpret_cast<float4*>(smem + (size_t)stage * STAGE + X_BYTES);
-        static_assert(X_BYTES / 16 == 64 * 16, "splitter: 16 float4 per thread");
-        float4 v[16];
+        constexpr int NV = X_BYTES / 16 / 64;
+        static_assert(NV * 64 * 16 == X_BYTES, "splitter: whole float4s per thread");
+        float4 v[NV];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = src[t64 + 64 * u];
+        for (int u = 0; u < NV; ++u) v[u] = src[t64 + 64 * u];
 #pragma unroll
-        for (int u = 0; u < 16; ++u)
+        for (int u = 0; u < NV; ++u)
           dst[t64 + 64 * u] = make_float4(tf32_lo(v[u].x), tf32_lo(v[u].y), tf32_lo(v[u].z), tf32_lo(v[u].w));
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 64;" ::: "memory");     // the 64 splitter threads; then ONE release-arrive per CTA
-        if (t64 == 0) mbar_arrive_cluster(map_to_cta(split_bar(stage), 0));
+        asm volatile("bar.sync 1, 64;" ::: "memory");     // the 64 splitter threads; then ONE arrive per CTA.  (A
+        // release at CLUSTER scope here cost ~2000 cycles per stage: the 3xTF32 pair kernel ran at half the speed of the
+        // one-CTA kernel.  The consumer of X_lo is this CTA's own tensor core -- each SM of a pair reads its own A rows --
+        // so the proxy fence above plus the default CTA-scope release is what orders the writes before the MMA.)
+        if (t64 == 0) mbar_arrive_cluster_relaxed(map_to_cta(split_bar(stage), 0));
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -333,9 +342,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) ncon
 }  // namespace tc2
 
 // Eligible: batched or K-concatenated supports shared by all samples.  Returns -1 when not eligible.
-template <bool X3>
+template <bool X3, int BLOCK_K>
 static int node_gemm_tc2_impl(const NodeTcArgs& a, cudaStream_t stream) {
   using namespace tc2;
+  constexpr int X_BYTES = SLABS * BLOCK_K * CH * 4;
   const long long nslabs = (long long)a.B * a.L;
   Maps maps;
   Params p;
@@ -367,7 +377,7 @@ static int node_gemm_tc2_impl(const NodeTcArgs& a, cudaStream_t stream) {
     }
   }
   p.n_wt = (a.V + p.n_tile - 1) / p.n_tile;
-  const int S_BYTES = (p.n_tile / 2) * BLOCK_K * 4;
+  const int S_BYTES = ((p.n_tile / 2) * BLOCK_K * 4 + 1023) & ~1023;
   const int stage_bytes = (X3 ? 2 : 1) * (X_BYTES + S_BYTES);
   p.stages = (tc::SMEM_LIMIT - 2048) / stage_bytes;
   if (p.stages > MAXSTAGES) p.stages = MAXSTAGES;
@@ -386,13 +396,14 @@ static int node_gemm_tc2_impl(const NodeTcArgs& a, cudaStream_t stream) {
     cuuint64_t sd[2] = {(cuuint64_t)a.V, (cuuint64_t)a.V};
     cuuint64_t ss[1] = {(cuuint64_t)a.ld * 4};
     cuuint32_t sb[2] = {BLOCK_K, (cuuint32_t)(p.n_tile / 2)};
-    GWN_TRY(tc::encode(&maps.s[s], a.S[s], 2, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_128B));
+    const CUtensorMapSwizzle s_swz = BLOCK_K == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    GWN_TRY(tc::encode(&maps.s[s], a.S[s], 2, sd, ss, sb, s_swz));
     if (X3) {
       if (!a.Slo[s] || (reinterpret_cast<uintptr_t>(a.Slo[s]) & 15)) {
         set_error("node_gemm_tc2: 3xTF32 mode needs 16-byte aligned support remainders");
         return GWN_ERR_UNSUPPORTED;
       }
-      GWN_TRY(tc::encode(&maps.slo[s], a.Slo[s], 2, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_128B));
+      GWN_TRY(tc::encode(&maps.slo[s], a.Slo[s], 2, sd, ss, sb, s_swz));
     } else {
       maps.slo[s] = maps.s[s];
     }
@@ -407,7 +418,7 @@ static int node_gemm_tc2_impl(const NodeTcArgs& a, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(nconv_tc2_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT);
+    attr_err = cudaFuncSetAttribute(nconv_tc2_kernel<X3, BLOCK_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT);
   });
   if (attr_err != cudaSuccess) {
     set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(attr_err));
@@ -416,7 +427,7 @@ static int node_gemm_tc2_impl(const NodeTcArgs& a, cudaStream_t stream) {
   int num_sms = tc_num_sms() & ~1;
   long long want = 2 * tiles;
   const int grid = (int)(want < num_sms ? want : num_sms);
-  GWN_CUDA(launch_kernel(nconv_tc2_kernel<X3>, dim3(grid), dim3(NUM_THREADS), smem_bytes, stream, maps, p));
+  GWN_CUDA(launch_kernel(nconv_tc2_kernel<X3, BLOCK_K>, dim3(grid), dim3(NUM_THREADS), smem_bytes, stream, maps, p));
   count_launch();
   return 0;
 }

@@ -11,9 +11,12 @@ namespace tc {
 constexpr int BLOCK_M = 128;   // 4 slabs x 32 channels
 constexpr int SLABS = 4;
 constexpr int CH = 32;
-constexpr int BLOCK_K = 32;    // nodes per pipeline stage: one 128-byte swizzle row of K for the support tile
+// Nodes per pipeline stage, BK = 32 (one 128-byte swizzle row of K for the support tile) or 16 (64-byte rows, SWIZZLE_64B):
+// in the 3xTF32 mode a stage holds four planes [X | X_lo | S | S_lo] and only TWO 32-node stages fit beside each other
+// at V ~ 200 -- the MMA issuer then waited for data 40-50 % of the time (ncu r02h: producer blocked on `empty`, splitter
+// on `full`, tensor pipe 53 % active).  Half-size stages put five in the same shared memory: same bytes in flight, but
+// the loads run four stages ahead of the MMAs instead of one.
 constexpr int UMMA_K = 8;      // kind::tf32: 32 bytes of K per instruction
-constexpr int X_STAGE_BYTES = SLABS * BLOCK_K * CH * 4;   // 16 KB
 constexpr int NUM_THREADS = 256;                          // warps 0-3: control roles, warps 4-7: epilogue
 constexpr int ACC_COLS = 256;                             // TMEM columns per accumulator buffer (2 buffers)
 
@@ -38,15 +41,19 @@ struct Params {
 // X3 = 3xTF32 mode (fp32-grade): D = X.S + X.S_lo + X_lo.S with S_lo precomputed in global memory and X_lo produced
 // in shared memory by warps 2 and 3 from the tile TMA just landed (see tcpos.cuh; kind::tf32 truncates, so the fp32
 // tiles themselves are the high parts).  Stage layout: [X | X_lo | S | S_lo].
-template <bool X3>
+template <bool X3, int BLOCK_K>
 __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
+  constexpr int X_STAGE_BYTES = SLABS * BLOCK_K * CH * 4;   // 16 KB (BK = 32) / 8 KB (BK = 16)
+  constexpr int S_ROW_BYTES = BLOCK_K * 4;                  // one support row of a stage: 128 B (SWIZZLE_128B) / 64 B (SWIZZLE_64B)
+  constexpr uint32_t S_LAYOUT = BLOCK_K == 32 ? 2u : 4u;    // descriptor layout type of the K-major support tile
+  constexpr uint32_t S_SBO = 8 * S_ROW_BYTES;               // 8-row groups
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;           // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
   constexpr int NPL = X3 ? 2 : 1;
   constexpr int XB = NPL * X_STAGE_BYTES;                 // X planes of one stage
-  const int s_tile = p.n_tile * 128;                      // one support plane of one stage
+  const int s_tile = p.n_tile * S_ROW_BYTES;              // one support plane of one stage
   const int stage_bytes = XB + NPL * s_tile;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   const uint32_t bar0 = base + p.stages * stage_bytes;
@@ -150,13 +157,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
           uint64_t adesc = make_desc(xs + kk * (UMMA_K * 128), BLOCK_K * 128, 4 * 128, 1);
           uint32_t idesc_k = idesc;
           if (p.mode == 2) {   // debug: A := first 128 rows of the support tile, K-major
-            adesc = make_desc(bs + kk * (UMMA_K * 4), 16, 1024);
+            adesc = make_desc(bs + kk * (UMMA_K * 4), 16, S_SBO, S_LAYOUT);
             idesc_k = idesc & ~(1u << 15);
           }
-          // B (support, K-major): rows of 128 B (32 k), 8-row groups 1024 B apart; this k-step starts 32 B in
-          const uint64_t bdesc = make_desc(bs + kk * (UMMA_K * 4), 16, 1024);
+          // B (support, K-major): rows of BLOCK_K floats, 8-row groups S_SBO apart; this k-step starts 32 B further in
+          const uint64_t bdesc = make_desc(bs + kk * (UMMA_K * 4), 16, S_SBO, S_LAYOUT);
           if (p.mode != 1) tc_mma_tf32(d_tmem, adesc, bdesc, idesc_k, (it > 0 || kk > 0) ? 1u : 0u);
-          if (X3) tc_mma_tf32(d_tmem, adesc, make_desc(bs + s_tile + kk * (UMMA_K * 4), 16, 1024), idesc_k, 1u);
+          if (X3) tc_mma_tf32(d_tmem, adesc, make_desc(bs + s_tile + kk * (UMMA_K * 4), 16, S_SBO, S_LAYOUT), idesc_k, 1u);
         }
         }
         __syncwarp();
@@ -167,7 +174,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
             tc_mma_tf32(d_tmem, make_desc(xs + X_STAGE_BYTES + kk * (UMMA_K * 128), BLOCK_K * 128, 4 * 128, 1),
-                        make_desc(bs + kk * (UMMA_K * 4), 16, 1024), idesc, 1u);
+                        make_desc(bs + kk * (UMMA_K * 4), 16, S_SBO, S_LAYOUT), idesc, 1u);
           }
           __syncwarp();
         }
@@ -193,14 +200,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
         if (!mbar_wait(full_bar(stage), phase, 6)) { ok = false; break; }
         const float4* src = reinterpret_cast<const float4*>(smem + (size_t)stage * stage_bytes);
         float4* dst = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + X_STAGE_BYTES);
-        {   // 16 float4 per thread: all loads in flight before the first use (with 4 at a time the two splitter
+        {   // 16 (8) float4 per thread: all loads in flight before the first use (with 4 at a time the two splitter
             // warps were busy ~100 % of the time, stalled on LDS results: ncu source page of the reduction kernel)
-          static_assert(X_STAGE_BYTES / 16 == 64 * 16, "splitter: 16 float4 per thread");
-          float4 v[16];
+          constexpr int NV = X_STAGE_BYTES / 16 / 64;
+          static_assert(NV * 64 * 16 == X_STAGE_BYTES, "splitter: whole float4s per thread");
+          float4 v[NV];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) v[u] = src[t64 + 64 * u];
+          for (int u = 0; u < NV; ++u) v[u] = src[t64 + 64 * u];
 #pragma unroll
-          for (int u = 0; u < 16; ++u)
+          for (int u = 0; u < NV; ++u)
             dst[t64 + 64 * u] = make_float4(tf32_lo(v[u].x), tf32_lo(v[u].y), tf32_lo(v[u].z), tf32_lo(v[u].w));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -320,9 +328,10 @@ static int tc_num_sms() {
   return n;
 }
 
-template <bool X3>
+template <bool X3, int BLOCK_K>
 static int node_gemm_tc_impl(const NodeTcArgs& a, cudaStream_t stream) {
   using namespace tc;
+  constexpr int X_STAGE_BYTES = SLABS * BLOCK_K * CH * 4;
   if (a.nsup < 1 || a.nsup > TC_MAXSUP) {
     set_error("node_gemm_tc: %d supports (max %d)", a.nsup, TC_MAXSUP);
     return GWN_ERR_UNSUPPORTED;
@@ -366,7 +375,7 @@ static int node_gemm_tc_impl(const NodeTcArgs& a, cudaStream_t stream) {
     }
   }
   p.n_wt = (a.V + p.n_tile - 1) / p.n_tile;
-  const int stage_bytes = (X3 ? 2 : 1) * (X_STAGE_BYTES + p.n_tile * 128);
+  const int stage_bytes = (X3 ? 2 : 1) * (X_STAGE_BYTES + p.n_tile * BLOCK_K * 4);
   p.stages = (SMEM_LIMIT - 2048) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) {
@@ -403,13 +412,14 @@ static int node_gemm_tc_impl(const NodeTcArgs& a, cudaStream_t stream) {
       cuuint32_t xb[3] = {CH, BLOCK_K, SLABS};
       GWN_TRY(encode(&maps.x[s], a.X[s], 3, xd, xs, xb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     }
-    GWN_TRY(encode(&maps.s[s], a.S[s], srank, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_128B));
+    const CUtensorMapSwizzle s_swz = BLOCK_K == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    GWN_TRY(encode(&maps.s[s], a.S[s], srank, sd, ss, sb, s_swz));
     if (X3) {
       if (!a.Slo[s] || (reinterpret_cast<uintptr_t>(a.Slo[s]) & 15)) {
         set_error("node_gemm_tc: 3xTF32 mode needs 16-byte aligned support remainders");
         return GWN_ERR_UNSUPPORTED;
       }
-      GWN_TRY(encode(&maps.slo[s], a.Slo[s], srank, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_128B));
+      GWN_TRY(encode(&maps.slo[s], a.Slo[s], srank, sd, ss, sb, s_swz));
     } else {
       maps.slo[s] = maps.s[s];
     }
@@ -427,7 +437,7 @@ static int node_gemm_tc_impl(const NodeTcArgs& a, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(nconv_tc_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    attr_err = cudaFuncSetAttribute(nconv_tc_kernel<X3, BLOCK_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   });
   const int num_sms = tc_num_sms();
   if (attr_err != cudaSuccess) {
@@ -435,7 +445,7 @@ static int node_gemm_tc_impl(const NodeTcArgs& a, cudaStream_t stream) {
     return GWN_ERR_CUDA;
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  GWN_CUDA(launch_kernel(nconv_tc_kernel<X3>, dim3(grid), dim3(NUM_THREADS), smem_bytes, stream, maps, p));
+  GWN_CUDA(launch_kernel(nconv_tc_kernel<X3, BLOCK_K>, dim3(grid), dim3(NUM_THREADS), smem_bytes, stream, maps, p));
   count_launch();
   return 0;
 }
@@ -452,19 +462,33 @@ int node_gemm_tc(const NodeTcArgs& a, cudaStream_t stream) {
     const char* e = getenv("GWNET_B200_NCONV_2CTA");
     return !(e && e[0] == '0');
   }();
-  // Smallest graph that takes the CTA-pair kernel (GWNET_B200_NCONV_2CTA_MINV for A/B runs).  Default V > 256: at
-  // V ~ 200 a tile has only 7 k-blocks and the pair kernel measured 3-5 % SLOWER than the one-CTA kernel in both
-  // tiers (r02c/r02d sweeps, METR-LA step 2.82-2.89 vs 2.74 ms) -- neither kernel is paced by MMA issue there.
-  static const int min_v = [] {
+  // Which graphs take the CTA-pair kernel (GWNET_B200_NCONV_2CTA_MINV overrides both thresholds for A/B runs):
+  //   V > 256: always -- the one-CTA kernel is bound by its L2 -> SM operand fill there (544 vs 774 TFLOP/s at N = 2048);
+  //   V <= 256, 3xTF32: pairs with half-size stages (seven 29 KB stages per CTA): METR-LA step 2.71 -> 2.65 ms (r02l);
+  //   V <= 256, tf32: the one-CTA kernel (both are HBM-bound there: 5.7 TB/s at V = 207, and it is 1 % faster).
+  static const int min_v_env = [] {
     const char* e = getenv("GWNET_B200_NCONV_2CTA_MINV");
-    return e ? atoi(e) : 257;
+    return e ? atoi(e) : -1;
   }();
+  const int min_v = min_v_env >= 0 ? min_v_env : (a.Slo[0] ? 16 : 257);
   if (two_cta && !a.per_sample && a.V >= min_v && a.V >= 16 && a.nsup >= 1 && a.nsup <= TC_MAXSUP && a.ld % 4 == 0 && a.ld >= a.V &&
       (long long)a.B * a.L > 0) {
-    const int st = a.Slo[0] ? node_gemm_tc2_impl<true>(a, stream) : node_gemm_tc2_impl<false>(a, stream);
+    static const int bk2 = [] {   // GWNET_B200_NCONV2_BK = 32: 32-node stages also on small graphs (A/B runs)
+      const char* e = getenv("GWNET_B200_NCONV2_BK");
+      return (e && atoi(e) == 32) ? 32 : 16;
+    }();
+    int st;
+    if (bk2 == 16 && a.V <= 256) st = a.Slo[0] ? node_gemm_tc2_impl<true, 16>(a, stream) : node_gemm_tc2_impl<false, 16>(a, stream);
+    else st = a.Slo[0] ? node_gemm_tc2_impl<true, 32>(a, stream) : node_gemm_tc2_impl<false, 32>(a, stream);
     if (st >= 0) return st;
   }
-  return a.Slo[0] ? node_gemm_tc_impl<true>(a, stream) : node_gemm_tc_impl<false>(a, stream);
+  // 3xTF32 on small graphs: half-size stages (see BLOCK_K above); GWNET_B200_NCONV_BK=32 restores the 32-node stages
+  static const int bk_x3 = [] {
+    const char* e = getenv("GWNET_B200_NCONV_BK");
+    return (e && atoi(e) == 32) ? 32 : 16;
+  }();
+  if (a.Slo[0]) return (bk_x3 == 16 && a.V <= 256) ? node_gemm_tc_impl<true, 16>(a, stream) : node_gemm_tc_impl<true, 32>(a, stream);
+  return node_gemm_tc_impl<false, 32>(a, stream);
 }
 
 }  // namespace gwn

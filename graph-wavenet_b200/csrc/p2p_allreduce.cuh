@@ -80,11 +80,14 @@ __global__ void __launch_bounds__(P2P_THREADS) p2p_allreduce_gradnorm_kernel(con
   __syncthreads();
   double s = 0.0;
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += (i64)gridDim.x * blockDim.x) {
-    float4 acc = p2p_load4(a.grad[0] + 4 * i);
-    for (int q = 1; q < a.world; ++q) {
-      const float4 v = p2p_load4(a.grad[q] + 4 * i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
+    float4 v[P2P_MAXRANKS];       // all peers' loads in flight before the first use (one NVLink round trip, not `world`)
+#pragma unroll
+    for (int q = 0; q < P2P_MAXRANKS; ++q)
+      if (q < a.world) v[q] = p2p_load4(a.grad[q] + 4 * i);
+    float4 acc = v[0];
+#pragma unroll
+    for (int q = 1; q < P2P_MAXRANKS; ++q)
+      if (q < a.world) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }   // rank order on every rank
     st4(a.out + 4 * i, acc);
     if (a.live4[i]) s += (double)acc.x * acc.x + (double)acc.y * acc.y + (double)acc.z * acc.z + (double)acc.w * acc.w;
   }

@@ -45,18 +45,21 @@ def check(B, L, V):
 
 def perf(V, B, L, iters=10):
     gen = torch.Generator().manual_seed(V)
-    S = torch.softmax(torch.randn(V, V, generator=gen), dim=1).to(dev).contiguous()
+    ld = (V + 3) // 4 * 4
+    S = torch.zeros(V, ld)
+    S[:, :V] = torch.softmax(torch.randn(V, V, generator=gen), dim=1)
+    S = S.to(dev).contiguous()
     Slo = torch.empty_like(S)
     lib.check(lib.dll.gwn_split_lo(S.data_ptr(), Slo.data_ptr(), S.numel(), st))
     x = torch.randn(B, L, V, 32, device=dev)
     y = torch.empty_like(x)
     for tier in ("tf32", "fp32x3"):
         for _ in range(3):
-            run(tier, x, S, Slo, V, y, B, L, V)
+            run(tier, x, S, Slo, ld, y, B, L, V)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(iters):
-            run(tier, x, S, Slo, V, y, B, L, V)
+            run(tier, x, S, Slo, ld, y, B, L, V)
         e1.record(); e1.synchronize()
         ms = e0.elapsed_time(e1) / iters
         print(json.dumps({"perf": mode, "V": V, "B": B, "L": L, "tier": tier, "us": round(ms * 1e3, 1),
@@ -65,10 +68,18 @@ def perf(V, B, L, iters=10):
 
 if __name__ == "__main__":
     ok = True
-    if not (len(sys.argv) > 1 and sys.argv[1] in ("perf_only", "ncu")):
+    if not (len(sys.argv) > 1 and sys.argv[1] in ("perf_only", "ncu", "small", "ncu_small")):
         for B, L, V in [(2, 3, 300), (5, 1, 325), (1, 8, 512), (3, 7, 1000), (2, 12, 2048), (1, 1, 257)]:
             ok = check(B, L, V) and ok
         print("correctness:", "OK" if ok else "FAILED", flush=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "small":     # METR-LA-sized graphs: one-CTA vs pair kernel (GWNET_B200_NCONV_2CTA_MINV=0)
+        perf(207, 64, 12, iters=20)
+        perf(207, 64, 96, iters=10)
+        perf(256, 64, 96, iters=10)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ncu_small":  # profiler run on the METR-LA-sized contraction
+        perf(207, 64, 96, iters=2)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ncu":        # short run for the profiler: 5 launches per tier at config 4's layer-0 shape
         perf(2048, 64, 24, iters=2)
         sys.exit(0)
