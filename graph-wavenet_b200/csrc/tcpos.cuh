@@ -78,8 +78,13 @@ struct TpParams {
 // planes are precomputed; the A remainder is produced in shared memory by two otherwise idle warps (2, 3) from the
 // tile TMA just landed: the element-wise split preserves the swizzled layout.  kind::tf32 ignores the low 13
 // mantissa bits of its operands (probed: tests/tools/tf32_rounding_probe.py), so the fp32 A tile itself serves as A_hi.
-template <class EP, int NCT, bool X3>   // NCT > 0: compile-time column count (keeps per-slot epilogue state in registers)
+// BK = channels of a K segment per pipeline stage: 32 (default: one stage per segment, rows of 128 B, SWIZZLE_128B) or 16
+// (opt-in experiment: two half-segment stages, 64-byte rows, SWIZZLE_64B; see launch_tcpos).  Resident weights only.
+template <class EP, int NCT, bool X3, int BK = 32>   // NCT > 0: compile-time column count (keeps per-slot epilogue state in registers)
 __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const __grid_constant__ TpMaps maps, const TpParams p, const EP ep_in) {
+  constexpr int A_BYTES = 128 * BK * 4;                   // one stage of the A operand: 128 rows x BK floats
+  constexpr int KH = 32 / BK;                             // stages per 32-channel K segment
+  constexpr uint32_t A_SBO = 8 * BK * 4, A_LAYOUT = BK == 32 ? 2u : 4u;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
   // Streamed weights (head layers, N <= 128 per tile) keep W_lo's k-block behind W's inside every stage: same trick.
   const bool NCAT = X3 && !EP::kDirectStore && (NCT > 0 ? NCT <= 64 : (p.wstream != 0 && p.N <= 128));
   const int w_blk = p.N * 128;                            // one k-block of weights: [N rows][128 B]
-  const int STG = NPL * TP_A_BYTES + (p.wstream ? NPL * w_blk : 0);   // bytes per stage: [A | A_lo | (W blk | W_lo blk)]
+  const int STG = NPL * A_BYTES + (p.wstream ? NPL * w_blk : 0);      // bytes per stage: [A | A_lo | (W blk | W_lo blk)]
   const int w_plane = p.nseg * w_blk;                     // resident weights: [plane][seg][N rows][128 B]
   const int w_bytes = p.wstream ? 0 : NPL * w_plane;
   const uint32_t a0 = base + w_bytes;                     // A stages: [A | A_lo]
@@ -186,13 +191,14 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
         eb ^= 1;
         if (eb == 0) ephase ^= 1u;
       }
-      for (int s = 0; s < p.nseg; ++s) {
+      for (int sh = 0; sh < p.nseg * KH; ++sh) {
+        const int s = sh / KH, h = sh - s * KH;
         if (!mbar_wait_warp(empty_bar(stage), phase ^ 1u, 11)) { ok = false; break; }
         if (elect_one()) {
-          mbar_expect_tx(full_bar(stage), TP_A_BYTES + (p.wstream ? NPL * w_blk : 0));
-          tma_load_3d(a0 + stage * STG, &maps.a[s], full_bar(stage), p.col0[s], rt * 128 + p.rshift[s], b);
+          mbar_expect_tx(full_bar(stage), A_BYTES + (p.wstream ? NPL * w_blk : 0));
+          tma_load_3d(a0 + stage * STG, &maps.a[s], full_bar(stage), p.col0[s] + h * BK, rt * 128 + p.rshift[s], b);
           if (p.wstream) {
-            const uint32_t wdst = a0 + stage * STG + NPL * TP_A_BYTES;
+            const uint32_t wdst = a0 + stage * STG + NPL * A_BYTES;
             tma_load_2d(wdst, &maps.w, full_bar(stage), s * 32, nt * p.N);
             if (X3) tma_load_2d(wdst + w_blk, &maps.wlo, full_bar(stage), s * 32, nt * p.N);
           }
@@ -213,22 +219,25 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
       if (!mbar_wait_warp(tempty_bar(acc), accphase ^ 1u, 13)) break;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
-      for (int s = 0; s < p.nseg; ++s) {
+      for (int sh = 0; sh < p.nseg * KH; ++sh) {
+        const int s = sh / KH, h = sh - s * KH;
         if (!mbar_wait_warp(full_bar(stage), phase, 14)) { ok = false; break; }
         tc_fence_after();
         const uint32_t as = a0 + stage * STG;
-        const uint32_t ws = p.wstream ? as + NPL * TP_A_BYTES : (NCAT ? base + s * 2 * w_blk : base + s * w_blk);
+        // this stage's k-block of the weights: the segment's [N rows][128 B] tile, h * BK floats into every row
+        const uint32_t ws = (p.wstream ? as + NPL * A_BYTES : (NCAT ? base + s * 2 * w_blk : base + s * w_blk)) + h * (BK * 4);
         const uint32_t wlo_off = p.wstream ? (uint32_t)w_blk : (uint32_t)w_plane;
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            // both operands K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart, this k-step 32 B in
-            const uint64_t ad = make_desc(as + kk * 32, 16, 1024), wd = make_desc(ws + kk * 32, 16, 1024);
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            // both operands K-major: A rows of BK floats (8-row groups A_SBO apart), W rows of 128 B (SWIZZLE_128B,
+            // 8-row groups 1024 B apart); this k-step 32 B further in
+            const uint64_t ad = make_desc(as + kk * 32, 16, A_SBO, A_LAYOUT), wd = make_desc(ws + kk * 32, 16, 1024);
             if (NCAT) {   // A.[W | W_lo]: 2N columns
               const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * p.N) >> 3) << 17);
-              tc_mma_tf32(d_tmem, ad, wd, idesc2, (s > 0 || kk > 0) ? 1u : 0u);
+              tc_mma_tf32(d_tmem, ad, wd, idesc2, (sh > 0 || kk > 0) ? 1u : 0u);
             } else {
-              tc_mma_tf32(d_tmem, ad, wd, idesc, (s > 0 || kk > 0) ? 1u : 0u);
+              tc_mma_tf32(d_tmem, ad, wd, idesc, (sh > 0 || kk > 0) ? 1u : 0u);
               if (X3) tc_mma_tf32(d_tmem, ad, make_desc(ws + wlo_off + kk * 32, 16, 1024), idesc, 1u);
             }
           }
@@ -239,8 +248,8 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              tc_mma_tf32(d_tmem, make_desc(as + TP_A_BYTES + kk * 32, 16, 1024), make_desc(ws + kk * 32, 16, 1024), idesc, 1u);
+            for (int kk = 0; kk < BK / 8; ++kk)
+              tc_mma_tf32(d_tmem, make_desc(as + A_BYTES + kk * 32, 16, A_SBO, A_LAYOUT), make_desc(ws + kk * 32, 16, 1024), idesc, 1u);
           }
           __syncwarp();
         }
@@ -261,18 +270,19 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
     uint32_t phase = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
-      for (int s = 0; s < p.nseg; ++s) {
+      for (int sh = 0; sh < p.nseg * KH; ++sh) {
         if (!mbar_wait(full_bar(stage), phase, 17)) { ok = false; break; }
         const float4* src = reinterpret_cast<const float4*>(smem + w_bytes + (size_t)stage * STG);
-        float4* dst = reinterpret_cast<float4*>(smem + w_bytes + (size_t)stage * STG + TP_A_BYTES);
-        {   // 16 float4 per thread: all loads in flight before the first use (with 4 at a time the two splitter
+        float4* dst = reinterpret_cast<float4*>(smem + w_bytes + (size_t)stage * STG + A_BYTES);
+        {   // 16 (8) float4 per thread: all loads in flight before the first use (with 4 at a time the two splitter
             // warps were busy ~100 % of the time, stalled on LDS results: ncu source page of the reduction kernel)
-          static_assert(TP_A_BYTES / 16 == 64 * 16, "splitter: 16 float4 per thread");
-          float4 v[16];
+          constexpr int NV = A_BYTES / 16 / 64;
+          static_assert(NV * 64 * 16 == A_BYTES, "splitter: whole float4s per thread");
+          float4 v[NV];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) v[u] = src[t64 + 64 * u];
+          for (int u = 0; u < NV; ++u) v[u] = src[t64 + 64 * u];
 #pragma unroll
-          for (int u = 0; u < 16; ++u)
+          for (int u = 0; u < NV; ++u)
             dst[t64 + 64 * u] = make_float4(tf32_lo(v[u].x), tf32_lo(v[u].y), tf32_lo(v[u].z), tf32_lo(v[u].w));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
@@ -415,7 +425,7 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
 #endif
 
 // Returns 0 after launching; -1 when the shape is not eligible (caller falls back); > 0 on error.
-template <int NCT, bool X3, class EP>
+template <int NCT, bool X3, int BK, class EP>
 int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
 #if GWN_EMU
   (void)a; (void)ep; (void)stream;
@@ -438,7 +448,8 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
   if (tiles > 2147483647LL) return -1;
   p.total_tiles = (int)tiles;
   const int w_bytes = a.wstream ? 0 : (X3 ? 2 : 1) * a.nseg * a.N * 128;
-  const int STG = (X3 ? 2 : 1) * (TP_A_BYTES + (a.wstream ? a.N * 128 : 0));
+  if (BK != 32 && a.wstream) return -1;                   // half-size stages: resident weights only
+  const int STG = (X3 ? 2 : 1) * (128 * BK * 4 + (a.wstream ? a.N * 128 : 0));
   constexpr int NSO = (EP::kGroups == 1) ? 2 : 2 * ((NCT > 0 && NCT / EP::kAccPerBlock == 1) ? 1 : 2);
   constexpr int FIXED = (NSO + 2 * EP::kAddends) * TP_A_BYTES;   // output staging tiles + addend tiles
   p.stages = (SMEM_LIMIT - 2048 - w_bytes - FIXED) / STG;
@@ -481,8 +492,8 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
     if ((reinterpret_cast<uintptr_t>(g.src) & 15) || g.row_width % 4 != 0 || g.col0 >= g.row_width) return -1;   // a box past the row end reads zeros
     cuuint64_t d[3] = {(cuuint64_t)g.row_width, (cuuint64_t)g.rows_src, (cuuint64_t)a.nb};
     cuuint64_t st[2] = {(cuuint64_t)g.row_width * 4, (cuuint64_t)g.rows_src * g.row_width * 4};
-    cuuint32_t box[3] = {32, 128, 1};
-    GWN_TRY(encode(&maps.a[s], g.src, 3, d, st, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    cuuint32_t box[3] = {(cuuint32_t)BK, 128, 1};
+    GWN_TRY(encode(&maps.a[s], g.src, 3, d, st, box, BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
     p.col0[s] = g.col0;
     p.rshift[s] = g.rshift;
   }
@@ -503,7 +514,7 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
   for (int k = 0; k < 2; ++k)
     if (!p.add_on[k]) maps.add[k] = maps.out;
   const int smem_bytes = w_bytes + p.stages * STG + FIXED + 1024 + 1024;
-  static cudaError_t attr = cudaFuncSetAttribute(tcpos_kernel<EP, NCT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  static cudaError_t attr = cudaFuncSetAttribute(tcpos_kernel<EP, NCT, X3, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   if (attr != cudaSuccess) {
     set_error("tcpos: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr));
     return GWN_ERR_CUDA;
@@ -515,7 +526,7 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
     return n;
   }();
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  GWN_CUDA(launch_kernel(tcpos_kernel<EP, NCT, X3>, dim3(grid), dim3(128 + 128 * EP::kGroups), smem_bytes, stream, maps, p, ep));
+  GWN_CUDA(launch_kernel(tcpos_kernel<EP, NCT, X3, BK>, dim3(grid), dim3(128 + 128 * EP::kGroups), smem_bytes, stream, maps, p, ep));
   count_launch();
   return 0;
 #endif
@@ -523,7 +534,20 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
 
 template <int NCT, class EP>
 int launch_tcpos(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
-  return a.Wp_lo ? launch_tcpos_impl<NCT, true>(a, ep, stream) : launch_tcpos_impl<NCT, false>(a, ep, stream);
+  if (!a.Wp_lo) return launch_tcpos_impl<NCT, false, 32>(a, ep, stream);
+  // 3xTF32 with resident weights: GWNET_B200_TCPOS_BK=16 selects half-size stages (A/B runs).  Measured (r02o): no gain --
+  // METR-LA step 2.685 vs 2.644 ms, mlp forward 316 vs 300 us: unlike the node contraction these kernels are bound by
+  // the BYTES in flight per SM (three 16 KB raw planes beside 57 KB of weights and 64 KB of staging tiles), and six
+  // half-size stages hold the same bytes as three full ones.
+  static const bool half = [] {
+    const char* e = getenv("GWNET_B200_TCPOS_BK");
+    return e && atoi(e) == 16;
+  }();
+  if (half && !a.wstream) {
+    const int st = launch_tcpos_impl<NCT, true, 16>(a, ep, stream);
+    if (st >= 0) return st;
+  }
+  return launch_tcpos_impl<NCT, true, 32>(a, ep, stream);
 }
 
 }  // namespace gwn
