@@ -189,7 +189,9 @@ def roofline_leg(lib, step_fn, dev, steps=5):
                       "tensor_frac": tfs / tens_peak, "flop_per_byte": ai, "bound": "tensor" if ai > ridge else "hbm"})
     table.sort(key=lambda r: -r["share"])
     # kernel families: which hand-written kernel runs each operator's dominant launch
-    fam_of = {"nconv_fwd": "nconv_tc_kernel", "nconv_bwd_dx_hops": "nconv_tc_kernel", "nconv_bwd_dx_sum": "nconv_tc_kernel",
+    # node contraction: CTA-pair kernel (nconv_tc2.cuh) in the 3xTF32 tier, one-CTA kernel in the tf32 tier at this graph size
+    nck = "nconv_tc2_kernel" if tier == "fp32x3" else "nconv_tc_kernel"
+    fam_of = {"nconv_fwd": nck, "nconv_bwd_dx_hops": nck, "nconv_bwd_dx_sum": nck,
               "nconv_bwd_dA": "tcred_kernel", "gcn_mlp_wgrad": "tcred_kernel", "gated_tcn_wgrad": "tcred_kernel",
               "gated_tcn_fwd": "tcpos_kernel<RowGate>", "gated_tcn_bwd_gate": "tcpos_kernel<RowGateBwd>",
               "gated_tcn_dgrad": "tcpos_kernel<RowTcnDgrad>", "gcn_mlp_fwd": "tcpos_kernel<RowMlp>",

@@ -12,7 +12,8 @@
  *   - every function returns 0 on success, else a gwn_status / cudaError code;
  *     gwn_last_error() returns a thread-local message.  Nothing throws or exits.
  *   - the caller owns every buffer (parameters, activations, workspace); the
- *     library allocates no device memory.
+ *     library allocates no device memory (one explicit exception: gwn_p2p_alloc,
+ *     the IPC-exportable gradient buffer of the data-parallel exchange).
  *   - all work is ordered on the cudaStream_t passed as `stream` (void*), on the
  *     caller's current device; no implicit synchronisation; re-entrant (forward
  *     is called from the main thread, backward from PyTorch's autograd thread).
