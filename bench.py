@@ -437,6 +437,20 @@ def run_native(args):
         roof = roofline_leg(lib, step_resident, dev)
         tr.use_graph = graph_mode
 
+    # BASELINE config 5 as written: GLOBAL batch 512 split 512/N per GPU (strong scaling), same step, same tier
+    strong = None
+    if not args.skip_strong and 512 % world == 0:
+        bs = 512 // world
+        gen_s = torch.Generator().manual_seed(200 + rank)
+        sx, sy = O.synthetic_batch(bs, NODES, SEQ, IN_DIM, gen_s)
+        sx, sy = sx.to(dev), sy.to(dev)
+        for _ in range(3):
+            tr.train(sx, sy)
+        ms_s = timed(lambda i: tr.train(sx, sy), max(10, args.steps // 4))
+        strong = {"global_batch": 512, "batch_per_gpu": bs, "ms_per_step": ms_s, "value": 512 / (ms_s * 1e-3), "unit": "samples/s",
+                  "scaling": "strong", "what": "BASELINE config 5: METR-LA shape at global batch 512 = 512/N per GPU"}
+        del sx, sy
+
     tiers = None
     if world == 1 and not args.skip_tiers and args.precision in ("fp32x3", "tf32"):
         other = "tf32" if args.precision == "fp32x3" else "fp32x3"
@@ -473,6 +487,8 @@ def run_native(args):
                 "model_tflops": algorithmic_gflop_per_step(BATCH * world) / ms, "clocks": clocks}
         if tiers:
             line["other_tiers"] = tiers
+        if strong:
+            line["strong_512"] = strong
         if roof is not None:
             line["roofline"], line["operators"] = roof
         if world == 1 and not args.skip_extras:
@@ -502,6 +518,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the fused step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only")
     ap.add_argument("--skip-roofline", action="store_true", help="profiling runs only")
+    ap.add_argument("--skip-strong", action="store_true", help="skip the strong-scaling record (global batch 512 = 512/N per GPU)")
     ap.add_argument("--skip-extras", action="store_true",
                     help="skip the N=1 context records (gcn contraction at N=2048/4096, reference eager on the GPU, config-4 step)")
     args = ap.parse_args()

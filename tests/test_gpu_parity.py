@@ -346,7 +346,7 @@ def test_dropout_statistics_and_determinism(M):
 
 
 # ------------------------------------------------------------------------------------------------ tcgen05 (tf32) tier
-@pytest.mark.parametrize("B,L,V", [(1, 4, 32), (2, 3, 207), (3, 5, 50), (5, 1, 325), (2, 2, 300), (7, 3, 17)])
+@pytest.mark.parametrize("B,L,V", [(1, 4, 32), (2, 3, 207), (3, 5, 50), (5, 1, 325), (2, 2, 300), (7, 3, 17), (3, 3, 1000), (9, 1, 256)])
 def test_tcgen05_node_contract(M, B, L, V):
     """gwn_node_contract on the tcgen05/TMEM/TMA kernel vs fp64: ragged node counts (V % 16, V % 32 != 0, V > 256)
     and slab counts that do not fill the 4-slab tile."""
@@ -367,6 +367,14 @@ def test_tcgen05_node_contract(M, B, L, V):
     assert lib.dll.gwn_tc_error_flag(1) == 0
     assert not torch.isnan(y).any()
     assert_close_rel(y, ref, 2e-3, "tf32 node contraction")
+    # the same contraction in the fp32-grade 3xTF32 tier (the default one): 1e-5 against fp64
+    Slo = torch.empty_like(Sd)
+    lib.check(lib.dll.gwn_split_lo(Sd.data_ptr(), Slo.data_ptr(), Sd.numel(), st))
+    y3 = torch.full((B, L, V, 32), float("nan"), device=dev)
+    lib.check(lib.dll.gwn_node_contract_x3(xd.data_ptr(), Sd.data_ptr(), Slo.data_ptr(), ld, y3.data_ptr(), B, L, V, 32, st))
+    torch.cuda.synchronize()
+    assert lib.dll.gwn_tc_error_flag(1) == 0
+    assert_close_rel(y3, ref, 1e-5, "3xTF32 node contraction")
 
 
 @pytest.mark.parametrize("name", ["c32"])
