@@ -32,6 +32,11 @@ struct NodeTcArgs {
 
 // Returns GWN_ERR_UNSUPPORTED (with a message) when the shape cannot use this kernel.
 int node_gemm_tc(const NodeTcArgs& a, cudaStream_t stream);
+// Both hops of an order-2 gcn for all supports in ONE launch (gcn_hops_fused.cuh: support resident in shared memory, hop 2
+// fed from the hop-1 accumulator in tensor memory; single-pass TF32 tier, V <= 256).  S[s]: K-contiguous supports [V][ld];
+// Y1[s] / Y2[s]: the hop-1 / hop-2 tensors.  0 = launched, -1 = not eligible (run two node_gemm_tc launches), > 0 = error.
+int gcn_hops_fused_tc(const float* x, const float* const* S, int nsup, int ld, float* const* Y1, float* const* Y2, int B, int L, int V,
+                      cudaStream_t stream);
 int tc_error_flag(int reset);
 void tc_set_debug_buffer(float* p);
 void tc_set_debug_mode(int m);

@@ -493,6 +493,8 @@ int node_gemm_tc(const NodeTcArgs& a, cudaStream_t stream) {
 
 }  // namespace gwn
 
+#include "gcn_hops_fused.cuh"
+
 #else   // GWN_EMU: the tensor-core tier exists only on the GPU
 namespace gwn {
 void tc_set_debug_buffer(float*) {}
@@ -502,5 +504,6 @@ int node_gemm_tc(const NodeTcArgs&, cudaStream_t) {
   set_error("the tcgen05 tier is not part of the host emulation");
   return GWN_ERR_UNSUPPORTED;
 }
+int gcn_hops_fused_tc(const float*, const float* const*, int, int, float* const*, float* const*, int, int, int, cudaStream_t) { return -1; }
 }  // namespace gwn
 #endif

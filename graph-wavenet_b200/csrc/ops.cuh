@@ -329,6 +329,17 @@ inline int gcn_hops_forward(const GcnShape& g, const float* x, const SupportView
                             cudaStream_t stream, const TcSupports* tcs = nullptr, i64 hop_stride = 0) {
   const i64 PD = hop_stride > 0 ? hop_stride : (i64)g.B * g.L * g.V * g.D;
   ProfScope prof("nconv_fwd", stream, 4.0 * PD * (1 + g.S + 2.0 * g.S * (g.order - 1)), 2.0 * PD * g.V * g.S * g.order);
+  if (tcs && tcs->precision == GWN_PREC_TF32 && !tcs->per_sample && g.order == 2 && g.D == 32 && hop_stride == 0 && g.S <= TC_MAXSUP) {
+    // tf32 tier, small graph: both hops of all supports in ONE launch (support resident in shared memory, hop 2 from TMEM)
+    float* Y1[MAXSUP];
+    float* Y2[MAXSUP];
+    for (int s = 0; s < g.S; ++s) {
+      Y1[s] = hops + (i64)(hop_index(g, s, 1) - 1) * PD;
+      Y2[s] = hops + (i64)(hop_index(g, s, 2) - 1) * PD;
+    }
+    const int st = gcn_hops_fused_tc(x, tcs->S, g.S, tcs->ld, Y1, Y2, g.B, g.L, g.V, stream);
+    if (st >= 0) return st;
+  }
   for (int k = 1; k <= g.order; ++k) {
     const float* X[MAXSUP];
     float* Y[MAXSUP];

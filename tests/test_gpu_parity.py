@@ -207,6 +207,47 @@ def test_gcn_operator_tensor_core_tiers(M, S, order, p, tier):
         assert_close_rel(a.grad, r.grad, tol, f"gcn[{tier}] dA")
 
 
+@pytest.mark.parametrize("B,L,V,S", [(2, 3, 53, 1), (3, 5, 207, 3), (1, 1, 16, 2), (5, 2, 256, 2), (9, 1, 207, 3)])
+def test_fused_hop_chain_tf32(M, B, L, V, S):
+    """gcn_hops_fused_kernel (tf32 tier, V <= 256, order 2): the support resident in shared memory, hop 2 fed from the
+    hop-1 accumulator in tensor memory.  Both hop tensors of every support against fp64 at the tier's own rounding
+    (single-pass TF32 operands: ~8e-4 per contraction), through gwn_gcn_fwd."""
+    import ctypes
+    from graph_wavenet_b200 import native as NV
+    lib = NV.get_lib()
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    gen = torch.Generator().manual_seed(V + L + S)
+    x = torch.randn(B, L, V, 32, generator=gen)
+    sup = [torch.softmax(torch.randn(V, V, generator=gen), dim=1) * (1 + torch.rand(V, V, generator=gen)) for _ in range(S)]
+    W = (torch.randn(32, (2 * S + 1) * 32, generator=gen) * 0.1).to(dev)
+    b = torch.zeros(32, device=dev)
+    xd = x.to(dev)
+    supd = [s.to(dev).contiguous() for s in sup]
+    hops = torch.full((2 * S, B, L, V, 32), float("nan"), device=dev)
+    y = torch.empty(B, L, V, 32, device=dev)
+    d = NV.GwnGcnDesc(B, L, V, 32, 32, S, 2, NV.PREC_TF32, NV.DROPOUT_NONE, 0.0, 0, 0)
+    ws = torch.empty(int(lib.dll.gwn_gcn_workspace_floats(ctypes.byref(d), 0)), device=dev)
+    sp = NV.ptr_array([s.data_ptr() for s in supd])
+    lds = (ctypes.c_int64 * S)(*[V] * S)
+    lib.dll.gwn_launch_count(1)
+    lib.check(lib.dll.gwn_gcn_fwd(ctypes.byref(d), xd.data_ptr(), sp, lds, W.data_ptr(), b.data_ptr(), None, hops.data_ptr(), y.data_ptr(),
+                                  ws.data_ptr(), st), "gwn_gcn_fwd")
+    torch.cuda.synchronize()
+    assert lib.dll.gwn_tc_error_flag(1) == 0
+    assert int(lib.dll.gwn_launch_count(1)) == S + 1 + 1          # S support packs + ONE hop-chain launch + the mlp
+    assert not torch.isnan(hops).any()
+    segs = [x.double()]
+    for s in range(S):
+        h1 = torch.einsum("blvc,vw->blwc", x.double(), sup[s].double())
+        h2 = torch.einsum("blvc,vw->blwc", h1, sup[s].double())
+        assert_close_rel(hops[2 * s], h1, 2e-3, f"fused hop 1, support {s}")
+        assert_close_rel(hops[2 * s + 1], h2, 3e-3, f"fused hop 2, support {s}")
+        segs += [h1, h2]
+    yr = torch.einsum("blvk,ok->blvo", torch.cat(segs, dim=3), W.double().cpu())
+    assert_close_rel(y, yr, 5e-3, "gcn output on the fused hop chain")
+
+
 def test_linear_operator(M):
     dev = torch.device("cuda:0")
     gen = torch.Generator().manual_seed(4)
