@@ -327,7 +327,7 @@ static int build_plan(gwn_plan* p) {
   // head on tcgen05: default widths only (K segments of 32, column tiles of <= 256)
   p->head_tc = (c.precision == GWN_PREC_TF32 || c.precision == GWN_PREC_FP32X3) && D == 32 && nL <= TP_MAXSEG &&
                Sk % 32 == 0 && Sk <= 512 && (Sk <= 128 || Sk % 256 == 0) && E % 32 == 0 && E <= 512 &&
-               (E <= 128 || E % 256 == 0) && c.out_dim <= 16 && (nL * D <= 128 || (nL * D) % 256 == 0);
+               (E <= 128 || E % 256 == 0) && c.out_dim <= 256 && (nL * D <= 128 || (nL * D) % 256 == 0);
   {
     const bool hx3 = p->head_tc && c.precision == GWN_PREC_FP32X3;
     p->o_hk_wcat = take(p->head_tc ? (i64)Sk * nL * D : 0);
@@ -774,11 +774,17 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
       memset(&t, 0, sizeof(t));
       for (int q = 0; q < E / 32; ++q) t.seg[q] = TcPosSeg{ws + p->o_e1, (int)PT, E, 32 * q, 0};
       t.nseg = E / 32; t.nb = 1; t.rows_out = (int)PT; t.Wp = P_<float>(prm, p->i_e2w); t.Wp_lo = h3 ? ws + p->o_hk_e2lo : nullptr;
-      t.N = 16; t.w_rows = c.out_dim;
+      t.w_rows = c.out_dim;
       RowNCHW ep;
       memset(&ep, 0, sizeof(ep));
       ep.y = a->output; ep.bias = P_<float>(prm, p->i_e2b); ep.O = c.out_dim; ep.N = N; ep.T = p->T_out;
-      hs = launch_tcpos<16>(t, ep, st);
+      if (c.out_dim <= 16) {   // the 12-step configurations: 16 output columns, weights resident
+        t.N = 16;
+        hs = launch_tcpos<16>(t, ep, st);
+      } else {                 // longer horizons (the fork's seq_length 48): wider tile, weights streamed per k-block
+        t.N = round_up(c.out_dim, 16); t.wstream = 1; t.N_total = t.N;
+        hs = launch_tcpos<0>(t, ep, st);
+      }
       if (hs > 0) return hs;
       GWN_CHECK_ARG(hs == 0, "forward: head layer 3 not eligible for the tcgen05 path after layers 1-2 ran on it");
       head_done = true;
@@ -904,8 +910,9 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     {  // (a) de1 = (dout . W2) * (e1 > 0)
       TcPosArgs t;
       memset(&t, 0, sizeof(t));
-      t.seg[0] = TcPosSeg{dout, (int)PT, p->ldo, 0, 0};
-      t.nseg = 1; t.nb = 1; t.rows_out = (int)PT; t.Wp = sc + p->o_hb_w2t; t.Wp_lo = h3 ? sc + p->o_hb_w2t_lo : nullptr;
+      const int nsd = (p->ldo + 31) / 32;   // K = out_dim columns of dout in 32-wide segments (the last one reads zeros past the row)
+      for (int q = 0; q < nsd; ++q) t.seg[q] = TcPosSeg{dout, (int)PT, p->ldo, 32 * q, 0};
+      t.nseg = nsd; t.nb = 1; t.rows_out = (int)PT; t.Wp = sc + p->o_hb_w2t; t.Wp_lo = h3 ? sc + p->o_hb_w2t_lo : nullptr;
       t.N = E <= TN ? E : TN; t.wstream = 1; t.N_total = E; t.w_k = p->ldo;
       t.out = de1; t.out_width = E; t.out_nblk = E / 32;
       RowDense ep;
@@ -985,14 +992,14 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
       return launch_slot_reduce4(tsc.partial, r, nout, f, st);
     return launch_slot_reduce(tsc.partial, r, nout, f, st);
   };
-  if (hb_tc && E % 32 == 0 && E / 32 <= TR_MAXSRC && Sk / 32 <= TR_MAXSRC && O <= 32) {
+  if (hb_tc && E % 32 == 0 && E / 32 <= TR_MAXSRC && Sk / 32 <= TR_MAXSRC && O <= 256) {
     int rs;
     {  // (b) dW2[o][e] = sum_p dout[p][o] e1[p][e], db2[o] = sum_p dout[p][o]
       TcRedSrc ab_[TR_MAXSRC];
       float* blk[TR_MAXSRC];
       for (int j = 0; j < E / 32; ++j) { ab_[j] = TcRedSrc{e1, (int)PT, E, 32 * j, 0, 0}; blk[j] = G(p->i_e2w) + 32 * j; }
       float* bias[1] = {G(p->i_e2b)};
-      rs = head_wgrad_tc(ab_, E / 32, TcRedSrc{dout, (int)PT, p->ldo, 0, 0, 0}, 32, O, 1, (int)PT, blk, E, bias, 1);
+      rs = head_wgrad_tc(ab_, E / 32, TcRedSrc{dout, (int)PT, p->ldo, 0, 0, 0}, round_up(O, 32), O, 1, (int)PT, blk, E, bias, 1);
       if (rs > 0) return rs;
     }
     if (rs == 0) {  // (d) dW1[e][sk] = sum_p de1[p][e] skip[p][sk], db1[e] = sum_p de1[p][e]
