@@ -355,7 +355,10 @@ static int node_gemm_tc2_impl(const NodeTcArgs& a, cudaStream_t stream) {
   p.nkb = (a.V + BLOCK_K - 1) / BLOCK_K;
   const int nout = a.kcat ? 1 : a.nsup;
   const int n_clusters = (tc_num_sms() & ~1) / 2;
-  p.n_tile = 256;
+  {   // V > 256: the fewest column tiles of <= 256 nodes, BALANCED (V = 325: 2 x 176 instead of 256 + a 69-node tile padded to 256)
+    const int nw = (a.V + 255) / 256;
+    p.n_tile = round_up((a.V + nw - 1) / nw, 16);
+  }
   if (a.V <= 256) {
     // Small graphs: 8-slab row tiles alone are coarse against 74 clusters (METR-LA, K-concatenated dX sum at L = 12:
     // 96 tiles = 1.3 rounds).  Splitting the output columns multiplies the tile count at the price of narrower (per
