@@ -49,7 +49,7 @@ class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region."""
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.begin = index, [], None, 0
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -66,6 +66,17 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_ready(self, timeout=4.0):
+        """nvidia-smi's start-up (NVML initialisation, hundreds of ms of driver calls) must not land in the timed region:
+        the caller starts the sampler before the warm-up steps and waits here for its first row."""
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        """Rows from here on belong to the timed region."""
+        self.begin = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -76,7 +87,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[self.begin:] or self.rows
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -421,11 +433,13 @@ def run_native(args):
     torch.cuda.synchronize(dev)
     launches_per_step = int(lib.dll.gwn_launch_count(1))
     tr.use_graph = graph_mode
-    for i in range(max(args.warmup, 3)):
-        step_resident(i)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    sampler.mark()
     ms = timed(step_resident, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     for i in range(2):
