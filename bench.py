@@ -437,6 +437,7 @@ def run_native(args):
     if rank == 0:
         sampler.start()
         sampler.wait_ready()
+    barrier()   # rank 0 may have waited up to seconds for nvidia-smi: the peers' exchange kernels must not spin on it
     for i in range(max(args.warmup, 3)):
         step_resident(i)
     sampler.mark()
