@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       mbar_init(empty_bar(s), 1);
     }
     for (int l = 0; l < 2; ++l) {
-      mbar_init(split_bar(l), (p.drain > 0) ? 64 : 192);
+      mbar_init(split_bar(l), 192);
       mbar_init(loempty_bar(l), 1);
     }
     mbar_init(done_bar, 1);
@@ -340,36 +340,42 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     }
   }
   // ===================================================== splitter: remainders of the TMA-written A blocks and of B.
-  // Warps 2-3, joined by the four epilogue warps when those would otherwise idle until the end (no drain): the
-  // support gradient splits 58 KB per chunk and was bound by two splitter warps (200 us -> 112 us with the split
-  // disabled, against 182 us with the MMAs disabled).
-  const int nsplit = (p.drain > 0) ? 64 : 192;
+  // Warps 2-3 and the four epilogue warps (192 threads).  Two splitter warps alone bound these kernels: the support
+  // gradient splits 58 KB per chunk (200 us -> 112 us with the split disabled, against 182 us with the MMAs disabled),
+  // and in the drain mode of the weight gradients -- where the epilogue warps used to sit on `tfull` between their
+  // periodic drains -- ncu had the two splitter warps 93 % busy, the producer blocked on `empty` 75 % and the tensor
+  // pipe 12 % active (r02w).  The epilogue warps therefore split every chunk too and fit their drains in between.
+  constexpr int nsplit = 192;
+  const int t64 = threadIdx.x - 64;
+  const int a_live = (p.mode == 0 ? na_loc * 4096 : p.a_bytes) / 16, b_live = p.b_bytes / 16;
+  auto split_chunk = [&](int stage, int lq, uint32_t phase, uint32_t lphase) -> bool {
+    if (!mbar_wait(loempty_bar(lq), lphase ^ 1u, 28)) return false;   // the MMAs that read this remainder buffer have retired
+    if (!mbar_wait(full_bar(stage), phase, 25)) return false;
+    uint8_t* sp = smem + (size_t)stage * stage_bytes;
+    uint8_t* lp = lo_ptr + (size_t)lq * plane_bytes;
+    const float4* a_src = reinterpret_cast<const float4*>(sp);
+    float4* a_dst = reinterpret_cast<float4*>(lp);
+#pragma unroll 4
+    for (int i = t64; i < a_live; i += nsplit) {
+      const float4 v = a_src[i];
+      a_dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+    }
+    const float4* b_src = reinterpret_cast<const float4*>(sp + p.a_bytes);
+    float4* b_dst = reinterpret_cast<float4*>(lp + p.a_bytes);
+#pragma unroll 4
+    for (int i = t64; i < b_live; i += nsplit) {
+      const float4 v = b_src[i];
+      b_dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive(split_bar(lq));
+    return true;
+  };
   if (X3 && (warp == 2 || warp == 3 || (warp >= 4 && p.drain == 0))) {
-    const int t64 = threadIdx.x - 64;
     int stage = 0, lq = 0;
     uint32_t phase = 0, lphase = 0;
-    const int a_live = (p.mode == 0 ? na_loc * 4096 : p.a_bytes) / 16, b_live = p.b_bytes / 16;
     for (int c = c_beg; c < c_end; c += c_step) {
-      if (!mbar_wait(loempty_bar(lq), lphase ^ 1u, 28)) break;   // the MMAs that read this remainder buffer have retired
-      if (!mbar_wait(full_bar(stage), phase, 25)) break;
-      uint8_t* sp = smem + (size_t)stage * stage_bytes;
-      uint8_t* lp = lo_ptr + (size_t)lq * plane_bytes;
-      const float4* a_src = reinterpret_cast<const float4*>(sp);
-      float4* a_dst = reinterpret_cast<float4*>(lp);
-#pragma unroll 8
-      for (int i = t64; i < a_live; i += nsplit) {
-        const float4 v = a_src[i];
-        a_dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
-      }
-      const float4* b_src = reinterpret_cast<const float4*>(sp + p.a_bytes);
-      float4* b_dst = reinterpret_cast<float4*>(lp + p.a_bytes);
-#pragma unroll 8
-      for (int i = t64; i < b_live; i += nsplit) {
-        const float4 v = b_src[i];
-        b_dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(split_bar(lq));
+      if (!split_chunk(stage, lq, phase, lphase)) break;
       if (++lq == LQ) { lq = 0; lphase ^= 1u; }
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
@@ -389,9 +395,9 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       for (int i = 0; i < 64; ++i) sum[i] = 0.0f;
       const int ndrain = (n_my + p.drain - 1) / p.drain;
       bool ok = true;
-      for (int d = 0; d < ndrain && ok; ++d) {
+      auto drain_one = [&](int d) -> bool {     // add accumulator buffer d & 1 (hand-over number d) to the registers
         const int buf = d & 1;
-        if (!mbar_wait(tfull_bar(buf), (uint32_t)(d >> 1) & 1u, 27)) { ok = false; break; }
+        if (!mbar_wait(tfull_bar(buf), (uint32_t)(d >> 1) & 1u, 27)) return false;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(buf * p.mtiles * p.N);
 #pragma unroll
@@ -406,6 +412,23 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
         }
         tc_fence_before();
         mbar_arrive(tempty_bar(buf));
+        return true;
+      };
+      if (X3) {
+        // split every chunk with warps 2-3; hand-over d (after chunk (d + 1) * drain - 1, or the last chunk) is drained
+        // one chunk later, AFTER this warp's share of that chunk's split: the issuer needs the split of chunk i before it
+        // can issue anything, while the MMAs of hand-over d were issued a chunk ago and complete on their own.
+        int stage = 0, lq = 0, i = 0;
+        uint32_t phase = 0, lphase = 0;
+        for (int c = c_beg; c < c_end && ok; c += c_step, ++i) {
+          if (!split_chunk(stage, lq, phase, lphase)) { ok = false; break; }
+          if (++lq == LQ) { lq = 0; lphase ^= 1u; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          if (i > 0 && i % p.drain == 0) ok = drain_one(i / p.drain - 1);
+        }
+        if (ok && ndrain > 0) ok = drain_one(ndrain - 1);
+      } else {
+        for (int d = 0; d < ndrain && ok; ++d) ok = drain_one(d);
       }
       if (ok) {
 #pragma unroll
