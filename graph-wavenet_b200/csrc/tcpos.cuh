@@ -97,13 +97,20 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
   // Streamed weights (head layers, N <= 128 per tile) keep W_lo's k-block behind W's inside every stage: same trick.
   const bool NCAT = X3 && !EP::kDirectStore && (NCT > 0 ? NCT <= 64 : (p.wstream != 0 && p.N <= 128));
   const int w_blk = p.N * 128;                            // one k-block of weights: [N rows][128 B]
-  const int STG = NPL * A_BYTES + (p.wstream ? NPL * w_blk : 0);      // bytes per stage: [A | A_lo | (W blk | W_lo blk)]
+  // Raw stages [A | (W blk | W_lo blk)] are what TMA writes -- the bytes in flight; the remainders A_lo live in their OWN
+  // ring of LQ buffers (as in tcred.cuh): with A_lo inside every stage a CTA had three stages beside the mlp's resident
+  // weights and staging tiles, 48 KB in flight per SM, and these kernels are bound by exactly that.  A remainder buffer
+  // is busy from the split until its MMA retires (commit -> loempty); a raw stage from the TMA until the same commit --
+  // NOT earlier: the splitter reads the raw tile, so the stage may only be handed back once split[l] has been seen.
+  constexpr int LQ = X3 ? 2 : 0;
+  const int STG = A_BYTES + (p.wstream ? NPL * w_blk : 0);
   const int w_plane = p.nseg * w_blk;                     // resident weights: [plane][seg][N rows][128 B]
   const int w_bytes = p.wstream ? 0 : NPL * w_plane;
-  const uint32_t a0 = base + w_bytes;                     // A stages: [A | A_lo]
+  const uint32_t a0 = base + w_bytes;                     // raw stages
+  const uint32_t lo0 = a0 + p.stages * STG;               // remainder ring
   constexpr int NSO = (EP::kGroups == 1) ? 2 : 2 * ((NCT > 0 && NCT / EP::kAccPerBlock == 1) ? 1 : 2);   // output staging tiles
-  const uint32_t so0 = a0 + p.stages * STG;               // [128 rows][128 B] each, SWIZZLE_128B
-  uint8_t* so_ptr = smem + w_bytes + (size_t)p.stages * STG;
+  const uint32_t so0 = lo0 + LQ * A_BYTES;                // [128 rows][128 B] each, SWIZZLE_128B
+  uint8_t* so_ptr = smem + w_bytes + (size_t)p.stages * STG + (size_t)LQ * A_BYTES;
   constexpr int NADD = EP::kAddends;                      // addend tiles: 2 buffers (tile parity) x NADD
   const uint32_t ad0 = so0 + NSO * TP_A_BYTES;
   const uint8_t* ad_ptr = so_ptr + NSO * TP_A_BYTES;
@@ -111,14 +118,16 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
   uint64_t* bars = reinterpret_cast<uint64_t*>(so_ptr + (NSO + 2 * NADD) * TP_A_BYTES);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
-  auto split_bar = [&](int s) { return bar0 + 8u * (2 * p.stages + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * p.stages + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * p.stages + 2 + a); };
-  const uint32_t w_bar = bar0 + 8u * (3 * p.stages + 4);
-  auto efull_bar = [&](int e) { return bar0 + 8u * (3 * p.stages + 5 + e); };
-  auto eempty_bar = [&](int e) { return bar0 + 8u * (3 * p.stages + 7 + e); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 9);
-  float* red = reinterpret_cast<float*>(bars + 3 * p.stages + 10);   // 2 x 64 floats for the statistics reduces
+  const int nb2 = 2 * p.stages;
+  auto split_bar = [&](int l) { return bar0 + 8u * (nb2 + l); };          // remainder buffer l filled (l < 2)
+  auto loempty_bar = [&](int l) { return bar0 + 8u * (nb2 + 2 + l); };    // ... and consumed
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (nb2 + 4 + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (nb2 + 6 + a); };
+  const uint32_t w_bar = bar0 + 8u * (nb2 + 8);
+  auto efull_bar = [&](int e) { return bar0 + 8u * (nb2 + 9 + e); };
+  auto eempty_bar = [&](int e) { return bar0 + 8u * (nb2 + 11 + e); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + nb2 + 13);
+  float* red = reinterpret_cast<float*>(bars + nb2 + 14);   // 2 x 64 floats for the statistics reduces
 
   const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -132,7 +141,10 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(split_bar(s), 64);
+    }
+    for (int l = 0; l < 2; ++l) {
+      mbar_init(split_bar(l), 64);
+      mbar_init(loempty_bar(l), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -198,7 +210,7 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
           mbar_expect_tx(full_bar(stage), A_BYTES + (p.wstream ? NPL * w_blk : 0));
           tma_load_3d(a0 + stage * STG, &maps.a[s], full_bar(stage), p.col0[s] + h * BK, rt * 128 + p.rshift[s], b);
           if (p.wstream) {
-            const uint32_t wdst = a0 + stage * STG + NPL * A_BYTES;
+            const uint32_t wdst = a0 + stage * STG + A_BYTES;
             tma_load_2d(wdst, &maps.w, full_bar(stage), s * 32, nt * p.N);
             if (X3) tma_load_2d(wdst + w_blk, &maps.wlo, full_bar(stage), s * 32, nt * p.N);
           }
@@ -211,8 +223,8 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
     // ===================================================== MMA issuer: D[128 x N] += A[128 x 32] . Wseg[N x 32]^T
     // (whole warp loops, one elected lane issues)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int stage = 0, acc = 0;
-    uint32_t phase = 0, accphase = 0;
+    int stage = 0, acc = 0, lq = 0;
+    uint32_t phase = 0, accphase = 0, lphase = 0;
     bool ok = p.wstream ? true : mbar_wait_warp(w_bar, 0, 12);
     tc_fence_after();
     for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
@@ -225,7 +237,7 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
         tc_fence_after();
         const uint32_t as = a0 + stage * STG;
         // this stage's k-block of the weights: the segment's [N rows][128 B] tile, h * BK floats into every row
-        const uint32_t ws = (p.wstream ? as + NPL * A_BYTES : (NCAT ? base + s * 2 * w_blk : base + s * w_blk)) + h * (BK * 4);
+        const uint32_t ws = (p.wstream ? as + A_BYTES : (NCAT ? base + s * 2 * w_blk : base + s * w_blk)) + h * (BK * 4);
         const uint32_t wlo_off = p.wstream ? (uint32_t)w_blk : (uint32_t)w_plane;
         if (elect_one()) {
 #pragma unroll
@@ -244,17 +256,24 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
         }
         __syncwarp();
         if (X3) {   // the A_lo term last: the split of this stage overlaps the MMAs above
-          if (!mbar_wait_warp(split_bar(stage), phase, 16)) { ok = false; break; }
+          if (!mbar_wait_warp(split_bar(lq), lphase, 16)) { ok = false; break; }
           tc_fence_after();
+          const uint32_t al = lo0 + (uint32_t)(lq * A_BYTES);
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < BK / 8; ++kk)
-              tc_mma_tf32(d_tmem, make_desc(as + A_BYTES + kk * 32, 16, A_SBO, A_LAYOUT), make_desc(ws + kk * 32, 16, 1024), idesc, 1u);
+              tc_mma_tf32(d_tmem, make_desc(al + kk * 32, 16, A_SBO, A_LAYOUT), make_desc(ws + kk * 32, 16, 1024), idesc, 1u);
           }
           __syncwarp();
         }
-        if (elect_one()) tc_commit(empty_bar(stage));
+        if (elect_one()) {
+          tc_commit(empty_bar(stage));             // after split[lq]: the splitter has read the raw tile
+          if (X3) tc_commit(loempty_bar(lq));
+        }
         __syncwarp();
+        if (X3) {
+          if (++lq == LQ) { lq = 0; lphase ^= 1u; }
+        }
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
       if (!ok) break;
@@ -266,14 +285,15 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
   } else if (X3 && (warp == 2 || warp == 3)) {
     // ===================================================== splitter: A_lo = A - tf32_trunc(A), 64 threads, 16 float4 each
     const int t64 = threadIdx.x - 64;
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = 0, lq = 0;
+    uint32_t phase = 0, lphase = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
       for (int sh = 0; sh < p.nseg * KH; ++sh) {
+        if (!mbar_wait(loempty_bar(lq), lphase ^ 1u, 20)) { ok = false; break; }   // the MMA that read this buffer has retired
         if (!mbar_wait(full_bar(stage), phase, 17)) { ok = false; break; }
         const float4* src = reinterpret_cast<const float4*>(smem + w_bytes + (size_t)stage * STG);
-        float4* dst = reinterpret_cast<float4*>(smem + w_bytes + (size_t)stage * STG + A_BYTES);
+        float4* dst = reinterpret_cast<float4*>(smem + w_bytes + (size_t)p.stages * STG + (size_t)lq * A_BYTES);
         {   // 16 (8) float4 per thread: all loads in flight before the first use (with 4 at a time the two splitter
             // warps were busy ~100 % of the time, stalled on LDS results: ncu source page of the reduction kernel)
           constexpr int NV = A_BYTES / 16 / 64;
@@ -286,7 +306,8 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
             dst[t64 + 64 * u] = make_float4(tf32_lo(v[u].x), tf32_lo(v[u].y), tf32_lo(v[u].z), tf32_lo(v[u].w));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-        mbar_arrive(split_bar(stage));
+        mbar_arrive(split_bar(lq));
+        if (++lq == LQ) { lq = 0; lphase ^= 1u; }
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -326,7 +347,14 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
         ar.row[1] = ad_ptr + (size_t)(buf * NADD + (NADD > 1 ? 1 : 0)) * TP_A_BYTES + r * 128;
         ar.x = (uint32_t)(r & 7);
         ep.load_addends(ar, valid);
-        if constexpr (!EP::kLazyAddends) mbar_arrive(eempty_bar(buf));
+        if constexpr (!EP::kLazyAddends) {
+          // Registers hold the rows from here on, so the buffer can go back to the producer -- but its next use is a TMA
+          // write (async proxy) and these were generic-proxy reads: without the proxy fence the arrive was observed
+          // while LDS data were still outstanding, and once the producer could run two tiles ahead (4 raw stages in
+          // RowGateBwd) the next tile's rows landed in the buffer first: dpre rows off by ~1e-2.
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(eempty_bar(buf));
+        }
       }
       if (!mbar_wait(tfull_bar(buf), bphase, 15)) break;
       tc_fence_after();
@@ -401,7 +429,10 @@ __global__ void __launch_bounds__(128 + 128 * EP::kGroups, 1) tcpos_kernel(const
         for (int blk = 0; blk * APB < ncols; ++blk) do_block(blk);
       }
       if constexpr (EP::kLazyAddends) {   // consume16 read the staged addend tiles: hand them back only now
-        if (has_add) mbar_arrive(eempty_bar(buf));
+        if (has_add) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(eempty_bar(buf));
+        }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
@@ -449,10 +480,11 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
   p.total_tiles = (int)tiles;
   const int w_bytes = a.wstream ? 0 : (X3 ? 2 : 1) * a.nseg * a.N * 128;
   if (BK != 32 && a.wstream) return -1;                   // half-size stages: resident weights only
-  const int STG = (X3 ? 2 : 1) * (128 * BK * 4 + (a.wstream ? a.N * 128 : 0));
+  const int LO_BYTES = X3 ? 2 * 128 * BK * 4 : 0;      // the remainder ring (2 buffers)
+  const int STG = 128 * BK * 4 + (a.wstream ? (X3 ? 2 : 1) * a.N * 128 : 0);
   constexpr int NSO = (EP::kGroups == 1) ? 2 : 2 * ((NCT > 0 && NCT / EP::kAccPerBlock == 1) ? 1 : 2);
   constexpr int FIXED = (NSO + 2 * EP::kAddends) * TP_A_BYTES;   // output staging tiles + addend tiles
-  p.stages = (SMEM_LIMIT - 2048 - w_bytes - FIXED) / STG;
+  p.stages = (SMEM_LIMIT - 2048 - w_bytes - FIXED - LO_BYTES) / STG;
   for (int k = 0; k < 2; ++k) {
     const TcPosSeg& g = a.addend[k];
     if (!g.src || k >= EP::kAddends) continue;
@@ -513,7 +545,7 @@ int launch_tcpos_impl(const TcPosArgs& a, const EP& ep, cudaStream_t stream) {
   }
   for (int k = 0; k < 2; ++k)
     if (!p.add_on[k]) maps.add[k] = maps.out;
-  const int smem_bytes = w_bytes + p.stages * STG + FIXED + 1024 + 1024;
+  const int smem_bytes = w_bytes + p.stages * STG + LO_BYTES + FIXED + 1024 + 1024;
   static cudaError_t attr = cudaFuncSetAttribute(tcpos_kernel<EP, NCT, X3, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   if (attr != cudaSuccess) {
     set_error("tcpos: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr));
