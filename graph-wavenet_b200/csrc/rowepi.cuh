@@ -97,8 +97,22 @@ struct RowStats32 {
 // tanh / sigmoid of the gate on the tf32 tier: ex2.approx-based (2 MUFU + 3 FMA-class instructions each, ~1e-7
 // absolute error) instead of the ~35-instruction tanhf / expf sequences -- with one epilogue warp per scheduler the
 // accurate versions made the gate epilogue, not HBM, the limiter of the gated-conv kernels (ncu r01b).
-__device__ __forceinline__ float gate_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float gate_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+// ex2 / rcp are issued as the bare .ftz MUFU forms: __expf and __fdividef wrap the same two instructions in range
+// fix-ups (FSETP + predicated FMULs for denormal inputs / huge denominators) that cannot trigger here -- the gate
+// saturates: ex2 -> +inf gives rcp(inf) = 0, ex2 -> 0 gives rcp(1) = 1 -- and the gate epilogue is instruction-bound
+// (ncu r02x: its 8 warps 85 % busy, the issuer waiting for a free accumulator 55 % of the time).
+__device__ __forceinline__ float mufu_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gate_sigmoid(float x) { return mufu_rcp(1.0f + mufu_ex2(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float gate_tanh(float x) { return fmaf(-2.0f, mufu_rcp(mufu_ex2(2.8853900817779268f * x) + 1.0f), 1.0f); }
 
 // model.py:208-212 -- accumulator columns interleaved (f0,g0,f1,g1,...), N = 64 -> 32 gated outputs.
 struct RowGate {
