@@ -111,8 +111,12 @@ __device__ __forceinline__ float mufu_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float gate_sigmoid(float x) { return mufu_rcp(1.0f + mufu_ex2(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float gate_tanh(float x) { return fmaf(-2.0f, mufu_rcp(mufu_ex2(2.8853900817779268f * x) + 1.0f), 1.0f); }
+constexpr float kSigmScale = -1.4426950408889634f, kTanhScale = 2.8853900817779268f;   // -log2(e), 2 log2(e)
+__device__ __forceinline__ float gate_sigmoid(float x) { return mufu_rcp(1.0f + mufu_ex2(kSigmScale * x)); }
+__device__ __forceinline__ float gate_tanh(float x) { return fmaf(-2.0f, mufu_rcp(mufu_ex2(kTanhScale * x) + 1.0f), 1.0f); }
+// the same with the bias folded into the exponent: sb = kSigmScale * bias, tb = kTanhScale * bias
+__device__ __forceinline__ float gate_sigmoid_b(float v, float sb) { return mufu_rcp(1.0f + mufu_ex2(fmaf(v, kSigmScale, sb))); }
+__device__ __forceinline__ float gate_tanh_b(float v, float tb) { return fmaf(-2.0f, mufu_rcp(mufu_ex2(fmaf(v, kTanhScale, tb)) + 1.0f), 1.0f); }
 
 // model.py:208-212 -- accumulator columns interleaved (f0,g0,f1,g1,...), N = 64 -> 32 gated outputs.
 struct RowGate {
@@ -125,13 +129,17 @@ struct RowGate {
   float* y;          // [P, 32] (written through the kernel's output tensor map)
   const float* bf;
   const float* bg;
-  __device__ __forceinline__ void init() {}
+  float tb[32], sb[32];   // biases in registers, pre-scaled for the exponentials (64 LDGs per tile and thread otherwise)
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { tb[j] = kTanhScale * __ldg(bf + j); sb[j] = kSigmScale * __ldg(bg + j); }
+  }
   __device__ __forceinline__ void load_addends(const AddendRows&, bool) {}
   __device__ __forceinline__ void consume16(i64, int c0, int, const float (&v)[16], const RowSink& out) {
-    const int ch0 = c0 >> 1;
+    const int ch0 = c0 >> 1;   // compile-time after unrolling (NCT > 0): tb / sb stay in registers
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = gate_tanh(v[2 * j] + __ldg(bf + ch0 + j)) * gate_sigmoid(v[2 * j + 1] + __ldg(bg + ch0 + j));
+    for (int j = 0; j < 8; ++j) o[j] = gate_tanh_b(v[2 * j], tb[ch0 + j]) * gate_sigmoid_b(v[2 * j + 1], sb[ch0 + j]);
     out.put4(ch0, o[0], o[1], o[2], o[3]);
     out.put4(ch0 + 4, o[4], o[5], o[6], o[7]);
   }
@@ -151,7 +159,11 @@ struct RowGateBwd {
   const float* bf;
   const float* bg;
   float g[32];
-  __device__ __forceinline__ void init() {}
+  float tb[32], sb[32];   // pre-scaled biases in registers (see RowGate)
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { tb[j] = kTanhScale * __ldg(bf + j); sb[j] = kSigmScale * __ldg(bg + j); }
+  }
   __device__ __forceinline__ void load_addends(const AddendRows& a, bool valid) {
     if (valid) a.load<32>(0, 0, g);
   }
@@ -160,7 +172,7 @@ struct RowGateBwd {
     float o[16];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float f = gate_tanh(v[2 * j] + __ldg(bf + ch0 + j)), s = gate_sigmoid(v[2 * j + 1] + __ldg(bg + ch0 + j));
+      const float f = gate_tanh_b(v[2 * j], tb[ch0 + j]), s = gate_sigmoid_b(v[2 * j + 1], sb[ch0 + j]);
       const float gg = g[ch0 + j];
       o[2 * j] = gg * s * (1.0f - f * f);
       o[2 * j + 1] = gg * f * s * (1.0f - s);
