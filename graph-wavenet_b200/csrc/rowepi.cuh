@@ -199,27 +199,50 @@ struct RowMlp {
   double* stats;       // nullable
   float rrow[32];
   RowStats32 cs;
-  __device__ __forceinline__ void init() { cs.reset(); }
+  __device__ __forceinline__ void init() {
+    cs.reset();
+    vec = ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(rac)) & 15) == 0;
+  }
   __device__ __forceinline__ void load_addends(const AddendRows& a, bool valid) {
     if (res && valid) a.load<32>(0, 0, rrow);
   }
+  // 16 per-channel constants as four 128-bit loads (the address is warp-uniform); the flat parameter buffer and the
+  // workspace keep every tensor 16-byte aligned, checked once in init()
+  bool vec;
+  __device__ __forceinline__ void load16(const float* p, float (&r)[16]) const {
+    if (vec) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(p) + q);
+        r[4 * q] = f.x; r[4 * q + 1] = f.y; r[4 * q + 2] = f.z; r[4 * q + 3] = f.w;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) r[c] = __ldg(p + c);
+    }
+  }
   __device__ __forceinline__ void consume16(i64 m, int c0, int, const float (&v)[16], const RowSink& out) {
-    float o[16];
+    float o[16], bs[16];
     const i64 e = m * 32 + c0;
+    load16(bias + c0, bs);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       float kp[8];
       drop.keep8(e + 8 * q, kp);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = 8 * q + i;
-        float r = (v[c] + __ldg(bias + c0 + c)) * kp[i];
-        if (res) {
-          float x = rrow[c0 + c];
-          if (rac) x = fmaf(x, __ldg(rac + c0 + c), __ldg(rac + 32 + c0 + c));
-          r += x;
-        }
-        o[c] = r;
+      for (int i = 0; i < 8; ++i) o[8 * q + i] = (v[8 * q + i] + bs[8 * q + i]) * kp[i];
+    }
+    // the null checks sit OUTSIDE the unrolled loops (inside, the compiler kept one branch per element: 64 per row)
+    if (res) {
+      if (rac) {
+        float a[16], b[16];
+        load16(rac + c0, a);
+        load16(rac + 32 + c0, b);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) o[c] += fmaf(rrow[c0 + c], a[c], b[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) o[c] += rrow[c0 + c];
       }
     }
     out.put16(c0, o);
@@ -285,10 +308,16 @@ struct RowTcnDgrad {
       float ur[16];
       ar.load<16>(1, c0, ur);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float xh = (ur[c] - __ldg(mr + c0 + c)) * __ldg(mr + 32 + c0 + c);
-        cs.s1[c0 + c] += o[c];
-        cs.s2[c0 + c] += o[c] * xh;
+      for (int q = 0; q < 4; ++q) {   // mean / rstd of 4 channels per 128-bit load (workspace rows are 16-byte aligned)
+        const float4 mu = __ldg(reinterpret_cast<const float4*>(mr + c0) + q), rs = __ldg(reinterpret_cast<const float4*>(mr + 32 + c0) + q);
+        const float mu_[4] = {mu.x, mu.y, mu.z, mu.w}, rs_[4] = {rs.x, rs.y, rs.z, rs.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 4 * q + j;
+          const float xh = (ur[c] - mu_[j]) * rs_[j];
+          cs.s1[c0 + c] += o[c];
+          cs.s2[c0 + c] += o[c] * xh;
+        }
       }
     }
   }
