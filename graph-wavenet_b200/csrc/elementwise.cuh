@@ -422,13 +422,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply8_kernel(float* __restrict__ 
   const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = (int)((t0 * 8) & (i64)(C - 1));
   float a[8], mean[8], rstd[8], m1[8], m2[8];
+  const double inv_count = 1.0 / count;   // ONE fp64 division per thread: 16 of them (x 256 threads x ~1200 blocks) were
+                                          // a ~5 us prologue per launch on a GPU with 64 fp64 lanes per SM
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     a[j] = ac[c0 + j];
     mean[j] = mr[c0 + j];
     rstd[j] = mr[C + c0 + j];
-    m1[j] = training ? (float)(sb[c0 + j] / count) : 0.0f;
-    m2[j] = training ? (float)(sb[C + c0 + j] / count) : 0.0f;
+    m1[j] = training ? (float)(sb[c0 + j] * inv_count) : 0.0f;
+    m2[j] = training ? (float)(sb[C + c0 + j] * inv_count) : 0.0f;
   }
   if (t0 * 8 < C) {
 #pragma unroll

@@ -202,6 +202,10 @@ struct RowMlp {
   __device__ __forceinline__ void init() {
     cs.reset();
     vec = ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(rac)) & 15) == 0;
+    if (drop.seed_dev) {   // the step's Philox key: read once per kernel instead of once per 8 elements
+      drop.seed = (uint64_t)*drop.seed_dev;
+      drop.seed_dev = nullptr;
+    }
   }
   __device__ __forceinline__ void load_addends(const AddendRows& a, bool valid) {
     if (res && valid) a.load<32>(0, 0, rrow);
