@@ -302,6 +302,89 @@ __global__ void __launch_bounds__(256) start_wgrad32_kernel(const float* __restr
     else if (f < F) atomicAdd(dW + c * F + f, sum);
   }
 }
+// Block-per-(b, t) versions: the warp-per-position kernels above decode (b, t, n) with four integer divisions per
+// position and keep 32 lanes busy with one 128-byte row -- ~100 warp instructions per position, 28 / 25 us for tensors a
+// streaming kernel moves in 5.  Here a block owns one (sample, time step) row of N positions, decoded ONCE; a thread owns
+// 4 channels (one 128-bit access) of every 32nd node, its weights in registers.  Same FMA order as above.
+__global__ void __launch_bounds__(256) start_fwd32b_kernel(const float* __restrict__ in, Strides4 is, const float* __restrict__ W,
+                                                           const float* __restrict__ bias, float* __restrict__ x0, int F, int N,
+                                                           int L0, int pad) {
+  GWN_PDL_ENTRY();
+  const int bt = blockIdx.x, b = bt / L0, t = bt - b * L0;
+  const int c4 = (threadIdx.x & 7) * 4;
+  float w[4][START_MAXF], bs[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    bs[j] = bias[c4 + j];
+#pragma unroll
+    for (int f = 0; f < START_MAXF; ++f) w[j][f] = f < F ? W[(c4 + j) * F + f] : 0.0f;
+  }
+  const bool live = t >= pad;
+  const float* src = in + (i64)b * is.s[0] + (i64)(live ? t - pad : 0) * is.s[3];
+  float* dst = x0 + (size_t)bt * N * 32 + c4;
+  for (int n = threadIdx.x >> 3; n < N; n += 32) {
+    float xin[START_MAXF];
+#pragma unroll
+    for (int f = 0; f < START_MAXF; ++f) xin[f] = (live && f < F) ? __ldg(src + (i64)n * is.s[2] + (i64)f * is.s[1]) : 0.0f;
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float acc = bs[j];
+#pragma unroll
+      for (int f = 0; f < START_MAXF; ++f) acc = fmaf(w[j][f], xin[f], acc);
+      o[j] = acc;
+    }
+    st4(dst + (size_t)n * 32, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+__global__ void __launch_bounds__(256) start_wgrad32b_kernel(const float* __restrict__ dx0, const float* __restrict__ in, Strides4 is,
+                                                             float* dW, float* db, int F, int N, int L0, int pad) {
+  __shared__ float red[8][8][4 * (START_MAXF + 1)];   // [warp][channel quad][4 channels x (F features + bias)]
+  GWN_PDL_ENTRY();
+  const int bt = blockIdx.x, b = bt / L0, t = bt - b * L0;
+  const int q = threadIdx.x & 7, c4 = q * 4, warp = threadIdx.x >> 5;
+  float acc[4][START_MAXF + 1];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int f = 0; f <= START_MAXF; ++f) acc[j][f] = 0.0f;
+  const bool live = t >= pad;
+  const float* src = in + (i64)b * is.s[0] + (i64)(live ? t - pad : 0) * is.s[3];
+  const float* g = dx0 + (size_t)bt * N * 32 + c4;
+  for (int n = threadIdx.x >> 3; n < N; n += 32) {
+    const float4 v4 = ld4(g + (size_t)n * 32);
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    float xin[START_MAXF];
+#pragma unroll
+    for (int f = 0; f < START_MAXF; ++f) xin[f] = (live && f < F) ? __ldg(src + (i64)n * is.s[2] + (i64)f * is.s[1]) : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[j][START_MAXF] += v[j];
+#pragma unroll
+      for (int f = 0; f < START_MAXF; ++f) acc[j][f] = fmaf(v[j], xin[f], acc[j][f]);
+    }
+  }
+  // the 4 node groups of a warp (lanes q, q + 8, q + 16, q + 24), then the 8 warps through shared memory
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int f = 0; f <= START_MAXF; ++f) {
+      float x = acc[j][f];
+      x += __shfl_xor_sync(0xffffffffu, x, 8);
+      x += __shfl_xor_sync(0xffffffffu, x, 16);
+      if ((threadIdx.x & 31) < 8) red[warp][q][j * (START_MAXF + 1) + f] = x;
+    }
+  __syncthreads();
+  constexpr int NV = 32 * (START_MAXF + 1);
+  for (int k = threadIdx.x; k < NV; k += blockDim.x) {
+    const int c = k / (START_MAXF + 1), f = k - c * (START_MAXF + 1);
+    float sum = 0.0f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) sum += red[y][c >> 2][(c & 3) * (START_MAXF + 1) + f];
+    if (f == START_MAXF) atomicAdd(db + c, sum);
+    else if (f < F) atomicAdd(dW + c * F + f, sum);
+  }
+}
 // dE2[k,w] += sum_{v in this block's slice} E1[v,k] dR[v,w]: thread = column w (coalesced dR rows, broadcast E1),
 // blockIdx.y = slice of v; the element-per-output kernel above ran 207-long dependent chains on 9 blocks (38 us).
 __global__ void __launch_bounds__(256) adp_bwd_cols_split_kernel(const float* __restrict__ dR, const float* __restrict__ E1, int R,

@@ -622,9 +622,8 @@ static int plan_forward(gwn_plan* p, const gwn_forward_args* a) {
     for (int k = 0; k < 4; ++k) is.s[k] = a->input_strides[k];
 #if !GWN_EMU
     if (C == 32 && c.in_dim <= START_MAXF && p->P0() < 2147483647LL) {
-      const i64 blocks = std::min<i64>((p->P0() + 7) / 8, 148 * 16);
-      GWN_CUDA(launch_kernel(start_fwd32_kernel, dim3((unsigned)blocks), dim3(256), 0, st, a->input, is, P_<float>(prm, p->i_startw),
-                             P_<float>(prm, p->i_startb), ws + p->o_x0, B, c.in_dim, N, p->L0, p->pad));
+      GWN_CUDA(launch_kernel(start_fwd32b_kernel, dim3((unsigned)(B * p->L0)), dim3(256), 0, st, a->input, is,
+                             P_<float>(prm, p->i_startw), P_<float>(prm, p->i_startb), ws + p->o_x0, c.in_dim, N, p->L0, p->pad));
       count_launch();
     } else
 #endif
@@ -1457,8 +1456,8 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     if (C == 32 && c.in_dim <= START_MAXF && p->P0() < 2147483647LL) {   // warp-per-position reduction (elementwise.cuh)
       Strides4 is;
       for (int k = 0; k < 4; ++k) is.s[k] = a->input_strides[k];
-      GWN_CUDA(launch_kernel(start_wgrad32_kernel, dim3(148 * 8), dim3(256), 0, st, (const float*)cur, a->input, is,
-                             G(p->i_startw), G(p->i_startb), B, c.in_dim, N, p->L0, p->pad));
+      GWN_CUDA(launch_kernel(start_wgrad32b_kernel, dim3((unsigned)(B * p->L0)), dim3(256), 0, st, (const float*)cur, a->input, is,
+                             G(p->i_startw), G(p->i_startb), c.in_dim, N, p->L0, p->pad));
       count_launch();
       sw_done = true;
     }
