@@ -338,30 +338,33 @@ __global__ void __launch_bounds__(256) start_fwd32b_kernel(const float* __restri
   }
 }
 __global__ void __launch_bounds__(256) start_wgrad32b_kernel(const float* __restrict__ dx0, const float* __restrict__ in, Strides4 is,
-                                                             float* dW, float* db, int F, int N, int L0, int pad) {
+                                                             float* dW, float* db, int F, int N, int L0, int pad, int nbt) {
   __shared__ float red[8][8][4 * (START_MAXF + 1)];   // [warp][channel quad][4 channels x (F features + bias)]
   GWN_PDL_ENTRY();
-  const int bt = blockIdx.x, b = bt / L0, t = bt - b * L0;
   const int q = threadIdx.x & 7, c4 = q * 4, warp = threadIdx.x >> 5;
   float acc[4][START_MAXF + 1];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int f = 0; f <= START_MAXF; ++f) acc[j][f] = 0.0f;
-  const bool live = t >= pad;
-  const float* src = in + (i64)b * is.s[0] + (i64)(live ? t - pad : 0) * is.s[3];
-  const float* g = dx0 + (size_t)bt * N * 32 + c4;
-  for (int n = threadIdx.x >> 3; n < N; n += 32) {
-    const float4 v4 = ld4(g + (size_t)n * 32);
-    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-    float xin[START_MAXF];
+  for (int bt = blockIdx.x; bt < nbt; bt += gridDim.x) {   // a few rows per block: 160 atomics per BLOCK at the end
+    const int b = bt / L0, t = bt - b * L0;
+    const bool live = t >= pad;
+    const float* src = in + (i64)b * is.s[0] + (i64)(live ? t - pad : 0) * is.s[3];
+    const float* g = dx0 + (size_t)bt * N * 32 + c4;
+#pragma unroll 4
+    for (int n = threadIdx.x >> 3; n < N; n += 32) {
+      const float4 v4 = ld4(g + (size_t)n * 32);
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+      float xin[START_MAXF];
 #pragma unroll
-    for (int f = 0; f < START_MAXF; ++f) xin[f] = (live && f < F) ? __ldg(src + (i64)n * is.s[2] + (i64)f * is.s[1]) : 0.0f;
+      for (int f = 0; f < START_MAXF; ++f) xin[f] = (live && f < F) ? __ldg(src + (i64)n * is.s[2] + (i64)f * is.s[1]) : 0.0f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      acc[j][START_MAXF] += v[j];
+      for (int j = 0; j < 4; ++j) {
+        acc[j][START_MAXF] += v[j];
 #pragma unroll
-      for (int f = 0; f < START_MAXF; ++f) acc[j][f] = fmaf(v[j], xin[f], acc[j][f]);
+        for (int f = 0; f < START_MAXF; ++f) acc[j][f] = fmaf(v[j], xin[f], acc[j][f]);
+      }
     }
   }
   // the 4 node groups of a warp (lanes q, q + 8, q + 16, q + 24), then the 8 warps through shared memory

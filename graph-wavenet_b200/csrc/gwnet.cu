@@ -1456,8 +1456,9 @@ static int plan_backward(gwn_plan* p, const gwn_backward_args* a, bool dout_read
     if (C == 32 && c.in_dim <= START_MAXF && p->P0() < 2147483647LL) {   // warp-per-position reduction (elementwise.cuh)
       Strides4 is;
       for (int k = 0; k < 4; ++k) is.s[k] = a->input_strides[k];
-      GWN_CUDA(launch_kernel(start_wgrad32b_kernel, dim3((unsigned)(B * p->L0)), dim3(256), 0, st, (const float*)cur, a->input, is,
-                             G(p->i_startw), G(p->i_startb), c.in_dim, N, p->L0, p->pad));
+      const int nbt = B * p->L0;
+      GWN_CUDA(launch_kernel(start_wgrad32b_kernel, dim3((unsigned)std::min(nbt, 148 * 8)), dim3(256), 0, st, (const float*)cur,
+                             a->input, is, G(p->i_startw), G(p->i_startb), c.in_dim, N, p->L0, p->pad, nbt));
       count_launch();
       sw_done = true;
     }
