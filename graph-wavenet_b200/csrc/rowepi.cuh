@@ -340,15 +340,31 @@ struct RowDense {
   const float* bias;   // nullable, indexed by the absolute output column
   const float* gate;   // nullable [M][ldg]: ReLU mask of the forward activation (backward)
   int ldg, relu;
-  __device__ __forceinline__ void init() {}
+  bool vec;   // bias 16-byte aligned: 128-bit loads of the (warp-uniform) bias values
+  __device__ __forceinline__ void init() { vec = (reinterpret_cast<uintptr_t>(bias) & 15) == 0; }
   __device__ __forceinline__ void load_addends(const AddendRows&, bool) {}
   __device__ __forceinline__ void consume16(i64 m, int c0, int n0, const float (&v)[16], const RowSink& out) {
     float o[16];
-    const int ca = n0 + c0;   // absolute output column
+    const int ca = n0 + c0;   // absolute output column (multiple of 16)
+    // the null / mode checks sit outside the element loops (see RowMlp)
+    if (bias) {
+      if (vec) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float r = v[j] + (bias ? __ldg(bias + ca + j) : 0.0f);
-      o[j] = relu ? fmaxf(r, 0.0f) : r;
+        for (int q = 0; q < 4; ++q) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ca) + q);
+          o[4 * q] = v[4 * q] + b4.x; o[4 * q + 1] = v[4 * q + 1] + b4.y; o[4 * q + 2] = v[4 * q + 2] + b4.z; o[4 * q + 3] = v[4 * q + 3] + b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = v[j] + __ldg(bias + ca + j);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = v[j] + 0.0f;
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.0f);
     }
     if (gate) {
       const float4* gp = reinterpret_cast<const float4*>(gate + m * ldg + ca);
