@@ -35,7 +35,7 @@ using tc::tc_ld16; using tc::tc_wait_ld; using tc::make_desc;
 
 constexpr int SLABS = 4, CH = 32, UMMA_K = 8;
 constexpr int ACC_COLS = 256;                       // TMEM columns per accumulator buffer (2 buffers)
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;                     // producer, MMA issuer, 2 splitter warps, 2 x 4 epilogue warps
 constexpr int MAXSTAGES = 8;
 
 struct Maps {
@@ -151,7 +151,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) ncon
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);
+      mbar_init(tempty_bar(a), 16);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -272,7 +272,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) ncon
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue (both CTAs): own 128 TMEM lanes = own 4 slabs
-    const int ew = warp - 4;
+    // Two sets of four warps drain every accumulator, each set its own half of the column groups: most launches of the
+    // model give a cluster one to four tiles, so the last tile's epilogue -- one warp per scheduler, ~100 KB of adds
+    // and stores -- is not hidden behind anything; splitting it halves that tail.
+    const int ew = (warp - 4) & 3, eh = (warp - 4) >> 2;
     int acc = 0;
     uint32_t accphase = 0;
     for (int tile = cl; tile < p.total_tiles; tile += ncl) {
@@ -294,7 +297,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) ncon
       const int w_base = wt * N_TILE;
       const bool has_ad = slab_ok && ad != nullptr, has_ad2 = slab_ok && ad2 != nullptr;   // warp-uniform
       constexpr int GC = 64;
-      for (int g0 = 0; g0 < N_TILE; g0 += GC) {
+      const int ngrp = (N_TILE + GC - 1) / GC, gsplit = ((ngrp + 1) >> 1) * GC;   // set 0: groups [0, ceil(ngrp/2)), set 1: the rest
+      for (int g0 = eh ? gsplit : 0; g0 < (eh ? N_TILE : gsplit); g0 += GC) {
         if (w_base + g0 >= p.V) break;   // warp-uniform: nothing left in this column tile
         float av[GC];
 #pragma unroll
