@@ -17,7 +17,7 @@ constexpr int CH = 32;
 // on `full`, tensor pipe 53 % active).  Half-size stages put five in the same shared memory: same bytes in flight, but
 // the loads run four stages ahead of the MMAs instead of one.
 constexpr int UMMA_K = 8;      // kind::tf32: 32 bytes of K per instruction
-constexpr int NUM_THREADS = 256;                          // warps 0-3: control roles, warps 4-7: epilogue
+constexpr int NUM_THREADS = 384;                          // warps 0-3: control roles, warps 4-11: two epilogue sets (nconv_tc2.cuh)
 constexpr int ACC_COLS = 256;                             // TMEM columns per accumulator buffer (2 buffers)
 
 struct Maps {
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue: TMEM -> registers -> global
-    const int ew = warp - 4;             // == warp % 4: TMEM lanes 32*ew .. 32*ew+31 = slab ew of the tile, lane = channel
+    const int ew = (warp - 4) & 3, eh = (warp - 4) >> 2;   // ew == warp % 4: TMEM lanes 32*ew .. 32*ew+31 = slab ew of the tile, lane = channel; eh: column-group half
     int acc = 0;
     uint32_t accphase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nconv_tc_kernel(const __grid_c
       // launches paid one exposed L2/HBM round trip per 16 columns -- 13 per tile -- and ran 1.4-2x longer than the
       // addend-free forward launches of the same MMA work (ncu launch lists r01c/r01f).
       constexpr int GC = 64;
-      for (int g0 = 0; g0 < p.n_tile; g0 += GC) {
+      const int ngrp = (p.n_tile + GC - 1) / GC, gsplit = ((ngrp + 1) >> 1) * GC;
+      for (int g0 = eh ? gsplit : 0; g0 < (eh ? p.n_tile : gsplit); g0 += GC) {
         float av[GC];
 #pragma unroll
         for (int j = 0; j < GC; ++j) av[j] = 0.0f;
