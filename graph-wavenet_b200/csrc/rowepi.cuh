@@ -117,6 +117,22 @@ __device__ __forceinline__ float gate_tanh(float x) { return fmaf(-2.0f, mufu_rc
 // the same with the bias folded into the exponent: sb = kSigmScale * bias, tb = kTanhScale * bias
 __device__ __forceinline__ float gate_sigmoid_b(float v, float sb) { return mufu_rcp(1.0f + mufu_ex2(fmaf(v, kSigmScale, sb))); }
 __device__ __forceinline__ float gate_tanh_b(float v, float tb) { return fmaf(-2.0f, mufu_rcp(mufu_ex2(fmaf(v, kTanhScale, tb)) + 1.0f), 1.0f); }
+// Two gates with ONE reciprocal (the gate epilogues are MUFU-bound: 4 quarter-rate instructions per gated output with
+// the helpers above, 2.5 here).  With ea = e^{2a}, eb = e^{-b}: tanh(a) = (ea - 1) / (1 + ea), sigmoid(b) = 1 / (1 + eb),
+// so every factor of a pair is a product of  r = 1 / ((1+ea0)(1+eb0)(1+ea1)(1+eb1))  with the other denominators.
+// The exponents are clamped at 30: 2^30 leaves tanh within 2^-29 of 1 and sigmoid within 2^-30 of 0 (below fp32
+// resolution of the results) and keeps the four-factor product under 2^124, so r stays a normal number.
+struct GatePair { float num[2], q1[2], p1[2], den[2], r; };   // num = ea - 1, q1 = 1 + ea, p1 = 1 + eb, den = q1 * p1
+__device__ __forceinline__ GatePair gate_pair(float vf0, float vg0, float vf1, float vg1, float tb0, float sb0, float tb1,
+                                              float sb1) {
+  GatePair g;
+  const float ea0 = mufu_ex2(fminf(fmaf(vf0, kTanhScale, tb0), 30.0f)), eb0 = mufu_ex2(fminf(fmaf(vg0, kSigmScale, sb0), 30.0f));
+  const float ea1 = mufu_ex2(fminf(fmaf(vf1, kTanhScale, tb1), 30.0f)), eb1 = mufu_ex2(fminf(fmaf(vg1, kSigmScale, sb1), 30.0f));
+  g.num[0] = ea0 - 1.0f; g.q1[0] = ea0 + 1.0f; g.p1[0] = eb0 + 1.0f; g.den[0] = g.q1[0] * g.p1[0];
+  g.num[1] = ea1 - 1.0f; g.q1[1] = ea1 + 1.0f; g.p1[1] = eb1 + 1.0f; g.den[1] = g.q1[1] * g.p1[1];
+  g.r = mufu_rcp(g.den[0] * g.den[1]);
+  return g;
+}
 
 // model.py:208-212 -- accumulator columns interleaved (f0,g0,f1,g1,...), N = 64 -> 32 gated outputs.
 struct RowGate {
@@ -139,7 +155,12 @@ struct RowGate {
     const int ch0 = c0 >> 1;   // compile-time after unrolling (NCT > 0): tb / sb stay in registers
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = gate_tanh_b(v[2 * j], tb[ch0 + j]) * gate_sigmoid_b(v[2 * j + 1], sb[ch0 + j]);
+    for (int j = 0; j < 8; j += 2) {   // tanh(a) sigmoid(b) = (ea - 1) / den
+      const GatePair g = gate_pair(v[2 * j], v[2 * j + 1], v[2 * j + 2], v[2 * j + 3], tb[ch0 + j], sb[ch0 + j], tb[ch0 + j + 1],
+                                   sb[ch0 + j + 1]);
+      o[j] = g.num[0] * (g.r * g.den[1]);
+      o[j + 1] = g.num[1] * (g.r * g.den[0]);
+    }
     out.put4(ch0, o[0], o[1], o[2], o[3]);
     out.put4(ch0 + 4, o[4], o[5], o[6], o[7]);
   }
@@ -171,11 +192,17 @@ struct RowGateBwd {
     const int ch0 = c0 >> 1;
     float o[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float f = gate_tanh_b(v[2 * j], tb[ch0 + j]), s = gate_sigmoid_b(v[2 * j + 1], sb[ch0 + j]);
-      const float gg = g[ch0 + j];
-      o[2 * j] = gg * s * (1.0f - f * f);
-      o[2 * j + 1] = gg * f * s * (1.0f - s);
+    for (int j = 0; j < 8; j += 2) {
+      const GatePair gp = gate_pair(v[2 * j], v[2 * j + 1], v[2 * j + 2], v[2 * j + 3], tb[ch0 + j], sb[ch0 + j], tb[ch0 + j + 1],
+                                    sb[ch0 + j + 1]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float rd = gp.r * gp.den[1 - h];   // 1 / den of this gate
+        const float s = rd * gp.q1[h], f = gp.num[h] * (rd * gp.p1[h]);
+        const float gg = g[ch0 + j + h];
+        o[2 * (j + h)] = gg * s * (1.0f - f * f);
+        o[2 * (j + h) + 1] = gg * f * s * (1.0f - s);
+      }
     }
     out.put16(c0 & 31, o);
   }
