@@ -97,6 +97,9 @@ struct TrParams {
   int lo_stages;   // 3xTF32: buffers of the remainder ring (0 otherwise)
   int interleave;  // K chunks dealt round-robin to the CTAs of an output tile instead of in contiguous ranges
   int abox;        // multi-job: the job's A blocks are the consecutive segments 0..na-1, unshifted: ONE 4-D TMA box
+  int ncat;        // 3xTF32, drain mode (N = 32 or 64): A.[B | B_lo] as ONE instruction of twice the width (the splitter puts the
+                   // remainder blocks right behind B's) into accumulator columns [0,N) | [N,2N) that the drain adds; with the
+                   // measured 66 + 0.75 N cycles per tcgen05.mma a k-step of N = 32 costs 114 + 90 cycles instead of 3 x 90
 };
 
 // X3 = 3xTF32 mode (fp32-grade): both operands are activations, so warps 2 and 3 split BOTH tiles of a stage into
@@ -105,20 +108,25 @@ struct TrParams {
 // stages hold bytes in flight, and with remainders inside every stage a 227 KB CTA had just two or three of them --
 // 64 KB in flight per SM, ~3 TB/s on the whole GPU whatever the MMA cost.  A remainder buffer is busy from the split
 // until its MMAs retire (commit -> loempty), a raw stage from the TMA until the same commit (-> empty).
-template <bool X3>
+template <bool X3, bool NCAT = false>   // NCAT: the N-concatenated remainder product (TrParams::ncat), its own instantiation
 __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ TrMaps maps, const TrParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const int plane_bytes = p.a_bytes + p.b_bytes;
-  const int stage_bytes = plane_bytes;                 // raw stage [A | B]; remainder buffer [A_lo | B_lo], same size
+  // raw stage [A | B]; remainder buffer [A_lo | B_lo], same size.  ncat (see TrParams): the splitter writes B_lo right
+  // behind B INSIDE the raw stage -- [A | B | B_lo], so that [B | B_lo] is one operand of twice the width -- and the
+  // remainder buffers hold A_lo only (a raw stage is handed back by the same commit that frees the remainder buffer).
+  constexpr bool kNcat = X3 && NCAT;
+  const int stage_bytes = plane_bytes + (kNcat ? p.b_bytes : 0);
+  const int lo_bytes = kNcat ? p.a_bytes : plane_bytes;
   const int LQ = X3 ? p.lo_stages : 0;
   const uint32_t st0 = base;
   const uint32_t lo0 = st0 + p.stages * stage_bytes;   // remainder ring
   uint8_t* lo_ptr = smem + (size_t)p.stages * stage_bytes;
-  const uint32_t bar0 = lo0 + LQ * plane_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(lo_ptr + (size_t)LQ * plane_bytes);
+  const uint32_t bar0 = lo0 + LQ * lo_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lo_ptr + (size_t)LQ * lo_bytes);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
   const int nb2 = 2 * p.stages;
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       for (int i = threadIdx.x; i < nfill; i += 256) blk[i] = i < 1024 ? 1.0f : 0.0f;
     }
     for (int l = 0; l < LQ; ++l) {   // their remainders are zero
-      float* lo = reinterpret_cast<float*>(lo_ptr + (size_t)l * plane_bytes + (size_t)na_loc * 4096);
+      float* lo = reinterpret_cast<float*>(lo_ptr + (size_t)l * lo_bytes + (size_t)na_loc * 4096);
       const int nfill = (p.mtiles * 4 - na_loc) * 1024;
       for (int i = threadIdx.x; i < nfill; i += 256) lo[i] = 0.0f;
     }
@@ -255,7 +263,10 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     bool first = true;
     int acc = 0, in_acc = 0;                 // drain mode: current TMEM buffer, chunks accumulated in it
     uint32_t accphase[2] = {0u, 0u};
-    const uint32_t acc_cols = (uint32_t)(p.mtiles * p.N);
+    constexpr bool ncat = X3 && NCAT;
+    const uint32_t accN = (uint32_t)(ncat ? 2 * p.N : p.N);   // accumulator columns per row tile
+    const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * p.N) >> 3) << 17);
+    const uint32_t acc_cols = (uint32_t)p.mtiles * accN;
     uint32_t tm0 = tmem_base;
     bool ok = true;
     for (int c = c_beg; c < c_end; c += c_step) {
@@ -269,7 +280,7 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       tc_fence_after();
       const uint32_t sa = st0 + stage * stage_bytes, sb = sa + p.a_bytes;
       auto descs = [&](int t, int kk, uint64_t& adesc, uint64_t& bdesc) {
-        if (p.mode == 0) {
+        if (NCAT || p.mode == 0) {
           // MN-major, 32-byte-atom swizzle: atoms of 4 k-rows x 128 B (SBO 512 B), next 32-wide block 4096 B on (LBO)
           adesc = make_desc(sa + t * 16384 + kk * 1024, 4096, 512, 1);
           bdesc = make_desc(sb + kk * 1024, 4096, 512, 1);
@@ -278,10 +289,11 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
           bdesc = make_desc(sb + kk * 32, 16, 1024, 2);
         }
       };
+      if (!ncat) {
       if (elect_one()) {
 #pragma unroll 1
       for (int t = 0; t < p.mtiles; ++t) {
-        const uint32_t d_tmem = tm0 + (uint32_t)(t * p.N);
+        const uint32_t d_tmem = tm0 + (uint32_t)t * accN;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           uint64_t adesc, bdesc;
@@ -291,24 +303,42 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       }
       }
       __syncwarp();
+      }
       if (X3) {   // remainder terms after the split of this stage (it ran while the MMAs above were issued); the remainder
                   // planes sit plane_bytes further, same layout
         if (!mbar_wait_warp(split_bar(lq), lphase, 24)) { ok = false; break; }
         tc_fence_after();
         // remainder buffer lq relative to raw stage `stage` (descriptor start addresses are in 16-byte units)
-        const uint64_t off = (uint64_t)(((lo0 + (uint32_t)lq * plane_bytes) - sa) >> 4);
-        if (elect_one()) {
+        const uint64_t off = (uint64_t)(((lo0 + (uint32_t)lq * lo_bytes) - sa) >> 4);
+        // (two copies of the loop: the issuing thread paces these kernels, a branch per MMA is measurable)
+        if (ncat) {   // [B | B_lo]: the remainder blocks follow B's in the raw stage, same 4096-byte block stride
+          if (elect_one()) {
 #pragma unroll 1
-        for (int t = 0; t < p.mtiles; ++t) {
-          const uint32_t d_tmem = tm0 + (uint32_t)(t * p.N);
+          for (int t = 0; t < p.mtiles; ++t) {
+            const uint32_t d_tmem = tm0 + (uint32_t)t * accN;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            uint64_t adesc, bdesc;
-            descs(t, kk, adesc, bdesc);
-            tc_mma_tf32(d_tmem, adesc, bdesc + off, idesc, 1u);
-            tc_mma_tf32(d_tmem, adesc + off, bdesc, idesc, 1u);
+            for (int kk = 0; kk < 4; ++kk) {
+              uint64_t adesc, bdesc;
+              descs(t, kk, adesc, bdesc);
+              tc_mma_tf32(d_tmem, adesc, bdesc, idesc2, (!first || kk > 0) ? 1u : 0u);
+              tc_mma_tf32(d_tmem, adesc + off, bdesc, idesc, 1u);
+            }
           }
-        }
+          }
+        } else {
+          if (elect_one()) {
+#pragma unroll 1
+          for (int t = 0; t < p.mtiles; ++t) {
+            const uint32_t d_tmem = tm0 + (uint32_t)t * accN;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              uint64_t adesc, bdesc;
+              descs(t, kk, adesc, bdesc);
+              tc_mma_tf32(d_tmem, adesc, bdesc + off, idesc, 1u);
+              tc_mma_tf32(d_tmem, adesc + off, bdesc, idesc, 1u);
+            }
+          }
+          }
         }
         __syncwarp();
       }
@@ -352,7 +382,7 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
     if (!mbar_wait(loempty_bar(lq), lphase ^ 1u, 28)) return false;   // the MMAs that read this remainder buffer have retired
     if (!mbar_wait(full_bar(stage), phase, 25)) return false;
     uint8_t* sp = smem + (size_t)stage * stage_bytes;
-    uint8_t* lp = lo_ptr + (size_t)lq * plane_bytes;
+    uint8_t* lp = lo_ptr + (size_t)lq * lo_bytes;
     const float4* a_src = reinterpret_cast<const float4*>(sp);
     float4* a_dst = reinterpret_cast<float4*>(lp);
 #pragma unroll 4
@@ -361,7 +391,7 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
       a_dst[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
     }
     const float4* b_src = reinterpret_cast<const float4*>(sp + p.a_bytes);
-    float4* b_dst = reinterpret_cast<float4*>(lp + p.a_bytes);
+    float4* b_dst = reinterpret_cast<float4*>(kNcat ? sp + plane_bytes : lp + p.a_bytes);
 #pragma unroll 4
     for (int i = t64; i < b_live; i += nsplit) {
       const float4 v = b_src[i];
@@ -399,15 +429,31 @@ __global__ void __launch_bounds__(256, 1) tcred_kernel(const __grid_constant__ T
         const int buf = d & 1;
         if (!mbar_wait(tfull_bar(buf), (uint32_t)(d >> 1) & 1u, 27)) return false;
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(buf * p.mtiles * p.N);
+        if (kNcat) {   // N-concatenated product: the A.B_lo columns sit p.N columns behind the main ones
+          const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(buf * p.mtiles * 2 * p.N);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g < ngrp) {
-            uint32_t r[16];
-            tc_ld16(taddr + (uint32_t)((g / gpt) * p.N + (g % gpt) * 16), r);
-            tc_wait_ld();
+          for (int g = 0; g < 4; ++g) {
+            if (g < ngrp) {
+              uint32_t r[16], r2[16];
+              const uint32_t col = (uint32_t)((g / gpt) * 2 * p.N + (g % gpt) * 16);
+              tc_ld16(taddr + col, r);
+              tc_ld16(taddr + col + (uint32_t)p.N, r2);
+              tc_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sum[g * 16 + j] += __uint_as_float(r[j]);
+              for (int j = 0; j < 16; ++j) sum[g * 16 + j] += __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+            }
+          }
+        } else {
+          const uint32_t taddr = tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(buf * p.mtiles * p.N);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g < ngrp) {
+              uint32_t r[16];
+              tc_ld16(taddr + (uint32_t)((g / gpt) * p.N + (g % gpt) * 16), r);
+              tc_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) sum[g * 16 + j] += __uint_as_float(r[j]);
+            }
           }
         }
         tc_fence_before();
@@ -663,6 +709,14 @@ inline int launch_slot_reduce(const float* partial, const TcRedResult& r, i64 no
 }
 #endif
 
+// GWNET_B200_TCRED_NCAT=0 turns the N-concatenated remainder product (TrParams::ncat) off for A/B runs.
+inline int tcred_ncat_enabled() {
+  static const int on = [] {
+    const char* e = getenv("GWNET_B200_TCRED_NCAT");
+    return e ? atoi(e) : 1;
+  }();
+  return on;
+}
 // 0 = launched, -1 = not eligible (caller falls back), > 0 = error.
 inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* res) {
 #if GWN_EMU
@@ -787,9 +841,13 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
     }();
     p.interleave = inter;
   }
-  const int stage_bytes = p.a_bytes + p.b_bytes;          // raw stage; the 3xTF32 remainder ring has 2 buffers of the same size
+  if (a.mode == 0 && p.mtiles * p.N <= 64) p.drain = 16;
+  p.ncat = (a.x3 && p.drain > 0 && tcred_ncat_enabled()) ? 1 : 0;
+  // raw stage [A | B] (+ B_lo with ncat); the 3xTF32 remainder ring has 2 buffers [A_lo | B_lo] (A_lo only with ncat)
+  const int stage_bytes = p.a_bytes + p.b_bytes * (p.ncat ? 2 : 1);
+  const int lo_bytes = p.ncat ? p.a_bytes : p.a_bytes + p.b_bytes;
   p.lo_stages = a.x3 ? 2 : 0;
-  p.stages = (SMEM_LIMIT - 2048 - p.lo_stages * stage_bytes) / stage_bytes;
+  p.stages = (SMEM_LIMIT - 2048 - p.lo_stages * lo_bytes) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) return -1;
   // grid: a multiple of the output tile count, every CTA gets at least one chunk
@@ -802,15 +860,16 @@ inline int launch_tcred(const TcRedArgs& a, cudaStream_t stream, TcRedResult* re
   p.slot_floats = (i64)p.mtiles * 128 * p.N;
   if ((i64)grid * p.slot_floats > a.partial_floats) return -1;
   p.partial = a.partial;
-  if (a.mode == 0 && p.mtiles * p.N <= 64) p.drain = 16;
-  const int smem_bytes = (p.stages + p.lo_stages) * stage_bytes + 1024 + 256;
+  const int smem_bytes = p.stages * stage_bytes + p.lo_stages * lo_bytes + 1024 + 256;
   static cudaError_t attr = cudaFuncSetAttribute(tcred_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   static cudaError_t attr3 = cudaFuncSetAttribute(tcred_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-  if (attr != cudaSuccess || attr3 != cudaSuccess) {
-    set_error("tcred: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr != cudaSuccess ? attr : attr3));
+  static cudaError_t attr3c = cudaFuncSetAttribute(tcred_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  if (attr != cudaSuccess || attr3 != cudaSuccess || attr3c != cudaSuccess) {
+    set_error("tcred: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr != cudaSuccess ? attr : attr3 != cudaSuccess ? attr3 : attr3c));
     return GWN_ERR_CUDA;
   }
-  if (a.x3) GWN_CUDA(launch_kernel(tcred_kernel<true>, dim3(grid), dim3(256), smem_bytes, stream, maps, p));
+  if (a.x3 && p.ncat) GWN_CUDA(launch_kernel(tcred_kernel<true, true>, dim3(grid), dim3(256), smem_bytes, stream, maps, p));
+  else if (a.x3) GWN_CUDA(launch_kernel(tcred_kernel<true>, dim3(grid), dim3(256), smem_bytes, stream, maps, p));
   else GWN_CUDA(launch_kernel(tcred_kernel<false>, dim3(grid), dim3(256), smem_bytes, stream, maps, p));
   GWN_LAUNCH_CHECK();
   count_launch();
@@ -895,6 +954,7 @@ inline int launch_tcred_jobs(const TcRedJobsArgs& a, cudaStream_t stream, TcRedR
   int T = sms;
   if (p.mtiles * p.N <= 64) {
     p.drain = 16;   // short chains by draining into registers: one round of CTAs is enough
+    p.ncat = (a.x3 && tcred_ncat_enabled()) ? 1 : 0;
   } else {
     long long want = (tot + 47) / 48;
     want = (want + sms - 1) / sms * sms;
@@ -934,22 +994,26 @@ inline int launch_tcred_jobs(const TcRedJobsArgs& a, cudaStream_t stream, TcRedR
     }();
     p.interleave = inter;
   }
-  const int stage_bytes = p.a_bytes + p.b_bytes;          // raw stage; the 3xTF32 remainder ring has 2 buffers of the same size
+  // raw stage [A | B] (+ B_lo with ncat); the 3xTF32 remainder ring has 2 buffers [A_lo | B_lo] (A_lo only with ncat)
+  const int stage_bytes = p.a_bytes + p.b_bytes * (p.ncat ? 2 : 1);
+  const int lo_bytes = p.ncat ? p.a_bytes : p.a_bytes + p.b_bytes;
   p.lo_stages = a.x3 ? 2 : 0;
-  p.stages = (SMEM_LIMIT - 2048 - p.lo_stages * stage_bytes) / stage_bytes;
+  p.stages = (SMEM_LIMIT - 2048 - p.lo_stages * lo_bytes) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) return -1;
   p.slot_floats = (i64)p.mtiles * 128 * p.N;
   if ((i64)grid * p.slot_floats > a.partial_floats) return -1;
   p.partial = a.partial;
-  const int smem_bytes = (p.stages + p.lo_stages) * stage_bytes + 1024 + 256;
+  const int smem_bytes = p.stages * stage_bytes + p.lo_stages * lo_bytes + 1024 + 256;
   static cudaError_t attr = cudaFuncSetAttribute(tcred_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   static cudaError_t attr3 = cudaFuncSetAttribute(tcred_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-  if (attr != cudaSuccess || attr3 != cudaSuccess) {
-    set_error("tcred: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr != cudaSuccess ? attr : attr3));
+  static cudaError_t attr3c = cudaFuncSetAttribute(tcred_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  if (attr != cudaSuccess || attr3 != cudaSuccess || attr3c != cudaSuccess) {
+    set_error("tcred: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr != cudaSuccess ? attr : attr3 != cudaSuccess ? attr3 : attr3c));
     return GWN_ERR_CUDA;
   }
-  if (a.x3) GWN_CUDA(launch_kernel(tcred_kernel<true>, dim3(grid), dim3(256), smem_bytes, stream, maps, p));
+  if (a.x3 && p.ncat) GWN_CUDA(launch_kernel(tcred_kernel<true, true>, dim3(grid), dim3(256), smem_bytes, stream, maps, p));
+  else if (a.x3) GWN_CUDA(launch_kernel(tcred_kernel<true>, dim3(grid), dim3(256), smem_bytes, stream, maps, p));
   else GWN_CUDA(launch_kernel(tcred_kernel<false>, dim3(grid), dim3(256), smem_bytes, stream, maps, p));
   count_launch();
   res->nslots = grid; res->mtiles = p.mtiles; res->N = p.N; res->n_nt = 1; res->n_mg = 1; res->slot_floats = p.slot_floats;
