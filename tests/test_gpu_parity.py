@@ -697,6 +697,19 @@ def test_launch_switches_off_still_match_the_oracle():
     assert "[smoke]" in r.stdout
 
 
+def test_weight_gradient_reductions_without_the_concatenated_remainder_product():
+    """The 3xTF32 weight-gradient reductions run A.[B | B_lo] as one instruction by default (tcred_kernel<true, true>,
+    DESIGN 4.3); GWNET_B200_TCRED_NCAT=0 selects the three-instruction form (tcred_kernel<true, false>), which the
+    non-drain reductions still use -- keep both against the oracle."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GWNET_B200_TCRED_NCAT="0")
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "[smoke]" in r.stdout
+
+
 
 # ------------------------------------------------------------------------------------------------ round-2 parity additions
 @pytest.mark.parametrize("tier", ["fp32x3", "tf32"])
